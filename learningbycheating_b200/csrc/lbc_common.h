@@ -1,0 +1,172 @@
+// lbc_common.h -- shared plumbing for the LBC image-agent training engine (sm_100a).
+//
+// Two build modes:
+//   * product: nvcc -gencode arch=compute_100a,code=sm_100a  -> liblbc_b200.so (CUDA only,
+//     no CPU path; every entry point works on device pointers).
+//   * LBC_HOST_EMU: g++ -x c++ of the SAME sources, kernels of the correctness-first path run
+//     as plain loops over host pointers.  Test infrastructure for `pytest -m "not gpu"` (host
+//     logic: graph executor, buffer plan, parameter table).  Never loaded by the package.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifdef LBC_HOST_EMU
+#define LBC_HD
+#define LBC_DEV
+typedef void* lbc_stream_t;
+#else
+#include <cuda_runtime.h>
+#define LBC_HD __host__ __device__
+#define LBC_DEV __device__
+typedef cudaStream_t lbc_stream_t;
+#endif
+
+namespace lbc {
+
+// ------------------------------------------------------------------ errors
+struct Error : std::runtime_error {
+  explicit Error(const std::string& s) : std::runtime_error(s) {}
+};
+#define LBC_CHECK(cond, msg)                                                            \
+  do {                                                                                  \
+    if (!(cond)) throw ::lbc::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + \
+                                    ": " + (msg));                                      \
+  } while (0)
+
+#ifndef LBC_HOST_EMU
+#define LBC_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      throw ::lbc::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + \
+                         #call + " -> " + cudaGetErrorString(e_));                      \
+  } while (0)
+#endif
+
+// ------------------------------------------------------------------ bf16 storage type
+// Bit-compatible with __nv_bfloat16; own struct so the same code compiles for the host emu.
+struct bf16 {
+  uint16_t v;
+};
+LBC_HD inline float bf16_to_float(bf16 h) {
+  uint32_t u = ((uint32_t)h.v) << 16;
+  float f;
+#if defined(__CUDA_ARCH__)
+  f = __uint_as_float(u);
+#else
+  memcpy(&f, &u, 4);
+#endif
+  return f;
+}
+LBC_HD inline bf16 float_to_bf16(float f) {
+  uint32_t u;
+#if defined(__CUDA_ARCH__)
+  u = __float_as_uint(f);
+#else
+  memcpy(&u, &f, 4);
+#endif
+  bf16 h;
+  if ((u & 0x7fffffffu) > 0x7f800000u) {  // NaN
+    h.v = 0x7fff;
+    return h;
+  }
+  u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even
+  h.v = (uint16_t)(u >> 16);
+  return h;
+}
+
+template <class T>
+LBC_HD inline float ldf(const T* p, int64_t i);
+template <>
+LBC_HD inline float ldf<float>(const float* p, int64_t i) {
+  return p[i];
+}
+template <>
+LBC_HD inline float ldf<bf16>(const bf16* p, int64_t i) {
+  return bf16_to_float(p[i]);
+}
+template <class T>
+LBC_HD inline void stf(T* p, int64_t i, float v);
+template <>
+LBC_HD inline void stf<float>(float* p, int64_t i, float v) {
+  p[i] = v;
+}
+template <>
+LBC_HD inline void stf<bf16>(bf16* p, int64_t i, float v) {
+  p[i] = float_to_bf16(v);
+}
+
+// ------------------------------------------------------------------ device memory
+inline void* dev_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 16;
+#ifdef LBC_HOST_EMU
+  void* p = nullptr;
+  if (posix_memalign(&p, 256, bytes) != 0) throw Error("host-emu alloc failed");
+  return p;
+#else
+  void* p = nullptr;
+  LBC_CUDA(cudaMalloc(&p, bytes));
+  return p;
+#endif
+}
+inline void dev_free(void* p) {
+  if (!p) return;
+#ifdef LBC_HOST_EMU
+  free(p);
+#else
+  cudaFree(p);
+#endif
+}
+inline void dev_memset(void* p, int v, size_t bytes, lbc_stream_t s) {
+#ifdef LBC_HOST_EMU
+  (void)s;
+  memset(p, v, bytes);
+#else
+  LBC_CUDA(cudaMemsetAsync(p, v, bytes, s));
+#endif
+}
+inline void dev_copy(void* dst, const void* src, size_t bytes, lbc_stream_t s) {
+#ifdef LBC_HOST_EMU
+  (void)s;
+  memcpy(dst, src, bytes);
+#else
+  LBC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+#endif
+}
+
+// ------------------------------------------------------------------ par_for
+// The correctness-first kernels are "independent thread" kernels: one logical thread per
+// output element, no shared memory, no atomics -> bitwise deterministic, and the same body
+// runs under the host emulation.  Tag names the kernel in ncu launch lists.
+#ifdef LBC_HOST_EMU
+template <class Tag, class F>
+inline void par_for(lbc_stream_t, int64_t n, F f) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) f(i);
+}
+#else
+template <class Tag, class F>
+__global__ void __launch_bounds__(256) par_for_kernel(int64_t n, F f) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f(i);
+}
+template <class Tag, class F>
+inline void par_for(lbc_stream_t s, int64_t n, F f) {
+  if (n <= 0) return;
+  const int bs = 256;
+  int64_t nb = (n + bs - 1) / bs;
+  LBC_CHECK(nb < (1ll << 31), "par_for grid too large");
+  par_for_kernel<Tag, F><<<(unsigned)nb, bs, 0, s>>>(n, f);
+  LBC_CUDA(cudaGetLastError());
+}
+#endif
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace lbc
