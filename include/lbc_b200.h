@@ -1,0 +1,103 @@
+/* lbc_b200.h -- C ABI of the B200-native LearningByCheating image-agent training hot path.
+ *
+ * The reference (dotchen/LearningByCheating) has no FFI / plugin registry: its boundary for this
+ * path is the Python nn.Module protocol.  This header is the native surface the
+ * drop-in Python classes in learningbycheating_b200/ bind with ctypes; each entry point cites the
+ * reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions: every pointer is a DEVICE pointer (cudaMalloc'd, fp32 unless stated), tensors are
+ * contiguous in the reference's own layouts (images NCHW, parameters as in state_dict()), `stream`
+ * is a cudaStream_t passed as void* (NULL = legacy default stream).  All functions return 0 on
+ * success and a non-zero code on failure; lbc_last_error() then returns a message.  Nothing here
+ * falls back to the CPU: without a CUDA device the calls fail.
+ */
+#ifndef LBC_B200_H
+#define LBC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lbc_net lbc_net_t;
+
+#define LBC_NET_IMAGE_RESNET34 0    /* ImagePolicyModelSS('resnet34'),  bird_view/models/image.py:22-89   */
+#define LBC_NET_BIRDVIEW_RESNET18 1 /* BirdViewPolicyModelSS('resnet18'), bird_view/models/birdview.py:47-79 */
+#define LBC_PREC_F32 0  /* fp32 storage + fp32 math: parity mode (<=1e-3 vs the reference CPU path) */
+#define LBC_PREC_BF16 1 /* bf16 NHWC activations / tcgen05 bf16 MMA, fp32 accumulation + statistics  */
+
+const char* lbc_last_error(void);
+/* 1 = CUDA sm_100a build (the product), 0 = host-emulation build used only by the CPU unit tests */
+int lbc_device_kind(void);
+const char* lbc_build_info(void);
+/* enable / disable the tcgen05 + fused kernels (tests compare them with the correctness-first kernels) */
+int lbc_set_fast_kernels(int enabled);
+
+/* ---- network object: nn.Module construction (image.py:23-62, common.py:69-83, resnet.py:95-146) ---- */
+int lbc_net_create(int kind, int precision, int max_batch, lbc_net_t** out);
+void lbc_net_destroy(lbc_net_t* net);
+/* parameter table in named_parameters() order; offsets index the flat fp32 parameter/gradient arrays */
+int lbc_net_num_params(const lbc_net_t* net);
+int lbc_net_param_info(const lbc_net_t* net, int i, const char** name, int* ndim, int shape[4], int64_t* numel,
+                       int64_t* offset, int* on_path);
+/* BatchNorm running_mean / running_var buffers; offsets index the flat fp32 buffer array */
+int lbc_net_num_buffers(const lbc_net_t* net);
+int lbc_net_buffer_info(const lbc_net_t* net, int i, const char** name, int64_t* numel, int64_t* offset);
+int64_t lbc_net_total_params(const lbc_net_t* net);
+int64_t lbc_net_total_buffers(const lbc_net_t* net);
+int64_t lbc_net_workspace_bytes(const lbc_net_t* net);
+/* bind caller-owned flat arrays (the nn.Parameters / .grad / BN buffers are views of them) */
+int lbc_net_bind(lbc_net_t* net, float* params, float* grads, float* buffers);
+
+/* nn.Module.__call__ -> ImagePolicyModelSS.forward (image.py:64-89) / BirdViewPolicyModelSS.forward
+ * (birdview.py:61-79).  image: [B,C,H,W] fp32 NCHW (RGB in [0,1]; normalisation common.py:108 is applied
+ * inside), speed [B], command_onehot [B,4] (train_utils.py:33-40).  train!=0: batch-statistics BN with
+ * running-buffer update (net.train()); train==0: running statistics (net.eval()).
+ * out_pred [B,5,2], out_preds [B,4,5,2] (either may be NULL). */
+int lbc_net_forward(lbc_net_t* net, const float* image, const float* speed, const float* command_onehot, int B,
+                    int train, float* out_pred, float* out_preds, void* stream);
+/* loss.backward() through the network (train_image_phase0.py:184): upstream gradients wrt out_pred [B,5,2]
+ * and/or out_preds [B,4,5,2] (NULL = none); writes every on-path parameter gradient into the bound
+ * gradient array (overwrites, like backward() after zero_grad()). */
+int lbc_net_backward(lbc_net_t* net, const float* d_pred, const float* d_preds, void* stream);
+/* copy an internal activation out as fp32 NCHW ("stem.raw", "stem.pool", "conv.layer1.0", ...,
+ * "deconv.1|4|7", "logits"); returns element count or -1 */
+int64_t lbc_net_read_tap(lbc_net_t* net, const char* name, float* out, int64_t capacity, void* stream);
+
+/* ---- losses ---- */
+/* CoordConverter.__call__ + _project_image_xy, training/train_image_phase0.py:54-79 (device-side, no
+ * host round trip): teacher map coords [count,2] in [-1,1] -> image pixels, clipped to [0,w]x[0,h] */
+int lbc_phase0_target(const float* teacher_pred, float* target_px, int64_t count, float w, float h, float fov_deg,
+                      float world_y, float fixed_offset, void* stream);
+/* per-sample L1: loss_b[n] = mean_d |a*sa+ta - (b*sb+tb)| with sb = sbx for even d, sby for odd d;
+ * da[n,d] = gout[n]*sign(.)*sa/D (gout NULL -> 1/N, i.e. d(mean loss)).  Covers LocationLoss.forward of
+ * train_image_phase0.py:86-89, train_image_phase1.py:66-70 and train_birdview.py:33-54 ('l1'). */
+int lbc_l1_loss(const float* a, const float* b, int N, int D, float sa, float ta, float sbx, float sby, float tb,
+                const float* gout, float* loss_b, float* da, void* stream);
+/* CoordConverter.__call__, training/train_image_phase1.py:43-64, and its backward */
+int lbc_phase1_convert_fwd(const float* p, float* out, int64_t count, float w, float h, float fov_deg,
+                           float world_y, float fixed_offset, void* stream);
+int lbc_phase1_convert_bwd(const float* p, const float* dout, float* dp, int64_t count, float w, float h,
+                           float fov_deg, float world_y, float fixed_offset, void* stream);
+
+/* ---- optimizer: torch.optim.Adam(lr).step() (train_image_phase0.py:231,185), one flat range ---- */
+int lbc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+/* ---- single-op entry points (fp32 NHWC; used by the parity tests of each kernel) ---- */
+int lbc_op_conv_fwd(const float* x, const float* w_ref, float* y, int N, int H, int W, int Ci, int Co, int K,
+                    int stride, int pad, int precision, void* stream);
+int lbc_op_conv_dgrad(const float* dy, const float* w_ref, float* dx, int N, int H, int W, int Ci, int Co, int K,
+                      int stride, int pad, int precision, void* stream);
+int lbc_op_conv_wgrad(const float* x, const float* dy, float* dw_ref, int N, int H, int W, int Ci, int Co, int K,
+                      int stride, int pad, int precision, void* stream);
+int lbc_op_bn_train(const float* x, const float* gamma, const float* beta, const float* residual, int relu,
+                    float* y, float* mean, float* var, int64_t M, int C, void* stream);
+int lbc_op_bn_bwd(const float* dy, const float* x, const float* gamma, float* dgamma, float* dbeta, float* dx,
+                  int64_t M, int C, void* stream);
+int lbc_op_maxpool(const float* x, float* y, const float* dy, float* dx, int N, int H, int W, int C, void* stream);
+int lbc_op_spatial_softmax(const float* logits, float* out_xy, int rows, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

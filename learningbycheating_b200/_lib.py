@@ -1,0 +1,122 @@
+"""ctypes binding of include/lbc_b200.h (the C ABI of the native hot path).
+
+The package loads exactly one library: ``liblbc_b200.so`` next to this file (built in-tree by
+``learningbycheating_b200/build.py`` with nvcc for sm_100a).  If it is missing or no CUDA device is
+usable the package raises -- there is no CPU / PyTorch fallback.  ``use_library_for_tests`` exists
+only so the ``-m "not gpu"`` unit tests can point the binding at the host-emulation build of the same
+sources (tests/hostemu/), which exercises the host-side logic on machines without a GPU.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liblbc_b200.so")
+_lib = None
+_host_emu = False
+
+c_f32p = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+
+
+class LbcError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    vp, i, f, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int64
+    sigs = {
+        "lbc_last_error": (ctypes.c_char_p, []),
+        "lbc_device_kind": (i, []),
+        "lbc_build_info": (ctypes.c_char_p, []),
+        "lbc_set_fast_kernels": (i, [i]),
+        "lbc_net_create": (i, [i, i, i, ctypes.POINTER(vp)]),
+        "lbc_net_destroy": (None, [vp]),
+        "lbc_net_num_params": (i, [vp]),
+        "lbc_net_param_info": (i, [vp, i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(i), ctypes.POINTER(i * 4),
+                                   ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i)]),
+        "lbc_net_num_buffers": (i, [vp]),
+        "lbc_net_buffer_info": (i, [vp, i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(i64), ctypes.POINTER(i64)]),
+        "lbc_net_total_params": (i64, [vp]),
+        "lbc_net_total_buffers": (i64, [vp]),
+        "lbc_net_workspace_bytes": (i64, [vp]),
+        "lbc_net_bind": (i, [vp, vp, vp, vp]),
+        "lbc_net_forward": (i, [vp, vp, vp, vp, i, i, vp, vp, vp]),
+        "lbc_net_backward": (i, [vp, vp, vp, vp]),
+        "lbc_net_read_tap": (i64, [vp, ctypes.c_char_p, vp, i64, vp]),
+        "lbc_phase0_target": (i, [vp, vp, i64, f, f, f, f, f, vp]),
+        "lbc_l1_loss": (i, [vp, vp, i, i, f, f, f, f, f, vp, vp, vp, vp]),
+        "lbc_phase1_convert_fwd": (i, [vp, vp, i64, f, f, f, f, f, vp]),
+        "lbc_phase1_convert_bwd": (i, [vp, vp, vp, i64, f, f, f, f, f, vp]),
+        "lbc_adam_step": (i, [vp, vp, vp, vp, i64, f, f, f, f, i, f, vp]),
+        "lbc_op_conv_fwd": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
+        "lbc_op_conv_dgrad": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
+        "lbc_op_conv_wgrad": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
+        "lbc_op_bn_train": (i, [vp, vp, vp, vp, i, vp, vp, vp, i64, i, vp]),
+        "lbc_op_bn_bwd": (i, [vp, vp, vp, vp, vp, vp, i64, i, vp]),
+        "lbc_op_maxpool": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
+        "lbc_op_spatial_softmax": (i, [vp, vp, i, i, i, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)   # AttributeError here == the library does not export the header's symbol
+        fn.restype = res
+        fn.argtypes = args
+    return sorted(sigs)
+
+
+EXPORTED_SYMBOLS = None
+
+
+def lib():
+    """The loaded native library; raises LbcError when the CUDA build is absent."""
+    global _lib, EXPORTED_SYMBOLS
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise LbcError(
+                "native library %s not found -- run `python -m learningbycheating_b200.build cuda` "
+                "(or __graft_entry__.build()); there is no CPU fallback" % _LIB_PATH)
+        l = ctypes.CDLL(_LIB_PATH)
+        EXPORTED_SYMBOLS = _declare(l)
+        _lib = l
+    return _lib
+
+
+def use_library_for_tests(path):
+    """TESTS ONLY: bind to the host-emulation build (device kind 0) instead of the CUDA library."""
+    global _lib, _host_emu, EXPORTED_SYMBOLS
+    l = ctypes.CDLL(path)
+    EXPORTED_SYMBOLS = _declare(l)
+    if l.lbc_device_kind() != 0:
+        raise LbcError("use_library_for_tests expects the host-emulation build")
+    _lib = l
+    _host_emu = True
+
+
+def is_host_emulation():
+    return _host_emu
+
+
+def check(rc):
+    if rc != 0:
+        raise LbcError(lib().lbc_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL); validates device / dtype / contiguity."""
+    if t is None:
+        return None
+    import torch
+    if not t.is_contiguous():
+        raise LbcError("tensor must be contiguous")
+    if _host_emu:
+        if t.is_cuda:
+            raise LbcError("host-emulation test build takes CPU tensors")
+    elif not t.is_cuda:
+        raise LbcError("liblbc_b200 takes CUDA tensors only (got a %s tensor); no CPU path exists" % t.device)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    if _host_emu:
+        return None
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

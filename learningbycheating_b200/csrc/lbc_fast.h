@@ -1,0 +1,30 @@
+// lbc_fast.h -- hooks from the graph executor into the sm_100a fast kernels (tcgen05 implicit-GEMM
+// convolutions, fused BN / head kernels).  Each hook returns false when it does not handle the
+// call (shape / dtype not covered, or host-emulation build) and the executor then runs the
+// correctness-first kernel of lbc_ref_ops.h instead.
+#pragma once
+#include "lbc_common.h"
+#include "lbc_net.h"
+
+namespace lbc {
+namespace fast {
+
+// global switch (tests flip it to compare fast kernels against the correctness-first ones)
+bool enabled();
+void set_enabled(bool on);
+
+bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s);
+
+template <class T>
+inline bool conv_fwd(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s) {
+  (void)c; (void)x; (void)y; (void)B; (void)s;
+  return false;
+}
+template <>
+inline bool conv_fwd<bf16>(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s) {
+  if (!enabled()) return false;
+  return conv_fwd_bf16(c, x, y, B, s);
+}
+
+}  // namespace fast
+}  // namespace lbc

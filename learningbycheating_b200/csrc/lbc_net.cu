@@ -1,0 +1,479 @@
+// lbc_net.cu -- graph executor: builds the layer plan of ImagePolicyModelSS('resnet34') /
+// BirdViewPolicyModelSS('resnet18') and runs forward / backward over NHWC activations in HBM.
+// Reference call stack being replaced: SURVEY.md 3.3 (image.py:64-89, resnet.py:148-159,38-54).
+#include "lbc_net.h"
+
+#include <type_traits>
+
+#include "lbc_fast.h"
+
+namespace lbc {
+
+namespace ref {
+struct k_nhwc_to_nchw;
+template <class T>
+void nhwc_to_nchw_f32(lbc_stream_t s, const T* x, float* out, int N, int H, int W, int C) {
+  int64_t n = (int64_t)N * C * H * W;
+  par_for<k_nhwc_to_nchw>(s, n, [=] LBC_HD(int64_t i) {
+    int w = (int)(i % W);
+    int64_t t = i / W;
+    int h = (int)(t % H);
+    t /= H;
+    int c = (int)(t % C);
+    int b = (int)(t / C);
+    out[i] = ldf(x, (((int64_t)b * H + h) * W + w) * C + c);
+  });
+}
+}  // namespace ref
+
+static const float kBnEps = 1e-5f;
+static const float kBnMomentum = 0.1f;
+
+template <class T>
+class Net : public NetBase {
+ public:
+  struct Block {
+    ConvL c1, c2, cd;
+    BNL b1, b2, bd;
+    bool ds = false;
+    int Cin, Cout, Hin, Win, Hout, Wout;
+    T *r1 = nullptr, *a1 = nullptr, *r2 = nullptr, *rd = nullptr, *idn = nullptr, *out = nullptr;
+    const T* xin = nullptr;
+    std::string name;
+  };
+  std::vector<void*> allocs;
+  ConvL stem;
+  BNL stem_bn;
+  int stem_oh, stem_ow, pool_h, pool_w;
+  T *x0 = nullptr, *r_stem = nullptr, *a_stem = nullptr, *pool = nullptr;
+  uint8_t* pool_idx = nullptr;
+  std::vector<Block> blocks;
+  int trunk_h, trunk_w;
+  BNL dbn[3];
+  ConvL dcv[3];
+  T *dec_in[3], *dec_bn[3], *dec_out[3];
+  BNL hbn[4];
+  int64_t hw_off[4], hb_off[4];
+  float *logits = nullptr, *dlogits = nullptr, *rowmax = nullptr, *rowsum = nullptr, *preds = nullptr;
+  float *onehot_saved = nullptr, *speed_saved = nullptr;
+  double* headS = nullptr;
+  T* g[4];
+  float* ws_f = nullptr;
+  int64_t ws_f_n = 0;
+  double* ws_d = nullptr;
+  size_t total_bytes = 0;
+  int cur_B = 0;
+  bool cur_train = false;
+  bool normalize = false;
+
+  template <class U>
+  U* alloc(int64_t n) {
+    size_t bytes = (size_t)n * sizeof(U);
+    void* p = dev_alloc(bytes);
+    allocs.push_back(p);
+    total_bytes += bytes;
+    return (U*)p;
+  }
+  ~Net() override {
+    for (void* p : allocs) dev_free(p);
+  }
+  size_t workspace_bytes() const override { return total_bytes; }
+
+  // ------------------------------------------------------------------ parameter table
+  int64_t add_param(const std::string& name, std::vector<int> shape, bool on_path = true) {
+    ParamInfo pi;
+    pi.name = name;
+    pi.ndim = (int)shape.size();
+    pi.numel = 1;
+    for (int i = 0; i < 4; ++i) pi.shape[i] = i < pi.ndim ? shape[i] : 1;
+    for (int d : shape) pi.numel *= d;
+    pi.offset = n_params;
+    pi.on_path = on_path;
+    n_params += pi.numel;
+    params.push_back(pi);
+    return pi.offset;
+  }
+  void add_bn(const std::string& prefix, int C, BNL& bn) {
+    bn.C = C;
+    bn.g_off = add_param(prefix + ".weight", {C});
+    bn.b_off = add_param(prefix + ".bias", {C});
+    for (int i = 0; i < 2; ++i) {
+      BufferInfo bi;
+      bi.name = prefix + (i == 0 ? ".running_mean" : ".running_var");
+      bi.numel = C;
+      bi.offset = n_buffers;
+      n_buffers += C;
+      buffers.push_back(bi);
+      (i == 0 ? bn.rm_off : bn.rv_off) = bi.offset;
+    }
+    bn.mean = alloc<float>(C);
+    bn.var = alloc<float>(C);
+    bn.rstd = alloc<float>(C);
+  }
+  void add_conv(const std::string& name, int Ci, int Co, int K, int stride, int pad, int H, int W, ConvL& c) {
+    c.Ci = Ci;
+    c.Co = Co;
+    c.K = K;
+    c.stride = stride;
+    c.pad = pad;
+    c.H = H;
+    c.W = W;
+    c.OH = (H + 2 * pad - K) / stride + 1;
+    c.OW = (W + 2 * pad - K) / stride + 1;
+    c.w_off = add_param(name + ".weight", {Co, Ci, K, K});
+    c.wp = alloc<T>((int64_t)Co * K * K * Ci);
+  }
+  // nn.ConvTranspose2d(Cin, Cout, 3, 2, 1, 1): as the input-gradient of a 3x3/s2/p1 conv whose
+  // conv-role Co = deconv Cin, Ci = deconv Cout; conv-role input is the (2h x 2w) deconv output.
+  void add_deconv(const std::string& name, int Cin, int Cout, int h, int w, ConvL& c) {
+    c.deconv = true;
+    c.Ci = Cout;
+    c.Co = Cin;
+    c.K = 3;
+    c.stride = 2;
+    c.pad = 1;
+    c.H = 2 * h;
+    c.W = 2 * w;
+    c.OH = h;
+    c.OW = w;
+    c.w_off = add_param(name + ".weight", {Cin, Cout, 3, 3});
+    c.b_off = add_param(name + ".bias", {Cout});
+    c.wp = alloc<T>((int64_t)Cin * 9 * Cout);
+  }
+
+  Net(NetKind k, Precision p, int maxB) {
+    kind = k;
+    prec = p;
+    max_batch = maxB;
+    std::vector<int> layers;
+    if (k == NET_IMAGE_RESNET34) {
+      in_ch = 3;
+      in_h = 160;
+      in_w = 384;
+      layers = {3, 4, 6, 3};
+      normalize = true;
+    } else {
+      in_ch = 7;
+      in_h = 192;
+      in_w = 192;
+      layers = {2, 2, 2, 2};
+      normalize = false;
+    }
+    const int64_t B = maxB;
+    // ---- stem (resnet.py:102-106)
+    add_conv("conv.conv1", in_ch, 64, 7, 2, 3, in_h, in_w, stem);
+    add_bn("conv.bn1", 64, stem_bn);
+    stem_oh = stem.OH;
+    stem_ow = stem.OW;
+    pool_h = (stem_oh + 2 - 3) / 2 + 1;
+    pool_w = (stem_ow + 2 - 3) / 2 + 1;
+    x0 = alloc<T>(B * in_h * in_w * in_ch);
+    r_stem = alloc<T>(B * stem_oh * stem_ow * 64);
+    a_stem = alloc<T>(B * stem_oh * stem_ow * 64);
+    pool = alloc<T>(B * pool_h * pool_w * 64);
+    pool_idx = alloc<uint8_t>(B * pool_h * pool_w * 64);
+    // ---- BasicBlocks (resnet.py:25-54,132-146)
+    int C = 64, H = pool_h, W = pool_w;
+    const T* prev = pool;
+    for (int li = 0; li < 4; ++li) {
+      int planes = 64 << li;
+      for (int bi = 0; bi < layers[li]; ++bi) {
+        blocks.emplace_back();
+        Block& b = blocks.back();
+        b.name = "conv.layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+        int stride = (li > 0 && bi == 0) ? 2 : 1;
+        b.Cin = C;
+        b.Cout = planes;
+        b.Hin = H;
+        b.Win = W;
+        add_conv(b.name + ".conv1", C, planes, 3, stride, 1, H, W, b.c1);
+        add_bn(b.name + ".bn1", planes, b.b1);
+        b.Hout = b.c1.OH;
+        b.Wout = b.c1.OW;
+        add_conv(b.name + ".conv2", planes, planes, 3, 1, 1, b.Hout, b.Wout, b.c2);
+        add_bn(b.name + ".bn2", planes, b.b2);
+        b.ds = (stride != 1 || C != planes);
+        if (b.ds) {
+          add_conv(b.name + ".downsample.0", C, planes, 1, stride, 0, H, W, b.cd);
+          add_bn(b.name + ".downsample.1", planes, b.bd);
+        }
+        int64_t ne = B * b.Hout * b.Wout * planes;
+        b.r1 = alloc<T>(ne);
+        b.a1 = alloc<T>(ne);
+        b.r2 = alloc<T>(ne);
+        b.out = alloc<T>(ne);
+        if (b.ds) {
+          b.rd = alloc<T>(ne);
+          b.idn = alloc<T>(ne);
+        }
+        b.xin = prev;
+        prev = b.out;
+        C = planes;
+        H = b.Hout;
+        W = b.Wout;
+      }
+    }
+    trunk_h = H;
+    trunk_w = W;
+    // conv.fc exists in the state_dict but is never executed (resnet.py:112,148-159)
+    add_param("conv.fc.weight", {1000, 512}, false);
+    add_param("conv.fc.bias", {1000}, false);
+    // ---- decoder (image.py:37-47 / birdview.py:34-44)
+    int dc_in[3] = {640, 256, 128}, dc_out[3] = {256, 128, 64};
+    int h = H, w = W;
+    for (int i = 0; i < 3; ++i) {
+      add_bn("deconv." + std::to_string(3 * i), dc_in[i], dbn[i]);
+      add_deconv("deconv." + std::to_string(3 * i + 1), dc_in[i], dc_out[i], h, w, dcv[i]);
+      dec_bn[i] = alloc<T>(B * h * w * dc_in[i]);
+      dec_in[i] = i == 0 ? alloc<T>(B * h * w * dc_in[0]) : dec_out[i - 1];
+      h *= 2;
+      w *= 2;
+      dec_out[i] = alloc<T>(B * h * w * dc_out[i]);
+    }
+    head_h = h;
+    head_w = w;
+    // ---- heads (image.py:54-60)
+    for (int k2 = 0; k2 < 4; ++k2) {
+      std::string p2 = "location_pred." + std::to_string(k2);
+      add_bn(p2 + ".0", 64, hbn[k2]);
+      hw_off[k2] = add_param(p2 + ".1.weight", {5, 64, 1, 1});
+      hb_off[k2] = add_param(p2 + ".1.bias", {5});
+    }
+    int HW = head_h * head_w;
+    logits = alloc<float>(B * 20 * HW);
+    dlogits = alloc<float>(B * 20 * HW);
+    rowmax = alloc<float>(B * 20);
+    rowsum = alloc<float>(B * 20);
+    preds = alloc<float>(B * 40);
+    onehot_saved = alloc<float>(B * 4);
+    speed_saved = alloc<float>(B);
+    headS = alloc<double>(20 * 65);
+    // ---- scratch
+    int64_t gmax = B * stem_oh * stem_ow * 64;
+    for (int i = 0; i < 4; ++i) g[i] = alloc<T>(gmax);
+    ws_f_n = 4 << 20;
+    ws_f = alloc<float>(ws_f_n);
+    int64_t wd = (1 << 20);
+    if (B * 20 * 65 + 4096 > wd) wd = B * 20 * 65 + 4096;
+    ws_d = alloc<double>(wd);
+  }
+
+  // ------------------------------------------------------------------ op wrappers (fast-path hooks)
+  void pack_weights(lbc_stream_t s) {
+    auto pk = [&](ConvL& c) { ref::pack_weight<T>(s, P + c.w_off, (T*)c.wp, c.Co, c.Ci, c.K); };
+    pk(stem);
+    for (Block& b : blocks) {
+      pk(b.c1);
+      pk(b.c2);
+      if (b.ds) pk(b.cd);
+    }
+    for (int i = 0; i < 3; ++i) pk(dcv[i]);
+  }
+  void conv_forward(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s) {
+    if (fast::conv_fwd<T>(c, x, y, B, s)) return;
+    ref::conv_fwd<T>(s, x, (const T*)c.wp, nullptr, false, y, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
+                     c.OW);
+  }
+  void conv_backward_data(const ConvL& c, const T* dy, T* dx, int B, bool accumulate, lbc_stream_t s) {
+    ref::conv_dgrad<T>(s, dy, (const T*)c.wp, dx, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, nullptr,
+                       false, accumulate);
+  }
+  void conv_backward_weight(const ConvL& c, const T* x, const T* dy, int B, lbc_stream_t s) {
+    ref::conv_wgrad<T>(s, x, dy, G + c.w_off, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, ws_f, ws_f_n);
+  }
+  void bn_forward(BNL& bn, const T* x, int64_t M, const T* residual, bool relu, T* y, bool train, lbc_stream_t s) {
+    if (train) {
+      ref::bn_stats<T>(s, x, M, bn.C, bn.mean, bn.var, ws_d);
+      ref::bn_finalize(s, bn.mean, bn.var, bn.C, M, kBnEps, kBnMomentum, bn.rstd, BUF + bn.rm_off, BUF + bn.rv_off);
+    } else {
+      ref::bn_eval_stats(s, BUF + bn.rm_off, BUF + bn.rv_off, bn.C, kBnEps, bn.mean, bn.rstd);
+    }
+    ref::bn_apply<T>(s, x, bn.mean, bn.rstd, P + bn.g_off, P + bn.b_off, residual, relu, y, M, bn.C);
+  }
+  void bn_backward(BNL& bn, const T* dy, const T* x, T* dx, int64_t M, lbc_stream_t s) {
+    ref::bn_bwd<T>(s, dy, x, bn.mean, bn.rstd, P + bn.g_off, G + bn.g_off, G + bn.b_off, dx, M, bn.C, ws_d);
+  }
+  ref::HeadParams head_params(bool train) {
+    ref::HeadParams hp;
+    for (int k = 0; k < 4; ++k) {
+      hp.gamma[k] = P + hbn[k].g_off;
+      hp.beta[k] = P + hbn[k].b_off;
+      hp.w[k] = P + hw_off[k];
+      hp.bias[k] = P + hb_off[k];
+      hp.mean[k] = train ? hbn[0].mean : hbn[k].mean;
+      hp.rstd[k] = train ? hbn[0].rstd : hbn[k].rstd;
+    }
+    return hp;
+  }
+
+  // ------------------------------------------------------------------ forward
+  void forward(const float* image, const float* speed, const float* onehot, int B, bool train, float* out_pred,
+               float* out_preds, lbc_stream_t s) override {
+    LBC_CHECK(P && BUF, "lbc_net_forward: parameters not bound");
+    LBC_CHECK(B >= 1 && B <= max_batch, "lbc_net_forward: batch " + std::to_string(B) + " outside [1, max_batch]");
+    LBC_CHECK(!train || B * head_h * head_w > 1, "train-mode BatchNorm needs more than one value per channel");
+    cur_B = B;
+    cur_train = train;
+    pack_weights(s);
+    dev_copy(onehot_saved, onehot, sizeof(float) * B * 4, s);
+    dev_copy(speed_saved, speed, sizeof(float) * B, s);
+    ref::input_to_nhwc<T>(s, image, x0, B, in_ch, in_h, in_w, in_ch, normalize, 0.485f, 0.456f, 0.406f, 0.229f,
+                          0.224f, 0.225f);
+    // stem
+    conv_forward(stem, x0, r_stem, B, s);
+    bn_forward(stem_bn, r_stem, (int64_t)B * stem_oh * stem_ow, nullptr, true, a_stem, train, s);
+    ref::maxpool_fwd<T>(s, a_stem, pool, pool_idx, B, stem_oh, stem_ow, 64, pool_h, pool_w);
+    // residual blocks
+    for (Block& b : blocks) {
+      int64_t M = (int64_t)B * b.Hout * b.Wout;
+      conv_forward(b.c1, b.xin, b.r1, B, s);
+      bn_forward(b.b1, b.r1, M, nullptr, true, b.a1, train, s);
+      conv_forward(b.c2, b.a1, b.r2, B, s);
+      const T* identity = b.xin;
+      if (b.ds) {
+        conv_forward(b.cd, b.xin, b.rd, B, s);
+        bn_forward(b.bd, b.rd, M, nullptr, false, b.idn, train, s);
+        identity = b.idn;
+      }
+      bn_forward(b.b2, b.r2, M, identity, true, b.out, train, s);
+    }
+    // late fusion of speed (image.py:77-79)
+    const T* trunk = blocks.back().out;
+    int hw = trunk_h * trunk_w;
+    ref::concat_speed<T>(s, trunk, speed, dec_in[0], B, hw, 512, 128);
+    // decoder: BN -> deconv(+bias) -> ReLU
+    int h = trunk_h, w = trunk_w;
+    for (int i = 0; i < 3; ++i) {
+      bn_forward(dbn[i], dec_in[i], (int64_t)B * h * w, nullptr, false, dec_bn[i], train, s);
+      const ConvL& c = dcv[i];
+      ref::conv_dgrad<T>(s, dec_bn[i], (const T*)c.wp, dec_out[i], B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
+                         c.OW, P + c.b_off, true, false);
+      h *= 2;
+      w *= 2;
+    }
+    // heads
+    const T* hfeat = dec_out[2];
+    int HW = head_h * head_w;
+    int64_t M = (int64_t)B * HW;
+    if (train) {
+      ref::bn_stats<T>(s, hfeat, M, 64, hbn[0].mean, hbn[0].var, ws_d);
+      for (int k = 0; k < 4; ++k)
+        ref::bn_finalize(s, hbn[0].mean, hbn[0].var, 64, M, kBnEps, kBnMomentum, hbn[k].rstd, BUF + hbn[k].rm_off,
+                         BUF + hbn[k].rv_off);
+    } else {
+      for (int k = 0; k < 4; ++k)
+        ref::bn_eval_stats(s, BUF + hbn[k].rm_off, BUF + hbn[k].rv_off, 64, kBnEps, hbn[k].mean, hbn[k].rstd);
+    }
+    ref::head_logits<T>(s, hfeat, head_params(train), logits, B, HW, 64);
+    ref::head_softmax(s, logits, rowmax, rowsum, preds, B, head_h, head_w);
+    if (out_preds) dev_copy(out_preds, preds, sizeof(float) * B * 40, s);
+    if (out_pred) ref::head_select(s, preds, onehot_saved, out_pred, B);
+  }
+
+  // ------------------------------------------------------------------ backward
+  void backward(const float* d_pred, const float* d_preds, lbc_stream_t s) override {
+    LBC_CHECK(G, "lbc_net_backward: gradient buffer not bound");
+    LBC_CHECK(cur_B > 0 && cur_train, "lbc_net_backward: no train-mode forward to differentiate");
+    LBC_CHECK(d_pred || d_preds, "lbc_net_backward: no upstream gradient");
+    const int B = cur_B;
+    const int HW = head_h * head_w;
+    T* gcur = g[0];
+    T* tA = g[1];
+    T* tB = g[2];
+    T* gnext = g[3];
+    // heads
+    const T* hfeat = dec_out[2];
+    ref::HeadParams hp = head_params(true);
+    ref::HeadGrads hg;
+    for (int k = 0; k < 4; ++k) {
+      hg.dgamma[k] = G + hbn[k].g_off;
+      hg.dbeta[k] = G + hbn[k].b_off;
+      hg.dw[k] = G + hw_off[k];
+      hg.dbias[k] = G + hb_off[k];
+    }
+    ref::head_dlogits(s, logits, rowmax, rowsum, preds, onehot_saved, d_pred, d_preds, dlogits, B, head_h, head_w);
+    ref::head_s<T>(s, dlogits, hfeat, hbn[0].mean, hbn[0].rstd, headS, B, HW, 64, ws_d);
+    ref::head_param_grads(s, headS, hp, hg, 64);
+    ref::head_dh<T>(s, dlogits, hfeat, hbn[0].mean, hbn[0].rstd, hp, hg, gcur, B, HW, 64);
+    // decoder, last stage first
+    for (int i = 2; i >= 0; --i) {
+      const ConvL& c = dcv[i];
+      int64_t Mout = (int64_t)B * c.H * c.W;   // deconv output pixels
+      int64_t Min = (int64_t)B * c.OH * c.OW;  // deconv input pixels
+      ref::relu_mask_inplace<T>(s, gcur, dec_out[i], Mout * c.Ci);
+      ref::colsum<T>(s, gcur, Mout, c.Ci, G + c.b_off, ws_d);
+      conv_backward_weight(c, gcur, dec_bn[i], B, s);  // conv-role x = d(out), dy = deconv input
+      ref::conv_fwd<T>(s, gcur, (const T*)c.wp, nullptr, false, tA, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
+                       c.OW);
+      bn_backward(dbn[i], tA, dec_in[i], gnext, Min, s);
+      std::swap(gcur, gnext);
+    }
+    // drop the 128 speed channels (no gradient path to a parameter through them)
+    ref::slice_channels<T>(s, gcur, gnext, (int64_t)B * trunk_h * trunk_w, 640, 512);
+    std::swap(gcur, gnext);
+    // residual blocks in reverse
+    for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
+      Block& b = blocks[bi];
+      int64_t M = (int64_t)B * b.Hout * b.Wout;
+      int64_t ne = M * b.Cout;
+      ref::relu_mask_inplace<T>(s, gcur, b.out, ne);  // gcur = d(sum)
+      bn_backward(b.b2, gcur, b.r2, tA, M, s);        // tA = d r2
+      conv_backward_weight(b.c2, b.a1, tA, B, s);
+      conv_backward_data(b.c2, tA, tB, B, false, s);  // tB = d a1
+      ref::relu_mask_inplace<T>(s, tB, b.a1, ne);
+      bn_backward(b.b1, tB, b.r1, tA, M, s);  // tA = d r1
+      conv_backward_weight(b.c1, b.xin, tA, B, s);
+      conv_backward_data(b.c1, tA, gnext, B, false, s);  // gnext = d xin (main path)
+      if (b.ds) {
+        bn_backward(b.bd, gcur, b.rd, tA, M, s);  // tA = d rd
+        conv_backward_weight(b.cd, b.xin, tA, B, s);
+        conv_backward_data(b.cd, tA, gnext, B, true, s);
+      } else {
+        ref::add_inplace<T>(s, gnext, gcur, ne);
+      }
+      std::swap(gcur, gnext);
+    }
+    // stem: maxpool -> relu -> bn -> conv1 weight gradient (no input gradient)
+    ref::maxpool_bwd<T>(s, gcur, pool_idx, tA, B, stem_oh, stem_ow, 64, pool_h, pool_w);
+    int64_t Ms = (int64_t)B * stem_oh * stem_ow;
+    ref::relu_mask_inplace<T>(s, tA, a_stem, Ms * 64);
+    bn_backward(stem_bn, tA, r_stem, tB, Ms, s);
+    conv_backward_weight(stem, x0, tB, B, s);
+  }
+
+  // ------------------------------------------------------------------ taps
+  int64_t read_tap(const char* name_c, float* out, int64_t cap, lbc_stream_t s) override {
+    std::string name(name_c);
+    const int B = cur_B;
+    LBC_CHECK(B > 0, "read_tap before forward");
+    auto emit = [&](const T* x, int H, int W, int C) -> int64_t {
+      int64_t n = (int64_t)B * H * W * C;
+      LBC_CHECK(n <= cap, "read_tap: output buffer too small");
+      ref::nhwc_to_nchw_f32<T>(s, x, out, B, H, W, C);
+      return n;
+    };
+    if (name == "stem.raw") return emit(r_stem, stem_oh, stem_ow, 64);
+    if (name == "stem.pool") return emit(pool, pool_h, pool_w, 64);
+    for (Block& b : blocks)
+      if (name == b.name) return emit(b.out, b.Hout, b.Wout, b.Cout);
+    for (int i = 0; i < 3; ++i)
+      if (name == "deconv." + std::to_string(3 * i + 1)) return emit(dec_out[i], dcv[i].H, dcv[i].W, dcv[i].Ci);
+    if (name == "logits") {
+      int64_t n = (int64_t)B * 20 * head_h * head_w;
+      LBC_CHECK(n <= cap, "read_tap: output buffer too small");
+      dev_copy(out, logits, sizeof(float) * n, s);
+      return n;
+    }
+    throw Error("read_tap: unknown tap '" + name + "'");
+  }
+};
+
+std::unique_ptr<NetBase> make_net(NetKind kind, Precision prec, int max_batch) {
+  LBC_CHECK(kind == NET_IMAGE_RESNET34 || kind == NET_BIRDVIEW_RESNET18, "unknown net kind");
+  LBC_CHECK(max_batch >= 1, "max_batch must be >= 1");
+  if (prec == PREC_F32) return std::unique_ptr<NetBase>(new Net<float>(kind, prec, max_batch));
+  if (prec == PREC_BF16) return std::unique_ptr<NetBase>(new Net<bf16>(kind, prec, max_batch));
+  throw Error("unknown precision");
+}
+
+}  // namespace lbc

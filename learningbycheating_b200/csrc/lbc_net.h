@@ -1,0 +1,73 @@
+// lbc_net.h -- native graph executor for ImagePolicyModelSS / BirdViewPolicyModelSS
+// (bird_view/models/image.py:22-89, birdview.py:47-79): parameter table in the reference's
+// state_dict order, activation plan in HBM (NHWC), forward (train / eval BN), backward.
+//
+// Parameters, gradients and BN running buffers are flat fp32 arrays OWNED BY THE CALLER (the
+// Python nn.Module re-points its nn.Parameters at views of them, so torch.save / load_state_dict /
+// torch.optim.Adam keep working).  Layouts inside the flat arrays are the reference's:
+// Conv2d [Co][Ci][K][K], ConvTranspose2d [Ci][Co][K][K].
+#pragma once
+#include <memory>
+
+#include "lbc_common.h"
+#include "lbc_ref_ops.h"
+
+namespace lbc {
+
+enum NetKind { NET_IMAGE_RESNET34 = 0, NET_BIRDVIEW_RESNET18 = 1 };
+enum Precision { PREC_F32 = 0, PREC_BF16 = 1 };
+
+struct ParamInfo {
+  std::string name;
+  int ndim;
+  int shape[4];
+  int64_t numel;
+  int64_t offset;  // into the flat parameter / gradient arrays
+  bool on_path;    // false for conv.fc.* (never trained: grad is None in the reference)
+};
+struct BufferInfo {  // running_mean / running_var, in state_dict order
+  std::string name;
+  int64_t numel;
+  int64_t offset;
+};
+
+struct ConvL {
+  int Ci = 0, Co = 0, K = 0, stride = 1, pad = 0;  // conv roles (for a deconv: Co = deconv C_in)
+  int H = 0, W = 0, OH = 0, OW = 0;                // conv-role input / output spatial size
+  int64_t w_off = -1, b_off = -1;
+  bool deconv = false;
+  void* wp = nullptr;  // packed [Co][K][K][Ci]
+};
+struct BNL {
+  int C = 0;
+  int64_t g_off = -1, b_off = -1, rm_off = -1, rv_off = -1;
+  float *mean = nullptr, *var = nullptr, *rstd = nullptr;  // saved batch statistics
+};
+
+class NetBase {
+ public:
+  virtual ~NetBase() {}
+  NetKind kind;
+  Precision prec;
+  int max_batch = 0;
+  int in_ch = 0, in_h = 0, in_w = 0, head_h = 0, head_w = 0;
+  std::vector<ParamInfo> params;
+  std::vector<BufferInfo> buffers;
+  int64_t n_params = 0, n_buffers = 0;
+  float *P = nullptr, *G = nullptr, *BUF = nullptr;  // bound flat arrays
+  void bind(float* p, float* g, float* b) {
+    P = p;
+    G = g;
+    BUF = b;
+  }
+  virtual void forward(const float* image, const float* speed, const float* onehot, int B, bool train,
+                       float* out_pred, float* out_preds, lbc_stream_t s) = 0;
+  virtual void backward(const float* d_pred, const float* d_preds, lbc_stream_t s) = 0;
+  // debugging / parity taps: copy a named internal tensor out as fp32 NCHW
+  virtual int64_t read_tap(const char* name, float* out, int64_t cap, lbc_stream_t s) = 0;
+  virtual size_t workspace_bytes() const = 0;
+};
+
+std::unique_ptr<NetBase> make_net(NetKind kind, Precision prec, int max_batch);
+
+}  // namespace lbc

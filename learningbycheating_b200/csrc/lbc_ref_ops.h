@@ -20,6 +20,11 @@ struct k_head_softmax; struct k_head_select; struct k_head_dlogits; struct k_hea
 struct k_head_dh; struct k_pack_w; struct k_adam; struct k_l1_loss; struct k_phase0_target; struct k_phase1_fwd;
 struct k_phase1_bwd; struct k_cast; struct k_speed_stats; struct k_scale;
 
+// accumulator type: double for the fp32 parity path (the CPU oracle's blocked GEMMs / double-accumulating
+// reductions are far more accurate than a sequential fp32 sum), float for bf16 storage
+template <class T> struct Acc { typedef float type; };
+template <> struct Acc<float> { typedef double type; };
+
 // ---------------------------------------------------------------------------------------------
 // image NCHW fp32 -> NHWC T, optional (x-mean)/std   (bird_view/models/common.py:108-109)
 template <class T>
@@ -60,7 +65,8 @@ void conv_fwd(lbc_stream_t s, const T* x, const T* w, const float* bias, bool re
     int64_t q = p / OW;
     int oh = (int)(q % OH);
     int b = (int)(q / OH);
-    float acc = bias ? bias[co] : 0.f;
+    typedef typename Acc<T>::type acc_t;
+    acc_t acc = bias ? (acc_t)bias[co] : (acc_t)0;
     for (int kh = 0; kh < K; ++kh) {
       int ih = oh * stride - pad + kh;
       if (ih < 0 || ih >= H) continue;
@@ -69,18 +75,19 @@ void conv_fwd(lbc_stream_t s, const T* x, const T* w, const float* bias, bool re
         if (iw < 0 || iw >= W) continue;
         const T* xp = x + (((int64_t)b * H + ih) * W + iw) * Ci;
         const T* wp = w + (((int64_t)co * K + kh) * K + kw) * Ci;
-        float a0 = 0.f, a1 = 0.f;
+        acc_t a0 = 0, a1 = 0;
         int ci = 0;
         for (; ci + 1 < Ci; ci += 2) {
-          a0 += ldf(xp, ci) * ldf(wp, ci);
-          a1 += ldf(xp, ci + 1) * ldf(wp, ci + 1);
+          a0 += (acc_t)ldf(xp, ci) * (acc_t)ldf(wp, ci);
+          a1 += (acc_t)ldf(xp, ci + 1) * (acc_t)ldf(wp, ci + 1);
         }
-        if (ci < Ci) a0 += ldf(xp, ci) * ldf(wp, ci);
+        if (ci < Ci) a0 += (acc_t)ldf(xp, ci) * (acc_t)ldf(wp, ci);
         acc += a0 + a1;
       }
     }
-    if (relu) acc = acc > 0.f ? acc : 0.f;
-    stf(y, i, acc);
+    float r = (float)acc;
+    if (relu) r = r > 0.f ? r : 0.f;
+    stf(y, i, r);
   });
 }
 
@@ -98,7 +105,8 @@ void conv_dgrad(lbc_stream_t s, const T* dy, const T* w, T* dx, int N, int H, in
     int64_t q = p / W;
     int ih = (int)(q % H);
     int b = (int)(q / H);
-    float acc = bias_ci ? bias_ci[ci] : 0.f;
+    typedef typename Acc<T>::type acc_t;
+    acc_t acc = bias_ci ? (acc_t)bias_ci[ci] : (acc_t)0;
     for (int kh = 0; kh < K; ++kh) {
       int t = ih + pad - kh;
       if (t < 0 || (t % stride) != 0) continue;
@@ -112,14 +120,15 @@ void conv_dgrad(lbc_stream_t s, const T* dy, const T* w, T* dx, int N, int H, in
         const T* dyp = dy + (((int64_t)b * OH + oh) * OW + ow) * Co;
         const T* wp = w + ((int64_t)kh * K + kw) * Ci + ci;
         int64_t wstride = (int64_t)K * K * Ci;
-        float a0 = 0.f;
-        for (int co = 0; co < Co; ++co) a0 += ldf(dyp, co) * ldf(wp, (int64_t)co * wstride);
+        acc_t a0 = 0;
+        for (int co = 0; co < Co; ++co) a0 += (acc_t)ldf(dyp, co) * (acc_t)ldf(wp, (int64_t)co * wstride);
         acc += a0;
       }
     }
-    if (accumulate) acc += ldf(dx, i);
-    if (relu) acc = acc > 0.f ? acc : 0.f;
-    stf(dx, i, acc);
+    if (accumulate) acc += (acc_t)ldf(dx, i);
+    float r = (float)acc;
+    if (relu) r = r > 0.f ? r : 0.f;
+    stf(dx, i, r);
   });
 }
 
@@ -149,22 +158,23 @@ void conv_wgrad(lbc_stream_t s, const T* x, const T* dy, float* dw_ref, int N, i
     int64_t chunk = t / Co;
     int64_t r0 = chunk * rows_per, r1 = r0 + rows_per;
     if (r1 > rows) r1 = rows;
-    float acc = 0.f;
+    typedef typename Acc<T>::type acc_t;
+    acc_t acc = 0;
     for (int64_t r = r0; r < r1; ++r) {
       int b = (int)(r / OH), oh = (int)(r % OH);
       int ih = oh * stride - pad + kh;
       if (ih < 0 || ih >= H) continue;
       const T* dyp = dy + (((int64_t)b * OH + oh) * OW) * Co + co;
       const T* xp = x + (((int64_t)b * H + ih) * W) * Ci + ci;
-      float a = 0.f;
+      acc_t a = 0;
       for (int ow = 0; ow < OW; ++ow) {
         int iw = ow * stride - pad + kw;
         if (iw < 0 || iw >= W) continue;
-        a += ldf(dyp, (int64_t)ow * Co) * ldf(xp, (int64_t)iw * Ci);
+        a += (acc_t)ldf(dyp, (int64_t)ow * Co) * (acc_t)ldf(xp, (int64_t)iw * Ci);
       }
       acc += a;
     }
-    ws[i] = acc;
+    ws[i] = (float)acc;
   });
   par_for<k_reduce_part>(s, wsize, [=] LBC_HD(int64_t i) {
     double a = 0.0;
@@ -458,10 +468,11 @@ struct HeadParams {
   const float* beta[4];
   const float* w[4];     // [5][C]
   const float* bias[4];  // [5]
+  const float* mean[4];  // per-head BN statistics (train: all four alias the shared batch stats)
+  const float* rstd[4];
 };
 template <class T>
-void head_logits(lbc_stream_t s, const T* h, const float* mean, const float* rstd, HeadParams hp, float* logits,
-                 int N, int HW, int C) {
+void head_logits(lbc_stream_t s, const T* h, HeadParams hp, float* logits, int N, int HW, int C) {
   // logits layout [N][20][HW]
   int64_t n = (int64_t)N * 20 * HW;
   par_for<k_head_logits>(s, n, [=] LBC_HD(int64_t i) {
@@ -474,6 +485,8 @@ void head_logits(lbc_stream_t s, const T* h, const float* mean, const float* rst
     const float* g = hp.gamma[k];
     const float* be = hp.beta[k];
     const float* w = hp.w[k] + j * C;
+    const float* mean = hp.mean[k];
+    const float* rstd = hp.rstd[k];
     float acc = hp.bias[k][j];
     for (int c = 0; c < C; ++c) {
       float z = (ldf(hpix, c) - mean[c]) * rstd[c] * g[c] + be[c];

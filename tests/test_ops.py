@@ -1,0 +1,191 @@
+"""Single-kernel parity through the C ABI (lbc_op_*): each op against torch's CPU implementation on the same
+seeded inputs, at the distinct shapes of the path.  The CPU variants run the host-emulation build (host logic +
+kernel bodies); the gpu variants run the same calls through liblbc_b200.so on the B200, fp32 and bf16."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+def _L():
+    from learningbycheating_b200 import _lib
+    return _lib
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+CONV_CASES = [
+    # N, H, W, Ci, Co, K, stride, pad
+    (2, 12, 20, 3, 16, 7, 2, 3),     # stem-like
+    (2, 10, 24, 64, 64, 3, 1, 1),    # layer1-like 3x3 s1
+    (2, 10, 24, 64, 128, 3, 2, 1),   # stage transition 3x3 s2
+    (2, 10, 24, 64, 128, 1, 2, 0),   # downsample 1x1 s2
+    (3, 5, 12, 128, 128, 3, 1, 1),   # odd spatial size like layer4
+]
+
+
+def _conv_case(dev, case, precision, tol):
+    _lib = _L()
+    N, H, W, Ci, Co, K, s, p = case
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, K, K, generator=g) / (Ci * K * K) ** 0.5
+    y_ref = F.conv2d(x, w, None, s, p)
+    OH, OW = y_ref.shape[2:]
+    dy = torch.randn(N, Co, OH, OW, generator=g)
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, w, dy, s, p)
+    dw_ref = torch.nn.grad.conv2d_weight(x, w.shape, dy, s, p)
+    L = _lib.lib()
+    xd, wd, dyd = _nhwc(x).to(dev), w.contiguous().to(dev), _nhwc(dy).to(dev)
+    y = torch.empty(N, OH, OW, Co, device=dev)
+    _lib.check(L.lbc_op_conv_fwd(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(y), N, H, W, Ci, Co, K, s, p, precision, None))
+    dx = torch.empty(N, H, W, Ci, device=dev)
+    _lib.check(L.lbc_op_conv_dgrad(_lib.ptr(dyd), _lib.ptr(wd), _lib.ptr(dx), N, H, W, Ci, Co, K, s, p, precision, None))
+    dw = torch.empty(Co, Ci, K, K, device=dev)
+    _lib.check(L.lbc_op_conv_wgrad(_lib.ptr(xd), _lib.ptr(dyd), _lib.ptr(dw), N, H, W, Ci, Co, K, s, p, precision, None))
+    for got, ref, what in ((_nchw(y.cpu()), y_ref, "fwd"), (_nchw(dx.cpu()), dx_ref, "dgrad"), (dw.cpu(), dw_ref, "wgrad")):
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        assert err < tol, (what, case, err)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_ops_cpu(backend, case):
+    _conv_case(backend, case, 0, 2e-5)
+
+
+def test_conv_ops_bf16_storage_cpu(backend):
+    _conv_case(backend, CONV_CASES[1], 1, 3e-2)
+
+
+def _bn_case(dev, M, C, relu, with_res):
+    _lib = _L()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(M, C, generator=g) * 2 + 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    res = torch.randn(M, C, generator=g) if with_res else None
+    xt = x.t().reshape(1, C, M, 1).clone().requires_grad_(True)
+    gp, bp = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y_ref = F.batch_norm(xt, None, None, gp, bp, True, 0.1, 1e-5)
+    dy = torch.randn(M, C, generator=g)
+    y_ref.backward(dy.t().reshape(1, C, M, 1))
+    out_ref = y_ref.detach().reshape(C, M).t()
+    if with_res:
+        out_ref = out_ref + res
+    if relu:
+        out_ref = out_ref.clamp_min(0)
+    L = _lib.lib()
+    d = lambda t: None if t is None else t.contiguous().to(dev)
+    y, mean, var = torch.empty(M, C, device=dev), torch.empty(C, device=dev), torch.empty(C, device=dev)
+    _lib.check(L.lbc_op_bn_train(_lib.ptr(d(x)), _lib.ptr(d(gamma)), _lib.ptr(d(beta)), _lib.ptr(d(res)), int(relu),
+                                 _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var), M, C, None))
+    assert (y.cpu() - out_ref).abs().max() < 2e-5
+    assert (mean.cpu() - x.mean(0)).abs().max() < 1e-5
+    assert (var.cpu() - x.var(0, unbiased=False)).abs().max() < 2e-5
+    dg, db, dx = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty(M, C, device=dev)
+    _lib.check(L.lbc_op_bn_bwd(_lib.ptr(d(dy)), _lib.ptr(d(x)), _lib.ptr(d(gamma)), _lib.ptr(dg), _lib.ptr(db),
+                               _lib.ptr(dx), M, C, None))
+    assert (dg.cpu() - gp.grad).abs().max() < 1e-4 * max(1.0, gp.grad.abs().max().item())
+    assert (db.cpu() - bp.grad).abs().max() < 1e-4 * max(1.0, bp.grad.abs().max().item())
+    assert (dx.cpu() - xt.grad.reshape(C, M).t()).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("M,C,relu,res", [(1000, 64, True, False), (777, 128, True, True), (60, 640, False, False)])
+def test_bn_ops_cpu(backend, M, C, relu, res):
+    _bn_case(backend, M, C, relu, res)
+
+
+def _maxpool_case(dev):
+    _lib = _L()
+    g = torch.Generator().manual_seed(9)
+    N, H, W, C = 2, 10, 12, 8
+    x = torch.randn(N, C, H, W, generator=g).clamp_min(0).requires_grad_(True)   # post-ReLU: ties at 0
+    y_ref = F.max_pool2d(x, 3, 2, 1)
+    dy = torch.randn(y_ref.shape, generator=g)
+    (y_ref * dy).sum().backward()
+    L = _lib.lib()
+    xd, dyd = _nhwc(x.detach()).to(dev), _nhwc(dy).to(dev)
+    y = torch.empty(N, y_ref.shape[2], y_ref.shape[3], C, device=dev)
+    dx = torch.empty(N, H, W, C, device=dev)
+    _lib.check(L.lbc_op_maxpool(_lib.ptr(xd), _lib.ptr(y), _lib.ptr(dyd), _lib.ptr(dx), N, H, W, C, None))
+    assert torch.equal(_nchw(y.cpu()), y_ref.detach())
+    # ties only happen at exact zeros where the ReLU mask kills the gradient: compare masked
+    mask = (x.detach() > 0).float()
+    assert torch.allclose(_nchw(dx.cpu()) * mask, x.grad * mask, atol=1e-6)
+
+
+def test_maxpool_cpu(backend):
+    _maxpool_case(backend)
+
+
+def _softmax_case(dev):
+    """SpatialSoftmax known answers the reference left commented out (common.py:192-201) + random logits."""
+    _lib = _L()
+    from lbc_testing import gold
+    ka = gold("spatial_softmax_known.npz")
+    L = _lib.lib()
+    logits = torch.zeros(20, 48 * 48)
+    keys = list(ka.files)
+    for r, key in enumerate(keys):
+        i, j = map(int, key.split("_"))
+        logits[r, i * 48 + j] = 100
+    g = torch.Generator().manual_seed(11)
+    logits[len(keys):] = torch.randn(20 - len(keys), 48 * 48, generator=g) * 3
+    out = torch.empty(20, 2, device=dev)
+    _lib.check(L.lbc_op_spatial_softmax(_lib.ptr(logits.to(dev)), _lib.ptr(out), 20, 48, 48, None))
+    out = out.cpu()
+    for r, key in enumerate(keys):
+        np.testing.assert_allclose(out[r].numpy(), ka[key].reshape(-1), atol=1e-6)
+    import lbc_oracle as orc
+    px, py = orc.spatial_grid(48, 48)
+    w = torch.softmax(logits, -1)
+    ref = torch.stack([(px * w).sum(-1), (py * w).sum(-1)], -1)
+    assert (out - ref).abs().max() < 1e-6
+
+
+def test_spatial_softmax_cpu(backend):
+    _softmax_case(backend)
+
+
+def test_errors_are_loud(backend):
+    _lib = _L()
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    assert L.lbc_net_create(7, 0, 2, ctypes.byref(h)) != 0
+    assert b"unknown net kind" in L.lbc_last_error()
+    with pytest.raises(_lib.LbcError):
+        _lib.check(L.lbc_adam_step(None, None, None, None, 0, 1e-4, 0.9, 0.999, 1e-8, 0, 1.0, None))
+
+
+# ------------------------------------------------------------------ on the B200
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_ops_gpu_fp32(backend, case):
+    assert backend == "cuda"
+    _conv_case("cuda", case, 0, 2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CONV_CASES[1:])
+def test_conv_ops_gpu_bf16(backend, case):
+    assert backend == "cuda"
+    _conv_case("cuda", case, 1, 3e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,C,relu,res", [(1000, 64, True, False), (777, 128, True, True), (60, 640, False, False)])
+def test_bn_ops_gpu(backend, M, C, relu, res):
+    _bn_case("cuda", M, C, relu, res)
+
+
+@pytest.mark.gpu
+def test_maxpool_softmax_gpu(backend):
+    _maxpool_case("cuda")
+    _softmax_case("cuda")
