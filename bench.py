@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the ResNet-34 160x384 waypoint train step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU implementation of the same step
+
+Workload (config.workload = "config2"): BASELINE.json configs[1] -- ImagePolicyModelSS('resnet34'), synthetic
+batch 256/GPU, one full training step = student forward (train-mode BN) + phase-0 L1 waypoint loss against fixed
+image-space targets + backward + Adam(lr=1e-4); data-parallel replicas all-reduce the gradient once per step.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+GFLOP_PER_TRAIN_IMG = 28.034      # 3 x 9.441116 - 0.289014 (no dgrad for the stem)
+METRIC = "images/sec (ResNet34 160x384 waypoint train step)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def synthetic(B, seed, torch):
+    g = torch.Generator().manual_seed(seed)
+    rgb = torch.randint(0, 256, (B, 3, 160, 384), dtype=torch.uint8, generator=g).float() / 255
+    speed = torch.rand(B, generator=g) * 10
+    cmd = torch.randint(1, 5, (B,), generator=g).float()
+    target = torch.rand(B, 5, 2, generator=g) * torch.tensor([384.0, 160.0])
+    return rgb, speed, cmd, target
+
+
+def cpu_step_rate(torch, B, warm, iters, threads=None):
+    """The reference's CPU implementation of the step (oracle port: torch CPU kernels + Adam), images/s."""
+    import lbc_oracle as orc
+    import learningbycheating_b200 as lbc
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = orc.leafify(lbc.ImagePolicyModelSS("resnet34", all_branch=True).state_dict())
+    rgb, speed, cmd, target = synthetic(B, 1, torch)
+    oh = orc.one_hot(cmd)
+    st = orc.new_adam_state()
+
+    def step():
+        for k in orc.param_keys(sd):
+            sd[k].grad = None
+        pred, _, newbuf = orc.policy_forward(sd, rgb, speed, oh, "resnet34", True, True)
+        loss = orc.phase0_loss(pred, target).mean()
+        loss.backward()
+        st["step"] += 1
+        with torch.no_grad():
+            pk = [k for k in orc.param_keys(sd) if sd[k].grad is not None]
+            for k in pk:
+                if k not in st["m"]:
+                    st["m"][k] = torch.zeros_like(sd[k])
+                    st["v"][k] = torch.zeros_like(sd[k])
+            orc.adam_step({k: sd[k] for k in pk}, {k: sd[k].grad for k in pk}, st["m"], st["v"], st["step"])
+            for k, v in newbuf.items():
+                sd[k] = v
+        return float(loss.detach())
+
+    for _ in range(warm):
+        step()
+    t0 = time.time()
+    for _ in range(iters):
+        step()
+    dt = time.time() - t0
+    return B * iters / dt, dt / iters
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = 8
+    rate, sec = cpu_step_rate(torch, B, max(1, min(args.warmup, 2)), max(1, args.steps), cores)
+    sample = "oracle port (torch CPU fp32) of the config2 step on a bounded sample: batch %d per step" % B
+    out = dict(impl="reference", metric=METRIC, value=rate, unit="images/s", n_gpus=args.gpus, steps=args.steps,
+               warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype="f32", data="synthetic",
+               config=dict(workload="config2", step="student fwd+bwd+Adam, phase-0 L1 vs fixed targets", batch_per_step=B),
+               cpu_baseline=dict(value=rate, unit="images/s", cores=torch.get_num_threads(), kind="port", sample=sample),
+               e2e=dict(value=rate, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import learningbycheating_b200 as lbc
+    from learningbycheating_b200 import _lib, train_image_phase0 as p0
+    from learningbycheating_b200.distributed import DataParallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a B200; there is no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    L.lbc_set_fast_kernels(0 if args.no_fast else 1)
+    B = args.batch
+    torch.manual_seed(0)
+    net = lbc.ImagePolicyModelSS("resnet34", all_branch=True, lbc_precision=args.precision).to(dev).train()
+    opt = lbc.Adam(net.parameters(), lr=1e-4)
+    dp = DataParallel(net, opt)
+    crit = p0.LocationLoss(device=dev)
+    rgb_h, speed_h, cmd_h, target_h = synthetic(B, 1 + rank, torch)
+    rgb, speed, target = rgb_h.to(dev), speed_h.to(dev), target_h.to(dev)
+    oh = lbc.one_hot(cmd_h).to(dev)
+
+    def step():
+        pred, _ = net(rgb, speed, oh)
+        loss = crit(pred, target).mean()
+        opt.zero_grad()
+        loss.backward()
+        dp.step_after_backward()
+        return loss
+
+    step()                      # builds the native engine (allocations) outside every timed region
+    dp.sync_initial_state()
+    for _ in range(args.warmup):
+        step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    n0 = L.lbc_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.lbc_kernel_launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    rgb_p, speed_p, target_p = rgb_h.pin_memory(), speed_h.pin_memory(), target_h.pin_memory()
+
+    def e2e_step():
+        r = rgb_p.to(dev, non_blocking=True)
+        s = speed_p.to(dev, non_blocking=True)
+        c = lbc.one_hot(cmd_h).pin_memory().to(dev, non_blocking=True)
+        tg = target_p.to(dev, non_blocking=True)
+        pred, _ = net(r, s, c)
+        l = crit(pred, tg).mean()
+        opt.zero_grad()
+        l.backward()
+        dp.step_after_backward()
+        return l.item()           # device -> host read of the step's loss
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        lv = e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(t.item()) / 1e3)
+    h2d = rgb_p.numel() * 4 + speed_p.numel() * 4 + B * 4 * 4 + target_p.numel() * 4
+
+    # ---- per-category device timing (CUDA events on the launching stream) for the roofline of the dominant kernel
+    roof = None
+    cats = {}
+    if rank == 0:
+        import ctypes
+        peaks = load_peaks()
+        L.lbc_prof_reset()
+        L.lbc_prof_enable(1)
+        nprof = 2
+        for _ in range(nprof):
+            step()
+        torch.cuda.synchronize()
+        L.lbc_prof_enable(0)
+        for cat in ("conv_fwd", "conv_dgrad", "conv_wgrad", "bn_fwd", "bn_bwd"):
+            msd, cnt, fl, by = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_double()
+            _lib.check(L.lbc_prof_get(cat.encode(), ctypes.byref(msd), ctypes.byref(cnt), ctypes.byref(fl), ctypes.byref(by)))
+            cats[cat] = dict(ms_per_step=msd.value / nprof, launches_per_step=cnt.value / nprof,
+                             gflop_per_step=fl.value / nprof / 1e9, gbytes_per_step=by.value / nprof / 1e9)
+        L.lbc_prof_reset()
+        conv_ms = sum(cats[c]["ms_per_step"] for c in ("conv_fwd", "conv_dgrad", "conv_wgrad"))
+        conv_gf = sum(cats[c]["gflop_per_step"] for c in ("conv_fwd", "conv_dgrad", "conv_wgrad"))
+        achieved = conv_gf / conv_ms if conv_ms > 0 else 0.0     # GFLOP/ms == TFLOP/s
+        roof = dict(bound="tensor", kernel="implicit-GEMM convolutions (fwd+dgrad+wgrad, all layers)",
+                    achieved=achieved, peak=peaks["tf_sust"], unit="TFLOP/s", frac=achieved / peaks["tf_sust"],
+                    traffic=None, peak_source=peaks["source"] + " bf16_tflops_sustained", per_category=cats)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, sec = cpu_step_rate(torch, 8, 1, 4, cores)
+        cpu_base = dict(value=rate, unit="images/s", cores=torch.get_num_threads(), kind="port",
+                        sample="oracle port (torch CPU fp32) of the same step, batch 8, 4 timed iterations")
+
+    if rank == 0:
+        out = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                   dtype=("bf16" if args.precision == "bf16" else "f32"), data="synthetic",
+                   config=dict(workload="config2", model="ImagePolicyModelSS resnet34 160x384", global_batch=world * B,
+                               batch_per_gpu=B, parallelism="dp%d" % world,
+                               step="student fwd+bwd+Adam, phase-0 L1 vs fixed targets",
+                               l2="inputs+activations per step (>5 GB) far exceed the 126 MB L2; no explicit flush",
+                               fast_kernels=not args.no_fast),
+                   e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, steps=e2e_steps),
+                   gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu_base,
+                   step_tflops=value * GFLOP_PER_TRAIN_IMG / 1e3, last_loss=float(loss))
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-fast", action="store_true", help="correctness-first kernels only")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

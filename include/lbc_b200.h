@@ -32,6 +32,16 @@ const char* lbc_build_info(void);
 /* enable / disable the tcgen05 + fused kernels (tests compare them with the correctness-first kernels) */
 int lbc_set_fast_kernels(int enabled);
 
+/* ---- instrumentation used by bench.py ---- */
+/* number of kernels this library has launched so far (all streams) */
+long long lbc_kernel_launch_count(void);
+/* per-category CUDA-event timing of the engine's ops ("conv_fwd", "conv_dgrad", "conv_wgrad", "bn_fwd",
+ * "bn_bwd", "pool", "elementwise", "head", "pack"): enable, run steps, then read totals.  flops / bytes are the
+ * ALGORITHMIC figures of the timed launches. */
+int lbc_prof_enable(int on);
+int lbc_prof_reset(void);
+int lbc_prof_get(const char* category, double* total_ms, long long* count, double* flops, double* bytes);
+
 /* ---- network object: nn.Module construction (image.py:23-62, common.py:69-83, resnet.py:95-146) ---- */
 int lbc_net_create(int kind, int precision, int max_batch, lbc_net_t** out);
 void lbc_net_destroy(lbc_net_t* net);

@@ -29,6 +29,11 @@ def _declare(lib):
         "lbc_device_kind": (i, []),
         "lbc_build_info": (ctypes.c_char_p, []),
         "lbc_set_fast_kernels": (i, [i]),
+        "lbc_kernel_launch_count": (ctypes.c_longlong, []),
+        "lbc_prof_enable": (i, [i]),
+        "lbc_prof_reset": (i, []),
+        "lbc_prof_get": (i, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong),
+                             ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
         "lbc_net_create": (i, [i, i, i, ctypes.POINTER(vp)]),
         "lbc_net_destroy": (None, [vp]),
         "lbc_net_num_params": (i, [vp]),

@@ -111,6 +111,47 @@ int lbc_set_fast_kernels(int enabled) {
   return 0;
 }
 
+long long lbc_kernel_launch_count(void) { return g_launches; }
+int lbc_prof_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+int lbc_prof_reset(void) {
+#ifndef LBC_HOST_EMU
+  cudaDeviceSynchronize();
+  for (auto& e : g_prof) {
+    cudaEventDestroy(e.e0);
+    cudaEventDestroy(e.e1);
+  }
+#endif
+  g_prof.clear();
+  return 0;
+}
+int lbc_prof_get(const char* category, double* total_ms, long long* count, double* flops, double* bytes) {
+  return guarded([&] {
+    double ms = 0, fl = 0, by = 0;
+    long long n = 0;
+#ifndef LBC_HOST_EMU
+    LBC_CUDA(cudaDeviceSynchronize());
+#endif
+    for (auto& e : g_prof) {
+      if (e.cat != category) continue;
+#ifndef LBC_HOST_EMU
+      float t = 0.f;
+      LBC_CUDA(cudaEventElapsedTime(&t, e.e0, e.e1));
+      ms += t;
+#endif
+      fl += e.flops;
+      by += e.bytes;
+      ++n;
+    }
+    *total_ms = ms;
+    *count = n;
+    *flops = fl;
+    *bytes = by;
+  });
+}
+
 int lbc_net_create(int kind, int precision, int max_batch, lbc_net_t** out) {
   return guarded([&] {
     require_device();

@@ -140,6 +140,44 @@ inline void dev_copy(void* dst, const void* src, size_t bytes, lbc_stream_t s) {
 #endif
 }
 
+// ------------------------------------------------------------------ launch counter + per-category profiler
+// g_launches counts every kernel the library launches (bench.py reports it as gpu_launches).
+extern long long g_launches;
+struct ProfEntry {
+  std::string cat;
+  double flops, bytes;
+#ifndef LBC_HOST_EMU
+  cudaEvent_t e0, e1;
+#endif
+};
+extern bool g_prof_on;
+extern std::vector<ProfEntry> g_prof;
+// RAII: brackets the launches of one op with CUDA events on the launching stream when profiling is on.
+struct ProfScope {
+  bool on;
+  lbc_stream_t s;
+  size_t idx;
+  ProfScope(const char* cat, lbc_stream_t stream, double flops, double bytes) : on(g_prof_on), s(stream), idx(0) {
+    if (!on) return;
+    ProfEntry e;
+    e.cat = cat;
+    e.flops = flops;
+    e.bytes = bytes;
+#ifndef LBC_HOST_EMU
+    cudaEventCreate(&e.e0);
+    cudaEventCreate(&e.e1);
+    cudaEventRecord(e.e0, s);
+#endif
+    idx = g_prof.size();
+    g_prof.push_back(e);
+  }
+  ~ProfScope() {
+#ifndef LBC_HOST_EMU
+    if (on) cudaEventRecord(g_prof[idx].e1, s);
+#endif
+  }
+};
+
 // ------------------------------------------------------------------ par_for
 // The correctness-first kernels are "independent thread" kernels: one logical thread per
 // output element, no shared memory, no atomics -> bitwise deterministic, and the same body
@@ -147,6 +185,7 @@ inline void dev_copy(void* dst, const void* src, size_t bytes, lbc_stream_t s) {
 #ifdef LBC_HOST_EMU
 template <class Tag, class F>
 inline void par_for(lbc_stream_t, int64_t n, F f) {
+  ++g_launches;
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) f(i);
 }
@@ -163,6 +202,7 @@ inline void par_for(lbc_stream_t s, int64_t n, F f) {
   int64_t nb = (n + bs - 1) / bs;
   LBC_CHECK(nb < (1ll << 31), "par_for grid too large");
   par_for_kernel<Tag, F><<<(unsigned)nb, bs, 0, s>>>(n, f);
+  ++g_launches;
   LBC_CUDA(cudaGetLastError());
 }
 #endif

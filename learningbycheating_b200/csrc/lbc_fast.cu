@@ -2,6 +2,9 @@
 #include "lbc_fast.h"
 
 namespace lbc {
+long long g_launches = 0;
+bool g_prof_on = false;
+std::vector<ProfEntry> g_prof;
 namespace fast {
 
 static bool g_enabled = true;

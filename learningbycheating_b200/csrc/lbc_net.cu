@@ -269,19 +269,27 @@ class Net : public NetBase {
     }
     for (int i = 0; i < 3; ++i) pk(dcv[i]);
   }
+  static double conv_flops(const ConvL& c, int B) {
+    return 2.0 * B * c.OH * c.OW * (double)c.Co * c.K * c.K * c.Ci;
+  }
   void conv_forward(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s) {
+    ProfScope ps("conv_fwd", s, conv_flops(c, B), 0);
     if (fast::conv_fwd<T>(c, x, y, B, s)) return;
     ref::conv_fwd<T>(s, x, (const T*)c.wp, nullptr, false, y, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
                      c.OW);
   }
   void conv_backward_data(const ConvL& c, const T* dy, T* dx, int B, bool accumulate, lbc_stream_t s) {
+    ProfScope ps("conv_dgrad", s, conv_flops(c, B), 0);
     ref::conv_dgrad<T>(s, dy, (const T*)c.wp, dx, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, nullptr,
                        false, accumulate);
   }
   void conv_backward_weight(const ConvL& c, const T* x, const T* dy, int B, lbc_stream_t s) {
+    ProfScope ps("conv_wgrad", s, conv_flops(c, B), 0);
     ref::conv_wgrad<T>(s, x, dy, G + c.w_off, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, ws_f, ws_f_n);
   }
   void bn_forward(BNL& bn, const T* x, int64_t M, const T* residual, bool relu, T* y, bool train, lbc_stream_t s) {
+    // algorithmic bytes: stats read (train) + apply read (+residual) + write
+    ProfScope ps("bn_fwd", s, 0, (double)M * bn.C * sizeof(T) * ((train ? 1 : 0) + 2 + (residual ? 1 : 0)));
     if (train) {
       ref::bn_stats<T>(s, x, M, bn.C, bn.mean, bn.var, ws_d);
       ref::bn_finalize(s, bn.mean, bn.var, bn.C, M, kBnEps, kBnMomentum, bn.rstd, BUF + bn.rm_off, BUF + bn.rv_off);
@@ -291,6 +299,8 @@ class Net : public NetBase {
     ref::bn_apply<T>(s, x, bn.mean, bn.rstd, P + bn.g_off, P + bn.b_off, residual, relu, y, M, bn.C);
   }
   void bn_backward(BNL& bn, const T* dy, const T* x, T* dx, int64_t M, lbc_stream_t s) {
+    // algorithmic bytes: reduce pass reads dy,x ; apply pass reads dy,x writes dx
+    ProfScope ps("bn_bwd", s, 0, (double)M * bn.C * sizeof(T) * 5);
     ref::bn_bwd<T>(s, dy, x, bn.mean, bn.rstd, P + bn.g_off, G + bn.g_off, G + bn.b_off, dx, M, bn.C, ws_d);
   }
   ref::HeadParams head_params(bool train) {
@@ -346,6 +356,7 @@ class Net : public NetBase {
     for (int i = 0; i < 3; ++i) {
       bn_forward(dbn[i], dec_in[i], (int64_t)B * h * w, nullptr, false, dec_bn[i], train, s);
       const ConvL& c = dcv[i];
+      ProfScope ps("conv_dgrad", s, conv_flops(c, B), 0);
       ref::conv_dgrad<T>(s, dec_bn[i], (const T*)c.wp, dec_out[i], B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
                          c.OW, P + c.b_off, true, false);
       h *= 2;
@@ -403,8 +414,11 @@ class Net : public NetBase {
       ref::relu_mask_inplace<T>(s, gcur, dec_out[i], Mout * c.Ci);
       ref::colsum<T>(s, gcur, Mout, c.Ci, G + c.b_off, ws_d);
       conv_backward_weight(c, gcur, dec_bn[i], B, s);  // conv-role x = d(out), dy = deconv input
-      ref::conv_fwd<T>(s, gcur, (const T*)c.wp, nullptr, false, tA, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
-                       c.OW);
+      {
+        ProfScope ps("conv_fwd", s, conv_flops(c, B), 0);
+        ref::conv_fwd<T>(s, gcur, (const T*)c.wp, nullptr, false, tA, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad,
+                         c.OH, c.OW);
+      }
       bn_backward(dbn[i], tA, dec_in[i], gnext, Min, s);
       std::swap(gcur, gnext);
     }
