@@ -53,7 +53,7 @@ def build_cuda(force=False, verbose=False):
         if verbose:
             print(out)
         objs.append(obj)
-    _run([nvcc, "-shared", "-o", CUDA_LIB] + objs + ["-lcudart"])
+    _run([nvcc, "-shared", "-o", CUDA_LIB] + objs)   # static cudart (nvcc default)
     return CUDA_LIB
 
 

@@ -19,11 +19,13 @@
 #ifdef LBC_HOST_EMU
 #define LBC_HD
 #define LBC_DEV
+#define LBC_LAMBDA
 typedef void* lbc_stream_t;
 #else
 #include <cuda_runtime.h>
 #define LBC_HD __host__ __device__
 #define LBC_DEV __device__
+#define LBC_LAMBDA __device__   /* extended lambdas of par_for: device-only closures */
 typedef cudaStream_t lbc_stream_t;
 #endif
 

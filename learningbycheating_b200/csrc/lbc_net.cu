@@ -14,7 +14,7 @@ struct k_nhwc_to_nchw;
 template <class T>
 void nhwc_to_nchw_f32(lbc_stream_t s, const T* x, float* out, int N, int H, int W, int C) {
   int64_t n = (int64_t)N * C * H * W;
-  par_for<k_nhwc_to_nchw>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_nhwc_to_nchw>(s, n, [=] LBC_LAMBDA(int64_t i) {
     int w = (int)(i % W);
     int64_t t = i / W;
     int h = (int)(t % H);

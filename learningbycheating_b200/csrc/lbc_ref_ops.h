@@ -31,7 +31,7 @@ template <class T>
 void input_to_nhwc(lbc_stream_t s, const float* img, T* out, int N, int C, int H, int W, int Cpad,
                    bool normalize, float m0, float m1, float m2, float s0, float s1, float s2) {
   int64_t n = (int64_t)N * H * W * Cpad;
-  par_for<k_input_nhwc>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_input_nhwc>(s, n, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % Cpad);
     int64_t p = i / Cpad;
     int w = (int)(p % W);
@@ -58,7 +58,7 @@ template <class T>
 void conv_fwd(lbc_stream_t s, const T* x, const T* w, const float* bias, bool relu, T* y, int N, int H,
               int W, int Ci, int Co, int K, int stride, int pad, int OH, int OW) {
   int64_t n = (int64_t)N * OH * OW * Co;
-  par_for<k_conv_fwd>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_conv_fwd>(s, n, [=] LBC_LAMBDA(int64_t i) {
     int co = (int)(i % Co);
     int64_t p = i / Co;
     int ow = (int)(p % OW);
@@ -98,7 +98,7 @@ template <class T>
 void conv_dgrad(lbc_stream_t s, const T* dy, const T* w, T* dx, int N, int H, int W, int Ci, int Co, int K,
                 int stride, int pad, int OH, int OW, const float* bias_ci, bool relu, bool accumulate) {
   int64_t n = (int64_t)N * H * W * Ci;
-  par_for<k_conv_dgrad>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_conv_dgrad>(s, n, [=] LBC_LAMBDA(int64_t i) {
     int ci = (int)(i % Ci);
     int64_t p = i / Ci;
     int iw = (int)(p % W);
@@ -147,7 +147,7 @@ void conv_wgrad(lbc_stream_t s, const T* x, const T* dy, float* dw_ref, int N, i
   LBC_CHECK(P >= 1, "conv_wgrad workspace too small");
   int64_t rows_per = cdiv(rows, P);
   P = cdiv(rows, rows_per);
-  par_for<k_conv_wgrad_part>(s, P * wsize, [=] LBC_HD(int64_t i) {
+  par_for<k_conv_wgrad_part>(s, P * wsize, [=] LBC_LAMBDA(int64_t i) {
     int ci = (int)(i % Ci);
     int64_t t = i / Ci;
     int kw = (int)(t % K);
@@ -176,7 +176,7 @@ void conv_wgrad(lbc_stream_t s, const T* x, const T* dy, float* dw_ref, int N, i
     }
     ws[i] = (float)acc;
   });
-  par_for<k_reduce_part>(s, wsize, [=] LBC_HD(int64_t i) {
+  par_for<k_reduce_part>(s, wsize, [=] LBC_LAMBDA(int64_t i) {
     double a = 0.0;
     for (int64_t c = 0; c < P; ++c) a += (double)ws[c * wsize + i];
     int ci = (int)(i % Ci);
@@ -193,7 +193,7 @@ void conv_wgrad(lbc_stream_t s, const T* x, const T* dy, float* dw_ref, int N, i
 template <class T>
 void pack_weight(lbc_stream_t s, const float* w_ref, T* w_packed, int Co, int Ci, int K) {
   int64_t n = (int64_t)Co * K * K * Ci;
-  par_for<k_pack_w>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_pack_w>(s, n, [=] LBC_LAMBDA(int64_t i) {
     int ci = (int)(i % Ci);
     int64_t t = i / Ci;
     int kw = (int)(t % K);
@@ -220,7 +220,7 @@ void bn_stats(lbc_stream_t s, const T* x, int64_t M, int C, float* mean, float* 
   P = cdiv(M, per);
   double* part = ws;
   double* dmean = ws + P * C;  // C doubles
-  par_for<k_bn_sum_part>(s, P * C, [=] LBC_HD(int64_t i) {
+  par_for<k_bn_sum_part>(s, P * C, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C);
     int64_t ch = i / C;
     int64_t r0 = ch * per, r1 = r0 + per;
@@ -229,14 +229,14 @@ void bn_stats(lbc_stream_t s, const T* x, int64_t M, int C, float* mean, float* 
     for (int64_t r = r0; r < r1; ++r) a += (double)ldf(x, r * C + c);
     part[i] = a;
   });
-  par_for<k_reduce_part>(s, C, [=] LBC_HD(int64_t c) {
+  par_for<k_reduce_part>(s, C, [=] LBC_LAMBDA(int64_t c) {
     double a = 0.0;
     for (int64_t ch = 0; ch < P; ++ch) a += part[ch * C + c];
     a /= (double)M;
     dmean[c] = a;
     mean[c] = (float)a;
   });
-  par_for<k_bn_var_part>(s, P * C, [=] LBC_HD(int64_t i) {
+  par_for<k_bn_var_part>(s, P * C, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C);
     int64_t ch = i / C;
     int64_t r0 = ch * per, r1 = r0 + per;
@@ -249,7 +249,7 @@ void bn_stats(lbc_stream_t s, const T* x, int64_t M, int C, float* mean, float* 
     }
     part[i] = a;
   });
-  par_for<k_reduce_part>(s, C, [=] LBC_HD(int64_t c) {
+  par_for<k_reduce_part>(s, C, [=] LBC_LAMBDA(int64_t c) {
     double a = 0.0;
     for (int64_t ch = 0; ch < P; ++ch) a += part[ch * C + c];
     var_biased[c] = (float)(a / (double)M);
@@ -259,7 +259,7 @@ void bn_stats(lbc_stream_t s, const T* x, int64_t M, int C, float* mean, float* 
 // rstd = 1/sqrt(var+eps); running stats: rm <- (1-mom) rm + mom*mean ; rv <- (1-mom) rv + mom*var*M/(M-1)
 inline void bn_finalize(lbc_stream_t s, const float* mean, const float* var_biased, int C, int64_t M, float eps,
                         float momentum, float* rstd, float* running_mean, float* running_var) {
-  par_for<k_bn_finalize>(s, C, [=] LBC_HD(int64_t c) {
+  par_for<k_bn_finalize>(s, C, [=] LBC_LAMBDA(int64_t c) {
     float v = var_biased[c];
     rstd[c] = 1.0f / sqrtf(v + eps);
     if (running_mean) {
@@ -272,7 +272,7 @@ inline void bn_finalize(lbc_stream_t s, const float* mean, const float* var_bias
 // eval mode: mean = running_mean, rstd from running_var
 inline void bn_eval_stats(lbc_stream_t s, const float* running_mean, const float* running_var, int C, float eps,
                           float* mean, float* rstd) {
-  par_for<k_bn_finalize>(s, C, [=] LBC_HD(int64_t c) {
+  par_for<k_bn_finalize>(s, C, [=] LBC_LAMBDA(int64_t c) {
     mean[c] = running_mean[c];
     rstd[c] = 1.0f / sqrtf(running_var[c] + eps);
   });
@@ -282,7 +282,7 @@ inline void bn_eval_stats(lbc_stream_t s, const float* running_mean, const float
 template <class T>
 void bn_apply(lbc_stream_t s, const T* x, const float* mean, const float* rstd, const float* gamma,
               const float* beta, const T* residual, bool relu, T* y, int64_t M, int C) {
-  par_for<k_bn_apply>(s, M * C, [=] LBC_HD(int64_t i) {
+  par_for<k_bn_apply>(s, M * C, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C);
     float v = (ldf(x, i) - mean[c]) * rstd[c] * gamma[c] + beta[c];
     if (residual) v += ldf(residual, i);
@@ -301,7 +301,7 @@ void bn_bwd(lbc_stream_t s, const T* dy, const T* x, const float* mean, const fl
   P = cdiv(M, per);
   double* p0 = ws;
   double* p1 = ws + P * C;
-  par_for<k_bn_bwd_part>(s, P * C, [=] LBC_HD(int64_t i) {
+  par_for<k_bn_bwd_part>(s, P * C, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C);
     int64_t ch = i / C;
     int64_t r0 = ch * per, r1 = r0 + per;
@@ -317,7 +317,7 @@ void bn_bwd(lbc_stream_t s, const T* dy, const T* x, const float* mean, const fl
     p0[i] = a;
     p1[i] = b;
   });
-  par_for<k_bn_bwd_final>(s, C, [=] LBC_HD(int64_t c) {
+  par_for<k_bn_bwd_final>(s, C, [=] LBC_LAMBDA(int64_t c) {
     double a = 0.0, b = 0.0;
     for (int64_t ch = 0; ch < P; ++ch) {
       a += p0[ch * C + c];
@@ -328,7 +328,7 @@ void bn_bwd(lbc_stream_t s, const T* dy, const T* x, const float* mean, const fl
   });
   if (dx) {
     float invM = 1.0f / (float)M;
-    par_for<k_bn_bwd_apply>(s, M * C, [=] LBC_HD(int64_t i) {
+    par_for<k_bn_bwd_apply>(s, M * C, [=] LBC_LAMBDA(int64_t i) {
       int c = (int)(i % C);
       float xh = (ldf(x, i) - mean[c]) * rstd[c];
       float v = gamma[c] * rstd[c] * (ldf(dy, i) - dbeta[c] * invM - xh * dgamma[c] * invM);
@@ -342,7 +342,7 @@ void bn_bwd(lbc_stream_t s, const T* dy, const T* x, const float* mean, const fl
 template <class T>
 void maxpool_fwd(lbc_stream_t s, const T* x, T* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW) {
   int64_t n = (int64_t)N * OH * OW * C;
-  par_for<k_maxpool_fwd>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_maxpool_fwd>(s, n, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C);
     int64_t p = i / C;
     int ow = (int)(p % OW);
@@ -372,7 +372,7 @@ template <class T>
 void maxpool_bwd(lbc_stream_t s, const T* dy, const uint8_t* idx, T* dx, int N, int H, int W, int C, int OH,
                  int OW) {
   int64_t n = (int64_t)N * H * W * C;
-  par_for<k_maxpool_bwd>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_maxpool_bwd>(s, n, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C);
     int64_t p = i / C;
     int iw = (int)(p % W);
@@ -402,18 +402,18 @@ void maxpool_bwd(lbc_stream_t s, const T* dy, const uint8_t* idx, T* dx, int N, 
 // elementwise helpers
 template <class T>
 void relu_mask_inplace(lbc_stream_t s, T* g, const T* act, int64_t n) {  // g *= (act > 0)   nn.ReLU(True) bwd
-  par_for<k_relu_mask>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_relu_mask>(s, n, [=] LBC_LAMBDA(int64_t i) {
     if (!(ldf(act, i) > 0.f)) stf(g, i, 0.f);
   });
 }
 template <class T>
 void add_inplace(lbc_stream_t s, T* dst, const T* src, int64_t n) {
-  par_for<k_add>(s, n, [=] LBC_HD(int64_t i) { stf(dst, i, ldf(dst, i) + ldf(src, i)); });
+  par_for<k_add>(s, n, [=] LBC_LAMBDA(int64_t i) { stf(dst, i, ldf(dst, i) + ldf(src, i)); });
 }
 // dst += g * (act > 0)
 template <class T>
 void add_masked_inplace(lbc_stream_t s, T* dst, const T* g, const T* act, int64_t n) {
-  par_for<k_add>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_add>(s, n, [=] LBC_LAMBDA(int64_t i) {
     if (ldf(act, i) > 0.f) stf(dst, i, ldf(dst, i) + ldf(g, i));
   });
 }
@@ -422,7 +422,7 @@ template <class T>
 void concat_speed(lbc_stream_t s, const T* trunk, const float* speed, T* out, int N, int HW, int Ct, int Cs) {
   int C = Ct + Cs;
   int64_t n = (int64_t)N * HW * C;
-  par_for<k_concat_speed>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_concat_speed>(s, n, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C);
     int64_t m = i / C;
     float v = c < Ct ? ldf(trunk, m * Ct + c) : speed[m / HW];
@@ -431,7 +431,7 @@ void concat_speed(lbc_stream_t s, const T* trunk, const float* speed, T* out, in
 }
 template <class T>
 void slice_channels(lbc_stream_t s, const T* src, T* dst, int64_t M, int Csrc, int Cdst) {
-  par_for<k_slice>(s, M * Cdst, [=] LBC_HD(int64_t i) {
+  par_for<k_slice>(s, M * Cdst, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % Cdst);
     int64_t m = i / Cdst;
     stf(dst, i, ldf(src, m * Csrc + c));
@@ -443,7 +443,7 @@ void colsum(lbc_stream_t s, const T* dy, int64_t M, int C, float* out, double* w
   int64_t P = bn_chunks(M, C);
   int64_t per = cdiv(M, P);
   P = cdiv(M, per);
-  par_for<k_colsum_part>(s, P * C, [=] LBC_HD(int64_t i) {
+  par_for<k_colsum_part>(s, P * C, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C);
     int64_t ch = i / C;
     int64_t r0 = ch * per, r1 = r0 + per;
@@ -452,7 +452,7 @@ void colsum(lbc_stream_t s, const T* dy, int64_t M, int C, float* out, double* w
     for (int64_t r = r0; r < r1; ++r) a += (double)ldf(dy, r * C + c);
     ws[i] = a;
   });
-  par_for<k_reduce_part>(s, C, [=] LBC_HD(int64_t c) {
+  par_for<k_reduce_part>(s, C, [=] LBC_LAMBDA(int64_t c) {
     double a = 0.0;
     for (int64_t ch = 0; ch < P; ++ch) a += ws[ch * C + c];
     out[c] = (float)a;
@@ -475,7 +475,7 @@ template <class T>
 void head_logits(lbc_stream_t s, const T* h, HeadParams hp, float* logits, int N, int HW, int C) {
   // logits layout [N][20][HW]
   int64_t n = (int64_t)N * 20 * HW;
-  par_for<k_head_logits>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_head_logits>(s, n, [=] LBC_LAMBDA(int64_t i) {
     int pix = (int)(i % HW);
     int64_t t = i / HW;
     int kj = (int)(t % 20);
@@ -499,7 +499,7 @@ void head_logits(lbc_stream_t s, const T* h, HeadParams hp, float* logits, int N
 inline void head_softmax(lbc_stream_t s, const float* logits, float* rowmax, float* rowsum, float* preds, int N,
                          int H, int W) {
   int HW = H * W;
-  par_for<k_head_softmax>(s, (int64_t)N * 20, [=] LBC_HD(int64_t r) {
+  par_for<k_head_softmax>(s, (int64_t)N * 20, [=] LBC_LAMBDA(int64_t r) {
     const float* l = logits + r * HW;
     float m = -INFINITY;
     for (int p = 0; p < HW; ++p) m = l[p] > m ? l[p] : m;
@@ -521,7 +521,7 @@ inline void head_softmax(lbc_stream_t s, const float* logits, float* rowmax, flo
 }
 // select_branch (common.py:29-35): pred[n,j,:] = sum_k onehot[n,k]*preds[n,k,j,:]
 inline void head_select(lbc_stream_t s, const float* preds, const float* onehot, float* pred, int N) {
-  par_for<k_head_select>(s, (int64_t)N * 10, [=] LBC_HD(int64_t i) {
+  par_for<k_head_select>(s, (int64_t)N * 10, [=] LBC_LAMBDA(int64_t i) {
     int e = (int)(i % 10);
     int b = (int)(i / 10);
     float a = 0.f;
@@ -534,7 +534,7 @@ inline void head_dlogits(lbc_stream_t s, const float* logits, const float* rowma
                          const float* preds, const float* onehot, const float* d_pred, const float* d_preds,
                          float* dlogits, int N, int H, int W) {
   int HW = H * W;
-  par_for<k_head_dlogits>(s, (int64_t)N * 20 * HW, [=] LBC_HD(int64_t i) {
+  par_for<k_head_dlogits>(s, (int64_t)N * 20 * HW, [=] LBC_LAMBDA(int64_t i) {
     int p = (int)(i % HW);
     int64_t r = i / HW;
     int kj = (int)(r % 20);
@@ -563,7 +563,7 @@ void head_s(lbc_stream_t s, const float* dlogits, const T* h, const float* mean,
             int N, int HW, int C, double* ws) {
   int C1 = C + 1;
   int64_t P = N;  // one chunk per image
-  par_for<k_head_s_part>(s, P * 20 * C1, [=] LBC_HD(int64_t i) {
+  par_for<k_head_s_part>(s, P * 20 * C1, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C1);
     int64_t t = i / C1;
     int kj = (int)(t % 20);
@@ -578,7 +578,7 @@ void head_s(lbc_stream_t s, const float* dlogits, const T* h, const float* mean,
     }
     ws[i] = a;
   });
-  par_for<k_reduce_part>(s, 20 * C1, [=] LBC_HD(int64_t i) {
+  par_for<k_reduce_part>(s, 20 * C1, [=] LBC_LAMBDA(int64_t i) {
     double a = 0.0;
     for (int64_t b = 0; b < P; ++b) a += ws[b * 20 * C1 + i];
     S[i] = a;
@@ -593,7 +593,7 @@ struct HeadGrads {
 // dW_k[j,c] = gamma_kc S1 + beta_kc S0 ; dbias = S0 ; dgamma_kc = sum_j W S1 ; dbeta_kc = sum_j W S0
 inline void head_param_grads(lbc_stream_t s, const double* S, HeadParams hp, HeadGrads hg, int C) {
   int C1 = C + 1;
-  par_for<k_head_param_grads>(s, 4 * C1, [=] LBC_HD(int64_t i) {
+  par_for<k_head_param_grads>(s, 4 * C1, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C1);
     int k = (int)(i / C1);
     if (c == C) {
@@ -617,7 +617,7 @@ template <class T>
 void head_dh(lbc_stream_t s, const float* dlogits, const T* h, const float* mean, const float* rstd, HeadParams hp,
              HeadGrads hg, T* dh, int N, int HW, int C) {
   float invM = 1.0f / (float)((int64_t)N * HW);
-  par_for<k_head_dh>(s, (int64_t)N * HW * C, [=] LBC_HD(int64_t i) {
+  par_for<k_head_dh>(s, (int64_t)N * HW * C, [=] LBC_LAMBDA(int64_t i) {
     int c = (int)(i % C);
     int64_t m = i / C;
     int p = (int)(m % HW);
@@ -640,7 +640,7 @@ void head_dh(lbc_stream_t s, const float* dlogits, const T* h, const float* mean
 inline void phase0_target(lbc_stream_t s, const float* t_pred, float* target_px, int64_t count, float w, float h,
                           float fov_deg, float world_y, float fixed_offset) {
   double f = (double)w / (2.0 * tan((double)fov_deg * 3.14159265358979323846 / 360.0));
-  par_for<k_phase0_target>(s, count, [=] LBC_HD(int64_t i) {
+  par_for<k_phase0_target>(s, count, [=] LBC_LAMBDA(int64_t i) {
     const float CROP = 192.f, PPM = 5.f;
     float tx = (t_pred[i * 2] + 1.f) * CROP / 2.f;
     float ty = (t_pred[i * 2 + 1] + 1.f) * CROP / 2.f;
@@ -662,7 +662,7 @@ inline void phase0_target(lbc_stream_t s, const float* t_pred, float* target_px,
 // covers train_image_phase0.py:86-89, train_image_phase1.py:66-70, train_birdview.py:33-54 (l1)
 inline void l1_loss(lbc_stream_t s, const float* a, const float* b, int N, int D, float sa, float ta, float sbx,
                     float sby, float tb, const float* gout, float* loss_b, float* da) {
-  par_for<k_l1_loss>(s, N, [=] LBC_HD(int64_t n) {
+  par_for<k_l1_loss>(s, N, [=] LBC_LAMBDA(int64_t n) {
     double acc = 0.0;
     float go = gout ? gout[n] : 1.0f / (float)N;
     for (int d = 0; d < D; ++d) {
@@ -682,7 +682,7 @@ inline float focal_px(float w, float fov_deg) {
 inline void phase1_convert_fwd(lbc_stream_t s, const float* p, float* out, int64_t count, float w, float h,
                                float fov_deg, float world_y, float fixed_offset) {
   float f = focal_px(w, fov_deg);
-  par_for<k_phase1_fwd>(s, count, [=] LBC_HD(int64_t i) {
+  par_for<k_phase1_fwd>(s, count, [=] LBC_LAMBDA(int64_t i) {
     const float CROP = 192.f, PPM = 5.f;
     float cx = (p[i * 2] + 1.f) * w / 2.f, cy = (p[i * 2 + 1] + 1.f) * h / 2.f;
     float xt = (cx - w / 2.f) / f, yt = (cy - h / 2.f) / f;
@@ -694,7 +694,7 @@ inline void phase1_convert_fwd(lbc_stream_t s, const float* p, float* out, int64
 inline void phase1_convert_bwd(lbc_stream_t s, const float* p, const float* dout, float* dp, int64_t count, float w,
                                float h, float fov_deg, float world_y, float fixed_offset) {
   float f = focal_px(w, fov_deg);
-  par_for<k_phase1_bwd>(s, count, [=] LBC_HD(int64_t i) {
+  par_for<k_phase1_bwd>(s, count, [=] LBC_LAMBDA(int64_t i) {
     const float PPM = 5.f;
     float cx = (p[i * 2] + 1.f) * w / 2.f, cy = (p[i * 2 + 1] + 1.f) * h / 2.f;
     float xt = (cx - w / 2.f) / f, yt = (cy - h / 2.f) / f;
@@ -717,7 +717,7 @@ inline void adam(lbc_stream_t s, float* p, const float* g, float* m, float* v, i
   double bc2 = 1.0 - pow((double)b2, (double)step);
   float step_size = (float)((double)lr / bc1);
   float bc2_sqrt = (float)sqrt(bc2);
-  par_for<k_adam>(s, n, [=] LBC_HD(int64_t i) {
+  par_for<k_adam>(s, n, [=] LBC_LAMBDA(int64_t i) {
     float gi = g[i] * grad_scale;
     float mi = m[i] + (1.f - b1) * (gi - m[i]);
     float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -730,7 +730,7 @@ inline void adam(lbc_stream_t s, float* p, const float* g, float* m, float* v, i
 
 template <class TS, class TD>
 void cast(lbc_stream_t s, const TS* src, TD* dst, int64_t n) {
-  par_for<k_cast>(s, n, [=] LBC_HD(int64_t i) { stf(dst, i, ldf(src, i)); });
+  par_for<k_cast>(s, n, [=] LBC_LAMBDA(int64_t i) { stf(dst, i, ldf(src, i)); });
 }
 
 }  // namespace ref
