@@ -293,9 +293,14 @@ int lbc_op_conv_dgrad(const float* dy, const float* w_ref, float* dx, int N, int
       ref::conv_dgrad<float>(s, dy, wp, dx, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, nullptr, false, false);
     } else {
       bf16 *xb = t.get<bf16>(nx), *wb = t.get<bf16>(nw), *yb = t.get<bf16>(ny);
+      bf16* wtb = t.get<bf16>(nw);
       ref::cast<float, bf16>(s, dy, yb, ny);
       ref::pack_weight<bf16>(s, w_ref, wb, Co, Ci, K);
-      ref::conv_dgrad<bf16>(s, yb, wb, xb, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, nullptr, false, false);
+      ref::pack_weight_t<bf16>(s, w_ref, wtb, Co, Ci, K);
+      c.wp = wb;
+      c.wpt = wtb;
+      if (!fast::conv_dgrad<bf16>(c, yb, xb, N, nullptr, false, s))
+        ref::conv_dgrad<bf16>(s, yb, wb, xb, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, nullptr, false, false);
       ref::cast<bf16, float>(s, xb, dx, nx);
     }
     sync_stream(s);

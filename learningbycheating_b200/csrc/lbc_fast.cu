@@ -11,11 +11,6 @@ static bool g_enabled = true;
 bool enabled() { return g_enabled; }
 void set_enabled(bool on) { g_enabled = on; }
 
-#ifdef LBC_HOST_EMU
-bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, lbc_stream_t) { return false; }
-#else
-bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, lbc_stream_t) { return false; }
-#endif
 
 }  // namespace fast
 }  // namespace lbc

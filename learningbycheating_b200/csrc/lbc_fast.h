@@ -26,5 +26,19 @@ inline bool conv_fwd<bf16>(const ConvL& c, const bf16* x, bf16* y, int B, lbc_st
   return conv_fwd_bf16(c, x, y, B, s);
 }
 
+bool conv_dgrad_bf16(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu, lbc_stream_t s);
+
+template <class T>
+inline bool conv_dgrad(const ConvL& c, const T* dy, T* dx, int B, const float* bias_ci, bool relu, lbc_stream_t s) {
+  (void)c; (void)dy; (void)dx; (void)B; (void)bias_ci; (void)relu; (void)s;
+  return false;
+}
+template <>
+inline bool conv_dgrad<bf16>(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu,
+                             lbc_stream_t s) {
+  if (!enabled()) return false;
+  return conv_dgrad_bf16(c, dy, dx, B, bias_ci, relu, s);
+}
+
 }  // namespace fast
 }  // namespace lbc

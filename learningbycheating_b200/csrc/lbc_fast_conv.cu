@@ -1,0 +1,564 @@
+// lbc_fast_conv.cu -- im2col-free implicit-GEMM convolutions on the sm_100a tensor cores.
+//
+//   D[128 output positions x BN channels] (fp32, TMEM) += A[128 x 64] (bf16, smem) * B[BN x 64]^T (bf16, smem)
+//
+// * A tile = a 4-D TMA box {64 ch, TW, TH, TN} of the NHWC activation at the tap's spatial offset: the
+//   hardware zero-fills out-of-bounds coordinates, which IS the convolution padding (and the batch tail).
+//   The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle == the UMMA K-major
+//   SWIZZLE_128B canonical layout, so no im2col buffer ever exists.
+// * Stride-2 convolutions read the four (row, column) parity sub-views of the input (tensor maps with doubled
+//   strides), so every TMA load is unit-stride; the data gradient of a stride-2 convolution (== the forward of
+//   nn.ConvTranspose2d(3,2,1,1), image.py:39-46) is four such GEMMs writing the four parity sub-views of dx.
+// * One persistent CTA per SM, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one
+//   elected lane) + TMEM owner, warps 2-5 = epilogue (tcgen05.ld -> bias/ReLU -> bf16 -> swizzled smem -> TMA
+//   store).  smem ring of STAGES {A,B} tiles, two TMEM accumulators so the epilogue of tile i overlaps the MMAs
+//   of tile i+1.
+//
+// Reference ops replaced: every nn.Conv2d of resnet.BasicBlock (resnet.py:15-22,38-54), its input gradient, and
+// the decoder's ConvTranspose2d (image.py:39-46).
+#ifndef LBC_HOST_EMU
+#include <cuda.h>
+#include <cuda_bf16.h>
+#endif
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "lbc_fast.h"
+
+namespace lbc {
+namespace fast {
+
+#ifndef LBC_HOST_EMU
+
+// ------------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled encode_fn() {
+  static PFN_encodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) throw Error("cuTensorMapEncodeTiled unavailable");
+    return (PFN_encodeTiled)p;
+  }();
+  return fn;
+}
+
+// bf16 tensor [N][H][W][C] with arbitrary (16 B aligned) strides; box {64, bw, bh, bn}, 128 B swizzle, zero OOB fill
+static CUtensorMap make_map_4d(const void* base, int C, int W, int H, int N, int64_t sW, int64_t sH, int64_t sN, int bw,
+                               int bh, int bn) {
+  typedef std::tuple<const void*, int, int, int, int, int64_t, int64_t, int64_t, int, int, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key(base, C, W, H, N, sW, sH, sN, bw, bh, bn);
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sW, (cuuint64_t)sH, (cuuint64_t)sN};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LBC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed: " + std::to_string((int)r));
+  cache[key] = m;
+  return m;
+}
+// bf16 matrix [rows][K] (K contiguous); box {64, brows}
+static CUtensorMap make_map_2d(const void* base, int64_t K, int64_t rows, int brows) {
+  typedef std::tuple<const void*, int64_t, int64_t, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key(base, K, rows, brows);
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(K * 2)};
+  cuuint32_t box[2] = {64, (cuuint32_t)brows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LBC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: " + std::to_string((int)r));
+  cache[key] = m;
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------- device helpers
+struct ConvGemmParams {
+  int TW, TH, TN;                   // output-position tile = TN*TH*TW = 128
+  int tiles_w, tiles_h, tiles_n;    // tiles per dimension
+  int n_tiles_n;                    // N (channel) tiles
+  int num_taps, k_chunks;           // K loop = num_taps * k_chunks iterations of 64
+  int tap_dh[9], tap_dw[9], tap_map[9], tap_koff[9];
+  const float* bias;                // per output channel or null
+  int relu;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin == 64) t0 = clock64();
+    if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) {
+      printf("lbc conv_gemm: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, void* dst, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int A_BYTES = 128 * 128;  // 128 positions x 64 bf16
+
+template <int BN, int STAGES>
+struct SmemPlan {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
+};
+
+// ------------------------------------------------------------------------------------------- the kernel
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
+                 const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
+                 const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mO, const ConvGemmParams p) {
+  typedef SmemPlan<BN, STAGES> SP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* out_stage = smem + STAGES * SP::STAGE_BYTES;
+  uint64_t* full = (uint64_t*)(smem + SP::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int num_tiles = tiles_m * p.n_tiles_n;
+  const int k_iters = p.num_taps * p.k_chunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles_n;
+        const int m_tile = tile / p.n_tiles_n;
+        const int w0 = (m_tile % p.tiles_w) * p.TW;
+        const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int mid = p.tap_map[tap];
+          const CUtensorMap* ma = mid == 0 ? &mA0 : (mid == 1 ? &mA1 : (mid == 2 ? &mA2 : &mA3));
+          const int dh = p.tap_dh[tap], dw = p.tap_dw[tap], koff = p.tap_koff[tap];
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * SP::STAGE_BYTES;
+            mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
+            tma_load_4d(ma, sa, &full[stage], kc * 64, w0 + dw, h0 + dh, n0);
+            tma_load_2d(&mB, sa + A_BYTES, &full[stage], koff + kc * 64, n_tile * BN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * SP::STAGE_BYTES);
+          const uint64_t ad = umma_desc_k_sw128(sa);
+          const uint64_t bd = umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)  // 4 x (K=16) per 64-wide chunk: advance 32 B inside the swizzle atom
+            umma_bf16(tmem_d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+          umma_commit(&empty[stage]);                    // frees the smem slot when these MMAs retire
+          if (k == k_iters - 1) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 64);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int n_tile = tile % p.n_tiles_n;
+      const int m_tile = tile / p.n_tiles_n;
+      const int w0 = (m_tile % p.tiles_w) * p.TW;
+      const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.TH;
+      const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
+      mbar_wait(&tfull[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging buffer free again
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        const int col0 = n_tile * BN + ch * 32;
+        uint8_t* rowp = out_stage + (ch >> 1) * A_BYTES + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = __uint_as_float(r[j * 8 + e * 2]);
+            float b = __uint_as_float(r[j * 8 + e * 2 + 1]);
+            if (p.bias) {
+              a += __ldg(p.bias + col0 + j * 8 + e * 2);
+              b += __ldg(p.bias + col0 + j * 8 + e * 2 + 1);
+            }
+            if (p.relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const int chunk16 = (ch & 1) * 4 + j;  // 16-byte chunk index inside the 128-byte row
+          *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tempty[acc]);  // accumulator drained: the MMA warp may reuse it
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b) tma_store_4d(&mO, out_stage + b * A_BYTES, n_tile * BN + b * 64, w0, h0, n0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+static int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+static int pow2_divisor(int x, int cap) {
+  int p = 1;
+  while (p * 2 <= cap && x % (p * 2) == 0) p *= 2;
+  return p;
+}
+// 128-position tile {TW, TH, TN} for an (OH x OW) output plane; false when the plane has no power-of-two factors
+static bool tile_geometry(int OH, int OW, int B, ConvGemmParams& p) {
+  int TW = pow2_divisor(OW, 32);
+  int TH = pow2_divisor(OH, 128 / TW);
+  int TN = 128 / (TW * TH);
+  p.TW = TW;
+  p.TH = TH;
+  p.TN = TN;
+  p.tiles_w = OW / TW;
+  p.tiles_h = OH / TH;
+  p.tiles_n = (B + TN - 1) / TN;
+  return TN <= 256;
+}
+
+template <int BN, int STAGES>
+static void launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUtensorMap& mO, const ConvGemmParams& p,
+                        lbc_stream_t s) {
+  typedef SmemPlan<BN, STAGES> SP;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    configured = true;
+  }
+  int tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  conv_gemm_kernel<BN, STAGES><<<grid, 192, SP::TOTAL, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO, p);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+}
+static void dispatch_gemm(int BN, const CUtensorMap* mA, const CUtensorMap& mB, const CUtensorMap& mO,
+                          const ConvGemmParams& p, lbc_stream_t s) {
+  if (BN == 64)
+    launch_gemm<64, 6>(mA, mB, mO, p, s);
+  else if (BN == 128)
+    launch_gemm<128, 5>(mA, mB, mO, p, s);
+  else
+    launch_gemm<256, 3>(mA, mB, mO, p, s);
+}
+static int pick_bn(int C) { return C == 64 ? 64 : (C % 256 == 0 ? 256 : 128); }
+
+static bool supported(const ConvL& c) {
+  if (c.Ci % 64 || c.Co % 64) return false;
+  if (!((c.K == 3 && c.pad == 1) || (c.K == 1 && c.pad == 0))) return false;
+  if (c.stride == 2) return (c.H % 2 == 0) && (c.W % 2 == 0) && c.OH * 2 == c.H && c.OW * 2 == c.W;
+  return c.stride == 1 && c.OH == c.H && c.OW == c.W;
+}
+
+// y = conv(x, w):  x [B,H,W,Ci], packed weights [Co][K*K][Ci], y [B,OH,OW,Co]
+bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s) {
+  if (!supported(c)) return false;
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  if (!tile_geometry(c.OH, c.OW, B, p)) return false;
+  const int BN = pick_bn(c.Co);
+  p.n_tiles_n = c.Co / BN;
+  p.num_taps = c.K * c.K;
+  p.k_chunks = c.Ci / 64;
+  CUtensorMap mA[4];
+  const int64_t eb = 2;
+  if (c.stride == 1) {
+    mA[0] = make_map_4d(x, c.Ci, c.W, c.H, B, c.Ci * eb, (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH,
+                        p.TN);
+    mA[1] = mA[2] = mA[3] = mA[0];
+    for (int kh = 0; kh < c.K; ++kh)
+      for (int kw = 0; kw < c.K; ++kw) {
+        int t = kh * c.K + kw;
+        p.tap_dh[t] = kh - c.pad;
+        p.tap_dw[t] = kw - c.pad;
+        p.tap_map[t] = 0;
+        p.tap_koff[t] = t * c.Ci;
+      }
+  } else {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        mA[a * 2 + b] = make_map_4d(x + ((int64_t)a * c.W + b) * c.Ci, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb,
+                                    2 * (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
+    for (int kh = 0; kh < c.K; ++kh)
+      for (int kw = 0; kw < c.K; ++kw) {
+        int t = kh * c.K + kw;
+        int th = kh - c.pad, tw = kw - c.pad;  // input row = 2*oh + th
+        int a = ((th % 2) + 2) % 2, b = ((tw % 2) + 2) % 2;
+        p.tap_dh[t] = (th - a) / 2;
+        p.tap_dw[t] = (tw - b) / 2;
+        p.tap_map[t] = a * 2 + b;
+        p.tap_koff[t] = t * c.Ci;
+      }
+  }
+  CUtensorMap mB = make_map_2d(c.wp, (int64_t)c.K * c.K * c.Ci, c.Co, BN);
+  CUtensorMap mO = make_map_4d(y, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb, (int64_t)c.OH * c.OW * c.Co * eb,
+                               p.TW, p.TH, p.TN);
+  dispatch_gemm(BN, mA, mB, mO, p, s);
+  return true;
+}
+
+// dx = conv_dgrad(dy, w):  dy [B,OH,OW,Co], transposed pack wt [Ci][K*K][Co], dx [B,H,W,Ci] (+bias[ci]) (relu)
+// stride 1: one GEMM with mirrored taps; stride 2: one GEMM per output parity (also ConvTranspose2d forward).
+bool conv_dgrad_bf16(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu, lbc_stream_t s) {
+  if (!supported(c) || !c.wpt) return false;
+  if (c.K == 1) return false;  // 1x1/s2 downsample gradient scatters into one parity only: handled by the caller
+  const int64_t eb = 2;
+  const int BN = pick_bn(c.Ci);
+  CUtensorMap mB = make_map_2d(c.wpt, (int64_t)c.K * c.K * c.Co, c.Ci, BN);
+  if (c.stride == 1) {
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    if (!tile_geometry(c.H, c.W, B, p)) return false;
+    p.n_tiles_n = c.Ci / BN;
+    p.num_taps = c.K * c.K;
+    p.k_chunks = c.Co / 64;
+    p.bias = bias_ci;
+    p.relu = relu ? 1 : 0;
+    CUtensorMap mA[4];
+    mA[0] = make_map_4d(dy, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb, (int64_t)c.OH * c.OW * c.Co * eb, p.TW,
+                        p.TH, p.TN);
+    mA[1] = mA[2] = mA[3] = mA[0];
+    for (int kh = 0; kh < c.K; ++kh)
+      for (int kw = 0; kw < c.K; ++kw) {
+        int t = kh * c.K + kw;
+        p.tap_dh[t] = c.pad - kh;
+        p.tap_dw[t] = c.pad - kw;
+        p.tap_map[t] = 0;
+        p.tap_koff[t] = t * c.Co;
+      }
+    CUtensorMap mO = make_map_4d(dx, c.Ci, c.W, c.H, B, c.Ci * eb, (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb,
+                                 p.TW, p.TH, p.TN);
+    dispatch_gemm(BN, mA, mB, mO, p, s);
+    return true;
+  }
+  // stride 2: dx[n, 2i+a, 2j+b, :] = sum over taps kh with (a + pad - kh) even: dy[n, i + (a+pad-kh)/2, ...]
+  ConvGemmParams base;
+  memset(&base, 0, sizeof(base));
+  if (!tile_geometry(c.OH, c.OW, B, base)) return false;
+  base.n_tiles_n = c.Ci / BN;
+  base.k_chunks = c.Co / 64;
+  base.bias = bias_ci;
+  base.relu = relu ? 1 : 0;
+  CUtensorMap mA[4];
+  mA[0] = make_map_4d(dy, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb, (int64_t)c.OH * c.OW * c.Co * eb, base.TW,
+                      base.TH, base.TN);
+  mA[1] = mA[2] = mA[3] = mA[0];
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      ConvGemmParams p = base;
+      int nt = 0;
+      for (int kh = 0; kh < c.K; ++kh) {
+        if ((a + c.pad - kh) % 2 != 0) continue;
+        for (int kw = 0; kw < c.K; ++kw) {
+          if ((b + c.pad - kw) % 2 != 0) continue;
+          p.tap_dh[nt] = (a + c.pad - kh) / 2;
+          p.tap_dw[nt] = (b + c.pad - kw) / 2;
+          p.tap_map[nt] = 0;
+          p.tap_koff[nt] = (kh * c.K + kw) * c.Co;
+          ++nt;
+        }
+      }
+      p.num_taps = nt;
+      CUtensorMap mO = make_map_4d(dx + ((int64_t)a * c.W + b) * c.Ci, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb,
+                                   2 * (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
+      dispatch_gemm(BN, mA, mB, mO, p, s);
+    }
+  return true;
+}
+
+#else   // LBC_HOST_EMU: no tensor cores on the host; the executor runs the correctness-first kernels
+bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, lbc_stream_t) { return false; }
+bool conv_dgrad_bf16(const ConvL&, const bf16*, bf16*, int, const float*, bool, lbc_stream_t) { return false; }
+#endif
+
+}  // namespace fast
+}  // namespace lbc

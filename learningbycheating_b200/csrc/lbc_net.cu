@@ -122,6 +122,7 @@ class Net : public NetBase {
     c.OW = (W + 2 * pad - K) / stride + 1;
     c.w_off = add_param(name + ".weight", {Co, Ci, K, K});
     c.wp = alloc<T>((int64_t)Co * K * K * Ci);
+    c.wpt = alloc<T>((int64_t)Co * K * K * Ci);
   }
   // nn.ConvTranspose2d(Cin, Cout, 3, 2, 1, 1): as the input-gradient of a 3x3/s2/p1 conv whose
   // conv-role Co = deconv Cin, Ci = deconv Cout; conv-role input is the (2h x 2w) deconv output.
@@ -139,6 +140,7 @@ class Net : public NetBase {
     c.w_off = add_param(name + ".weight", {Cin, Cout, 3, 3});
     c.b_off = add_param(name + ".bias", {Cout});
     c.wp = alloc<T>((int64_t)Cin * 9 * Cout);
+    c.wpt = alloc<T>((int64_t)Cin * 9 * Cout);
   }
 
   Net(NetKind k, Precision p, int maxB) {
@@ -260,7 +262,11 @@ class Net : public NetBase {
 
   // ------------------------------------------------------------------ op wrappers (fast-path hooks)
   void pack_weights(lbc_stream_t s) {
-    auto pk = [&](ConvL& c) { ref::pack_weight<T>(s, P + c.w_off, (T*)c.wp, c.Co, c.Ci, c.K); };
+    ProfScope ps("pack", s, 0, 0);
+    auto pk = [&](ConvL& c) {
+      ref::pack_weight<T>(s, P + c.w_off, (T*)c.wp, c.Co, c.Ci, c.K);
+      if (std::is_same<T, bf16>::value && &c != &stem) ref::pack_weight_t<T>(s, P + c.w_off, (T*)c.wpt, c.Co, c.Ci, c.K);
+    };
     pk(stem);
     for (Block& b : blocks) {
       pk(b.c1);
@@ -280,6 +286,7 @@ class Net : public NetBase {
   }
   void conv_backward_data(const ConvL& c, const T* dy, T* dx, int B, bool accumulate, lbc_stream_t s) {
     ProfScope ps("conv_dgrad", s, conv_flops(c, B), 0);
+    if (!accumulate && fast::conv_dgrad<T>(c, dy, dx, B, nullptr, false, s)) return;
     ref::conv_dgrad<T>(s, dy, (const T*)c.wp, dx, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, nullptr,
                        false, accumulate);
   }
@@ -357,8 +364,9 @@ class Net : public NetBase {
       bn_forward(dbn[i], dec_in[i], (int64_t)B * h * w, nullptr, false, dec_bn[i], train, s);
       const ConvL& c = dcv[i];
       ProfScope ps("conv_dgrad", s, conv_flops(c, B), 0);
-      ref::conv_dgrad<T>(s, dec_bn[i], (const T*)c.wp, dec_out[i], B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
-                         c.OW, P + c.b_off, true, false);
+      if (!fast::conv_dgrad<T>(c, dec_bn[i], dec_out[i], B, P + c.b_off, true, s))
+        ref::conv_dgrad<T>(s, dec_bn[i], (const T*)c.wp, dec_out[i], B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
+                           c.OW, P + c.b_off, true, false);
       h *= 2;
       w *= 2;
     }
@@ -414,11 +422,7 @@ class Net : public NetBase {
       ref::relu_mask_inplace<T>(s, gcur, dec_out[i], Mout * c.Ci);
       ref::colsum<T>(s, gcur, Mout, c.Ci, G + c.b_off, ws_d);
       conv_backward_weight(c, gcur, dec_bn[i], B, s);  // conv-role x = d(out), dy = deconv input
-      {
-        ProfScope ps("conv_fwd", s, conv_flops(c, B), 0);
-        ref::conv_fwd<T>(s, gcur, (const T*)c.wp, nullptr, false, tA, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad,
-                         c.OH, c.OW);
-      }
+      conv_forward(c, gcur, tA, B, s);
       bn_backward(dbn[i], tA, dec_in[i], gnext, Min, s);
       std::swap(gcur, gnext);
     }

@@ -36,7 +36,8 @@ struct ConvL {
   int H = 0, W = 0, OH = 0, OW = 0;                // conv-role input / output spatial size
   int64_t w_off = -1, b_off = -1;
   bool deconv = false;
-  void* wp = nullptr;  // packed [Co][K][K][Ci]
+  void* wp = nullptr;   // packed [Co][K][K][Ci]  (GEMM B operand of the forward conv)
+  void* wpt = nullptr;  // packed [Ci][K][K][Co]  (GEMM B operand of the data gradient / deconv forward)
 };
 struct BNL {
   int C = 0;

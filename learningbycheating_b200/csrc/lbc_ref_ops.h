@@ -204,6 +204,21 @@ void pack_weight(lbc_stream_t s, const float* w_ref, T* w_packed, int Co, int Ci
   });
 }
 
+// reference layout [Co][Ci][K][K] fp32 -> transposed pack [Ci][K][K][Co] T
+template <class T>
+void pack_weight_t(lbc_stream_t s, const float* w_ref, T* w_packed, int Co, int Ci, int K) {
+  int64_t n = (int64_t)Co * K * K * Ci;
+  par_for<k_pack_w>(s, n, [=] LBC_LAMBDA(int64_t i) {
+    int co = (int)(i % Co);
+    int64_t t = i / Co;
+    int kw = (int)(t % K);
+    t /= K;
+    int kh = (int)(t % K);
+    int ci = (int)(t / K);
+    stf(w_packed, i, w_ref[(((int64_t)co * Ci + ci) * K + kh) * K + kw]);
+  });
+}
+
 // ---------------------------------------------------------------------------------------------
 // BatchNorm2d, train mode (torch BN as constructed at resnet.py:104, image.py:38,56)
 // column statistics over M rows of C channels.  ws: >= 2*P*C doubles.

@@ -38,9 +38,13 @@ def _conv_case(dev, case, precision, tol):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(N, Ci, H, W, generator=g)
     w = torch.randn(Co, Ci, K, K, generator=g) / (Ci * K * K) ** 0.5
+    if precision == 1:      # bf16 path: compare on bf16-representable operands (isolates indexing from rounding)
+        x, w = x.bfloat16().float(), w.bfloat16().float()
     y_ref = F.conv2d(x, w, None, s, p)
     OH, OW = y_ref.shape[2:]
     dy = torch.randn(N, Co, OH, OW, generator=g)
+    if precision == 1:
+        dy = dy.bfloat16().float()
     dx_ref = torch.nn.grad.conv2d_input(x.shape, w, dy, s, p)
     dw_ref = torch.nn.grad.conv2d_weight(x, w.shape, dy, s, p)
     L = _lib.lib()
@@ -177,6 +181,33 @@ def test_conv_ops_gpu_fp32(backend, case):
 def test_conv_ops_gpu_bf16(backend, case):
     assert backend == "cuda"
     _conv_case("cuda", case, 1, 3e-2)
+
+
+# the real layer shapes of the path (tcgen05 implicit-GEMM kernels): (N,H,W,Ci,Co,K,stride,pad)
+FAST_CASES = [
+    (3, 40, 96, 64, 64, 3, 1, 1),      # layer1 3x3
+    (3, 40, 96, 64, 128, 3, 2, 1),     # layer2.0.conv1 3x3/s2
+    (3, 40, 96, 64, 128, 1, 2, 0),     # layer2.0.downsample 1x1/s2
+    (3, 20, 48, 128, 128, 3, 1, 1),    # layer2
+    (9, 10, 24, 256, 256, 3, 1, 1),    # layer3 (TN=8 -> batch tail tile)
+    (33, 5, 12, 512, 512, 3, 1, 1),    # layer4 (TN=32 -> two batch tiles, second almost empty)
+    (2, 10, 24, 256, 640, 3, 2, 1),    # deconv.1 as a conv-role s2 conv (Co=640 -> BN=128 x5)
+    (2, 40, 96, 64, 128, 3, 2, 1),     # deconv.7
+    (2, 48, 48, 64, 64, 3, 1, 1),      # teacher layer1
+    (5, 6, 6, 512, 512, 3, 1, 1),      # teacher layer4
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FAST_CASES)
+def test_tcgen05_conv_gpu(backend, case):
+    """fast (tcgen05) kernels vs torch on bf16-rounded operands; wgrad still runs the correctness-first kernel"""
+    assert backend == "cuda"
+    from learningbycheating_b200 import _lib
+    _lib.check(_lib.lib().lbc_set_fast_kernels(1))
+    n0 = _lib.lib().lbc_kernel_launch_count()
+    _conv_case("cuda", case, 1, 2e-2)
+    assert _lib.lib().lbc_kernel_launch_count() > n0
 
 
 @pytest.mark.gpu
