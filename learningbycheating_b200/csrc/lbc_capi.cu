@@ -322,7 +322,8 @@ int lbc_op_conv_wgrad(const float* x, const float* dy, float* dw_ref, int N, int
       bf16 *xb = t.get<bf16>(nx), *yb = t.get<bf16>(ny);
       ref::cast<float, bf16>(s, x, xb, nx);
       ref::cast<float, bf16>(s, dy, yb, ny);
-      ref::conv_wgrad<bf16>(s, xb, yb, dw_ref, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, ws, wsn);
+      if (!fast::conv_wgrad<bf16>(c, xb, yb, dw_ref, N, ws, wsn, s))
+        ref::conv_wgrad<bf16>(s, xb, yb, dw_ref, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, ws, wsn);
     }
     sync_stream(s);
   });

@@ -40,5 +40,18 @@ inline bool conv_dgrad<bf16>(const ConvL& c, const bf16* dy, bf16* dx, int B, co
   return conv_dgrad_bf16(c, dy, dx, B, bias_ci, relu, s);
 }
 
+bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch,
+                     int64_t scratch_floats, lbc_stream_t s);
+template <class T>
+inline bool conv_wgrad(const ConvL&, const T*, const T*, float*, int, float*, int64_t, lbc_stream_t) {
+  return false;
+}
+template <>
+inline bool conv_wgrad<bf16>(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch,
+                             int64_t scratch_floats, lbc_stream_t s) {
+  if (!enabled()) return false;
+  return conv_wgrad_bf16(c, x, dy, dw_ref, B, scratch, scratch_floats, s);
+}
+
 }  // namespace fast
 }  // namespace lbc

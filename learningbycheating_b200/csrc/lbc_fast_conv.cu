@@ -555,9 +555,268 @@ bool conv_dgrad_bf16(const ConvL& c, const bf16* dy, bf16* dx, int B, const floa
   return true;
 }
 
+
+// =============================================================================================================
+// Weight gradient:  dW[co][tap][ci] = sum_{n,oh,ow} dy[n,oh,ow,co] * x[n, oh*s-p+kh, ow*s-p+kw, ci]
+//
+//   D[128 co x BNW ci] (fp32, TMEM) += A[128 co x 128 pixels] * B[BNW ci x 128 pixels]^T, both operands "MN-major":
+//   a TMA box {64 ch, TW, TH, TN} lands as [128 pixels][64 ch] rows of 128 B (128 B swizzle) = the UMMA MN-major
+//   SWIZZLE_128B canonical layout with K = pixels (8-row groups 1024 B apart, 64-channel blocks LBO apart).
+//   One CTA per (co tile, tap, ci tile, K split); split-K partials are reduced with fp32 red.global.add into a
+//   packed [Co][tap][Ci] scratch that a tiny kernel then permutes into the reference's [Co][Ci][kh][kw] .grad.
+// =============================================================================================================
+struct WgradParams {
+  int TW, TH, TN, tiles_w, tiles_h, tiles_n;
+  int k_tiles, k_per_split, splits;
+  int co_tiles, ci_tiles, num_taps;
+  int tap_dh[9], tap_dw[9], tap_map[9];
+  int Co, Ci;
+  float* out;  // [Co][num_taps][Ci] fp32, pre-zeroed
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // distance between 64-element MN blocks
+  d |= (uint64_t)(1024 >> 4) << 32;                  // distance between 8-row K groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BNW, int STAGES>
+struct WgradSmem {
+  static constexpr int A_ST = 2 * A_BYTES;            // 128 co = 2 boxes
+  static constexpr int B_ST = (BNW / 64) * A_BYTES;   // BNW ci
+  static constexpr int STAGE_BYTES = A_ST + B_ST;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int BNW, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant__ CUtensorMap mX0,
+                  const __grid_constant__ CUtensorMap mX1, const __grid_constant__ CUtensorMap mX2,
+                  const __grid_constant__ CUtensorMap mX3, const WgradParams p) {
+  typedef WgradSmem<BNW, STAGES> SP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + SP::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = BNW <= 32 ? 32 : (BNW <= 64 ? 64 : (BNW <= 128 ? 128 : 256));
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // decode this CTA's work: (split, co_tile, tap, ci_tile)
+  int id = blockIdx.x;
+  const int ci_tile = id % p.ci_tiles;
+  id /= p.ci_tiles;
+  const int tap = id % p.num_taps;
+  id /= p.num_taps;
+  const int co_tile = id % p.co_tiles;
+  const int split = id / p.co_tiles;
+  const int kt0 = split * p.k_per_split;
+  int kt1 = kt0 + p.k_per_split;
+  if (kt1 > p.k_tiles) kt1 = p.k_tiles;
+  const int n_k = kt1 - kt0;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const int mid = p.tap_map[tap];
+      const CUtensorMap* mx = mid == 0 ? &mX0 : (mid == 1 ? &mX1 : (mid == 2 ? &mX2 : &mX3));
+      const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        const int w0 = (kt % p.tiles_w) * p.TW;
+        const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.TN;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * SP::STAGE_BYTES;
+        mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
+        tma_load_4d(&mDY, sa, &full[stage], co_tile * 128, w0, h0, n0);
+        tma_load_4d(&mDY, sa + A_BYTES, &full[stage], co_tile * 128 + 64, w0, h0, n0);  // OOB -> zeros when Co == 64
+#pragma unroll
+        for (int b = 0; b < BNW / 64; ++b)
+          tma_load_4d(mx, sa + SP::A_ST + b * A_BYTES, &full[stage], ci_tile * BNW + b * 64, w0 + dw, h0 + dh, n0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // D=f32, A=B=bf16, both MN-major (bits 15,16), N=BNW, M=128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BNW >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < n_k; ++k) {
+      mbar_wait(&full[stage], phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * SP::STAGE_BYTES);
+        const uint64_t ad = umma_desc_mn_sw128(sa, A_BYTES);
+        const uint64_t bd = umma_desc_mn_sw128(sa + SP::A_ST, A_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // 8 x (K=16 pixels): advance two 8-row groups = 2048 B
+          umma_bf16(tmem_base, ad + (uint64_t)(kk * (2048 >> 4)), bd + (uint64_t)(kk * (2048 >> 4)), idesc, (k | kk) != 0);
+        umma_commit(&empty[stage]);
+        if (k == n_k - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (n_k > 0) {
+    const int q = warp & 3;
+    const int co = co_tile * 128 + q * 32 + lane;
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < BNW / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(taddr + ch * 32, r);
+      if (co < p.Co) {
+        float* dst = p.out + ((int64_t)co * p.num_taps + tap) * p.Ci + ci_tile * BNW + ch * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// packed fp32 [Co][taps][Ci] -> reference layout [Co][Ci][K][K]
+__global__ void wgrad_unpack_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int Ci, int KK) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = (int64_t)Co * Ci * KK;
+  if (i >= n) return;
+  int t = (int)(i % KK);
+  int64_t r = i / KK;
+  int ci = (int)(r % Ci);
+  int co = (int)(r / Ci);
+  dst[i] = src[((int64_t)co * KK + t) * Ci + ci];
+}
+
+template <int BNW, int STAGES>
+static void launch_wgrad(const CUtensorMap& mDY, const CUtensorMap* mX, const WgradParams& p, lbc_stream_t s) {
+  typedef WgradSmem<BNW, STAGES> SP;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BNW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    configured = true;
+  }
+  int grid = p.splits * p.co_tiles * p.num_taps * p.ci_tiles;
+  wgrad_gemm_kernel<BNW, STAGES><<<grid, 192, SP::TOTAL, s>>>(mDY, mX[0], mX[1], mX[2], mX[3], p);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+}
+
+// x [B,H,W,Ci], dy [B,OH,OW,Co] -> dw_ref fp32 [Co][Ci][K][K]; scratch >= Co*K*K*Ci floats
+bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch,
+                     int64_t scratch_floats, lbc_stream_t s) {
+  if (!supported(c)) return false;
+  const int KK = c.K * c.K;
+  const int64_t wsize = (int64_t)c.Co * KK * c.Ci;
+  if (wsize > scratch_floats) return false;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  ConvGemmParams g;
+  if (!tile_geometry(c.OH, c.OW, B, g)) return false;
+  p.TW = g.TW;
+  p.TH = g.TH;
+  p.TN = g.TN;
+  p.tiles_w = g.tiles_w;
+  p.tiles_h = g.tiles_h;
+  p.tiles_n = g.tiles_n;
+  p.k_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  const int BNW = c.Ci >= 128 ? 128 : 64;
+  p.co_tiles = (c.Co + 127) / 128;
+  p.ci_tiles = c.Ci / BNW;
+  p.num_taps = KK;
+  p.Co = c.Co;
+  p.Ci = c.Ci;
+  p.out = scratch;
+  const int out_tiles = p.co_tiles * p.ci_tiles * KK;
+  int splits = (2 * sm_count() + out_tiles - 1) / out_tiles;
+  if (splits > p.k_tiles / 4) splits = p.k_tiles / 4;
+  if (splits < 1) splits = 1;
+  p.k_per_split = (p.k_tiles + splits - 1) / splits;
+  p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
+  const int64_t eb = 2;
+  CUtensorMap mDY = make_map_4d(dy, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb,
+                                (int64_t)c.OH * c.OW * c.Co * eb, p.TW, p.TH, p.TN);
+  CUtensorMap mX[4];
+  if (c.stride == 1) {
+    mX[0] = make_map_4d(x, c.Ci, c.W, c.H, B, c.Ci * eb, (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH,
+                        p.TN);
+    mX[1] = mX[2] = mX[3] = mX[0];
+    for (int kh = 0; kh < c.K; ++kh)
+      for (int kw = 0; kw < c.K; ++kw) {
+        int t = kh * c.K + kw;
+        p.tap_dh[t] = kh - c.pad;
+        p.tap_dw[t] = kw - c.pad;
+        p.tap_map[t] = 0;
+      }
+  } else {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        mX[a * 2 + b] = make_map_4d(x + ((int64_t)a * c.W + b) * c.Ci, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb,
+                                    2 * (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
+    for (int kh = 0; kh < c.K; ++kh)
+      for (int kw = 0; kw < c.K; ++kw) {
+        int t = kh * c.K + kw;
+        int th = kh - c.pad, tw = kw - c.pad;
+        int a = ((th % 2) + 2) % 2, b = ((tw % 2) + 2) % 2;
+        p.tap_dh[t] = (th - a) / 2;
+        p.tap_dw[t] = (tw - b) / 2;
+        p.tap_map[t] = a * 2 + b;
+      }
+  }
+  LBC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * wsize, s));
+  if (BNW == 128)
+    launch_wgrad<128, 3>(mDY, mX, p, s);
+  else
+    launch_wgrad<64, 4>(mDY, mX, p, s);
+  int64_t n = wsize;
+  wgrad_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(scratch, dw_ref, c.Co, c.Ci, KK);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+
 #else   // LBC_HOST_EMU: no tensor cores on the host; the executor runs the correctness-first kernels
 bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, lbc_stream_t) { return false; }
 bool conv_dgrad_bf16(const ConvL&, const bf16*, bf16*, int, const float*, bool, lbc_stream_t) { return false; }
+bool conv_wgrad_bf16(const ConvL&, const bf16*, const bf16*, float*, int, float*, int64_t, lbc_stream_t) { return false; }
 #endif
 
 }  // namespace fast

@@ -292,6 +292,7 @@ class Net : public NetBase {
   }
   void conv_backward_weight(const ConvL& c, const T* x, const T* dy, int B, lbc_stream_t s) {
     ProfScope ps("conv_wgrad", s, conv_flops(c, B), 0);
+    if (fast::conv_wgrad<T>(c, x, dy, G + c.w_off, B, ws_f, ws_f_n, s)) return;
     ref::conv_wgrad<T>(s, x, dy, G + c.w_off, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, ws_f, ws_f_n);
   }
   void bn_forward(BNL& bn, const T* x, int64_t M, const T* residual, bool relu, T* y, bool train, lbc_stream_t s) {
