@@ -12,5 +12,81 @@ bool enabled() { return g_enabled; }
 void set_enabled(bool on) { g_enabled = on; }
 
 
+#ifdef LBC_HOST_EMU
+bool stem_im2col_bf16(const float*, bf16*, int, int, int, int, int, int, int, bool, lbc_stream_t) { return false; }
+bool stem_pack_weight_bf16(const float*, bf16*, int, int, lbc_stream_t) { return false; }
+bool stem_unpack_wgrad(const float*, float*, int, int, lbc_stream_t) { return false; }
+#else
+struct k_stem_im2col;
+struct k_stem_pack;
+struct k_stem_unpack;
+
+bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, int OH, int OW, int Kp, bool normalize,
+                      lbc_stream_t s) {
+  if (!enabled()) return false;
+  const int G = Kp / 8;
+  const int KT = 49 * C;
+  int64_t n = (int64_t)B * OH * OW * G;
+  par_for<k_stem_im2col>(s, n, [=] __device__(int64_t i) {
+    int g = (int)(i % G);
+    int64_t pix = i / G;
+    int ow = (int)(pix % OW);
+    int64_t t = pix / OW;
+    int oh = (int)(t % OH);
+    int b = (int)(t / OH);
+    uint32_t pk[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int k = g * 8 + e2 * 2 + h;
+        float val = 0.f;
+        if (k < KT) {
+          int tap = k / C, c = k - tap * C;
+          int kh = tap / 7, kw = tap - kh * 7;
+          int ih = oh * 2 - 3 + kh, iw = ow * 2 - 3 + kw;
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+            val = __ldg(img + (((int64_t)b * C + c) * H + ih) * W + iw);
+            if (normalize) {
+              float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+              float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+              val = (val - mean) / sd;
+            }
+          }
+        }
+        v[h] = val;
+      }
+      pk[e2] = (uint32_t)float_to_bf16(v[0]).v | ((uint32_t)float_to_bf16(v[1]).v << 16);
+    }
+    reinterpret_cast<uint4*>(col)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  });
+  return true;
+}
+bool stem_pack_weight_bf16(const float* w_ref, bf16* wp, int C, int Kp, lbc_stream_t s) {
+  par_for<k_stem_pack>(s, (int64_t)64 * Kp, [=] __device__(int64_t i) {
+    int k = (int)(i % Kp);
+    int co = (int)(i / Kp);
+    float v = 0.f;
+    if (k < 49 * C) {
+      int tap = k / C, c = k - tap * C;
+      v = w_ref[((int64_t)co * C + c) * 49 + tap];
+    }
+    wp[i] = float_to_bf16(v);
+  });
+  return true;
+}
+bool stem_unpack_wgrad(const float* dw_col, float* dw_ref, int C, int Kp, lbc_stream_t s) {
+  par_for<k_stem_unpack>(s, (int64_t)64 * C * 49, [=] __device__(int64_t i) {
+    int tap = (int)(i % 49);
+    int64_t t = i / 49;
+    int c = (int)(t % C);
+    int co = (int)(t / C);
+    dw_ref[i] = dw_col[(int64_t)co * Kp + tap * C + c];
+  });
+  return true;
+}
+#endif
+
 }  // namespace fast
 }  // namespace lbc

@@ -53,5 +53,12 @@ inline bool conv_wgrad<bf16>(const ConvL& c, const bf16* x, const bf16* dy, floa
   return conv_wgrad_bf16(c, x, dy, dw_ref, B, scratch, scratch_floats, s);
 }
 
+// ---- stem (7x7/s2, C_in = 3 or 7): explicit im2col (fused NCHW fp32 -> bf16 + RGB normalisation) feeding the
+// same tcgen05 GEMM kernels as a 1x1 convolution over the [B,OH,OW,Kp] column tensor (Kp = 49*C padded to 64).
+bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, int OH, int OW, int Kp, bool normalize,
+                      lbc_stream_t s);
+bool stem_pack_weight_bf16(const float* w_ref, bf16* wp, int C, int Kp, lbc_stream_t s);      // [64][C][7][7] -> [64][Kp]
+bool stem_unpack_wgrad(const float* dw_col, float* dw_ref, int C, int Kp, lbc_stream_t s);    // [64][Kp] -> [64][C][7][7]
+
 }  // namespace fast
 }  // namespace lbc

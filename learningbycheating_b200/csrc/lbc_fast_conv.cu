@@ -758,7 +758,7 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
   p.tiles_h = g.tiles_h;
   p.tiles_n = g.tiles_n;
   p.k_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
-  const int BNW = c.Ci >= 128 ? 128 : 64;
+  const int BNW = (c.Ci % 128 == 0) ? 128 : 64;
   p.co_tiles = (c.Co + 127) / 128;
   p.ci_tiles = c.Ci / BNW;
   p.num_taps = KK;

@@ -47,6 +47,11 @@ class Net : public NetBase {
   int stem_oh, stem_ow, pool_h, pool_w;
   T *x0 = nullptr, *r_stem = nullptr, *a_stem = nullptr, *pool = nullptr;
   uint8_t* pool_idx = nullptr;
+  // bf16 fast path of the stem: im2col columns [B,OH,OW,Kp] + a 1x1 "conv" descriptor over them
+  T* stem_col = nullptr;
+  ConvL stem_gemm;
+  float* stem_dw_col = nullptr;
+  bool stem_fast_used = false;
   std::vector<Block> blocks;
   int trunk_h, trunk_w;
   BNL dbn[3];
@@ -174,6 +179,19 @@ class Net : public NetBase {
     a_stem = alloc<T>(B * stem_oh * stem_ow * 64);
     pool = alloc<T>(B * pool_h * pool_w * 64);
     pool_idx = alloc<uint8_t>(B * pool_h * pool_w * 64);
+    if (std::is_same<T, bf16>::value) {
+      int Kp = ((49 * in_ch + 63) / 64) * 64;
+      stem_gemm.Ci = Kp;
+      stem_gemm.Co = 64;
+      stem_gemm.K = 1;
+      stem_gemm.stride = 1;
+      stem_gemm.pad = 0;
+      stem_gemm.H = stem_gemm.OH = stem_oh;
+      stem_gemm.W = stem_gemm.OW = stem_ow;
+      stem_gemm.wp = alloc<T>(64 * Kp);
+      stem_col = alloc<T>(B * stem_oh * stem_ow * Kp);
+      stem_dw_col = alloc<float>(64 * Kp);
+    }
     // ---- BasicBlocks (resnet.py:25-54,132-146)
     int C = 64, H = pool_h, W = pool_w;
     const T* prev = pool;
@@ -268,6 +286,8 @@ class Net : public NetBase {
       if (std::is_same<T, bf16>::value && &c != &stem) ref::pack_weight_t<T>(s, P + c.w_off, (T*)c.wpt, c.Co, c.Ci, c.K);
     };
     pk(stem);
+    if (std::is_same<T, bf16>::value)
+      fast::stem_pack_weight_bf16(P + stem.w_off, (bf16*)stem_gemm.wp, in_ch, stem_gemm.Ci, s);
     for (Block& b : blocks) {
       pk(b.c1);
       pk(b.c2);
@@ -335,10 +355,18 @@ class Net : public NetBase {
     pack_weights(s);
     dev_copy(onehot_saved, onehot, sizeof(float) * B * 4, s);
     dev_copy(speed_saved, speed, sizeof(float) * B, s);
-    ref::input_to_nhwc<T>(s, image, x0, B, in_ch, in_h, in_w, in_ch, normalize, 0.485f, 0.456f, 0.406f, 0.229f,
-                          0.224f, 0.225f);
     // stem
-    conv_forward(stem, x0, r_stem, B, s);
+    stem_fast_used = false;
+    if (std::is_same<T, bf16>::value) {
+      ProfScope ps("conv_fwd", s, conv_flops(stem, B), 0);
+      if (fast::stem_im2col_bf16(image, (bf16*)stem_col, B, in_ch, in_h, in_w, stem_oh, stem_ow, stem_gemm.Ci, normalize, s))
+        stem_fast_used = fast::conv_fwd<T>(stem_gemm, stem_col, r_stem, B, s);
+    }
+    if (!stem_fast_used) {
+      ref::input_to_nhwc<T>(s, image, x0, B, in_ch, in_h, in_w, in_ch, normalize, 0.485f, 0.456f, 0.406f, 0.229f,
+                            0.224f, 0.225f);
+      conv_forward(stem, x0, r_stem, B, s);
+    }
     bn_forward(stem_bn, r_stem, (int64_t)B * stem_oh * stem_ow, nullptr, true, a_stem, train, s);
     ref::maxpool_fwd<T>(s, a_stem, pool, pool_idx, B, stem_oh, stem_ow, 64, pool_h, pool_w);
     // residual blocks
@@ -457,7 +485,16 @@ class Net : public NetBase {
     int64_t Ms = (int64_t)B * stem_oh * stem_ow;
     ref::relu_mask_inplace<T>(s, tA, a_stem, Ms * 64);
     bn_backward(stem_bn, tA, r_stem, tB, Ms, s);
-    conv_backward_weight(stem, x0, tB, B, s);
+    bool stem_wgrad_done = false;
+    if (stem_fast_used) {
+      ProfScope ps("conv_wgrad", s, conv_flops(stem, B), 0);
+      if (fast::conv_wgrad<T>(stem_gemm, stem_col, tB, stem_dw_col, B, ws_f, ws_f_n, s))
+        stem_wgrad_done = fast::stem_unpack_wgrad(stem_dw_col, G + stem.w_off, in_ch, stem_gemm.Ci, s);
+    }
+    if (!stem_wgrad_done) {
+      LBC_CHECK(!stem_fast_used, "stem weight gradient: fast path failed after a fast forward");
+      conv_backward_weight(stem, x0, tB, B, s);
+    }
   }
 
   // ------------------------------------------------------------------ taps
