@@ -53,6 +53,71 @@ inline bool conv_wgrad<bf16>(const ConvL& c, const bf16* x, const bf16* dy, floa
   return conv_wgrad_bf16(c, x, dy, dw_ref, B, scratch, scratch_floats, s);
 }
 
+// ---- HBM-bound bf16 kernels (lbc_fast_elem.cu) -------------------------------------------------------------
+bool bn_stats_bf16(const bf16* x, int64_t M, int C, float* sums, lbc_stream_t s);
+bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const float* gamma, const float* beta, float eps,
+                   float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
+                   const bf16* residual, bool relu, bool train, bf16* y, lbc_stream_t s);
+bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
+                 const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s);
+bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s);
+bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                          bf16* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, lbc_stream_t s);
+bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, bf16* dx, int N, int H, int W, int C, int OH, int OW,
+                           lbc_stream_t s);
+
+// generic-T front ends: only T = bf16 has fast kernels
+template <class T> struct Fast {
+  static bool bn_fwd(const T*, int64_t, int, const float*, const float*, float, float, float*, float*, float*, float*,
+                     const T*, bool, bool, T*, float*, lbc_stream_t) { return false; }
+  static bool bn_bwd(const T*, const T*, const T*, const float*, const float*, const float*, float*, float*, T*, int64_t, int,
+                     float*, lbc_stream_t) { return false; }
+  static bool ew(T*, const T*, const T*, int64_t, int, lbc_stream_t) { return false; }
+  static bool colsum(const T*, int64_t, int, float*, float*, lbc_stream_t) { return false; }
+  static bool pool_fwd(const T*, const float*, const float*, const float*, const float*, T*, uint8_t*, int, int, int, int, int,
+                       int, lbc_stream_t) { return false; }
+  static bool pool_bwd(const T*, const uint8_t*, const T*, const float*, const float*, const float*, const float*, T*, int, int,
+                       int, int, int, int, lbc_stream_t) { return false; }
+};
+template <> struct Fast<bf16> {
+  // train: statistics + apply (two launches); eval: apply with the running statistics.  sums: >= 2C floats scratch
+  static bool bn_fwd(const bf16* x, int64_t M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                     float* rm, float* rv, float* saved_mean, float* saved_rstd, const bf16* res, bool relu, bool train,
+                     bf16* y, float* sums, lbc_stream_t s) {
+    if (!enabled()) return false;
+    if (train && !bn_stats_bf16(x, M, C, sums, s)) return false;
+    return bn_apply_bf16(x, sums, M, C, gamma, beta, eps, momentum, rm, rv, saved_mean, saved_rstd, res, relu, train, y, s);
+  }
+  static bool bn_bwd(const bf16* dy, const bf16* mask, const bf16* x, const float* mean, const float* rstd, const float* gamma,
+                     float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s) {
+    if (!enabled()) return false;
+    return bn_bwd_bf16(dy, mask, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, sums, s);
+  }
+  static bool ew(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s) {
+    if (!enabled()) return false;
+    return ew_bf16(dst, src, act, n, mode, s);
+  }
+  // column sums (deconv bias gradient) = first half of the BN statistics kernel's output
+  static bool colsum(const bf16* x, int64_t M, int C, float* out_via_sums, float* sums, lbc_stream_t s) {
+    if (!enabled()) return false;
+    if (!bn_stats_bf16(x, M, C, sums, s)) return false;
+    dev_copy(out_via_sums, sums, sizeof(float) * C, s);
+    return true;
+  }
+  static bool pool_fwd(const bf16* x, const float* mean, const float* rstd, const float* gamma, const float* beta, bf16* y,
+                       uint8_t* idx, int N, int H, int W, int C, int OH, int OW, lbc_stream_t s) {
+    if (!enabled()) return false;
+    return bn_relu_maxpool_bf16(x, mean, rstd, gamma, beta, y, idx, N, H, W, C, OH, OW, s);
+  }
+  static bool pool_bwd(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, bf16* dx, int N, int H, int W, int C, int OH, int OW,
+                       lbc_stream_t s) {
+    if (!enabled()) return false;
+    return maxpool_relu_bwd_bf16(dy, idx, x, mean, rstd, gamma, beta, dx, N, H, W, C, OH, OW, s);
+  }
+};
+
 // ---- stem (7x7/s2, C_in = 3 or 7): explicit im2col (fused NCHW fp32 -> bf16 + RGB normalisation) feeding the
 // same tcgen05 GEMM kernels as a 1x1 convolution over the [B,OH,OW,Kp] column tensor (Kp = 49*C padded to 64).
 bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, int OH, int OW, int Kp, bool normalize,

@@ -1,0 +1,584 @@
+// lbc_fast_elem.cu -- HBM-bound kernels of the bf16 path: train-mode BatchNorm (statistics, apply with fused
+// residual / ReLU, backward with the ReLU mask fused), MaxPool, masked adds.  NHWC bf16, one thread owns 8
+// consecutive channels (one 16-byte vector) of a fixed channel group and strides over rows, so per-channel
+// parameters live in registers and every global access is a coalesced 128-bit transaction; several independent
+// loads are kept in flight per thread.  Reductions: per-thread fp32 partials -> shared memory -> one fp32 atomic
+// per channel per block.  Reference ops: nn.BatchNorm2d in train mode + nn.ReLU(inplace) + residual add
+// (resnet.py:31-53, image.py:38-46) and their autograd backward (SURVEY.md 9.1 closed forms).
+#include "lbc_fast.h"
+
+#ifndef LBC_HOST_EMU
+#include <cuda_bf16.h>
+#endif
+
+namespace lbc {
+namespace fast {
+
+#ifndef LBC_HOST_EMU
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+static int sm_count2() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+struct RowGeom {
+  int tpr, rpi, threads, grid;
+};
+static RowGeom row_geom(int64_t M, int C, int blocks_per_sm) {
+  RowGeom g;
+  g.tpr = C / 8;
+  g.rpi = 256 / g.tpr;
+  if (g.rpi < 1) g.rpi = 1;
+  g.threads = g.rpi * g.tpr;
+  int64_t need = (M + g.rpi - 1) / g.rpi;
+  int64_t cap = (int64_t)sm_count2() * blocks_per_sm;
+  g.grid = (int)(need < cap ? need : cap);
+  if (g.grid < 1) g.grid = 1;
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------- BN statistics
+// sums[0..C) += sum_rows x ; sums[C..2C) += sum_rows x^2      (sums pre-zeroed)
+__global__ void __launch_bounds__(320) bn_stats_kernel(const uint4* __restrict__ x, int64_t M, int tpr, int rpi, float* sums,
+                                                       int C) {
+  extern __shared__ float red[];  // [threads][16]
+  const int t = threadIdx.x;
+  const int cg = t % tpr, r = t / tpr;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * rpi;
+  int64_t row = (int64_t)blockIdx.x * rpi + r;
+  for (; row + 3 * stride < M; row += 4 * stride) {
+    uint4 v0 = ldg_stream(x + row * tpr + cg);
+    uint4 v1 = ldg_stream(x + (row + stride) * tpr + cg);
+    uint4 v2 = ldg_stream(x + (row + 2 * stride) * tpr + cg);
+    uint4 v3 = ldg_stream(x + (row + 3 * stride) * tpr + cg);
+    float f[8];
+    unpack8(v0, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+    unpack8(v1, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+    unpack8(v2, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+    unpack8(v3, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+  }
+  for (; row < M; row += stride) {
+    float f[8];
+    unpack8(ldg_stream(x + row * tpr + cg), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[t * 16 + j] = s[j];
+    red[t * 16 + 8 + j] = q[j];
+  }
+  __syncthreads();
+  if (t < tpr) {
+    for (int rr = 1; rr < rpi; ++rr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += red[(rr * tpr + t) * 16 + j];
+        q[j] += red[(rr * tpr + t) * 16 + 8 + j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(sums + t * 8 + j, s[j]);
+      atomicAdd(sums + C + t * 8 + j, q[j]);
+    }
+  }
+}
+
+bool bn_stats_bf16(const bf16* x, int64_t M, int C, float* sums, lbc_stream_t s) {
+  if (C % 8 || C > 2560) return false;
+  RowGeom g = row_geom(M, C, 8);
+  LBC_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s));
+  bn_stats_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>((const uint4*)x, M, g.tpr, g.rpi, sums, C);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------- BN apply
+struct BnApplyArgs {
+  const uint4* x;
+  const uint4* res;
+  uint4* y;
+  const float* sums;   // train: [2C] sum / sumsq
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* saved_mean;
+  float* saved_rstd;
+  int64_t M;
+  int C, tpr, rpi;
+  float eps, momentum;
+  int relu, train;
+};
+__global__ void __launch_bounds__(320) bn_apply_kernel(const BnApplyArgs a) {
+  const int t = threadIdx.x;
+  const int cg = t % a.tpr, r = t / a.tpr;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    float mean, rstd;
+    if (a.train) {
+      double m = (double)a.sums[c] / (double)a.M;
+      double var = (double)a.sums[a.C + c] / (double)a.M - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+      if (blockIdx.x == 0 && r == 0) {
+        a.saved_mean[c] = mean;
+        a.saved_rstd[c] = rstd;
+        a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * mean;
+        double unb = var * ((double)a.M / (double)(a.M > 1 ? a.M - 1 : 1));
+        a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unb;
+      }
+    } else {
+      mean = a.running_mean[c];
+      rstd = 1.0f / sqrtf(a.running_var[c] + a.eps);
+      if (blockIdx.x == 0 && r == 0) {
+        a.saved_mean[c] = mean;
+        a.saved_rstd[c] = rstd;
+      }
+    }
+    sc[j] = a.gamma[c] * rstd;
+    sh[j] = a.beta[c] - mean * sc[j];
+  }
+  const int64_t stride = (int64_t)gridDim.x * a.rpi;
+  for (int64_t row = (int64_t)blockIdx.x * a.rpi + r; row < a.M; row += 2 * stride) {
+    const int64_t i0 = row * a.tpr + cg;
+    const int64_t row1 = row + stride;
+    const bool has1 = row1 < a.M;
+    const int64_t i1 = row1 * a.tpr + cg;
+    uint4 v0 = ldg_stream(a.x + i0);
+    uint4 v1 = has1 ? ldg_stream(a.x + i1) : v0;
+    uint4 r0, r1;
+    if (a.res) {
+      r0 = ldg_stream(a.res + i0);
+      r1 = has1 ? ldg_stream(a.res + i1) : r0;
+    }
+    float f[8], g[8];
+    unpack8(v0, f);
+    if (a.res) unpack8(r0, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = f[j] * sc[j] + sh[j];
+      if (a.res) v += g[j];
+      if (a.relu) v = fmaxf(v, 0.f);
+      f[j] = v;
+    }
+    a.y[i0] = pack8(f);
+    if (has1) {
+      unpack8(v1, f);
+      if (a.res) unpack8(r1, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = f[j] * sc[j] + sh[j];
+        if (a.res) v += g[j];
+        if (a.relu) v = fmaxf(v, 0.f);
+        f[j] = v;
+      }
+      a.y[i1] = pack8(f);
+    }
+  }
+}
+
+bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const float* gamma, const float* beta, float eps,
+                   float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
+                   const bf16* residual, bool relu, bool train, bf16* y, lbc_stream_t s) {
+  if (C % 8 || C > 2560) return false;
+  RowGeom g = row_geom(M, C, 8);
+  BnApplyArgs a;
+  a.x = (const uint4*)x;
+  a.res = (const uint4*)residual;
+  a.y = (uint4*)y;
+  a.sums = sums;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.running_mean = running_mean;
+  a.running_var = running_var;
+  a.saved_mean = saved_mean;
+  a.saved_rstd = saved_rstd;
+  a.M = M;
+  a.C = C;
+  a.tpr = g.tpr;
+  a.rpi = g.rpi;
+  a.eps = eps;
+  a.momentum = momentum;
+  a.relu = relu ? 1 : 0;
+  a.train = train ? 1 : 0;
+  bn_apply_kernel<<<g.grid, g.threads, 0, s>>>(a);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------- BN backward
+// pass 1: sums[0..C) += sum dy_m ; sums[C..2C) += sum dy_m * xhat,  dy_m = dy * (act > 0) when act != null
+__global__ void __launch_bounds__(320) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
+                                                            const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, int64_t M, int tpr, int rpi,
+                                                            float* sums, int C) {
+  extern __shared__ float red[];
+  const int t = threadIdx.x;
+  const int cg = t % tpr, r = t / tpr;
+  float mu[8], rs[8], s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = mean[cg * 8 + j];
+    rs[j] = rstd[cg * 8 + j];
+    s0[j] = s1[j] = 0.f;
+  }
+  const int64_t stride = (int64_t)gridDim.x * rpi;
+  for (int64_t row = (int64_t)blockIdx.x * rpi + r; row < M; row += 2 * stride) {
+    const int64_t i0 = row * tpr + cg;
+    const bool has1 = row + stride < M;
+    const int64_t i1 = (row + stride) * tpr + cg;
+    uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
+    uint4 d1 = has1 ? ldg_stream(dy + i1) : d0, x1 = has1 ? ldg_stream(x + i1) : x0;
+    uint4 a0, a1;
+    if (act) {
+      a0 = ldg_stream(act + i0);
+      a1 = has1 ? ldg_stream(act + i1) : a0;
+    }
+    float fd[8], fx[8], fa[8];
+    unpack8(d0, fd);
+    unpack8(x0, fx);
+    if (act) unpack8(a0, fa);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
+      s0[j] += g;
+      s1[j] += g * ((fx[j] - mu[j]) * rs[j]);
+    }
+    if (has1) {
+      unpack8(d1, fd);
+      unpack8(x1, fx);
+      if (act) unpack8(a1, fa);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
+        s0[j] += g;
+        s1[j] += g * ((fx[j] - mu[j]) * rs[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[t * 16 + j] = s0[j];
+    red[t * 16 + 8 + j] = s1[j];
+  }
+  __syncthreads();
+  if (t < tpr) {
+    for (int rr = 1; rr < rpi; ++rr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s0[j] += red[(rr * tpr + t) * 16 + j];
+        s1[j] += red[(rr * tpr + t) * 16 + 8 + j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(sums + t * 8 + j, s0[j]);
+      atomicAdd(sums + C + t * 8 + j, s1[j]);
+    }
+  }
+}
+// pass 2: dx = gamma*rstd*(dy_m - dbeta/M - xhat*dgamma/M); block 0 also publishes dgamma / dbeta
+__global__ void __launch_bounds__(320) bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
+                                                           const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ sums, float* dgamma, float* dbeta,
+                                                           uint4* __restrict__ dx, int64_t M, int tpr, int rpi, int C) {
+  const int t = threadIdx.x;
+  const int cg = t % tpr, r = t / tpr;
+  float mu[8], rs[8], k0[8], k1[8], k2[8];
+  const float invM = 1.0f / (float)M;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    mu[j] = mean[c];
+    rs[j] = rstd[c];
+    const float db = sums[c], dg = sums[C + c];
+    if (blockIdx.x == 0 && r == 0) {
+      dbeta[c] = db;
+      dgamma[c] = dg;
+    }
+    k0[j] = gamma[c] * rs[j];   // dx = k0*(g - k1 - xhat*k2)
+    k1[j] = db * invM;
+    k2[j] = dg * invM;
+  }
+  if (!dx) return;
+  const int64_t stride = (int64_t)gridDim.x * rpi;
+  for (int64_t row = (int64_t)blockIdx.x * rpi + r; row < M; row += 2 * stride) {
+    const int64_t i0 = row * tpr + cg;
+    const bool has1 = row + stride < M;
+    const int64_t i1 = (row + stride) * tpr + cg;
+    uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
+    uint4 d1 = has1 ? ldg_stream(dy + i1) : d0, x1 = has1 ? ldg_stream(x + i1) : x0;
+    uint4 a0, a1;
+    if (act) {
+      a0 = ldg_stream(act + i0);
+      a1 = has1 ? ldg_stream(act + i1) : a0;
+    }
+    float fd[8], fx[8], fa[8], o[8];
+    unpack8(d0, fd);
+    unpack8(x0, fx);
+    if (act) unpack8(a0, fa);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
+      o[j] = k0[j] * (g - k1[j] - (fx[j] - mu[j]) * rs[j] * k2[j]);
+    }
+    dx[i0] = pack8(o);
+    if (has1) {
+      unpack8(d1, fd);
+      unpack8(x1, fx);
+      if (act) unpack8(a1, fa);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
+        o[j] = k0[j] * (g - k1[j] - (fx[j] - mu[j]) * rs[j] * k2[j]);
+      }
+      dx[i1] = pack8(o);
+    }
+  }
+}
+
+bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
+                 const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s) {
+  if (C % 8 || C > 2560) return false;
+  RowGeom g = row_geom(M, C, 6);
+  LBC_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s));
+  bn_bwd_reduce_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
+      (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, sums, C);
+  ++g_launches;
+  bn_bwd_apply_kernel<<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, gamma,
+                                                  sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------- elementwise
+// mode 0: dst = dst + src ; mode 1: dst = dst + src*(act>0) ; mode 2: dst = dst*(act>0) (src ignored)
+__global__ void __launch_bounds__(256) ew_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
+                                                 const uint4* __restrict__ act, int64_t n, int mode) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float a[8], b[8], m[8];
+    unpack8(dst[i], a);
+    if (mode != 2) unpack8(ldg_stream(src + i), b);
+    if (mode != 0) unpack8(ldg_stream(act + i), m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (mode == 0) a[j] += b[j];
+      else if (mode == 1) a[j] += (m[j] > 0.f) ? b[j] : 0.f;
+      else a[j] = (m[j] > 0.f) ? a[j] : 0.f;
+    }
+    dst[i] = pack8(a);
+  }
+}
+bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s) {
+  if (n % 8) return false;
+  int64_t nv = n / 8;
+  int64_t blocks = (nv + 255) / 256;
+  int64_t cap = (int64_t)sm_count2() * 16;
+  if (blocks > cap) blocks = cap;
+  ew_kernel<<<(unsigned)blocks, 256, 0, s>>>((uint4*)dst, (const uint4*)src, (const uint4*)act, nv, mode);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------- stem BN+ReLU+MaxPool
+// pool[n,oh,ow,:] = max over the 3x3/s2/p1 window of relu(bn(x)); idx = kh*3+kw of the first maximum.
+// (resnet.py:150-152).  One thread per (output position, 8 channels); the BN+ReLU activation is never written.
+__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, uint4* __restrict__ y,
+                                                              uint2* __restrict__ idx, int N, int H, int W, int tpr, int OH,
+                                                              int OW) {
+  const int64_t total = (int64_t)N * OH * OW * tpr;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int cg = (int)(i % tpr);
+    int64_t p = i / tpr;
+    const int ow = (int)(p % OW);
+    p /= OW;
+    const int oh = (int)(p % OH);
+    const int b = (int)(p / OH);
+    float sc[8], sh[8], best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      sc[j] = gamma[c] * rstd[c];
+      sh[j] = beta[c] - mean[c] * sc[j];
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * 2 - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * 2 - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        float f[8];
+        unpack8(__ldg(x + (((int64_t)b * H + ih) * W + iw) * tpr + cg), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = fmaxf(f[j] * sc[j] + sh[j], 0.f);
+          // compare on the bf16-rounded activation, exactly what a materialised a_stem would hold
+          v = __bfloat162float(__float2bfloat16_rn(v));
+          if (v > best[j]) {
+            best[j] = v;
+            bi[j] = kh * 3 + kw;
+          }
+        }
+      }
+    }
+    y[i] = pack8(best);
+    uint2 id;
+    id.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    id.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    idx[i] = id;
+  }
+}
+bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                          bf16* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, lbc_stream_t s) {
+  if (C % 8) return false;
+  int64_t total = (int64_t)N * OH * OW * (C / 8);
+  int64_t blocks = (total + 255) / 256;
+  int64_t cap = (int64_t)sm_count2() * 16;
+  if (blocks > cap) blocks = cap;
+  bn_relu_maxpool_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y, (uint2*)idx, N, H,
+                                                         W, C / 8, OH, OW);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+// d(bn-relu output)[n,h,w,:] = sum over the <=4 pooling windows that selected (h,w), times the ReLU mask recomputed
+// from the raw conv output; written as the upstream gradient of the stem BatchNorm.
+__global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+                                                               const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, uint4* __restrict__ dx, int N,
+                                                               int H, int W, int tpr, int OH, int OW) {
+  const int64_t total = (int64_t)N * H * W * tpr;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int cg = (int)(i % tpr);
+    int64_t p = i / tpr;
+    const int iw = (int)(p % W);
+    p /= W;
+    const int ih = (int)(p % H);
+    const int b = (int)(p / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int t = ih + 1 - kh;
+      if (t < 0 || (t & 1)) continue;
+      const int oh = t >> 1;
+      if (oh >= OH) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int u = iw + 1 - kw;
+        if (u < 0 || (u & 1)) continue;
+        const int ow = u >> 1;
+        if (ow >= OW) continue;
+        const int64_t o = (((int64_t)b * OH + oh) * OW + ow) * tpr + cg;
+        const uint2 id = __ldg(idx + o);
+        float g[8];
+        unpack8(__ldg(dy + o), g);
+        const uint32_t want = (uint32_t)(kh * 3 + kw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t sel = ((j < 4 ? id.x : id.y) >> ((j & 3) * 8)) & 0xffu;
+          if (sel == want) acc[j] += g[j];
+        }
+      }
+    }
+    float f[8];
+    unpack8(ldg_stream(x + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      const float scj = gamma[c] * rstd[c];
+      const float v = f[j] * scj + (beta[c] - mean[c] * scj);
+      if (!(v > 0.f)) acc[j] = 0.f;
+    }
+    dx[i] = pack8(acc);
+  }
+}
+bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, bf16* dx, int N, int H, int W, int C, int OH, int OW,
+                           lbc_stream_t s) {
+  if (C % 8) return false;
+  int64_t total = (int64_t)N * H * W * (C / 8);
+  int64_t blocks = (total + 255) / 256;
+  int64_t cap = (int64_t)sm_count2() * 16;
+  if (blocks > cap) blocks = cap;
+  maxpool_relu_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean, rstd, gamma,
+                                                          beta, (uint4*)dx, N, H, W, C / 8, OH, OW);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+
+#else  // LBC_HOST_EMU
+bool bn_stats_bf16(const bf16*, int64_t, int, float*, lbc_stream_t) { return false; }
+bool bn_apply_bf16(const bf16*, const float*, int64_t, int, const float*, const float*, float, float, float*, float*, float*,
+                   float*, const bf16*, bool, bool, bf16*, lbc_stream_t) { return false; }
+bool bn_bwd_bf16(const bf16*, const bf16*, const bf16*, const float*, const float*, const float*, float*, float*, bf16*,
+                 int64_t, int, float*, lbc_stream_t) { return false; }
+bool ew_bf16(bf16*, const bf16*, const bf16*, int64_t, int, lbc_stream_t) { return false; }
+bool bn_relu_maxpool_bf16(const bf16*, const float*, const float*, const float*, const float*, bf16*, uint8_t*, int, int, int,
+                          int, int, int, lbc_stream_t) { return false; }
+bool maxpool_relu_bwd_bf16(const bf16*, const uint8_t*, const bf16*, const float*, const float*, const float*, const float*,
+                           bf16*, int, int, int, int, int, int, lbc_stream_t) { return false; }
+#endif
+
+}  // namespace fast
+}  // namespace lbc

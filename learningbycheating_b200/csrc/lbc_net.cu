@@ -66,6 +66,8 @@ class Net : public NetBase {
   float* ws_f = nullptr;
   int64_t ws_f_n = 0;
   double* ws_d = nullptr;
+  float* bn_sums = nullptr;  // 2*C floats scratch of the fast BN kernels
+  bool stem_pool_fused = false;
   size_t total_bytes = 0;
   int cur_B = 0;
   bool cur_train = false;
@@ -276,6 +278,7 @@ class Net : public NetBase {
     int64_t wd = (1 << 20);
     if (B * 20 * 65 + 4096 > wd) wd = B * 20 * 65 + 4096;
     ws_d = alloc<double>(wd);
+    bn_sums = alloc<float>(2 * 1024);
   }
 
   // ------------------------------------------------------------------ op wrappers (fast-path hooks)
@@ -318,6 +321,9 @@ class Net : public NetBase {
   void bn_forward(BNL& bn, const T* x, int64_t M, const T* residual, bool relu, T* y, bool train, lbc_stream_t s) {
     // algorithmic bytes: stats read (train) + apply read (+residual) + write
     ProfScope ps("bn_fwd", s, 0, (double)M * bn.C * sizeof(T) * ((train ? 1 : 0) + 2 + (residual ? 1 : 0)));
+    if (fast::Fast<T>::bn_fwd(x, M, bn.C, P + bn.g_off, P + bn.b_off, kBnEps, kBnMomentum, BUF + bn.rm_off, BUF + bn.rv_off,
+                              bn.mean, bn.rstd, residual, relu, train, y, bn_sums, s))
+      return;
     if (train) {
       ref::bn_stats<T>(s, x, M, bn.C, bn.mean, bn.var, ws_d);
       ref::bn_finalize(s, bn.mean, bn.var, bn.C, M, kBnEps, kBnMomentum, bn.rstd, BUF + bn.rm_off, BUF + bn.rv_off);
@@ -326,10 +332,26 @@ class Net : public NetBase {
     }
     ref::bn_apply<T>(s, x, bn.mean, bn.rstd, P + bn.g_off, P + bn.b_off, residual, relu, y, M, bn.C);
   }
-  void bn_backward(BNL& bn, const T* dy, const T* x, T* dx, int64_t M, lbc_stream_t s) {
-    // algorithmic bytes: reduce pass reads dy,x ; apply pass reads dy,x writes dx
-    ProfScope ps("bn_bwd", s, 0, (double)M * bn.C * sizeof(T) * 5);
+  // dy_m = dy * (mask_act > 0) when mask_act != null (the ReLU that follows the BN, nn.ReLU(True) backward).
+  // Correctness-first path: masks dy in place first; fast path: the mask is fused into both passes, dy untouched.
+  void bn_backward(BNL& bn, T* dy, const T* mask_act, const T* x, T* dx, int64_t M, lbc_stream_t s) {
+    // algorithmic bytes: reduce pass reads dy,(mask),x ; apply pass reads dy,(mask),x writes dx
+    ProfScope ps("bn_bwd", s, 0, (double)M * bn.C * sizeof(T) * (5 + (mask_act ? 2 : 0)));
+    if (fast::Fast<T>::bn_bwd(dy, mask_act, x, bn.mean, bn.rstd, P + bn.g_off, G + bn.g_off, G + bn.b_off, dx, M, bn.C,
+                              bn_sums, s))
+      return;
+    if (mask_act) ref::relu_mask_inplace<T>(s, dy, mask_act, M * bn.C);
     ref::bn_bwd<T>(s, dy, x, bn.mean, bn.rstd, P + bn.g_off, G + bn.g_off, G + bn.b_off, dx, M, bn.C, ws_d);
+  }
+  void relu_mask(T* g, const T* act, int64_t n, lbc_stream_t s) {
+    ProfScope ps("elementwise", s, 0, (double)n * sizeof(T) * 3);
+    if (fast::Fast<T>::ew(g, nullptr, act, n, 2, s)) return;
+    ref::relu_mask_inplace<T>(s, g, act, n);
+  }
+  void add_masked(T* dst, const T* g, const T* act, int64_t n, lbc_stream_t s) {
+    ProfScope ps("elementwise", s, 0, (double)n * sizeof(T) * 4);
+    if (fast::Fast<T>::ew(dst, g, act, n, 1, s)) return;
+    ref::add_masked_inplace<T>(s, dst, g, act, n);
   }
   ref::HeadParams head_params(bool train) {
     ref::HeadParams hp;
@@ -367,8 +389,33 @@ class Net : public NetBase {
                             0.224f, 0.225f);
       conv_forward(stem, x0, r_stem, B, s);
     }
-    bn_forward(stem_bn, r_stem, (int64_t)B * stem_oh * stem_ow, nullptr, true, a_stem, train, s);
-    ref::maxpool_fwd<T>(s, a_stem, pool, pool_idx, B, stem_oh, stem_ow, 64, pool_h, pool_w);
+    stem_pool_fused = false;
+    {
+      const int64_t Ms = (int64_t)B * stem_oh * stem_ow;
+      if (std::is_same<T, bf16>::value && fast::enabled()) {
+        // statistics -> (mean, rstd, running buffers) -> fused BN+ReLU+MaxPool; the activation is never written
+        ProfScope ps("bn_fwd", s, 0, (double)Ms * 64 * sizeof(T) * 2.25);
+        bool ok = true;
+        if (train) {
+          ok = fast::bn_stats_bf16((const bf16*)r_stem, Ms, 64, bn_sums, s);
+          if (ok) {
+            ref::bn_finalize_sums(s, bn_sums, 64, Ms, kBnEps, kBnMomentum, stem_bn.mean, stem_bn.rstd, BUF + stem_bn.rm_off,
+                                  BUF + stem_bn.rv_off);
+          }
+        } else {
+          ref::bn_eval_stats(s, BUF + stem_bn.rm_off, BUF + stem_bn.rv_off, 64, kBnEps, stem_bn.mean, stem_bn.rstd);
+        }
+        if (ok)
+          stem_pool_fused = fast::Fast<T>::pool_fwd(r_stem, stem_bn.mean, stem_bn.rstd, P + stem_bn.g_off, P + stem_bn.b_off,
+                                                    pool, pool_idx, B, stem_oh, stem_ow, 64, pool_h, pool_w, s);
+        LBC_CHECK(ok && stem_pool_fused, "stem BN+ReLU+MaxPool fast path failed");
+      }
+      if (!stem_pool_fused) {
+        bn_forward(stem_bn, r_stem, Ms, nullptr, true, a_stem, train, s);
+        ProfScope ps("pool", s, 0, (double)Ms * 64 * sizeof(T) * 1.25);
+        ref::maxpool_fwd<T>(s, a_stem, pool, pool_idx, B, stem_oh, stem_ow, 64, pool_h, pool_w);
+      }
+    }
     // residual blocks
     for (Block& b : blocks) {
       int64_t M = (int64_t)B * b.Hout * b.Wout;
@@ -448,11 +495,12 @@ class Net : public NetBase {
       const ConvL& c = dcv[i];
       int64_t Mout = (int64_t)B * c.H * c.W;   // deconv output pixels
       int64_t Min = (int64_t)B * c.OH * c.OW;  // deconv input pixels
-      ref::relu_mask_inplace<T>(s, gcur, dec_out[i], Mout * c.Ci);
-      ref::colsum<T>(s, gcur, Mout, c.Ci, G + c.b_off, ws_d);
+      relu_mask(gcur, dec_out[i], Mout * c.Ci, s);
+      if (!fast::Fast<T>::colsum(gcur, Mout, c.Ci, G + c.b_off, bn_sums, s))
+        ref::colsum<T>(s, gcur, Mout, c.Ci, G + c.b_off, ws_d);
       conv_backward_weight(c, gcur, dec_bn[i], B, s);  // conv-role x = d(out), dy = deconv input
       conv_forward(c, gcur, tA, B, s);
-      bn_backward(dbn[i], tA, dec_in[i], gnext, Min, s);
+      bn_backward(dbn[i], tA, nullptr, dec_in[i], gnext, Min, s);
       std::swap(gcur, gnext);
     }
     // drop the 128 speed channels (no gradient path to a parameter through them)
@@ -463,28 +511,37 @@ class Net : public NetBase {
       Block& b = blocks[bi];
       int64_t M = (int64_t)B * b.Hout * b.Wout;
       int64_t ne = M * b.Cout;
-      ref::relu_mask_inplace<T>(s, gcur, b.out, ne);  // gcur = d(sum)
-      bn_backward(b.b2, gcur, b.r2, tA, M, s);        // tA = d r2
+      // gcur = d(out); the block-final ReLU mask (out > 0) is applied inside every consumer of gcur
+      bn_backward(b.b2, gcur, b.out, b.r2, tA, M, s);  // tA = d r2
       conv_backward_weight(b.c2, b.a1, tA, B, s);
-      conv_backward_data(b.c2, tA, tB, B, false, s);  // tB = d a1
-      ref::relu_mask_inplace<T>(s, tB, b.a1, ne);
-      bn_backward(b.b1, tB, b.r1, tA, M, s);  // tA = d r1
+      conv_backward_data(b.c2, tA, tB, B, false, s);   // tB = d a1 (before the ReLU mask a1 > 0)
+      bn_backward(b.b1, tB, b.a1, b.r1, tA, M, s);     // tA = d r1
       conv_backward_weight(b.c1, b.xin, tA, B, s);
       conv_backward_data(b.c1, tA, gnext, B, false, s);  // gnext = d xin (main path)
       if (b.ds) {
-        bn_backward(b.bd, gcur, b.rd, tA, M, s);  // tA = d rd
+        bn_backward(b.bd, gcur, b.out, b.rd, tA, M, s);  // tA = d rd
         conv_backward_weight(b.cd, b.xin, tA, B, s);
         conv_backward_data(b.cd, tA, gnext, B, true, s);
       } else {
-        ref::add_inplace<T>(s, gnext, gcur, ne);
+        add_masked(gnext, gcur, b.out, ne, s);
       }
       std::swap(gcur, gnext);
     }
     // stem: maxpool -> relu -> bn -> conv1 weight gradient (no input gradient)
-    ref::maxpool_bwd<T>(s, gcur, pool_idx, tA, B, stem_oh, stem_ow, 64, pool_h, pool_w);
     int64_t Ms = (int64_t)B * stem_oh * stem_ow;
-    ref::relu_mask_inplace<T>(s, tA, a_stem, Ms * 64);
-    bn_backward(stem_bn, tA, r_stem, tB, Ms, s);
+    if (stem_pool_fused) {
+      ProfScope ps("pool", s, 0, (double)Ms * 64 * sizeof(T) * 2.5);
+      bool ok = fast::Fast<T>::pool_bwd(gcur, pool_idx, r_stem, stem_bn.mean, stem_bn.rstd, P + stem_bn.g_off,
+                                        P + stem_bn.b_off, tA, B, stem_oh, stem_ow, 64, pool_h, pool_w, s);
+      LBC_CHECK(ok, "stem MaxPool/ReLU backward fast path failed");
+      bn_backward(stem_bn, tA, nullptr, r_stem, tB, Ms, s);
+    } else {
+      {
+        ProfScope ps("pool", s, 0, (double)Ms * 64 * sizeof(T) * 1.25);
+        ref::maxpool_bwd<T>(s, gcur, pool_idx, tA, B, stem_oh, stem_ow, 64, pool_h, pool_w);
+      }
+      bn_backward(stem_bn, tA, a_stem, r_stem, tB, Ms, s);
+    }
     bool stem_wgrad_done = false;
     if (stem_fast_used) {
       ProfScope ps("conv_wgrad", s, conv_flops(stem, B), 0);

@@ -284,6 +284,19 @@ inline void bn_finalize(lbc_stream_t s, const float* mean, const float* var_bias
     }
   });
 }
+// same from (sum, sum of squares) accumulated by the fast statistics kernel
+inline void bn_finalize_sums(lbc_stream_t s, const float* sums, int C, int64_t M, float eps, float momentum, float* mean,
+                             float* rstd, float* running_mean, float* running_var) {
+  par_for<k_bn_finalize>(s, C, [=] LBC_LAMBDA(int64_t c) {
+    double m = (double)sums[c] / (double)M;
+    double var = (double)sums[C + c] / (double)M - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * ((double)M / (double)(M > 1 ? M - 1 : 1)));
+  });
+}
 // eval mode: mean = running_mean, rstd from running_var
 inline void bn_eval_stats(lbc_stream_t s, const float* running_mean, const float* running_var, int C, float eps,
                           float* mean, float* rstd) {
