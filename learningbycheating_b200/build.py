@@ -11,7 +11,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SOURCES = ["lbc_capi.cu", "lbc_net.cu", "lbc_fast.cu", "lbc_fast_conv.cu", "lbc_fast_elem.cu"]
+SOURCES = ["lbc_capi.cu", "lbc_net.cu", "lbc_fast.cu", "lbc_fast_conv.cu", "lbc_fast_elem.cu", "lbc_fast_head.cu"]
 CUDA_LIB = os.path.join(PKG, "liblbc_b200.so")
 EMU_LIB = os.path.join(ROOT, "tests", "hostemu", "liblbc_hostemu.so")
 

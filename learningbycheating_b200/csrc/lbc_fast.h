@@ -5,6 +5,7 @@
 #pragma once
 #include "lbc_common.h"
 #include "lbc_net.h"
+#include "lbc_ref_ops.h"
 
 namespace lbc {
 namespace fast {
@@ -117,6 +118,14 @@ template <> struct Fast<bf16> {
     return maxpool_relu_bwd_bf16(dy, idx, x, mean, rstd, gamma, beta, dx, N, H, W, C, OH, OW, s);
   }
 };
+
+// ---- fused waypoint heads (lbc_fast_head.cu); fold: >=1300 floats, coef: >=128 floats, S: [20][65] doubles
+bool head_forward_bf16(const bf16* h, ref::HeadParams hp, float* fold, float* logits, float* rowmax, float* rowsum,
+                       float* preds, int N, int H, int W, lbc_stream_t s);
+bool head_backward_s_bf16(const float* dlogits, const bf16* h, const float* mean, const float* rstd, double* S, int N, int HW,
+                          lbc_stream_t s);
+bool head_backward_dh_bf16(const float* dlogits, const bf16* h, ref::HeadParams hp, ref::HeadGrads hg, const float* fold,
+                           float* coef, bf16* dh, int N, int HW, lbc_stream_t s);
 
 // ---- stem (7x7/s2, C_in = 3 or 7): explicit im2col (fused NCHW fp32 -> bf16 + RGB normalisation) feeding the
 // same tcgen05 GEMM kernels as a 1x1 convolution over the [B,OH,OW,Kp] column tensor (Kp = 49*C padded to 64).

@@ -67,6 +67,9 @@ class Net : public NetBase {
   int64_t ws_f_n = 0;
   double* ws_d = nullptr;
   float* bn_sums = nullptr;  // 2*C floats scratch of the fast BN kernels
+  float* head_fold = nullptr;  // folded BN+1x1 map A[20][64], b'[20]; coef c0/c1 [128]
+  bool head_fast_used = false;
+  bool head_mask_fused = false;
   bool stem_pool_fused = false;
   size_t total_bytes = 0;
   int cur_B = 0;
@@ -279,6 +282,7 @@ class Net : public NetBase {
     if (B * 20 * 65 + 4096 > wd) wd = B * 20 * 65 + 4096;
     ws_d = alloc<double>(wd);
     bn_sums = alloc<float>(2 * 1024);
+    head_fold = alloc<float>(1300 + 128 + 28);
   }
 
   // ------------------------------------------------------------------ op wrappers (fast-path hooks)
@@ -450,7 +454,18 @@ class Net : public NetBase {
     const T* hfeat = dec_out[2];
     int HW = head_h * head_w;
     int64_t M = (int64_t)B * HW;
-    if (train) {
+    ProfScope ps_head("head", s, 0, (double)M * 64 * sizeof(T) * 2 + (double)M * 20 * 4 * 2);
+    bool head_stats_done = false;
+    if (train && std::is_same<T, bf16>::value && fast::enabled()) {
+      if (fast::bn_stats_bf16((const bf16*)hfeat, M, 64, bn_sums, s)) {
+        for (int k = 0; k < 4; ++k)   // same statistics, four sets of running buffers (image.py:56)
+          ref::bn_finalize_sums(s, bn_sums, 64, M, kBnEps, kBnMomentum, hbn[0].mean, hbn[k].rstd, BUF + hbn[k].rm_off,
+                                BUF + hbn[k].rv_off);
+        head_stats_done = true;
+      }
+    }
+    if (head_stats_done) {
+    } else if (train) {
       ref::bn_stats<T>(s, hfeat, M, 64, hbn[0].mean, hbn[0].var, ws_d);
       for (int k = 0; k < 4; ++k)
         ref::bn_finalize(s, hbn[0].mean, hbn[0].var, 64, M, kBnEps, kBnMomentum, hbn[k].rstd, BUF + hbn[k].rm_off,
@@ -459,8 +474,14 @@ class Net : public NetBase {
       for (int k = 0; k < 4; ++k)
         ref::bn_eval_stats(s, BUF + hbn[k].rm_off, BUF + hbn[k].rv_off, 64, kBnEps, hbn[k].mean, hbn[k].rstd);
     }
-    ref::head_logits<T>(s, hfeat, head_params(train), logits, B, HW, 64);
-    ref::head_softmax(s, logits, rowmax, rowsum, preds, B, head_h, head_w);
+    head_fast_used = false;
+    if (std::is_same<T, bf16>::value)
+      head_fast_used = fast::head_forward_bf16((const bf16*)hfeat, head_params(train), head_fold, logits, rowmax, rowsum, preds,
+                                               B, head_h, head_w, s);
+    if (!head_fast_used) {
+      ref::head_logits<T>(s, hfeat, head_params(train), logits, B, HW, 64);
+      ref::head_softmax(s, logits, rowmax, rowsum, preds, B, head_h, head_w);
+    }
     if (out_preds) dev_copy(out_preds, preds, sizeof(float) * B * 40, s);
     if (out_pred) ref::head_select(s, preds, onehot_saved, out_pred, B);
   }
@@ -487,15 +508,25 @@ class Net : public NetBase {
       hg.dbias[k] = G + hb_off[k];
     }
     ref::head_dlogits(s, logits, rowmax, rowsum, preds, onehot_saved, d_pred, d_preds, dlogits, B, head_h, head_w);
-    ref::head_s<T>(s, dlogits, hfeat, hbn[0].mean, hbn[0].rstd, headS, B, HW, 64, ws_d);
-    ref::head_param_grads(s, headS, hp, hg, 64);
-    ref::head_dh<T>(s, dlogits, hfeat, hbn[0].mean, hbn[0].rstd, hp, hg, gcur, B, HW, 64);
+    head_mask_fused = false;
+    {
+      ProfScope ps_head("head", s, 0, (double)B * HW * 64 * sizeof(T) * 3 + (double)B * HW * 20 * 4 * 3);
+      bool s_done = false;
+      if (std::is_same<T, bf16>::value && head_fast_used)
+        s_done = fast::head_backward_s_bf16(dlogits, (const bf16*)hfeat, hbn[0].mean, hbn[0].rstd, headS, B, HW, s);
+      if (!s_done) ref::head_s<T>(s, dlogits, hfeat, hbn[0].mean, hbn[0].rstd, headS, B, HW, 64, ws_d);
+      ref::head_param_grads(s, headS, hp, hg, 64);
+      if (s_done)
+        head_mask_fused = fast::head_backward_dh_bf16(dlogits, (const bf16*)hfeat, hp, hg, head_fold, head_fold + 1300,
+                                                      (bf16*)gcur, B, HW, s);
+      if (!head_mask_fused) ref::head_dh<T>(s, dlogits, hfeat, hbn[0].mean, hbn[0].rstd, hp, hg, gcur, B, HW, 64);
+    }
     // decoder, last stage first
     for (int i = 2; i >= 0; --i) {
       const ConvL& c = dcv[i];
       int64_t Mout = (int64_t)B * c.H * c.W;   // deconv output pixels
       int64_t Min = (int64_t)B * c.OH * c.OW;  // deconv input pixels
-      relu_mask(gcur, dec_out[i], Mout * c.Ci, s);
+      if (!(i == 2 && head_mask_fused)) relu_mask(gcur, dec_out[i], Mout * c.Ci, s);
       if (!fast::Fast<T>::colsum(gcur, Mout, c.Ci, G + c.b_off, bn_sums, s))
         ref::colsum<T>(s, gcur, Mout, c.Ci, G + c.b_off, ws_d);
       conv_backward_weight(c, gcur, dec_bn[i], B, s);  // conv-role x = d(out), dy = deconv input

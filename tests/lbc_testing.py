@@ -102,8 +102,13 @@ def check_step0_against_golden(rec, g, out_tol, loss_tol, grad_global_tol, grad_
         l2 = float(gr.double().norm())
         gl2 += l2 * l2
         ref = float(g[key])
-        if ref < 1e-7:          # head 1x1 bias / head BN beta: mathematically zero gradient
-            assert l2 < 1e-5, (k, l2)
+        if k.startswith("location_pred.") and (k.endswith(".0.bias") or k.endswith(".1.bias")):
+            # head BN beta / 1x1-conv bias: mathematically zero gradient (softmax shift invariance);
+            # both sides hold rounding noise only -> absolute bound relative to the global gradient norm
+            assert l2 <= 1e-5 * max(1.0, float(g["step0/grad_global_l2"])), (k, l2)
+            continue
+        if ref < 1e-12:         # branch never selected in this batch (phase 0): exactly zero in the reference
+            assert l2 < 1e-6, (k, l2)
             continue
         full = "step0/grad/%s/full" % k
         if full in g.files:
