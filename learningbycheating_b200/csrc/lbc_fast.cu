@@ -21,9 +21,71 @@ struct k_stem_im2col;
 struct k_stem_pack;
 struct k_stem_unpack;
 
+// One block = 64 consecutive output positions of one output row.  Gather: thread (pos, c*7+kh) walks the 7 kw taps of
+// one input row (lanes = consecutive positions -> 8-byte lane stride, L1-resident reuse); the [64][Kp] bf16 tile is
+// staged in shared memory and written back as one contiguous 64*Kp*2-byte run with 16-byte stores.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, uint4* __restrict__ col, int C, int H,
+                                                          int W, int OH, int OW, int Kp, int normalize) {
+  extern __shared__ uint16_t tile[];  // [64][Kp]
+  const int segs = OW / 64;
+  int blk = blockIdx.x;
+  const int seg = blk % segs;
+  blk /= segs;
+  const int oh = blk % OH;
+  const int b = blk / OH;
+  const int ow0 = seg * 64;
+  const int KT = 49 * C;
+  // zero the K padding
+  for (int i = threadIdx.x; i < 64 * (Kp - KT); i += 256) {
+    int pos = i / (Kp - KT), k = KT + i % (Kp - KT);
+    tile[pos * Kp + k] = 0;
+  }
+  const int pos = threadIdx.x & 63;
+  const int ow = ow0 + pos;
+  for (int ck = threadIdx.x >> 6; ck < C * 7; ck += 4) {
+    const int c = ck / 7, kh = ck - c * 7;
+    const int ih = oh * 2 - 3 + kh;
+    const bool rowok = ih >= 0 && ih < H;
+    const float* rowp = img + (((int64_t)b * C + c) * H + (rowok ? ih : 0)) * W;
+    float mean = 0.f;
+    if (normalize) {
+      mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+    }
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw) {
+      const int iw = ow * 2 - 3 + kw;
+      float v = 0.f;
+      if (rowok && iw >= 0 && iw < W) {
+        v = __ldg(rowp + iw);
+        if (normalize) v = (v - mean) / (c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f));
+      }
+      tile[pos * Kp + (kh * 7 + kw) * C + c] = float_to_bf16(v).v;
+    }
+  }
+
+  __syncthreads();
+  const int64_t base = (((int64_t)b * OH + oh) * OW + ow0) * Kp / 8;  // in uint4 units
+  const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+  for (int i = threadIdx.x; i < 64 * Kp / 8; i += 256) col[base + i] = t4[i];
+}
+
 bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, int OH, int OW, int Kp, bool normalize,
                       lbc_stream_t s) {
   if (!enabled()) return false;
+  if (OW % 64 == 0 && Kp % 8 == 0) {
+    static bool configured = false;
+    const int smem = 64 * Kp * 2;
+    if (!configured) {
+      LBC_CUDA(cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 512 * 2));
+      configured = true;
+    }
+    if (smem <= 64 * 512 * 2) {
+      stem_im2col_kernel<<<B * OH * (OW / 64), 256, smem, s>>>(img, (uint4*)col, C, H, W, OH, OW, Kp, normalize ? 1 : 0);
+      ++g_launches;
+      LBC_CUDA(cudaGetLastError());
+      return true;
+    }
+  }
   const int G = Kp / 8;
   const int KT = 49 * C;
   int64_t n = (int64_t)B * OH * OW * G;

@@ -41,6 +41,16 @@ inline bool conv_dgrad<bf16>(const ConvL& c, const bf16* dy, bf16* dx, int B, co
   return conv_dgrad_bf16(c, dy, dx, B, bias_ci, relu, s);
 }
 
+bool conv_dgrad_ds_bf16(const ConvL& c1, const bf16* dy1, const bf16* dy_ds, bf16* dx, int B, lbc_stream_t s);
+template <class T>
+inline bool conv_dgrad_ds(const ConvL&, const T*, const T*, T*, int, lbc_stream_t) {
+  return false;
+}
+template <>
+inline bool conv_dgrad_ds<bf16>(const ConvL& c1, const bf16* dy1, const bf16* dy_ds, bf16* dx, int B, lbc_stream_t s) {
+  if (!enabled()) return false;
+  return conv_dgrad_ds_bf16(c1, dy1, dy_ds, dx, B, s);
+}
 bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch,
                      int64_t scratch_floats, lbc_stream_t s);
 template <class T>

@@ -488,7 +488,20 @@ bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s
 
 // dx = conv_dgrad(dy, w):  dy [B,OH,OW,Co], transposed pack wt [Ci][K*K][Co], dx [B,H,W,Ci] (+bias[ci]) (relu)
 // stride 1: one GEMM with mirrored taps; stride 2: one GEMM per output parity (also ConvTranspose2d forward).
+static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu,
+                            const bf16* dy_ds, lbc_stream_t s);
 bool conv_dgrad_bf16(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu, lbc_stream_t s) {
+  return conv_dgrad_impl(c, dy, dx, B, bias_ci, relu, nullptr, s);
+}
+// gradient wrt the input of a residual block's entry: dgrad(3x3/s2 conv1)(dy1) + dgrad(1x1/s2 downsample)(dy_ds).
+// The 1x1/s2 gradient only touches the (even,even) parity, where it is one more K-slab of the same GEMM
+// (A = dy_ds, B = the [Ci][Co] downsample weights stored behind conv1's centre tap in c1.wcomb).
+bool conv_dgrad_ds_bf16(const ConvL& c1, const bf16* dy1, const bf16* dy_ds, bf16* dx, int B, lbc_stream_t s) {
+  if (!c1.wcomb || c1.stride != 2 || c1.K != 3) return false;
+  return conv_dgrad_impl(c1, dy1, dx, B, nullptr, false, dy_ds, s);
+}
+static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu,
+                            const bf16* dy_ds, lbc_stream_t s) {
   if (!supported(c) || !c.wpt) return false;
   if (c.K == 1) return false;  // 1x1/s2 downsample gradient scatters into one parity only: handled by the caller
   const int64_t eb = 2;
@@ -532,10 +545,28 @@ bool conv_dgrad_bf16(const ConvL& c, const bf16* dy, bf16* dx, int B, const floa
   mA[0] = make_map_4d(dy, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb, (int64_t)c.OH * c.OW * c.Co * eb, base.TW,
                       base.TH, base.TN);
   mA[1] = mA[2] = mA[3] = mA[0];
+  if (dy_ds)
+    mA[1] = make_map_4d(dy_ds, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb, (int64_t)c.OH * c.OW * c.Co * eb,
+                        base.TW, base.TH, base.TN);
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       ConvGemmParams p = base;
       int nt = 0;
+      if (dy_ds && a == 0 && b == 0) {
+        // centre tap of the 3x3 (kh=kw=1 -> dh=dw=0) + the downsample slab
+        p.tap_dh[0] = p.tap_dw[0] = 0;
+        p.tap_map[0] = 0;
+        p.tap_koff[0] = 0;
+        p.tap_dh[1] = p.tap_dw[1] = 0;
+        p.tap_map[1] = 1;
+        p.tap_koff[1] = c.Co;
+        p.num_taps = 2;
+        CUtensorMap mBc = make_map_2d(c.wcomb, (int64_t)2 * c.Co, c.Ci, BN);
+        CUtensorMap mO = make_map_4d(dx, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb, 2 * (int64_t)c.W * c.Ci * eb,
+                                     (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
+        dispatch_gemm(BN, mA, mBc, mO, p, s);
+        continue;
+      }
       for (int kh = 0; kh < c.K; ++kh) {
         if ((a + c.pad - kh) % 2 != 0) continue;
         for (int kw = 0; kw < c.K; ++kw) {
@@ -817,6 +848,7 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
 bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, lbc_stream_t) { return false; }
 bool conv_dgrad_bf16(const ConvL&, const bf16*, bf16*, int, const float*, bool, lbc_stream_t) { return false; }
 bool conv_wgrad_bf16(const ConvL&, const bf16*, const bf16*, float*, int, float*, int64_t, lbc_stream_t) { return false; }
+bool conv_dgrad_ds_bf16(const ConvL&, const bf16*, const bf16*, bf16*, int, lbc_stream_t) { return false; }
 #endif
 
 }  // namespace fast

@@ -64,8 +64,10 @@ static RowGeom row_geom(int64_t M, int C, int blocks_per_sm) {
 }
 
 // ------------------------------------------------------------------------------------------- BN statistics
-// sums[0..C) += sum_rows x ; sums[C..2C) += sum_rows x^2      (sums pre-zeroed)
-__global__ void __launch_bounds__(320) bn_stats_kernel(const uint4* __restrict__ x, int64_t M, int tpr, int rpi, float* sums,
+// partial[blockIdx][0..C) = sum_rows x ; partial[blockIdx][C..2C) = sum_rows x^2 over this block's rows.
+// No atomics: same-address fp32 atomics from ~1000 blocks serialise in L2 (~95 us per launch measured); the
+// partials are reduced by col_finalize kernels -> deterministic results.
+__global__ void __launch_bounds__(320) bn_stats_kernel(const uint4* __restrict__ x, int64_t M, int tpr, int rpi, float* partial,
                                                        int C) {
   extern __shared__ float red[];  // [threads][16]
   const int t = threadIdx.x;
@@ -114,20 +116,52 @@ __global__ void __launch_bounds__(320) bn_stats_kernel(const uint4* __restrict__
         q[j] += red[(rr * tpr + t) * 16 + 8 + j];
       }
     }
+    float* dst = partial + (int64_t)blockIdx.x * 2 * C;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(sums + t * 8 + j, s[j]);
-      atomicAdd(sums + C + t * 8 + j, q[j]);
+      dst[t * 8 + j] = s[j];
+      dst[C + t * 8 + j] = q[j];
     }
   }
+}
+// sums[col] = sum_p partial[p][col] for col < 2C.  32 columns x 8 partial-lanes per block.
+__global__ void __launch_bounds__(256) col_finalize_kernel(const float* __restrict__ partial, int P, int C2, float* sums) {
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane8 = threadIdx.x >> 5;
+  __shared__ float red[8][33];
+  float a = 0.f;
+  if (col < C2)
+    for (int p = lane8; p < P; p += 8) a += partial[(int64_t)p * C2 + col];
+  red[lane8][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (lane8 == 0 && col < C2) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+    sums[col] = t;
+  }
+}
+static float* partial_buffer() {
+  static float* p = [] {
+    void* q = nullptr;
+    cudaMalloc(&q, sizeof(float) * (size_t)4096 * 2 * 2560);
+    return (float*)q;
+  }();
+  return p;
+}
+static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_stream_t s) {
+  col_finalize_kernel<<<(C2 + 31) / 32, 256, 0, s>>>(partial, P, C2, sums);
+  ++g_launches;
 }
 
 bool bn_stats_bf16(const bf16* x, int64_t M, int C, float* sums, lbc_stream_t s) {
   if (C % 8 || C > 2560) return false;
-  RowGeom g = row_geom(M, C, 8);
-  LBC_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s));
-  bn_stats_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>((const uint4*)x, M, g.tpr, g.rpi, sums, C);
+  RowGeom g = row_geom(M, C, 6);
+  float* part = partial_buffer();
+  if (!part) return false;
+  bn_stats_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>((const uint4*)x, M, g.tpr, g.rpi, part, C);
   ++g_launches;
+  col_finalize(part, g.grid, 2 * C, sums, s);
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -255,7 +289,7 @@ bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const flo
 __global__ void __launch_bounds__(320) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
                                                             const uint4* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, int64_t M, int tpr, int rpi,
-                                                            float* sums, int C) {
+                                                            float* partial, int C) {
   extern __shared__ float red[];
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
@@ -314,10 +348,11 @@ __global__ void __launch_bounds__(320) bn_bwd_reduce_kernel(const uint4* __restr
         s1[j] += red[(rr * tpr + t) * 16 + 8 + j];
       }
     }
+    float* dst = partial + (int64_t)blockIdx.x * 2 * C;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(sums + t * 8 + j, s0[j]);
-      atomicAdd(sums + C + t * 8 + j, s1[j]);
+      dst[t * 8 + j] = s0[j];
+      dst[C + t * 8 + j] = s1[j];
     }
   }
 }
@@ -386,10 +421,12 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
                  const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s) {
   if (C % 8 || C > 2560) return false;
   RowGeom g = row_geom(M, C, 6);
-  LBC_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s));
+  float* part = partial_buffer();
+  if (!part) return false;
   bn_bwd_reduce_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
-      (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, sums, C);
+      (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C);
   ++g_launches;
+  col_finalize(part, g.grid, 2 * C, sums, s);
   bn_bwd_apply_kernel<<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, gamma,
                                                   sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C);
   ++g_launches;

@@ -221,6 +221,7 @@ class Net : public NetBase {
         if (b.ds) {
           add_conv(b.name + ".downsample.0", C, planes, 1, stride, 0, H, W, b.cd);
           add_bn(b.name + ".downsample.1", planes, b.bd);
+          if (std::is_same<T, bf16>::value && stride == 2) b.c1.wcomb = alloc<T>((int64_t)C * 2 * planes);
         }
         int64_t ne = B * b.Hout * b.Wout * planes;
         b.r1 = alloc<T>(ne);
@@ -299,6 +300,7 @@ class Net : public NetBase {
       pk(b.c1);
       pk(b.c2);
       if (b.ds) pk(b.cd);
+      if (b.c1.wcomb) ref::pack_weight_comb<T>(s, P + b.c1.w_off, P + b.cd.w_off, (T*)b.c1.wcomb, b.c1.Co, b.c1.Ci);
     }
     for (int i = 0; i < 3; ++i) pk(dcv[i]);
   }
@@ -548,12 +550,20 @@ class Net : public NetBase {
       conv_backward_data(b.c2, tA, tB, B, false, s);   // tB = d a1 (before the ReLU mask a1 > 0)
       bn_backward(b.b1, tB, b.a1, b.r1, tA, M, s);     // tA = d r1
       conv_backward_weight(b.c1, b.xin, tA, B, s);
-      conv_backward_data(b.c1, tA, gnext, B, false, s);  // gnext = d xin (main path)
       if (b.ds) {
-        bn_backward(b.bd, gcur, b.out, b.rd, tA, M, s);  // tA = d rd
-        conv_backward_weight(b.cd, b.xin, tA, B, s);
-        conv_backward_data(b.cd, tA, gnext, B, true, s);
+        bn_backward(b.bd, gcur, b.out, b.rd, tB, M, s);  // tB = d rd (d a1 is dead by now)
+        conv_backward_weight(b.cd, b.xin, tB, B, s);
+        bool fused = false;
+        {
+          ProfScope ps("conv_dgrad", s, conv_flops(b.c1, B) + conv_flops(b.cd, B), 0);
+          fused = fast::conv_dgrad_ds<T>(b.c1, tA, tB, gnext, B, s);   // gnext = dgrad(conv1) + dgrad(downsample)
+        }
+        if (!fused) {
+          conv_backward_data(b.c1, tA, gnext, B, false, s);
+          conv_backward_data(b.cd, tB, gnext, B, true, s);
+        }
       } else {
+        conv_backward_data(b.c1, tA, gnext, B, false, s);  // gnext = d xin (main path)
         add_masked(gnext, gcur, b.out, ne, s);
       }
       std::swap(gcur, gnext);

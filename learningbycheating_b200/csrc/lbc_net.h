@@ -38,6 +38,7 @@ struct ConvL {
   bool deconv = false;
   void* wp = nullptr;   // packed [Co][K][K][Ci]  (GEMM B operand of the forward conv)
   void* wpt = nullptr;  // packed [Ci][K][K][Co]  (GEMM B operand of the data gradient / deconv forward)
+  void* wcomb = nullptr;  // block-entry 3x3/s2 conv only: [Ci][2*Co] = [centre tap of this conv | 1x1/s2 downsample]^T
 };
 struct BNL {
   int C = 0;

@@ -219,6 +219,18 @@ void pack_weight_t(lbc_stream_t s, const float* w_ref, T* w_packed, int Co, int 
   });
 }
 
+// block-entry combined pack: wcomb[ci][k], k < Co: centre tap of the 3x3 conv W1[k][ci][1][1]; k >= Co: Wd[k-Co][ci]
+template <class T>
+void pack_weight_comb(lbc_stream_t s, const float* w1_ref, const float* wd_ref, T* wcomb, int Co, int Ci) {
+  int64_t n = (int64_t)Ci * 2 * Co;
+  par_for<k_pack_w>(s, n, [=] LBC_LAMBDA(int64_t i) {
+    int k = (int)(i % (2 * Co));
+    int ci = (int)(i / (2 * Co));
+    float v = k < Co ? w1_ref[(((int64_t)k * Ci + ci) * 3 + 1) * 3 + 1] : wd_ref[(int64_t)(k - Co) * Ci + ci];
+    stf(wcomb, i, v);
+  });
+}
+
 // ---------------------------------------------------------------------------------------------
 // BatchNorm2d, train mode (torch BN as constructed at resnet.py:104, image.py:38,56)
 // column statistics over M rows of C channels.  ws: >= 2*P*C doubles.
