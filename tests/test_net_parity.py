@@ -142,45 +142,55 @@ def test_student_step_gpu_bf16_deviation(backend, fast):
         _lib.check(_lib.lib().lbc_set_fast_kernels(1))
 
 
+def _grads_with_fixed_upstream(precision, fast, B=4):
+    """forward + backward with a FIXED upstream gradient (no sign() discontinuity of the L1 loss in the way)."""
+    import learningbycheating_b200 as lbc
+    from learningbycheating_b200 import _lib
+    _lib.check(_lib.lib().lbc_set_fast_kernels(fast))
+    try:
+        s, _ = build_models("cuda", precision)
+        s.train()
+        b = batch_on("cuda", B)
+        oh = lbc.one_hot(b["command"].cpu()).to("cuda")
+        pred, preds = s(b["rgb"], b["speed"], oh)
+        g = torch.Generator().manual_seed(5)
+        r1 = torch.randn(pred.shape, generator=g).cuda()
+        r2 = torch.randn(preds.shape, generator=g).cuda()
+        torch.autograd.backward([pred, preds], [r1, r2])
+        return pred.detach().cpu(), {k: p.grad.detach().clone().cpu() for k, p in s.named_parameters() if p.grad is not None}
+    finally:
+        _lib.check(_lib.lib().lbc_set_fast_kernels(1))
+
+
 @pytest.mark.gpu
 def test_bf16_fast_kernels_match_correctness_first_kernels_gpu(backend):
-    """Same bf16 step through the tcgen05 / fused kernels and through the correctness-first kernels: every
-    parameter gradient must agree to bf16 noise (an indexing bug in any fast kernel gives O(1) differences)."""
-    from learningbycheating_b200 import _lib
-    recs = {}
-    for fast in (0, 1):
-        _lib.check(_lib.lib().lbc_set_fast_kernels(fast))
-        try:
-            _, _, r = run_student_steps("cuda", "bf16", 4, 0, 1)
-        finally:
-            _lib.check(_lib.lib().lbc_set_fast_kernels(1))
-        recs[fast] = r[0]
-    assert rel_err(recs[1]["pred"], recs[0]["pred"]) < 0.2
-    # BatchNorm gamma/beta gradients are sums of (by construction) zero-mean bf16 tensors: in bf16 storage they are
-    # rounding-noise dominated at B=4 in BOTH kernel families (measured ~100% vs the fp32 golden, see DESIGN.md
-    # "bf16 mode"), so the kernel-vs-kernel check uses the convolution / deconvolution weight gradients, and
-    # measures each family against the fp32 golden.
-    g = gold("student_B4_phase0.npz")
+    """Same bf16 step through the tcgen05 / fused kernels and through the correctness-first kernels, and the fp32
+    parity path as the yardstick: an indexing bug in any fast kernel gives O(1) differences, bf16 rounding does not."""
+    p32, g32 = _grads_with_fixed_upstream("fp32", 1)
+    p0, g0 = _grads_with_fixed_upstream("bf16", 0)
+    p1, g1 = _grads_with_fixed_upstream("bf16", 1)
+    print("pred deviation vs fp32: correctness-first bf16 %.3e, fast bf16 %.3e" % (rel_err(p0, p32), rel_err(p1, p32)))
     rows = []
-    for k, g0 in recs[0]["grads"].items():
-        g1 = recs[1]["grads"][k]
-        if g0 is None:
-            assert g1 is None
+    for k, ref in g32.items():
+        n = float(ref.double().norm())
+        if n < 1e-6:
             continue
-        if g0.dim() != 4 or k.startswith("location_pred"):
-            continue
-        n0 = float(g0.double().norm())
-        e01 = float((g1.double() - g0.double()).norm()) / n0
-        cos = float((g1.double() * g0.double()).sum()) / (n0 * float(g1.double().norm()))
-        rows.append((e01, cos, k))
+        e0 = float((g0[k].double() - ref.double()).norm()) / n
+        e1 = float((g1[k].double() - ref.double()).norm()) / n
+        rows.append((e1, e0, k))
     rows.sort(reverse=True)
-    print("conv-weight gradients, fast vs correctness-first kernels (bf16): worst rel diff / cosine:", rows[:4])
-    assert len(rows) == 39
-    assert all(c > 0.9 for _, c, _ in rows), rows[:4]
-    ref_l2 = float(g["step0/grad_global_l2"])
-    for fast in (0, 1):
-        l2 = sum(float(v.double().norm()) ** 2 for v in recs[fast]["grads"].values() if v is not None) ** 0.5
-        assert abs(l2 - ref_l2) < 0.1 * ref_l2
+    print("per-tensor gradient error vs fp32 (fast bf16, correctness-first bf16, name), worst 6:")
+    for r in rows[:6]:
+        print("   %.3f %.3f %s" % r)
+    import statistics
+    med1 = statistics.median(r[0] for r in rows)
+    med0 = statistics.median(r[1] for r in rows)
+    print("median error: fast %.4f correctness-first %.4f" % (med1, med0))
+    # Both bf16 kernel families sit at the SAME distance from fp32: that distance is the bf16 *storage* noise of this
+    # ill-conditioned graph at random init and B=4 (DESIGN.md "bf16 mode: measured deviation"), not a kernel property.
+    assert med1 < 1.25 * med0 + 0.05
+    assert rows[0][0] < 1.5 * max(r[1] for r in rows) + 0.1
+    assert rel_err(p1, p32) < 1.5 * rel_err(p0, p32) + 0.05
 
 
 @pytest.mark.gpu
