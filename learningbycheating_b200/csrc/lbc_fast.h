@@ -14,17 +14,17 @@ namespace fast {
 bool enabled();
 void set_enabled(bool on);
 
-bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s);
+bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s);
 
 template <class T>
-inline bool conv_fwd(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s) {
-  (void)c; (void)x; (void)y; (void)B; (void)s;
+inline bool conv_fwd(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s, const float* bias_co = nullptr) {
+  (void)c; (void)x; (void)y; (void)B; (void)s; (void)bias_co;
   return false;
 }
 template <>
-inline bool conv_fwd<bf16>(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s) {
+inline bool conv_fwd<bf16>(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s, const float* bias_co) {
   if (!enabled()) return false;
-  return conv_fwd_bf16(c, x, y, B, s);
+  return conv_fwd_bf16(c, x, y, B, bias_co, s);
 }
 
 bool conv_dgrad_bf16(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu, lbc_stream_t s);
@@ -68,7 +68,7 @@ inline bool conv_wgrad<bf16>(const ConvL& c, const bf16* x, const bf16* dy, floa
 bool bn_stats_bf16(const bf16* x, int64_t M, int C, float* sums, lbc_stream_t s);
 bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
-                   const bf16* residual, bool relu, bool train, bf16* y, lbc_stream_t s);
+                   const bf16* residual, bool relu, bool train, bf16* y, float* negshift, lbc_stream_t s);
 bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
                  const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s);
 bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s);
@@ -81,7 +81,7 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
 // generic-T front ends: only T = bf16 has fast kernels
 template <class T> struct Fast {
   static bool bn_fwd(const T*, int64_t, int, const float*, const float*, float, float, float*, float*, float*, float*,
-                     const T*, bool, bool, T*, float*, lbc_stream_t) { return false; }
+                     const T*, bool, bool, T*, float*, float*, lbc_stream_t) { return false; }
   static bool bn_bwd(const T*, const T*, const T*, const float*, const float*, const float*, float*, float*, T*, int64_t, int,
                      float*, lbc_stream_t) { return false; }
   static bool ew(T*, const T*, const T*, int64_t, int, lbc_stream_t) { return false; }
@@ -95,10 +95,11 @@ template <> struct Fast<bf16> {
   // train: statistics + apply (two launches); eval: apply with the running statistics.  sums: >= 2C floats scratch
   static bool bn_fwd(const bf16* x, int64_t M, int C, const float* gamma, const float* beta, float eps, float momentum,
                      float* rm, float* rv, float* saved_mean, float* saved_rstd, const bf16* res, bool relu, bool train,
-                     bf16* y, float* sums, lbc_stream_t s) {
+                     bf16* y, float* sums, float* negshift, lbc_stream_t s) {
     if (!enabled()) return false;
     if (train && !bn_stats_bf16(x, M, C, sums, s)) return false;
-    return bn_apply_bf16(x, sums, M, C, gamma, beta, eps, momentum, rm, rv, saved_mean, saved_rstd, res, relu, train, y, s);
+    return bn_apply_bf16(x, sums, M, C, gamma, beta, eps, momentum, rm, rv, saved_mean, saved_rstd, res, relu, train, y,
+                         negshift, s);
   }
   static bool bn_bwd(const bf16* dy, const bf16* mask, const bf16* x, const float* mean, const float* rstd, const float* gamma,
                      float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s) {

@@ -440,7 +440,7 @@ static bool supported(const ConvL& c) {
 }
 
 // y = conv(x, w):  x [B,H,W,Ci], packed weights [Co][K*K][Ci], y [B,OH,OW,Co]
-bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s) {
+bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s) {
   if (!supported(c)) return false;
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -449,6 +449,7 @@ bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s
   p.n_tiles_n = c.Co / BN;
   p.num_taps = c.K * c.K;
   p.k_chunks = c.Ci / 64;
+  p.bias = bias_co;   // per-output-channel constant added before the bf16 rounding (centring shift, see lbc_net.cu)
   CUtensorMap mA[4];
   const int64_t eb = 2;
   if (c.stride == 1) {
@@ -845,7 +846,7 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
 }
 
 #else   // LBC_HOST_EMU: no tensor cores on the host; the executor runs the correctness-first kernels
-bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, lbc_stream_t) { return false; }
+bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, const float*, lbc_stream_t) { return false; }
 bool conv_dgrad_bf16(const ConvL&, const bf16*, bf16*, int, const float*, bool, lbc_stream_t) { return false; }
 bool conv_wgrad_bf16(const ConvL&, const bf16*, const bf16*, float*, int, float*, int64_t, lbc_stream_t) { return false; }
 bool conv_dgrad_ds_bf16(const ConvL&, const bf16*, const bf16*, bf16*, int, lbc_stream_t) { return false; }

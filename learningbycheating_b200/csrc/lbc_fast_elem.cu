@@ -178,6 +178,7 @@ struct BnApplyArgs {
   float* running_var;
   float* saved_mean;
   float* saved_rstd;
+  float* negshift;     // x holds (conv output + negshift[c]); null = no centring shift
   int64_t M;
   int C, tpr, rpi;
   float eps, momentum;
@@ -200,12 +201,14 @@ __global__ void __launch_bounds__(320) bn_apply_kernel(const BnApplyArgs a) {
       if (blockIdx.x == 0 && r == 0) {
         a.saved_mean[c] = mean;
         a.saved_rstd[c] = rstd;
-        a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * mean;
+        const float true_mean = a.negshift ? (float)(m - (double)a.negshift[c]) : mean;
+        if (a.negshift) a.negshift[c] = -true_mean;   // centring estimate for the next forward pass
+        a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * true_mean;
         double unb = var * ((double)a.M / (double)(a.M > 1 ? a.M - 1 : 1));
         a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unb;
       }
     } else {
-      mean = a.running_mean[c];
+      mean = a.running_mean[c] + (a.negshift ? a.negshift[c] : 0.f);
       rstd = 1.0f / sqrtf(a.running_var[c] + a.eps);
       if (blockIdx.x == 0 && r == 0) {
         a.saved_mean[c] = mean;
@@ -256,10 +259,11 @@ __global__ void __launch_bounds__(320) bn_apply_kernel(const BnApplyArgs a) {
 
 bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
-                   const bf16* residual, bool relu, bool train, bf16* y, lbc_stream_t s) {
+                   const bf16* residual, bool relu, bool train, bf16* y, float* negshift, lbc_stream_t s) {
   if (C % 8 || C > 2560) return false;
   RowGeom g = row_geom(M, C, 8);
   BnApplyArgs a;
+  a.negshift = negshift;
   a.x = (const uint4*)x;
   a.res = (const uint4*)residual;
   a.y = (uint4*)y;
@@ -607,7 +611,7 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
 #else  // LBC_HOST_EMU
 bool bn_stats_bf16(const bf16*, int64_t, int, float*, lbc_stream_t) { return false; }
 bool bn_apply_bf16(const bf16*, const float*, int64_t, int, const float*, const float*, float, float, float*, float*, float*,
-                   float*, const bf16*, bool, bool, bf16*, lbc_stream_t) { return false; }
+                   float*, const bf16*, bool, bool, bf16*, float*, lbc_stream_t) { return false; }
 bool bn_bwd_bf16(const bf16*, const bf16*, const bf16*, const float*, const float*, const float*, float*, float*, bf16*,
                  int64_t, int, float*, lbc_stream_t) { return false; }
 bool ew_bf16(bf16*, const bf16*, const bf16*, int64_t, int, lbc_stream_t) { return false; }

@@ -67,6 +67,8 @@ class Net : public NetBase {
   int64_t ws_f_n = 0;
   double* ws_d = nullptr;
   float* bn_sums = nullptr;  // 2*C floats scratch of the fast BN kernels
+  float* negshift_all = nullptr;  // [n_buffers] (indexed like the running_mean entries)
+  std::vector<BNL*> conv_bns;     // BNs fed directly by a trunk convolution
   float* head_fold = nullptr;  // folded BN+1x1 map A[20][64], b'[20]; coef c0/c1 [128]
   bool head_fast_used = false;
   bool head_mask_fused = false;
@@ -283,6 +285,16 @@ class Net : public NetBase {
     if (B * 20 * 65 + 4096 > wd) wd = B * 20 * 65 + 4096;
     ws_d = alloc<double>(wd);
     bn_sums = alloc<float>(2 * 1024);
+    if (std::is_same<T, bf16>::value) {
+      negshift_all = alloc<float>(n_buffers);
+      dev_memset(negshift_all, 0, sizeof(float) * n_buffers, (lbc_stream_t)0);
+      stem_bn.negshift = negshift_all + stem_bn.rm_off;
+      for (Block& b : blocks) {
+        b.b1.negshift = negshift_all + b.b1.rm_off;
+        b.b2.negshift = negshift_all + b.b2.rm_off;
+        if (b.ds) b.bd.negshift = negshift_all + b.bd.rm_off;
+      }
+    }
     head_fold = alloc<float>(1300 + 128 + 28);
   }
 
@@ -307,11 +319,13 @@ class Net : public NetBase {
   static double conv_flops(const ConvL& c, int B) {
     return 2.0 * B * c.OH * c.OW * (double)c.Co * c.K * c.K * c.Ci;
   }
-  void conv_forward(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s) {
+  // returns true when the per-channel centring shift `negshift` was added to the stored output (fast path only)
+  bool conv_forward(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s, const float* negshift = nullptr) {
     ProfScope ps("conv_fwd", s, conv_flops(c, B), 0);
-    if (fast::conv_fwd<T>(c, x, y, B, s)) return;
+    if (fast::conv_fwd<T>(c, x, y, B, s, negshift)) return negshift != nullptr;
     ref::conv_fwd<T>(s, x, (const T*)c.wp, nullptr, false, y, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
                      c.OW);
+    return false;
   }
   void conv_backward_data(const ConvL& c, const T* dy, T* dx, int B, bool accumulate, lbc_stream_t s) {
     ProfScope ps("conv_dgrad", s, conv_flops(c, B), 0);
@@ -324,12 +338,14 @@ class Net : public NetBase {
     if (fast::conv_wgrad<T>(c, x, dy, G + c.w_off, B, ws_f, ws_f_n, s)) return;
     ref::conv_wgrad<T>(s, x, dy, G + c.w_off, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, ws_f, ws_f_n);
   }
-  void bn_forward(BNL& bn, const T* x, int64_t M, const T* residual, bool relu, T* y, bool train, lbc_stream_t s) {
+  void bn_forward(BNL& bn, const T* x, int64_t M, const T* residual, bool relu, T* y, bool train, lbc_stream_t s,
+                  bool shifted = false) {
     // algorithmic bytes: stats read (train) + apply read (+residual) + write
     ProfScope ps("bn_fwd", s, 0, (double)M * bn.C * sizeof(T) * ((train ? 1 : 0) + 2 + (residual ? 1 : 0)));
     if (fast::Fast<T>::bn_fwd(x, M, bn.C, P + bn.g_off, P + bn.b_off, kBnEps, kBnMomentum, BUF + bn.rm_off, BUF + bn.rv_off,
-                              bn.mean, bn.rstd, residual, relu, train, y, bn_sums, s))
+                              bn.mean, bn.rstd, residual, relu, train, y, bn_sums, shifted ? bn.negshift : nullptr, s))
       return;
+    LBC_CHECK(!shifted, "BatchNorm fast path unavailable after a shifted convolution");
     if (train) {
       ref::bn_stats<T>(s, x, M, bn.C, bn.mean, bn.var, ws_d);
       ref::bn_finalize(s, bn.mean, bn.var, bn.C, M, kBnEps, kBnMomentum, bn.rstd, BUF + bn.rm_off, BUF + bn.rv_off);
@@ -383,12 +399,13 @@ class Net : public NetBase {
     pack_weights(s);
     dev_copy(onehot_saved, onehot, sizeof(float) * B * 4, s);
     dev_copy(speed_saved, speed, sizeof(float) * B, s);
+    if (!train && negshift_all && fast::enabled()) ref::negate_into(s, BUF, negshift_all, n_buffers);  // centre on running_mean
     // stem
     stem_fast_used = false;
     if (std::is_same<T, bf16>::value) {
       ProfScope ps("conv_fwd", s, conv_flops(stem, B), 0);
       if (fast::stem_im2col_bf16(image, (bf16*)stem_col, B, in_ch, in_h, in_w, stem_oh, stem_ow, stem_gemm.Ci, normalize, s))
-        stem_fast_used = fast::conv_fwd<T>(stem_gemm, stem_col, r_stem, B, s);
+        stem_fast_used = fast::conv_fwd<T>(stem_gemm, stem_col, r_stem, B, s, stem_bn.negshift);
     }
     if (!stem_fast_used) {
       ref::input_to_nhwc<T>(s, image, x0, B, in_ch, in_h, in_w, in_ch, normalize, 0.485f, 0.456f, 0.406f, 0.229f,
@@ -406,10 +423,11 @@ class Net : public NetBase {
           ok = fast::bn_stats_bf16((const bf16*)r_stem, Ms, 64, bn_sums, s);
           if (ok) {
             ref::bn_finalize_sums(s, bn_sums, 64, Ms, kBnEps, kBnMomentum, stem_bn.mean, stem_bn.rstd, BUF + stem_bn.rm_off,
-                                  BUF + stem_bn.rv_off);
+                                  BUF + stem_bn.rv_off, stem_fast_used ? stem_bn.negshift : nullptr);
           }
         } else {
-          ref::bn_eval_stats(s, BUF + stem_bn.rm_off, BUF + stem_bn.rv_off, 64, kBnEps, stem_bn.mean, stem_bn.rstd);
+          ref::bn_eval_stats(s, BUF + stem_bn.rm_off, BUF + stem_bn.rv_off, 64, kBnEps, stem_bn.mean, stem_bn.rstd,
+                             stem_fast_used ? stem_bn.negshift : nullptr);
         }
         if (ok)
           stem_pool_fused = fast::Fast<T>::pool_fwd(r_stem, stem_bn.mean, stem_bn.rstd, P + stem_bn.g_off, P + stem_bn.b_off,
@@ -425,16 +443,16 @@ class Net : public NetBase {
     // residual blocks
     for (Block& b : blocks) {
       int64_t M = (int64_t)B * b.Hout * b.Wout;
-      conv_forward(b.c1, b.xin, b.r1, B, s);
-      bn_forward(b.b1, b.r1, M, nullptr, true, b.a1, train, s);
-      conv_forward(b.c2, b.a1, b.r2, B, s);
+      bool sh1 = conv_forward(b.c1, b.xin, b.r1, B, s, b.b1.negshift);
+      bn_forward(b.b1, b.r1, M, nullptr, true, b.a1, train, s, sh1);
+      bool sh2 = conv_forward(b.c2, b.a1, b.r2, B, s, b.b2.negshift);
       const T* identity = b.xin;
       if (b.ds) {
-        conv_forward(b.cd, b.xin, b.rd, B, s);
-        bn_forward(b.bd, b.rd, M, nullptr, false, b.idn, train, s);
+        bool shd = conv_forward(b.cd, b.xin, b.rd, B, s, b.bd.negshift);
+        bn_forward(b.bd, b.rd, M, nullptr, false, b.idn, train, s, shd);
         identity = b.idn;
       }
-      bn_forward(b.b2, b.r2, M, identity, true, b.out, train, s);
+      bn_forward(b.b2, b.r2, M, identity, true, b.out, train, s, sh2);
     }
     // late fusion of speed (image.py:77-79)
     const T* trunk = blocks.back().out;

@@ -44,6 +44,9 @@ struct BNL {
   int C = 0;
   int64_t g_off = -1, b_off = -1, rm_off = -1, rv_off = -1;
   float *mean = nullptr, *var = nullptr, *rstd = nullptr;  // saved batch statistics
+  // bf16 path: the conv feeding this BN stores (output + negshift[c]) so that the bf16 rounding acts on a centred
+  // tensor; negshift = -(previous batch mean) (train) or -running_mean (eval).  See DESIGN.md "centring shift".
+  float* negshift = nullptr;
 };
 
 class NetBase {

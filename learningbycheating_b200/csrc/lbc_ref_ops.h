@@ -18,7 +18,10 @@ struct k_maxpool_bwd; struct k_relu_mask; struct k_add; struct k_bn_bwd_part; st
 struct k_bn_bwd_apply; struct k_concat_speed; struct k_slice; struct k_colsum_part; struct k_head_logits;
 struct k_head_softmax; struct k_head_select; struct k_head_dlogits; struct k_head_s_part; struct k_head_param_grads;
 struct k_head_dh; struct k_pack_w; struct k_adam; struct k_l1_loss; struct k_phase0_target; struct k_phase1_fwd;
-struct k_phase1_bwd; struct k_cast; struct k_speed_stats; struct k_scale;
+struct k_phase1_bwd; struct k_cast; struct k_speed_stats; struct k_scale; struct k_negate;
+inline void negate_into(lbc_stream_t s, const float* src, float* dst, int64_t n) {
+  par_for<k_negate>(s, n, [=] LBC_LAMBDA(int64_t i) { dst[i] = -src[i]; });
+}
 
 // accumulator type: double for the fp32 parity path (the CPU oracle's blocked GEMMs / double-accumulating
 // reductions are far more accurate than a sequential fp32 sum), float for bf16 storage
@@ -298,22 +301,24 @@ inline void bn_finalize(lbc_stream_t s, const float* mean, const float* var_bias
 }
 // same from (sum, sum of squares) accumulated by the fast statistics kernel
 inline void bn_finalize_sums(lbc_stream_t s, const float* sums, int C, int64_t M, float eps, float momentum, float* mean,
-                             float* rstd, float* running_mean, float* running_var) {
+                             float* rstd, float* running_mean, float* running_var, float* negshift = nullptr) {
   par_for<k_bn_finalize>(s, C, [=] LBC_LAMBDA(int64_t c) {
     double m = (double)sums[c] / (double)M;
     double var = (double)sums[C + c] / (double)M - m * m;
     if (var < 0.0) var = 0.0;
     mean[c] = (float)m;
     rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    double true_mean = negshift ? m - (double)negshift[c] : m;   // statistics were taken on (x + negshift)
+    if (negshift) negshift[c] = -(float)true_mean;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)true_mean;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * ((double)M / (double)(M > 1 ? M - 1 : 1)));
   });
 }
 // eval mode: mean = running_mean, rstd from running_var
 inline void bn_eval_stats(lbc_stream_t s, const float* running_mean, const float* running_var, int C, float eps,
-                          float* mean, float* rstd) {
+                          float* mean, float* rstd, const float* negshift = nullptr) {
   par_for<k_bn_finalize>(s, C, [=] LBC_LAMBDA(int64_t c) {
-    mean[c] = running_mean[c];
+    mean[c] = running_mean[c] + (negshift ? negshift[c] : 0.f);
     rstd[c] = 1.0f / sqrtf(running_var[c] + eps);
   });
 }

@@ -152,6 +152,8 @@ def _grads_with_fixed_upstream(precision, fast, B=4):
         s.train()
         b = batch_on("cuda", B)
         oh = lbc.one_hot(b["command"].cpu()).to("cuda")
+        with torch.no_grad():
+            s(b["rgb"], b["speed"], oh)     # warm-up pass: populates the bf16 path's per-channel centring estimates
         pred, preds = s(b["rgb"], b["speed"], oh)
         g = torch.Generator().manual_seed(5)
         r1 = torch.randn(pred.shape, generator=g).cuda()
