@@ -26,7 +26,8 @@ struct k_stem_unpack;
 // staged in shared memory and written back as one contiguous 64*Kp*2-byte run with 16-byte stores.
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, uint4* __restrict__ col, int C, int H,
                                                           int W, int OH, int OW, int Kp, int normalize) {
-  extern __shared__ uint16_t tile[];  // [64][Kp]
+  extern __shared__ uint16_t tile[];  // [64][Kp + 2]: odd word stride -> lanes (positions) hit distinct banks
+  const int KS = Kp + 2;
   const int segs = OW / 64;
   int blk = blockIdx.x;
   const int seg = blk % segs;
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   // zero the K padding
   for (int i = threadIdx.x; i < 64 * (Kp - KT); i += 256) {
     int pos = i / (Kp - KT), k = KT + i % (Kp - KT);
-    tile[pos * Kp + k] = 0;
+    tile[pos * KS + k] = 0;
   }
   const int pos = threadIdx.x & 63;
   const int ow = ow0 + pos;
@@ -59,14 +60,19 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
         v = __ldg(rowp + iw);
         if (normalize) v = (v - mean) / (c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f));
       }
-      tile[pos * Kp + (kh * 7 + kw) * C + c] = float_to_bf16(v).v;
+      tile[pos * KS + (kh * 7 + kw) * C + c] = float_to_bf16(v).v;
     }
   }
 
   __syncthreads();
-  const int64_t base = (((int64_t)b * OH + oh) * OW + ow0) * Kp / 8;  // in uint4 units
-  const uint4* t4 = reinterpret_cast<const uint4*>(tile);
-  for (int i = threadIdx.x; i < 64 * Kp / 8; i += 256) col[base + i] = t4[i];
+  const int64_t base = (((int64_t)b * OH + oh) * OW + ow0) * Kp / 2;  // in 32-bit words
+  const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
+  uint32_t* out32 = reinterpret_cast<uint32_t*>(col);
+  const int wpr = Kp / 2;
+  for (int i = threadIdx.x; i < 64 * wpr; i += 256) {
+    const int r = i / wpr, w = i - r * wpr;
+    out32[base + i] = t32[r * (KS / 2) + w];
+  }
 }
 
 bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, int OH, int OW, int Kp, bool normalize,
@@ -74,12 +80,12 @@ bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, i
   if (!enabled()) return false;
   if (OW % 64 == 0 && Kp % 8 == 0) {
     static bool configured = false;
-    const int smem = 64 * Kp * 2;
+    const int smem = 64 * (Kp + 2) * 2;
     if (!configured) {
-      LBC_CUDA(cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 512 * 2));
+      LBC_CUDA(cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 514 * 2));
       configured = true;
     }
-    if (smem <= 64 * 512 * 2) {
+    if (smem <= 64 * 514 * 2) {
       stem_im2col_kernel<<<B * OH * (OW / 64), 256, smem, s>>>(img, (uint4*)col, C, H, W, OH, OW, Kp, normalize ? 1 : 0);
       ++g_launches;
       LBC_CUDA(cudaGetLastError());

@@ -124,20 +124,20 @@ __global__ void __launch_bounds__(320) bn_stats_kernel(const uint4* __restrict__
     }
   }
 }
-// sums[col] = sum_p partial[p][col] for col < 2C.  32 columns x 8 partial-lanes per block.
-__global__ void __launch_bounds__(256) col_finalize_kernel(const float* __restrict__ partial, int P, int C2, float* sums) {
+// sums[col] = sum_p partial[p][col] for col < 2C.  32 columns x 32 partial-lanes per block (1024 threads).
+__global__ void __launch_bounds__(1024) col_finalize_kernel(const float* __restrict__ partial, int P, int C2, float* sums) {
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int lane8 = threadIdx.x >> 5;
-  __shared__ float red[8][33];
+  const int pl = threadIdx.x >> 5;
+  __shared__ float red[32][33];
   float a = 0.f;
   if (col < C2)
-    for (int p = lane8; p < P; p += 8) a += partial[(int64_t)p * C2 + col];
-  red[lane8][threadIdx.x & 31] = a;
+    for (int p = pl; p < P; p += 32) a += partial[(int64_t)p * C2 + col];
+  red[pl][threadIdx.x & 31] = a;
   __syncthreads();
-  if (lane8 == 0 && col < C2) {
+  if (pl == 0 && col < C2) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+    for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x & 31];
     sums[col] = t;
   }
 }
@@ -150,7 +150,7 @@ static float* partial_buffer() {
   return p;
 }
 static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_stream_t s) {
-  col_finalize_kernel<<<(C2 + 31) / 32, 256, 0, s>>>(partial, P, C2, sums);
+  col_finalize_kernel<<<(C2 + 31) / 32, 1024, 0, s>>>(partial, P, C2, sums);
   ++g_launches;
 }
 

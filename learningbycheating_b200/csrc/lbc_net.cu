@@ -68,6 +68,8 @@ class Net : public NetBase {
   double* ws_d = nullptr;
   float* bn_sums = nullptr;  // 2*C floats scratch of the fast BN kernels
   float* negshift_all = nullptr;  // [n_buffers] (indexed like the running_mean entries)
+  std::vector<ref::PackEntry> pack_host;
+  ref::PackEntry* pack_dev = nullptr;
   std::vector<BNL*> conv_bns;     // BNs fed directly by a trunk convolution
   float* head_fold = nullptr;  // folded BN+1x1 map A[20][64], b'[20]; coef c0/c1 [128]
   bool head_fast_used = false;
@@ -295,26 +297,72 @@ class Net : public NetBase {
         if (b.ds) b.bd.negshift = negshift_all + b.bd.rm_off;
       }
     }
+    // weight-pack table (one launch per forward)
+    auto add_pack = [&](const ConvL& c, bool with_t) {
+      ref::PackEntry e;
+      e.src_off = c.w_off;
+      e.src2_off = 0;
+      e.dst = c.wp;
+      e.type = 0;
+      e.Co = c.Co;
+      e.Ci = c.Ci;
+      e.K = c.K;
+      e.aux = 0;
+      e.n = (int64_t)c.Co * c.K * c.K * c.Ci;
+      pack_host.push_back(e);
+      if (with_t) {
+        e.dst = c.wpt;
+        e.type = 1;
+        pack_host.push_back(e);
+      }
+    };
+    const bool is_bf16 = std::is_same<T, bf16>::value;
+    add_pack(stem, false);
+    for (Block& b : blocks) {
+      add_pack(b.c1, is_bf16);
+      add_pack(b.c2, is_bf16);
+      if (b.ds) add_pack(b.cd, is_bf16);
+      if (b.c1.wcomb) {
+        ref::PackEntry e;
+        e.src_off = b.c1.w_off;
+        e.src2_off = b.cd.w_off;
+        e.dst = b.c1.wcomb;
+        e.type = 2;
+        e.Co = b.c1.Co;
+        e.Ci = b.c1.Ci;
+        e.K = 3;
+        e.aux = 0;
+        e.n = (int64_t)b.c1.Ci * 2 * b.c1.Co;
+        pack_host.push_back(e);
+      }
+    }
+    for (int i = 0; i < 3; ++i) add_pack(dcv[i], is_bf16);
+    if (is_bf16) {
+      ref::PackEntry e;
+      e.src_off = stem.w_off;
+      e.src2_off = 0;
+      e.dst = stem_gemm.wp;
+      e.type = 3;
+      e.Co = 64;
+      e.Ci = in_ch;
+      e.K = 7;
+      e.aux = stem_gemm.Ci;
+      e.n = (int64_t)64 * stem_gemm.Ci;
+      pack_host.push_back(e);
+    }
+    pack_dev = alloc<ref::PackEntry>((int64_t)pack_host.size());
+#ifdef LBC_HOST_EMU
+    memcpy(pack_dev, pack_host.data(), sizeof(ref::PackEntry) * pack_host.size());
+#else
+    LBC_CUDA(cudaMemcpy(pack_dev, pack_host.data(), sizeof(ref::PackEntry) * pack_host.size(), cudaMemcpyHostToDevice));
+#endif
     head_fold = alloc<float>(1300 + 128 + 28);
   }
 
   // ------------------------------------------------------------------ op wrappers (fast-path hooks)
   void pack_weights(lbc_stream_t s) {
     ProfScope ps("pack", s, 0, 0);
-    auto pk = [&](ConvL& c) {
-      ref::pack_weight<T>(s, P + c.w_off, (T*)c.wp, c.Co, c.Ci, c.K);
-      if (std::is_same<T, bf16>::value && &c != &stem) ref::pack_weight_t<T>(s, P + c.w_off, (T*)c.wpt, c.Co, c.Ci, c.K);
-    };
-    pk(stem);
-    if (std::is_same<T, bf16>::value)
-      fast::stem_pack_weight_bf16(P + stem.w_off, (bf16*)stem_gemm.wp, in_ch, stem_gemm.Ci, s);
-    for (Block& b : blocks) {
-      pk(b.c1);
-      pk(b.c2);
-      if (b.ds) pk(b.cd);
-      if (b.c1.wcomb) ref::pack_weight_comb<T>(s, P + b.c1.w_off, P + b.cd.w_off, (T*)b.c1.wcomb, b.c1.Co, b.c1.Ci);
-    }
-    for (int i = 0; i < 3; ++i) pk(dcv[i]);
+    ref::pack_all<T>(s, P, pack_dev, (int)pack_host.size());
   }
   static double conv_flops(const ConvL& c, int B) {
     return 2.0 * B * c.OH * c.OW * (double)c.Co * c.K * c.K * c.Ci;

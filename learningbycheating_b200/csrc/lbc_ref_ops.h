@@ -234,6 +234,60 @@ void pack_weight_comb(lbc_stream_t s, const float* w1_ref, const float* wd_ref, 
   });
 }
 
+// all weight packs of a network in ONE launch (table-driven; replaces ~230 tiny launches per step)
+//   type 0: [Co][Ci][K][K] -> [Co][K][K][Ci]      type 1: -> [Ci][K][K][Co] (transposed)
+//   type 2: block-entry combined [Ci][2Co]        type 3: stem [64][C][7][7] -> [64][Kp] (k = tap*C + c, zero padded)
+struct PackEntry {
+  int64_t src_off, src2_off;
+  void* dst;
+  int type, Co, Ci, K, aux;
+  int64_t n;
+};
+struct k_pack_all;
+template <class T>
+void pack_all(lbc_stream_t s, const float* P, const PackEntry* table, int n_entries) {
+  const int64_t LANES = 32768;
+  par_for<k_pack_all>(s, (int64_t)n_entries * LANES, [=] LBC_LAMBDA(int64_t t) {
+    const PackEntry e = table[t / LANES];
+    const float* src = P + e.src_off;
+    T* dst = (T*)e.dst;
+    for (int64_t i = t % LANES; i < e.n; i += LANES) {
+      float v;
+      if (e.type == 0) {
+        int ci = (int)(i % e.Ci);
+        int64_t r = i / e.Ci;
+        int kw = (int)(r % e.K);
+        r /= e.K;
+        int kh = (int)(r % e.K);
+        int co = (int)(r / e.K);
+        v = src[(((int64_t)co * e.Ci + ci) * e.K + kh) * e.K + kw];
+      } else if (e.type == 1) {
+        int co = (int)(i % e.Co);
+        int64_t r = i / e.Co;
+        int kw = (int)(r % e.K);
+        r /= e.K;
+        int kh = (int)(r % e.K);
+        int ci = (int)(r / e.K);
+        v = src[(((int64_t)co * e.Ci + ci) * e.K + kh) * e.K + kw];
+      } else if (e.type == 2) {
+        int k = (int)(i % (2 * e.Co));
+        int ci = (int)(i / (2 * e.Co));
+        v = k < e.Co ? src[(((int64_t)k * e.Ci + ci) * 3 + 1) * 3 + 1] : (P + e.src2_off)[(int64_t)(k - e.Co) * e.Ci + ci];
+      } else {
+        int Kp = e.aux, C = e.Ci;
+        int k = (int)(i % Kp);
+        int co = (int)(i / Kp);
+        v = 0.f;
+        if (k < 49 * C) {
+          int tap = k / C, c = k - tap * C;
+          v = src[((int64_t)co * C + c) * 49 + tap];
+        }
+      }
+      stf(dst, i, v);
+    }
+  });
+}
+
 // ---------------------------------------------------------------------------------------------
 // BatchNorm2d, train mode (torch BN as constructed at resnet.py:104, image.py:38,56)
 // column statistics over M rows of C channels.  ws: >= 2*P*C doubles.
