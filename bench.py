@@ -246,15 +246,16 @@ def run_ours(args):
     # ---- per-category device timing (CUDA events on the launching stream) for the roofline of the dominant kernel
     roof = None
     cats = {}
+    nprof = 2
+    if rank == 0:
+        L.lbc_prof_reset()
+        L.lbc_prof_enable(1)
+    for _ in range(nprof):      # every rank steps (the step contains the gradient all-reduce); rank 0 records
+        step()
+    torch.cuda.synchronize()
     if rank == 0:
         import ctypes
         peaks = load_peaks()
-        L.lbc_prof_reset()
-        L.lbc_prof_enable(1)
-        nprof = 2
-        for _ in range(nprof):
-            step()
-        torch.cuda.synchronize()
         L.lbc_prof_enable(0)
         for cat in ("conv_fwd", "conv_dgrad", "conv_wgrad", "bn_fwd", "bn_bwd"):
             msd, cnt, fl, by = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_double()
