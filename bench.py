@@ -214,27 +214,32 @@ def run_ours(args):
     ms = float(t.item())
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    # ---- end to end through the public API with HOST buffers (pinned): every step's inputs are copied host->device
+    # inside the timed region (on the package's CudaPrefetcher side stream, overlapping the previous step's compute)
+    # and the step's loss is read back device->host.
+    from learningbycheating_b200.data import CudaPrefetcher
     rgb_p, speed_p, target_p = rgb_h.pin_memory(), speed_h.pin_memory(), target_h.pin_memory()
+    e2e_steps = max(3, min(args.steps, 8))
 
-    def e2e_step():
-        r = rgb_p.to(dev, non_blocking=True)
-        s = speed_p.to(dev, non_blocking=True)
-        c = lbc.one_hot(cmd_h).pin_memory().to(dev, non_blocking=True)
-        tg = target_p.to(dev, non_blocking=True)
-        pred, _ = net(r, s, c)
-        l = crit(pred, tg).mean()
-        opt.zero_grad()
-        l.backward()
-        dp.step_after_backward()
-        return l.item()           # device -> host read of the step's loss
+    def host_batches(n):
+        for _ in range(n):
+            yield (rgb_p, speed_p, lbc.one_hot(cmd_h).pin_memory(), target_p)
 
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
+    def e2e_run(n):
+        last = None
+        for r, s_, c, tg in CudaPrefetcher(host_batches(n), dev):
+            pred, _ = net(r, s_, c)
+            l = crit(pred, tg).mean()
+            opt.zero_grad()
+            l.backward()
+            dp.step_after_backward()
+            last = l.item()            # device -> host read of the step's loss
+        return last
+
+    e2e_run(2)
     barrier()
     e0.record()
-    for _ in range(e2e_steps):
-        lv = e2e_step()
+    e2e_run(e2e_steps)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)

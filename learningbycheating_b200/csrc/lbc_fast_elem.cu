@@ -67,7 +67,7 @@ static RowGeom row_geom(int64_t M, int C, int blocks_per_sm) {
 // partial[blockIdx][0..C) = sum_rows x ; partial[blockIdx][C..2C) = sum_rows x^2 over this block's rows.
 // No atomics: same-address fp32 atomics from ~1000 blocks serialise in L2 (~95 us per launch measured); the
 // partials are reduced by col_finalize kernels -> deterministic results.
-__global__ void __launch_bounds__(320) bn_stats_kernel(const uint4* __restrict__ x, int64_t M, int tpr, int rpi, float* partial,
+__global__ void __launch_bounds__(256, 6) bn_stats_kernel(const uint4* __restrict__ x, int64_t M, int tpr, int rpi, float* partial,
                                                        int C) {
   extern __shared__ float red[];  // [threads][16]
   const int t = threadIdx.x;
@@ -184,7 +184,7 @@ struct BnApplyArgs {
   float eps, momentum;
   int relu, train;
 };
-__global__ void __launch_bounds__(320) bn_apply_kernel(const BnApplyArgs a) {
+__global__ void __launch_bounds__(256, 4) bn_apply_kernel(const BnApplyArgs a) {
   const int t = threadIdx.x;
   const int cg = t % a.tpr, r = t / a.tpr;
   float sc[8], sh[8];
@@ -290,58 +290,41 @@ bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const flo
 
 // ------------------------------------------------------------------------------------------- BN backward
 // pass 1: sums[0..C) += sum dy_m ; sums[C..2C) += sum dy_m * xhat,  dy_m = dy * (act > 0) when act != null
-__global__ void __launch_bounds__(320) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
                                                             const uint4* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, int64_t M, int tpr, int rpi,
                                                             float* partial, int C) {
   extern __shared__ float red[];
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
-  float mu[8], rs[8], s0[8], s1[8];
+  float mu[8], s0[8], s1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mu[j] = mean[cg * 8 + j];
-    rs[j] = rstd[cg * 8 + j];
     s0[j] = s1[j] = 0.f;
   }
   const int64_t stride = (int64_t)gridDim.x * rpi;
-  for (int64_t row = (int64_t)blockIdx.x * rpi + r; row < M; row += 2 * stride) {
+#pragma unroll 2
+  for (int64_t row = (int64_t)blockIdx.x * rpi + r; row < M; row += stride) {
     const int64_t i0 = row * tpr + cg;
-    const bool has1 = row + stride < M;
-    const int64_t i1 = (row + stride) * tpr + cg;
-    uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
-    uint4 d1 = has1 ? ldg_stream(dy + i1) : d0, x1 = has1 ? ldg_stream(x + i1) : x0;
-    uint4 a0, a1;
-    if (act) {
-      a0 = ldg_stream(act + i0);
-      a1 = has1 ? ldg_stream(act + i1) : a0;
-    }
+    const uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
+    uint4 a0 = d0;
+    if (act) a0 = ldg_stream(act + i0);
     float fd[8], fx[8], fa[8];
     unpack8(d0, fd);
     unpack8(x0, fx);
-    if (act) unpack8(a0, fa);
+    unpack8(a0, fa);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
       s0[j] += g;
-      s1[j] += g * ((fx[j] - mu[j]) * rs[j]);
-    }
-    if (has1) {
-      unpack8(d1, fd);
-      unpack8(x1, fx);
-      if (act) unpack8(a1, fa);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
-        s0[j] += g;
-        s1[j] += g * ((fx[j] - mu[j]) * rs[j]);
-      }
+      s1[j] += g * (fx[j] - mu[j]);
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     red[t * 16 + j] = s0[j];
-    red[t * 16 + 8 + j] = s1[j];
+    red[t * 16 + 8 + j] = s1[j] * rstd[cg * 8 + j];   // sum g*xhat = rstd * sum g*(x-mu)
   }
   __syncthreads();
   if (t < tpr) {
@@ -361,70 +344,54 @@ __global__ void __launch_bounds__(320) bn_bwd_reduce_kernel(const uint4* __restr
   }
 }
 // pass 2: dx = gamma*rstd*(dy_m - dbeta/M - xhat*dgamma/M); block 0 also publishes dgamma / dbeta
-__global__ void __launch_bounds__(320) bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
                                                            const uint4* __restrict__ x, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ sums, float* dgamma, float* dbeta,
                                                            uint4* __restrict__ dx, int64_t M, int tpr, int rpi, int C) {
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
-  float mu[8], rs[8], k0[8], k1[8], k2[8];
+  // dx = k0*(g - db/M - xhat*dg/M) = k0*g + kb*x + ka,  kb = -k0*rstd*dg/M,  ka = -k0*db/M - kb*mean
+  float k0[8], kb[8], ka[8];
   const float invM = 1.0f / (float)M;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cg * 8 + j;
-    mu[j] = mean[c];
-    rs[j] = rstd[c];
+    const float mu = mean[c], rs = rstd[c];
     const float db = sums[c], dg = sums[C + c];
     if (blockIdx.x == 0 && r == 0) {
       dbeta[c] = db;
       dgamma[c] = dg;
     }
-    k0[j] = gamma[c] * rs[j];   // dx = k0*(g - k1 - xhat*k2)
-    k1[j] = db * invM;
-    k2[j] = dg * invM;
+    k0[j] = gamma[c] * rs;
+    kb[j] = -k0[j] * rs * dg * invM;
+    ka[j] = -k0[j] * db * invM - kb[j] * mu;
   }
   if (!dx) return;
   const int64_t stride = (int64_t)gridDim.x * rpi;
-  for (int64_t row = (int64_t)blockIdx.x * rpi + r; row < M; row += 2 * stride) {
+#pragma unroll 2
+  for (int64_t row = (int64_t)blockIdx.x * rpi + r; row < M; row += stride) {
     const int64_t i0 = row * tpr + cg;
-    const bool has1 = row + stride < M;
-    const int64_t i1 = (row + stride) * tpr + cg;
-    uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
-    uint4 d1 = has1 ? ldg_stream(dy + i1) : d0, x1 = has1 ? ldg_stream(x + i1) : x0;
-    uint4 a0, a1;
-    if (act) {
-      a0 = ldg_stream(act + i0);
-      a1 = has1 ? ldg_stream(act + i1) : a0;
-    }
+    const uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
+    uint4 a0 = d0;
+    if (act) a0 = ldg_stream(act + i0);
     float fd[8], fx[8], fa[8], o[8];
     unpack8(d0, fd);
     unpack8(x0, fx);
-    if (act) unpack8(a0, fa);
+    unpack8(a0, fa);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
-      o[j] = k0[j] * (g - k1[j] - (fx[j] - mu[j]) * rs[j] * k2[j]);
+      o[j] = fmaf(k0[j], g, fmaf(kb[j], fx[j], ka[j]));
     }
     dx[i0] = pack8(o);
-    if (has1) {
-      unpack8(d1, fd);
-      unpack8(x1, fx);
-      if (act) unpack8(a1, fa);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
-        o[j] = k0[j] * (g - k1[j] - (fx[j] - mu[j]) * rs[j] * k2[j]);
-      }
-      dx[i1] = pack8(o);
-    }
   }
 }
 
 bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
                  const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s) {
   if (C % 8 || C > 2560) return false;
-  RowGeom g = row_geom(M, C, 6);
+  RowGeom g = row_geom(M, C, 4);
   float* part = partial_buffer();
   if (!part) return false;
   bn_bwd_reduce_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
