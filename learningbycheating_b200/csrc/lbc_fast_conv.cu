@@ -798,10 +798,23 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
   p.Ci = c.Ci;
   p.out = scratch;
   const int out_tiles = p.co_tiles * p.ci_tiles * KK;
-  int splits = (2 * sm_count() + out_tiles - 1) / out_tiles;
-  if (splits > p.k_tiles / 4) splits = p.k_tiles / 4;
-  if (splits < 1) splits = 1;
-  p.k_per_split = (p.k_tiles + splits - 1) / splits;
+  // one CTA per SM (shared memory), so the grid runs in waves of sm_count(): pick the K split that fills whole waves
+  // (a 297-CTA grid on 148 SMs is THREE waves, the last one with a single CTA).
+  int best_splits = 1;
+  double best_cost = 1e30;
+  const int max_splits = p.k_tiles / 4 > 0 ? p.k_tiles / 4 : 1;
+  for (int sp = 1; sp <= max_splits && sp <= 64; ++sp) {
+    int kps = (p.k_tiles + sp - 1) / sp;
+    int real = (p.k_tiles + kps - 1) / kps;
+    int ctas = real * out_tiles;
+    int waves = (ctas + sm_count() - 1) / sm_count();
+    double cost = (double)waves * (kps + 6);   // time ~ waves x (k iterations per CTA + fixed prologue/epilogue)
+    if (cost < best_cost) {
+      best_cost = cost;
+      best_splits = sp;
+    }
+  }
+  p.k_per_split = (p.k_tiles + best_splits - 1) / best_splits;
   p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
   const int64_t eb = 2;
   CUtensorMap mDY = make_map_4d(dy, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb,
