@@ -87,14 +87,15 @@ def _bn_case(dev, M, C, relu, with_res):
         out_ref = out_ref.clamp_min(0)
     L = _lib.lib()
     d = lambda t: None if t is None else t.contiguous().to(dev)
+    xd, gd, bd, rd, dyd = d(x), d(gamma), d(beta), d(res), d(dy)     # keep the device copies alive across the calls
     y, mean, var = torch.empty(M, C, device=dev), torch.empty(C, device=dev), torch.empty(C, device=dev)
-    _lib.check(L.lbc_op_bn_train(_lib.ptr(d(x)), _lib.ptr(d(gamma)), _lib.ptr(d(beta)), _lib.ptr(d(res)), int(relu),
+    _lib.check(L.lbc_op_bn_train(_lib.ptr(xd), _lib.ptr(gd), _lib.ptr(bd), _lib.ptr(rd), int(relu),
                                  _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var), M, C, None))
     assert (y.cpu() - out_ref).abs().max() < 2e-5
     assert (mean.cpu() - x.mean(0)).abs().max() < 1e-5
     assert (var.cpu() - x.var(0, unbiased=False)).abs().max() < 2e-5
     dg, db, dx = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty(M, C, device=dev)
-    _lib.check(L.lbc_op_bn_bwd(_lib.ptr(d(dy)), _lib.ptr(d(x)), _lib.ptr(d(gamma)), _lib.ptr(dg), _lib.ptr(db),
+    _lib.check(L.lbc_op_bn_bwd(_lib.ptr(dyd), _lib.ptr(xd), _lib.ptr(gd), _lib.ptr(dg), _lib.ptr(db),
                                _lib.ptr(dx), M, C, None))
     assert (dg.cpu() - gp.grad).abs().max() < 1e-4 * max(1.0, gp.grad.abs().max().item())
     assert (db.cpu() - bp.grad).abs().max() < 1e-4 * max(1.0, bp.grad.abs().max().item())
@@ -143,7 +144,8 @@ def _softmax_case(dev):
     g = torch.Generator().manual_seed(11)
     logits[len(keys):] = torch.randn(20 - len(keys), 48 * 48, generator=g) * 3
     out = torch.empty(20, 2, device=dev)
-    _lib.check(L.lbc_op_spatial_softmax(_lib.ptr(logits.to(dev)), _lib.ptr(out), 20, 48, 48, None))
+    logits_d = logits.to(dev)
+    _lib.check(L.lbc_op_spatial_softmax(_lib.ptr(logits_d), _lib.ptr(out), 20, 48, 48, None))
     out = out.cpu()
     for r, key in enumerate(keys):
         np.testing.assert_allclose(out[r].numpy(), ka[key].reshape(-1), atol=1e-6)
