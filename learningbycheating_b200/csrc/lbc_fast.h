@@ -14,17 +14,24 @@ namespace fast {
 bool enabled();
 void set_enabled(bool on);
 
-bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s);
+// stat_partial != null: the epilogue also writes per-tile column sums / sums of squares of the stored output
+// ([*stat_rows][2*Co] floats) so that the BatchNorm statistics pass over the tensor disappears.
+bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s,
+                   float* stat_partial = nullptr, int* stat_rows = nullptr);
+float* stat_partial_buffer();      // shared scratch of the statistics partials (single stream)
+bool col_finalize_bf16(const float* partial, int rows, int C2, float* sums, lbc_stream_t s);
 
 template <class T>
-inline bool conv_fwd(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s, const float* bias_co = nullptr) {
-  (void)c; (void)x; (void)y; (void)B; (void)s; (void)bias_co;
+inline bool conv_fwd(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s, const float* bias_co = nullptr,
+                     float* stat_partial = nullptr, int* stat_rows = nullptr) {
+  (void)c; (void)x; (void)y; (void)B; (void)s; (void)bias_co; (void)stat_partial; (void)stat_rows;
   return false;
 }
 template <>
-inline bool conv_fwd<bf16>(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s, const float* bias_co) {
+inline bool conv_fwd<bf16>(const ConvL& c, const bf16* x, bf16* y, int B, lbc_stream_t s, const float* bias_co,
+                           float* stat_partial, int* stat_rows) {
   if (!enabled()) return false;
-  return conv_fwd_bf16(c, x, y, B, bias_co, s);
+  return conv_fwd_bf16(c, x, y, B, bias_co, s, stat_partial, stat_rows);
 }
 
 bool conv_dgrad_bf16(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu, lbc_stream_t s);
@@ -81,7 +88,7 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
 // generic-T front ends: only T = bf16 has fast kernels
 template <class T> struct Fast {
   static bool bn_fwd(const T*, int64_t, int, const float*, const float*, float, float, float*, float*, float*, float*,
-                     const T*, bool, bool, T*, float*, float*, lbc_stream_t) { return false; }
+                     const T*, bool, bool, T*, float*, float*, lbc_stream_t, int = 0) { return false; }
   static bool bn_bwd(const T*, const T*, const T*, const float*, const float*, const float*, float*, float*, T*, int64_t, int,
                      float*, lbc_stream_t) { return false; }
   static bool ew(T*, const T*, const T*, int64_t, int, lbc_stream_t) { return false; }
@@ -95,9 +102,13 @@ template <> struct Fast<bf16> {
   // train: statistics + apply (two launches); eval: apply with the running statistics.  sums: >= 2C floats scratch
   static bool bn_fwd(const bf16* x, int64_t M, int C, const float* gamma, const float* beta, float eps, float momentum,
                      float* rm, float* rv, float* saved_mean, float* saved_rstd, const bf16* res, bool relu, bool train,
-                     bf16* y, float* sums, float* negshift, lbc_stream_t s) {
+                     bf16* y, float* sums, float* negshift, lbc_stream_t s, int conv_stat_rows = 0) {
     if (!enabled()) return false;
-    if (train && !bn_stats_bf16(x, M, C, sums, s)) return false;
+    if (train && conv_stat_rows > 0) {   // statistics partials already written by the producing conv's epilogue
+      if (!col_finalize_bf16(stat_partial_buffer(), conv_stat_rows, 2 * C, sums, s)) return false;
+    } else if (train && !bn_stats_bf16(x, M, C, sums, s)) {
+      return false;
+    }
     return bn_apply_bf16(x, sums, M, C, gamma, beta, eps, momentum, rm, rv, saved_mean, saved_rstd, res, relu, train, y,
                          negshift, s);
   }

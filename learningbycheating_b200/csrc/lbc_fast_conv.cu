@@ -100,6 +100,10 @@ struct ConvGemmParams {
   int tap_dh[9], tap_dw[9], tap_map[9], tap_koff[9];
   const float* bias;                // per output channel or null
   int relu;
+  // optional BatchNorm statistics of the stored (bf16-rounded) output: partial[m_tile][2*stat_C] (sum | sum of squares)
+  float* stat_partial;
+  int stat_C;
+  int valid_n;                      // batch size (rows of images >= valid_n are the zero-filled tail)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -200,7 +204,8 @@ struct SmemPlan {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + alignment slack
+  static constexpr int RED_OFF = BAR_OFF + 256;       // 128 x 4 floats: column-statistics scratch
+  static constexpr int TOTAL = RED_OFF + 2048 + 1024;  // barriers + scratch + alignment slack
 };
 
 // ------------------------------------------------------------------------------------------- the kernel
@@ -366,6 +371,51 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         for (int b = 0; b < BN / 64; ++b) tma_store_4d(&mO, out_stage + b * A_BYTES, n_tile * BN + b * 64, w0, h0, n0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      if (p.stat_partial) {
+        // per-channel sum / sum of squares of this tile's bf16 outputs, read back from the staging tile
+        constexpr int PAIRS = BN / 2, TPP = 128 / PAIRS, RPT = 128 / TPP;
+        float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
+        const int e = threadIdx.x - 64;
+        const int pair = e % PAIRS, sub = e / PAIRS;
+        const int col = 2 * pair;
+        const uint8_t* boxp = out_stage + (col >> 6) * A_BYTES + ((col & 7) >> 1) * 4;
+        const int chunk = (col & 63) >> 3;
+        int nvalid = p.valid_n - n0;
+        nvalid = nvalid < 0 ? 0 : (nvalid > p.TN ? p.TN : nvalid);
+        const int valid_rows = nvalid * p.TH * p.TW;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        for (int r = sub * RPT; r < (sub + 1) * RPT && r < valid_rows; ++r) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(boxp + r * 128 + ((chunk ^ (r & 7)) << 4));
+          const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+          s0 += a;
+          s1 += b;
+          q0 += a * a;
+          q1 += b * b;
+        }
+        if (TPP > 1) {
+          red[e * 4 + 0] = s0;
+          red[e * 4 + 1] = s1;
+          red[e * 4 + 2] = q0;
+          red[e * 4 + 3] = q1;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (sub == 0) {
+#pragma unroll
+            for (int t2 = 1; t2 < TPP; ++t2) {
+              s0 += red[(t2 * PAIRS + pair) * 4 + 0];
+              s1 += red[(t2 * PAIRS + pair) * 4 + 1];
+              q0 += red[(t2 * PAIRS + pair) * 4 + 2];
+              q1 += red[(t2 * PAIRS + pair) * 4 + 3];
+            }
+          }
+        }
+        if (sub == 0) {
+          float* dst = p.stat_partial + (int64_t)m_tile * 2 * p.stat_C + n_tile * BN + col;
+          dst[0] = s0;
+          dst[1] = s1;
+          dst[p.stat_C] = q0;
+          dst[p.stat_C + 1] = q1;
+        }
+      }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -440,7 +490,8 @@ static bool supported(const ConvL& c) {
 }
 
 // y = conv(x, w):  x [B,H,W,Ci], packed weights [Co][K*K][Ci], y [B,OH,OW,Co]
-bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s) {
+bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s,
+                   float* stat_partial, int* stat_rows) {
   if (!supported(c)) return false;
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -450,6 +501,10 @@ bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* b
   p.num_taps = c.K * c.K;
   p.k_chunks = c.Ci / 64;
   p.bias = bias_co;   // per-output-channel constant added before the bf16 rounding (centring shift, see lbc_net.cu)
+  p.stat_partial = stat_partial;
+  p.stat_C = c.Co;
+  p.valid_n = B;
+  if (stat_rows) *stat_rows = p.tiles_w * p.tiles_h * p.tiles_n;
   CUtensorMap mA[4];
   const int64_t eb = 2;
   if (c.stride == 1) {
@@ -859,7 +914,7 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
 }
 
 #else   // LBC_HOST_EMU: no tensor cores on the host; the executor runs the correctness-first kernels
-bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, const float*, lbc_stream_t) { return false; }
+bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, const float*, lbc_stream_t, float*, int*) { return false; }
 bool conv_dgrad_bf16(const ConvL&, const bf16*, bf16*, int, const float*, bool, lbc_stream_t) { return false; }
 bool conv_wgrad_bf16(const ConvL&, const bf16*, const bf16*, float*, int, float*, int64_t, lbc_stream_t) { return false; }
 bool conv_dgrad_ds_bf16(const ConvL&, const bf16*, const bf16*, bf16*, int, lbc_stream_t) { return false; }

@@ -154,6 +154,14 @@ static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_s
   ++g_launches;
 }
 
+float* stat_partial_buffer() { return partial_buffer(); }
+bool col_finalize_bf16(const float* partial, int rows, int C2, float* sums, lbc_stream_t s) {
+  if (!partial || (int64_t)rows * C2 > (int64_t)4096 * 2 * 2560) return false;
+  col_finalize(partial, rows, C2, sums, s);
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+
 bool bn_stats_bf16(const bf16* x, int64_t M, int C, float* sums, lbc_stream_t s) {
   if (C % 8 || C > 2560) return false;
   RowGeom g = row_geom(M, C, 6);
@@ -582,6 +590,8 @@ bool bn_apply_bf16(const bf16*, const float*, int64_t, int, const float*, const 
 bool bn_bwd_bf16(const bf16*, const bf16*, const bf16*, const float*, const float*, const float*, float*, float*, bf16*,
                  int64_t, int, float*, lbc_stream_t) { return false; }
 bool ew_bf16(bf16*, const bf16*, const bf16*, int64_t, int, lbc_stream_t) { return false; }
+float* stat_partial_buffer() { return nullptr; }
+bool col_finalize_bf16(const float*, int, int, float*, lbc_stream_t) { return false; }
 bool bn_relu_maxpool_bf16(const bf16*, const float*, const float*, const float*, const float*, bf16*, uint8_t*, int, int, int,
                           int, int, int, lbc_stream_t) { return false; }
 bool maxpool_relu_bwd_bf16(const bf16*, const uint8_t*, const bf16*, const float*, const float*, const float*, const float*,

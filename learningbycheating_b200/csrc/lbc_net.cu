@@ -368,9 +368,20 @@ class Net : public NetBase {
     return 2.0 * B * c.OH * c.OW * (double)c.Co * c.K * c.K * c.Ci;
   }
   // returns true when the per-channel centring shift `negshift` was added to the stored output (fast path only)
-  bool conv_forward(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s, const float* negshift = nullptr) {
+  // stat_rows != null: ask the fast kernel to also emit the BatchNorm statistics partials of its output
+  // (*stat_rows = number of partial rows, 0 when not emitted)
+  bool conv_forward(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s, const float* negshift = nullptr,
+                    int* stat_rows = nullptr) {
     ProfScope ps("conv_fwd", s, conv_flops(c, B), 0);
-    if (fast::conv_fwd<T>(c, x, y, B, s, negshift)) return negshift != nullptr;
+    if (stat_rows) *stat_rows = 0;
+    float* part = (stat_rows && cur_train && (int64_t)c.Co * 2 * ((int64_t)B * c.OH * c.OW / 128 + 64) <= (int64_t)4096 * 2 * 2560)
+                      ? fast::stat_partial_buffer()
+                      : nullptr;
+    int rows = 0;
+    if (fast::conv_fwd<T>(c, x, y, B, s, negshift, part, &rows)) {
+      if (stat_rows && part) *stat_rows = rows;
+      return negshift != nullptr;
+    }
     ref::conv_fwd<T>(s, x, (const T*)c.wp, nullptr, false, y, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
                      c.OW);
     return false;
@@ -387,12 +398,14 @@ class Net : public NetBase {
     ref::conv_wgrad<T>(s, x, dy, G + c.w_off, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, ws_f, ws_f_n);
   }
   void bn_forward(BNL& bn, const T* x, int64_t M, const T* residual, bool relu, T* y, bool train, lbc_stream_t s,
-                  bool shifted = false) {
+                  bool shifted = false, int conv_stat_rows = 0) {
     // algorithmic bytes: stats read (train) + apply read (+residual) + write
     ProfScope ps("bn_fwd", s, 0, (double)M * bn.C * sizeof(T) * ((train ? 1 : 0) + 2 + (residual ? 1 : 0)));
     if (fast::Fast<T>::bn_fwd(x, M, bn.C, P + bn.g_off, P + bn.b_off, kBnEps, kBnMomentum, BUF + bn.rm_off, BUF + bn.rv_off,
-                              bn.mean, bn.rstd, residual, relu, train, y, bn_sums, shifted ? bn.negshift : nullptr, s))
+                              bn.mean, bn.rstd, residual, relu, train, y, bn_sums, shifted ? bn.negshift : nullptr, s,
+                              conv_stat_rows))
       return;
+    LBC_CHECK(conv_stat_rows == 0, "BatchNorm fast path unavailable after a statistics-emitting convolution");
     LBC_CHECK(!shifted, "BatchNorm fast path unavailable after a shifted convolution");
     if (train) {
       ref::bn_stats<T>(s, x, M, bn.C, bn.mean, bn.var, ws_d);
@@ -491,16 +504,18 @@ class Net : public NetBase {
     // residual blocks
     for (Block& b : blocks) {
       int64_t M = (int64_t)B * b.Hout * b.Wout;
-      bool sh1 = conv_forward(b.c1, b.xin, b.r1, B, s, b.b1.negshift);
-      bn_forward(b.b1, b.r1, M, nullptr, true, b.a1, train, s, sh1);
-      bool sh2 = conv_forward(b.c2, b.a1, b.r2, B, s, b.b2.negshift);
+      // each conv's statistics partials live in ONE shared scratch: finalise (inside bn_forward) before the next conv
+      int sr = 0;
+      bool sh1 = conv_forward(b.c1, b.xin, b.r1, B, s, b.b1.negshift, &sr);
+      bn_forward(b.b1, b.r1, M, nullptr, true, b.a1, train, s, sh1, sr);
       const T* identity = b.xin;
       if (b.ds) {
-        bool shd = conv_forward(b.cd, b.xin, b.rd, B, s, b.bd.negshift);
-        bn_forward(b.bd, b.rd, M, nullptr, false, b.idn, train, s, shd);
+        bool shd = conv_forward(b.cd, b.xin, b.rd, B, s, b.bd.negshift, &sr);
+        bn_forward(b.bd, b.rd, M, nullptr, false, b.idn, train, s, shd, sr);
         identity = b.idn;
       }
-      bn_forward(b.b2, b.r2, M, identity, true, b.out, train, s, sh2);
+      bool sh2 = conv_forward(b.c2, b.a1, b.r2, B, s, b.b2.negshift, &sr);
+      bn_forward(b.b2, b.r2, M, identity, true, b.out, train, s, sh2, sr);
     }
     // late fusion of speed (image.py:77-79)
     const T* trunk = blocks.back().out;
