@@ -659,6 +659,9 @@ struct WgradParams {
   int tap_dh[9], tap_dw[9], tap_map[9];
   int Co, Ci;
   float* out;  // [Co][num_taps][Ci] fp32, pre-zeroed
+  // swap mode (Co == 64): M = two (tap, 64-channel ci chunk) combos of x, N = the 64 output channels of dy, so the
+  // 128-row MMA is full instead of half zero padding
+  int swap, num_combos, chunks_per_tap;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -714,14 +717,26 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  // decode this CTA's work: (split, co_tile, tap, ci_tile)
+  // decode this CTA's work: (split, co_tile, tap, ci_tile)   [swap mode: (split, combo pair)]
   int id = blockIdx.x;
-  const int ci_tile = id % p.ci_tiles;
-  id /= p.ci_tiles;
-  const int tap = id % p.num_taps;
-  id /= p.num_taps;
-  const int co_tile = id % p.co_tiles;
-  const int split = id / p.co_tiles;
+  int ci_tile, tap, co_tile, split, combo0 = 0, combo1 = 0;
+  if (p.swap) {
+    const int pairs = (p.num_combos + 1) / 2;
+    const int pair = id % pairs;
+    split = id / pairs;
+    combo0 = pair * 2;
+    combo1 = combo0 + 1 < p.num_combos ? combo0 + 1 : combo0;   // odd tail: duplicate (rows 64..127 are then ignored)
+    ci_tile = 0;
+    tap = 0;
+    co_tile = 0;
+  } else {
+    ci_tile = id % p.ci_tiles;
+    id /= p.ci_tiles;
+    tap = id % p.num_taps;
+    id /= p.num_taps;
+    co_tile = id % p.co_tiles;
+    split = id / p.co_tiles;
+  }
   const int kt0 = split * p.k_per_split;
   int kt1 = kt0 + p.k_per_split;
   if (kt1 > p.k_tiles) kt1 = p.k_tiles;
@@ -729,9 +744,14 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
 
   if (warp == 0) {
     if (elect_one()) {
-      const int mid = p.tap_map[tap];
-      const CUtensorMap* mx = mid == 0 ? &mX0 : (mid == 1 ? &mX1 : (mid == 2 ? &mX2 : &mX3));
-      const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+      const int tapA = p.swap ? combo0 / p.chunks_per_tap : tap;
+      const int tapB = p.swap ? combo1 / p.chunks_per_tap : tap;
+      const int midA = p.tap_map[tapA], midB = p.tap_map[tapB];
+      const CUtensorMap* mx = midA == 0 ? &mX0 : (midA == 1 ? &mX1 : (midA == 2 ? &mX2 : &mX3));
+      const CUtensorMap* mx2 = midB == 0 ? &mX0 : (midB == 1 ? &mX1 : (midB == 2 ? &mX2 : &mX3));
+      const int dh = p.tap_dh[tapA], dw = p.tap_dw[tapA];
+      const int dh2 = p.tap_dh[tapB], dw2 = p.tap_dw[tapB];
+      const int cA = p.swap ? (combo0 % p.chunks_per_tap) * 64 : 0, cB = p.swap ? (combo1 % p.chunks_per_tap) * 64 : 0;
       int stage = 0;
       uint32_t phase = 0;
       for (int kt = kt0; kt < kt1; ++kt) {
@@ -741,6 +761,16 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = smem + stage * SP::STAGE_BYTES;
         mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
+        if (p.swap) {   // A = two x boxes (M = 2 x 64 input channels), B = dy (N = 64 output channels); BNW == 64
+          tma_load_4d(mx, sa, &full[stage], cA, w0 + dw, h0 + dh, n0);
+          tma_load_4d(mx2, sa + A_BYTES, &full[stage], cB, w0 + dw2, h0 + dh2, n0);
+          tma_load_4d(&mDY, sa + SP::A_ST, &full[stage], 0, w0, h0, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         tma_load_4d(&mDY, sa, &full[stage], co_tile * 128, w0, h0, n0);
         tma_load_4d(&mDY, sa + A_BYTES, &full[stage], co_tile * 128 + 64, w0, h0, n0);  // OOB -> zeros when Co == 64
 #pragma unroll
@@ -787,7 +817,20 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
     for (int ch = 0; ch < BNW / 32; ++ch) {
       uint32_t r[32];
       tmem_ld32(taddr + ch * 32, r);
-      if (co < p.Co) {
+      if (p.swap) {
+        const int m = q * 32 + lane;
+        const int which = m >> 6;
+        const int combo = which ? combo1 : combo0;
+        if (which == 0 || combo1 != combo0) {
+          const int tp = combo / p.chunks_per_tap;
+          const int ci = (combo % p.chunks_per_tap) * 64 + (m & 63);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int con = ch * 32 + j;   // output channel
+            atomicAdd(p.out + ((int64_t)con * p.num_taps + tp) * p.Ci + ci, __uint_as_float(r[j]));
+          }
+        }
+      } else if (co < p.Co) {
         float* dst = p.out + ((int64_t)co * p.num_taps + tap) * p.Ci + ci_tile * BNW + ch * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
@@ -821,7 +864,7 @@ static void launch_wgrad(const CUtensorMap& mDY, const CUtensorMap* mX, const Wg
     LBC_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BNW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
     configured = true;
   }
-  int grid = p.splits * p.co_tiles * p.num_taps * p.ci_tiles;
+  int grid = p.swap ? p.splits * ((p.num_combos + 1) / 2) : p.splits * p.co_tiles * p.num_taps * p.ci_tiles;
   wgrad_gemm_kernel<BNW, STAGES><<<grid, 192, SP::TOTAL, s>>>(mDY, mX[0], mX[1], mX[2], mX[3], p);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
@@ -845,14 +888,17 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
   p.tiles_h = g.tiles_h;
   p.tiles_n = g.tiles_n;
   p.k_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
-  const int BNW = (c.Ci % 128 == 0) ? 128 : 64;
+  p.swap = (c.Co == 64) ? 1 : 0;
+  const int BNW = p.swap ? 64 : ((c.Ci % 128 == 0) ? 128 : 64);
   p.co_tiles = (c.Co + 127) / 128;
   p.ci_tiles = c.Ci / BNW;
   p.num_taps = KK;
   p.Co = c.Co;
   p.Ci = c.Ci;
   p.out = scratch;
-  const int out_tiles = p.co_tiles * p.ci_tiles * KK;
+  p.chunks_per_tap = c.Ci / 64;
+  p.num_combos = KK * p.chunks_per_tap;
+  const int out_tiles = p.swap ? (p.num_combos + 1) / 2 : p.co_tiles * p.ci_tiles * KK;
   // one CTA per SM (shared memory), so the grid runs in waves of sm_count(): pick the K split that fills whole waves
   // (a 297-CTA grid on 148 SMs is THREE waves, the last one with a single CTA).
   int best_splits = 1;
