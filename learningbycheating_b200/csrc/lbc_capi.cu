@@ -107,7 +107,8 @@ const char* lbc_build_info(void) {
 #endif
 }
 int lbc_set_fast_kernels(int enabled) {
-  fast::set_enabled(enabled != 0);
+  fast::set_enabled((enabled & 1) != 0);
+  fast::set_c64_variant((enabled & 2) == 0);   // bit 1 set: keep the generic tap-per-box kernel for 64->64 3x3 convs
   return 0;
 }
 

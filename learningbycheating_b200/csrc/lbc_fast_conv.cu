@@ -426,6 +426,254 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------- 3x3/s1, 64 output channels
+// Layer-1-type convolutions (N = 64) are bound by L2->SM operand traffic, not by the tensor pipe: with one TMA box per
+// tap every input pixel crosses the L2->SM link 9 times and the 72 KB of weights once per tile.  This variant
+//   * keeps ALL weights resident in shared memory for the life of the persistent CTA, and
+//   * loads ONE activation box per kernel ROW ({64 ch, 8+2 columns, TH, TN} = 160 rows of 128 B) and feeds the three
+//     kw taps from it by starting the UMMA descriptor 0/1/2 rows (128 B) into the box: with an 8-pixel-wide tile each
+//     8-row core-matrix group is one image row, so consecutive groups are exactly 10 rows = 1280 B apart (the
+//     descriptor's stride-byte-offset) and the 128-byte swizzle, being a function of the shared-memory address, stays
+//     consistent between the TMA write and the shifted MMA read.
+// => 3 x 20 KB per tile instead of 9 x 16 KB + 72 KB.
+struct ConvKwParams {
+  int TH, TN, tiles_w, tiles_h, tiles_n;
+  int k_chunks;
+  int row_dh[3];        // spatial row offset of kernel-row group g
+  int shift[3][3];      // row shift (0..2) into the 10-wide box for tap j of group g
+  int koff[3][3];       // K offset of that tap in the packed weight matrix
+  const float* bias;
+  int relu;
+  float* stat_partial;
+  int stat_C;
+  int valid_n;
+};
+constexpr int AKW_BYTES = 160 * 128;
+
+template <int STAGES>
+struct SmemPlanKw {
+  static constexpr int BN = 64;
+  static constexpr int BRES_BYTES = 9 * BN * 128;   // one 64-channel K chunk of all nine taps
+  static constexpr int OUT_OFF = STAGES * AKW_BYTES + BRES_BYTES;
+  static constexpr int BAR_OFF = OUT_OFF + A_BYTES;
+  static constexpr int RED_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = RED_OFF + 2048 + 1024;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_c64_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
+                   const __grid_constant__ CUtensorMap mO, const ConvKwParams p) {
+  typedef SmemPlanKw<STAGES> SP;
+  constexpr int BN = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* bres = smem + STAGES * AKW_BYTES;
+  uint8_t* out_stage = smem + SP::OUT_OFF;
+  uint64_t* full = (uint64_t*)(smem + SP::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bfull + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    mbar_init(bfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // resident weights: nine [64 x 64] tiles (k_chunks == 1)
+      mbar_expect_tx(bfull, SP::BRES_BYTES);
+      for (int g = 0; g < 3; ++g)
+        for (int j = 0; j < 3; ++j) tma_load_2d(&mB, bres + (g * 3 + j) * (BN * 128), bfull, p.koff[g][j], 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int w0 = (tile % p.tiles_w) * 8;
+        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
+        for (int g = 0; g < 3; ++g) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], AKW_BYTES);
+          tma_load_4d(&mA, smem + stage * AKW_BYTES, &full[stage], 0, w0 - 1, h0 + p.row_dh[g], n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    mbar_wait(bfull, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int g = 0; g < 3; ++g) {
+        mbar_wait(&full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * AKW_BYTES);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const uint64_t ad = umma_desc_k_sw128_sbo(sa + p.shift[g][j] * 128, 1280);
+            const uint64_t bd = umma_desc_k_sw128(smem_u32(bres + (g * 3 + j) * (BN * 128)));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(tmem_d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (g | j | kk) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (g == 2) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 64);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_tile = tile;
+      const int w0 = (tile % p.tiles_w) * 8;
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
+      const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
+      mbar_wait(&tfull[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        const int col0 = ch * 32;
+        uint8_t* rowp = out_stage + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = __uint_as_float(r[j * 8 + e * 2]);
+            float b = __uint_as_float(r[j * 8 + e * 2 + 1]);
+            if (p.bias) {
+              a += __ldg(p.bias + col0 + j * 8 + e * 2);
+              b += __ldg(p.bias + col0 + j * 8 + e * 2 + 1);
+            }
+            if (p.relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const int chunk16 = (ch & 1) * 4 + j;
+          *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tempty[acc]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+        tma_store_4d(&mO, out_stage, 0, w0, h0, n0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (p.stat_partial) {
+        constexpr int PAIRS = BN / 2, TPP = 128 / PAIRS, RPT = 128 / TPP;
+        float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
+        const int e = threadIdx.x - 64;
+        const int pair = e % PAIRS, sub = e / PAIRS;
+        const int col = 2 * pair;
+        const uint8_t* boxp = out_stage + ((col & 7) >> 1) * 4;
+        const int chunk = (col & 63) >> 3;
+        int nvalid = p.valid_n - n0;
+        nvalid = nvalid < 0 ? 0 : (nvalid > p.TN ? p.TN : nvalid);
+        const int valid_rows = nvalid * p.TH * 8;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        for (int r2 = sub * RPT; r2 < (sub + 1) * RPT && r2 < valid_rows; ++r2) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(boxp + r2 * 128 + ((chunk ^ (r2 & 7)) << 4));
+          const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+          s0 += a;
+          s1 += b;
+          q0 += a * a;
+          q1 += b * b;
+        }
+        red[e * 4 + 0] = s0;
+        red[e * 4 + 1] = s1;
+        red[e * 4 + 2] = q0;
+        red[e * 4 + 3] = q1;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (sub == 0) {
+#pragma unroll
+          for (int t2 = 1; t2 < TPP; ++t2) {
+            s0 += red[(t2 * PAIRS + pair) * 4 + 0];
+            s1 += red[(t2 * PAIRS + pair) * 4 + 1];
+            q0 += red[(t2 * PAIRS + pair) * 4 + 2];
+            q1 += red[(t2 * PAIRS + pair) * 4 + 3];
+          }
+          float* dst = p.stat_partial + (int64_t)m_tile * 2 * p.stat_C + col;
+          dst[0] = s0;
+          dst[1] = s1;
+          dst[p.stat_C] = q0;
+          dst[p.stat_C + 1] = q1;
+        }
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 static int sm_count() {
   static int n = [] {
@@ -489,10 +737,66 @@ static bool supported(const ConvL& c) {
   return c.stride == 1 && c.OH == c.H && c.OW == c.W;
 }
 
+
+// 3x3 / stride 1 / 64 -> 64 channels (forward: mirrored=false, taps (kh-1, kw-1); data gradient: mirrored=true)
+static bool g_c64_variant = true;
+void set_c64_variant(bool on) { g_c64_variant = on; }
+static bool try_conv3x3_c64(const bf16* in, const void* wpack, bf16* out, int B, int H, int W, bool mirrored,
+                            const float* bias, bool relu, float* stat_partial, int* stat_rows, lbc_stream_t s) {
+  if (!g_c64_variant || (W % 8) != 0) return false;
+  ConvKwParams p;
+  memset(&p, 0, sizeof(p));
+  int TH = pow2_divisor(H, 16);
+  int TN = 16 / TH;
+  p.TH = TH;
+  p.TN = TN;
+  p.tiles_w = W / 8;
+  p.tiles_h = H / TH;
+  p.tiles_n = (B + TN - 1) / TN;
+  p.k_chunks = 1;
+  for (int g = 0; g < 3; ++g) {
+    // group g covers spatial row offset dh = g - 1; forward: kh = g, data gradient: kh = 2 - g
+    p.row_dh[g] = g - 1;
+    const int kh = mirrored ? 2 - g : g;
+    for (int j = 0; j < 3; ++j) {
+      // box column 0 is w0-1, so tap with column offset dw reads rows shifted by dw + 1
+      const int kw = j;
+      const int dw = mirrored ? 1 - kw : kw - 1;
+      p.shift[g][j] = dw + 1;
+      p.koff[g][j] = (kh * 3 + kw) * 64;
+    }
+  }
+  p.bias = bias;
+  p.relu = relu ? 1 : 0;
+  p.stat_partial = stat_partial;
+  p.stat_C = 64;
+  p.valid_n = B;
+  if (stat_rows) *stat_rows = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int64_t eb = 2;
+  CUtensorMap mA = make_map_4d(in, 64, W, H, B, 64 * eb, (int64_t)W * 64 * eb, (int64_t)H * W * 64 * eb, 10, TH, TN);
+  CUtensorMap mB = make_map_2d(wpack, (int64_t)9 * 64, 64, 64);
+  CUtensorMap mO = make_map_4d(out, 64, W, H, B, 64 * eb, (int64_t)W * 64 * eb, (int64_t)H * W * 64 * eb, 8, TH, TN);
+  typedef SmemPlanKw<5> SP;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(conv3x3_c64_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    configured = true;
+  }
+  int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  conv3x3_c64_kernel<5><<<grid, 192, SP::TOTAL, s>>>(mA, mB, mO, p);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+
 // y = conv(x, w):  x [B,H,W,Ci], packed weights [Co][K*K][Ci], y [B,OH,OW,Co]
 bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s,
                    float* stat_partial, int* stat_rows) {
   if (!supported(c)) return false;
+  if (c.K == 3 && c.stride == 1 && c.Ci == 64 && c.Co == 64 &&
+      try_conv3x3_c64(x, c.wp, y, B, c.H, c.W, false, bias_co, false, stat_partial, stat_rows, s))
+    return true;
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   if (!tile_geometry(c.OH, c.OW, B, p)) return false;
@@ -564,6 +868,9 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
   const int BN = pick_bn(c.Ci);
   CUtensorMap mB = make_map_2d(c.wpt, (int64_t)c.K * c.K * c.Co, c.Ci, BN);
   if (c.stride == 1) {
+    if (c.K == 3 && c.Ci == 64 && c.Co == 64 && !dy_ds &&
+        try_conv3x3_c64(dy, c.wpt, dx, B, c.H, c.W, true, bias_ci, relu, nullptr, nullptr, s))
+      return true;
     ConvGemmParams p;
     memset(&p, 0, sizeof(p));
     if (!tile_geometry(c.H, c.W, B, p)) return false;
@@ -964,6 +1271,7 @@ bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, const float*, lbc_stre
 bool conv_dgrad_bf16(const ConvL&, const bf16*, bf16*, int, const float*, bool, lbc_stream_t) { return false; }
 bool conv_wgrad_bf16(const ConvL&, const bf16*, const bf16*, float*, int, float*, int64_t, lbc_stream_t) { return false; }
 bool conv_dgrad_ds_bf16(const ConvL&, const bf16*, const bf16*, bf16*, int, lbc_stream_t) { return false; }
+void set_c64_variant(bool) {}
 #endif
 
 }  // namespace fast
