@@ -400,7 +400,7 @@ class Net : public NetBase {
   void bn_forward(BNL& bn, const T* x, int64_t M, const T* residual, bool relu, T* y, bool train, lbc_stream_t s,
                   bool shifted = false, int conv_stat_rows = 0) {
     // algorithmic bytes: stats read (train) + apply read (+residual) + write
-    ProfScope ps("bn_fwd", s, 0, (double)M * bn.C * sizeof(T) * ((train ? 1 : 0) + 2 + (residual ? 1 : 0)));
+    ProfScope ps("bn_fwd", s, 0, (double)M * bn.C * sizeof(T) * ((train && conv_stat_rows == 0 ? 1 : 0) + 2 + (residual ? 1 : 0)));
     if (fast::Fast<T>::bn_fwd(x, M, bn.C, P + bn.g_off, P + bn.b_off, kBnEps, kBnMomentum, BUF + bn.rm_off, BUF + bn.rv_off,
                               bn.mean, bn.rstd, residual, relu, train, y, bn_sums, shifted ? bn.negshift : nullptr, s,
                               conv_stat_rows))
