@@ -65,6 +65,13 @@ int lbc_net_bind(lbc_net_t* net, float* params, float* grads, float* buffers);
  * out_pred [B,5,2], out_preds [B,4,5,2] (either may be NULL). */
 int lbc_net_forward(lbc_net_t* net, const float* image, const float* speed, const float* command_onehot, int B,
                     int train, float* out_pred, float* out_preds, void* stream);
+/* Same, taking the camera frame (or bird's-eye masks) as uint8 exactly as stored by the data collector
+ * (data_collector.py:234-252: rgb u8[160,384,3]; bird_view/utils/datasets/image_lmdb.py:133-135,190 applies
+ * torchvision ToTensor = /255 on the host): layout 0 = [B,C,H,W] u8, 1 = [B,H,W,C] u8.  The /255 conversion is done
+ * on the device, so the host->device copy is 4x smaller.  Results are bit-identical to
+ * lbc_net_forward on float(image)/255. */
+int lbc_net_forward_u8(lbc_net_t* net, const uint8_t* image_u8, int layout, const float* speed,
+                       const float* command_onehot, int B, int train, float* out_pred, float* out_preds, void* stream);
 /* loss.backward() through the network (train_image_phase0.py:184): upstream gradients wrt out_pred [B,5,2]
  * and/or out_preds [B,4,5,2] (NULL = none); writes every on-path parameter gradient into the bound
  * gradient array (overwrites, like backward() after zero_grad()). */

@@ -46,6 +46,7 @@ def _declare(lib):
         "lbc_net_workspace_bytes": (i64, [vp]),
         "lbc_net_bind": (i, [vp, vp, vp, vp]),
         "lbc_net_forward": (i, [vp, vp, vp, vp, i, i, vp, vp, vp]),
+        "lbc_net_forward_u8": (i, [vp, vp, i, vp, vp, i, i, vp, vp, vp]),
         "lbc_net_backward": (i, [vp, vp, vp, vp]),
         "lbc_net_read_tap": (i64, [vp, ctypes.c_char_p, vp, i64, vp]),
         "lbc_phase0_target": (i, [vp, vp, i64, f, f, f, f, f, vp]),

@@ -273,7 +273,12 @@ class PolicyNetBase(nn.Module):
     # ------------------------------------------------------------------ forward / backward
     def _check_inputs(self, x, velocity, command):
         C, H, W = self._lbc_input_shape
-        if x.dim() != 4 or tuple(x.shape[1:]) != (C, H, W):
+        if x.dtype == torch.uint8:
+            # frames as stored on disk (u8, /255 applied on the device): [B,C,H,W] or [B,H,W,C]
+            if x.dim() != 4 or (tuple(x.shape[1:]) != (C, H, W) and tuple(x.shape[1:]) != (H, W, C)):
+                raise _lib.LbcError("expected uint8 input [B,%d,%d,%d] or [B,%d,%d,%d], got %s"
+                                    % (C, H, W, H, W, C, tuple(x.shape)))
+        elif x.dim() != 4 or tuple(x.shape[1:]) != (C, H, W):
             raise _lib.LbcError("expected input [B,%d,%d,%d], got %s" % (C, H, W, tuple(x.shape)))
         B = x.shape[0]
         if tuple(velocity.shape) != (B,) or tuple(command.shape) != (B, 4):
@@ -283,8 +288,8 @@ class PolicyNetBase(nn.Module):
         for t in (x, velocity, command):
             if t.device != dev:
                 raise _lib.LbcError("input on %s but the model is on %s" % (t.device, dev))
-            if t.dtype != torch.float32:
-                raise _lib.LbcError("inputs must be float32 (got %s)" % t.dtype)
+            if t.dtype != torch.float32 and not (t is x and t.dtype == torch.uint8):
+                raise _lib.LbcError("inputs must be float32 (or a uint8 frame tensor); got %s" % t.dtype)
         return B
 
     def _native_forward(self, x, velocity, command, train):
@@ -293,9 +298,15 @@ class PolicyNetBase(nn.Module):
         x, velocity, command = x.contiguous(), velocity.contiguous(), command.contiguous()
         pred = torch.empty(B, 5, 2, dtype=torch.float32, device=st.device)
         preds = torch.empty(B, 4, 5, 2, dtype=torch.float32, device=st.device)
-        _lib.check(_lib.lib().lbc_net_forward(st.handle, _lib.ptr(x), _lib.ptr(velocity), _lib.ptr(command), B,
-                                              1 if train else 0, _lib.ptr(pred), _lib.ptr(preds),
-                                              _lib.stream_ptr(st.device)))
+        if x.dtype == torch.uint8:
+            layout = 0 if tuple(x.shape[1:]) == tuple(self._lbc_input_shape) else 1
+            _lib.check(_lib.lib().lbc_net_forward_u8(st.handle, _lib.ptr(x), layout, _lib.ptr(velocity), _lib.ptr(command),
+                                                     B, 1 if train else 0, _lib.ptr(pred), _lib.ptr(preds),
+                                                     _lib.stream_ptr(st.device)))
+        else:
+            _lib.check(_lib.lib().lbc_net_forward(st.handle, _lib.ptr(x), _lib.ptr(velocity), _lib.ptr(command), B,
+                                                  1 if train else 0, _lib.ptr(pred), _lib.ptr(preds),
+                                                  _lib.stream_ptr(st.device)))
         if train:
             torch._foreach_add_(st.nbt, 1)     # BatchNorm2d.num_batches_tracked += 1
         return pred, preds

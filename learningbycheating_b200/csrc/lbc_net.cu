@@ -569,6 +569,21 @@ class Net : public NetBase {
     if (out_pred) ref::head_select(s, preds, onehot_saved, out_pred, B);
   }
 
+  float* img_f32 = nullptr;
+  int64_t img_f32_n = 0;
+  void forward_u8(const uint8_t* image, int layout, const float* speed, const float* onehot, int B, bool train,
+                  float* out_pred, float* out_preds, lbc_stream_t s) override {
+    LBC_CHECK(layout == 0 || layout == 1, "lbc_net_forward_u8: layout must be 0 (NCHW) or 1 (NHWC)");
+    LBC_CHECK(B >= 1 && B <= max_batch, "lbc_net_forward_u8: batch outside [1, max_batch]");
+    const int64_t need = (int64_t)max_batch * in_ch * in_h * in_w;
+    if (!img_f32) {
+      img_f32 = alloc<float>(need);
+      img_f32_n = need;
+    }
+    ref::u8_to_f32_nchw(s, image, img_f32, B, in_ch, in_h, in_w, layout);
+    forward(img_f32, speed, onehot, B, train, out_pred, out_preds, s);
+  }
+
   // ------------------------------------------------------------------ backward
   void backward(const float* d_pred, const float* d_preds, lbc_stream_t s) override {
     LBC_CHECK(G, "lbc_net_backward: gradient buffer not bound");

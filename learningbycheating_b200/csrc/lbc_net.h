@@ -67,6 +67,9 @@ class NetBase {
   }
   virtual void forward(const float* image, const float* speed, const float* onehot, int B, bool train,
                        float* out_pred, float* out_preds, lbc_stream_t s) = 0;
+  // uint8 frames ([B,C,H,W] or [B,H,W,C]): ToTensor's /255 on the device, then the float path
+  virtual void forward_u8(const uint8_t* image, int layout, const float* speed, const float* onehot, int B, bool train,
+                          float* out_pred, float* out_preds, lbc_stream_t s) = 0;
   virtual void backward(const float* d_pred, const float* d_preds, lbc_stream_t s) = 0;
   // debugging / parity taps: copy a named internal tensor out as fp32 NCHW
   virtual int64_t read_tap(const char* name, float* out, int64_t cap, lbc_stream_t s) = 0;

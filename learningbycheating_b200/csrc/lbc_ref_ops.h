@@ -54,6 +54,25 @@ void input_to_nhwc(lbc_stream_t s, const float* img, T* out, int N, int C, int H
   });
 }
 
+// torchvision ToTensor on the device: u8 ([B,C,H,W] layout 0 or [B,H,W,C] layout 1) -> fp32 [B,C,H,W] in [0,1]
+struct k_u8_to_f32;
+inline void u8_to_f32_nchw(lbc_stream_t s, const uint8_t* src, float* dst, int N, int C, int H, int W, int layout) {
+  int64_t n = (int64_t)N * C * H * W;
+  par_for<k_u8_to_f32>(s, n, [=] LBC_LAMBDA(int64_t i) {
+    int64_t j = i;
+    if (layout == 1) {
+      int w = (int)(i % W);
+      int64_t t = i / W;
+      int h = (int)(t % H);
+      t /= H;
+      int c = (int)(t % C);
+      int b = (int)(t / C);
+      j = (((int64_t)b * H + h) * W + w) * C + c;
+    }
+    dst[i] = (float)src[j] / 255.0f;
+  });
+}
+
 // ---------------------------------------------------------------------------------------------
 // y[n,oh,ow,co] = sum x[n,oh*s-p+kh,ow*s-p+kw,ci] * w[co,kh,kw,ci]  (+bias[co]) (relu)
 // nn.Conv2d semantics, bird_view/models/resnet.py:15-22,102-103

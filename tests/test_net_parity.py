@@ -70,6 +70,24 @@ def test_eval_mode_and_state_dict_roundtrip_cpu(backend):
         assert torch.is_tensor(s2(b["rgb"], b["speed"], oh))
 
 
+def test_uint8_frames_match_float_frames_cpu(backend):
+    """frames fed as uint8 ([B,C,H,W] or the on-disk [B,H,W,C]) give bit-identical results to
+    torchvision ToTensor (u8/255) done on the host."""
+    import learningbycheating_b200 as lbc
+    dev = backend
+    s, _ = build_models(dev, "fp32")
+    s.eval()
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (2, 3, 160, 384), dtype=torch.uint8, generator=g)
+    speed, cmd = torch.rand(2, generator=g) * 10, torch.tensor([1., 3.])
+    oh = lbc.one_hot(cmd).to(dev)
+    with torch.no_grad():
+        pf, _ = s((u8.float() / 255).to(dev), speed.to(dev), oh)
+        p0, _ = s(u8.to(dev), speed.to(dev), oh)
+        p1, _ = s(u8.permute(0, 2, 3, 1).contiguous().to(dev), speed.to(dev), oh)
+    assert torch.equal(pf, p0) and torch.equal(pf, p1)
+
+
 def test_torch_adam_also_works_cpu(backend):
     """Parameters are ordinary leaf nn.Parameters: the reference's own torch.optim.Adam drives the module too
     and agrees with the fused native Adam."""
@@ -116,6 +134,7 @@ def test_student_step_gpu_fp32(backend, B, phase):
 @pytest.mark.gpu
 def test_eval_roundtrip_validation_gpu(backend):
     test_eval_mode_and_state_dict_roundtrip_cpu("cuda")
+    test_uint8_frames_match_float_frames_cpu("cuda")
     test_input_validation_cpu("cuda")
     test_torch_adam_also_works_cpu("cuda")
     test_birdview_training_cpu("cuda")
