@@ -227,9 +227,11 @@ def run_ours(args):
     rgb_p, speed_p, target_p = rgb_h.pin_memory(), speed_h.pin_memory(), target_h.pin_memory()
     e2e_steps = max(3, min(args.steps, 8))
 
+    oh_p = lbc.one_hot(cmd_h).pin_memory()     # pinned once, as a DataLoader(pin_memory=True) thread would hand it over
+
     def host_batches(n, frames):
         for _ in range(n):
-            yield (frames, speed_p, lbc.one_hot(cmd_h).pin_memory(), target_p)
+            yield (frames, speed_p, oh_p, target_p)
 
     def e2e_run(n, frames):
         last = None
