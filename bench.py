@@ -245,7 +245,7 @@ def run_ours(args):
         return last
 
     def e2e_measure(frames):
-        e2e_run(2, frames)
+        e2e_run(3, frames)
         barrier()
         e0.record()
         e2e_run(e2e_steps, frames)
@@ -256,8 +256,10 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return world * B * e2e_steps / (float(tt.item()) / 1e3)
 
-    e2e_value = e2e_measure(rgb_u8_p)
+    e2e_run(2, rgb_p)               # both variants warmed (pinned-host / side-stream allocator pools) before either is timed
+    e2e_run(2, rgb_u8_p)
     e2e_fp32 = e2e_measure(rgb_p)
+    e2e_value = e2e_measure(rgb_u8_p)
     small = speed_p.numel() * 4 + B * 4 * 4 + target_p.numel() * 4
     h2d = rgb_u8_p.numel() + small
     h2d_fp32 = rgb_p.numel() * 4 + small
