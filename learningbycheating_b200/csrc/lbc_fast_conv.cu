@@ -728,7 +728,23 @@ static void dispatch_gemm(int BN, const CUtensorMap* mA, const CUtensorMap& mB, 
   else
     launch_gemm<256, 3>(mA, mB, mO, p, s);
 }
-static int pick_bn(int C) { return C == 64 ? 64 : (C % 256 == 0 ? 256 : 128); }
+// N tile: 256 where it divides, unless the 128-wide tiling fills the persistent grid's rounds clearly better
+// (static round-robin over 148 CTAs: 480 tiles = 3.24 rounds -> 81 %, 960 tiles = 6.49 -> 93 %).
+static int pick_bn(int C, int tiles_m = 0) {
+  if (C == 64) return 64;
+  if (C % 256 != 0) return 128;
+  static int policy = [] {
+    const char* e = getenv("LBC_BN_POLICY");
+    return e ? atoi(e) : 0;   // measured: 256-wide tiles win despite the round quantisation (18.14 vs 18.44 ms/step)
+  }();
+  if (policy == 0 || tiles_m <= 0) return 256;
+  auto eff = [&](int bn) {
+    int tiles = tiles_m * (C / bn);
+    int rounds = (tiles + sm_count() - 1) / sm_count();
+    return (double)tiles / ((double)rounds * sm_count());
+  };
+  return eff(128) > eff(256) + 0.08 ? 128 : 256;
+}
 
 static bool supported(const ConvL& c) {
   if (c.Ci % 64 || c.Co % 64) return false;
@@ -800,7 +816,7 @@ bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* b
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   if (!tile_geometry(c.OH, c.OW, B, p)) return false;
-  const int BN = pick_bn(c.Co);
+  const int BN = pick_bn(c.Co, p.tiles_w * p.tiles_h * p.tiles_n);
   p.n_tiles_n = c.Co / BN;
   p.num_taps = c.K * c.K;
   p.k_chunks = c.Ci / 64;
@@ -865,7 +881,10 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
   if (!supported(c) || !c.wpt) return false;
   if (c.K == 1) return false;  // 1x1/s2 downsample gradient scatters into one parity only: handled by the caller
   const int64_t eb = 2;
-  const int BN = pick_bn(c.Ci);
+  ConvGemmParams g0;
+  memset(&g0, 0, sizeof(g0));
+  if (!tile_geometry(c.stride == 1 ? c.H : c.OH, c.stride == 1 ? c.W : c.OW, B, g0)) return false;
+  const int BN = pick_bn(c.Ci, g0.tiles_w * g0.tiles_h * g0.tiles_n);
   CUtensorMap mB = make_map_2d(c.wpt, (int64_t)c.K * c.K * c.Co, c.Ci, BN);
   if (c.stride == 1) {
     if (c.K == 3 && c.Ci == 64 && c.Co == 64 && !dy_ds &&
