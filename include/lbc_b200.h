@@ -96,6 +96,10 @@ int lbc_phase1_convert_fwd(const float* p, float* out, int64_t count, float w, f
 int lbc_phase1_convert_bwd(const float* p, const float* dout, float* dp, int64_t count, float w, float h,
                            float fov_deg, float world_y, float fixed_offset, void* stream);
 
+/* get_weight, training/phase2_utils.py:50-59: per-sample replay-buffer weight of the DAgger stage;
+ * learner_map / teacher_map [N,5,2] in map coords [-1,1] */
+int lbc_phase2_weight(const float* learner_map, const float* teacher_map, float* weight, int N, void* stream);
+
 /* ---- optimizer: torch.optim.Adam(lr).step() (train_image_phase0.py:231,185), one flat range ---- */
 int lbc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream);

@@ -53,6 +53,7 @@ def _declare(lib):
         "lbc_l1_loss": (i, [vp, vp, i, i, f, f, f, f, f, vp, vp, vp, vp]),
         "lbc_phase1_convert_fwd": (i, [vp, vp, i64, f, f, f, f, f, vp]),
         "lbc_phase1_convert_bwd": (i, [vp, vp, vp, i64, f, f, f, f, f, vp]),
+        "lbc_phase2_weight": (i, [vp, vp, vp, i, vp]),
         "lbc_adam_step": (i, [vp, vp, vp, vp, i64, f, f, f, f, i, f, vp]),
         "lbc_op_conv_fwd": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
         "lbc_op_conv_dgrad": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),

@@ -252,6 +252,12 @@ int lbc_phase1_convert_bwd(const float* p, const float* dout, float* dp, int64_t
     ref::phase1_convert_bwd(S(stream), p, dout, dp, count, w, h, fov_deg, world_y, fixed_offset);
   });
 }
+int lbc_phase2_weight(const float* learner_map, const float* teacher_map, float* weight, int N, void* stream) {
+  return guarded([&] {
+    require_device();
+    ref::phase2_weight(S(stream), learner_map, teacher_map, weight, N);
+  });
+}
 int lbc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
   return guarded([&] {

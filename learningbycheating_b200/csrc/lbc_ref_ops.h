@@ -793,6 +793,21 @@ inline void l1_loss(lbc_stream_t s, const float* a, const float* b, int N, int D
     if (loss_b) loss_b[n] = (float)(acc / (double)D);
   });
 }
+// phase-2 (DAgger) replay-buffer weight, training/phase2_utils.py:50-59 (get_weight): per sample
+//   mean_j( (|learner - teacher| * [0.7, 0.3]).sum(xy) * 0.7^j ),  learner already in map coords [-1,1]
+struct k_phase2_weight;
+inline void phase2_weight(lbc_stream_t s, const float* learner, const float* teacher, float* weight, int N) {
+  par_for<k_phase2_weight>(s, N, [=] LBC_LAMBDA(int64_t n) {
+    float acc = 0.f, decay = 1.f;
+    for (int j = 0; j < 5; ++j) {
+      float dx = fabsf(learner[(n * 5 + j) * 2] - teacher[(n * 5 + j) * 2]) * 0.7f;
+      float dy = fabsf(learner[(n * 5 + j) * 2 + 1] - teacher[(n * 5 + j) * 2 + 1]) * 0.3f;
+      acc += (dx + dy) * decay;
+      decay *= 0.7f;
+    }
+    weight[n] = acc / 5.f;
+  });
+}
 // phase-1 CoordConverter (train_image_phase1.py:43-64): image [-1,1] -> map pixels, and its backward
 inline float focal_px(float w, float fov_deg) {
   return (float)((double)w / (2.0 * tan((double)fov_deg * 3.14159265358979323846 / 360.0)));

@@ -80,3 +80,14 @@ def phase1_convert(p, w, h, fov, world_y, fixed_offset):
     if p.dtype != torch.float32 or p.shape[-1] != 2:
         raise _lib.LbcError("phase1_convert expects float32 [...,2]")
     return _Phase1ConvertFn.apply(p, float(w), float(h), float(fov), float(world_y), float(fixed_offset))
+
+
+def phase2_weight(learner_map, teacher_map):
+    """training/phase2_utils.py:50-59 ``get_weight`` (replay-buffer resampling weight, no gradient)."""
+    a = learner_map.detach().contiguous().float()
+    b = teacher_map.detach().contiguous().float()
+    if a.shape != b.shape or a.dim() != 3 or tuple(a.shape[1:]) != (5, 2):
+        raise _lib.LbcError("phase2_weight expects two [N,5,2] tensors")
+    out = torch.empty(a.shape[0], dtype=torch.float32, device=a.device)
+    _lib.check(_lib.lib().lbc_phase2_weight(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.shape[0], _lib.stream_ptr(a.device)))
+    return out

@@ -160,6 +160,17 @@ def test_spatial_softmax_cpu(backend):
     _softmax_case(backend)
 
 
+def test_phase2_weight_cpu(backend):
+    """training/phase2_utils.py:50-59 restated with torch ops vs the native kernel."""
+    from learningbycheating_b200 import losses
+    g = torch.Generator().manual_seed(2)
+    a, b = torch.rand(7, 5, 2, generator=g) * 2 - 1, torch.rand(7, 5, 2, generator=g) * 2 - 1
+    decay = torch.tensor([0.7 ** i for i in range(5)])
+    ref = torch.mean((torch.abs(a - b) * torch.tensor([0.7, 0.3])).sum(dim=-1) * decay, dim=-1)
+    out = losses.phase2_weight(a.to(backend), b.to(backend)).cpu()
+    assert (out - ref).abs().max() < 1e-6
+
+
 def test_errors_are_loud(backend):
     _lib = _L()
     L = _lib.lib()
