@@ -215,6 +215,32 @@ def test_bf16_fast_kernels_match_correctness_first_kernels_gpu(backend):
 
 
 @pytest.mark.gpu
+def test_birdview_training_bf16_gpu(backend):
+    """config 5 architecture (ResNet-18, 7-channel 192x192 input, 48x48 heads) through the tcgen05 path: two Adam steps,
+    first-step loss within bf16 noise of the fp32 golden, both kernel families agree, loss goes down."""
+    import learningbycheating_b200 as lbc
+    from learningbycheating_b200 import _lib, train_birdview as tb
+    g = gold("birdview_B2.npz")
+    out = {}
+    for fast in (0, 1):
+        _lib.check(_lib.lib().lbc_set_fast_kernels(fast))
+        try:
+            _, t = build_models("cuda", "bf16", teacher_all_branch=False)
+            b = batch_on("cuda", 2)
+            opt = lbc.Adam(t.parameters(), lr=1e-4)
+            data = [(b["birdview"], b["location"], b["command"].cpu(), b["speed"])] * 3
+            ls = tb.train_or_eval(tb.LocationLoss(choice='l1'), t, data, opt, True, dict(device="cuda", log_iterations=1000), False)
+            out[fast] = [float(x) for x in ls]
+        finally:
+            _lib.check(_lib.lib().lbc_set_fast_kernels(1))
+    ref0 = float(g["step0/loss_mean"])
+    for fast in (0, 1):
+        assert abs(out[fast][0] - ref0) < 0.02 * ref0, out
+        assert out[fast][2] < out[fast][0], out
+    assert abs(out[0][1] - out[1][1]) < 0.05 * out[0][1], out
+
+
+@pytest.mark.gpu
 def test_full_size_properties_gpu(backend):
     """BASELINE config 2 size (B=256, bf16): size-independent properties -- finite outputs in [-1,1], loss
     decreases over Adam steps on a fixed batch, BN counters advance, gradients finite, conv.fc untouched."""
