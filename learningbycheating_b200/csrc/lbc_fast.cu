@@ -15,6 +15,8 @@ void set_enabled(bool on) { g_enabled = on; }
 #ifdef LBC_HOST_EMU
 bool stem_im2col_bf16(const float*, bf16*, int, int, int, int, int, int, int, bool, lbc_stream_t) { return false; }
 bool stem_pack_weight_bf16(const float*, bf16*, int, int, lbc_stream_t) { return false; }
+bool stem_pad4_bf16(const float*, bf16*, int, int, int, int, bool, lbc_stream_t) { return false; }
+bool stem_pack_w224_bf16(const float*, bf16*, int, lbc_stream_t) { return false; }
 bool stem_unpack_wgrad(const float*, float*, int, int, lbc_stream_t) { return false; }
 #else
 struct k_stem_im2col;
@@ -128,6 +130,52 @@ bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, i
       pk[e2] = (uint32_t)float_to_bf16(v[0]).v | ((uint32_t)float_to_bf16(v[1]).v << 16);
     }
     reinterpret_cast<uint4*>(col)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  });
+  return true;
+}
+struct k_stem_pad4;
+struct k_stem_w224;
+// x4[b][ih+3][iw+4][c] = normalised pixel (c < C), zero elsewhere (borders, 4th channel)
+bool stem_pad4_bf16(const float* img, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s) {
+  if (!enabled() || C > 4) return false;
+  const int HP = H + 6, WP = W + 8;
+  int64_t n = (int64_t)B * HP * WP;
+  par_for<k_stem_pad4>(s, n, [=] __device__(int64_t i) {
+    int col = (int)(i % WP);
+    int64_t t = i / WP;
+    int row = (int)(t % HP);
+    int b = (int)(t / HP);
+    int ih = row - 3, iw = col - 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      for (int c = 0; c < C; ++c) {
+        float x = __ldg(img + (((int64_t)b * C + c) * H + ih) * W + iw);
+        if (normalize) {
+          float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+          float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+          x = (x - mean) / sd;
+        }
+        v[c] = x;
+      }
+    }
+    uint2 o;
+    o.x = (uint32_t)float_to_bf16(v[0]).v | ((uint32_t)float_to_bf16(v[1]).v << 16);
+    o.y = (uint32_t)float_to_bf16(v[2]).v | ((uint32_t)float_to_bf16(v[3]).v << 16);
+    reinterpret_cast<uint2*>(x4)[i] = o;
+  });
+  return true;
+}
+// w224[co][kh][kw'][c]: kw' = kw + 1 in 0..7 (kw' = 0 and c >= C are zero)
+bool stem_pack_w224_bf16(const float* w_ref, bf16* w224, int C, lbc_stream_t s) {
+  par_for<k_stem_w224>(s, (int64_t)64 * 224, [=] __device__(int64_t i) {
+    int e = (int)(i % 32);
+    int64_t t = i / 32;
+    int kh = (int)(t % 7);
+    int co = (int)(t / 7);
+    int kwp = e >> 2, c = e & 3;
+    float v = 0.f;
+    if (kwp >= 1 && c < C) v = w_ref[(((int64_t)co * C + c) * 7 + kh) * 7 + (kwp - 1)];
+    w224[i] = float_to_bf16(v);
   });
   return true;
 }

@@ -674,6 +674,369 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant
   }
 }
 
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes);
+
+// ------------------------------------------------------------------------------------------- stem 7x7/s2 (C_in <= 4)
+// The stem as an implicit GEMM straight from a zero-padded NHWC4 bf16 copy of the image ([B][H+6][W+8][4]):
+// for output pixel (oh, ow) and kernel row kh, the 8 pixels x 4 channels = 32 bf16 = 64 contiguous bytes starting at
+// padded pixel (2*oh + kh, 2*ow) are exactly that tap row of the im2col matrix (first pixel and 4th channel carry zero
+// weights).  A tensor map whose W-stride is 16 B (overlapping 64-byte windows; accepted by cuTensorMapEncodeTiled and
+// verified on the B200) therefore lets TMA build the A operand with NO column tensor: 7 boxes {32, TW, TH, TN} per tile,
+// K = 7 x 32.  64-byte rows -> SWIZZLE_64B operands (8-row groups 512 B apart).  Weights (28 KB) stay resident.
+struct StemParams {
+  int TW, TH, TN, tiles_w, tiles_h, tiles_n;
+  const float* bias;
+  float* stat_partial;
+  int stat_C;
+  int valid_n;
+};
+constexpr int ASTEM_BYTES = 128 * 64;
+
+template <int STAGES>
+struct SmemPlanStem {
+  static constexpr int BRES_BYTES = 7 * 64 * 64;
+  static constexpr int OUT_OFF = STAGES * ASTEM_BYTES + BRES_BYTES;
+  static constexpr int BAR_OFF = OUT_OFF + A_BYTES;
+  static constexpr int RED_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = RED_OFF + 2048 + 1024;
+};
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;   // 8 rows x 64 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;            // SWIZZLE_64B
+  return d;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(192, 2)
+stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant__ CUtensorMap mX1,
+                 const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mO, const StemParams p) {
+  typedef SmemPlanStem<STAGES> SP;
+  constexpr int BN = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* bres = smem + STAGES * ASTEM_BYTES;
+  uint8_t* out_stage = smem + SP::OUT_OFF;
+  uint64_t* full = (uint64_t*)(smem + SP::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bfull + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    mbar_init(bfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bfull, SP::BRES_BYTES);
+      for (int kh = 0; kh < 7; ++kh) tma_load_2d(&mB, bres + kh * 4096, bfull, kh * 32, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int w0 = (tile % p.tiles_w) * p.TW;
+        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
+        for (int kh = 0; kh < 7; ++kh) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], ASTEM_BYTES);
+          tma_load_4d((kh & 1) ? &mX1 : &mX0, smem + stage * ASTEM_BYTES, &full[stage], 0, w0, h0 + (kh >> 1), n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    mbar_wait(bfull, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kh = 0; kh < 7; ++kh) {
+        mbar_wait(&full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint64_t ad = umma_desc_k_sw64(smem_u32(smem + stage * ASTEM_BYTES));
+          const uint64_t bd = umma_desc_k_sw64(smem_u32(bres + kh * 4096));
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            umma_bf16(tmem_d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (kh | kk) != 0);
+          umma_commit(&empty[stage]);
+          if (kh == 6) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 64);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_tile = tile;
+      const int w0 = (tile % p.tiles_w) * p.TW;
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
+      const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
+      mbar_wait(&tfull[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        const int col0 = ch * 32;
+        uint8_t* rowp = out_stage + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = __uint_as_float(r[j * 8 + e * 2]);
+            float b = __uint_as_float(r[j * 8 + e * 2 + 1]);
+            if (p.bias) {
+              a += __ldg(p.bias + col0 + j * 8 + e * 2);
+              b += __ldg(p.bias + col0 + j * 8 + e * 2 + 1);
+            }
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const int chunk16 = (ch & 1) * 4 + j;
+          *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tempty[acc]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+        tma_store_4d(&mO, out_stage, 0, w0, h0, n0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (p.stat_partial) {
+        constexpr int PAIRS = BN / 2, TPP = 128 / PAIRS, RPT = 128 / TPP;
+        float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
+        const int e = threadIdx.x - 64;
+        const int pair = e % PAIRS, sub = e / PAIRS;
+        const int col = 2 * pair;
+        const uint8_t* boxp = out_stage + ((col & 7) >> 1) * 4;
+        const int chunk = (col & 63) >> 3;
+        int nvalid = p.valid_n - n0;
+        nvalid = nvalid < 0 ? 0 : (nvalid > p.TN ? p.TN : nvalid);
+        const int valid_rows = nvalid * p.TH * p.TW;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        for (int r2 = sub * RPT; r2 < (sub + 1) * RPT && r2 < valid_rows; ++r2) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(boxp + r2 * 128 + ((chunk ^ (r2 & 7)) << 4));
+          const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+          s0 += a;
+          s1 += b;
+          q0 += a * a;
+          q1 += b * b;
+        }
+        red[e * 4 + 0] = s0;
+        red[e * 4 + 1] = s1;
+        red[e * 4 + 2] = q0;
+        red[e * 4 + 3] = q1;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (sub == 0) {
+#pragma unroll
+          for (int t2 = 1; t2 < TPP; ++t2) {
+            s0 += red[(t2 * PAIRS + pair) * 4 + 0];
+            s1 += red[(t2 * PAIRS + pair) * 4 + 1];
+            q0 += red[(t2 * PAIRS + pair) * 4 + 2];
+            q1 += red[(t2 * PAIRS + pair) * 4 + 3];
+          }
+          float* dst = p.stat_partial + (int64_t)m_tile * 2 * p.stat_C + col;
+          dst[0] = s0;
+          dst[1] = s1;
+          dst[p.stat_C] = q0;
+          dst[p.stat_C + 1] = q1;
+        }
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// Stem weight gradient from the same padded image: D[(kh, e)][co] = sum_pixels x4win[pix, kh][e] * dy[pix][co];
+// M tile = 4 kernel rows x 32 window elements (two M tiles cover kh 0..7, row 7 unused), N = 64, K = pixels.
+// A: four {32, TW, TH, TN} boxes (MN-major, SWIZZLE_64B, blocks 8 KB apart); B: one dy box (MN-major, SWIZZLE_128B).
+struct StemWgradParams {
+  int TW, TH, TN, tiles_w, tiles_h, tiles_n;
+  int k_tiles, k_per_split, splits;
+  int C;           // real input channels (<= 4)
+  float* dw_ref;   // [64][C][7][7] fp32, pre-zeroed
+};
+__device__ __forceinline__ uint64_t umma_desc_mn_sw64(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // distance between 32-element MN blocks
+  d |= (uint64_t)(512 >> 4) << 32;                    // 8 K rows x 64 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant__ CUtensorMap mX0,
+                  const __grid_constant__ CUtensorMap mX1, const StemWgradParams p) {
+  constexpr int A_ST = 4 * ASTEM_BYTES, STAGE_BYTES = A_ST + A_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 64;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int mt = blockIdx.x & 1;          // kernel rows 4*mt .. 4*mt+3
+  const int split = blockIdx.x >> 1;
+  const int kt0 = split * p.k_per_split;
+  int kt1 = kt0 + p.k_per_split;
+  if (kt1 > p.k_tiles) kt1 = p.k_tiles;
+  const int n_k = kt1 - kt0;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        const int w0 = (kt % p.tiles_w) * p.TW;
+        const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.TN;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        mbar_expect_tx(&full[stage], STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int kh = mt * 4 + j;
+          if (kh > 6) kh = 6;   // row 7 does not exist: load a valid duplicate, its output rows are skipped
+          tma_load_4d((kh & 1) ? &mX1 : &mX0, sa + j * ASTEM_BYTES, &full[stage], 0, w0, h0 + (kh >> 1), n0);
+        }
+        tma_load_4d(&mDY, sa + A_ST, &full[stage], 0, w0, h0, n0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < n_k; ++k) {
+      mbar_wait(&full[stage], phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t ad = umma_desc_mn_sw64(sa, ASTEM_BYTES);
+        const uint64_t bd = umma_desc_mn_sw128(sa + A_ST, A_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // 16 pixels per MMA: two 8-row groups = 1024 B (A, 64-B rows) / 2048 B (B, 128-B rows)
+          umma_bf16(tmem_base, ad + (uint64_t)(kk * (1024 >> 4)), bd + (uint64_t)(kk * (2048 >> 4)), idesc, (k | kk) != 0);
+        umma_commit(&empty[stage]);
+        if (k == n_k - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (n_k > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int kh = mt * 4 + (m >> 5);
+    const int e = m & 31;
+    const int kwp = e >> 2, c = e & 3;
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(taddr + ch * 32, r);
+      if (kh < 7 && kwp >= 1 && c < p.C) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = ch * 32 + j;
+          atomicAdd(p.dw_ref + (((int64_t)co * p.C + c) * 7 + kh) * 7 + (kwp - 1), __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 static int sm_count() {
   static int n = [] {
@@ -801,6 +1164,108 @@ static bool try_conv3x3_c64(const bf16* in, const void* wpack, bf16* out, int B,
   int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int grid = tiles < sm_count() ? tiles : sm_count();
   conv3x3_c64_kernel<5><<<grid, 192, SP::TOTAL, s>>>(mA, mB, mO, p);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+
+
+// ---- stem host side: x4 = zero-padded NHWC4 bf16 image [B][H+6][W+8][4] ----
+static CUtensorMap make_map_stem(const void* base, int OW, int rows2, int B, int64_t pitch_bytes, int64_t img_bytes, int bw,
+                                 int bh, int bn) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {32, (cuuint64_t)OW, (cuuint64_t)rows2, (cuuint64_t)B};
+  cuuint64_t strides[3] = {16, (cuuint64_t)(2 * pitch_bytes), (cuuint64_t)img_bytes};   // 16 B: overlapping 64-byte windows
+  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LBC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stem window map) failed: " + std::to_string((int)r));
+  return m;
+}
+static CUtensorMap make_map_2d_sw64(const void* base, int64_t K, int64_t rows, int brows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(K * 2)};
+  cuuint32_t box[2] = {32, (cuuint32_t)brows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LBC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stem weights) failed: " + std::to_string((int)r));
+  return m;
+}
+static bool stem_geometry(int OH, int OW, int B, int& TW, int& TH, int& TN) {
+  TW = pow2_divisor(OW, 32);
+  TH = pow2_divisor(OH, 128 / TW);
+  TN = 128 / (TW * TH);
+  return (OW % TW) == 0 && (OH % TH) == 0 && TN <= 256;
+}
+// raw[B,OH,OW,64] = conv7x7/s2(x4) (+ negshift), optional BN statistics partials
+bool stem_conv_bf16(const bf16* x4, const bf16* w224, bf16* raw, int B, int H, int W, int OH, int OW, const float* bias,
+                    float* stat_partial, int* stat_rows, lbc_stream_t s) {
+  if ((H % 2) || (W % 2) || OH * 2 != H || OW * 2 != W) return false;
+  StemParams p;
+  memset(&p, 0, sizeof(p));
+  if (!stem_geometry(OH, OW, B, p.TW, p.TH, p.TN)) return false;
+  p.tiles_w = OW / p.TW;
+  p.tiles_h = OH / p.TH;
+  p.tiles_n = (B + p.TN - 1) / p.TN;
+  p.bias = bias;
+  p.stat_partial = stat_partial;
+  p.stat_C = 64;
+  p.valid_n = B;
+  if (stat_rows) *stat_rows = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int64_t pitch = (int64_t)(W + 8) * 8, img = pitch * (H + 6);
+  CUtensorMap mX0 = make_map_stem(x4, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN);
+  CUtensorMap mX1 = make_map_stem((const uint8_t*)x4 + pitch, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN);
+  CUtensorMap mB = make_map_2d_sw64(w224, 224, 64, 64);
+  const int64_t eb = 2;
+  CUtensorMap mO = make_map_4d(raw, 64, OW, OH, B, 64 * eb, (int64_t)OW * 64 * eb, (int64_t)OH * OW * 64 * eb, p.TW, p.TH, p.TN);
+  typedef SmemPlanStem<7> SP;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(stem_conv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    configured = true;
+  }
+  int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
+  stem_conv_kernel<7><<<grid, 192, SP::TOTAL, s>>>(mX0, mX1, mB, mO, p);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+// dw_ref[64][C][7][7] = sum_pixels dy x window(x4); dw_ref is zeroed here
+bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C, int H, int W, int OH, int OW, lbc_stream_t s) {
+  if ((H % 2) || (W % 2) || OH * 2 != H || OW * 2 != W || C > 4) return false;
+  StemWgradParams p;
+  memset(&p, 0, sizeof(p));
+  if (!stem_geometry(OH, OW, B, p.TW, p.TH, p.TN)) return false;
+  p.tiles_w = OW / p.TW;
+  p.tiles_h = OH / p.TH;
+  p.tiles_n = (B + p.TN - 1) / p.TN;
+  p.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  int splits = sm_count() / 2;
+  if (splits > p.k_tiles / 4) splits = p.k_tiles / 4 > 0 ? p.k_tiles / 4 : 1;
+  p.k_per_split = (p.k_tiles + splits - 1) / splits;
+  p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
+  p.C = C;
+  p.dw_ref = dw_ref;
+  const int64_t pitch = (int64_t)(W + 8) * 8, img = pitch * (H + 6);
+  CUtensorMap mX0 = make_map_stem(x4, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN);
+  CUtensorMap mX1 = make_map_stem((const uint8_t*)x4 + pitch, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN);
+  const int64_t eb = 2;
+  CUtensorMap mDY = make_map_4d(dy, 64, OW, OH, B, 64 * eb, (int64_t)OW * 64 * eb, (int64_t)OH * OW * 64 * eb, p.TW, p.TH, p.TN);
+  constexpr int STAGES = 4;
+  const int smem = STAGES * (4 * ASTEM_BYTES + A_BYTES) + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  LBC_CUDA(cudaMemsetAsync(dw_ref, 0, sizeof(float) * 64 * C * 49, s));
+  stem_wgrad_kernel<STAGES><<<2 * p.splits, 192, smem, s>>>(mDY, mX0, mX1, p);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -1291,6 +1756,8 @@ bool conv_dgrad_bf16(const ConvL&, const bf16*, bf16*, int, const float*, bool, 
 bool conv_wgrad_bf16(const ConvL&, const bf16*, const bf16*, float*, int, float*, int64_t, lbc_stream_t) { return false; }
 bool conv_dgrad_ds_bf16(const ConvL&, const bf16*, const bf16*, bf16*, int, lbc_stream_t) { return false; }
 void set_c64_variant(bool) {}
+bool stem_conv_bf16(const bf16*, const bf16*, bf16*, int, int, int, int, int, const float*, float*, int*, lbc_stream_t) { return false; }
+bool stem_wgrad_bf16(const bf16*, const bf16*, float*, int, int, int, int, int, int, lbc_stream_t) { return false; }
 #endif
 
 }  // namespace fast

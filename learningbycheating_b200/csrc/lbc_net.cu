@@ -52,6 +52,10 @@ class Net : public NetBase {
   ConvL stem_gemm;
   float* stem_dw_col = nullptr;
   bool stem_fast_used = false;
+  // C_in <= 4: zero-padded NHWC4 bf16 image + overlapping-window TMA instead of the column tensor
+  T* stem_x4 = nullptr;
+  T* stem_w224 = nullptr;
+  bool stem_direct_used = false;
   std::vector<Block> blocks;
   int trunk_h, trunk_w;
   BNL dbn[3];
@@ -198,8 +202,13 @@ class Net : public NetBase {
       stem_gemm.H = stem_gemm.OH = stem_oh;
       stem_gemm.W = stem_gemm.OW = stem_ow;
       stem_gemm.wp = alloc<T>(64 * Kp);
-      stem_col = alloc<T>(B * stem_oh * stem_ow * Kp);
       stem_dw_col = alloc<float>(64 * Kp);
+      if (in_ch <= 4) {
+        stem_x4 = alloc<T>(B * (in_h + 6) * (in_w + 8) * 4);
+        stem_w224 = alloc<T>(64 * 224);
+      } else {
+        stem_col = alloc<T>(B * stem_oh * stem_ow * Kp);
+      }
     }
     // ---- BasicBlocks (resnet.py:25-54,132-146)
     int C = 64, H = pool_h, W = pool_w;
@@ -463,7 +472,19 @@ class Net : public NetBase {
     if (!train && negshift_all && fast::enabled()) ref::negate_into(s, BUF, negshift_all, n_buffers);  // centre on running_mean
     // stem
     stem_fast_used = false;
-    if (std::is_same<T, bf16>::value) {
+    stem_direct_used = false;
+    int stem_stat_rows = 0;
+    if (std::is_same<T, bf16>::value && stem_x4 && fast::enabled()) {
+      ProfScope ps("conv_fwd", s, conv_flops(stem, B), 0);
+      float* part = train ? fast::stat_partial_buffer() : nullptr;
+      bool ok = fast::stem_pad4_bf16(image, (bf16*)stem_x4, B, in_ch, in_h, in_w, normalize, s) &&
+                fast::stem_pack_w224_bf16(P + stem.w_off, (bf16*)stem_w224, in_ch, s) &&
+                fast::stem_conv_bf16((const bf16*)stem_x4, (const bf16*)stem_w224, (bf16*)r_stem, B, in_h, in_w, stem_oh,
+                                     stem_ow, stem_bn.negshift, part, &stem_stat_rows, s);
+      LBC_CHECK(ok, "stem direct (overlapping-window TMA) path failed");
+      stem_fast_used = stem_direct_used = true;
+      if (!part) stem_stat_rows = 0;
+    } else if (std::is_same<T, bf16>::value && stem_col) {
       ProfScope ps("conv_fwd", s, conv_flops(stem, B), 0);
       if (fast::stem_im2col_bf16(image, (bf16*)stem_col, B, in_ch, in_h, in_w, stem_oh, stem_ow, stem_gemm.Ci, normalize, s))
         stem_fast_used = fast::conv_fwd<T>(stem_gemm, stem_col, r_stem, B, s, stem_bn.negshift);
@@ -481,7 +502,8 @@ class Net : public NetBase {
         ProfScope ps("bn_fwd", s, 0, (double)Ms * 64 * sizeof(T) * 2.25);
         bool ok = true;
         if (train) {
-          ok = fast::bn_stats_bf16((const bf16*)r_stem, Ms, 64, bn_sums, s);
+          ok = stem_stat_rows > 0 ? fast::col_finalize_bf16(fast::stat_partial_buffer(), stem_stat_rows, 128, bn_sums, s)
+                                  : fast::bn_stats_bf16((const bf16*)r_stem, Ms, 64, bn_sums, s);
           if (ok) {
             ref::bn_finalize_sums(s, bn_sums, 64, Ms, kBnEps, kBnMomentum, stem_bn.mean, stem_bn.rstd, BUF + stem_bn.rm_off,
                                   BUF + stem_bn.rv_off, stem_fast_used ? stem_bn.negshift : nullptr);
@@ -680,7 +702,12 @@ class Net : public NetBase {
       bn_backward(stem_bn, tA, a_stem, r_stem, tB, Ms, s);
     }
     bool stem_wgrad_done = false;
-    if (stem_fast_used) {
+    if (stem_direct_used) {
+      ProfScope ps("conv_wgrad", s, conv_flops(stem, B), 0);
+      stem_wgrad_done = fast::stem_wgrad_bf16((const bf16*)stem_x4, (const bf16*)tB, G + stem.w_off, B, in_ch, in_h, in_w,
+                                              stem_oh, stem_ow, s);
+      LBC_CHECK(stem_wgrad_done, "stem direct weight gradient failed");
+    } else if (stem_fast_used) {
       ProfScope ps("conv_wgrad", s, conv_flops(stem, B), 0);
       if (fast::conv_wgrad<T>(stem_gemm, stem_col, tB, stem_dw_col, B, ws_f, ws_f_n, s))
         stem_wgrad_done = fast::stem_unpack_wgrad(stem_dw_col, G + stem.w_off, in_ch, stem_gemm.Ci, s);
