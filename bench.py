@@ -234,14 +234,20 @@ def run_ours(args):
             yield (frames, speed_p, oh_p, target_p)
 
     def e2e_run(n, frames):
-        last = None
+        # every step's loss is read back to the host; the read of step i is issued after step i+1 has been enqueued
+        # (as a logging loop would do), so the device never drains waiting for the host
+        last, pending = None, None
         for r, s_, c, tg in CudaPrefetcher(host_batches(n, frames), dev):
             pred, _ = net(r, s_, c)
             l = crit(pred, tg).mean()
             opt.zero_grad()
             l.backward()
             dp.step_after_backward()
-            last = l.item()            # device -> host read of the step's loss
+            if pending is not None:
+                last = pending.item()  # device -> host read of the previous step's loss
+            pending = l.detach()
+        if pending is not None:
+            last = pending.item()
         return last
 
     def e2e_measure(frames):
