@@ -124,21 +124,30 @@ __global__ void __launch_bounds__(256, 6) bn_stats_kernel(const uint4* __restric
     }
   }
 }
-// sums[col] = sum_p partial[p][col] for col < 2C.  32 columns x 32 partial-lanes per block (1024 threads).
-__global__ void __launch_bounds__(1024) col_finalize_kernel(const float* __restrict__ partial, int P, int C2, float* sums) {
+// sums[col] (+)= sum_p partial[p][col] for col < 2C.  32 columns x 32 partial-lanes per block (1024 threads); when there
+// are many partial rows (conv-epilogue statistics: one row per 128-pixel tile) the rows are split over blockIdx.y and
+// the (<= 32) block results are combined with one fp32 atomic each into the pre-zeroed sums.
+__global__ void __launch_bounds__(1024) col_finalize_kernel(const float* __restrict__ partial, int P, int C2, float* sums,
+                                                            int rows_per_block, int use_atomic) {
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int pl = threadIdx.x >> 5;
   __shared__ float red[32][33];
+  const int p0 = blockIdx.y * rows_per_block;
+  int p1 = p0 + rows_per_block;
+  if (p1 > P) p1 = P;
   float a = 0.f;
   if (col < C2)
-    for (int p = pl; p < P; p += 32) a += partial[(int64_t)p * C2 + col];
+    for (int p = p0 + pl; p < p1; p += 32) a += partial[(int64_t)p * C2 + col];
   red[pl][threadIdx.x & 31] = a;
   __syncthreads();
   if (pl == 0 && col < C2) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x & 31];
-    sums[col] = t;
+    if (use_atomic)
+      atomicAdd(sums + col, t);
+    else
+      sums[col] = t;
   }
 }
 static float* partial_buffer() {
@@ -150,7 +159,13 @@ static float* partial_buffer() {
   return p;
 }
 static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_stream_t s) {
-  col_finalize_kernel<<<(C2 + 31) / 32, 1024, 0, s>>>(partial, P, C2, sums);
+  int rb = P / 512;          // >= 512 rows per block (16 per thread) before splitting
+  if (rb > 32) rb = 32;
+  if (rb < 1) rb = 1;
+  const int rows_per_block = (P + rb - 1) / rb;
+  rb = (P + rows_per_block - 1) / rows_per_block;
+  if (rb > 1) cudaMemsetAsync(sums, 0, sizeof(float) * C2, s);
+  col_finalize_kernel<<<dim3((C2 + 31) / 32, rb), 1024, 0, s>>>(partial, P, C2, sums, rows_per_block, rb > 1 ? 1 : 0);
   ++g_launches;
 }
 
