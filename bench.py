@@ -92,6 +92,13 @@ def synthetic(B, seed, torch):
     return rgb, speed, cmd, target
 
 
+def cpu_threads():
+    """Threads for the CPU arm.  Measured on the 128-thread GPU host: torch/oneDNN on this B=8 step is ~20x SLOWER with
+    128 intra-op threads (0.6 img/s) than with a few dozen, so the arm uses min(cores, LBC_CPU_THREADS or 32)."""
+    n = os.cpu_count() or 1
+    return max(1, min(n, int(os.environ.get("LBC_CPU_THREADS", "32"))))
+
+
 def cpu_step_rate(torch, B, warm, iters, threads=None):
     """The reference's CPU implementation of the step (oracle port: torch CPU kernels + Adam), images/s."""
     import lbc_oracle as orc
@@ -136,11 +143,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     B = 8
     rate, sec = cpu_step_rate(torch, B, max(1, min(args.warmup, 2)), max(1, args.steps), cores)
-    sample = "oracle port (torch CPU fp32) of the config2 step on a bounded sample: batch %d per step" % B
+    sample = ("oracle port (torch CPU fp32) of the config2 step on a bounded sample: batch %d per step, %d of %d host "
+              "threads (more threads are slower for this batch)" % (B, cores, os.cpu_count() or 1))
     out = dict(impl="reference", metric=METRIC, value=rate, unit="images/s", n_gpus=args.gpus, steps=args.steps,
                warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype="f32", data="synthetic",
@@ -313,10 +321,11 @@ def run_ours(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = cpu_threads()
         rate, sec = cpu_step_rate(torch, 8, 1, 4, cores)
         cpu_base = dict(value=rate, unit="images/s", cores=torch.get_num_threads(), kind="port",
-                        sample="oracle port (torch CPU fp32) of the same step, batch 8, 4 timed iterations")
+                        sample="oracle port (torch CPU fp32) of the same step, batch 8, 4 timed iterations, %d of %d host threads"
+                               % (cores, os.cpu_count() or 1))
 
     if rank == 0:
         out = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
