@@ -16,11 +16,31 @@ CUDA_LIB = os.path.join(PKG, "liblbc_b200.so")
 EMU_LIB = os.path.join(ROOT, "tests", "hostemu", "liblbc_hostemu.so")
 
 
+def _digest(deps):
+    """Content hash of the sources (mtimes do not survive the snapshot that carries the tree to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted(deps):
+        if d.endswith((".o", ".so")):
+            continue
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _newer(target, deps):
-    if not os.path.exists(target):
+    """True when `target` is missing or was not built from the current contents of `deps`."""
+    stamp = target + ".srchash"
+    if not os.path.exists(target) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(stamp) as f:
+        return f.read().strip() != _digest(deps)
+
+
+def _stamp(target, deps):
+    with open(target + ".srchash", "w") as f:
+        f.write(_digest(deps))
 
 
 def _deps():
@@ -54,6 +74,7 @@ def build_cuda(force=False, verbose=False):
             print(out)
         objs.append(obj)
     _run([nvcc, "-shared", "-o", CUDA_LIB] + objs)   # static cudart (nvcc default)
+    _stamp(CUDA_LIB, _deps())
     return CUDA_LIB
 
 
@@ -65,6 +86,7 @@ def build_hostemu(force=False):
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-o", EMU_LIB]
     _run(cmd)
+    _stamp(EMU_LIB, _deps())
     return EMU_LIB
 
 

@@ -18,6 +18,8 @@ void set_enabled(bool on);
 // ([*stat_rows][2*Co] floats) so that the BatchNorm statistics pass over the tensor disappears.
 bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s,
                    float* stat_partial = nullptr, int* stat_rows = nullptr);
+void set_pair_mode(int mode);     // bit 0: CTA-pair (cta_group::2) implicit-GEMM kernels for the >= 128-wide N tiles
+int pair_mode();
 void set_c64_variant(bool on);   // resident-weight / shared-row variant of the 3x3 64->64 convolution (tests toggle it)
 float* stat_partial_buffer();      // shared scratch of the statistics partials (single stream)
 bool col_finalize_bf16(const float* partial, int rows, int C2, float* sums, lbc_stream_t s);

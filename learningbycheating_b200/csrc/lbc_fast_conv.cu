@@ -196,11 +196,64 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- CTA-pair (cta_group::2) helpers: two CTAs of one TPC form a cluster and issue ONE 256-row MMA; each CTA stages
+// its own 128 rows of A and HALF of the B tile, so the L2->SM operand traffic per flop drops by a third (BN = 256).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // (default .release.cta form, as in the multicast pipelines of CUTLASS: the TMEM reads are ordered by tcgen05.wait::ld +
+  // tcgen05.fence::before_thread_sync, no global-memory fence is needed per tile)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the executing CTA's smem, the transaction bytes are signalled on the
+// LEADER CTA's mbarrier (bar_cluster = mapa(full[stage], 0))
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, void* dst, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, void* dst, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 constexpr int A_BYTES = 128 * 128;  // 128 positions x 64 bf16
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 struct SmemPlan {
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = PAIR ? BN * 64 : BN * 128;   // CTA pair: each CTA stages BN/2 rows of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
@@ -209,12 +262,17 @@ struct SmemPlan {
 };
 
 // ------------------------------------------------------------------------------------------- the kernel
-template <int BN, int STAGES>
+// PAIR = true: launched as clusters of two CTAs (one TPC).  The pair computes a 256-position x BN tile with ONE
+// tcgen05.mma.cta_group::2 stream issued by the leader (cluster rank 0): every CTA stages its own 128 positions of A
+// and BN/2 rows of B (its TMA loads signal the LEADER's full barrier), the leader's commits are multicast to the
+// empty / accumulator-full barriers of both CTAs, both epilogues arrive on the leader's accumulator-empty barrier.
+// Each CTA's 128 x BN slice of the accumulator lives in its own TMEM, so the epilogue is unchanged.
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(192, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                  const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
                  const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mO, const ConvGemmParams p) {
-  typedef SmemPlan<BN, STAGES> SP;
+  typedef SmemPlan<BN, STAGES, PAIR> SP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* out_stage = smem + STAGES * SP::STAGE_BYTES;
@@ -235,32 +293,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], PAIR ? 256 : 128);   // pair: the epilogue threads of both CTAs arrive on the leader's
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (PAIR)
+    cluster_sync_all();   // barrier inits of BOTH CTAs visible before any remote arrive / multicast commit
+  else
+    __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int num_tiles = tiles_m * p.n_tiles_n;
   const int k_iters = p.num_taps * p.k_chunks;
+  // tile walk.  single CTA: tile = blockIdx.x + i*gridDim.x over tiles_m*n_tiles_n (m_tile = tile / n_tiles_n).
+  // pair: the same walk over ceil(tiles_m/2)*n_tiles_n PAIR tiles by pair index; this CTA owns m_tile = 2*(..)+rank,
+  // which for an odd tiles_m can be one past the end: its coordinates are past the batch, so TMA zero-fills the
+  // loads and clips the store, and only the statistics row has to be skipped.
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int walk0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int walk_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_tiles = (PAIR ? (tiles_m + 1) / 2 : tiles_m) * p.n_tiles_n;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = walk0; tile < num_tiles; tile += walk_step) {
         const int n_tile = tile % p.n_tiles_n;
-        const int m_tile = tile / p.n_tiles_n;
+        const int m_tile = PAIR ? 2 * (tile / p.n_tiles_n) + (int)crank : tile / p.n_tiles_n;
         const int w0 = (m_tile % p.tiles_w) * p.TW;
         const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -271,9 +345,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * SP::STAGE_BYTES;
-            mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
-            tma_load_4d(ma, sa, &full[stage], kc * 64, w0 + dw, h0 + dh, n0);
-            tma_load_2d(&mB, sa + A_BYTES, &full[stage], koff + kc * 64, n_tile * BN);
+            if constexpr (PAIR) {
+              // the leader's barrier collects the bytes of both CTAs (the peer's may land before this expect_tx:
+              // the tx-count goes transiently negative inside the phase, which mbarrier allows)
+              if (crank == 0) mbar_expect_tx(&full[stage], 2 * SP::STAGE_BYTES);
+              const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+              tma_load_4d_pair(ma, sa, lead_full, kc * 64, w0 + dw, h0 + dh, n0);
+              tma_load_2d_pair(&mB, sa + A_BYTES, lead_full, koff + kc * 64, n_tile * BN + (int)crank * (BN / 2));
+            } else {
+              mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
+              tma_load_4d(ma, sa, &full[stage], kc * 64, w0 + dw, h0 + dh, n0);
+              tma_load_2d(&mB, sa + A_BYTES, &full[stage], koff + kc * 64, n_tile * BN);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -283,13 +366,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // ===================== MMA issuer (pair: the leader CTA only) =====================
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128 (pair: M=256 over the two CTAs)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = walk0; tile < num_tiles && crank == 0; tile += walk_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -303,10 +387,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           const uint64_t ad = umma_desc_k_sw128(sa);
           const uint64_t bd = umma_desc_k_sw128(sa + A_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)  // 4 x (K=16) per 64-wide chunk: advance 32 B inside the swizzle atom
-            umma_bf16(tmem_d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
-          umma_commit(&empty[stage]);                    // frees the smem slot when these MMAs retire
-          if (k == k_iters - 1) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+          for (int kk = 0; kk < 4; ++kk) {  // 4 x (K=16) per 64-wide chunk: advance 32 B inside the swizzle atom
+            if constexpr (PAIR)
+              umma_bf16_pair(tmem_d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+            else
+              umma_bf16(tmem_d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+          }
+          if constexpr (PAIR) {
+            umma_commit_pair(&empty[stage]);                    // frees the slot in both CTAs
+            if (k == k_iters - 1) umma_commit_pair(&tfull[acc]);  // both epilogues
+          } else {
+            umma_commit(&empty[stage]);                    // frees the smem slot when these MMAs retire
+            if (k == k_iters - 1) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -321,11 +414,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     const int row = q * 32 + lane;
     const bool issuer = (threadIdx.x == 64);
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = walk0; tile < num_tiles; tile += walk_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % p.n_tiles_n;
-      const int m_tile = tile / p.n_tiles_n;
+      const int m_tile = PAIR ? 2 * (tile / p.n_tiles_n) + (int)crank : tile / p.n_tiles_n;
       const int w0 = (m_tile % p.tiles_w) * p.TW;
       const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.TH;
       const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -363,7 +456,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&tempty[acc]);  // accumulator drained: the MMA warp may reuse it
+      if constexpr (PAIR)
+        mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));  // on the leader's barrier (256 arrivals per phase)
+      else
+        mbar_arrive(&tempty[acc]);  // accumulator drained: the MMA warp may reuse it
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (issuer) {
@@ -371,7 +467,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         for (int b = 0; b < BN / 64; ++b) tma_store_4d(&mO, out_stage + b * A_BYTES, n_tile * BN + b * 64, w0, h0, n0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      if (p.stat_partial) {
+      if (p.stat_partial && m_tile < tiles_m) {
         // per-channel sum / sum of squares of this tile's bf16 outputs, read back from the staging tile
         constexpr int PAIRS = BN / 2, TPP = 128 / PAIRS, RPT = 128 / TPP;
         float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
@@ -420,9 +516,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  if constexpr (PAIR) {
+    __syncwarp();
+    cluster_sync_all();   // the peer's smem / TMEM are operands of the leader's MMAs until both CTAs are done
+    if (warp == 1)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  } else {
+    __syncthreads();
+    if (warp == 1) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
   }
 }
 
@@ -1073,17 +1176,75 @@ static void launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUte
   typedef SmemPlan<BN, STAGES> SP;
   static bool configured = false;
   if (!configured) {
-    LBC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    LBC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
     configured = true;
   }
   int tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_kernel<BN, STAGES><<<grid, 192, SP::TOTAL, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO, p);
+  conv_gemm_kernel<BN, STAGES, false><<<grid, 192, SP::TOTAL, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO, p);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
 }
-static void dispatch_gemm(int BN, const CUtensorMap* mA, const CUtensorMap& mB, const CUtensorMap& mO,
+// CTA-pair variant: clusters of 2 (one TPC), persistent over ceil(tiles_m/2) * n_tiles_n pair tiles
+template <int BN, int STAGES>
+static void launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, const CUtensorMap& mO, const ConvGemmParams& p,
+                             lbc_stream_t s) {
+  typedef SmemPlan<BN, STAGES, true> SP;
+  static_assert(SP::TOTAL <= 232448, "smem plan of the CTA-pair kernel exceeds 227 KB");
+  auto kern = conv_gemm_kernel<BN, STAGES, true>;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(192, 1, 1);
+  cfg.dynamicSmemBytes = SP::TOTAL;
+  cfg.stream = (cudaStream_t)s;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    LBC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2), 1, 1);
+    int n = 0;
+    // co-resident clusters (a GPC with an unpaired SM cannot host one): a persistent grid must not exceed it
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = sm_count() / 2;
+    }
+    max_clusters = n < sm_count() / 2 ? n : sm_count() / 2;
+  }
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int pair_tiles = ((tiles_m + 1) / 2) * p.n_tiles_n;
+  const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
+  cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
+  LBC_CUDA(cudaLaunchKernelEx(&cfg, kern, mA[0], mA[1], mA[2], mA[3], mBhalf, mO, p));
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+}
+// bit 0: CTA-pair (cta_group::2) kernels for the BN >= 128 GEMMs.  Default from LBC_PAIR (0 until validated on the GPU).
+static int g_pair_mode = [] {
+  const char* e = getenv("LBC_PAIR");
+  return e ? atoi(e) : 0;
+}();
+void set_pair_mode(int mode) { g_pair_mode = mode; }
+int pair_mode() { return g_pair_mode; }
+
+// mB: weights [rows][K]; the box height is chosen here (BN rows, or BN/2 for the CTA-pair kernels)
+static void dispatch_gemm(int BN, const CUtensorMap* mA, const void* wbase, int64_t wK, int64_t wrows, const CUtensorMap& mO,
                           const ConvGemmParams& p, lbc_stream_t s) {
+  const bool pair = (g_pair_mode & 1) && BN >= 128;
+  if (pair) {
+    CUtensorMap mB = make_map_2d(wbase, wK, wrows, BN / 2);
+    if (BN == 128)
+      launch_gemm_pair<128, 7>(mA, mB, mO, p, s);
+    else
+      launch_gemm_pair<256, 4>(mA, mB, mO, p, s);
+    return;
+  }
+  CUtensorMap mB = make_map_2d(wbase, wK, wrows, BN);
   if (BN == 64)
     launch_gemm<64, 6>(mA, mB, mO, p, s);
   else if (BN == 128)
@@ -1320,10 +1481,9 @@ bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* b
         p.tap_koff[t] = t * c.Ci;
       }
   }
-  CUtensorMap mB = make_map_2d(c.wp, (int64_t)c.K * c.K * c.Ci, c.Co, BN);
   CUtensorMap mO = make_map_4d(y, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb, (int64_t)c.OH * c.OW * c.Co * eb,
                                p.TW, p.TH, p.TN);
-  dispatch_gemm(BN, mA, mB, mO, p, s);
+  dispatch_gemm(BN, mA, c.wp, (int64_t)c.K * c.K * c.Ci, c.Co, mO, p, s);
   return true;
 }
 
@@ -1350,7 +1510,7 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
   memset(&g0, 0, sizeof(g0));
   if (!tile_geometry(c.stride == 1 ? c.H : c.OH, c.stride == 1 ? c.W : c.OW, B, g0)) return false;
   const int BN = pick_bn(c.Ci, g0.tiles_w * g0.tiles_h * g0.tiles_n);
-  CUtensorMap mB = make_map_2d(c.wpt, (int64_t)c.K * c.K * c.Co, c.Ci, BN);
+  const int64_t wtK = (int64_t)c.K * c.K * c.Co;
   if (c.stride == 1) {
     if (c.K == 3 && c.Ci == 64 && c.Co == 64 && !dy_ds &&
         try_conv3x3_c64(dy, c.wpt, dx, B, c.H, c.W, true, bias_ci, relu, nullptr, nullptr, s))
@@ -1377,7 +1537,7 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
       }
     CUtensorMap mO = make_map_4d(dx, c.Ci, c.W, c.H, B, c.Ci * eb, (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb,
                                  p.TW, p.TH, p.TN);
-    dispatch_gemm(BN, mA, mB, mO, p, s);
+    dispatch_gemm(BN, mA, c.wpt, wtK, c.Ci, mO, p, s);
     return true;
   }
   // stride 2: dx[n, 2i+a, 2j+b, :] = sum over taps kh with (a + pad - kh) even: dy[n, i + (a+pad-kh)/2, ...]
@@ -1408,10 +1568,9 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
         p.tap_map[1] = 1;
         p.tap_koff[1] = c.Co;
         p.num_taps = 2;
-        CUtensorMap mBc = make_map_2d(c.wcomb, (int64_t)2 * c.Co, c.Ci, BN);
         CUtensorMap mO = make_map_4d(dx, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb, 2 * (int64_t)c.W * c.Ci * eb,
                                      (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
-        dispatch_gemm(BN, mA, mBc, mO, p, s);
+        dispatch_gemm(BN, mA, c.wcomb, (int64_t)2 * c.Co, c.Ci, mO, p, s);
         continue;
       }
       for (int kh = 0; kh < c.K; ++kh) {
@@ -1428,7 +1587,7 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
       p.num_taps = nt;
       CUtensorMap mO = make_map_4d(dx + ((int64_t)a * c.W + b) * c.Ci, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb,
                                    2 * (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
-      dispatch_gemm(BN, mA, mB, mO, p, s);
+      dispatch_gemm(BN, mA, c.wpt, wtK, c.Ci, mO, p, s);
     }
   return true;
 }
@@ -1756,6 +1915,8 @@ bool conv_dgrad_bf16(const ConvL&, const bf16*, bf16*, int, const float*, bool, 
 bool conv_wgrad_bf16(const ConvL&, const bf16*, const bf16*, float*, int, float*, int64_t, lbc_stream_t) { return false; }
 bool conv_dgrad_ds_bf16(const ConvL&, const bf16*, const bf16*, bf16*, int, lbc_stream_t) { return false; }
 void set_c64_variant(bool) {}
+void set_pair_mode(int) {}
+int pair_mode() { return 0; }
 bool stem_conv_bf16(const bf16*, const bf16*, bf16*, int, int, int, int, int, const float*, float*, int*, lbc_stream_t) { return false; }
 bool stem_wgrad_bf16(const bf16*, const bf16*, float*, int, int, int, int, int, int, lbc_stream_t) { return false; }
 #endif

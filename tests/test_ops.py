@@ -211,16 +211,26 @@ FAST_CASES = [
 ]
 
 
+def _pair_default():
+    import os
+    return 4 if int(os.environ.get("LBC_PAIR", "0") or 0) & 1 else 8
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("case", FAST_CASES)
-def test_tcgen05_conv_gpu(backend, case):
-    """fast (tcgen05) kernels vs torch on bf16-rounded operands; wgrad still runs the correctness-first kernel"""
+def test_tcgen05_conv_gpu(backend, case, pair):
+    """fast (tcgen05) kernels vs torch on bf16-rounded operands; wgrad still runs the correctness-first kernel.
+    pair=1: the CTA-pair (cta_group::2, 256-row MMA) variant of the >= 128-wide implicit GEMMs."""
     assert backend == "cuda"
     from learningbycheating_b200 import _lib
-    _lib.check(_lib.lib().lbc_set_fast_kernels(1))
-    n0 = _lib.lib().lbc_kernel_launch_count()
-    _conv_case("cuda", case, 1, 2e-2)
-    assert _lib.lib().lbc_kernel_launch_count() > n0
+    _lib.check(_lib.lib().lbc_set_fast_kernels(1 | (4 if pair else 8)))
+    try:
+        n0 = _lib.lib().lbc_kernel_launch_count()
+        _conv_case("cuda", case, 1, 2e-2)
+        assert _lib.lib().lbc_kernel_launch_count() > n0
+    finally:
+        _lib.check(_lib.lib().lbc_set_fast_kernels(1 | _pair_default()))
 
 
 @pytest.mark.gpu
