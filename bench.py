@@ -174,8 +174,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
-    pair = args.pair if args.pair >= 0 else int(os.environ.get("LBC_PAIR", "0") or 0) & 1
-    L.lbc_set_fast_kernels((0 if args.no_fast else 1) | (4 if pair else 8))
+    pair = args.pair if args.pair >= 0 else int(os.environ.get("LBC_PAIR", "0") or 0)   # bit 0: CTA-pair GEMMs, bit 1: wgrad3
+    L.lbc_set_fast_kernels((0 if args.no_fast else 1) | (4 if pair & 1 else 8) | (16 if pair & 2 else 32))
     B = args.batch
     torch.manual_seed(0)
     net = lbc.ImagePolicyModelSS("resnet34", all_branch=True, lbc_precision=args.precision).to(dev).train()
@@ -336,7 +336,7 @@ def run_ours(args):
                                batch_per_gpu=B, parallelism="dp%d" % world,
                                step="student fwd+bwd+Adam, phase-0 L1 vs fixed targets",
                                l2="inputs+activations per step (>5 GB) far exceed the 126 MB L2; no explicit flush",
-                               fast_kernels=not args.no_fast, cta_pair_gemm=bool(pair)),
+                               fast_kernels=not args.no_fast, cta_pair_gemm=bool(pair & 1), wgrad_row_of_taps=bool(pair & 2)),
                    e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, steps=e2e_steps,
                             frames="uint8 NHWC host frames (pinned), copied on the prefetch stream every step",
                             fp32_frames=dict(value=e2e_fp32, h2d_bytes_per_step=h2d_fp32)),
@@ -357,8 +357,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-fast", action="store_true", help="correctness-first kernels only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pair", type=int, default=-1, help="1/0: CTA-pair (cta_group::2) implicit-GEMM kernels on/off "
-                                                         "(default: LBC_PAIR or the library default)")
+    ap.add_argument("--pair", type=int, default=-1, help="kernel variants: bit 0 = CTA-pair (cta_group::2) implicit-GEMM kernels, "
+                                                         "bit 1 = row-of-taps weight gradient (default: LBC_PAIR)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -109,7 +109,14 @@ const char* lbc_build_info(void) {
 int lbc_set_fast_kernels(int enabled) {
   fast::set_enabled((enabled & 1) != 0);
   fast::set_c64_variant((enabled & 2) == 0);   // bit 1 set: keep the generic tap-per-box kernel for 64->64 3x3 convs
-  if (enabled & (4 | 8)) fast::set_pair_mode((enabled & 4) ? 1 : 0);   // bit 2: CTA-pair GEMM kernels on, bit 3: off (neither: keep LBC_PAIR's default)
+  // variant switches (absent bits keep the LBC_PAIR default): 4 / 8 = CTA-pair (cta_group::2) conv GEMMs on / off,
+  // 16 / 32 = row-of-taps weight-gradient kernel on / off
+  int m = fast::pair_mode();
+  if (enabled & 4) m |= 1;
+  if (enabled & 8) m &= ~1;
+  if (enabled & 16) m |= 2;
+  if (enabled & 32) m &= ~2;
+  fast::set_pair_mode(m);
   return 0;
 }
 

@@ -80,7 +80,8 @@ bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const flo
                    float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
                    const bf16* residual, bool relu, bool train, bf16* y, float* negshift, lbc_stream_t s);
 bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
-                 const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s);
+                 const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s,
+                 const float* beta_own = nullptr);   // beta_own: mask_act is relu(this BN's output) -> recomputed from x
 bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s);
 bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           bf16* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, lbc_stream_t s);
@@ -93,7 +94,7 @@ template <class T> struct Fast {
   static bool bn_fwd(const T*, int64_t, int, const float*, const float*, float, float, float*, float*, float*, float*,
                      const T*, bool, bool, T*, float*, float*, lbc_stream_t, int = 0) { return false; }
   static bool bn_bwd(const T*, const T*, const T*, const float*, const float*, const float*, float*, float*, T*, int64_t, int,
-                     float*, lbc_stream_t) { return false; }
+                     float*, lbc_stream_t, const float* = nullptr) { return false; }
   static bool ew(T*, const T*, const T*, int64_t, int, lbc_stream_t) { return false; }
   static bool colsum(const T*, int64_t, int, float*, float*, lbc_stream_t) { return false; }
   static bool pool_fwd(const T*, const float*, const float*, const float*, const float*, T*, uint8_t*, int, int, int, int, int,
@@ -116,9 +117,10 @@ template <> struct Fast<bf16> {
                          negshift, s);
   }
   static bool bn_bwd(const bf16* dy, const bf16* mask, const bf16* x, const float* mean, const float* rstd, const float* gamma,
-                     float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s) {
+                     float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s,
+                     const float* beta_own = nullptr) {
     if (!enabled()) return false;
-    return bn_bwd_bf16(dy, mask, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, sums, s);
+    return bn_bwd_bf16(dy, mask, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, sums, s, beta_own);
   }
   static bool ew(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s) {
     if (!enabled()) return false;

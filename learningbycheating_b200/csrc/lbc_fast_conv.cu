@@ -1794,6 +1794,161 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------- 3x3 weight gradient, row of taps
+// The one-tap kernel above moves 64 KB of operands through L2 per 4.2 MFLOP (64 FLOP/B): with every SM streaming at
+// once that is the L2->SM fabric limit (~12 TB/s), not the tensor pipe.  Here one CTA owns the THREE taps of a kernel
+// row for a (128 co x 128 ci) tile: per 64-pixel K step it loads the dy tile once (16 KB) and three shifted x tiles
+// (48 KB) and issues three MMA groups into three TMEM accumulators (384 columns) -> 98 FLOP/B.
+struct Wgrad3Params {
+  int TW, TH, TN, tiles_w, tiles_h, tiles_n;   // 64-pixel K tile = TN*TH*TW
+  int k_tiles, k_per_split, splits;
+  int co_tiles, ci_tiles;
+  int tap_dh[9], tap_dw[9], tap_map[9];
+  int Co, Ci;
+  float* out;  // [Co][9][Ci] fp32, pre-zeroed
+};
+constexpr int W3_BOX = 64 * 128;   // 64 pixels x 64 channels bf16
+
+template <int STAGES>
+struct Wgrad3Smem {
+  static constexpr int A_ST = 2 * W3_BOX;          // dy: 128 co = 2 boxes
+  static constexpr int B_ST = 3 * 2 * W3_BOX;      // x: 3 taps x 128 ci
+  static constexpr int STAGE_BYTES = A_ST + B_ST;  // 64 KB
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant__ CUtensorMap mX0,
+                   const __grid_constant__ CUtensorMap mX1, const __grid_constant__ CUtensorMap mX2,
+                   const __grid_constant__ CUtensorMap mX3, const Wgrad3Params p) {
+  typedef Wgrad3Smem<STAGES> SP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + SP::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 512;   // 3 accumulators x 128 columns
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this CTA's work: (split, co_tile, kernel row, ci_tile)
+  int id = blockIdx.x;
+  const int ci_tile = id % p.ci_tiles;
+  id /= p.ci_tiles;
+  const int krow = id % 3;
+  id /= 3;
+  const int co_tile = id % p.co_tiles;
+  const int split = id / p.co_tiles;
+  const int kt0 = split * p.k_per_split;
+  int kt1 = kt0 + p.k_per_split;
+  if (kt1 > p.k_tiles) kt1 = p.k_tiles;
+  const int n_k = kt1 - kt0;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        const int w0 = (kt % p.tiles_w) * p.TW;
+        const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.TN;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * SP::STAGE_BYTES;
+        mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
+        tma_load_4d(&mDY, sa, &full[stage], co_tile * 128, w0, h0, n0);
+        tma_load_4d(&mDY, sa + W3_BOX, &full[stage], co_tile * 128 + 64, w0, h0, n0);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const int tap = krow * 3 + t;
+          const int mid = p.tap_map[tap];
+          const CUtensorMap* mx = mid == 0 ? &mX0 : (mid == 1 ? &mX1 : (mid == 2 ? &mX2 : &mX3));
+          uint8_t* sb = sa + SP::A_ST + t * 2 * W3_BOX;
+          tma_load_4d(mx, sb, &full[stage], ci_tile * 128, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+          tma_load_4d(mx, sb + W3_BOX, &full[stage], ci_tile * 128 + 64, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // D=f32, A=B=bf16, both MN-major (bits 15,16), N=128, M=128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < n_k; ++k) {
+      mbar_wait(&full[stage], phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * SP::STAGE_BYTES);
+        const uint64_t ad = umma_desc_mn_sw128(sa, W3_BOX);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const uint64_t bd = umma_desc_mn_sw128(sa + SP::A_ST + t * 2 * W3_BOX, W3_BOX);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)  // 4 x (K=16 pixels): advance two 8-row groups = 2048 B
+            umma_bf16(tmem_base + t * 128, ad + (uint64_t)(kk * (2048 >> 4)), bd + (uint64_t)(kk * (2048 >> 4)), idesc,
+                      (k | kk) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (k == n_k - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (n_k > 0) {
+    const int q = warp & 3;
+    const int co = co_tile * 128 + q * 32 + lane;
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + t * 128 + ch * 32, r);
+        if (co < p.Co) {
+          float* dst = p.out + ((int64_t)co * 9 + krow * 3 + t) * p.Ci + ci_tile * 128 + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // packed fp32 [Co][taps][Ci] -> reference layout [Co][Ci][K][K]
 __global__ void wgrad_unpack_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int Ci, int KK) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1820,6 +1975,86 @@ static void launch_wgrad(const CUtensorMap& mDY, const CUtensorMap* mX, const Wg
   LBC_CUDA(cudaGetLastError());
 }
 
+// bit 1 of the pair/variant mode (LBC_PAIR / lbc_set_fast_kernels bit 4): row-of-taps weight-gradient kernel
+static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch, lbc_stream_t s) {
+  if (!(g_pair_mode & 2)) return false;
+  if (c.K != 3 || c.pad != 1 || (c.Co % 128) || (c.Ci % 128)) return false;
+  Wgrad3Params p;
+  memset(&p, 0, sizeof(p));
+  // 64-pixel K tile {TW, TH, TN}
+  p.TW = pow2_divisor(c.OW, 32);
+  p.TH = pow2_divisor(c.OH, 64 / p.TW);
+  p.TN = 64 / (p.TW * p.TH);
+  if (p.TN > 256) return false;
+  p.tiles_w = c.OW / p.TW;
+  p.tiles_h = c.OH / p.TH;
+  p.tiles_n = (B + p.TN - 1) / p.TN;
+  p.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.co_tiles = c.Co / 128;
+  p.ci_tiles = c.Ci / 128;
+  p.Co = c.Co;
+  p.Ci = c.Ci;
+  p.out = scratch;
+  const int out_tiles = p.co_tiles * p.ci_tiles * 3;
+  int best_splits = 1;
+  double best_cost = 1e30;
+  const int max_splits = p.k_tiles / 8 > 0 ? p.k_tiles / 8 : 1;
+  for (int sp = 1; sp <= max_splits && sp <= 148; ++sp) {
+    int kps = (p.k_tiles + sp - 1) / sp;
+    int real = (p.k_tiles + kps - 1) / kps;
+    int ctas = real * out_tiles;
+    int waves = (ctas + sm_count() - 1) / sm_count();
+    double cost = (double)waves * (kps + 10);   // k iterations per CTA + prologue / 48 K-atomic epilogue
+    if (cost < best_cost) {
+      best_cost = cost;
+      best_splits = sp;
+    }
+  }
+  p.k_per_split = (p.k_tiles + best_splits - 1) / best_splits;
+  p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
+  const int64_t eb = 2;
+  CUtensorMap mDY = make_map_4d(dy, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb,
+                                (int64_t)c.OH * c.OW * c.Co * eb, p.TW, p.TH, p.TN);
+  CUtensorMap mX[4];
+  if (c.stride == 1) {
+    mX[0] = make_map_4d(x, c.Ci, c.W, c.H, B, c.Ci * eb, (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH,
+                        p.TN);
+    mX[1] = mX[2] = mX[3] = mX[0];
+    for (int t = 0; t < 9; ++t) {
+      p.tap_dh[t] = t / 3 - c.pad;
+      p.tap_dw[t] = t % 3 - c.pad;
+      p.tap_map[t] = 0;
+    }
+  } else {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        mX[a * 2 + b] = make_map_4d(x + ((int64_t)a * c.W + b) * c.Ci, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb,
+                                    2 * (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
+    for (int t = 0; t < 9; ++t) {
+      int th = t / 3 - c.pad, tw = t % 3 - c.pad;
+      int a = ((th % 2) + 2) % 2, b = ((tw % 2) + 2) % 2;
+      p.tap_dh[t] = (th - a) / 2;
+      p.tap_dw[t] = (tw - b) / 2;
+      p.tap_map[t] = a * 2 + b;
+    }
+  }
+  typedef Wgrad3Smem<3> SP;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(wgrad3_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    configured = true;
+  }
+  const int64_t wsize = (int64_t)c.Co * 9 * c.Ci;
+  LBC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * wsize, s));
+  const int grid = p.splits * out_tiles;
+  wgrad3_gemm_kernel<3><<<grid, 192, SP::TOTAL, s>>>(mDY, mX[0], mX[1], mX[2], mX[3], p);
+  ++g_launches;
+  wgrad_unpack_kernel<<<(unsigned)((wsize + 255) / 256), 256, 0, s>>>(scratch, dw_ref, c.Co, c.Ci, 9);
+  ++g_launches;
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+
 // x [B,H,W,Ci], dy [B,OH,OW,Co] -> dw_ref fp32 [Co][Ci][K][K]; scratch >= Co*K*K*Ci floats
 bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch,
                      int64_t scratch_floats, lbc_stream_t s) {
@@ -1827,6 +2062,7 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
   const int KK = c.K * c.K;
   const int64_t wsize = (int64_t)c.Co * KK * c.Ci;
   if (wsize > scratch_floats) return false;
+  if (try_wgrad3(c, x, dy, dw_ref, B, scratch, s)) return true;
   WgradParams p;
   memset(&p, 0, sizeof(p));
   ConvGemmParams g;

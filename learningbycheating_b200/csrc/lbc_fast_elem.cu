@@ -316,15 +316,20 @@ bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const flo
 __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
                                                             const uint4* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, int64_t M, int tpr, int rpi,
-                                                            float* partial, int C) {
+                                                            float* partial, int C, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta_own) {
   extern __shared__ float red[];
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
-  float mu[8], s0[8], s1[8];
+  float mu[8], s0[8], s1[8], sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mu[j] = mean[cg * 8 + j];
     s0[j] = s1[j] = 0.f;
+    // beta_own != null: the mask is the ReLU of THIS BatchNorm's own output, act > 0 <=> x*sc + sh > 0 with the very
+    // expressions of bn_apply_kernel -- recomputed from x (already being read) instead of reading the activation
+    sc[j] = beta_own ? gamma[cg * 8 + j] * rstd[cg * 8 + j] : 0.f;
+    sh[j] = beta_own ? beta_own[cg * 8 + j] - mu[j] * sc[j] : 0.f;
   }
   const int64_t stride = (int64_t)gridDim.x * rpi;
 #pragma unroll 2
@@ -332,13 +337,14 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const uint4* __re
     const int64_t i0 = row * tpr + cg;
     const uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
     uint4 a0 = d0;
-    if (act) a0 = ldg_stream(act + i0);
+    if (act && !beta_own) a0 = ldg_stream(act + i0);
     float fd[8], fx[8], fa[8];
     unpack8(d0, fd);
     unpack8(x0, fx);
     unpack8(a0, fa);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      if (beta_own) fa[j] = fx[j] * sc[j] + sh[j];
       float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
       s0[j] += g;
       s1[j] += g * (fx[j] - mu[j]);
@@ -371,11 +377,12 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
                                                            const uint4* __restrict__ x, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ sums, float* dgamma, float* dbeta,
-                                                           uint4* __restrict__ dx, int64_t M, int tpr, int rpi, int C) {
+                                                           uint4* __restrict__ dx, int64_t M, int tpr, int rpi, int C,
+                                                           const float* __restrict__ beta_own) {
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
   // dx = k0*(g - db/M - xhat*dg/M) = k0*g + kb*x + ka,  kb = -k0*rstd*dg/M,  ka = -k0*db/M - kb*mean
-  float k0[8], kb[8], ka[8];
+  float k0[8], kb[8], ka[8], sh[8];
   const float invM = 1.0f / (float)M;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -386,7 +393,8 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
       dbeta[c] = db;
       dgamma[c] = dg;
     }
-    k0[j] = gamma[c] * rs;
+    k0[j] = gamma[c] * rs;            // == sc of bn_apply_kernel
+    sh[j] = beta_own ? beta_own[c] - mu * k0[j] : 0.f;
     kb[j] = -k0[j] * rs * dg * invM;
     ka[j] = -k0[j] * db * invM - kb[j] * mu;
   }
@@ -397,13 +405,14 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
     const int64_t i0 = row * tpr + cg;
     const uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
     uint4 a0 = d0;
-    if (act) a0 = ldg_stream(act + i0);
+    if (act && !beta_own) a0 = ldg_stream(act + i0);
     float fd[8], fx[8], fa[8], o[8];
     unpack8(d0, fd);
     unpack8(x0, fx);
     unpack8(a0, fa);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      if (beta_own) fa[j] = fx[j] * k0[j] + sh[j];
       float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
       o[j] = fmaf(k0[j], g, fmaf(kb[j], fx[j], ka[j]));
     }
@@ -412,17 +421,23 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
 }
 
 bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
-                 const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s) {
+                 const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s,
+                 const float* beta_own) {
   if (C % 8 || C > 2560) return false;
+  static const bool recompute = [] {
+    const char* e = getenv("LBC_BN_MASK_RECOMPUTE");
+    return e ? atoi(e) != 0 : true;
+  }();
+  if (!recompute || !mask_act) beta_own = nullptr;
   RowGeom g = row_geom(M, C, 4);
   float* part = partial_buffer();
   if (!part) return false;
   bn_bwd_reduce_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
-      (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C);
+      (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, gamma, beta_own);
   ++g_launches;
   col_finalize(part, g.grid, 2 * C, sums, s);
   bn_bwd_apply_kernel<<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, gamma,
-                                                  sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C);
+                                                  sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -462,30 +477,40 @@ bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, l
 // ------------------------------------------------------------------------------------------- stem BN+ReLU+MaxPool
 // pool[n,oh,ow,:] = max over the 3x3/s2/p1 window of relu(bn(x)); idx = kh*3+kw of the first maximum.
 // (resnet.py:150-152).  One thread per (output position, 8 channels); the BN+ReLU activation is never written.
+// Both pooling kernels are instruction-bound, not HBM-bound, so: index arithmetic in IdxT (32-bit whenever the element
+// count allows), and the per-channel constants hoisted out of the grid-stride loop (the stride is a multiple of tpr,
+// so a thread keeps its channel group).
+template <typename IdxT>
 __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, uint4* __restrict__ y,
                                                               uint2* __restrict__ idx, int N, int H, int W, int tpr, int OH,
                                                               int OW) {
-  const int64_t total = (int64_t)N * OH * OW * tpr;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int cg = (int)(i % tpr);
-    int64_t p = i / tpr;
-    const int ow = (int)(p % OW);
-    p /= OW;
-    const int oh = (int)(p % OH);
-    const int b = (int)(p / OH);
-    float sc[8], sh[8], best[8];
+  const IdxT total = (IdxT)N * OH * OW * tpr;
+  const IdxT stride = (IdxT)gridDim.x * blockDim.x;   // multiple of tpr (tpr divides 256)
+  IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = (int)(i % (IdxT)tpr);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    sc[j] = gamma[c] * rstd[c];
+    sh[j] = beta[c] - mean[c] * sc[j];
+  }
+  for (; i < total; i += stride) {
+    IdxT p = i / (IdxT)tpr;
+    const int ow = (int)(p % (IdxT)OW);
+    p /= (IdxT)OW;
+    const int oh = (int)(p % (IdxT)OH);
+    const int b = (int)(p / (IdxT)OH);
+    float best[8];
     int bi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
-      sc[j] = gamma[c] * rstd[c];
-      sh[j] = beta[c] - mean[c] * sc[j];
       best[j] = -INFINITY;
       bi[j] = 0;
     }
+    const uint4* xb = x + (int64_t)b * H * W * tpr + cg;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int ih = oh * 2 - 1 + kh;
@@ -495,7 +520,7 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const uint4* __res
         const int iw = ow * 2 - 1 + kw;
         if (iw < 0 || iw >= W) continue;
         float f[8];
-        unpack8(__ldg(x + (((int64_t)b * H + ih) * W + iw) * tpr + cg), f);
+        unpack8(__ldg(xb + (ih * W + iw) * tpr), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v = fmaxf(f[j] * sc[j] + sh[j], 0.f);
@@ -517,36 +542,50 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const uint4* __res
 }
 bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           bf16* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, lbc_stream_t s) {
-  if (C % 8) return false;
+  if (C % 8 || 256 % (C / 8)) return false;
   int64_t total = (int64_t)N * OH * OW * (C / 8);
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
-  bn_relu_maxpool_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y, (uint2*)idx, N, H,
-                                                         W, C / 8, OH, OW);
+  if ((int64_t)N * H * W * (C / 8) < (int64_t)1 << 31)
+    bn_relu_maxpool_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
+                                                                       (uint2*)idx, N, H, W, C / 8, OH, OW);
+  else
+    bn_relu_maxpool_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
+                                                                      (uint2*)idx, N, H, W, C / 8, OH, OW);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
   return true;
 }
 // d(bn-relu output)[n,h,w,:] = sum over the <=4 pooling windows that selected (h,w), times the ReLU mask recomputed
 // from the raw conv output; written as the upstream gradient of the stem BatchNorm.
+template <typename IdxT>
 __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
                                                                const uint4* __restrict__ x, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, uint4* __restrict__ dx, int N,
                                                                int H, int W, int tpr, int OH, int OW) {
-  const int64_t total = (int64_t)N * H * W * tpr;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int cg = (int)(i % tpr);
-    int64_t p = i / tpr;
-    const int iw = (int)(p % W);
-    p /= W;
-    const int ih = (int)(p % H);
-    const int b = (int)(p / H);
+  const IdxT total = (IdxT)N * H * W * tpr;
+  const IdxT stride = (IdxT)gridDim.x * blockDim.x;   // multiple of tpr
+  IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = (int)(i % (IdxT)tpr);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    sc[j] = gamma[c] * rstd[c];
+    sh[j] = beta[c] - mean[c] * sc[j];
+  }
+  for (; i < total; i += stride) {
+    IdxT p = i / (IdxT)tpr;
+    const int iw = (int)(p % (IdxT)W);
+    p /= (IdxT)W;
+    const int ih = (int)(p % (IdxT)H);
+    const int b = (int)(p / (IdxT)H);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int64_t ob = (int64_t)b * OH * OW * tpr + cg;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int t = ih + 1 - kh;
@@ -559,7 +598,7 @@ __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __re
         if (u < 0 || (u & 1)) continue;
         const int ow = u >> 1;
         if (ow >= OW) continue;
-        const int64_t o = (((int64_t)b * OH + oh) * OW + ow) * tpr + cg;
+        const int64_t o = ob + (oh * OW + ow) * tpr;
         const uint2 id = __ldg(idx + o);
         float g[8];
         unpack8(__ldg(dy + o), g);
@@ -575,9 +614,7 @@ __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __re
     unpack8(ldg_stream(x + i), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
-      const float scj = gamma[c] * rstd[c];
-      const float v = f[j] * scj + (beta[c] - mean[c] * scj);
+      const float v = f[j] * sc[j] + sh[j];
       if (!(v > 0.f)) acc[j] = 0.f;
     }
     dx[i] = pack8(acc);
@@ -586,13 +623,17 @@ __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __re
 bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, bf16* dx, int N, int H, int W, int C, int OH, int OW,
                            lbc_stream_t s) {
-  if (C % 8) return false;
+  if (C % 8 || 256 % (C / 8)) return false;
   int64_t total = (int64_t)N * H * W * (C / 8);
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
-  maxpool_relu_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean, rstd, gamma,
-                                                          beta, (uint4*)dx, N, H, W, C / 8, OH, OW);
+  if (total < (int64_t)1 << 31)
+    maxpool_relu_bwd_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean,
+                                                                        rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW);
+  else
+    maxpool_relu_bwd_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean,
+                                                                       rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -603,7 +644,7 @@ bool bn_stats_bf16(const bf16*, int64_t, int, float*, lbc_stream_t) { return fal
 bool bn_apply_bf16(const bf16*, const float*, int64_t, int, const float*, const float*, float, float, float*, float*, float*,
                    float*, const bf16*, bool, bool, bf16*, float*, lbc_stream_t) { return false; }
 bool bn_bwd_bf16(const bf16*, const bf16*, const bf16*, const float*, const float*, const float*, float*, float*, bf16*,
-                 int64_t, int, float*, lbc_stream_t) { return false; }
+                 int64_t, int, float*, lbc_stream_t, const float*) { return false; }
 bool ew_bf16(bf16*, const bf16*, const bf16*, int64_t, int, lbc_stream_t) { return false; }
 float* stat_partial_buffer() { return nullptr; }
 bool col_finalize_bf16(const float*, int, int, float*, lbc_stream_t) { return false; }

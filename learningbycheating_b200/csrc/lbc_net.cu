@@ -426,11 +426,13 @@ class Net : public NetBase {
   }
   // dy_m = dy * (mask_act > 0) when mask_act != null (the ReLU that follows the BN, nn.ReLU(True) backward).
   // Correctness-first path: masks dy in place first; fast path: the mask is fused into both passes, dy untouched.
-  void bn_backward(BNL& bn, T* dy, const T* mask_act, const T* x, T* dx, int64_t M, lbc_stream_t s) {
+  // own_relu: mask_act is relu(bn(x)) of this very BatchNorm (no residual): the fast kernels then recompute the mask
+  // from x instead of reading the activation (2 of the 7 tensor passes disappear).
+  void bn_backward(BNL& bn, T* dy, const T* mask_act, const T* x, T* dx, int64_t M, lbc_stream_t s, bool own_relu = false) {
     // algorithmic bytes: reduce pass reads dy,(mask),x ; apply pass reads dy,(mask),x writes dx
-    ProfScope ps("bn_bwd", s, 0, (double)M * bn.C * sizeof(T) * (5 + (mask_act ? 2 : 0)));
+    ProfScope ps("bn_bwd", s, 0, (double)M * bn.C * sizeof(T) * (5 + (mask_act && !own_relu ? 2 : 0)));
     if (fast::Fast<T>::bn_bwd(dy, mask_act, x, bn.mean, bn.rstd, P + bn.g_off, G + bn.g_off, G + bn.b_off, dx, M, bn.C,
-                              bn_sums, s))
+                              bn_sums, s, own_relu ? P + bn.b_off : nullptr))
       return;
     if (mask_act) ref::relu_mask_inplace<T>(s, dy, mask_act, M * bn.C);
     ref::bn_bwd<T>(s, dy, x, bn.mean, bn.rstd, P + bn.g_off, G + bn.g_off, G + bn.b_off, dx, M, bn.C, ws_d);
@@ -666,7 +668,7 @@ class Net : public NetBase {
       bn_backward(b.b2, gcur, b.out, b.r2, tA, M, s);  // tA = d r2
       conv_backward_weight(b.c2, b.a1, tA, B, s);
       conv_backward_data(b.c2, tA, tB, B, false, s);   // tB = d a1 (before the ReLU mask a1 > 0)
-      bn_backward(b.b1, tB, b.a1, b.r1, tA, M, s);     // tA = d r1
+      bn_backward(b.b1, tB, b.a1, b.r1, tA, M, s, true);   // tA = d r1 (mask a1 > 0 recomputed from r1)
       conv_backward_weight(b.c1, b.xin, tA, B, s);
       if (b.ds) {
         bn_backward(b.bd, gcur, b.out, b.rd, tB, M, s);  // tB = d rd (d a1 is dead by now)

@@ -211,26 +211,29 @@ FAST_CASES = [
 ]
 
 
-def _pair_default():
+def _variant_default():
     import os
-    return 4 if int(os.environ.get("LBC_PAIR", "0") or 0) & 1 else 8
+    m = int(os.environ.get("LBC_PAIR", "0") or 0)
+    return (4 if m & 1 else 8) | (16 if m & 2 else 32)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("variant", ["base", "pair", "wgrad3"])
 @pytest.mark.parametrize("case", FAST_CASES)
-def test_tcgen05_conv_gpu(backend, case, pair):
-    """fast (tcgen05) kernels vs torch on bf16-rounded operands; wgrad still runs the correctness-first kernel.
-    pair=1: the CTA-pair (cta_group::2, 256-row MMA) variant of the >= 128-wide implicit GEMMs."""
+def test_tcgen05_conv_gpu(backend, case, variant):
+    """fast (tcgen05) kernels (forward, data gradient, weight gradient) vs torch on bf16-rounded operands.
+    pair: the CTA-pair (cta_group::2, 256-row MMA) variant of the >= 128-wide implicit GEMMs;
+    wgrad3: the row-of-taps weight-gradient kernel (three taps share one dy tile)."""
     assert backend == "cuda"
     from learningbycheating_b200 import _lib
-    _lib.check(_lib.lib().lbc_set_fast_kernels(1 | (4 if pair else 8)))
+    bits = {"base": 8 | 32, "pair": 4 | 32, "wgrad3": 8 | 16}[variant]
+    _lib.check(_lib.lib().lbc_set_fast_kernels(1 | bits))
     try:
         n0 = _lib.lib().lbc_kernel_launch_count()
         _conv_case("cuda", case, 1, 2e-2)
         assert _lib.lib().lbc_kernel_launch_count() > n0
     finally:
-        _lib.check(_lib.lib().lbc_set_fast_kernels(1 | _pair_default()))
+        _lib.check(_lib.lib().lbc_set_fast_kernels(1 | _variant_default()))
 
 
 @pytest.mark.gpu
