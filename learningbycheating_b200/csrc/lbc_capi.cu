@@ -116,6 +116,8 @@ int lbc_set_fast_kernels(int enabled) {
   if (enabled & 8) m &= ~1;
   if (enabled & 16) m |= 2;
   if (enabled & 32) m &= ~2;
+  if (enabled & 64) m |= 4;     // 64 / 128 = CTA-pair variant of the row-of-taps weight gradient on / off
+  if (enabled & 128) m &= ~4;
   fast::set_pair_mode(m);
   return 0;
 }

@@ -255,7 +255,10 @@ template <int BN, int STAGES, bool PAIR = false>
 struct SmemPlan {
   static constexpr int B_BYTES = PAIR ? BN * 64 : BN * 128;   // CTA pair: each CTA stages BN/2 rows of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
+  // epilogue staging: the whole 128 x BN bf16 tile, or (pair, BN = 256) two passes of 128 columns through half the
+  // space, which buys the fifth operand stage the pair kernel needs to cover its TMA round trip
+  static constexpr int OUT_PASSES = (PAIR && BN == 256) ? 2 : 1;
+  static constexpr int OUT_BYTES = (BN / 64) * A_BYTES / OUT_PASSES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
   static constexpr int RED_OFF = BAR_OFF + 256;       // 128 x 4 floats: column-statistics scratch
   static constexpr int TOTAL = RED_OFF + 2048 + 1024;  // barriers + scratch + alignment slack
@@ -424,92 +427,101 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
       mbar_wait(&tfull[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging buffer free again
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      constexpr int PASSES = SP::OUT_PASSES;
+      constexpr int CW = BN / PASSES;   // columns staged per pass
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(taddr + ch * 32, r);
-        const int col0 = n_tile * BN + ch * 32;
-        uint8_t* rowp = out_stage + (ch >> 1) * A_BYTES + row * 128;
+      for (int hp = 0; hp < PASSES; ++hp) {
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging buffer free again
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+        for (int cl = 0; cl < CW / 32; ++cl) {
+          const int ch = hp * (CW / 32) + cl;
+          uint32_t r[32];
+          tmem_ld32(taddr + ch * 32, r);
+          const int col0 = n_tile * BN + ch * 32;
+          uint8_t* rowp = out_stage + (cl >> 1) * A_BYTES + row * 128;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t pk[4];
+          for (int j = 0; j < 4; ++j) {
+            uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float a = __uint_as_float(r[j * 8 + e * 2]);
-            float b = __uint_as_float(r[j * 8 + e * 2 + 1]);
-            if (p.bias) {
-              a += __ldg(p.bias + col0 + j * 8 + e * 2);
-              b += __ldg(p.bias + col0 + j * 8 + e * 2 + 1);
+            for (int e = 0; e < 4; ++e) {
+              float a = __uint_as_float(r[j * 8 + e * 2]);
+              float b = __uint_as_float(r[j * 8 + e * 2 + 1]);
+              if (p.bias) {
+                a += __ldg(p.bias + col0 + j * 8 + e * 2);
+                b += __ldg(p.bias + col0 + j * 8 + e * 2 + 1);
+              }
+              if (p.relu) {
+                a = fmaxf(a, 0.f);
+                b = fmaxf(b, 0.f);
+              }
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            if (p.relu) {
-              a = fmaxf(a, 0.f);
-              b = fmaxf(b, 0.f);
-            }
-            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            const int chunk16 = (cl & 1) * 4 + j;  // 16-byte chunk index inside the 128-byte row
+            *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-          const int chunk16 = (ch & 1) * 4 + j;  // 16-byte chunk index inside the 128-byte row
-          *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      if constexpr (PAIR)
-        mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));  // on the leader's barrier (256 arrivals per phase)
-      else
-        mbar_arrive(&tempty[acc]);  // accumulator drained: the MMA warp may reuse it
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (issuer) {
+        if (hp == PASSES - 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if constexpr (PAIR)
+            mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));  // on the leader's barrier (256 arrivals per phase)
+          else
+            mbar_arrive(&tempty[acc]);  // accumulator drained: the MMA warp may reuse it
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
 #pragma unroll
-        for (int b = 0; b < BN / 64; ++b) tma_store_4d(&mO, out_stage + b * A_BYTES, n_tile * BN + b * 64, w0, h0, n0);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      if (p.stat_partial && m_tile < tiles_m) {
-        // per-channel sum / sum of squares of this tile's bf16 outputs, read back from the staging tile
-        constexpr int PAIRS = BN / 2, TPP = 128 / PAIRS, RPT = 128 / TPP;
-        float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
-        const int e = threadIdx.x - 64;
-        const int pair = e % PAIRS, sub = e / PAIRS;
-        const int col = 2 * pair;
-        const uint8_t* boxp = out_stage + (col >> 6) * A_BYTES + ((col & 7) >> 1) * 4;
-        const int chunk = (col & 63) >> 3;
-        int nvalid = p.valid_n - n0;
-        nvalid = nvalid < 0 ? 0 : (nvalid > p.TN ? p.TN : nvalid);
-        const int valid_rows = nvalid * p.TH * p.TW;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        for (int r = sub * RPT; r < (sub + 1) * RPT && r < valid_rows; ++r) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(boxp + r * 128 + ((chunk ^ (r & 7)) << 4));
-          const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
-          s0 += a;
-          s1 += b;
-          q0 += a * a;
-          q1 += b * b;
+          for (int b = 0; b < CW / 64; ++b)
+            tma_store_4d(&mO, out_stage + b * A_BYTES, n_tile * BN + hp * CW + b * 64, w0, h0, n0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (TPP > 1) {
-          red[e * 4 + 0] = s0;
-          red[e * 4 + 1] = s1;
-          red[e * 4 + 2] = q0;
-          red[e * 4 + 3] = q1;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (p.stat_partial && m_tile < tiles_m) {
+          // per-channel sum / sum of squares of this pass's bf16 outputs, read back from the staging tile
+          constexpr int PAIRS = CW / 2, TPP = 128 / PAIRS, RPT = 128 / TPP;
+          float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
+          const int e = threadIdx.x - 64;
+          const int pair = e % PAIRS, sub = e / PAIRS;
+          const int col = 2 * pair;
+          const uint8_t* boxp = out_stage + (col >> 6) * A_BYTES + ((col & 7) >> 1) * 4;
+          const int chunk = (col & 63) >> 3;
+          int nvalid = p.valid_n - n0;
+          nvalid = nvalid < 0 ? 0 : (nvalid > p.TN ? p.TN : nvalid);
+          const int valid_rows = nvalid * p.TH * p.TW;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          for (int r = sub * RPT; r < (sub + 1) * RPT && r < valid_rows; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(boxp + r * 128 + ((chunk ^ (r & 7)) << 4));
+            const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+            s0 += a;
+            s1 += b;
+            q0 += a * a;
+            q1 += b * b;
+          }
+          if (TPP > 1) {
+            red[e * 4 + 0] = s0;
+            red[e * 4 + 1] = s1;
+            red[e * 4 + 2] = q0;
+            red[e * 4 + 3] = q1;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (sub == 0) {
+#pragma unroll
+              for (int t2 = 1; t2 < TPP; ++t2) {
+                s0 += red[(t2 * PAIRS + pair) * 4 + 0];
+                s1 += red[(t2 * PAIRS + pair) * 4 + 1];
+                q0 += red[(t2 * PAIRS + pair) * 4 + 2];
+                q1 += red[(t2 * PAIRS + pair) * 4 + 3];
+              }
+            }
+          }
           if (sub == 0) {
-#pragma unroll
-            for (int t2 = 1; t2 < TPP; ++t2) {
-              s0 += red[(t2 * PAIRS + pair) * 4 + 0];
-              s1 += red[(t2 * PAIRS + pair) * 4 + 1];
-              q0 += red[(t2 * PAIRS + pair) * 4 + 2];
-              q1 += red[(t2 * PAIRS + pair) * 4 + 3];
-            }
+            float* dst = p.stat_partial + (int64_t)m_tile * 2 * p.stat_C + n_tile * BN + hp * CW + col;
+            dst[0] = s0;
+            dst[1] = s1;
+            dst[p.stat_C] = q0;
+            dst[p.stat_C + 1] = q1;
           }
-        }
-        if (sub == 0) {
-          float* dst = p.stat_partial + (int64_t)m_tile * 2 * p.stat_C + n_tile * BN + col;
-          dst[0] = s0;
-          dst[1] = s1;
-          dst[p.stat_C] = q0;
-          dst[p.stat_C + 1] = q1;
         }
       }
     }
@@ -1241,7 +1253,7 @@ static void dispatch_gemm(int BN, const CUtensorMap* mA, const void* wbase, int6
     if (BN == 128)
       launch_gemm_pair<128, 7>(mA, mB, mO, p, s);
     else
-      launch_gemm_pair<256, 4>(mA, mB, mO, p, s);
+      launch_gemm_pair<256, 5>(mA, mB, mO, p, s);
     return;
   }
   CUtensorMap mB = make_map_2d(wbase, wK, wrows, BN);
@@ -1795,35 +1807,40 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------- 3x3 weight gradient, row of taps
-// The one-tap kernel above moves 64 KB of operands through L2 per 4.2 MFLOP (64 FLOP/B): with every SM streaming at
-// once that is the L2->SM fabric limit (~12 TB/s), not the tensor pipe.  Here one CTA owns the THREE taps of a kernel
-// row for a (128 co x 128 ci) tile: per 64-pixel K step it loads the dy tile once (16 KB) and three shifted x tiles
-// (48 KB) and issues three MMA groups into three TMEM accumulators (384 columns) -> 98 FLOP/B.
+// The one-tap kernel above moves 64 KB of operands into the SM per 4.2 MFLOP (64 FLOP/B).  Measured on the B200 one SM
+// ingests ~65-70 B/clk from L2 (wgrad_gemm_kernel<128,3>: 64 KB per ~950 clk), so that kernel runs at half the
+// tensor rate.  Here one CTA owns the THREE taps of a kernel row for a (128 co x 128 ci) tile: per 64-pixel K step
+// it loads the dy tile once (16 KB) and three shifted x tiles (48 KB) and issues three MMA groups into three TMEM
+// accumulators (384 columns) -> 98 FLOP/B.  PAIR: two CTAs (co tiles 2c, 2c+1) share the x tiles through one
+// 256-row cta_group::2 MMA, each staging its dy tile and HALF of every x tile (40 KB per step, 157 FLOP/B).
+// Split-K partials are written with plain stores to partial[split][Co][9][Ci] and summed by wgrad3_reduce_kernel
+// (fp32 atomics from 49 splits cost more than the whole K loop).
 struct Wgrad3Params {
   int TW, TH, TN, tiles_w, tiles_h, tiles_n;   // 64-pixel K tile = TN*TH*TW
   int k_tiles, k_per_split, splits;
   int co_tiles, ci_tiles;
   int tap_dh[9], tap_dw[9], tap_map[9];
   int Co, Ci;
-  float* out;  // [Co][9][Ci] fp32, pre-zeroed
+  float* out;  // [splits][Co][9][Ci] fp32 partials
 };
 constexpr int W3_BOX = 64 * 128;   // 64 pixels x 64 channels bf16
 
-template <int STAGES>
+template <int STAGES, bool PAIR>
 struct Wgrad3Smem {
-  static constexpr int A_ST = 2 * W3_BOX;          // dy: 128 co = 2 boxes
-  static constexpr int B_ST = 3 * 2 * W3_BOX;      // x: 3 taps x 128 ci
-  static constexpr int STAGE_BYTES = A_ST + B_ST;  // 64 KB
+  static constexpr int A_ST = 2 * W3_BOX;                    // dy: 128 co = 2 boxes
+  static constexpr int B_TAP = (PAIR ? 1 : 2) * W3_BOX;      // x per tap: 128 ci (pair: this CTA's 64)
+  static constexpr int B_ST = 3 * B_TAP;
+  static constexpr int STAGE_BYTES = A_ST + B_ST;            // 64 KB (pair: 40 KB)
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
-template <int STAGES>
+template <int STAGES, bool PAIR>
 __global__ void __launch_bounds__(192, 1)
 wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant__ CUtensorMap mX0,
                    const __grid_constant__ CUtensorMap mX1, const __grid_constant__ CUtensorMap mX2,
                    const __grid_constant__ CUtensorMap mX3, const Wgrad3Params p) {
-  typedef Wgrad3Smem<STAGES> SP;
+  typedef Wgrad3Smem<STAGES, PAIR> SP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + SP::BAR_OFF);
@@ -1843,23 +1860,34 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (PAIR)
+    cluster_sync_all();
+  else
+    __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  // this CTA's work: (split, co_tile, kernel row, ci_tile)
-  int id = blockIdx.x;
+  // this CTA's work: (split, co tile [pair: co-tile pair + rank], kernel row, ci_tile)
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  int id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int ci_tile = id % p.ci_tiles;
   id /= p.ci_tiles;
   const int krow = id % 3;
   id /= 3;
-  const int co_tile = id % p.co_tiles;
-  const int split = id / p.co_tiles;
+  const int co_groups = PAIR ? p.co_tiles / 2 : p.co_tiles;
+  const int co_tile = PAIR ? 2 * (id % co_groups) + (int)crank : id % co_groups;
+  const int split = id / co_groups;
   const int kt0 = split * p.k_per_split;
   int kt1 = kt0 + p.k_per_split;
   if (kt1 > p.k_tiles) kt1 = p.k_tiles;
@@ -1875,17 +1903,32 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
         const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.TN;
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = smem + stage * SP::STAGE_BYTES;
-        mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
-        tma_load_4d(&mDY, sa, &full[stage], co_tile * 128, w0, h0, n0);
-        tma_load_4d(&mDY, sa + W3_BOX, &full[stage], co_tile * 128 + 64, w0, h0, n0);
+        if constexpr (PAIR) {
+          if (crank == 0) mbar_expect_tx(&full[stage], 2 * SP::STAGE_BYTES);
+          const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+          tma_load_4d_pair(&mDY, sa, lead_full, co_tile * 128, w0, h0, n0);
+          tma_load_4d_pair(&mDY, sa + W3_BOX, lead_full, co_tile * 128 + 64, w0, h0, n0);
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          const int tap = krow * 3 + t;
-          const int mid = p.tap_map[tap];
-          const CUtensorMap* mx = mid == 0 ? &mX0 : (mid == 1 ? &mX1 : (mid == 2 ? &mX2 : &mX3));
-          uint8_t* sb = sa + SP::A_ST + t * 2 * W3_BOX;
-          tma_load_4d(mx, sb, &full[stage], ci_tile * 128, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-          tma_load_4d(mx, sb + W3_BOX, &full[stage], ci_tile * 128 + 64, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+          for (int t = 0; t < 3; ++t) {
+            const int tap = krow * 3 + t;
+            const int mid = p.tap_map[tap];
+            const CUtensorMap* mx = mid == 0 ? &mX0 : (mid == 1 ? &mX1 : (mid == 2 ? &mX2 : &mX3));
+            tma_load_4d_pair(mx, sa + SP::A_ST + t * SP::B_TAP, lead_full, ci_tile * 128 + (int)crank * 64, w0 + p.tap_dw[tap],
+                             h0 + p.tap_dh[tap], n0);
+          }
+        } else {
+          mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
+          tma_load_4d(&mDY, sa, &full[stage], co_tile * 128, w0, h0, n0);
+          tma_load_4d(&mDY, sa + W3_BOX, &full[stage], co_tile * 128 + 64, w0, h0, n0);
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            const int tap = krow * 3 + t;
+            const int mid = p.tap_map[tap];
+            const CUtensorMap* mx = mid == 0 ? &mX0 : (mid == 1 ? &mX1 : (mid == 2 ? &mX2 : &mX3));
+            uint8_t* sb = sa + SP::A_ST + t * SP::B_TAP;
+            tma_load_4d(mx, sb, &full[stage], ci_tile * 128, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+            tma_load_4d(mx, sb + W3_BOX, &full[stage], ci_tile * 128 + 64, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+          }
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -1894,12 +1937,12 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // D=f32, A=B=bf16, both MN-major (bits 15,16), N=128, M=128
+    // D=f32, A=B=bf16, both MN-major (bits 15,16), N=128, M=128 (pair: 256 over the two CTAs)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
-                           ((uint32_t)(128 >> 4) << 24);
+                           ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
-    for (int k = 0; k < n_k; ++k) {
+    for (int k = 0; k < n_k && crank == 0; ++k) {
       mbar_wait(&full[stage], phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
@@ -1907,14 +1950,24 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
         const uint64_t ad = umma_desc_mn_sw128(sa, W3_BOX);
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const uint64_t bd = umma_desc_mn_sw128(sa + SP::A_ST + t * 2 * W3_BOX, W3_BOX);
+          const uint64_t bd = umma_desc_mn_sw128(sa + SP::A_ST + t * SP::B_TAP, W3_BOX);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)  // 4 x (K=16 pixels): advance two 8-row groups = 2048 B
-            umma_bf16(tmem_base + t * 128, ad + (uint64_t)(kk * (2048 >> 4)), bd + (uint64_t)(kk * (2048 >> 4)), idesc,
-                      (k | kk) != 0);
+          for (int kk = 0; kk < 4; ++kk) {  // 4 x (K=16 pixels): advance two 8-row groups = 2048 B
+            if constexpr (PAIR)
+              umma_bf16_pair(tmem_base + t * 128, ad + (uint64_t)(kk * (2048 >> 4)), bd + (uint64_t)(kk * (2048 >> 4)), idesc,
+                             (k | kk) != 0);
+            else
+              umma_bf16(tmem_base + t * 128, ad + (uint64_t)(kk * (2048 >> 4)), bd + (uint64_t)(kk * (2048 >> 4)), idesc,
+                        (k | kk) != 0);
+          }
         }
-        umma_commit(&empty[stage]);
-        if (k == n_k - 1) umma_commit(tfull);
+        if constexpr (PAIR) {
+          umma_commit_pair(&empty[stage]);
+          if (k == n_k - 1) umma_commit_pair(tfull);
+        } else {
+          umma_commit(&empty[stage]);
+          if (k == n_k - 1) umma_commit(tfull);
+        }
       }
       __syncwarp();
       if (++stage == STAGES) {
@@ -1935,18 +1988,41 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
         uint32_t r[32];
         tmem_ld32(taddr + t * 128 + ch * 32, r);
         if (co < p.Co) {
-          float* dst = p.out + ((int64_t)co * 9 + krow * 3 + t) * p.Ci + ci_tile * 128 + ch * 32;
+          float4* dst = reinterpret_cast<float4*>(p.out + (((int64_t)split * p.Co + co) * 9 + krow * 3 + t) * p.Ci +
+                                                  ci_tile * 128 + ch * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
         }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  if constexpr (PAIR) {
+    __syncwarp();
+    cluster_sync_all();
+    if (warp == 1)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  } else {
+    __syncthreads();
+    if (warp == 1) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
   }
+}
+// dst[co][ci][t] (reference layout) = sum_split partial[split][co][t][ci]; threads walk the partials in storage order
+__global__ void wgrad3_reduce_kernel(const float* __restrict__ part, float* __restrict__ dst, int Co, int Ci, int splits) {
+  const int64_t n = (int64_t)Co * 9 * Ci;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int s = 0; s < splits; ++s) a += part[(int64_t)s * n + i];
+  const int ci = (int)(i % Ci);
+  const int64_t r = i / Ci;
+  const int t = (int)(r % 9);
+  const int64_t co = r / 9;
+  dst[(co * Ci + ci) * 9 + t] = a;
 }
 
 // packed fp32 [Co][taps][Ci] -> reference layout [Co][Ci][K][K]
@@ -1976,8 +2052,88 @@ static void launch_wgrad(const CUtensorMap& mDY, const CUtensorMap* mX, const Wg
 }
 
 // bit 1 of the pair/variant mode (LBC_PAIR / lbc_set_fast_kernels bit 4): row-of-taps weight-gradient kernel
+// (bit 2: its CTA-pair variant where Co % 256 == 0)
+static float* wgrad3_partials(int64_t floats) {   // [splits][Co][9][Ci] scratch, grown on demand (single stream)
+  static float* buf = nullptr;
+  static int64_t cap = 0;
+  if (floats > cap) {
+    if (buf) {
+      cudaDeviceSynchronize();
+      cudaFree(buf);
+    }
+    void* q = nullptr;
+    if (cudaMalloc(&q, sizeof(float) * (size_t)floats) != cudaSuccess) {
+      cudaGetLastError();
+      buf = nullptr;
+      cap = 0;
+      return nullptr;
+    }
+    buf = (float*)q;
+    cap = floats;
+  }
+  return buf;
+}
+template <int STAGES, bool PAIR>
+static void launch_wgrad3(const CUtensorMap& mDY, const CUtensorMap* mX, const Wgrad3Params& p, int grid, lbc_stream_t s) {
+  typedef Wgrad3Smem<STAGES, PAIR> SP;
+  static_assert(SP::TOTAL <= 232448, "wgrad3 smem plan exceeds 227 KB");
+  auto kern = wgrad3_gemm_kernel<STAGES, PAIR>;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    configured = true;
+  }
+  if (!PAIR) {
+    kern<<<grid, 192, SP::TOTAL, s>>>(mDY, mX[0], mX[1], mX[2], mX[3], p);
+  } else {
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(192, 1, 1);
+    cfg.dynamicSmemBytes = SP::TOTAL;
+    cfg.stream = (cudaStream_t)s;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LBC_CUDA(cudaLaunchKernelEx(&cfg, kern, mDY, mX[0], mX[1], mX[2], mX[3], p));
+  }
+  ++g_launches;
+}
+static int wgrad3_pair_slots() {
+  static int slots = [] {
+    typedef Wgrad3Smem<5, true> SP;
+    auto kern = wgrad3_gemm_kernel<5, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2), 1, 1);
+    cfg.blockDim = dim3(192, 1, 1);
+    cfg.dynamicSmemBytes = SP::TOTAL;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = sm_count() / 2;
+    }
+    if (n > sm_count() / 2) n = sm_count() / 2;
+    return 2 * n;
+  }();
+  return slots;
+}
 static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch, lbc_stream_t s) {
+  (void)scratch;
   if (!(g_pair_mode & 2)) return false;
+  const bool pair = (g_pair_mode & 4) && (c.Co % 256 == 0);
   if (c.K != 3 || c.pad != 1 || (c.Co % 128) || (c.Ci % 128)) return false;
   Wgrad3Params p;
   memset(&p, 0, sizeof(p));
@@ -1994,8 +2150,8 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
   p.ci_tiles = c.Ci / 128;
   p.Co = c.Co;
   p.Ci = c.Ci;
-  p.out = scratch;
   const int out_tiles = p.co_tiles * p.ci_tiles * 3;
+  const int slots = pair ? wgrad3_pair_slots() : sm_count();   // CTAs resident at once (one per SM; clusters may fit fewer)
   int best_splits = 1;
   double best_cost = 1e30;
   const int max_splits = p.k_tiles / 8 > 0 ? p.k_tiles / 8 : 1;
@@ -2003,8 +2159,8 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
     int kps = (p.k_tiles + sp - 1) / sp;
     int real = (p.k_tiles + kps - 1) / kps;
     int ctas = real * out_tiles;
-    int waves = (ctas + sm_count() - 1) / sm_count();
-    double cost = (double)waves * (kps + 10);   // k iterations per CTA + prologue / 48 K-atomic epilogue
+    int waves = (ctas + slots - 1) / slots;
+    double cost = (double)waves * (kps + 6);   // k iterations per CTA + prologue / epilogue
     if (cost < best_cost) {
       best_cost = cost;
       best_splits = sp;
@@ -2038,18 +2194,15 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
       p.tap_map[t] = a * 2 + b;
     }
   }
-  typedef Wgrad3Smem<3> SP;
-  static bool configured = false;
-  if (!configured) {
-    LBC_CUDA(cudaFuncSetAttribute(wgrad3_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
-    configured = true;
-  }
   const int64_t wsize = (int64_t)c.Co * 9 * c.Ci;
-  LBC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * wsize, s));
-  const int grid = p.splits * out_tiles;
-  wgrad3_gemm_kernel<3><<<grid, 192, SP::TOTAL, s>>>(mDY, mX[0], mX[1], mX[2], mX[3], p);
-  ++g_launches;
-  wgrad_unpack_kernel<<<(unsigned)((wsize + 255) / 256), 256, 0, s>>>(scratch, dw_ref, c.Co, c.Ci, 9);
+  p.out = wgrad3_partials((int64_t)p.splits * wsize);
+  if (!p.out) return false;
+  const int grid = p.splits * out_tiles;   // pair: consecutive blocks (2c, 2c+1) form the cluster of co tiles (2c', 2c'+1)
+  if (pair)
+    launch_wgrad3<5, true>(mDY, mX, p, grid, s);
+  else
+    launch_wgrad3<3, false>(mDY, mX, p, grid, s);
+  wgrad3_reduce_kernel<<<(unsigned)((wsize + 255) / 256), 256, 0, s>>>(p.out, dw_ref, c.Co, c.Ci, p.splits);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
   return true;

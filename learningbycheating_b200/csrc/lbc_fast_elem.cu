@@ -313,7 +313,8 @@ bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const flo
 
 // ------------------------------------------------------------------------------------------- BN backward
 // pass 1: sums[0..C) += sum dy_m ; sums[C..2C) += sum dy_m * xhat,  dy_m = dy * (act > 0) when act != null
-__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
+template <bool OWN>
+__global__ void __launch_bounds__(256, OWN ? 3 : 4) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
                                                             const uint4* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, int64_t M, int tpr, int rpi,
                                                             float* partial, int C, const float* __restrict__ gamma,
@@ -328,24 +329,24 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const uint4* __re
     s0[j] = s1[j] = 0.f;
     // beta_own != null: the mask is the ReLU of THIS BatchNorm's own output, act > 0 <=> x*sc + sh > 0 with the very
     // expressions of bn_apply_kernel -- recomputed from x (already being read) instead of reading the activation
-    sc[j] = beta_own ? gamma[cg * 8 + j] * rstd[cg * 8 + j] : 0.f;
-    sh[j] = beta_own ? beta_own[cg * 8 + j] - mu[j] * sc[j] : 0.f;
+    sc[j] = OWN ? gamma[cg * 8 + j] * rstd[cg * 8 + j] : 0.f;
+    sh[j] = OWN ? beta_own[cg * 8 + j] - mu[j] * sc[j] : 0.f;
   }
   const int64_t stride = (int64_t)gridDim.x * rpi;
-#pragma unroll 2
+#pragma unroll(OWN ? 4 : 2)
   for (int64_t row = (int64_t)blockIdx.x * rpi + r; row < M; row += stride) {
     const int64_t i0 = row * tpr + cg;
     const uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
     uint4 a0 = d0;
-    if (act && !beta_own) a0 = ldg_stream(act + i0);
+    if (!OWN && act) a0 = ldg_stream(act + i0);
     float fd[8], fx[8], fa[8];
     unpack8(d0, fd);
     unpack8(x0, fx);
     unpack8(a0, fa);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (beta_own) fa[j] = fx[j] * sc[j] + sh[j];
-      float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
+      if (OWN) fa[j] = fx[j] * sc[j] + sh[j];
+      float g = ((OWN || act) && !(fa[j] > 0.f)) ? 0.f : fd[j];
       s0[j] += g;
       s1[j] += g * (fx[j] - mu[j]);
     }
@@ -373,6 +374,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const uint4* __re
   }
 }
 // pass 2: dx = gamma*rstd*(dy_m - dbeta/M - xhat*dgamma/M); block 0 also publishes dgamma / dbeta
+template <bool OWN>
 __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
                                                            const uint4* __restrict__ x, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
       dgamma[c] = dg;
     }
     k0[j] = gamma[c] * rs;            // == sc of bn_apply_kernel
-    sh[j] = beta_own ? beta_own[c] - mu * k0[j] : 0.f;
+    sh[j] = OWN ? beta_own[c] - mu * k0[j] : 0.f;
     kb[j] = -k0[j] * rs * dg * invM;
     ka[j] = -k0[j] * db * invM - kb[j] * mu;
   }
@@ -405,15 +407,15 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
     const int64_t i0 = row * tpr + cg;
     const uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
     uint4 a0 = d0;
-    if (act && !beta_own) a0 = ldg_stream(act + i0);
+    if (!OWN && act) a0 = ldg_stream(act + i0);
     float fd[8], fx[8], fa[8], o[8];
     unpack8(d0, fd);
     unpack8(x0, fx);
     unpack8(a0, fa);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (beta_own) fa[j] = fx[j] * k0[j] + sh[j];
-      float g = (act && !(fa[j] > 0.f)) ? 0.f : fd[j];
+      if (OWN) fa[j] = fx[j] * k0[j] + sh[j];
+      float g = ((OWN || act) && !(fa[j] > 0.f)) ? 0.f : fd[j];
       o[j] = fmaf(k0[j], g, fmaf(kb[j], fx[j], ka[j]));
     }
     dx[i0] = pack8(o);
@@ -432,12 +434,24 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
   RowGeom g = row_geom(M, C, 4);
   float* part = partial_buffer();
   if (!part) return false;
-  bn_bwd_reduce_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
+  if (beta_own) {
+    RowGeom g3 = row_geom(M, C, 3);
+    bn_bwd_reduce_kernel<true><<<g3.grid, g3.threads, g3.threads * 16 * sizeof(float), s>>>(
+        (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g3.tpr, g3.rpi, part, C, gamma, beta_own);
+    ++g_launches;
+    col_finalize(part, g3.grid, 2 * C, sums, s);
+    bn_bwd_apply_kernel<true><<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd,
+                                                          gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own);
+    ++g_launches;
+    LBC_CUDA(cudaGetLastError());
+    return true;
+  }
+  bn_bwd_reduce_kernel<false><<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
       (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, gamma, beta_own);
   ++g_launches;
   col_finalize(part, g.grid, 2 * C, sums, s);
-  bn_bwd_apply_kernel<<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, gamma,
-                                                  sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own);
+  bn_bwd_apply_kernel<false><<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd,
+                                                         gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
   return true;

@@ -214,11 +214,11 @@ FAST_CASES = [
 def _variant_default():
     import os
     m = int(os.environ.get("LBC_PAIR", "0") or 0)
-    return (4 if m & 1 else 8) | (16 if m & 2 else 32)
+    return (4 if m & 1 else 8) | (16 if m & 2 else 32) | (64 if m & 4 else 128)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["base", "pair", "wgrad3"])
+@pytest.mark.parametrize("variant", ["base", "pair", "wgrad3", "wgrad3pair"])
 @pytest.mark.parametrize("case", FAST_CASES)
 def test_tcgen05_conv_gpu(backend, case, variant):
     """fast (tcgen05) kernels (forward, data gradient, weight gradient) vs torch on bf16-rounded operands.
@@ -226,7 +226,7 @@ def test_tcgen05_conv_gpu(backend, case, variant):
     wgrad3: the row-of-taps weight-gradient kernel (three taps share one dy tile)."""
     assert backend == "cuda"
     from learningbycheating_b200 import _lib
-    bits = {"base": 8 | 32, "pair": 4 | 32, "wgrad3": 8 | 16}[variant]
+    bits = {"base": 8 | 32 | 128, "pair": 4 | 32 | 128, "wgrad3": 8 | 16 | 128, "wgrad3pair": 8 | 16 | 64}[variant]
     _lib.check(_lib.lib().lbc_set_fast_kernels(1 | bits))
     try:
         n0 = _lib.lib().lbc_kernel_launch_count()
