@@ -174,7 +174,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
-    pair = args.pair if args.pair >= 0 else int(os.environ.get("LBC_PAIR", "0") or 0)   # bit 0: CTA-pair GEMMs, bit 1: wgrad3
+    pair = args.pair if args.pair >= 0 else int(os.environ.get("LBC_PAIR", "7") or 0)   # bit 0: CTA-pair GEMMs, bit 1: wgrad3
     L.lbc_set_fast_kernels((0 if args.no_fast else 1) | (4 if pair & 1 else 8) | (16 if pair & 2 else 32) | (64 if pair & 4 else 128))
     B = args.batch
     torch.manual_seed(0)
@@ -305,17 +305,19 @@ def run_ours(args):
         bn_ms = cats["bn_fwd"]["ms_per_step"] + cats["bn_bwd"]["ms_per_step"]
         bn_gb = cats["bn_fwd"]["gbytes_per_step"] + cats["bn_bwd"]["gbytes_per_step"]
         bn_gbs = bn_gb / bn_ms * 1e3 if bn_ms > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
-        if os.path.exists(tpath):       # dram bytes per launch of the dominant kernels from the committed ncu --set full capture
+        if os.path.exists(tpath):       # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
             try:
-                traffic = json.load(open(tpath)).get("dominant_kernel_dram_bytes_per_launch")
+                dk = json.load(open(tpath)).get("dominant_kernel")
+                traffic, traffic_src = dk["dram_total"], dict(kernel=dk["kernel"], capture=dk["capture"],
+                                                             algorithmic_bytes=dk["algorithmic_bytes"])
             except Exception:
                 traffic = None
         roof = dict(bound="tensor", kernel="tcgen05 implicit-GEMM convolutions (fwd + dgrad + wgrad, all layers; CUDA-event "
                                            "brackets on the launching stream)",
                     achieved=achieved, peak=peaks["tf_sust"], unit="TFLOP/s", frac=achieved / peaks["tf_sust"],
-                    traffic=traffic, peak_source=peaks["source"] + " bf16_tflops_sustained (kernels timed inside a long step)",
+                    traffic=traffic, traffic_of=traffic_src, peak_source=peaks["source"] + " bf16_tflops_sustained (kernels timed inside a long step)",
                     hbm_kernels=dict(kernel="BatchNorm statistics/apply/backward kernels", achieved=bn_gbs, peak=peaks["hbm"],
                                      unit="GB/s", frac=bn_gbs / peaks["hbm"], bytes="algorithmic (DESIGN.md section 3)"),
                     per_category=cats)

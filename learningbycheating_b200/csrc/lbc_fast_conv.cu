@@ -255,9 +255,10 @@ template <int BN, int STAGES, bool PAIR = false>
 struct SmemPlan {
   static constexpr int B_BYTES = PAIR ? BN * 64 : BN * 128;   // CTA pair: each CTA stages BN/2 rows of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // epilogue staging: the whole 128 x BN bf16 tile, or (pair, BN = 256) two passes of 128 columns through half the
-  // space, which buys the fifth operand stage the pair kernel needs to cover its TMA round trip
-  static constexpr int OUT_PASSES = (PAIR && BN == 256) ? 2 : 1;
+  // epilogue staging: the whole 128 x BN bf16 tile in OUT_PASSES column passes.  Two passes of 128 columns would buy the
+  // pair kernel (BN = 256) a fifth operand stage; measured on the B200 that is no faster (52.3 vs 51.5 us per launch),
+  // so the tile is staged in one pass.
+  static constexpr int OUT_PASSES = 1;
   static constexpr int OUT_BYTES = (BN / 64) * A_BYTES / OUT_PASSES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
   static constexpr int RED_OFF = BAR_OFF + 256;       // 128 x 4 floats: column-statistics scratch
@@ -1236,10 +1237,13 @@ static void launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, c
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
 }
-// bit 0: CTA-pair (cta_group::2) kernels for the BN >= 128 GEMMs.  Default from LBC_PAIR (0 until validated on the GPU).
+// kernel variants (LBC_PAIR overrides; tests toggle them through lbc_set_fast_kernels):
+//   bit 0: CTA-pair (cta_group::2) kernels for the BN >= 128 conv GEMMs   bit 1: row-of-taps weight gradient
+//   bit 2: CTA-pair variant of the row-of-taps weight gradient (Co % 256 == 0)
+// All three validated on the B200 (parity tests green, 16.61 -> 15.87 ms per step at B = 256), hence on by default.
 static int g_pair_mode = [] {
   const char* e = getenv("LBC_PAIR");
-  return e ? atoi(e) : 0;
+  return e ? atoi(e) : 7;
 }();
 void set_pair_mode(int mode) { g_pair_mode = mode; }
 int pair_mode() { return g_pair_mode; }
@@ -1253,7 +1257,7 @@ static void dispatch_gemm(int BN, const CUtensorMap* mA, const void* wbase, int6
     if (BN == 128)
       launch_gemm_pair<128, 7>(mA, mB, mO, p, s);
     else
-      launch_gemm_pair<256, 5>(mA, mB, mO, p, s);
+      launch_gemm_pair<256, 4>(mA, mB, mO, p, s);
     return;
   }
   CUtensorMap mB = make_map_2d(wbase, wK, wrows, BN);
@@ -2011,18 +2015,26 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
     }
   }
 }
-// dst[co][ci][t] (reference layout) = sum_split partial[split][co][t][ci]; threads walk the partials in storage order
+// dst[co][ci][t] (reference layout) = sum_split partial[split][co][t][ci].  One thread per (co, ci): the nine reads of
+// a split are coalesced across ci, the nine results are 36 contiguous bytes of the reference layout.
 __global__ void wgrad3_reduce_kernel(const float* __restrict__ part, float* __restrict__ dst, int Co, int Ci, int splits) {
-  const int64_t n = (int64_t)Co * 9 * Ci;
+  const int64_t n = (int64_t)Co * Ci;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float a = 0.f;
-  for (int s = 0; s < splits; ++s) a += part[(int64_t)s * n + i];
   const int ci = (int)(i % Ci);
-  const int64_t r = i / Ci;
-  const int t = (int)(r % 9);
-  const int64_t co = r / 9;
-  dst[(co * Ci + ci) * 9 + t] = a;
+  const int64_t co = i / Ci;
+  float a[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) a[t] = 0.f;
+  const int64_t split_stride = n * 9;
+  const float* src = part + co * 9 * Ci + ci;
+  for (int s = 0; s < splits; ++s, src += split_stride) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) a[t] += src[(int64_t)t * Ci];
+  }
+  float* d = dst + i * 9;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) d[t] = a[t];
 }
 
 // packed fp32 [Co][taps][Ci] -> reference layout [Co][Ci][K][K]
@@ -2202,7 +2214,7 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
     launch_wgrad3<5, true>(mDY, mX, p, grid, s);
   else
     launch_wgrad3<3, false>(mDY, mX, p, grid, s);
-  wgrad3_reduce_kernel<<<(unsigned)((wsize + 255) / 256), 256, 0, s>>>(p.out, dw_ref, c.Co, c.Ci, p.splits);
+  wgrad3_reduce_kernel<<<(unsigned)((wsize / 9 + 255) / 256), 256, 0, s>>>(p.out, dw_ref, c.Co, c.Ci, p.splits);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
   return true;
