@@ -16,6 +16,7 @@ void set_enabled(bool on) { g_enabled = on; }
 bool stem_im2col_bf16(const float*, bf16*, int, int, int, int, int, int, int, bool, lbc_stream_t) { return false; }
 bool stem_pack_weight_bf16(const float*, bf16*, int, int, lbc_stream_t) { return false; }
 bool stem_pad4_bf16(const float*, bf16*, int, int, int, int, bool, lbc_stream_t) { return false; }
+bool stem_pad4_u8_bf16(const uint8_t*, int, bf16*, int, int, int, int, bool, lbc_stream_t) { return false; }
 bool stem_pack_w224_bf16(const float*, bf16*, int, lbc_stream_t) { return false; }
 bool stem_unpack_wgrad(const float*, float*, int, int, lbc_stream_t) { return false; }
 #else
@@ -150,6 +151,41 @@ bool stem_pad4_bf16(const float* img, bf16* x4, int B, int C, int H, int W, bool
     if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
       for (int c = 0; c < C; ++c) {
         float x = __ldg(img + (((int64_t)b * C + c) * H + ih) * W + iw);
+        if (normalize) {
+          float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+          float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+          x = (x - mean) / sd;
+        }
+        v[c] = x;
+      }
+    }
+    uint2 o;
+    o.x = (uint32_t)float_to_bf16(v[0]).v | ((uint32_t)float_to_bf16(v[1]).v << 16);
+    o.y = (uint32_t)float_to_bf16(v[2]).v | ((uint32_t)float_to_bf16(v[3]).v << 16);
+    reinterpret_cast<uint2*>(x4)[i] = o;
+  });
+  return true;
+}
+struct k_stem_pad4_u8;
+// same tensor straight from uint8 frames (layout 0 = [B,C,H,W], 1 = [B,H,W,C], the data collector's on-disk order):
+// ToTensor's x/255 (torchvision, image_lmdb.py:133-135) and the normalisation evaluated with the expressions of the
+// two-step path (u8_to_f32_nchw + stem_pad4_bf16), so the result is bit-identical while the 189 MB fp32 image
+// (one write + one read per step at B = 256) never exists.
+bool stem_pad4_u8_bf16(const uint8_t* img, int layout, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s) {
+  if (!enabled() || C > 4) return false;
+  const int HP = H + 6, WP = W + 8;
+  int64_t n = (int64_t)B * HP * WP;
+  par_for<k_stem_pad4_u8>(s, n, [=] __device__(int64_t i) {
+    int col = (int)(i % WP);
+    int64_t t = i / WP;
+    int row = (int)(t % HP);
+    int b = (int)(t / HP);
+    int ih = row - 3, iw = col - 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      for (int c = 0; c < C; ++c) {
+        const int64_t j = layout == 1 ? (((int64_t)b * H + ih) * W + iw) * C + c : (((int64_t)b * C + c) * H + ih) * W + iw;
+        float x = (float)__ldg(img + j) / 255.0f;
         if (normalize) {
           float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
           float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);

@@ -163,6 +163,7 @@ bool stem_unpack_wgrad(const float* dw_col, float* dw_ref, int C, int Kp, lbc_st
 
 // ---- stem without a column tensor (C_in <= 4): zero-padded NHWC4 bf16 image + overlapping-window TMA (lbc_fast_conv.cu)
 bool stem_pad4_bf16(const float* img, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s);
+bool stem_pad4_u8_bf16(const uint8_t* img, int layout, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s);
 bool stem_pack_w224_bf16(const float* w_ref, bf16* w224, int C, lbc_stream_t s);   // [64][C][7][7] -> [64][7][8 px][4 ch]
 bool stem_conv_bf16(const bf16* x4, const bf16* w224, bf16* raw, int B, int H, int W, int OH, int OW, const float* bias,
                     float* stat_partial, int* stat_rows, lbc_stream_t s);

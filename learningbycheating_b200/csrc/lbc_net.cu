@@ -479,7 +479,8 @@ class Net : public NetBase {
     if (std::is_same<T, bf16>::value && stem_x4 && fast::enabled()) {
       ProfScope ps("conv_fwd", s, conv_flops(stem, B), 0);
       float* part = train ? fast::stat_partial_buffer() : nullptr;
-      bool ok = fast::stem_pad4_bf16(image, (bf16*)stem_x4, B, in_ch, in_h, in_w, normalize, s) &&
+      bool ok = (u8_image ? fast::stem_pad4_u8_bf16(u8_image, u8_layout, (bf16*)stem_x4, B, in_ch, in_h, in_w, normalize, s)
+                          : fast::stem_pad4_bf16(image, (bf16*)stem_x4, B, in_ch, in_h, in_w, normalize, s)) &&
                 fast::stem_pack_w224_bf16(P + stem.w_off, (bf16*)stem_w224, in_ch, s) &&
                 fast::stem_conv_bf16((const bf16*)stem_x4, (const bf16*)stem_w224, (bf16*)r_stem, B, in_h, in_w, stem_oh,
                                      stem_ow, stem_bn.negshift, part, &stem_stat_rows, s);
@@ -595,10 +596,25 @@ class Net : public NetBase {
 
   float* img_f32 = nullptr;
   int64_t img_f32_n = 0;
+  const uint8_t* u8_image = nullptr;   // set only while forward_u8 drives forward() through the direct stem
+  int u8_layout = 0;
   void forward_u8(const uint8_t* image, int layout, const float* speed, const float* onehot, int B, bool train,
                   float* out_pred, float* out_preds, lbc_stream_t s) override {
     LBC_CHECK(layout == 0 || layout == 1, "lbc_net_forward_u8: layout must be 0 (NCHW) or 1 (NHWC)");
     LBC_CHECK(B >= 1 && B <= max_batch, "lbc_net_forward_u8: batch outside [1, max_batch]");
+    if (std::is_same<T, bf16>::value && stem_x4 && fast::enabled()) {
+      // direct stem: the padded NHWC4 bf16 operand is written straight from the uint8 frames (no fp32 image)
+      u8_image = image;
+      u8_layout = layout;
+      try {
+        forward(nullptr, speed, onehot, B, train, out_pred, out_preds, s);
+      } catch (...) {
+        u8_image = nullptr;
+        throw;
+      }
+      u8_image = nullptr;
+      return;
+    }
     const int64_t need = (int64_t)max_batch * in_ch * in_h * in_w;
     if (!img_f32) {
       img_f32 = alloc<float>(need);

@@ -141,6 +141,27 @@ def test_eval_roundtrip_validation_gpu(backend):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("train", [False, True])
+def test_uint8_frames_bf16_direct_stem_gpu(backend, train):
+    """bf16 fast path: uint8 frames go straight into the padded NHWC4 stem operand (no fp32 image on the device); the
+    result must be bit-identical to feeding ToTensor'ed float frames."""
+    assert backend == "cuda"
+    import learningbycheating_b200 as lbc
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (3, 3, 160, 384), dtype=torch.uint8, generator=g)
+    speed, cmd = torch.rand(3, generator=g) * 10, torch.tensor([1., 3., 4.])
+    oh = lbc.one_hot(cmd).to("cuda")
+    outs = []
+    for frames in ((u8.float() / 255), u8, u8.permute(0, 2, 3, 1).contiguous()):
+        # a fresh engine per variant: a train-mode forward moves the BN buffers and the engine's centring estimate
+        s, _ = build_models("cuda", "bf16")
+        s.train(train)
+        with torch.no_grad():
+            outs.append(s(frames.to("cuda"), speed.to("cuda"), oh)[0].clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fast", [0, 1])
 def test_student_step_gpu_bf16_deviation(backend, fast):
     """bf16 throughput mode: measured deviation from the fp32 reference is reported, and bounded loosely
