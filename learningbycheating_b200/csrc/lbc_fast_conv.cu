@@ -2015,26 +2015,43 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
     }
   }
 }
-// dst[co][ci][t] (reference layout) = sum_split partial[split][co][t][ci].  One thread per (co, ci): the nine reads of
-// a split are coalesced across ci, the nine results are 36 contiguous bytes of the reference layout.
+// dst[co][ci][t] (reference layout) = sum_split partial[split][co][t][ci].
+// Variant A: threads walk the partials in storage order (coalesced reads, 36-byte-strided writes).
 __global__ void wgrad3_reduce_kernel(const float* __restrict__ part, float* __restrict__ dst, int Co, int Ci, int splits) {
-  const int64_t n = (int64_t)Co * Ci;
+  const int64_t n = (int64_t)Co * 9 * Ci;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  float a = 0.f;
+  for (int s = 0; s < splits; ++s) a += part[(int64_t)s * n + i];
   const int ci = (int)(i % Ci);
-  const int64_t co = i / Ci;
-  float a[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) a[t] = 0.f;
-  const int64_t split_stride = n * 9;
-  const float* src = part + co * 9 * Ci + ci;
-  for (int s = 0; s < splits; ++s, src += split_stride) {
-#pragma unroll
-    for (int t = 0; t < 9; ++t) a[t] += src[(int64_t)t * Ci];
+  const int64_t r = i / Ci;
+  const int t = (int)(r % 9);
+  const int64_t co = r / 9;
+  dst[(co * Ci + ci) * 9 + t] = a;
+}
+// Variant B: one block per (co, 64 ci): 576 threads = (tap, ci) read coalesced rows of the partials, transpose through
+// shared memory and write the 576 contiguous floats of the reference layout.  (A one-thread-per-(co, ci) version had
+// too few threads -- 16 K for layer 2 -- and ran 2x slower than A.)
+__global__ void __launch_bounds__(576) wgrad3_reduce_tr_kernel(const float* __restrict__ part, float* __restrict__ dst, int Co,
+                                                               int Ci, int splits) {
+  __shared__ float tile[64 * 9];
+  const int cblocks = Ci / 64;
+  const int co = blockIdx.x / cblocks, ci0 = (blockIdx.x % cblocks) * 64;
+  const int t = threadIdx.x / 64, cl = threadIdx.x % 64;
+  const int64_t n9 = (int64_t)Co * 9 * Ci;
+  const float* src = part + ((int64_t)co * 9 + t) * Ci + ci0 + cl;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int s = 0;
+  for (; s + 3 < splits; s += 4) {
+    a0 += src[(int64_t)s * n9];
+    a1 += src[(int64_t)(s + 1) * n9];
+    a2 += src[(int64_t)(s + 2) * n9];
+    a3 += src[(int64_t)(s + 3) * n9];
   }
-  float* d = dst + i * 9;
-#pragma unroll
-  for (int t = 0; t < 9; ++t) d[t] = a[t];
+  for (; s < splits; ++s) a0 += src[(int64_t)s * n9];
+  tile[cl * 9 + t] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  dst[((int64_t)co * Ci + ci0) * 9 + threadIdx.x] = tile[threadIdx.x];
 }
 
 // packed fp32 [Co][taps][Ci] -> reference layout [Co][Ci][K][K]
@@ -2214,7 +2231,14 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
     launch_wgrad3<5, true>(mDY, mX, p, grid, s);
   else
     launch_wgrad3<3, false>(mDY, mX, p, grid, s);
-  wgrad3_reduce_kernel<<<(unsigned)((wsize / 9 + 255) / 256), 256, 0, s>>>(p.out, dw_ref, c.Co, c.Ci, p.splits);
+  static const int reduce_variant = [] {
+    const char* e = getenv("LBC_W3_REDUCE");
+    return e ? atoi(e) : 0;   // 0 = A (storage order; the variant validated in the 15.87 ms step), 1 = B (smem transpose)
+  }();
+  if (reduce_variant == 1)
+    wgrad3_reduce_tr_kernel<<<(unsigned)(c.Co * (c.Ci / 64)), 576, 0, s>>>(p.out, dw_ref, c.Co, c.Ci, p.splits);
+  else
+    wgrad3_reduce_kernel<<<(unsigned)((wsize + 255) / 256), 256, 0, s>>>(p.out, dw_ref, c.Co, c.Ci, p.splits);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
   return true;
