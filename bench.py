@@ -35,17 +35,19 @@ def load_peaks():
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 50 ms in a side process.  It is started before the warm-up (nvidia-smi needs a few hundred
+    ms to come up) and only the samples stamped inside [mark(), stop()] -- the timed regions -- are reported."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.windows = index, None, [], []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -54,31 +56,45 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):             # a timed region starts
+        self.windows.append([time.time(), None])
+
+    def end(self):              # ... and ends
+        if self.windows and self.windows[-1][1] is None:
+            self.windows[-1][1] = time.time()
 
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.end()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        sm, mx, power, reasons = [], None, [], set()
+        for stamp, ln in self.lines:
+            # a line is printed right after its sample is taken: keep those received inside the marked window
+            if self.windows and not any(a <= stamp <= b + 0.02 for a, b in self.windows):
+                continue
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                sm.append(float(f[1]))
+                mx = float(f[2])
+                power.append(float(f[3]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_min_mhz=(sm[0] if sm else None), sm_max_mhz=mx,
+                    power_w_max=(max(power) if power else None), reasons=sorted(reasons), samples=len(sm),
+                    window="device-resident timed loop + the two end-to-end timed loops")
 
 
 def synthetic(B, seed, torch):
@@ -196,6 +212,9 @@ def run_ours(args):
 
     step()                      # builds the native engine (allocations) outside every timed region
     dp.sync_initial_state()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()         # comes up during the warm-up; only samples after sampler.mark() are reported
     for _ in range(args.warmup):
         step()
 
@@ -204,10 +223,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
     barrier()
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     n0 = L.lbc_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -216,9 +234,10 @@ def run_ours(args):
         loss = step()
     e1.record()
     barrier()
+    if rank == 0:
+        sampler.end()
     ms = e0.elapsed_time(e1)
     launches = L.lbc_kernel_launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -262,10 +281,14 @@ def run_ours(args):
     def e2e_measure(frames):
         e2e_run(3, frames)
         barrier()
+        if rank == 0:
+            sampler.mark()
         e0.record()
         e2e_run(e2e_steps, frames)
         e1.record()
         barrier()
+        if rank == 0:
+            sampler.end()
         tt = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -275,6 +298,7 @@ def run_ours(args):
     e2e_run(2, rgb_u8_p)
     e2e_fp32 = e2e_measure(rgb_p)
     e2e_value = e2e_measure(rgb_u8_p)
+    clocks = sampler.stop() if rank == 0 else None
     small = speed_p.numel() * 4 + B * 4 * 4 + target_p.numel() * 4
     h2d = rgb_u8_p.numel() + small
     h2d_fp32 = rgb_p.numel() * 4 + small
