@@ -367,7 +367,7 @@ def run_ours(args):
                             frames="uint8 NHWC host frames (pinned), copied on the prefetch stream every step",
                             fp32_frames=dict(value=e2e_fp32, h2d_bytes_per_step=h2d_fp32)),
                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu_base,
-                   step_tflops=value * GFLOP_PER_TRAIN_IMG / 1e3, last_loss=float(loss))
+                   step_tflops=value * GFLOP_PER_TRAIN_IMG / 1e3, last_loss=float(loss.detach()))
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
