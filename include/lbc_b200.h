@@ -29,7 +29,10 @@ const char* lbc_last_error(void);
 /* 1 = CUDA sm_100a build (the product), 0 = host-emulation build used only by the CPU unit tests */
 int lbc_device_kind(void);
 const char* lbc_build_info(void);
-/* enable / disable the tcgen05 + fused kernels (tests compare them with the correctness-first kernels) */
+/* enable / disable the tcgen05 + fused kernels (tests compare them with the correctness-first kernels).
+ * bit 0: fast kernels on; bit 1: generic tap-per-box kernel for the 64->64 3x3 convolutions;
+ * variant switches (absent bits keep the LBC_PAIR default): 4 / 8 = CTA-pair (cta_group::2) conv GEMMs on / off,
+ * 16 / 32 = row-of-taps weight gradient on / off, 64 / 128 = its CTA-pair variant on / off. */
 int lbc_set_fast_kernels(int enabled);
 
 /* ---- instrumentation used by bench.py ---- */
