@@ -119,6 +119,8 @@ int lbc_set_fast_kernels(int enabled) {
   if (enabled & 64) m |= 4;     // 64 / 128 = CTA-pair variant of the row-of-taps weight gradient on / off
   if (enabled & 128) m &= ~4;
   fast::set_pair_mode(m);
+  if (enabled & 256) fast::set_experimental(fast::experimental() | 1);    // 256 / 512 = pair-walking weight pack on / off
+  if (enabled & 512) fast::set_experimental(fast::experimental() & ~1);
   return 0;
 }
 

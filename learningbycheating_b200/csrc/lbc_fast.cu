@@ -10,6 +10,14 @@ namespace fast {
 static bool g_enabled = true;
 bool enabled() { return g_enabled; }
 void set_enabled(bool on) { g_enabled = on; }
+// candidates validated on the CPU (host-emulation build, bit-exact data movement) but not yet MEASURED on the B200;
+// off by default, switched by lbc_set_fast_kernels bits 256 / 512 or LBC_EXPERIMENTAL (bit 0: pair-walking weight pack)
+static int g_experimental = [] {
+  const char* e = getenv("LBC_EXPERIMENTAL");
+  return e ? atoi(e) : 0;
+}();
+int experimental() { return g_experimental; }
+void set_experimental(int bits) { g_experimental = bits; }
 
 
 #ifdef LBC_HOST_EMU

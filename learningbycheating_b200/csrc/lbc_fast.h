@@ -13,6 +13,8 @@ namespace fast {
 // global switch (tests flip it to compare fast kernels against the correctness-first ones)
 bool enabled();
 void set_enabled(bool on);
+int experimental();            // bit 0: ref::pack_all_pairs instead of ref::pack_all
+void set_experimental(int bits);
 
 // stat_partial != null: the epilogue also writes per-tile column sums / sums of squares of the stored output
 // ([*stat_rows][2*Co] floats) so that the BatchNorm statistics pass over the tensor disappears.

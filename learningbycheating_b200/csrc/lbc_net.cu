@@ -371,7 +371,10 @@ class Net : public NetBase {
   // ------------------------------------------------------------------ op wrappers (fast-path hooks)
   void pack_weights(lbc_stream_t s) {
     ProfScope ps("pack", s, 0, 0);
-    ref::pack_all<T>(s, P, pack_dev, (int)pack_host.size());
+    if (fast::experimental() & 1)
+      ref::pack_all_pairs<T>(s, P, pack_dev, (int)pack_host.size());
+    else
+      ref::pack_all<T>(s, P, pack_dev, (int)pack_host.size());
   }
   static double conv_flops(const ConvL& c, int B) {
     return 2.0 * B * c.OH * c.OW * (double)c.Co * c.K * c.K * c.Ci;

@@ -307,6 +307,62 @@ void pack_all(lbc_stream_t s, const float* P, const PackEntry* table, int n_entr
   });
 }
 
+// Same table, walked by (co, ci) PAIRS for the conv layouts: a lane reads the K*K contiguous taps of one (co, ci) pair
+// and scatters them into the K*K rows of the packed operand.  type 0: consecutive lanes = consecutive ci -> the source
+// is one contiguous run and every store row is coalesced; type 1: consecutive lanes = consecutive co -> 36-byte source
+// chunks (1.8x sector amplification instead of 8x for the element walk) and coalesced stores.  No div/mod per element.
+struct k_pack_all_pairs;
+template <class T>
+void pack_all_pairs(lbc_stream_t s, const float* P, const PackEntry* table, int n_entries) {
+  const int64_t LANES = 32768;
+  par_for<k_pack_all_pairs>(s, (int64_t)n_entries * LANES, [=] LBC_LAMBDA(int64_t t) {
+    const PackEntry e = table[t / LANES];
+    const float* src = P + e.src_off;
+    T* dst = (T*)e.dst;
+    if (e.type == 0 || e.type == 1) {
+      const int KK = e.K * e.K;
+      const int64_t pairs = (int64_t)e.Co * e.Ci;
+      for (int64_t q = t % LANES; q < pairs; q += LANES) {
+        int co, ci;
+        if (e.type == 0) {
+          ci = (int)(q % e.Ci);
+          co = (int)(q / e.Ci);
+        } else {
+          co = (int)(q % e.Co);
+          ci = (int)(q / e.Co);
+        }
+        const float* sp = src + ((int64_t)co * e.Ci + ci) * KK;
+        if (e.type == 0) {
+          T* dp = dst + (int64_t)co * KK * e.Ci + ci;
+          for (int tap = 0; tap < KK; ++tap) stf(dp, (int64_t)tap * e.Ci, sp[tap]);
+        } else {
+          T* dp = dst + (int64_t)ci * KK * e.Co + co;
+          for (int tap = 0; tap < KK; ++tap) stf(dp, (int64_t)tap * e.Co, sp[tap]);
+        }
+      }
+      return;
+    }
+    for (int64_t i = t % LANES; i < e.n; i += LANES) {
+      float v;
+      if (e.type == 2) {
+        int k = (int)(i % (2 * e.Co));
+        int ci = (int)(i / (2 * e.Co));
+        v = k < e.Co ? src[(((int64_t)k * e.Ci + ci) * 3 + 1) * 3 + 1] : (P + e.src2_off)[(int64_t)(k - e.Co) * e.Ci + ci];
+      } else {
+        int Kp = e.aux, C = e.Ci;
+        int k = (int)(i % Kp);
+        int co = (int)(i / Kp);
+        v = 0.f;
+        if (k < 49 * C) {
+          int tap = k / C, c = k - tap * C;
+          v = src[((int64_t)co * C + c) * 49 + tap];
+        }
+      }
+      stf(dst, i, v);
+    }
+  });
+}
+
 // ---------------------------------------------------------------------------------------------
 // BatchNorm2d, train mode (torch BN as constructed at resnet.py:104, image.py:38,56)
 // column statistics over M rows of C channels.  ws: >= 2*P*C doubles.
