@@ -121,6 +121,8 @@ int lbc_set_fast_kernels(int enabled) {
   fast::set_pair_mode(m);
   if (enabled & 256) fast::set_experimental(fast::experimental() | 1);    // 256 / 512 = pair-walking weight pack on / off
   if (enabled & 512) fast::set_experimental(fast::experimental() & ~1);
+  if (enabled & 1024) fast::set_experimental(fast::experimental() | 2);   // 1024 / 2048 = register-blocked head kernels on / off
+  if (enabled & 2048) fast::set_experimental(fast::experimental() & ~2);
   return 0;
 }
 

@@ -80,6 +80,63 @@ __global__ void __launch_bounds__(128) head_logits_kernel(const uint4* __restric
   for (int kj = 0; kj < 20; ++kj) logits[(n * 20 + kj) * HW + p] = acc[kj];
 }
 
+// EXPERIMENTAL (experimental() & 2; not yet measured on the B200).  head_logits_kernel issues one broadcast LDS per FMA
+// (1280 per pixel) and is shared-memory-issue bound (116 us for a 126 MB read).  Here a thread owns FOUR pixels and reads
+// the folded coefficients as float4, so one LDS.128 feeds 16 FMAs.  Same accumulation order per (pixel, kj) -> bit-identical.
+__global__ void __launch_bounds__(128) head_logits4_kernel(const uint4* __restrict__ h, const float* __restrict__ fold,
+                                                           float* __restrict__ logits, int64_t npix, int HW) {
+  __shared__ __align__(16) float A[1300];
+  for (int i = threadIdx.x; i < 1300; i += 128) A[i] = fold[i];
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * 512 + threadIdx.x;
+  float acc[4][20];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int kj = 0; kj < 20; ++kj) acc[i][kj] = A[1280 + kj];
+#pragma unroll 1
+  for (int v = 0; v < 8; ++v) {
+    float f[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t pix = base + 128 * i;
+      if (pix < npix) {
+        unpack8h(__ldg(h + pix * 8 + v), f[i]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[i][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int kj = 0; kj < 20; ++kj) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&A[kj * 64 + v * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&A[kj * 64 + v * 8 + 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = acc[i][kj];
+        a += a0.x * f[i][0];
+        a += a0.y * f[i][1];
+        a += a0.z * f[i][2];
+        a += a0.w * f[i][3];
+        a += a1.x * f[i][4];
+        a += a1.y * f[i][5];
+        a += a1.z * f[i][6];
+        a += a1.w * f[i][7];
+        acc[i][kj] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t pix = base + 128 * i;
+    if (pix >= npix) continue;
+    const int64_t n = pix / HW;
+    const int p = (int)(pix - n * HW);
+#pragma unroll
+    for (int kj = 0; kj < 20; ++kj) logits[(n * 20 + kj) * HW + p] = acc[i][kj];
+  }
+}
+
 // one block per (n, kj) row; HW <= 128*32
 __global__ void __launch_bounds__(128) head_softmax_kernel(const float* __restrict__ logits, float* __restrict__ rowmax,
                                                            float* __restrict__ rowsum, float* __restrict__ preds, int H, int W) {
@@ -143,7 +200,10 @@ bool head_forward_bf16(const bf16* h, ref::HeadParams hp, float* fold, float* lo
   if (HW > 4096) return false;
   head_fold(hp, fold, s);
   const int64_t npix = (int64_t)N * HW;
-  head_logits_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, s>>>((const uint4*)h, fold, logits, npix, HW);
+  if (experimental() & 2)
+    head_logits4_kernel<<<(unsigned)((npix + 511) / 512), 128, 0, s>>>((const uint4*)h, fold, logits, npix, HW);
+  else
+    head_logits_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, s>>>((const uint4*)h, fold, logits, npix, HW);
   ++g_launches;
   head_softmax_kernel<<<N * 20, 128, 0, s>>>(logits, rowmax, rowsum, preds, H, W);
   ++g_launches;
@@ -260,6 +320,159 @@ __global__ void __launch_bounds__(128) head_dh_kernel(const float* __restrict__ 
   }
 }
 
+// EXPERIMENTAL (experimental() & 2): four pixels per thread, coefficients read as float4 over channels (one LDS.128 per
+// 16 FMAs instead of one LDS per FMA).  Same accumulation order per (pixel, channel) -> bit-identical to head_dh_kernel.
+__global__ void __launch_bounds__(128) head_dh4_kernel(const float* __restrict__ dlogits, const uint4* __restrict__ h,
+                                                       const float* __restrict__ fold, const float* __restrict__ coef,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       uint4* __restrict__ dh, int64_t npix, int HW) {
+  __shared__ __align__(16) float A[1280];
+  __shared__ __align__(16) float cf[256];  // c0, c1, mean, rstd
+  for (int i = threadIdx.x; i < 1280; i += 128) A[i] = fold[i];
+  if (threadIdx.x < 64) {
+    cf[threadIdx.x] = coef[threadIdx.x];
+    cf[64 + threadIdx.x] = coef[64 + threadIdx.x];
+    cf[128 + threadIdx.x] = mean[threadIdx.x];
+    cf[192 + threadIdx.x] = rstd[threadIdx.x];
+  }
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * 512 + threadIdx.x;
+  float d[4][20];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t pix = base + 128 * i;
+    const bool ok = pix < npix;
+    const int64_t n = ok ? pix / HW : 0;
+    const int p = ok ? (int)(pix - n * HW) : 0;
+#pragma unroll
+    for (int kj = 0; kj < 20; ++kj) d[i][kj] = ok ? dlogits[(n * 20 + kj) * HW + p] : 0.f;
+  }
+#pragma unroll 1
+  for (int v = 0; v < 8; ++v) {
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+#pragma unroll
+    for (int kj = 0; kj < 20; ++kj) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&A[kj * 64 + v * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&A[kj * 64 + v * 8 + 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dk = d[i][kj];
+        acc[i][0] += a0.x * dk;
+        acc[i][1] += a0.y * dk;
+        acc[i][2] += a0.z * dk;
+        acc[i][3] += a0.w * dk;
+        acc[i][4] += a1.x * dk;
+        acc[i][5] += a1.y * dk;
+        acc[i][6] += a1.z * dk;
+        acc[i][7] += a1.w * dk;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t pix = base + 128 * i;
+      if (pix >= npix) continue;
+      float f[8], o[8];
+      unpack8h(__ldg(h + pix * 8 + v), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = v * 8 + e;
+        const float xh = (f[e] - cf[128 + c]) * cf[192 + c];
+        const float a = acc[i][e] - cf[c] - xh * cf[64 + c];
+        o[e] = f[e] > 0.f ? a : 0.f;
+      }
+      uint4 w;
+      __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) hb[q] = __floats2bfloat162_rn(o[2 * q], o[2 * q + 1]);
+      dh[pix * 8 + v] = w;
+    }
+  }
+}
+
+// EXPERIMENTAL (experimental() & 2): moment matrix with 4 channels x 5 kj x 4 pixels per inner step (9 LDS.128 per 80 FMAs
+// instead of 6 LDS per 5 FMAs).  Thread = (channel quad 0..15, kj group 0..3, pixel quarter 0..3); the four pixel quarters are
+// combined in shared memory before the double atomics.  Summation order differs from head_s_kernel (tolerance-level equal).
+__global__ void __launch_bounds__(256) head_s4_kernel(const float* __restrict__ dlogits, const uint4* __restrict__ h,
+                                                      const float* __restrict__ mean, const float* __restrict__ rstd, double* S,
+                                                      int N, int HW) {
+  __shared__ __align__(16) float smem_f[128 * 68 + 20 * 128];   // 45 KB: hh | dl ; `part` reuses the hh space at the end
+  float(*hh)[68] = reinterpret_cast<float(*)[68]>(smem_f);
+  float(*dl)[128] = reinterpret_cast<float(*)[128]>(smem_f + 128 * 68);
+  float(*part)[20][65] = reinterpret_cast<float(*)[20][65]>(smem_f);   // 4 x 20 x 65 floats = 20.8 KB <= 34.8 KB
+  const int t = threadIdx.x;
+  const int cq = t & 15, grp = (t >> 4) & 3, pq = t >> 6;
+  float acc[5][4];
+  float acc0[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    acc0[j] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  }
+  const int tiles_per_img = (HW + 127) / 128;
+  const int ntiles = N * tiles_per_img;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / tiles_per_img;
+    const int p0 = (tile - n * tiles_per_img) * 128;
+    const int np = min(128, HW - p0);
+    __syncthreads();
+    for (int i = t; i < 20 * 128; i += 256) {
+      int kj = i >> 7, p = i & 127;
+      dl[kj][p] = p < np ? dlogits[((int64_t)n * 20 + kj) * HW + p0 + p] : 0.f;
+    }
+    for (int i = t; i < 128 * 8; i += 256) {
+      int p = i >> 3, v = i & 7;
+      float f[8];
+      if (p < np) {
+        unpack8h(__ldg(h + ((int64_t)n * HW + p0 + p) * 8 + v), f);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) hh[p][v * 8 + e] = p < np ? (f[e] - mean[v * 8 + e]) * rstd[v * 8 + e] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int pp = 0; pp < 32; pp += 4) {
+      const int p = pq * 32 + pp;
+      float4 x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4*>(&hh[p + i][cq * 4]);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float4 d4 = *reinterpret_cast<const float4*>(&dl[grp * 5 + j][p]);
+        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[j][0] += dv[i] * x[i].x;
+          acc[j][1] += dv[i] * x[i].y;
+          acc[j][2] += dv[i] * x[i].z;
+          acc[j][3] += dv[i] * x[i].w;
+        }
+        if (cq == 0) acc0[j] += (dv[0] + dv[1]) + (dv[2] + dv[3]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) part[pq][grp * 5 + j][cq * 4 + e] = acc[j][e];
+    if (cq == 0) part[pq][grp * 5 + j][64] = acc0[j];
+  }
+  __syncthreads();
+  for (int i = t; i < 20 * 65; i += 256) {
+    const int kj = i / 65, c = i - kj * 65;
+    const float v = (part[0][kj][c] + part[1][kj][c]) + (part[2][kj][c] + part[3][kj][c]);
+    atomicAdd(&S[kj * 65 + c], (double)v);
+  }
+}
+
 // S: [20][65] doubles (zeroed here).  Produces S, then the caller computes parameter grads (ref::head_param_grads),
 // then head_backward_dh_bf16 writes the masked d(h).
 bool head_backward_s_bf16(const float* dlogits, const bf16* h, const float* mean, const float* rstd, double* S, int N, int HW,
@@ -269,7 +482,10 @@ bool head_backward_s_bf16(const float* dlogits, const bf16* h, const float* mean
   int grid = sm_count3() * 2;
   int ntiles = N * ((HW + 127) / 128);
   if (grid > ntiles) grid = ntiles;
-  head_s_kernel<<<grid, 256, 0, s>>>(dlogits, (const uint4*)h, mean, rstd, S, N, HW);
+  if (experimental() & 2)
+    head_s4_kernel<<<grid, 256, 0, s>>>(dlogits, (const uint4*)h, mean, rstd, S, N, HW);
+  else
+    head_s_kernel<<<grid, 256, 0, s>>>(dlogits, (const uint4*)h, mean, rstd, S, N, HW);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -279,8 +495,12 @@ bool head_backward_dh_bf16(const float* dlogits, const bf16* h, ref::HeadParams 
   if (!enabled()) return false;
   const int64_t npix = (int64_t)N * HW;
   head_coef(hp, hg, coef, 1.0f / (float)npix, s);
-  head_dh_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, s>>>(dlogits, (const uint4*)h, fold, coef, hp.mean[0], hp.rstd[0],
-                                                              (uint4*)dh, npix, HW);
+  if (experimental() & 2)
+    head_dh4_kernel<<<(unsigned)((npix + 511) / 512), 128, 0, s>>>(dlogits, (const uint4*)h, fold, coef, hp.mean[0], hp.rstd[0],
+                                                                 (uint4*)dh, npix, HW);
+  else
+    head_dh_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, s>>>(dlogits, (const uint4*)h, fold, coef, hp.mean[0], hp.rstd[0],
+                                                                (uint4*)dh, npix, HW);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());
   return true;
