@@ -123,6 +123,8 @@ int lbc_set_fast_kernels(int enabled) {
   if (enabled & 512) fast::set_experimental(fast::experimental() & ~1);
   if (enabled & 1024) fast::set_experimental(fast::experimental() | 2);   // 1024 / 2048 = register-blocked head kernels on / off
   if (enabled & 2048) fast::set_experimental(fast::experimental() & ~2);
+  if (enabled & 4096) fast::set_experimental(fast::experimental() | 4);   // 4096 / 8192 = capped par_for grids on / off
+  if (enabled & 8192) fast::set_experimental(fast::experimental() & ~4);
   return 0;
 }
 

@@ -145,6 +145,8 @@ inline void dev_copy(void* dst, const void* src, size_t bytes, lbc_stream_t s) {
 // ------------------------------------------------------------------ launch counter + per-category profiler
 // g_launches counts every kernel the library launches (bench.py reports it as gpu_launches).
 extern long long g_launches;
+// > 0: par_for launches at most this many blocks and the threads walk the range with a grid stride (experimental() & 4)
+extern int g_par_for_max_blocks;
 struct ProfEntry {
   std::string cat;
   double flops, bytes;
@@ -194,8 +196,10 @@ inline void par_for(lbc_stream_t, int64_t n, F f) {
 #else
 template <class Tag, class F>
 __global__ void __launch_bounds__(256) par_for_kernel(int64_t n, F f) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) f(i);
+  // grid-stride walk; with the default (uncapped) grid the stride covers the whole range: exactly one iteration per thread
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll 1   // no trip-count arithmetic in front of the (normally single) iteration
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
 }
 template <class Tag, class F>
 inline void par_for(lbc_stream_t s, int64_t n, F f) {
@@ -203,6 +207,9 @@ inline void par_for(lbc_stream_t s, int64_t n, F f) {
   const int bs = 256;
   int64_t nb = (n + bs - 1) / bs;
   LBC_CHECK(nb < (1ll << 31), "par_for grid too large");
+  // EXPERIMENTAL: one-element threads make the 20 M-element kernels (stem_pad4, head_dlogits, adam) block-dispatch
+  // bound (88 K blocks of 256 one-element threads in 222 us); a capped grid lets each thread walk several elements
+  if (g_par_for_max_blocks > 0 && nb > g_par_for_max_blocks) nb = g_par_for_max_blocks;
   par_for_kernel<Tag, F><<<(unsigned)nb, bs, 0, s>>>(n, f);
   ++g_launches;
   LBC_CUDA(cudaGetLastError());

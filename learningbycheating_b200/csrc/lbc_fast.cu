@@ -3,6 +3,7 @@
 
 namespace lbc {
 long long g_launches = 0;
+int g_par_for_max_blocks = 0;
 bool g_prof_on = false;
 std::vector<ProfEntry> g_prof;
 namespace fast {
@@ -11,13 +12,30 @@ static bool g_enabled = true;
 bool enabled() { return g_enabled; }
 void set_enabled(bool on) { g_enabled = on; }
 // candidates validated on the CPU (host-emulation build, bit-exact data movement) but not yet MEASURED on the B200;
-// off by default, switched by lbc_set_fast_kernels bits 256 / 512 or LBC_EXPERIMENTAL (bit 0: pair-walking weight pack)
+// off by default, switched by lbc_set_fast_kernels or LBC_EXPERIMENTAL (bit 0: pair-walking weight pack, bit 1:
+// register-blocked head kernels, bit 2: capped par_for grids)
 static int g_experimental = [] {
   const char* e = getenv("LBC_EXPERIMENTAL");
   return e ? atoi(e) : 0;
 }();
+static void apply_experimental() {
+  int cap = 0;
+#ifndef LBC_HOST_EMU
+  if (g_experimental & 4) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cap = (sms > 0 ? sms : 148) * 32;
+  }
+#endif
+  g_par_for_max_blocks = cap;
+}
 int experimental() { return g_experimental; }
-void set_experimental(int bits) { g_experimental = bits; }
+void set_experimental(int bits) {
+  g_experimental = bits;
+  apply_experimental();
+}
+static const bool g_experimental_applied = (apply_experimental(), true);
 
 
 #ifdef LBC_HOST_EMU

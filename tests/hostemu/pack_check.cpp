@@ -8,6 +8,7 @@
 
 namespace lbc {
 long long g_launches = 0;   // normally defined by lbc_fast.cu
+int g_par_for_max_blocks = 0;
 bool g_prof_on = false;
 std::vector<ProfEntry> g_prof;
 }  // namespace lbc
