@@ -125,6 +125,8 @@ int lbc_set_fast_kernels(int enabled) {
   if (enabled & 2048) fast::set_experimental(fast::experimental() & ~2);
   if (enabled & 4096) fast::set_experimental(fast::experimental() | 4);   // 4096 / 8192 = capped par_for grids on / off
   if (enabled & 8192) fast::set_experimental(fast::experimental() & ~4);
+  if (enabled & 16384) fast::set_experimental(fast::experimental() | 8);   // 16384 / 32768 = one-launch BatchNorm backward on / off
+  if (enabled & 32768) fast::set_experimental(fast::experimental() & ~8);
   return 0;
 }
 

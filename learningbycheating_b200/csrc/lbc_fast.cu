@@ -13,7 +13,7 @@ bool enabled() { return g_enabled; }
 void set_enabled(bool on) { g_enabled = on; }
 // candidates validated on the CPU (host-emulation build, bit-exact data movement) but not yet MEASURED on the B200;
 // off by default, switched by lbc_set_fast_kernels or LBC_EXPERIMENTAL (bit 0: pair-walking weight pack, bit 1:
-// register-blocked head kernels, bit 2: capped par_for grids)
+// register-blocked head kernels, bit 2: capped par_for grids, bit 3: one-launch BatchNorm backward)
 static int g_experimental = [] {
   const char* e = getenv("LBC_EXPERIMENTAL");
   return e ? atoi(e) : 0;

@@ -13,7 +13,7 @@ namespace fast {
 // global switch (tests flip it to compare fast kernels against the correctness-first ones)
 bool enabled();
 void set_enabled(bool on);
-int experimental();            // bit 0: ref::pack_all_pairs instead of ref::pack_all; bit 1: register-blocked head kernels; bit 2: capped par_for grids
+int experimental();            // bit 0: ref::pack_all_pairs instead of ref::pack_all; bit 1: register-blocked head kernels; bit 2: capped par_for grids; bit 3: one-launch (cooperative) BatchNorm backward
 void set_experimental(int bits);
 
 // stat_partial != null: the epilogue also writes per-tile column sums / sums of squares of the stored output

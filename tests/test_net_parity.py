@@ -299,7 +299,7 @@ def test_full_size_properties_gpu(backend):
                     reason="candidate kernels not yet measured on the B200: run with LBC_TEST_EXPERIMENTAL=1")
 def test_experimental_kernels_match_default_gpu(backend):
     """lbc_set_fast_kernels bits 256 (pair-walking weight pack), 1024 (register-blocked head kernels), 4096 (capped par_for
-    grids): one bf16 train
+    grids), 16384 (one-launch BatchNorm backward): one bf16 train
     step must reproduce the default kernels -- predictions bit-identical (same accumulation order), gradients to fp32
     summation-order noise."""
     assert backend == "cuda"
@@ -308,7 +308,7 @@ def test_experimental_kernels_match_default_gpu(backend):
     L = _lib.lib()
     res = []
     try:
-        for bits in (512 | 2048 | 8192, 256 | 1024 | 4096):
+        for bits in (512 | 2048 | 8192 | 32768, 256 | 1024 | 4096 | 16384):
             _lib.check(L.lbc_set_fast_kernels(1 | bits))
             s, _ = build_models("cuda", "bf16")
             s.train()
@@ -317,7 +317,7 @@ def test_experimental_kernels_match_default_gpu(backend):
             (preds.abs().mean() + pred.abs().mean()).backward()
             res.append((preds.detach().clone(), torch.cat([p.grad.flatten() for p in s.parameters() if p.grad is not None])))
     finally:
-        _lib.check(L.lbc_set_fast_kernels(1 | 512 | 2048 | 8192))
+        _lib.check(L.lbc_set_fast_kernels(1 | 512 | 2048 | 8192 | 32768))
     assert torch.equal(res[0][0], res[1][0])
     g0, g1 = res[0][1], res[1][1]
     assert (g0 - g1).norm() <= 1e-4 * g0.norm()
