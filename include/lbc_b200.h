@@ -110,19 +110,43 @@ int lbc_phase2_weight(const float* learner_map, const float* teacher_map, float*
 int lbc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
-/* ---- single-op entry points (fp32 NHWC; used by the parity tests of each kernel) ---- */
+/* ---- launch trace (tests): which kernel family produced a result ---- */
+/* on != 0: clear and start recording the kernel-family name of every launch; 0: stop */
+int lbc_trace_enable(int on);
+/* "name<TAB>count<LF>" per family (tcgen05 kernels by their own names, e.g. "conv_gemm_kernel<256,pair>"; the
+ * correctness-first kernels as "... [with Tag = lbc::ref::k_conv_fwd]"); returns the full length, writes at most cap-1 chars */
+int lbc_trace_dump(char* buf, int cap);
+
+/* ---- single-op entry points (fp32 NHWC in/out; the parity tests of each kernel) ----
+ * precision LBC_PREC_F32: correctness-first fp32 kernels; LBC_PREC_BF16: operands rounded to bf16 storage and run
+ * through the kernels of the bf16 training step (tcgen05 GEMMs, fused BN / pool / head kernels).  Each op mirrors one
+ * reference op: nn.Conv2d (resnet.py:15-22) and its two gradients, nn.ConvTranspose2d+bias+ReLU (image.py:39-46),
+ * nn.BatchNorm2d train mode + residual + ReLU (resnet.py:41-53), nn.MaxPool2d (resnet.py:105), SpatialSoftmax
+ * (common.py:136-152), the four heads (image.py:54-60), the stem (resnet.py:102,148 + common.py:101-109). */
 int lbc_op_conv_fwd(const float* x, const float* w_ref, float* y, int N, int H, int W, int Ci, int Co, int K,
-                    int stride, int pad, int precision, void* stream);
+                    int stride, int pad, int precision, const float* bias_co, float* stats_out, void* stream);
 int lbc_op_conv_dgrad(const float* dy, const float* w_ref, float* dx, int N, int H, int W, int Ci, int Co, int K,
-                      int stride, int pad, int precision, void* stream);
+                      int stride, int pad, int precision, const float* bias_ci, int relu, void* stream);
+int lbc_op_block_dgrad_ds(const float* dy1, const float* dy_ds, const float* w1_ref, const float* wd_ref, float* dx, int N,
+                          int H, int W, int Ci, int Co, int precision, void* stream);
 int lbc_op_conv_wgrad(const float* x, const float* dy, float* dw_ref, int N, int H, int W, int Ci, int Co, int K,
                       int stride, int pad, int precision, void* stream);
 int lbc_op_bn_train(const float* x, const float* gamma, const float* beta, const float* residual, int relu,
-                    float* y, float* mean, float* var, int64_t M, int C, void* stream);
+                    float* y, float* mean, float* var, int64_t M, int C, int precision, float* running_mean,
+                    float* running_var, float* negshift, void* stream);
 int lbc_op_bn_bwd(const float* dy, const float* x, const float* gamma, float* dgamma, float* dbeta, float* dx,
-                  int64_t M, int C, void* stream);
+                  int64_t M, int C, int precision, const float* mask_act, const float* beta, int own_relu, void* stream);
+int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mode, int precision, void* stream);
 int lbc_op_maxpool(const float* x, float* y, const float* dy, float* dx, int N, int H, int W, int C, void* stream);
-int lbc_op_spatial_softmax(const float* logits, float* out_xy, int rows, int H, int W, void* stream);
+int lbc_op_bn_relu_maxpool(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                           float* y, const float* dy, float* dx, int N, int H, int W, int C, int precision, void* stream);
+int lbc_op_spatial_softmax(const float* logits, float* out_xy, int rows, int H, int W, int precision, void* stream);
+int lbc_op_head(const float* h, const float* gamma, const float* beta, const float* w, const float* bias, int N, int H, int W,
+                float* running_mean, float* running_var, float* logits_out, float* preds_out, const float* onehot,
+                const float* d_pred, const float* d_preds, float* dgamma, float* dbeta, float* dw, float* dbias, float* dh,
+                int* dh_masked, int precision, void* stream);
+int lbc_op_stem(const float* img, const uint8_t* img_u8, int layout, const float* w_ref, int normalize, int N, int C, int H,
+                int W, float* x4_out, float* y, float* stats_out, const float* dy, float* dw, int precision, void* stream);
 
 #ifdef __cplusplus
 }

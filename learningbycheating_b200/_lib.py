@@ -55,13 +55,21 @@ def _declare(lib):
         "lbc_phase1_convert_bwd": (i, [vp, vp, vp, i64, f, f, f, f, f, vp]),
         "lbc_phase2_weight": (i, [vp, vp, vp, i, vp]),
         "lbc_adam_step": (i, [vp, vp, vp, vp, i64, f, f, f, f, i, f, vp]),
-        "lbc_op_conv_fwd": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
-        "lbc_op_conv_dgrad": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
+        "lbc_trace_enable": (i, [i]),
+        "lbc_trace_dump": (i, [ctypes.c_char_p, i]),
+        "lbc_op_conv_fwd": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, vp, vp]),
+        "lbc_op_conv_dgrad": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, i, vp]),
+        "lbc_op_block_dgrad_ds": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]),
         "lbc_op_conv_wgrad": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
-        "lbc_op_bn_train": (i, [vp, vp, vp, vp, i, vp, vp, vp, i64, i, vp]),
-        "lbc_op_bn_bwd": (i, [vp, vp, vp, vp, vp, vp, i64, i, vp]),
+        "lbc_op_bn_train": (i, [vp, vp, vp, vp, i, vp, vp, vp, i64, i, i, vp, vp, vp, vp]),
+        "lbc_op_bn_bwd": (i, [vp, vp, vp, vp, vp, vp, i64, i, i, vp, vp, i, vp]),
+        "lbc_op_ew": (i, [vp, vp, vp, i64, i, i, vp]),
         "lbc_op_maxpool": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
-        "lbc_op_spatial_softmax": (i, [vp, vp, i, i, i, vp]),
+        "lbc_op_bn_relu_maxpool": (i, [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]),
+        "lbc_op_spatial_softmax": (i, [vp, vp, i, i, i, i, vp]),
+        "lbc_op_head": (i, [vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                            ctypes.POINTER(i), i, vp]),
+        "lbc_op_stem": (i, [vp, vp, i, vp, i, i, i, i, i, vp, vp, vp, vp, vp, i, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)   # AttributeError here == the library does not export the header's symbol
@@ -120,6 +128,23 @@ def ptr(t):
     elif not t.is_cuda:
         raise LbcError("liblbc_b200 takes CUDA tensors only (got a %s tensor); no CPU path exists" % t.device)
     return ctypes.c_void_p(t.data_ptr())
+
+
+def trace(on):
+    """Start (clearing) / stop recording which kernel families the library launches."""
+    lib().lbc_trace_enable(1 if on else 0)
+
+
+def trace_counts():
+    """{kernel family: launches} since trace(True)."""
+    n = lib().lbc_trace_dump(None, 0)
+    buf = ctypes.create_string_buffer(n + 1)
+    lib().lbc_trace_dump(buf, n + 1)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, _, cnt = line.rpartition("\t")
+        out[name] = int(cnt)
+    return out
 
 
 def stream_ptr(device=None):

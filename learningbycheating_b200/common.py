@@ -110,6 +110,16 @@ def _head_params(ow, oh, steps=5, commands=4):
     ])
 
 
+# id(nn.Parameter) -> weakref(owning module); kept outside the Parameter so that pickling / deepcopy of a module never meets
+# a weakref (optim.Adam uses it to find the flat arrays its parameters are views of, and re-validates identity there)
+_PARAM_OWNER = {}
+
+
+def owner_of(param):
+    ref = _PARAM_OWNER.get(id(param))
+    return ref() if ref is not None else None
+
+
 class _NativeState:
     """Flat fp32 storage shared between the nn.Module (views) and the native engine (pointers)."""
 
@@ -126,6 +136,10 @@ class _NativeState:
         self.buffer_views = None   # list of (tensor, view)
         self.nbt = None
         self.table = None
+        # the engine keeps the activations of the LATEST train-mode forward only: every such forward gets a generation
+        # number, an autograd node may differentiate only the generation it produced, and only once
+        self.fwd_gen = 0
+        self.bwd_done_gen = -1
 
     def destroy(self):
         if self.handle is not None:
@@ -143,12 +157,13 @@ class _PolicyFn(torch.autograd.Function):
     def forward(ctx, owner, image, velocity, command, anchor):
         pred, preds = owner._native_forward(image, velocity, command, True)
         ctx.owner = owner
+        ctx.gen = owner._lbc.fwd_gen
         ctx.set_materialize_grads(False)
         return pred, preds
 
     @staticmethod
     def backward(ctx, d_pred, d_preds):
-        ctx.owner._native_backward(d_pred, d_preds)
+        ctx.owner._native_backward(d_pred, d_preds, ctx.gen)
         return None, None, None, None, None
 
 
@@ -174,7 +189,35 @@ class PolicyNetBase(nn.Module):
     def __del__(self):
         st = self.__dict__.get("_lbc")
         if st is not None:
+            if st.param_views and _PARAM_OWNER is not None:    # (None during interpreter shutdown)
+                for p, _, _, _ in st.param_views:
+                    _PARAM_OWNER.pop(id(p), None)
             st.destroy()
+
+    # copy.deepcopy(net) / torch.save(net): the native handle (a ctypes pointer) and the flat views do not travel; the copy
+    # owns plain tensors and builds its own engine lazily at its first forward
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d.pop("_lbc", None)
+        d.pop("_lbc_anchor", None)
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        object.__setattr__(self, "_lbc", _NativeState())
+        object.__setattr__(self, "_lbc_anchor", None)
+        with torch.no_grad():
+            for p in self.parameters():
+                p.data = p.data.clone()
+            for b in self.buffers():
+                b.data = b.data.clone()
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__setstate__(copy.deepcopy(self.__getstate__(), memo))
+        return new
 
     # ------------------------------------------------------------------ native state
     def _first_param(self):
@@ -202,6 +245,11 @@ class PolicyNetBase(nn.Module):
             st.handle, st.device, st.precision, st.max_batch = h, dev, self.lbc_precision, max_batch
             st.table = self._read_table(h)
             st.flat_params = None
+        elif dev.type == "cuda" and torch.cuda.current_device() != dev.index:
+            # the library's scratch buffers / kernel attributes belong to the device that was current at first use: one
+            # process drives ONE GPU; anything else must fail loudly, not corrupt memory
+            raise _lib.LbcError("model lives on %s but the current CUDA device is cuda:%d -- liblbc_b200 drives one GPU per "
+                                "process (torch.cuda.set_device first)" % (dev, torch.cuda.current_device()))
         if st.flat_params is None or not self._views_intact():
             self._flatten()
         return st
@@ -253,7 +301,7 @@ class PolicyNetBase(nn.Module):
                 v = flat[off:off + numel].view(shape)
                 v.copy_(p.data)
                 p.data = v
-                p._lbc_owner = weakref.ref(self)
+                _PARAM_OWNER[id(p)] = weakref.ref(self)
                 views.append((p, v, grads[off:off + numel].view(shape), on_path))
             bufs = dict(self.named_buffers())
             fb = torch.zeros(st.table["n_buffers"], dtype=torch.float32, device=dev)
@@ -309,10 +357,18 @@ class PolicyNetBase(nn.Module):
                                                   _lib.stream_ptr(st.device)))
         if train:
             torch._foreach_add_(st.nbt, 1)     # BatchNorm2d.num_batches_tracked += 1
+            st.fwd_gen += 1
         return pred, preds
 
-    def _native_backward(self, d_pred, d_preds):
+    def _native_backward(self, d_pred, d_preds, gen=None):
         st = self._lbc
+        if gen is not None and gen != st.fwd_gen:
+            raise _lib.LbcError("backward() of a forward pass whose activations are gone: this model ran another train-mode "
+                                "forward (generation %d -> %d) before backward.  The engine keeps one set of activations; "
+                                "run logging / extra passes in eval() mode or after backward()" % (gen, st.fwd_gen))
+        if gen is not None and st.bwd_done_gen == gen:
+            raise _lib.LbcError("backward() called twice through the same forward pass (retain_graph is not supported: "
+                                "the activations are consumed in place)")
         if not self._views_intact():
             raise _lib.LbcError("parameters were moved / replaced between forward and backward")
         fresh = all(p.grad is None for p, _, _, on in st.param_views if on)
@@ -327,6 +383,8 @@ class PolicyNetBase(nn.Module):
         dp = d_pred.contiguous().float() if d_pred is not None else None
         dps = d_preds.contiguous().float() if d_preds is not None else None
         _lib.check(L.lbc_net_backward(st.handle, _lib.ptr(dp), _lib.ptr(dps), _lib.stream_ptr(st.device)))
+        if gen is not None:
+            st.bwd_done_gen = gen
         if fresh:
             for p, _, gview, on in st.param_views:
                 if on:

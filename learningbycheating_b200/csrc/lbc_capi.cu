@@ -3,6 +3,7 @@
 
 #include "../../include/lbc_b200.h"
 #include "lbc_fast.h"
+#include "lbc_head.h"
 #include "lbc_net.h"
 #include "lbc_ref_ops.h"
 
@@ -285,10 +286,29 @@ int lbc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
   });
 }
 
+// ------------------------------------------------------------------ launch trace
+int lbc_trace_enable(int on) {
+  if (on) trace_reset();
+  g_trace_on = on != 0;
+  return 0;
+}
+int lbc_trace_dump(char* buf, int cap) {
+  std::string t = trace_dump();
+  if (buf && cap > 0) {
+    int n = (int)t.size() < cap - 1 ? (int)t.size() : cap - 1;
+    memcpy(buf, t.data(), n);
+    buf[n] = 0;
+  }
+  return (int)t.size();
+}
+
 // ------------------------------------------------------------------ single-op entry points
+// precision LBC_PREC_F32: correctness-first fp32 kernels.  LBC_PREC_BF16: the operands are rounded to bf16 storage and go
+// through the kernels the bf16 training step runs (tcgen05 GEMMs, fused BN / pool / head kernels); results come back as
+// fp32.  The tests compare with torch on the same rounded operands and read lbc_trace_dump to see which kernel ran.
 
 int lbc_op_conv_fwd(const float* x, const float* w_ref, float* y, int N, int H, int W, int Ci, int Co, int K,
-                    int stride, int pad, int precision, void* stream) {
+                    int stride, int pad, int precision, const float* bias_co, float* stats_out, void* stream) {
   return guarded([&] {
     require_device();
     lbc_stream_t s = S(stream);
@@ -296,23 +316,34 @@ int lbc_op_conv_fwd(const float* x, const float* w_ref, float* y, int N, int H, 
     Tmp t;
     int64_t nx = (int64_t)N * H * W * Ci, ny = (int64_t)N * c.OH * c.OW * Co, nw = (int64_t)Co * K * K * Ci;
     if (precision == PREC_F32) {
+      LBC_CHECK(!stats_out, "lbc_op_conv_fwd: epilogue statistics exist on the bf16 path only");
       float* wp = t.get<float>(nw);
       ref::pack_weight<float>(s, w_ref, wp, Co, Ci, K);
-      ref::conv_fwd<float>(s, x, wp, nullptr, false, y, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW);
+      ref::conv_fwd<float>(s, x, wp, bias_co, false, y, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW);
     } else {
       bf16 *xb = t.get<bf16>(nx), *wb = t.get<bf16>(nw), *yb = t.get<bf16>(ny);
       ref::cast<float, bf16>(s, x, xb, nx);
       ref::pack_weight<bf16>(s, w_ref, wb, Co, Ci, K);
       c.wp = wb;
-      if (!fast::conv_fwd<bf16>(c, xb, yb, N, s))
-        ref::conv_fwd<bf16>(s, xb, wb, nullptr, false, yb, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW);
+      int rows = 0;
+      float* part = stats_out ? fast::stat_partial_buffer() : nullptr;
+      if (fast::conv_fwd<bf16>(c, xb, yb, N, s, bias_co, part, &rows)) {
+        if (stats_out) {
+          LBC_CHECK(part && rows > 0, "lbc_op_conv_fwd: the fast kernel emitted no statistics partials");
+          LBC_CHECK(fast::col_finalize_bf16(part, rows, 2 * Co, stats_out, s), "col_finalize failed");
+        }
+      } else {
+        LBC_CHECK(!stats_out, "lbc_op_conv_fwd: statistics requested but the fast kernel did not run");
+        ref::conv_fwd<bf16>(s, xb, wb, bias_co, false, yb, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW);
+      }
       ref::cast<bf16, float>(s, yb, y, ny);
     }
     sync_stream(s);
   });
 }
+// bias_ci / relu: the epilogue of nn.ConvTranspose2d(..)+bias -> ReLU (image.py:39-46), which is this data gradient
 int lbc_op_conv_dgrad(const float* dy, const float* w_ref, float* dx, int N, int H, int W, int Ci, int Co, int K,
-                      int stride, int pad, int precision, void* stream) {
+                      int stride, int pad, int precision, const float* bias_ci, int relu, void* stream) {
   return guarded([&] {
     require_device();
     lbc_stream_t s = S(stream);
@@ -322,7 +353,7 @@ int lbc_op_conv_dgrad(const float* dy, const float* w_ref, float* dx, int N, int
     if (precision == PREC_F32) {
       float* wp = t.get<float>(nw);
       ref::pack_weight<float>(s, w_ref, wp, Co, Ci, K);
-      ref::conv_dgrad<float>(s, dy, wp, dx, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, nullptr, false, false);
+      ref::conv_dgrad<float>(s, dy, wp, dx, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, bias_ci, relu != 0, false);
     } else {
       bf16 *xb = t.get<bf16>(nx), *wb = t.get<bf16>(nw), *yb = t.get<bf16>(ny);
       bf16* wtb = t.get<bf16>(nw);
@@ -331,8 +362,45 @@ int lbc_op_conv_dgrad(const float* dy, const float* w_ref, float* dx, int N, int
       ref::pack_weight_t<bf16>(s, w_ref, wtb, Co, Ci, K);
       c.wp = wb;
       c.wpt = wtb;
-      if (!fast::conv_dgrad<bf16>(c, yb, xb, N, nullptr, false, s))
-        ref::conv_dgrad<bf16>(s, yb, wb, xb, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, nullptr, false, false);
+      if (!fast::conv_dgrad<bf16>(c, yb, xb, N, bias_ci, relu != 0, s))
+        ref::conv_dgrad<bf16>(s, yb, wb, xb, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, bias_ci, relu != 0, false);
+      ref::cast<bf16, float>(s, xb, dx, nx);
+    }
+    sync_stream(s);
+  });
+}
+// gradient wrt the input of a stage-entry block: dgrad(3x3/s2 conv1)(dy1) + dgrad(1x1/s2 downsample)(dy_ds) (resnet.py:48-52)
+int lbc_op_block_dgrad_ds(const float* dy1, const float* dy_ds, const float* w1_ref, const float* wd_ref, float* dx, int N,
+                          int H, int W, int Ci, int Co, int precision, void* stream) {
+  return guarded([&] {
+    require_device();
+    lbc_stream_t s = S(stream);
+    ConvL c1 = make_conv(H, W, Ci, Co, 3, 2, 1), cd = make_conv(H, W, Ci, Co, 1, 2, 0);
+    Tmp t;
+    int64_t nx = (int64_t)N * H * W * Ci, ny = (int64_t)N * c1.OH * c1.OW * Co;
+    if (precision == PREC_F32) {
+      float *w1 = t.get<float>((int64_t)Co * 9 * Ci), *wd = t.get<float>((int64_t)Co * Ci);
+      ref::pack_weight<float>(s, w1_ref, w1, Co, Ci, 3);
+      ref::pack_weight<float>(s, wd_ref, wd, Co, Ci, 1);
+      ref::conv_dgrad<float>(s, dy1, w1, dx, N, H, W, Ci, Co, 3, 2, 1, c1.OH, c1.OW, nullptr, false, false);
+      ref::conv_dgrad<float>(s, dy_ds, wd, dx, N, H, W, Ci, Co, 1, 2, 0, cd.OH, cd.OW, nullptr, false, true);
+    } else {
+      bf16 *d1 = t.get<bf16>(ny), *d2 = t.get<bf16>(ny), *xb = t.get<bf16>(nx);
+      bf16 *w1 = t.get<bf16>((int64_t)Co * 9 * Ci), *w1t = t.get<bf16>((int64_t)Co * 9 * Ci), *wd = t.get<bf16>((int64_t)Co * Ci);
+      bf16* wcomb = t.get<bf16>((int64_t)Ci * 2 * Co);
+      ref::cast<float, bf16>(s, dy1, d1, ny);
+      ref::cast<float, bf16>(s, dy_ds, d2, ny);
+      ref::pack_weight<bf16>(s, w1_ref, w1, Co, Ci, 3);
+      ref::pack_weight_t<bf16>(s, w1_ref, w1t, Co, Ci, 3);
+      ref::pack_weight<bf16>(s, wd_ref, wd, Co, Ci, 1);
+      ref::pack_weight_comb<bf16>(s, w1_ref, wd_ref, wcomb, Co, Ci);
+      c1.wp = w1;
+      c1.wpt = w1t;
+      c1.wcomb = wcomb;
+      if (!fast::conv_dgrad_ds<bf16>(c1, d1, d2, xb, N, s)) {
+        ref::conv_dgrad<bf16>(s, d1, w1, xb, N, H, W, Ci, Co, 3, 2, 1, c1.OH, c1.OW, nullptr, false, false);
+        ref::conv_dgrad<bf16>(s, d2, wd, xb, N, H, W, Ci, Co, 1, 2, 0, cd.OH, cd.OW, nullptr, false, true);
+      }
       ref::cast<bf16, float>(s, xb, dx, nx);
     }
     sync_stream(s);
@@ -360,31 +428,107 @@ int lbc_op_conv_wgrad(const float* x, const float* dy, float* dw_ref, int N, int
     sync_stream(s);
   });
 }
+// nn.BatchNorm2d in train mode (+ residual, + ReLU) over [M][C].  running_mean / running_var (optional) are updated in
+// place; negshift (bf16 path, optional): x holds (true x + negshift[c]) -- the centring shift of DESIGN.md -- and is
+// replaced by -(batch mean of the true x).
 int lbc_op_bn_train(const float* x, const float* gamma, const float* beta, const float* residual, int relu,
-                    float* y, float* mean, float* var, int64_t M, int C, void* stream) {
+                    float* y, float* mean, float* var, int64_t M, int C, int precision, float* running_mean,
+                    float* running_var, float* negshift, void* stream) {
   return guarded([&] {
     require_device();
     lbc_stream_t s = S(stream);
     Tmp t;
-    double* ws = t.get<double>(1 << 20);
     float* rstd = t.get<float>(C);
-    ref::bn_stats<float>(s, x, M, C, mean, var, ws);
-    ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, nullptr, nullptr);
-    ref::bn_apply<float>(s, x, mean, rstd, gamma, beta, residual, relu != 0, y, M, C);
+    if (precision == PREC_F32) {
+      LBC_CHECK(!negshift, "lbc_op_bn_train: the centring shift exists on the bf16 path only");
+      double* ws = t.get<double>(1 << 20);
+      ref::bn_stats<float>(s, x, M, C, mean, var, ws);
+      ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, running_mean, running_var);
+      ref::bn_apply<float>(s, x, mean, rstd, gamma, beta, residual, relu != 0, y, M, C);
+    } else {
+      const int64_t n = M * C;
+      bf16 *xb = t.get<bf16>(n), *yb = t.get<bf16>(n), *rb = residual ? t.get<bf16>(n) : nullptr;
+      float *sums = t.get<float>(2 * C), *rm = running_mean ? running_mean : t.get<float>(C),
+            *rv = running_var ? running_var : t.get<float>(C);
+      if (!running_mean) dev_memset(rm, 0, sizeof(float) * C, s);
+      if (!running_var) dev_memset(rv, 0, sizeof(float) * C, s);
+      ref::cast<float, bf16>(s, x, xb, n);
+      if (residual) ref::cast<float, bf16>(s, residual, rb, n);
+      if (!fast::Fast<bf16>::bn_fwd(xb, M, C, gamma, beta, 1e-5f, 0.1f, rm, rv, mean, rstd, rb, relu != 0, true, yb, sums,
+                                    negshift, s)) {
+        LBC_CHECK(!negshift, "lbc_op_bn_train: centring shift requested but the fast kernels did not run");
+        double* ws = t.get<double>(1 << 20);
+        ref::bn_stats<bf16>(s, xb, M, C, mean, var, ws);
+        ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, rm, rv);
+        ref::bn_apply<bf16>(s, xb, mean, rstd, gamma, beta, rb, relu != 0, yb, M, C);
+      } else {
+        ref::rstd_to_var(s, rstd, var, C, 1e-5f);
+      }
+      ref::cast<bf16, float>(s, yb, y, n);
+    }
     sync_stream(s);
   });
 }
+// BatchNorm backward with batch statistics recomputed from x.  mask_act (optional, [M][C]): dy is first masked with
+// (mask_act > 0) -- the in-place ReLU that follows the BN; own_relu != 0: that activation is relu(bn(x)) of this very BN
+// (beta required), which the fast kernels recompute from x instead of reading mask_act.
 int lbc_op_bn_bwd(const float* dy, const float* x, const float* gamma, float* dgamma, float* dbeta, float* dx,
-                  int64_t M, int C, void* stream) {
+                  int64_t M, int C, int precision, const float* mask_act, const float* beta, int own_relu, void* stream) {
   return guarded([&] {
     require_device();
     lbc_stream_t s = S(stream);
     Tmp t;
     double* ws = t.get<double>(1 << 20);
     float *mean = t.get<float>(C), *var = t.get<float>(C), *rstd = t.get<float>(C);
-    ref::bn_stats<float>(s, x, M, C, mean, var, ws);
-    ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, nullptr, nullptr);
-    ref::bn_bwd<float>(s, dy, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, ws);
+    const int64_t n = M * C;
+    LBC_CHECK(!own_relu || (mask_act && beta), "lbc_op_bn_bwd: own_relu needs mask_act and beta");
+    if (precision == PREC_F32) {
+      float* dym = t.get<float>(n);
+      dev_copy(dym, dy, sizeof(float) * n, s);
+      if (mask_act) ref::relu_mask_inplace<float>(s, dym, mask_act, n);
+      ref::bn_stats<float>(s, x, M, C, mean, var, ws);
+      ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, nullptr, nullptr);
+      ref::bn_bwd<float>(s, dym, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, ws);
+    } else {
+      bf16 *xb = t.get<bf16>(n), *dyb = t.get<bf16>(n), *dxb = t.get<bf16>(n), *mb = mask_act ? t.get<bf16>(n) : nullptr;
+      float* sums = t.get<float>(2 * C);
+      ref::cast<float, bf16>(s, x, xb, n);
+      ref::cast<float, bf16>(s, dy, dyb, n);
+      if (mask_act) ref::cast<float, bf16>(s, mask_act, mb, n);
+      ref::bn_stats<bf16>(s, xb, M, C, mean, var, ws);
+      ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, nullptr, nullptr);
+      if (!fast::Fast<bf16>::bn_bwd(dyb, mb, xb, mean, rstd, gamma, dgamma, dbeta, dxb, M, C, sums, s, own_relu ? beta : nullptr)) {
+        if (mb) ref::relu_mask_inplace<bf16>(s, dyb, mb, n);
+        ref::bn_bwd<bf16>(s, dyb, xb, mean, rstd, gamma, dgamma, dbeta, dxb, M, C, ws);
+      }
+      ref::cast<bf16, float>(s, dxb, dx, n);
+    }
+    sync_stream(s);
+  });
+}
+// masked adds of the residual backward: mode 0 dst += src; 1 dst += src*(act>0); 2 dst *= (act>0)
+int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mode, int precision, void* stream) {
+  return guarded([&] {
+    require_device();
+    lbc_stream_t s = S(stream);
+    Tmp t;
+    LBC_CHECK(mode >= 0 && mode <= 2, "lbc_op_ew: mode 0..2");
+    if (precision == PREC_F32) {
+      if (mode == 0) ref::add_inplace<float>(s, dst, src, n);
+      else if (mode == 1) ref::add_masked_inplace<float>(s, dst, src, act, n);
+      else ref::relu_mask_inplace<float>(s, dst, act, n);
+    } else {
+      bf16 *d = t.get<bf16>(n), *sr = src ? t.get<bf16>(n) : nullptr, *a = act ? t.get<bf16>(n) : nullptr;
+      ref::cast<float, bf16>(s, dst, d, n);
+      if (src) ref::cast<float, bf16>(s, src, sr, n);
+      if (act) ref::cast<float, bf16>(s, act, a, n);
+      if (!fast::Fast<bf16>::ew(d, sr, a, n, mode, s)) {
+        if (mode == 0) ref::add_inplace<bf16>(s, d, sr, n);
+        else if (mode == 1) ref::add_masked_inplace<bf16>(s, d, sr, a, n);
+        else ref::relu_mask_inplace<bf16>(s, d, a, n);
+      }
+      ref::cast<bf16, float>(s, d, dst, n);
+    }
     sync_stream(s);
   });
 }
@@ -400,14 +544,209 @@ int lbc_op_maxpool(const float* x, float* y, const float* dy, float* dx, int N, 
     sync_stream(s);
   });
 }
-int lbc_op_spatial_softmax(const float* logits, float* out_xy, int rows, int H, int W, void* stream) {
+// stem tail: y = maxpool3x3/s2/p1(relu(bn(x))) with GIVEN statistics, and (dy, dx != null) its backward: dx = the
+// gradient wrt the BatchNorm output, i.e. maxpool backward times the ReLU mask (resnet.py:150-152)
+int lbc_op_bn_relu_maxpool(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                           float* y, const float* dy, float* dx, int N, int H, int W, int C, int precision, void* stream) {
+  return guarded([&] {
+    require_device();
+    lbc_stream_t s = S(stream);
+    int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+    Tmp t;
+    const int64_t nx = (int64_t)N * H * W * C, ny = (int64_t)N * OH * OW * C;
+    uint8_t* idx = t.get<uint8_t>(ny);
+    if (precision == PREC_F32) {
+      float* a = t.get<float>(nx);
+      ref::bn_apply<float>(s, x, mean, rstd, gamma, beta, nullptr, true, a, (int64_t)N * H * W, C);
+      ref::maxpool_fwd<float>(s, a, y, idx, N, H, W, C, OH, OW);
+      if (dy && dx) {
+        ref::maxpool_bwd<float>(s, dy, idx, dx, N, H, W, C, OH, OW);
+        ref::relu_mask_inplace<float>(s, dx, a, nx);
+      }
+    } else {
+      bf16 *xb = t.get<bf16>(nx), *yb = t.get<bf16>(ny), *dyb = t.get<bf16>(ny), *dxb = t.get<bf16>(nx);
+      ref::cast<float, bf16>(s, x, xb, nx);
+      const bool fwd = fast::Fast<bf16>::pool_fwd(xb, mean, rstd, gamma, beta, yb, idx, N, H, W, C, OH, OW, s);
+      bf16* a = nullptr;
+      if (!fwd) {
+        a = t.get<bf16>(nx);
+        ref::bn_apply<bf16>(s, xb, mean, rstd, gamma, beta, nullptr, true, a, (int64_t)N * H * W, C);
+        ref::maxpool_fwd<bf16>(s, a, yb, idx, N, H, W, C, OH, OW);
+      }
+      ref::cast<bf16, float>(s, yb, y, ny);
+      if (dy && dx) {
+        ref::cast<float, bf16>(s, dy, dyb, ny);
+        if (!(fwd && fast::Fast<bf16>::pool_bwd(dyb, idx, xb, mean, rstd, gamma, beta, dxb, N, H, W, C, OH, OW, s))) {
+          if (!a) {
+            a = t.get<bf16>(nx);
+            ref::bn_apply<bf16>(s, xb, mean, rstd, gamma, beta, nullptr, true, a, (int64_t)N * H * W, C);
+          }
+          ref::maxpool_bwd<bf16>(s, dyb, idx, dxb, N, H, W, C, OH, OW);
+          ref::relu_mask_inplace<bf16>(s, dxb, a, nx);
+        }
+        ref::cast<bf16, float>(s, dxb, dx, nx);
+      }
+    }
+    sync_stream(s);
+  });
+}
+int lbc_op_spatial_softmax(const float* logits, float* out_xy, int rows, int H, int W, int precision, void* stream) {
   return guarded([&] {
     require_device();
     lbc_stream_t s = S(stream);
     LBC_CHECK(rows % 20 == 0, "rows must be a multiple of 20 (4 heads x 5 steps)");
     Tmp t;
     float *rmax = t.get<float>(rows), *rsum = t.get<float>(rows);
-    ref::head_softmax(s, logits, rmax, rsum, out_xy, rows / 20, H, W);
+    if (!(precision == PREC_BF16 && fast::head_softmax_f32(logits, rmax, rsum, out_xy, rows / 20, H, W, s)))
+      ref::head_softmax(s, logits, rmax, rsum, out_xy, rows / 20, H, W);
+    sync_stream(s);
+  });
+}
+// The four waypoint heads (image.py:54-60,82-84) over h [N][H*W][64] (post-ReLU decoder output), train-mode BN.
+// gamma/beta [4][64], w [4][5][64], bias [4][5]; running_mean / running_var [4][64] updated in place (may be null).
+// Forward: logits_out [N][20][H*W] (may be null), preds_out [N][4][5][2].  Backward when d_pred or d_preds is given
+// (onehot [N][4] needed with d_pred): dgamma/dbeta/dw/dbias in the parameter layouts, dh [N][H*W][64];
+// *dh_masked = 1 when dh already carries the (h > 0) mask of the decoder's last ReLU (fused fast path).
+int lbc_op_head(const float* h, const float* gamma, const float* beta, const float* w, const float* bias, int N, int H, int W,
+                float* running_mean, float* running_var, float* logits_out, float* preds_out, const float* onehot,
+                const float* d_pred, const float* d_preds, float* dgamma, float* dbeta, float* dw, float* dbias, float* dh,
+                int* dh_masked, int precision, void* stream) {
+  return guarded([&] {
+    require_device();
+    lbc_stream_t s = S(stream);
+    Tmp t;
+    const int HW = H * W;
+    const int64_t M = (int64_t)N * HW;
+    HeadCtx hc;
+    hc.H = H;
+    hc.W = W;
+    hc.logits = t.get<float>(M * 20);
+    hc.dlogits = t.get<float>(M * 20);
+    hc.rowmax = t.get<float>(N * 20);
+    hc.rowsum = t.get<float>(N * 20);
+    hc.preds = t.get<float>(N * 40);
+    hc.S = t.get<double>(20 * 65);
+    hc.fold = t.get<float>(1300 + 128 + 28);
+    hc.bn_sums = t.get<float>(2 * 1024);
+    int64_t wd = (1 << 20);
+    if ((int64_t)N * 20 * 65 + 4096 > wd) wd = (int64_t)N * 20 * 65 + 4096;
+    hc.ws_d = t.get<double>(wd);
+    hc.var0 = t.get<float>(64);
+    float *rm = running_mean ? running_mean : t.get<float>(4 * 64), *rv = running_var ? running_var : t.get<float>(4 * 64);
+    if (!running_mean) dev_memset(rm, 0, sizeof(float) * 256, s);
+    if (!running_var) dev_memset(rv, 0, sizeof(float) * 256, s);
+    for (int k = 0; k < 4; ++k) {
+      hc.gamma[k] = gamma + k * 64;
+      hc.beta[k] = beta + k * 64;
+      hc.w[k] = w + k * 320;
+      hc.bias[k] = bias + k * 5;
+      hc.mean[k] = t.get<float>(64);
+      hc.rstd[k] = t.get<float>(64);
+      hc.rm[k] = rm + k * 64;
+      hc.rv[k] = rv + k * 64;
+    }
+    const bool bwd = d_pred || d_preds;
+    ref::HeadGrads hg;
+    if (bwd) {
+      LBC_CHECK(dgamma && dbeta && dw && dbias && dh, "lbc_op_head: backward outputs missing");
+      LBC_CHECK(!d_pred || onehot, "lbc_op_head: d_pred needs the command one-hot");
+      for (int k = 0; k < 4; ++k) {
+        hg.dgamma[k] = dgamma + k * 64;
+        hg.dbeta[k] = dbeta + k * 64;
+        hg.dw[k] = dw + k * 320;
+        hg.dbias[k] = dbias + k * 5;
+      }
+    }
+    if (precision == PREC_F32) {
+      head_forward<float>(hc, h, N, true, 1e-5f, 0.1f, s);
+      if (bwd) head_backward<float>(hc, h, onehot, d_pred, d_preds, hg, dh, N, s);
+    } else {
+      bf16 *hb = t.get<bf16>(M * 64), *dhb = t.get<bf16>(M * 64);
+      ref::cast<float, bf16>(s, h, hb, M * 64);
+      head_forward<bf16>(hc, hb, N, true, 1e-5f, 0.1f, s);
+      if (bwd) {
+        head_backward<bf16>(hc, hb, onehot, d_pred, d_preds, hg, dhb, N, s);
+        ref::cast<bf16, float>(s, dhb, dh, M * 64);
+      }
+    }
+    if (dh_masked) *dh_masked = hc.mask_fused ? 1 : 0;
+    if (logits_out) dev_copy(logits_out, hc.logits, sizeof(float) * M * 20, s);
+    if (preds_out) dev_copy(preds_out, hc.preds, sizeof(float) * N * 40, s);
+    sync_stream(s);
+  });
+}
+// Stem 7x7/s2 convolution straight from the frames (resnet.py:102,148; normalisation common.py:101-109 fused when
+// `normalize`): img fp32 [N][C][H][W] or (img_u8 != null) uint8 frames in layout 0 = [N][C][H][W] / 1 = [N][H][W][C] with
+// torchvision ToTensor's /255 applied on the device.  w_ref [64][C][7][7].  Outputs (each may be null): x4_out = the
+// zero-padded NHWC4 operand [N][H+6][W+8][4] (C <= 4, bf16 path only), y [N][OH][OW][64], stats_out [128] = per-channel
+// sum | sum of squares of the stored y (bf16 path), and with dy [N][OH][OW][64]: dw [64][C][7][7].
+int lbc_op_stem(const float* img, const uint8_t* img_u8, int layout, const float* w_ref, int normalize, int N, int C, int H,
+                int W, float* x4_out, float* y, float* stats_out, const float* dy, float* dw, int precision, void* stream) {
+  return guarded([&] {
+    require_device();
+    lbc_stream_t s = S(stream);
+    Tmp t;
+    LBC_CHECK(img || img_u8, "lbc_op_stem: no input");
+    ConvL c = make_conv(H, W, C, 64, 7, 2, 3);
+    const int OH = c.OH, OW = c.OW;
+    const int64_t nimg = (int64_t)N * C * H * W, ny = (int64_t)N * OH * OW * 64;
+    const float* imgf = img;
+    if (!img) {   // the float frames the two-step path would see
+      float* f = t.get<float>(nimg);
+      ref::u8_to_f32_nchw(s, img_u8, f, N, C, H, W, layout);
+      imgf = f;
+    }
+    if (precision == PREC_F32) {
+      LBC_CHECK(!x4_out && !stats_out, "lbc_op_stem: x4_out / stats_out exist on the bf16 path only");
+      float *x0 = t.get<float>((int64_t)N * H * W * C), *wp = t.get<float>((int64_t)64 * 49 * C);
+      ref::input_to_nhwc<float>(s, imgf, x0, N, C, H, W, C, normalize != 0, 0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f);
+      ref::pack_weight<float>(s, w_ref, wp, 64, C, 7);
+      if (y) ref::conv_fwd<float>(s, x0, wp, nullptr, false, y, N, H, W, C, 64, 7, 2, 3, OH, OW);
+      if (dy && dw) {
+        int64_t wsn = 4 << 20;
+        float* ws = t.get<float>(wsn);
+        ref::conv_wgrad<float>(s, x0, dy, dw, N, H, W, C, 64, 7, 2, 3, OH, OW, ws, wsn);
+      }
+    } else if (C <= 4) {
+      bf16 *x4 = t.get<bf16>((int64_t)N * (H + 6) * (W + 8) * 4), *w224 = t.get<bf16>(64 * 224), *yb = t.get<bf16>(ny);
+      bool ok = img_u8 && !img ? fast::stem_pad4_u8_bf16(img_u8, layout, x4, N, C, H, W, normalize != 0, s)
+                               : fast::stem_pad4_bf16(imgf, x4, N, C, H, W, normalize != 0, s);
+      LBC_CHECK(ok, "lbc_op_stem: stem_pad4 unavailable (fast kernels disabled or host-emulation build)");
+      if (x4_out) ref::cast<bf16, float>(s, x4, x4_out, (int64_t)N * (H + 6) * (W + 8) * 4);
+      LBC_CHECK(fast::stem_pack_w224_bf16(w_ref, w224, C, s), "stem_pack_w224 failed");
+      if (y) {
+        int rows = 0;
+        float* part = stats_out ? fast::stat_partial_buffer() : nullptr;
+        LBC_CHECK(fast::stem_conv_bf16(x4, w224, yb, N, H, W, OH, OW, nullptr, part, &rows, s), "stem_conv_bf16 declined the shape");
+        if (stats_out) LBC_CHECK(part && fast::col_finalize_bf16(part, rows, 128, stats_out, s), "col_finalize failed");
+        ref::cast<bf16, float>(s, yb, y, ny);
+      }
+      if (dy && dw) {
+        bf16* dyb = t.get<bf16>(ny);
+        ref::cast<float, bf16>(s, dy, dyb, ny);
+        LBC_CHECK(fast::stem_wgrad_bf16(x4, dyb, dw, N, C, H, W, OH, OW, s), "stem_wgrad_bf16 declined the shape");
+      }
+    } else {   // C > 4 (teacher, 7 channels): explicit bf16 column tensor + the generic GEMM kernels as a 1x1 convolution
+      LBC_CHECK(!x4_out && !stats_out, "lbc_op_stem: x4_out / stats_out need C <= 4");
+      const int Kp = ((49 * C + 63) / 64) * 64;
+      bf16 *col = t.get<bf16>((int64_t)N * OH * OW * Kp), *wp = t.get<bf16>((int64_t)64 * Kp), *yb = t.get<bf16>(ny);
+      ConvL g = make_conv(OH, OW, Kp, 64, 1, 1, 0);
+      g.wp = wp;
+      LBC_CHECK(fast::stem_im2col_bf16(imgf, col, N, C, H, W, OH, OW, Kp, normalize != 0, s), "stem_im2col unavailable");
+      LBC_CHECK(fast::stem_pack_weight_bf16(w_ref, wp, C, Kp, s), "stem_pack_weight failed");
+      if (y) {
+        LBC_CHECK(fast::conv_fwd<bf16>(g, col, yb, N, s), "stem GEMM declined the shape");
+        ref::cast<bf16, float>(s, yb, y, ny);
+      }
+      if (dy && dw) {
+        bf16* dyb = t.get<bf16>(ny);
+        int64_t wsn = 4 << 20;
+        float *ws = t.get<float>(wsn), *dwc = t.get<float>((int64_t)64 * Kp);
+        ref::cast<float, bf16>(s, dy, dyb, ny);
+        LBC_CHECK(fast::conv_wgrad<bf16>(g, col, dyb, dwc, N, ws, wsn, s), "stem weight-gradient GEMM declined the shape");
+        LBC_CHECK(fast::stem_unpack_wgrad(dwc, dw, C, Kp, s), "stem_unpack_wgrad failed");
+      }
+    }
     sync_stream(s);
   });
 }

@@ -145,6 +145,21 @@ inline void dev_copy(void* dst, const void* src, size_t bytes, lbc_stream_t s) {
 // ------------------------------------------------------------------ launch counter + per-category profiler
 // g_launches counts every kernel the library launches (bench.py reports it as gpu_launches).
 extern long long g_launches;
+// launch trace (tests): when on, every launch also records its kernel-family name, so a parity test can assert WHICH
+// kernel produced the result (a silent fast -> correctness-first fallback would otherwise pass).  lbc_trace_* in the C ABI.
+extern bool g_trace_on;
+void trace_note(const char* name);
+void trace_reset();
+std::string trace_dump();   // "name\tcount\n" per kernel family
+template <class Tag>
+inline const char* tag_name() {   // "... [with Tag = lbc::ref::k_conv_fwd]": works for the incomplete tag types
+  return __PRETTY_FUNCTION__;
+}
+#define LBC_LAUNCHED(name)                              \
+  do {                                                  \
+    ++::lbc::g_launches;                                \
+    if (::lbc::g_trace_on) ::lbc::trace_note(name);     \
+  } while (0)
 // > 0: par_for launches at most this many blocks and the threads walk the range with a grid stride (experimental() & 4)
 extern int g_par_for_max_blocks;
 struct ProfEntry {
@@ -189,7 +204,7 @@ struct ProfScope {
 #ifdef LBC_HOST_EMU
 template <class Tag, class F>
 inline void par_for(lbc_stream_t, int64_t n, F f) {
-  ++g_launches;
+  LBC_LAUNCHED(tag_name<Tag>());
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) f(i);
 }
@@ -211,7 +226,7 @@ inline void par_for(lbc_stream_t s, int64_t n, F f) {
   // bound (88 K blocks of 256 one-element threads in 222 us); a capped grid lets each thread walk several elements
   if (g_par_for_max_blocks > 0 && nb > g_par_for_max_blocks) nb = g_par_for_max_blocks;
   par_for_kernel<Tag, F><<<(unsigned)nb, bs, 0, s>>>(n, f);
-  ++g_launches;
+  LBC_LAUNCHED(tag_name<Tag>());
   LBC_CUDA(cudaGetLastError());
 }
 #endif

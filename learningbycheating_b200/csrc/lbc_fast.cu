@@ -1,8 +1,22 @@
 // lbc_fast.cu -- sm_100a fast kernels behind the hooks of lbc_fast.h.
 #include "lbc_fast.h"
 
+#include <map>
+
 namespace lbc {
 long long g_launches = 0;
+bool g_trace_on = false;
+static std::map<std::string, long long>& trace_map() {
+  static std::map<std::string, long long> m;
+  return m;
+}
+void trace_note(const char* name) { ++trace_map()[name]; }
+void trace_reset() { trace_map().clear(); }
+std::string trace_dump() {
+  std::string out;
+  for (auto& kv : trace_map()) out += kv.first + "\t" + std::to_string(kv.second) + "\n";
+  return out;
+}
 int g_par_for_max_blocks = 0;
 bool g_prof_on = false;
 std::vector<ProfEntry> g_prof;
@@ -116,7 +130,7 @@ bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, i
     }
     if (smem <= 64 * 514 * 2) {
       stem_im2col_kernel<<<B * OH * (OW / 64), 256, smem, s>>>(img, (uint4*)col, C, H, W, OH, OW, Kp, normalize ? 1 : 0);
-      ++g_launches;
+      LBC_LAUNCHED("stem_im2col_kernel");
       LBC_CUDA(cudaGetLastError());
       return true;
     }

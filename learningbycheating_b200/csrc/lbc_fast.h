@@ -23,7 +23,8 @@ bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* b
 void set_pair_mode(int mode);     // bit 0: CTA-pair (cta_group::2) implicit-GEMM kernels for the >= 128-wide N tiles
 int pair_mode();
 void set_c64_variant(bool on);   // resident-weight / shared-row variant of the 3x3 64->64 convolution (tests toggle it)
-float* stat_partial_buffer();      // shared scratch of the statistics partials (single stream)
+float* stat_partial_buffer();      // shared scratch of the statistics partials (single stream); null if the allocation failed
+int64_t stat_partial_capacity();   // its size in floats
 bool col_finalize_bf16(const float* partial, int rows, int C2, float* sums, lbc_stream_t s);
 
 template <class T>
@@ -151,6 +152,7 @@ template <> struct Fast<bf16> {
 // ---- fused waypoint heads (lbc_fast_head.cu); fold: >=1300 floats, coef: >=128 floats, S: [20][65] doubles
 bool head_forward_bf16(const bf16* h, ref::HeadParams hp, float* fold, float* logits, float* rowmax, float* rowsum,
                        float* preds, int N, int H, int W, lbc_stream_t s);
+bool head_softmax_f32(const float* logits, float* rowmax, float* rowsum, float* preds, int N, int H, int W, lbc_stream_t s);
 bool head_backward_s_bf16(const float* dlogits, const bf16* h, const float* mean, const float* rstd, double* S, int N, int HW,
                           lbc_stream_t s);
 bool head_backward_dh_bf16(const float* dlogits, const bf16* h, ref::HeadParams hp, ref::HeadGrads hg, const float* fold,

@@ -1195,7 +1195,7 @@ static void launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUte
   int tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
   int grid = tiles < sm_count() ? tiles : sm_count();
   conv_gemm_kernel<BN, STAGES, false><<<grid, 192, SP::TOTAL, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO, p);
-  ++g_launches;
+  LBC_LAUNCHED((BN == 64 ? "conv_gemm_kernel<64>" : BN == 128 ? "conv_gemm_kernel<128>" : "conv_gemm_kernel<256>"));
   LBC_CUDA(cudaGetLastError());
 }
 // CTA-pair variant: clusters of 2 (one TPC), persistent over ceil(tiles_m/2) * n_tiles_n pair tiles
@@ -1234,7 +1234,7 @@ static void launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, c
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
   cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
   LBC_CUDA(cudaLaunchKernelEx(&cfg, kern, mA[0], mA[1], mA[2], mA[3], mBhalf, mO, p));
-  ++g_launches;
+  LBC_LAUNCHED((BN == 128 ? "conv_gemm_kernel<128,pair>" : "conv_gemm_kernel<256,pair>"));
   LBC_CUDA(cudaGetLastError());
 }
 // kernel variants (LBC_PAIR overrides; tests toggle them through lbc_set_fast_kernels):
@@ -1341,7 +1341,7 @@ static bool try_conv3x3_c64(const bf16* in, const void* wpack, bf16* out, int B,
   int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int grid = tiles < sm_count() ? tiles : sm_count();
   conv3x3_c64_kernel<5><<<grid, 192, SP::TOTAL, s>>>(mA, mB, mO, p);
-  ++g_launches;
+  LBC_LAUNCHED("conv3x3_c64_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -1409,7 +1409,7 @@ bool stem_conv_bf16(const bf16* x4, const bf16* w224, bf16* raw, int B, int H, i
   int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
   stem_conv_kernel<7><<<grid, 192, SP::TOTAL, s>>>(mX0, mX1, mB, mO, p);
-  ++g_launches;
+  LBC_LAUNCHED("stem_conv_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -1443,7 +1443,7 @@ bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C
   }
   LBC_CUDA(cudaMemsetAsync(dw_ref, 0, sizeof(float) * 64 * C * 49, s));
   stem_wgrad_kernel<STAGES><<<2 * p.splits, 192, smem, s>>>(mDY, mX0, mX1, p);
-  ++g_launches;
+  LBC_LAUNCHED("stem_wgrad_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -2076,7 +2076,7 @@ static void launch_wgrad(const CUtensorMap& mDY, const CUtensorMap* mX, const Wg
   }
   int grid = p.swap ? p.splits * ((p.num_combos + 1) / 2) : p.splits * p.co_tiles * p.num_taps * p.ci_tiles;
   wgrad_gemm_kernel<BNW, STAGES><<<grid, 192, SP::TOTAL, s>>>(mDY, mX[0], mX[1], mX[2], mX[3], p);
-  ++g_launches;
+  LBC_LAUNCHED((BNW == 64 ? "wgrad_gemm_kernel<64>" : "wgrad_gemm_kernel<128>"));
   LBC_CUDA(cudaGetLastError());
 }
 
@@ -2130,7 +2130,7 @@ static void launch_wgrad3(const CUtensorMap& mDY, const CUtensorMap* mX, const W
     cfg.numAttrs = 1;
     LBC_CUDA(cudaLaunchKernelEx(&cfg, kern, mDY, mX[0], mX[1], mX[2], mX[3], p));
   }
-  ++g_launches;
+  LBC_LAUNCHED((PAIR ? "wgrad3_gemm_kernel<pair>" : "wgrad3_gemm_kernel"));
 }
 static int wgrad3_pair_slots() {
   static int slots = [] {
@@ -2239,7 +2239,7 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
     wgrad3_reduce_tr_kernel<<<(unsigned)(c.Co * (c.Ci / 64)), 576, 0, s>>>(p.out, dw_ref, c.Co, c.Ci, p.splits);
   else
     wgrad3_reduce_kernel<<<(unsigned)((wsize + 255) / 256), 256, 0, s>>>(p.out, dw_ref, c.Co, c.Ci, p.splits);
-  ++g_launches;
+  LBC_LAUNCHED("wgrad3_reduce_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -2329,7 +2329,7 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
     launch_wgrad<64, 4>(mDY, mX, p, s);
   int64_t n = wsize;
   wgrad_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(scratch, dw_ref, c.Co, c.Ci, KK);
-  ++g_launches;
+  LBC_LAUNCHED("wgrad_unpack_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }

@@ -151,14 +151,19 @@ __global__ void __launch_bounds__(1024) col_finalize_kernel(const float* __restr
       sums[col] = t;
   }
 }
+constexpr int64_t kPartialFloats = (int64_t)4096 * 2 * 2560;
 static float* partial_buffer() {
   static float* p = [] {
     void* q = nullptr;
-    cudaMalloc(&q, sizeof(float) * (size_t)4096 * 2 * 2560);
+    if (cudaMalloc(&q, sizeof(float) * (size_t)kPartialFloats) != cudaSuccess) {
+      cudaGetLastError();
+      q = nullptr;   // callers treat a null scratch as "fast path unavailable" and report it
+    }
     return (float*)q;
   }();
   return p;
 }
+int64_t stat_partial_capacity() { return kPartialFloats; }
 static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_stream_t s) {
   int rb = P / 512;          // >= 512 rows per block (16 per thread) before splitting
   if (rb > 32) rb = 32;
@@ -167,12 +172,12 @@ static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_s
   rb = (P + rows_per_block - 1) / rows_per_block;
   if (rb > 1) cudaMemsetAsync(sums, 0, sizeof(float) * C2, s);
   col_finalize_kernel<<<dim3((C2 + 31) / 32, rb), 1024, 0, s>>>(partial, P, C2, sums, rows_per_block, rb > 1 ? 1 : 0);
-  ++g_launches;
+  LBC_LAUNCHED("col_finalize_kernel");
 }
 
 float* stat_partial_buffer() { return partial_buffer(); }
 bool col_finalize_bf16(const float* partial, int rows, int C2, float* sums, lbc_stream_t s) {
-  if (!partial || (int64_t)rows * C2 > (int64_t)4096 * 2 * 2560) return false;
+  if (!partial || (int64_t)rows * C2 > kPartialFloats) return false;
   col_finalize(partial, rows, C2, sums, s);
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -184,7 +189,7 @@ bool bn_stats_bf16(const bf16* x, int64_t M, int C, float* sums, lbc_stream_t s)
   float* part = partial_buffer();
   if (!part) return false;
   bn_stats_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>((const uint4*)x, M, g.tpr, g.rpi, part, C);
-  ++g_launches;
+  LBC_LAUNCHED("bn_stats_kernel");
   col_finalize(part, g.grid, 2 * C, sums, s);
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -307,7 +312,7 @@ bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const flo
   a.relu = relu ? 1 : 0;
   a.train = train ? 1 : 0;
   bn_apply_kernel<<<g.grid, g.threads, 0, s>>>(a);
-  ++g_launches;
+  LBC_LAUNCHED("bn_apply_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -581,7 +586,7 @@ static bool launch_bn_bwd_fused(const bf16* dy, const bf16* mask_act, const bf16
     cudaGetLastError();
     return false;
   }
-  ++g_launches;
+  LBC_LAUNCHED((OWN ? "bn_bwd_fused_kernel<own>" : "bn_bwd_fused_kernel"));
   return true;
 }
 
@@ -611,21 +616,21 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
     RowGeom g3 = row_geom(M, C, 3);
     bn_bwd_reduce_kernel<true><<<g3.grid, g3.threads, g3.threads * 16 * sizeof(float), s>>>(
         (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g3.tpr, g3.rpi, part, C, gamma, beta_own);
-    ++g_launches;
+    LBC_LAUNCHED("bn_bwd_reduce_kernel<own>");
     col_finalize(part, g3.grid, 2 * C, sums, s);
     bn_bwd_apply_kernel<true><<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd,
                                                           gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own);
-    ++g_launches;
+    LBC_LAUNCHED("bn_bwd_apply_kernel<own>");
     LBC_CUDA(cudaGetLastError());
     return true;
   }
   bn_bwd_reduce_kernel<false><<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
       (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, gamma, beta_own);
-  ++g_launches;
+  LBC_LAUNCHED("bn_bwd_reduce_kernel");
   col_finalize(part, g.grid, 2 * C, sums, s);
   bn_bwd_apply_kernel<false><<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd,
                                                          gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own);
-  ++g_launches;
+  LBC_LAUNCHED("bn_bwd_apply_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -656,7 +661,7 @@ bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, l
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
   ew_kernel<<<(unsigned)blocks, 256, 0, s>>>((uint4*)dst, (const uint4*)src, (const uint4*)act, nv, mode);
-  ++g_launches;
+  LBC_LAUNCHED("ew_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -740,7 +745,7 @@ bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, c
   else
     bn_relu_maxpool_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
                                                                       (uint2*)idx, N, H, W, C / 8, OH, OW);
-  ++g_launches;
+  LBC_LAUNCHED("bn_relu_maxpool_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -821,7 +826,7 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
   else
     maxpool_relu_bwd_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean,
                                                                        rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW);
-  ++g_launches;
+  LBC_LAUNCHED("maxpool_relu_bwd_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -834,6 +839,7 @@ bool bn_bwd_bf16(const bf16*, const bf16*, const bf16*, const float*, const floa
                  int64_t, int, float*, lbc_stream_t, const float*) { return false; }
 bool ew_bf16(bf16*, const bf16*, const bf16*, int64_t, int, lbc_stream_t) { return false; }
 float* stat_partial_buffer() { return nullptr; }
+int64_t stat_partial_capacity() { return 0; }
 bool col_finalize_bf16(const float*, int, int, float*, lbc_stream_t) { return false; }
 bool bn_relu_maxpool_bf16(const bf16*, const float*, const float*, const float*, const float*, bf16*, uint8_t*, int, int, int,
                           int, int, int, lbc_stream_t) { return false; }

@@ -193,6 +193,14 @@ __global__ void __launch_bounds__(128) head_softmax_kernel(const float* __restri
   }
 }
 
+// SpatialSoftmax alone (common.py:136-152) over [N*20] rows of H*W logits
+bool head_softmax_f32(const float* logits, float* rowmax, float* rowsum, float* preds, int N, int H, int W, lbc_stream_t s) {
+  if (!enabled() || H * W > 4096) return false;
+  head_softmax_kernel<<<N * 20, 128, 0, s>>>(logits, rowmax, rowsum, preds, H, W);
+  LBC_LAUNCHED("head_softmax_kernel");
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
 bool head_forward_bf16(const bf16* h, ref::HeadParams hp, float* fold, float* logits, float* rowmax, float* rowsum,
                        float* preds, int N, int H, int W, lbc_stream_t s) {
   if (!enabled()) return false;
@@ -204,9 +212,9 @@ bool head_forward_bf16(const bf16* h, ref::HeadParams hp, float* fold, float* lo
     head_logits4_kernel<<<(unsigned)((npix + 511) / 512), 128, 0, s>>>((const uint4*)h, fold, logits, npix, HW);
   else
     head_logits_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, s>>>((const uint4*)h, fold, logits, npix, HW);
-  ++g_launches;
+  LBC_LAUNCHED(((experimental() & 2) ? "head_logits4_kernel" : "head_logits_kernel"));
   head_softmax_kernel<<<N * 20, 128, 0, s>>>(logits, rowmax, rowsum, preds, H, W);
-  ++g_launches;
+  LBC_LAUNCHED("head_softmax_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -486,7 +494,7 @@ bool head_backward_s_bf16(const float* dlogits, const bf16* h, const float* mean
     head_s4_kernel<<<grid, 256, 0, s>>>(dlogits, (const uint4*)h, mean, rstd, S, N, HW);
   else
     head_s_kernel<<<grid, 256, 0, s>>>(dlogits, (const uint4*)h, mean, rstd, S, N, HW);
-  ++g_launches;
+  LBC_LAUNCHED(((experimental() & 2) ? "head_s4_kernel" : "head_s_kernel"));
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -501,12 +509,13 @@ bool head_backward_dh_bf16(const float* dlogits, const bf16* h, ref::HeadParams 
   else
     head_dh_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, s>>>(dlogits, (const uint4*)h, fold, coef, hp.mean[0], hp.rstd[0],
                                                                 (uint4*)dh, npix, HW);
-  ++g_launches;
+  LBC_LAUNCHED(((experimental() & 2) ? "head_dh4_kernel" : "head_dh_kernel"));
   LBC_CUDA(cudaGetLastError());
   return true;
 }
 
 #else
+bool head_softmax_f32(const float*, float*, float*, float*, int, int, int, lbc_stream_t) { return false; }
 bool head_forward_bf16(const bf16*, ref::HeadParams, float*, float*, float*, float*, float*, int, int, int, lbc_stream_t) {
   return false;
 }

@@ -6,6 +6,7 @@
 #include <type_traits>
 
 #include "lbc_fast.h"
+#include "lbc_head.h"
 
 namespace lbc {
 
@@ -76,8 +77,6 @@ class Net : public NetBase {
   ref::PackEntry* pack_dev = nullptr;
   std::vector<BNL*> conv_bns;     // BNs fed directly by a trunk convolution
   float* head_fold = nullptr;  // folded BN+1x1 map A[20][64], b'[20]; coef c0/c1 [128]
-  bool head_fast_used = false;
-  bool head_mask_fused = false;
   bool stem_pool_fused = false;
   size_t total_bytes = 0;
   int cur_B = 0;
@@ -386,7 +385,7 @@ class Net : public NetBase {
                     int* stat_rows = nullptr) {
     ProfScope ps("conv_fwd", s, conv_flops(c, B), 0);
     if (stat_rows) *stat_rows = 0;
-    float* part = (stat_rows && cur_train && (int64_t)c.Co * 2 * ((int64_t)B * c.OH * c.OW / 128 + 64) <= (int64_t)4096 * 2 * 2560)
+    float* part = (stat_rows && cur_train && (int64_t)c.Co * 2 * ((int64_t)B * c.OH * c.OW / 128 + 64) <= fast::stat_partial_capacity())
                       ? fast::stat_partial_buffer()
                       : nullptr;
     int rows = 0;
@@ -450,17 +449,31 @@ class Net : public NetBase {
     if (fast::Fast<T>::ew(dst, g, act, n, 1, s)) return;
     ref::add_masked_inplace<T>(s, dst, g, act, n);
   }
-  ref::HeadParams head_params(bool train) {
-    ref::HeadParams hp;
+  HeadCtx hc;
+  HeadCtx& head_ctx() {   // (parameter / buffer pointers follow the currently bound flat arrays)
+    hc.H = head_h;
+    hc.W = head_w;
+    hc.logits = logits;
+    hc.dlogits = dlogits;
+    hc.rowmax = rowmax;
+    hc.rowsum = rowsum;
+    hc.preds = preds;
+    hc.S = headS;
+    hc.fold = head_fold;
+    hc.bn_sums = bn_sums;
+    hc.ws_d = ws_d;
+    hc.var0 = hbn[0].var;
     for (int k = 0; k < 4; ++k) {
-      hp.gamma[k] = P + hbn[k].g_off;
-      hp.beta[k] = P + hbn[k].b_off;
-      hp.w[k] = P + hw_off[k];
-      hp.bias[k] = P + hb_off[k];
-      hp.mean[k] = train ? hbn[0].mean : hbn[k].mean;
-      hp.rstd[k] = train ? hbn[0].rstd : hbn[k].rstd;
+      hc.gamma[k] = P + hbn[k].g_off;
+      hc.beta[k] = P + hbn[k].b_off;
+      hc.w[k] = P + hw_off[k];
+      hc.bias[k] = P + hb_off[k];
+      hc.mean[k] = hbn[k].mean;
+      hc.rstd[k] = hbn[k].rstd;
+      hc.rm[k] = BUF + hbn[k].rm_off;
+      hc.rv[k] = BUF + hbn[k].rv_off;
     }
-    return hp;
+    return hc;
   }
 
   // ------------------------------------------------------------------ forward
@@ -481,7 +494,10 @@ class Net : public NetBase {
     int stem_stat_rows = 0;
     if (std::is_same<T, bf16>::value && stem_x4 && fast::enabled()) {
       ProfScope ps("conv_fwd", s, conv_flops(stem, B), 0);
-      float* part = train ? fast::stat_partial_buffer() : nullptr;
+      // statistics partials from the epilogue only while they fit the shared scratch (one 128-float row per 128-pixel
+      // tile); larger batches fall back to the separate statistics pass (bn_stats_bf16 below)
+      const bool part_fits = ((int64_t)B * stem_oh * stem_ow / 128 + 64) * 128 <= fast::stat_partial_capacity();
+      float* part = (train && part_fits) ? fast::stat_partial_buffer() : nullptr;
       bool ok = (u8_image ? fast::stem_pad4_u8_bf16(u8_image, u8_layout, (bf16*)stem_x4, B, in_ch, in_h, in_w, normalize, s)
                           : fast::stem_pad4_bf16(image, (bf16*)stem_x4, B, in_ch, in_h, in_w, normalize, s)) &&
                 fast::stem_pack_w224_bf16(P + stem.w_off, (bf16*)stem_w224, in_ch, s) &&
@@ -563,35 +579,10 @@ class Net : public NetBase {
     }
     // heads
     const T* hfeat = dec_out[2];
-    int HW = head_h * head_w;
-    int64_t M = (int64_t)B * HW;
-    ProfScope ps_head("head", s, 0, (double)M * 64 * sizeof(T) * 2 + (double)M * 20 * 4 * 2);
-    bool head_stats_done = false;
-    if (train && std::is_same<T, bf16>::value && fast::enabled()) {
-      if (fast::bn_stats_bf16((const bf16*)hfeat, M, 64, bn_sums, s)) {
-        for (int k = 0; k < 4; ++k)   // same statistics, four sets of running buffers (image.py:56)
-          ref::bn_finalize_sums(s, bn_sums, 64, M, kBnEps, kBnMomentum, hbn[0].mean, hbn[k].rstd, BUF + hbn[k].rm_off,
-                                BUF + hbn[k].rv_off);
-        head_stats_done = true;
-      }
-    }
-    if (head_stats_done) {
-    } else if (train) {
-      ref::bn_stats<T>(s, hfeat, M, 64, hbn[0].mean, hbn[0].var, ws_d);
-      for (int k = 0; k < 4; ++k)
-        ref::bn_finalize(s, hbn[0].mean, hbn[0].var, 64, M, kBnEps, kBnMomentum, hbn[k].rstd, BUF + hbn[k].rm_off,
-                         BUF + hbn[k].rv_off);
-    } else {
-      for (int k = 0; k < 4; ++k)
-        ref::bn_eval_stats(s, BUF + hbn[k].rm_off, BUF + hbn[k].rv_off, 64, kBnEps, hbn[k].mean, hbn[k].rstd);
-    }
-    head_fast_used = false;
-    if (std::is_same<T, bf16>::value)
-      head_fast_used = fast::head_forward_bf16((const bf16*)hfeat, head_params(train), head_fold, logits, rowmax, rowsum, preds,
-                                               B, head_h, head_w, s);
-    if (!head_fast_used) {
-      ref::head_logits<T>(s, hfeat, head_params(train), logits, B, HW, 64);
-      ref::head_softmax(s, logits, rowmax, rowsum, preds, B, head_h, head_w);
+    {
+      const int64_t M = (int64_t)B * head_h * head_w;
+      ProfScope ps_head("head", s, 0, (double)M * 64 * sizeof(T) * 2 + (double)M * 20 * 4 * 2);
+      head_forward<T>(head_ctx(), hfeat, B, train, kBnEps, kBnMomentum, s);
     }
     if (out_preds) dev_copy(out_preds, preds, sizeof(float) * B * 40, s);
     if (out_pred) ref::head_select(s, preds, onehot_saved, out_pred, B);
@@ -640,7 +631,6 @@ class Net : public NetBase {
     T* gnext = g[3];
     // heads
     const T* hfeat = dec_out[2];
-    ref::HeadParams hp = head_params(true);
     ref::HeadGrads hg;
     for (int k = 0; k < 4; ++k) {
       hg.dgamma[k] = G + hbn[k].g_off;
@@ -648,20 +638,11 @@ class Net : public NetBase {
       hg.dw[k] = G + hw_off[k];
       hg.dbias[k] = G + hb_off[k];
     }
-    ref::head_dlogits(s, logits, rowmax, rowsum, preds, onehot_saved, d_pred, d_preds, dlogits, B, head_h, head_w);
-    head_mask_fused = false;
     {
       ProfScope ps_head("head", s, 0, (double)B * HW * 64 * sizeof(T) * 3 + (double)B * HW * 20 * 4 * 3);
-      bool s_done = false;
-      if (std::is_same<T, bf16>::value && head_fast_used)
-        s_done = fast::head_backward_s_bf16(dlogits, (const bf16*)hfeat, hbn[0].mean, hbn[0].rstd, headS, B, HW, s);
-      if (!s_done) ref::head_s<T>(s, dlogits, hfeat, hbn[0].mean, hbn[0].rstd, headS, B, HW, 64, ws_d);
-      ref::head_param_grads(s, headS, hp, hg, 64);
-      if (s_done)
-        head_mask_fused = fast::head_backward_dh_bf16(dlogits, (const bf16*)hfeat, hp, hg, head_fold, head_fold + 1300,
-                                                      (bf16*)gcur, B, HW, s);
-      if (!head_mask_fused) ref::head_dh<T>(s, dlogits, hfeat, hbn[0].mean, hbn[0].rstd, hp, hg, gcur, B, HW, 64);
+      head_backward<T>(head_ctx(), hfeat, onehot_saved, d_pred, d_preds, hg, gcur, B, s);
     }
+    const bool head_mask_fused = hc.mask_fused;
     // decoder, last stage first
     for (int i = 2; i >= 0; --i) {
       const ConvL& c = dcv[i];

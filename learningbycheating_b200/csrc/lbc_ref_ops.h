@@ -443,6 +443,10 @@ inline void bn_finalize_sums(lbc_stream_t s, const float* sums, int C, int64_t M
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * ((double)M / (double)(M > 1 ? M - 1 : 1)));
   });
 }
+struct k_rstd_to_var;
+inline void rstd_to_var(lbc_stream_t s, const float* rstd, float* var_biased, int C, float eps) {
+  par_for<k_rstd_to_var>(s, C, [=] LBC_LAMBDA(int64_t c) { var_biased[c] = 1.0f / (rstd[c] * rstd[c]) - eps; });
+}
 // eval mode: mean = running_mean, rstd from running_var
 inline void bn_eval_stats(lbc_stream_t s, const float* running_mean, const float* running_var, int C, float eps,
                           float* mean, float* rstd, const float* negshift = nullptr) {

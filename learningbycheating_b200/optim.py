@@ -35,8 +35,8 @@ class Adam:
 
     def _locate(self):
         """Find the module whose flat arrays the parameters are views of (PolicyNetBase._flatten)."""
-        ref = getattr(self.param_list[0], "_lbc_owner", None)
-        owner = ref() if ref is not None else None
+        from .common import owner_of
+        owner = owner_of(self.param_list[0])
         if owner is None:
             raise _lib.LbcError("Adam: parameters do not belong to an lbc model that has run a forward pass "
                                 "(use torch.optim.Adam for foreign parameters)")
@@ -59,9 +59,15 @@ class Adam:
         for p, _, gview, on in st.param_views:
             if on and (p.grad is None or p.grad.data_ptr() != gview.data_ptr()):
                 raise _lib.LbcError("Adam: gradients are not the native flat gradient views (mixed / replaced .grad)")
-        if self.exp_avg is None or self.exp_avg.numel() != flat.numel() or self.exp_avg.device != flat.device:
+        if self.exp_avg is None:
             self.exp_avg = torch.zeros_like(flat)
             self.exp_avg_sq = torch.zeros_like(flat)
+        elif self.exp_avg.numel() != flat.numel():
+            raise _lib.LbcError("Adam: moment buffers hold %d elements, the model has %d (state of another model?)"
+                                % (self.exp_avg.numel(), flat.numel()))
+        elif self.exp_avg.device != flat.device:     # e.g. a checkpoint loaded with map_location='cpu'
+            self.exp_avg = self.exp_avg.to(flat.device)
+            self.exp_avg_sq = self.exp_avg_sq.to(flat.device)
         if self._ranges is None:
             # contiguous runs of parameters that receive gradients (conv.fc.* never does: grad is None)
             runs = []
@@ -85,10 +91,17 @@ class Adam:
                                        self.step_count, float(self.grad_scale), sp))
 
     def state_dict(self):
+        """Own (flat) format -- NOT interchangeable with torch.optim.Adam.state_dict(): one exp_avg / exp_avg_sq array over
+        the model's flat parameter array instead of per-parameter entries."""
         return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
                     param_groups=[{k: v for k, v in g.items() if k != "params"} for g in self.param_groups])
 
     def load_state_dict(self, sd):
-        self.step_count = sd["step"]
+        if "state" in sd and "exp_avg" not in sd:
+            raise _lib.LbcError("Adam.load_state_dict: this is a torch.optim.Adam state_dict (per-parameter layout); "
+                                "lbc.Adam stores flat moment arrays (see Adam.state_dict)")
+        self.step_count = int(sd["step"])
         self.exp_avg, self.exp_avg_sq = sd["exp_avg"], sd["exp_avg_sq"]
+        if (self.exp_avg is None) != (self.exp_avg_sq is None):
+            raise _lib.LbcError("Adam.load_state_dict: exp_avg / exp_avg_sq must both be present")
         self._ranges = None
