@@ -24,6 +24,10 @@ typedef struct lbc_net lbc_net_t;
 #define LBC_NET_BIRDVIEW_RESNET18 1 /* BirdViewPolicyModelSS('resnet18'), bird_view/models/birdview.py:47-79 */
 #define LBC_PREC_F32 0  /* fp32 storage + fp32 math: parity mode (<=1e-3 vs the reference CPU path) */
 #define LBC_PREC_BF16 1 /* bf16 NHWC activations / tcgen05 bf16 MMA, fp32 accumulation + statistics  */
+/* fp32 NHWC storage, fp32 BN / softmax / loss / Adam; every convolution on the tcgen05 tensor cores with split-precision
+ * operands (each fp32 operand = hi + lo 16-bit planes, 3 MMAs per K block, fp32 TMEM accumulation, fp32 epilogue):
+ * parity-grade numerics (<=1e-3 vs the reference CPU path) at tensor-core speed */
+#define LBC_PREC_F32TC 2
 
 const char* lbc_last_error(void);
 /* 1 = CUDA sm_100a build (the product), 0 = host-emulation build used only by the CPU unit tests */

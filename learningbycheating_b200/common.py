@@ -18,7 +18,7 @@ from . import _lib
 
 KIND_IMAGE_RESNET34 = 0
 KIND_BIRDVIEW_RESNET18 = 1
-PRECISIONS = {"fp32": 0, "bf16": 1}
+PRECISIONS = {"fp32": 0, "bf16": 1, "fp32tc": 2}
 
 _RESNET_LAYERS = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3]}   # resnet.py:163-164
 

@@ -74,6 +74,15 @@ void sync_stream(lbc_stream_t s) {
   (void)s;
 #endif
 }
+// operand-split scratch of the fp32tc single-op calls
+fast::TcWork make_tcwork(Tmp& t, int64_t a_bytes, int64_t b_bytes) {
+  fast::TcWork w;
+  w.a_bytes = a_bytes;
+  w.b_bytes = b_bytes;
+  w.a16 = t.get<uint8_t>(a_bytes);
+  w.b16 = t.get<uint8_t>(b_bytes);
+  return w;
+}
 ConvL make_conv(int H, int W, int Ci, int Co, int K, int stride, int pad) {
   ConvL c;
   c.Ci = Ci;
@@ -320,6 +329,14 @@ int lbc_op_conv_fwd(const float* x, const float* w_ref, float* y, int N, int H, 
       float* wp = t.get<float>(nw);
       ref::pack_weight<float>(s, w_ref, wp, Co, Ci, K);
       ref::conv_fwd<float>(s, x, wp, bias_co, false, y, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW);
+    } else if (precision == PREC_F32TC) {
+      LBC_CHECK(!stats_out, "lbc_op_conv_fwd: epilogue statistics exist on the bf16 path only");
+      float *wp = t.get<float>(nw), *w16 = t.get<float>(nw);
+      ref::pack_weight<float>(s, w_ref, wp, Co, Ci, K);
+      LBC_CHECK(fast::tc_split(wp, w16, (int64_t)Co * K * K, Ci, fast::TC_F16, fast::kTcWeightScale, s), "tc_split unavailable");
+      c.wp16 = w16;
+      fast::TcWork tw = make_tcwork(t, nx * 4, 16);
+      LBC_CHECK(fast::conv_fwd_tc(c, x, nullptr, y, N, bias_co, false, fast::TC_F16, tw, s), "conv_fwd_tc declined the shape");
     } else {
       bf16 *xb = t.get<bf16>(nx), *wb = t.get<bf16>(nw), *yb = t.get<bf16>(ny);
       ref::cast<float, bf16>(s, x, xb, nx);
@@ -354,6 +371,15 @@ int lbc_op_conv_dgrad(const float* dy, const float* w_ref, float* dx, int N, int
       float* wp = t.get<float>(nw);
       ref::pack_weight<float>(s, w_ref, wp, Co, Ci, K);
       ref::conv_dgrad<float>(s, dy, wp, dx, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, bias_ci, relu != 0, false);
+    } else if (precision == PREC_F32TC) {
+      // relu != 0 marks the ConvTranspose2d forward (dy is an activation: fp16 planes); otherwise dy is a gradient (bf16 planes)
+      float *wt = t.get<float>(nw), *w16 = t.get<float>(nw);
+      ref::pack_weight_t<float>(s, w_ref, wt, Co, Ci, K);
+      LBC_CHECK(fast::tc_split(wt, w16, (int64_t)Ci * K * K, Co, fast::TC_F16, fast::kTcWeightScale, s), "tc_split unavailable");
+      c.wpt16 = w16;
+      fast::TcWork tw = make_tcwork(t, ny * 4, 16);
+      LBC_CHECK(fast::conv_dgrad_tc(c, dy, nullptr, dx, N, bias_ci, relu != 0, relu ? fast::TC_F16 : fast::TC_BF16, tw, s),
+                "conv_dgrad_tc declined the shape");
     } else {
       bf16 *xb = t.get<bf16>(nx), *wb = t.get<bf16>(nw), *yb = t.get<bf16>(ny);
       bf16* wtb = t.get<bf16>(nw);
@@ -384,6 +410,18 @@ int lbc_op_block_dgrad_ds(const float* dy1, const float* dy_ds, const float* w1_
       ref::pack_weight<float>(s, wd_ref, wd, Co, Ci, 1);
       ref::conv_dgrad<float>(s, dy1, w1, dx, N, H, W, Ci, Co, 3, 2, 1, c1.OH, c1.OW, nullptr, false, false);
       ref::conv_dgrad<float>(s, dy_ds, wd, dx, N, H, W, Ci, Co, 1, 2, 0, cd.OH, cd.OW, nullptr, false, true);
+    } else if (precision == PREC_F32TC) {
+      const int64_t nw = (int64_t)Co * 9 * Ci, nc = (int64_t)Ci * 2 * Co;
+      float *w1t = t.get<float>(nw), *w1t16 = t.get<float>(nw), *wc = t.get<float>(nc), *wc16 = t.get<float>(nc);
+      ref::pack_weight_t<float>(s, w1_ref, w1t, Co, Ci, 3);
+      ref::pack_weight_comb<float>(s, w1_ref, wd_ref, wc, Co, Ci);
+      LBC_CHECK(fast::tc_split(w1t, w1t16, (int64_t)Ci * 9, Co, fast::TC_F16, fast::kTcWeightScale, s) &&
+                    fast::tc_split(wc, wc16, (int64_t)Ci * 2, Co, fast::TC_F16, fast::kTcWeightScale, s),
+                "tc_split unavailable");
+      c1.wpt16 = w1t16;
+      c1.wcomb16 = wc16;
+      fast::TcWork tw = make_tcwork(t, ny * 4, ny * 4);
+      LBC_CHECK(fast::conv_dgrad_tc(c1, dy1, dy_ds, dx, N, nullptr, false, fast::TC_BF16, tw, s), "conv_dgrad_tc (fused) declined the shape");
     } else {
       bf16 *d1 = t.get<bf16>(ny), *d2 = t.get<bf16>(ny), *xb = t.get<bf16>(nx);
       bf16 *w1 = t.get<bf16>((int64_t)Co * 9 * Ci), *w1t = t.get<bf16>((int64_t)Co * 9 * Ci), *wd = t.get<bf16>((int64_t)Co * Ci);
@@ -418,6 +456,10 @@ int lbc_op_conv_wgrad(const float* x, const float* dy, float* dw_ref, int N, int
     float* ws = t.get<float>(wsn);
     if (precision == PREC_F32) {
       ref::conv_wgrad<float>(s, x, dy, dw_ref, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, ws, wsn);
+    } else if (precision == PREC_F32TC) {
+      fast::TcWork tw = make_tcwork(t, nx * 4, ny * 4);
+      LBC_CHECK(fast::conv_wgrad_tc(c, x, nullptr, dy, dw_ref, N, fast::TC_F16, fast::TC_BF16, ws, wsn, tw, s),
+                "conv_wgrad_tc declined the shape");
     } else {
       bf16 *xb = t.get<bf16>(nx), *yb = t.get<bf16>(ny);
       ref::cast<float, bf16>(s, x, xb, nx);
@@ -706,6 +748,26 @@ int lbc_op_stem(const float* img, const uint8_t* img_u8, int layout, const float
         int64_t wsn = 4 << 20;
         float* ws = t.get<float>(wsn);
         ref::conv_wgrad<float>(s, x0, dy, dw, N, H, W, C, 64, 7, 2, 3, OH, OW, ws, wsn);
+      }
+    } else if (precision == PREC_F32TC) {
+      LBC_CHECK(!x4_out && !stats_out, "lbc_op_stem: x4_out / stats_out exist on the bf16 path only");
+      const int Kp = ((49 * C + 63) / 64) * 64;
+      const int64_t npix = (int64_t)N * OH * OW;
+      float *x0 = t.get<float>((int64_t)N * H * W * C), *wp = t.get<float>((int64_t)64 * Kp), *wp16 = t.get<float>((int64_t)64 * Kp);
+      ref::input_to_nhwc<float>(s, imgf, x0, N, C, H, W, C, normalize != 0, 0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f);
+      ConvL g = make_conv(OH, OW, Kp, 64, 1, 1, 0);
+      ref::pack_stem_weight(s, w_ref, wp, C, Kp);
+      LBC_CHECK(fast::tc_split(wp, wp16, 64, Kp, fast::TC_F16, fast::kTcWeightScale, s), "tc_split unavailable");
+      g.wp16 = wp16;
+      fast::TcWork tw = make_tcwork(t, npix * Kp * 4, npix * 64 * 4);
+      LBC_CHECK(fast::tc_stem_im2col(x0, tw.a16, N, C, H, W, OH, OW, Kp, s), "tc_stem_im2col unavailable");
+      if (y) LBC_CHECK(fast::conv_fwd_tc(g, nullptr, tw.a16, y, N, nullptr, false, fast::TC_F16, tw, s), "stem GEMM (tc) declined the shape");
+      if (dy && dw) {
+        int64_t wsn = 4 << 20;
+        float *ws = t.get<float>(wsn), *dwc = t.get<float>((int64_t)64 * Kp);
+        LBC_CHECK(fast::conv_wgrad_tc(g, nullptr, tw.a16, dy, dwc, N, fast::TC_F16, fast::TC_BF16, ws, wsn, tw, s),
+                  "stem weight gradient (tc) declined the shape");
+        LBC_CHECK(fast::stem_unpack_wgrad(dwc, dw, C, Kp, s), "stem_unpack_wgrad failed");
       }
     } else if (C <= 4) {
       bf16 *x4 = t.get<bf16>((int64_t)N * (H + 6) * (W + 8) * 4), *w224 = t.get<bf16>(64 * 224), *yb = t.get<bf16>(ny);

@@ -19,6 +19,7 @@
 #ifndef LBC_HOST_EMU
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #endif
 
 #include <map>
@@ -47,24 +48,25 @@ static PFN_encodeTiled encode_fn() {
   return fn;
 }
 
-// bf16 tensor [N][H][W][C] with arbitrary (16 B aligned) strides; box {64, bw, bh, bn}, 128 B swizzle, zero OOB fill
+// 16-bit (bf16 / fp16: same tensor-map type for our purposes, TMA only moves the bits) or fp32 tensor [N][H][W][C] with
+// arbitrary (16 B aligned) strides; box {128 B of channels, bw, bh, bn}, 128 B swizzle, zero OOB fill
 static CUtensorMap make_map_4d(const void* base, int C, int W, int H, int N, int64_t sW, int64_t sH, int64_t sN, int bw,
-                               int bh, int bn) {
-  typedef std::tuple<const void*, int, int, int, int, int64_t, int64_t, int64_t, int, int, int> Key;
+                               int bh, int bn, bool f32 = false) {
+  typedef std::tuple<const void*, int, int, int, int, int64_t, int64_t, int64_t, int, int, int, bool> Key;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  Key key(base, C, W, H, N, sW, sH, sN, bw, bh, bn);
+  Key key(base, C, W, H, N, sW, sH, sN, bw, bh, bn, f32);
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)sW, (cuuint64_t)sH, (cuuint64_t)sN};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t box[4] = {f32 ? 32u : 64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_fn()(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                           const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LBC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed: " + std::to_string((int)r));
   cache[key] = m;
   return m;
@@ -104,6 +106,12 @@ struct ConvGemmParams {
   float* stat_partial;
   int stat_C;
   int valid_n;                      // batch size (rows of images >= valid_n are the zero-filled tail)
+  // split-precision mode (fp32tc): both operands are stored as two 16-bit planes [hi | lo] along K (A: channels
+  // [0,a_plane) hi, [a_plane,2*a_plane) lo; B: every tap slab [hi b_plane | lo b_plane]); the K loop runs the three
+  // products hi*hi + hi*lo + lo*hi into the same fp32 accumulator.  fmt: UMMA 16-bit operand format (0 = fp16, 1 = bf16).
+  int split, a_plane, b_plane;
+  uint32_t fmt_a, fmt_b;
+  float out_scale;                  // accumulator scale applied in the epilogue (undoes the power-of-two operand scaling)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -251,15 +259,15 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 
 constexpr int A_BYTES = 128 * 128;  // 128 positions x 64 bf16
 
-template <int BN, int STAGES, bool PAIR = false>
+template <int BN, int STAGES, bool PAIR = false, bool OUT_F32 = false>
 struct SmemPlan {
   static constexpr int B_BYTES = PAIR ? BN * 64 : BN * 128;   // CTA pair: each CTA stages BN/2 rows of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue staging: the whole 128 x BN bf16 tile in OUT_PASSES column passes.  Two passes of 128 columns would buy the
   // pair kernel (BN = 256) a fifth operand stage; measured on the B200 that is no faster (52.3 vs 51.5 us per launch),
-  // so the tile is staged in one pass.
-  static constexpr int OUT_PASSES = 1;
-  static constexpr int OUT_BYTES = (BN / 64) * A_BYTES / OUT_PASSES;
+  // so the tile is staged in one pass.  fp32 output: two passes of BN/2 columns through the same staging bytes.
+  static constexpr int OUT_PASSES = OUT_F32 ? 2 : 1;
+  static constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
   static constexpr int RED_OFF = BAR_OFF + 256;       // 128 x 4 floats: column-statistics scratch
   static constexpr int TOTAL = RED_OFF + 2048 + 1024;  // barriers + scratch + alignment slack
@@ -271,12 +279,12 @@ struct SmemPlan {
 // and BN/2 rows of B (its TMA loads signal the LEADER's full barrier), the leader's commits are multicast to the
 // empty / accumulator-full barriers of both CTAs, both epilogues arrive on the leader's accumulator-empty barrier.
 // Each CTA's 128 x BN slice of the accumulator lives in its own TMEM, so the epilogue is unchanged.
-template <int BN, int STAGES, bool PAIR>
+template <int BN, int STAGES, bool PAIR, bool OUT_F32>
 __global__ void __launch_bounds__(192, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                  const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
                  const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mO, const ConvGemmParams p) {
-  typedef SmemPlan<BN, STAGES, PAIR> SP;
+  typedef SmemPlan<BN, STAGES, PAIR, OUT_F32> SP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* out_stage = smem + STAGES * SP::STAGE_BYTES;
@@ -321,7 +329,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int k_iters = p.num_taps * p.k_chunks;
+  const int nterm = p.split ? 3 : 1;
+  const int k_iters = p.num_taps * nterm * p.k_chunks;
   // tile walk.  single CTA: tile = blockIdx.x + i*gridDim.x over tiles_m*n_tiles_n (m_tile = tile / n_tiles_n).
   // pair: the same walk over ceil(tiles_m/2)*n_tiles_n PAIR tiles by pair index; this CTA owns m_tile = 2*(..)+rank,
   // which for an odd tiles_m can be one past the end: its coordinates are past the batch, so TMA zero-fills the
@@ -346,24 +355,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           const int mid = p.tap_map[tap];
           const CUtensorMap* ma = mid == 0 ? &mA0 : (mid == 1 ? &mA1 : (mid == 2 ? &mA2 : &mA3));
           const int dh = p.tap_dh[tap], dw = p.tap_dw[tap], koff = p.tap_koff[tap];
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * SP::STAGE_BYTES;
-            if constexpr (PAIR) {
-              // the leader's barrier collects the bytes of both CTAs (the peer's may land before this expect_tx:
-              // the tx-count goes transiently negative inside the phase, which mbarrier allows)
-              if (crank == 0) mbar_expect_tx(&full[stage], 2 * SP::STAGE_BYTES);
-              const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-              tma_load_4d_pair(ma, sa, lead_full, kc * 64, w0 + dw, h0 + dh, n0);
-              tma_load_2d_pair(&mB, sa + A_BYTES, lead_full, koff + kc * 64, n_tile * BN + (int)crank * (BN / 2));
-            } else {
-              mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
-              tma_load_4d(ma, sa, &full[stage], kc * 64, w0 + dw, h0 + dh, n0);
-              tma_load_2d(&mB, sa + A_BYTES, &full[stage], koff + kc * 64, n_tile * BN);
-            }
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
+          for (int term = 0; term < nterm; ++term) {   // split mode: hi*hi, hi*lo, lo*hi
+            const int ac0 = term == 2 ? p.a_plane : 0;
+            const int bc0 = koff + (term == 1 ? p.b_plane : 0);
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * SP::STAGE_BYTES;
+              if constexpr (PAIR) {
+                // the leader's barrier collects the bytes of both CTAs (the peer's may land before this expect_tx:
+                // the tx-count goes transiently negative inside the phase, which mbarrier allows)
+                if (crank == 0) mbar_expect_tx(&full[stage], 2 * SP::STAGE_BYTES);
+                const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                tma_load_4d_pair(ma, sa, lead_full, ac0 + kc * 64, w0 + dw, h0 + dh, n0);
+                tma_load_2d_pair(&mB, sa + A_BYTES, lead_full, bc0 + kc * 64, n_tile * BN + (int)crank * (BN / 2));
+              } else {
+                mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
+                tma_load_4d(ma, sa, &full[stage], ac0 + kc * 64, w0 + dw, h0 + dh, n0);
+                tma_load_2d(&mB, sa + A_BYTES, &full[stage], bc0 + kc * 64, n_tile * BN);
+              }
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
             }
           }
         }
@@ -371,8 +384,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (pair: the leader CTA only) =====================
-    // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128 (pair: M=256 over the two CTAs)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+    // instruction descriptor: D=f32, A/B = bf16 (format 1) or fp16 (0), both K-major, N=BN, M=128 (pair: M=256 over the two CTAs)
+    const uint32_t idesc = (1u << 4) | (p.fmt_a << 7) | (p.fmt_b << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
@@ -441,6 +454,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           uint32_t r[32];
           tmem_ld32(taddr + ch * 32, r);
           const int col0 = n_tile * BN + ch * 32;
+          if constexpr (OUT_F32) {
+            // fp32 output: 32 columns = one 128-byte row of a {32 ch, TW, TH, TN} fp32 store box
+            uint8_t* rowp = out_stage + cl * A_BYTES + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = __uint_as_float(r[j * 4 + e]) * p.out_scale;
+                if (p.bias) a += __ldg(p.bias + col0 + j * 4 + e);
+                if (p.relu) a = fmaxf(a, 0.f);
+                v[e] = a;
+              }
+              *reinterpret_cast<float4*>(rowp + ((j ^ (row & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            continue;
+          }
           uint8_t* rowp = out_stage + (cl >> 1) * A_BYTES + row * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -474,12 +504,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (issuer) {
+          constexpr int BOXC = OUT_F32 ? 32 : 64;   // channels per 128-byte store box
 #pragma unroll
-          for (int b = 0; b < CW / 64; ++b)
-            tma_store_4d(&mO, out_stage + b * A_BYTES, n_tile * BN + hp * CW + b * 64, w0, h0, n0);
+          for (int b = 0; b < CW / BOXC; ++b)
+            tma_store_4d(&mO, out_stage + b * A_BYTES, n_tile * BN + hp * CW + b * BOXC, w0, h0, n0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (p.stat_partial && m_tile < tiles_m) {
+        if (!OUT_F32 && p.stat_partial && m_tile < tiles_m) {
           // per-channel sum / sum of squares of this pass's bf16 outputs, read back from the staging tile
           constexpr int PAIRS = CW / 2, TPP = 128 / PAIRS, RPT = 128 / TPP;
           float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
@@ -1183,28 +1214,32 @@ static bool tile_geometry(int OH, int OW, int B, ConvGemmParams& p) {
   return TN <= 256;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool OUT_F32 = false>
 static void launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUtensorMap& mO, const ConvGemmParams& p,
                         lbc_stream_t s) {
-  typedef SmemPlan<BN, STAGES> SP;
+  typedef SmemPlan<BN, STAGES, false, OUT_F32> SP;
   static bool configured = false;
   if (!configured) {
-    LBC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    LBC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, false, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  SP::TOTAL));
     configured = true;
   }
   int tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_kernel<BN, STAGES, false><<<grid, 192, SP::TOTAL, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO, p);
-  LBC_LAUNCHED((BN == 64 ? "conv_gemm_kernel<64>" : BN == 128 ? "conv_gemm_kernel<128>" : "conv_gemm_kernel<256>"));
+  conv_gemm_kernel<BN, STAGES, false, OUT_F32><<<grid, 192, SP::TOTAL, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO, p);
+  if (OUT_F32)
+    LBC_LAUNCHED((BN == 64 ? "conv_gemm_kernel<64,f32>" : BN == 128 ? "conv_gemm_kernel<128,f32>" : "conv_gemm_kernel<256,f32>"));
+  else
+    LBC_LAUNCHED((BN == 64 ? "conv_gemm_kernel<64>" : BN == 128 ? "conv_gemm_kernel<128>" : "conv_gemm_kernel<256>"));
   LBC_CUDA(cudaGetLastError());
 }
 // CTA-pair variant: clusters of 2 (one TPC), persistent over ceil(tiles_m/2) * n_tiles_n pair tiles
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool OUT_F32 = false>
 static void launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, const CUtensorMap& mO, const ConvGemmParams& p,
                              lbc_stream_t s) {
-  typedef SmemPlan<BN, STAGES, true> SP;
+  typedef SmemPlan<BN, STAGES, true, OUT_F32> SP;
   static_assert(SP::TOTAL <= 232448, "smem plan of the CTA-pair kernel exceeds 227 KB");
-  auto kern = conv_gemm_kernel<BN, STAGES, true>;
+  auto kern = conv_gemm_kernel<BN, STAGES, true, OUT_F32>;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
@@ -1234,7 +1269,10 @@ static void launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, c
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
   cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
   LBC_CUDA(cudaLaunchKernelEx(&cfg, kern, mA[0], mA[1], mA[2], mA[3], mBhalf, mO, p));
-  LBC_LAUNCHED((BN == 128 ? "conv_gemm_kernel<128,pair>" : "conv_gemm_kernel<256,pair>"));
+  if (OUT_F32)
+    LBC_LAUNCHED((BN == 128 ? "conv_gemm_kernel<128,pair,f32>" : "conv_gemm_kernel<256,pair,f32>"));
+  else
+    LBC_LAUNCHED((BN == 128 ? "conv_gemm_kernel<128,pair>" : "conv_gemm_kernel<256,pair>"));
   LBC_CUDA(cudaGetLastError());
 }
 // kernel variants (LBC_PAIR overrides; tests toggle them through lbc_set_fast_kernels):
@@ -1248,19 +1286,50 @@ static int g_pair_mode = [] {
 void set_pair_mode(int mode) { g_pair_mode = mode; }
 int pair_mode() { return g_pair_mode; }
 
+// Operand / output format of one implicit GEMM.  Default = the bf16 training step.  fp32tc (parity-grade tensor-core
+// mode): operands are [hi | lo] 16-bit planes of fp32 tensors (3 MMAs per K block), the output is stored as fp32.
+struct GemmMode {
+  bool split = false;
+  bool out_f32 = false;
+  uint32_t fmt_a = 1, fmt_b = 1;   // UMMA operand formats: 1 = bf16, 0 = fp16
+  float out_scale = 1.0f;
+};
+static void apply_mode(ConvGemmParams& p, const GemmMode& m, int a_plane, int b_plane) {
+  p.split = m.split ? 1 : 0;
+  p.a_plane = a_plane;
+  p.b_plane = b_plane;
+  p.fmt_a = m.fmt_a;
+  p.fmt_b = m.fmt_b;
+  p.out_scale = m.out_scale;
+}
 // mB: weights [rows][K]; the box height is chosen here (BN rows, or BN/2 for the CTA-pair kernels)
 static void dispatch_gemm(int BN, const CUtensorMap* mA, const void* wbase, int64_t wK, int64_t wrows, const CUtensorMap& mO,
-                          const ConvGemmParams& p, lbc_stream_t s) {
+                          const ConvGemmParams& p, lbc_stream_t s, bool out_f32 = false) {
   const bool pair = (g_pair_mode & 1) && BN >= 128;
   if (pair) {
     CUtensorMap mB = make_map_2d(wbase, wK, wrows, BN / 2);
-    if (BN == 128)
+    if (out_f32) {
+      if (BN == 128)
+        launch_gemm_pair<128, 7, true>(mA, mB, mO, p, s);
+      else
+        launch_gemm_pair<256, 4, true>(mA, mB, mO, p, s);
+    } else if (BN == 128) {
       launch_gemm_pair<128, 7>(mA, mB, mO, p, s);
-    else
+    } else {
       launch_gemm_pair<256, 4>(mA, mB, mO, p, s);
+    }
     return;
   }
   CUtensorMap mB = make_map_2d(wbase, wK, wrows, BN);
+  if (out_f32) {
+    if (BN == 64)
+      launch_gemm<64, 6, true>(mA, mB, mO, p, s);
+    else if (BN == 128)
+      launch_gemm<128, 5, true>(mA, mB, mO, p, s);
+    else
+      launch_gemm<256, 3, true>(mA, mB, mO, p, s);
+    return;
+  }
   if (BN == 64)
     launch_gemm<64, 6>(mA, mB, mO, p, s);
   else if (BN == 128)
@@ -1449,29 +1518,33 @@ bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C
 }
 
 // y = conv(x, w):  x [B,H,W,Ci], packed weights [Co][K*K][Ci], y [B,OH,OW,Co]
-bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s,
-                   float* stat_partial, int* stat_rows) {
+// (split mode: x [B,H,W,2Ci] = hi | lo planes, weights [Co][K*K][2Ci] = per tap hi | lo, y fp32)
+static bool conv_fwd_impl(const ConvL& c, const void* x, const void* wpack, void* y, int B, const float* bias_co, bool relu,
+                          lbc_stream_t s, float* stat_partial, int* stat_rows, const GemmMode& m) {
   if (!supported(c)) return false;
-  if (c.K == 3 && c.stride == 1 && c.Ci == 64 && c.Co == 64 &&
-      try_conv3x3_c64(x, c.wp, y, B, c.H, c.W, false, bias_co, false, stat_partial, stat_rows, s))
+  if (!m.split && !m.out_f32 && c.K == 3 && c.stride == 1 && c.Ci == 64 && c.Co == 64 && !relu &&
+      try_conv3x3_c64((const bf16*)x, wpack, (bf16*)y, B, c.H, c.W, false, bias_co, false, stat_partial, stat_rows, s))
     return true;
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   if (!tile_geometry(c.OH, c.OW, B, p)) return false;
   const int BN = pick_bn(c.Co, p.tiles_w * p.tiles_h * p.tiles_n);
+  const int CA = m.split ? 2 * c.Ci : c.Ci;   // channels of the stored x tensor / of one tap slab of the weights
   p.n_tiles_n = c.Co / BN;
   p.num_taps = c.K * c.K;
   p.k_chunks = c.Ci / 64;
-  p.bias = bias_co;   // per-output-channel constant added before the bf16 rounding (centring shift, see lbc_net.cu)
-  p.stat_partial = stat_partial;
+  p.bias = bias_co;   // per-output-channel constant added before the rounding (centring shift, see lbc_net.cu)
+  p.relu = relu ? 1 : 0;
+  p.stat_partial = m.out_f32 ? nullptr : stat_partial;
   p.stat_C = c.Co;
   p.valid_n = B;
-  if (stat_rows) *stat_rows = p.tiles_w * p.tiles_h * p.tiles_n;
+  apply_mode(p, m, c.Ci, c.Ci);
+  if (stat_rows) *stat_rows = m.out_f32 ? 0 : p.tiles_w * p.tiles_h * p.tiles_n;
   CUtensorMap mA[4];
   const int64_t eb = 2;
+  const bf16* xb = (const bf16*)x;
   if (c.stride == 1) {
-    mA[0] = make_map_4d(x, c.Ci, c.W, c.H, B, c.Ci * eb, (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH,
-                        p.TN);
+    mA[0] = make_map_4d(xb, CA, c.W, c.H, B, CA * eb, (int64_t)c.W * CA * eb, (int64_t)c.H * c.W * CA * eb, p.TW, p.TH, p.TN);
     mA[1] = mA[2] = mA[3] = mA[0];
     for (int kh = 0; kh < c.K; ++kh)
       for (int kw = 0; kw < c.K; ++kw) {
@@ -1479,13 +1552,13 @@ bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* b
         p.tap_dh[t] = kh - c.pad;
         p.tap_dw[t] = kw - c.pad;
         p.tap_map[t] = 0;
-        p.tap_koff[t] = t * c.Ci;
+        p.tap_koff[t] = t * CA;
       }
   } else {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
-        mA[a * 2 + b] = make_map_4d(x + ((int64_t)a * c.W + b) * c.Ci, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb,
-                                    2 * (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
+        mA[a * 2 + b] = make_map_4d(xb + ((int64_t)a * c.W + b) * CA, CA, c.W / 2, c.H / 2, B, 2 * CA * eb,
+                                    2 * (int64_t)c.W * CA * eb, (int64_t)c.H * c.W * CA * eb, p.TW, p.TH, p.TN);
     for (int kh = 0; kh < c.K; ++kh)
       for (int kw = 0; kw < c.K; ++kw) {
         int t = kh * c.K + kw;
@@ -1494,42 +1567,53 @@ bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* b
         p.tap_dh[t] = (th - a) / 2;
         p.tap_dw[t] = (tw - b) / 2;
         p.tap_map[t] = a * 2 + b;
-        p.tap_koff[t] = t * c.Ci;
+        p.tap_koff[t] = t * CA;
       }
   }
-  CUtensorMap mO = make_map_4d(y, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb, (int64_t)c.OH * c.OW * c.Co * eb,
-                               p.TW, p.TH, p.TN);
-  dispatch_gemm(BN, mA, c.wp, (int64_t)c.K * c.K * c.Ci, c.Co, mO, p, s);
+  const int64_t eo = m.out_f32 ? 4 : 2;
+  CUtensorMap mO = make_map_4d(y, c.Co, c.OW, c.OH, B, c.Co * eo, (int64_t)c.OW * c.Co * eo, (int64_t)c.OH * c.OW * c.Co * eo,
+                               p.TW, p.TH, p.TN, m.out_f32);
+  dispatch_gemm(BN, mA, wpack, (int64_t)c.K * c.K * CA, c.Co, mO, p, s, m.out_f32);
   return true;
+}
+bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s,
+                   float* stat_partial, int* stat_rows) {
+  return conv_fwd_impl(c, x, c.wp, y, B, bias_co, false, s, stat_partial, stat_rows, GemmMode());
 }
 
 // dx = conv_dgrad(dy, w):  dy [B,OH,OW,Co], transposed pack wt [Ci][K*K][Co], dx [B,H,W,Ci] (+bias[ci]) (relu)
 // stride 1: one GEMM with mirrored taps; stride 2: one GEMM per output parity (also ConvTranspose2d forward).
-static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu,
-                            const bf16* dy_ds, lbc_stream_t s);
+// (split mode: dy [B,OH,OW,2Co] hi | lo, wt [Ci][K*K][2Co] per tap hi | lo, wcomb [Ci][2][2Co], dx fp32)
+static bool conv_dgrad_impl(const ConvL& c, const void* dy, const void* wt, const void* wcomb, void* dx, int B,
+                            const float* bias_ci, bool relu, const void* dy_ds, lbc_stream_t s, const GemmMode& m);
 bool conv_dgrad_bf16(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu, lbc_stream_t s) {
-  return conv_dgrad_impl(c, dy, dx, B, bias_ci, relu, nullptr, s);
+  return conv_dgrad_impl(c, dy, c.wpt, c.wcomb, dx, B, bias_ci, relu, nullptr, s, GemmMode());
 }
 // gradient wrt the input of a residual block's entry: dgrad(3x3/s2 conv1)(dy1) + dgrad(1x1/s2 downsample)(dy_ds).
 // The 1x1/s2 gradient only touches the (even,even) parity, where it is one more K-slab of the same GEMM
 // (A = dy_ds, B = the [Ci][Co] downsample weights stored behind conv1's centre tap in c1.wcomb).
 bool conv_dgrad_ds_bf16(const ConvL& c1, const bf16* dy1, const bf16* dy_ds, bf16* dx, int B, lbc_stream_t s) {
   if (!c1.wcomb || c1.stride != 2 || c1.K != 3) return false;
-  return conv_dgrad_impl(c1, dy1, dx, B, nullptr, false, dy_ds, s);
+  return conv_dgrad_impl(c1, dy1, c1.wpt, c1.wcomb, dx, B, nullptr, false, dy_ds, s, GemmMode());
 }
-static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, const float* bias_ci, bool relu,
-                            const bf16* dy_ds, lbc_stream_t s) {
-  if (!supported(c) || !c.wpt) return false;
+static bool conv_dgrad_impl(const ConvL& c, const void* dy_v, const void* wt, const void* wcomb, void* dx_v, int B,
+                            const float* bias_ci, bool relu, const void* dy_ds_v, lbc_stream_t s, const GemmMode& m) {
+  if (!supported(c) || !wt) return false;
   if (c.K == 1) return false;  // 1x1/s2 downsample gradient scatters into one parity only: handled by the caller
+  const bf16* dy = (const bf16*)dy_v;
+  const bf16* dy_ds = (const bf16*)dy_ds_v;
   const int64_t eb = 2;
+  const int64_t eo = m.out_f32 ? 4 : 2;
+  uint8_t* dx = (uint8_t*)dx_v;
+  const int CA = m.split ? 2 * c.Co : c.Co;   // channels of the stored dy tensor / of one tap slab of wt
   ConvGemmParams g0;
   memset(&g0, 0, sizeof(g0));
   if (!tile_geometry(c.stride == 1 ? c.H : c.OH, c.stride == 1 ? c.W : c.OW, B, g0)) return false;
   const int BN = pick_bn(c.Ci, g0.tiles_w * g0.tiles_h * g0.tiles_n);
-  const int64_t wtK = (int64_t)c.K * c.K * c.Co;
+  const int64_t wtK = (int64_t)c.K * c.K * CA;
   if (c.stride == 1) {
-    if (c.K == 3 && c.Ci == 64 && c.Co == 64 && !dy_ds &&
-        try_conv3x3_c64(dy, c.wpt, dx, B, c.H, c.W, true, bias_ci, relu, nullptr, nullptr, s))
+    if (!m.split && !m.out_f32 && c.K == 3 && c.Ci == 64 && c.Co == 64 && !dy_ds &&
+        try_conv3x3_c64(dy, wt, (bf16*)dx_v, B, c.H, c.W, true, bias_ci, relu, nullptr, nullptr, s))
       return true;
     ConvGemmParams p;
     memset(&p, 0, sizeof(p));
@@ -1539,9 +1623,9 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
     p.k_chunks = c.Co / 64;
     p.bias = bias_ci;
     p.relu = relu ? 1 : 0;
+    apply_mode(p, m, c.Co, c.Co);
     CUtensorMap mA[4];
-    mA[0] = make_map_4d(dy, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb, (int64_t)c.OH * c.OW * c.Co * eb, p.TW,
-                        p.TH, p.TN);
+    mA[0] = make_map_4d(dy, CA, c.OW, c.OH, B, CA * eb, (int64_t)c.OW * CA * eb, (int64_t)c.OH * c.OW * CA * eb, p.TW, p.TH, p.TN);
     mA[1] = mA[2] = mA[3] = mA[0];
     for (int kh = 0; kh < c.K; ++kh)
       for (int kw = 0; kw < c.K; ++kw) {
@@ -1549,11 +1633,11 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
         p.tap_dh[t] = c.pad - kh;
         p.tap_dw[t] = c.pad - kw;
         p.tap_map[t] = 0;
-        p.tap_koff[t] = t * c.Co;
+        p.tap_koff[t] = t * CA;
       }
-    CUtensorMap mO = make_map_4d(dx, c.Ci, c.W, c.H, B, c.Ci * eb, (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb,
-                                 p.TW, p.TH, p.TN);
-    dispatch_gemm(BN, mA, c.wpt, wtK, c.Ci, mO, p, s);
+    CUtensorMap mO = make_map_4d(dx, c.Ci, c.W, c.H, B, c.Ci * eo, (int64_t)c.W * c.Ci * eo, (int64_t)c.H * c.W * c.Ci * eo,
+                                 p.TW, p.TH, p.TN, m.out_f32);
+    dispatch_gemm(BN, mA, wt, wtK, c.Ci, mO, p, s, m.out_f32);
     return true;
   }
   // stride 2: dx[n, 2i+a, 2j+b, :] = sum over taps kh with (a + pad - kh) even: dy[n, i + (a+pad-kh)/2, ...]
@@ -1564,13 +1648,14 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
   base.k_chunks = c.Co / 64;
   base.bias = bias_ci;
   base.relu = relu ? 1 : 0;
+  apply_mode(base, m, c.Co, c.Co);
   CUtensorMap mA[4];
-  mA[0] = make_map_4d(dy, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb, (int64_t)c.OH * c.OW * c.Co * eb, base.TW,
-                      base.TH, base.TN);
+  mA[0] = make_map_4d(dy, CA, c.OW, c.OH, B, CA * eb, (int64_t)c.OW * CA * eb, (int64_t)c.OH * c.OW * CA * eb, base.TW, base.TH,
+                      base.TN);
   mA[1] = mA[2] = mA[3] = mA[0];
   if (dy_ds)
-    mA[1] = make_map_4d(dy_ds, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb, (int64_t)c.OH * c.OW * c.Co * eb,
-                        base.TW, base.TH, base.TN);
+    mA[1] = make_map_4d(dy_ds, CA, c.OW, c.OH, B, CA * eb, (int64_t)c.OW * CA * eb, (int64_t)c.OH * c.OW * CA * eb, base.TW,
+                        base.TH, base.TN);
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       ConvGemmParams p = base;
@@ -1582,11 +1667,11 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
         p.tap_koff[0] = 0;
         p.tap_dh[1] = p.tap_dw[1] = 0;
         p.tap_map[1] = 1;
-        p.tap_koff[1] = c.Co;
+        p.tap_koff[1] = CA;
         p.num_taps = 2;
-        CUtensorMap mO = make_map_4d(dx, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb, 2 * (int64_t)c.W * c.Ci * eb,
-                                     (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
-        dispatch_gemm(BN, mA, c.wcomb, (int64_t)2 * c.Co, c.Ci, mO, p, s);
+        CUtensorMap mO = make_map_4d(dx, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eo, 2 * (int64_t)c.W * c.Ci * eo,
+                                     (int64_t)c.H * c.W * c.Ci * eo, p.TW, p.TH, p.TN, m.out_f32);
+        dispatch_gemm(BN, mA, wcomb, (int64_t)2 * CA, c.Ci, mO, p, s, m.out_f32);
         continue;
       }
       for (int kh = 0; kh < c.K; ++kh) {
@@ -1596,14 +1681,14 @@ static bool conv_dgrad_impl(const ConvL& c, const bf16* dy, bf16* dx, int B, con
           p.tap_dh[nt] = (a + c.pad - kh) / 2;
           p.tap_dw[nt] = (b + c.pad - kw) / 2;
           p.tap_map[nt] = 0;
-          p.tap_koff[nt] = (kh * c.K + kw) * c.Co;
+          p.tap_koff[nt] = (kh * c.K + kw) * CA;
           ++nt;
         }
       }
       p.num_taps = nt;
-      CUtensorMap mO = make_map_4d(dx + ((int64_t)a * c.W + b) * c.Ci, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb,
-                                   2 * (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
-      dispatch_gemm(BN, mA, c.wpt, wtK, c.Ci, mO, p, s);
+      CUtensorMap mO = make_map_4d(dx + ((int64_t)a * c.W + b) * c.Ci * eo, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eo,
+                                   2 * (int64_t)c.W * c.Ci * eo, (int64_t)c.H * c.W * c.Ci * eo, p.TW, p.TH, p.TN, m.out_f32);
+      dispatch_gemm(BN, mA, wt, wtK, c.Ci, mO, p, s, m.out_f32);
     }
   return true;
 }
@@ -1628,6 +1713,10 @@ struct WgradParams {
   // swap mode (Co == 64): M = two (tap, 64-channel ci chunk) combos of x, N = the 64 output channels of dy, so the
   // 128-row MMA is full instead of half zero padding
   int swap, num_combos, chunks_per_tap;
+  // split-precision mode: dy = [hi | lo] planes of dy_plane channels, x = [hi | lo] planes of x_plane channels; the K
+  // (pixel) loop runs 3 x k_tiles_real tiles: (dy hi, x hi), (dy hi, x lo), (dy lo, x hi).  k_tiles = 3 * k_tiles_real.
+  int split, k_tiles_real, dy_plane, x_plane;
+  uint32_t fmt_dy, fmt_x;   // UMMA formats (0 = fp16, 1 = bf16)
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -1720,7 +1809,10 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
       const int cA = p.swap ? (combo0 % p.chunks_per_tap) * 64 : 0, cB = p.swap ? (combo1 % p.chunks_per_tap) * 64 : 0;
       int stage = 0;
       uint32_t phase = 0;
-      for (int kt = kt0; kt < kt1; ++kt) {
+      for (int kt2 = kt0; kt2 < kt1; ++kt2) {
+        const int term = p.split ? kt2 / p.k_tiles_real : 0;
+        const int kt = kt2 - term * p.k_tiles_real;
+        const int dyo = term == 2 ? p.dy_plane : 0, xo = term == 1 ? p.x_plane : 0;
         const int w0 = (kt % p.tiles_w) * p.TW;
         const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -1728,20 +1820,20 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
         uint8_t* sa = smem + stage * SP::STAGE_BYTES;
         mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
         if (p.swap) {   // A = two x boxes (M = 2 x 64 input channels), B = dy (N = 64 output channels); BNW == 64
-          tma_load_4d(mx, sa, &full[stage], cA, w0 + dw, h0 + dh, n0);
-          tma_load_4d(mx2, sa + A_BYTES, &full[stage], cB, w0 + dw2, h0 + dh2, n0);
-          tma_load_4d(&mDY, sa + SP::A_ST, &full[stage], 0, w0, h0, n0);
+          tma_load_4d(mx, sa, &full[stage], cA + xo, w0 + dw, h0 + dh, n0);
+          tma_load_4d(mx2, sa + A_BYTES, &full[stage], cB + xo, w0 + dw2, h0 + dh2, n0);
+          tma_load_4d(&mDY, sa + SP::A_ST, &full[stage], dyo, w0, h0, n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
           continue;
         }
-        tma_load_4d(&mDY, sa, &full[stage], co_tile * 128, w0, h0, n0);
-        tma_load_4d(&mDY, sa + A_BYTES, &full[stage], co_tile * 128 + 64, w0, h0, n0);  // OOB -> zeros when Co == 64
+        tma_load_4d(&mDY, sa, &full[stage], co_tile * 128 + dyo, w0, h0, n0);
+        tma_load_4d(&mDY, sa + A_BYTES, &full[stage], co_tile * 128 + 64 + dyo, w0, h0, n0);  // OOB -> zeros when Co == 64
 #pragma unroll
         for (int b = 0; b < BNW / 64; ++b)
-          tma_load_4d(mx, sa + SP::A_ST + b * A_BYTES, &full[stage], ci_tile * BNW + b * 64, w0 + dw, h0 + dh, n0);
+          tma_load_4d(mx, sa + SP::A_ST + b * A_BYTES, &full[stage], ci_tile * BNW + b * 64 + xo, w0 + dw, h0 + dh, n0);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -1749,8 +1841,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // D=f32, A=B=bf16, both MN-major (bits 15,16), N=BNW, M=128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BNW >> 3) << 17) |
+    // D=f32, A / B = bf16 or fp16, both MN-major (bits 15,16), N=BNW, M=128   (swap mode: A = x, B = dy)
+    const uint32_t fa = p.swap ? p.fmt_x : p.fmt_dy, fb = p.swap ? p.fmt_dy : p.fmt_x;
+    const uint32_t idesc = (1u << 4) | (fa << 7) | (fb << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BNW >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
@@ -1826,6 +1919,8 @@ struct Wgrad3Params {
   int tap_dh[9], tap_dw[9], tap_map[9];
   int Co, Ci;
   float* out;  // [splits][Co][9][Ci] fp32 partials
+  int split, k_tiles_real, dy_plane, x_plane;   // split-precision mode, as in WgradParams
+  uint32_t fmt_dy, fmt_x;
 };
 constexpr int W3_BOX = 64 * 128;   // 64 pixels x 64 channels bf16
 
@@ -1901,7 +1996,10 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kt = kt0; kt < kt1; ++kt) {
+      for (int kt2 = kt0; kt2 < kt1; ++kt2) {
+        const int term = p.split ? kt2 / p.k_tiles_real : 0;
+        const int kt = kt2 - term * p.k_tiles_real;
+        const int dyo = term == 2 ? p.dy_plane : 0, xo = term == 1 ? p.x_plane : 0;
         const int w0 = (kt % p.tiles_w) * p.TW;
         const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -1910,28 +2008,28 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
         if constexpr (PAIR) {
           if (crank == 0) mbar_expect_tx(&full[stage], 2 * SP::STAGE_BYTES);
           const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-          tma_load_4d_pair(&mDY, sa, lead_full, co_tile * 128, w0, h0, n0);
-          tma_load_4d_pair(&mDY, sa + W3_BOX, lead_full, co_tile * 128 + 64, w0, h0, n0);
+          tma_load_4d_pair(&mDY, sa, lead_full, co_tile * 128 + dyo, w0, h0, n0);
+          tma_load_4d_pair(&mDY, sa + W3_BOX, lead_full, co_tile * 128 + 64 + dyo, w0, h0, n0);
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
             const int tap = krow * 3 + t;
             const int mid = p.tap_map[tap];
             const CUtensorMap* mx = mid == 0 ? &mX0 : (mid == 1 ? &mX1 : (mid == 2 ? &mX2 : &mX3));
-            tma_load_4d_pair(mx, sa + SP::A_ST + t * SP::B_TAP, lead_full, ci_tile * 128 + (int)crank * 64, w0 + p.tap_dw[tap],
+            tma_load_4d_pair(mx, sa + SP::A_ST + t * SP::B_TAP, lead_full, ci_tile * 128 + (int)crank * 64 + xo, w0 + p.tap_dw[tap],
                              h0 + p.tap_dh[tap], n0);
           }
         } else {
           mbar_expect_tx(&full[stage], SP::STAGE_BYTES);
-          tma_load_4d(&mDY, sa, &full[stage], co_tile * 128, w0, h0, n0);
-          tma_load_4d(&mDY, sa + W3_BOX, &full[stage], co_tile * 128 + 64, w0, h0, n0);
+          tma_load_4d(&mDY, sa, &full[stage], co_tile * 128 + dyo, w0, h0, n0);
+          tma_load_4d(&mDY, sa + W3_BOX, &full[stage], co_tile * 128 + 64 + dyo, w0, h0, n0);
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
             const int tap = krow * 3 + t;
             const int mid = p.tap_map[tap];
             const CUtensorMap* mx = mid == 0 ? &mX0 : (mid == 1 ? &mX1 : (mid == 2 ? &mX2 : &mX3));
             uint8_t* sb = sa + SP::A_ST + t * SP::B_TAP;
-            tma_load_4d(mx, sb, &full[stage], ci_tile * 128, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-            tma_load_4d(mx, sb + W3_BOX, &full[stage], ci_tile * 128 + 64, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+            tma_load_4d(mx, sb, &full[stage], ci_tile * 128 + xo, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+            tma_load_4d(mx, sb + W3_BOX, &full[stage], ci_tile * 128 + 64 + xo, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
           }
         }
         if (++stage == STAGES) {
@@ -1941,8 +2039,8 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // D=f32, A=B=bf16, both MN-major (bits 15,16), N=128, M=128 (pair: 256 over the two CTAs)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
+    // D=f32, A = dy, B = x (bf16 or fp16), both MN-major (bits 15,16), N=128, M=128 (pair: 256 over the two CTAs)
+    const uint32_t idesc = (1u << 4) | (p.fmt_dy << 7) | (p.fmt_x << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
                            ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
@@ -2159,9 +2257,11 @@ static int wgrad3_pair_slots() {
   }();
   return slots;
 }
-static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch, lbc_stream_t s) {
+static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch, lbc_stream_t s,
+                       const GemmMode& m) {
   (void)scratch;
   if (!(g_pair_mode & 2)) return false;
+  const int CX = m.split ? 2 * c.Ci : c.Ci, CY = m.split ? 2 * c.Co : c.Co;   // channels of the stored x / dy tensors
   const bool pair = (g_pair_mode & 4) && (c.Co % 256 == 0);
   if (c.K != 3 || c.pad != 1 || (c.Co % 128) || (c.Ci % 128)) return false;
   Wgrad3Params p;
@@ -2174,7 +2274,13 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
   p.tiles_w = c.OW / p.TW;
   p.tiles_h = c.OH / p.TH;
   p.tiles_n = (B + p.TN - 1) / p.TN;
-  p.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.k_tiles_real = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.k_tiles = (m.split ? 3 : 1) * p.k_tiles_real;
+  p.split = m.split ? 1 : 0;
+  p.dy_plane = c.Co;
+  p.x_plane = c.Ci;
+  p.fmt_dy = m.fmt_a;
+  p.fmt_x = m.fmt_b;
   p.co_tiles = c.Co / 128;
   p.ci_tiles = c.Ci / 128;
   p.Co = c.Co;
@@ -2198,12 +2304,11 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
   p.k_per_split = (p.k_tiles + best_splits - 1) / best_splits;
   p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
   const int64_t eb = 2;
-  CUtensorMap mDY = make_map_4d(dy, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb,
-                                (int64_t)c.OH * c.OW * c.Co * eb, p.TW, p.TH, p.TN);
+  CUtensorMap mDY = make_map_4d(dy, CY, c.OW, c.OH, B, CY * eb, (int64_t)c.OW * CY * eb, (int64_t)c.OH * c.OW * CY * eb, p.TW,
+                                p.TH, p.TN);
   CUtensorMap mX[4];
   if (c.stride == 1) {
-    mX[0] = make_map_4d(x, c.Ci, c.W, c.H, B, c.Ci * eb, (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH,
-                        p.TN);
+    mX[0] = make_map_4d(x, CX, c.W, c.H, B, CX * eb, (int64_t)c.W * CX * eb, (int64_t)c.H * c.W * CX * eb, p.TW, p.TH, p.TN);
     mX[1] = mX[2] = mX[3] = mX[0];
     for (int t = 0; t < 9; ++t) {
       p.tap_dh[t] = t / 3 - c.pad;
@@ -2213,8 +2318,8 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
   } else {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
-        mX[a * 2 + b] = make_map_4d(x + ((int64_t)a * c.W + b) * c.Ci, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb,
-                                    2 * (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
+        mX[a * 2 + b] = make_map_4d(x + ((int64_t)a * c.W + b) * CX, CX, c.W / 2, c.H / 2, B, 2 * CX * eb,
+                                    2 * (int64_t)c.W * CX * eb, (int64_t)c.H * c.W * CX * eb, p.TW, p.TH, p.TN);
     for (int t = 0; t < 9; ++t) {
       int th = t / 3 - c.pad, tw = t % 3 - c.pad;
       int a = ((th % 2) + 2) % 2, b = ((tw % 2) + 2) % 2;
@@ -2245,13 +2350,16 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
 }
 
 // x [B,H,W,Ci], dy [B,OH,OW,Co] -> dw_ref fp32 [Co][Ci][K][K]; scratch >= Co*K*K*Ci floats
-bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch,
-                     int64_t scratch_floats, lbc_stream_t s) {
+// (split mode: x [B,H,W,2Ci], dy [B,OH,OW,2Co] as hi | lo planes; fmt_a = format of dy, fmt_b = format of x)
+static bool conv_wgrad_impl(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch,
+                            int64_t scratch_floats, lbc_stream_t s, const GemmMode& m) {
   if (!supported(c)) return false;
+  if (m.split && c.Co != 64 && (c.Co % 128)) return false;   // the 128-row dy tile must not run into the lo plane
   const int KK = c.K * c.K;
   const int64_t wsize = (int64_t)c.Co * KK * c.Ci;
   if (wsize > scratch_floats) return false;
-  if (try_wgrad3(c, x, dy, dw_ref, B, scratch, s)) return true;
+  if (try_wgrad3(c, x, dy, dw_ref, B, scratch, s, m)) return true;
+  const int CX = m.split ? 2 * c.Ci : c.Ci, CY = m.split ? 2 * c.Co : c.Co;
   WgradParams p;
   memset(&p, 0, sizeof(p));
   ConvGemmParams g;
@@ -2262,7 +2370,13 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
   p.tiles_w = g.tiles_w;
   p.tiles_h = g.tiles_h;
   p.tiles_n = g.tiles_n;
-  p.k_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  p.k_tiles_real = g.tiles_w * g.tiles_h * g.tiles_n;
+  p.k_tiles = (m.split ? 3 : 1) * p.k_tiles_real;
+  p.split = m.split ? 1 : 0;
+  p.dy_plane = c.Co;
+  p.x_plane = c.Ci;
+  p.fmt_dy = m.fmt_a;
+  p.fmt_x = m.fmt_b;
   p.swap = (c.Co == 64) ? 1 : 0;
   const int BNW = p.swap ? 64 : ((c.Ci % 128 == 0) ? 128 : 64);
   p.co_tiles = (c.Co + 127) / 128;
@@ -2293,12 +2407,11 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
   p.k_per_split = (p.k_tiles + best_splits - 1) / best_splits;
   p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
   const int64_t eb = 2;
-  CUtensorMap mDY = make_map_4d(dy, c.Co, c.OW, c.OH, B, c.Co * eb, (int64_t)c.OW * c.Co * eb,
-                                (int64_t)c.OH * c.OW * c.Co * eb, p.TW, p.TH, p.TN);
+  CUtensorMap mDY = make_map_4d(dy, CY, c.OW, c.OH, B, CY * eb, (int64_t)c.OW * CY * eb, (int64_t)c.OH * c.OW * CY * eb, p.TW,
+                                p.TH, p.TN);
   CUtensorMap mX[4];
   if (c.stride == 1) {
-    mX[0] = make_map_4d(x, c.Ci, c.W, c.H, B, c.Ci * eb, (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH,
-                        p.TN);
+    mX[0] = make_map_4d(x, CX, c.W, c.H, B, CX * eb, (int64_t)c.W * CX * eb, (int64_t)c.H * c.W * CX * eb, p.TW, p.TH, p.TN);
     mX[1] = mX[2] = mX[3] = mX[0];
     for (int kh = 0; kh < c.K; ++kh)
       for (int kw = 0; kw < c.K; ++kw) {
@@ -2310,8 +2423,8 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
   } else {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
-        mX[a * 2 + b] = make_map_4d(x + ((int64_t)a * c.W + b) * c.Ci, c.Ci, c.W / 2, c.H / 2, B, 2 * c.Ci * eb,
-                                    2 * (int64_t)c.W * c.Ci * eb, (int64_t)c.H * c.W * c.Ci * eb, p.TW, p.TH, p.TN);
+        mX[a * 2 + b] = make_map_4d(x + ((int64_t)a * c.W + b) * CX, CX, c.W / 2, c.H / 2, B, 2 * CX * eb,
+                                    2 * (int64_t)c.W * CX * eb, (int64_t)c.H * c.W * CX * eb, p.TW, p.TH, p.TN);
     for (int kh = 0; kh < c.K; ++kh)
       for (int kw = 0; kw < c.K; ++kw) {
         int t = kh * c.K + kw;
@@ -2333,6 +2446,137 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
   LBC_CUDA(cudaGetLastError());
   return true;
 }
+bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch,
+                     int64_t scratch_floats, lbc_stream_t s) {
+  return conv_wgrad_impl(c, x, dy, dw_ref, B, scratch, scratch_floats, s, GemmMode());
+}
+
+// =============================================================================================================
+// fp32tc: split-precision front ends
+// =============================================================================================================
+template <bool F16>
+__global__ void __launch_bounds__(256) split16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, int64_t rows,
+                                                      int C8, float scale) {
+  const int64_t n = rows * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C8;
+    const int g = (int)(i - row * C8);
+    const float4 a = __ldg(src + i * 2), b = __ldg(src + i * 2 + 1);
+    const float v[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (F16) {
+        const float c0 = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), c1 = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
+        const __half h0 = __float2half_rn(c0), h1 = __float2half_rn(c1);
+        const __half l0 = __float2half_rn(c0 - __half2float(h0)), l1 = __float2half_rn(c1 - __half2float(h1));
+        hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      } else {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+        hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+    }
+    dst[row * 2 * C8 + g] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    dst[row * 2 * C8 + C8 + g] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+bool tc_split(const float* src, void* dst16, int64_t rows, int C, int fmt, float scale, lbc_stream_t s) {
+  if (C % 8) return false;
+  const int64_t n = rows * (C / 8);
+  if (n <= 0) return true;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (fmt == TC_F16)
+    split16_kernel<true><<<(unsigned)blocks, 256, 0, s>>>((const float4*)src, (uint4*)dst16, rows, C / 8, scale);
+  else
+    split16_kernel<false><<<(unsigned)blocks, 256, 0, s>>>((const float4*)src, (uint4*)dst16, rows, C / 8, scale);
+  LBC_LAUNCHED(fmt == TC_F16 ? "split16_kernel<f16>" : "split16_kernel<bf16>");
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+// one thread per (pixel, k): the 7x7/s2 window element k = (kh*7 + kw)*C + c of the NHWC fp32 image, split into fp16 hi | lo
+__global__ void __launch_bounds__(256) tc_stem_im2col_kernel(const float* __restrict__ x0, __half* __restrict__ col, int64_t npix,
+                                                             int C, int H, int W, int OH, int OW, int Kp) {
+  const int64_t n = npix * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / Kp;
+    const int k = (int)(i - pix * Kp);
+    float v = 0.f;
+    if (k < 49 * C) {
+      const int tap = k / C, c = k - tap * C;
+      const int kh = tap / 7, kw = tap - kh * 7;
+      const int ow = (int)(pix % OW);
+      const int64_t t = pix / OW;
+      const int oh = (int)(t % OH);
+      const int64_t b = t / OH;
+      const int ih = oh * 2 - 3 + kh, iw = ow * 2 - 3 + kw;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x0 + ((b * H + ih) * W + iw) * C + c);
+    }
+    const float cv = fminf(fmaxf(v, -65504.f), 65504.f);
+    const __half h = __float2half_rn(cv);
+    col[pix * 2 * Kp + k] = h;
+    col[pix * 2 * Kp + Kp + k] = __float2half_rn(cv - __half2float(h));
+  }
+}
+bool tc_stem_im2col(const float* x0, void* col16, int B, int C, int H, int W, int OH, int OW, int Kp, lbc_stream_t s) {
+  const int64_t npix = (int64_t)B * OH * OW;
+  int64_t blocks = (npix * Kp + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  tc_stem_im2col_kernel<<<(unsigned)blocks, 256, 0, s>>>(x0, (__half*)col16, npix, C, H, W, OH, OW, Kp);
+  LBC_LAUNCHED("tc_stem_im2col_kernel");
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+static GemmMode tc_mode(int fmt_a, int fmt_b, float out_scale) {
+  GemmMode m;
+  m.split = true;
+  m.out_f32 = true;
+  m.fmt_a = (uint32_t)fmt_a;
+  m.fmt_b = (uint32_t)fmt_b;
+  m.out_scale = out_scale;
+  return m;
+}
+bool conv_fwd_tc(const ConvL& c, const float* x, const void* x16, float* y, int B, const float* bias_co, bool relu, int x_fmt,
+                 const TcWork& w, lbc_stream_t s) {
+  if (!enabled() || !supported(c) || !c.wp16) return false;
+  if (!x16) {
+    const int64_t rows = (int64_t)B * c.H * c.W;
+    if (rows * c.Ci * 4 > w.a_bytes) return false;
+    if (!tc_split(x, w.a16, rows, c.Ci, x_fmt, 1.0f, s)) return false;
+    x16 = w.a16;
+  }
+  return conv_fwd_impl(c, x16, c.wp16, y, B, bias_co, relu, s, nullptr, nullptr, tc_mode(x_fmt, TC_F16, 1.0f / kTcWeightScale));
+}
+bool conv_dgrad_tc(const ConvL& c, const float* dy, const float* dy_ds, float* dx, int B, const float* bias_ci, bool relu,
+                   int dy_fmt, const TcWork& w, lbc_stream_t s) {
+  if (!enabled() || !supported(c) || !c.wpt16 || c.K == 1) return false;
+  if (dy_ds && (!c.wcomb16 || c.stride != 2 || c.K != 3)) return false;
+  const int64_t rows = (int64_t)B * c.OH * c.OW;
+  if (rows * c.Co * 4 > w.a_bytes || (dy_ds && rows * c.Co * 4 > w.b_bytes)) return false;
+  if (!tc_split(dy, w.a16, rows, c.Co, dy_fmt, 1.0f, s)) return false;
+  if (dy_ds && !tc_split(dy_ds, w.b16, rows, c.Co, dy_fmt, 1.0f, s)) return false;
+  return conv_dgrad_impl(c, w.a16, c.wpt16, c.wcomb16, dx, B, bias_ci, relu, dy_ds ? w.b16 : nullptr, s,
+                         tc_mode(dy_fmt, TC_F16, 1.0f / kTcWeightScale));
+}
+bool conv_wgrad_tc(const ConvL& c, const float* x, const void* x16, const float* dy, float* dw_ref, int B, int x_fmt, int dy_fmt,
+                   float* scratch, int64_t scratch_floats, const TcWork& w, lbc_stream_t s) {
+  if (!enabled() || !supported(c)) return false;
+  const int64_t rx = (int64_t)B * c.H * c.W, ry = (int64_t)B * c.OH * c.OW;
+  if (ry * c.Co * 4 > w.b_bytes) return false;
+  if (!x16) {
+    if (rx * c.Ci * 4 > w.a_bytes) return false;
+    if (!tc_split(x, w.a16, rx, c.Ci, x_fmt, 1.0f, s)) return false;
+    x16 = w.a16;
+  }
+  if (!tc_split(dy, w.b16, ry, c.Co, dy_fmt, 1.0f, s)) return false;
+  return conv_wgrad_impl(c, (const bf16*)x16, (const bf16*)w.b16, dw_ref, B, scratch, scratch_floats, s, tc_mode(dy_fmt, x_fmt, 1.0f));
+}
 
 #else   // LBC_HOST_EMU: no tensor cores on the host; the executor runs the correctness-first kernels
 bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, const float*, lbc_stream_t, float*, int*) { return false; }
@@ -2344,6 +2588,11 @@ void set_pair_mode(int) {}
 int pair_mode() { return 0; }
 bool stem_conv_bf16(const bf16*, const bf16*, bf16*, int, int, int, int, int, const float*, float*, int*, lbc_stream_t) { return false; }
 bool stem_wgrad_bf16(const bf16*, const bf16*, float*, int, int, int, int, int, int, lbc_stream_t) { return false; }
+bool tc_split(const float*, void*, int64_t, int, int, float, lbc_stream_t) { return false; }
+bool conv_fwd_tc(const ConvL&, const float*, const void*, float*, int, const float*, bool, int, const TcWork&, lbc_stream_t) { return false; }
+bool conv_dgrad_tc(const ConvL&, const float*, const float*, float*, int, const float*, bool, int, const TcWork&, lbc_stream_t) { return false; }
+bool conv_wgrad_tc(const ConvL&, const float*, const void*, const float*, float*, int, int, int, float*, int64_t, const TcWork&, lbc_stream_t) { return false; }
+bool tc_stem_im2col(const float*, void*, int, int, int, int, int, int, int, lbc_stream_t) { return false; }
 #endif
 
 }  // namespace fast

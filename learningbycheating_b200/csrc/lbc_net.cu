@@ -3,6 +3,7 @@
 // Reference call stack being replaced: SURVEY.md 3.3 (image.py:64-89, resnet.py:148-159,38-54).
 #include "lbc_net.h"
 
+#include <algorithm>
 #include <type_traits>
 
 #include "lbc_fast.h"
@@ -78,6 +79,10 @@ class Net : public NetBase {
   std::vector<BNL*> conv_bns;     // BNs fed directly by a trunk convolution
   float* head_fold = nullptr;  // folded BN+1x1 map A[20][64], b'[20]; coef c0/c1 [128]
   bool stem_pool_fused = false;
+  // PREC_F32TC (T = float): convolutions on the tensor cores with split-precision operands
+  bool tc = false;
+  fast::TcWork tcw;
+  bool stem_tc_used = false;
   size_t total_bytes = 0;
   int cur_B = 0;
   bool cur_train = false;
@@ -140,6 +145,10 @@ class Net : public NetBase {
     c.w_off = add_param(name + ".weight", {Co, Ci, K, K});
     c.wp = alloc<T>((int64_t)Co * K * K * Ci);
     c.wpt = alloc<T>((int64_t)Co * K * K * Ci);
+    if (tc) {   // [hi | lo] fp16 planes: 2 x 2 bytes per element
+      c.wp16 = alloc<float>((int64_t)Co * K * K * Ci);
+      c.wpt16 = alloc<float>((int64_t)Co * K * K * Ci);
+    }
   }
   // nn.ConvTranspose2d(Cin, Cout, 3, 2, 1, 1): as the input-gradient of a 3x3/s2/p1 conv whose
   // conv-role Co = deconv Cin, Ci = deconv Cout; conv-role input is the (2h x 2w) deconv output.
@@ -158,12 +167,18 @@ class Net : public NetBase {
     c.b_off = add_param(name + ".bias", {Cout});
     c.wp = alloc<T>((int64_t)Cin * 9 * Cout);
     c.wpt = alloc<T>((int64_t)Cin * 9 * Cout);
+    if (tc) {
+      c.wp16 = alloc<float>((int64_t)Cin * 9 * Cout);
+      c.wpt16 = alloc<float>((int64_t)Cin * 9 * Cout);
+    }
   }
 
   Net(NetKind k, Precision p, int maxB) {
     kind = k;
     prec = p;
     max_batch = maxB;
+    tc = (p == PREC_F32TC);
+    LBC_CHECK(!tc || (std::is_same<T, float>::value), "PREC_F32TC runs on fp32 storage");
     std::vector<int> layers;
     if (k == NET_IMAGE_RESNET34) {
       in_ch = 3;
@@ -191,7 +206,7 @@ class Net : public NetBase {
     a_stem = alloc<T>(B * stem_oh * stem_ow * 64);
     pool = alloc<T>(B * pool_h * pool_w * 64);
     pool_idx = alloc<uint8_t>(B * pool_h * pool_w * 64);
-    if (std::is_same<T, bf16>::value) {
+    if (std::is_same<T, bf16>::value || tc) {
       int Kp = ((49 * in_ch + 63) / 64) * 64;
       stem_gemm.Ci = Kp;
       stem_gemm.Co = 64;
@@ -202,7 +217,9 @@ class Net : public NetBase {
       stem_gemm.W = stem_gemm.OW = stem_ow;
       stem_gemm.wp = alloc<T>(64 * Kp);
       stem_dw_col = alloc<float>(64 * Kp);
-      if (in_ch <= 4) {
+      if (tc) {
+        stem_gemm.wp16 = alloc<float>(64 * Kp);
+      } else if (in_ch <= 4) {
         stem_x4 = alloc<T>(B * (in_h + 6) * (in_w + 8) * 4);
         stem_w224 = alloc<T>(64 * 224);
       } else {
@@ -233,7 +250,10 @@ class Net : public NetBase {
         if (b.ds) {
           add_conv(b.name + ".downsample.0", C, planes, 1, stride, 0, H, W, b.cd);
           add_bn(b.name + ".downsample.1", planes, b.bd);
-          if (std::is_same<T, bf16>::value && stride == 2) b.c1.wcomb = alloc<T>((int64_t)C * 2 * planes);
+          if ((std::is_same<T, bf16>::value || tc) && stride == 2) {
+            b.c1.wcomb = alloc<T>((int64_t)C * 2 * planes);
+            if (tc) b.c1.wcomb16 = alloc<float>((int64_t)C * 2 * planes);
+          }
         }
         int64_t ne = B * b.Hout * b.Wout * planes;
         b.r1 = alloc<T>(ne);
@@ -295,6 +315,14 @@ class Net : public NetBase {
     if (B * 20 * 65 + 4096 > wd) wd = B * 20 * 65 + 4096;
     ws_d = alloc<double>(wd);
     bn_sums = alloc<float>(2 * 1024);
+    if (tc) {
+      // operand-split scratch: a16 holds the largest conv operand (or the split stem column tensor), b16 the second
+      // operand of a weight gradient / the downsample gradient of a fused block-entry data gradient
+      tcw.b_bytes = gmax * 4;
+      tcw.a_bytes = std::max<int64_t>(gmax * 4, B * stem_oh * stem_ow * (int64_t)stem_gemm.Ci * 2 * 2);
+      tcw.a16 = alloc<uint8_t>(tcw.a_bytes);
+      tcw.b16 = alloc<uint8_t>(tcw.b_bytes);
+    }
     if (std::is_same<T, bf16>::value) {
       negshift_all = alloc<float>(n_buffers);
       dev_memset(negshift_all, 0, sizeof(float) * n_buffers, (lbc_stream_t)0);
@@ -324,7 +352,7 @@ class Net : public NetBase {
         pack_host.push_back(e);
       }
     };
-    const bool is_bf16 = std::is_same<T, bf16>::value;
+    const bool is_bf16 = std::is_same<T, bf16>::value || tc;   // (tc: the transposed / combined packs are needed too)
     add_pack(stem, false);
     for (Block& b : blocks) {
       add_pack(b.c1, is_bf16);
@@ -374,6 +402,25 @@ class Net : public NetBase {
       ref::pack_all_pairs<T>(s, P, pack_dev, (int)pack_host.size());
     else
       ref::pack_all<T>(s, P, pack_dev, (int)pack_host.size());
+    if (tc) {
+      bool ok = true;
+      auto split = [&](const void* src, void* dst, int64_t rows, int C) {
+        if (src && dst) ok = ok && fast::tc_split((const float*)src, dst, rows, C, fast::TC_F16, fast::kTcWeightScale, s);
+      };
+      auto split_conv = [&](const ConvL& c) {
+        split(c.wp, c.wp16, (int64_t)c.Co * c.K * c.K, c.Ci);
+        split(c.wpt, c.wpt16, (int64_t)c.Ci * c.K * c.K, c.Co);
+        split(c.wcomb, c.wcomb16, (int64_t)c.Ci * 2, c.Co);
+      };
+      for (Block& b : blocks) {
+        split_conv(b.c1);
+        split_conv(b.c2);
+        if (b.ds) split_conv(b.cd);
+      }
+      for (int i = 0; i < 3; ++i) split_conv(dcv[i]);
+      split(stem_gemm.wp, stem_gemm.wp16, 64, stem_gemm.Ci);
+      LBC_CHECK(ok, "PREC_F32TC: weight split failed (fast kernels disabled or host-emulation build)");
+    }
   }
   static double conv_flops(const ConvL& c, int B) {
     return 2.0 * B * c.OH * c.OW * (double)c.Co * c.K * c.K * c.Ci;
@@ -382,13 +429,19 @@ class Net : public NetBase {
   // stat_rows != null: ask the fast kernel to also emit the BatchNorm statistics partials of its output
   // (*stat_rows = number of partial rows, 0 when not emitted)
   bool conv_forward(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s, const float* negshift = nullptr,
-                    int* stat_rows = nullptr) {
+                    int* stat_rows = nullptr, bool x_is_grad = false) {
     ProfScope ps("conv_fwd", s, conv_flops(c, B), 0);
     if (stat_rows) *stat_rows = 0;
     float* part = (stat_rows && cur_train && (int64_t)c.Co * 2 * ((int64_t)B * c.OH * c.OW / 128 + 64) <= fast::stat_partial_capacity())
                       ? fast::stat_partial_buffer()
                       : nullptr;
     int rows = 0;
+    if (tc) {
+      LBC_CHECK(fast::conv_fwd_tc(c, (const float*)x, nullptr, (float*)y, B, nullptr, false, x_is_grad ? fast::TC_BF16 : fast::TC_F16,
+                                  tcw, s),
+                "PREC_F32TC: tensor-core convolution unavailable for this layer");
+      return false;
+    }
     if (fast::conv_fwd<T>(c, x, y, B, s, negshift, part, &rows)) {
       if (stat_rows && part) *stat_rows = rows;
       return negshift != nullptr;
@@ -399,12 +452,25 @@ class Net : public NetBase {
   }
   void conv_backward_data(const ConvL& c, const T* dy, T* dx, int B, bool accumulate, lbc_stream_t s) {
     ProfScope ps("conv_dgrad", s, conv_flops(c, B), 0);
+    if (tc && !accumulate && c.K != 1) {
+      LBC_CHECK(fast::conv_dgrad_tc(c, (const float*)dy, nullptr, (float*)dx, B, nullptr, false, fast::TC_BF16, tcw, s),
+                "PREC_F32TC: tensor-core data gradient unavailable for this layer");
+      return;
+    }
     if (!accumulate && fast::conv_dgrad<T>(c, dy, dx, B, nullptr, false, s)) return;
     ref::conv_dgrad<T>(s, dy, (const T*)c.wp, dx, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, nullptr,
                        false, accumulate);
   }
-  void conv_backward_weight(const ConvL& c, const T* x, const T* dy, int B, lbc_stream_t s) {
+  // x_is_grad: the conv-role x is a gradient and dy an activation (weight gradient of a ConvTranspose2d)
+  void conv_backward_weight(const ConvL& c, const T* x, const T* dy, int B, lbc_stream_t s, bool x_is_grad = false) {
     ProfScope ps("conv_wgrad", s, conv_flops(c, B), 0);
+    if (tc) {
+      LBC_CHECK(fast::conv_wgrad_tc(c, (const float*)x, nullptr, (const float*)dy, G + c.w_off, B,
+                                    x_is_grad ? fast::TC_BF16 : fast::TC_F16, x_is_grad ? fast::TC_F16 : fast::TC_BF16, ws_f, ws_f_n,
+                                    tcw, s),
+                "PREC_F32TC: tensor-core weight gradient unavailable for this layer");
+      return;
+    }
     if (fast::conv_wgrad<T>(c, x, dy, G + c.w_off, B, ws_f, ws_f_n, s)) return;
     ref::conv_wgrad<T>(s, x, dy, G + c.w_off, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, ws_f, ws_f_n);
   }
@@ -511,10 +577,19 @@ class Net : public NetBase {
       if (fast::stem_im2col_bf16(image, (bf16*)stem_col, B, in_ch, in_h, in_w, stem_oh, stem_ow, stem_gemm.Ci, normalize, s))
         stem_fast_used = fast::conv_fwd<T>(stem_gemm, stem_col, r_stem, B, s, stem_bn.negshift);
     }
+    stem_tc_used = false;
     if (!stem_fast_used) {
       ref::input_to_nhwc<T>(s, image, x0, B, in_ch, in_h, in_w, in_ch, normalize, 0.485f, 0.456f, 0.406f, 0.229f,
                             0.224f, 0.225f);
-      conv_forward(stem, x0, r_stem, B, s);
+      if (tc) {   // split fp16 column tensor -> the generic tensor-core GEMM as a 1x1 convolution over [B,OH,OW,2*Kp]
+        ProfScope ps("conv_fwd", s, conv_flops(stem, B), 0);
+        bool ok = fast::tc_stem_im2col((const float*)x0, tcw.a16, B, in_ch, in_h, in_w, stem_oh, stem_ow, stem_gemm.Ci, s) &&
+                  fast::conv_fwd_tc(stem_gemm, nullptr, tcw.a16, (float*)r_stem, B, nullptr, false, fast::TC_F16, tcw, s);
+        LBC_CHECK(ok, "PREC_F32TC: tensor-core stem unavailable");
+        stem_tc_used = true;
+      } else {
+        conv_forward(stem, x0, r_stem, B, s);
+      }
     }
     stem_pool_fused = false;
     {
@@ -571,7 +646,11 @@ class Net : public NetBase {
       bn_forward(dbn[i], dec_in[i], (int64_t)B * h * w, nullptr, false, dec_bn[i], train, s);
       const ConvL& c = dcv[i];
       ProfScope ps("conv_dgrad", s, conv_flops(c, B), 0);
-      if (!fast::conv_dgrad<T>(c, dec_bn[i], dec_out[i], B, P + c.b_off, true, s))
+      if (tc)
+        LBC_CHECK(fast::conv_dgrad_tc(c, (const float*)dec_bn[i], nullptr, (float*)dec_out[i], B, P + c.b_off, true, fast::TC_F16,
+                                      tcw, s),
+                  "PREC_F32TC: tensor-core ConvTranspose2d unavailable");
+      else if (!fast::conv_dgrad<T>(c, dec_bn[i], dec_out[i], B, P + c.b_off, true, s))
         ref::conv_dgrad<T>(s, dec_bn[i], (const T*)c.wp, dec_out[i], B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH,
                            c.OW, P + c.b_off, true, false);
       h *= 2;
@@ -651,8 +730,8 @@ class Net : public NetBase {
       if (!(i == 2 && head_mask_fused)) relu_mask(gcur, dec_out[i], Mout * c.Ci, s);
       if (!fast::Fast<T>::colsum(gcur, Mout, c.Ci, G + c.b_off, bn_sums, s))
         ref::colsum<T>(s, gcur, Mout, c.Ci, G + c.b_off, ws_d);
-      conv_backward_weight(c, gcur, dec_bn[i], B, s);  // conv-role x = d(out), dy = deconv input
-      conv_forward(c, gcur, tA, B, s);
+      conv_backward_weight(c, gcur, dec_bn[i], B, s, true);  // conv-role x = d(out), dy = deconv input
+      conv_forward(c, gcur, tA, B, s, nullptr, nullptr, true);
       bn_backward(dbn[i], tA, nullptr, dec_in[i], gnext, Min, s);
       std::swap(gcur, gnext);
     }
@@ -676,7 +755,11 @@ class Net : public NetBase {
         bool fused = false;
         {
           ProfScope ps("conv_dgrad", s, conv_flops(b.c1, B) + conv_flops(b.cd, B), 0);
-          fused = fast::conv_dgrad_ds<T>(b.c1, tA, tB, gnext, B, s);   // gnext = dgrad(conv1) + dgrad(downsample)
+          if (tc)
+            fused = fast::conv_dgrad_tc(b.c1, (const float*)tA, (const float*)tB, (float*)gnext, B, nullptr, false, fast::TC_BF16,
+                                        tcw, s);
+          else
+            fused = fast::conv_dgrad_ds<T>(b.c1, tA, tB, gnext, B, s);   // gnext = dgrad(conv1) + dgrad(downsample)
         }
         if (!fused) {
           conv_backward_data(b.c1, tA, gnext, B, false, s);
@@ -714,6 +797,15 @@ class Net : public NetBase {
       if (fast::conv_wgrad<T>(stem_gemm, stem_col, tB, stem_dw_col, B, ws_f, ws_f_n, s))
         stem_wgrad_done = fast::stem_unpack_wgrad(stem_dw_col, G + stem.w_off, in_ch, stem_gemm.Ci, s);
     }
+    if (!stem_wgrad_done && stem_tc_used) {
+      ProfScope ps("conv_wgrad", s, conv_flops(stem, B), 0);
+      bool ok = fast::tc_stem_im2col((const float*)x0, tcw.a16, B, in_ch, in_h, in_w, stem_oh, stem_ow, stem_gemm.Ci, s) &&
+                fast::conv_wgrad_tc(stem_gemm, nullptr, tcw.a16, (const float*)tB, stem_dw_col, B, fast::TC_F16, fast::TC_BF16, ws_f,
+                                    ws_f_n, tcw, s) &&
+                fast::stem_unpack_wgrad(stem_dw_col, G + stem.w_off, in_ch, stem_gemm.Ci, s);
+      LBC_CHECK(ok, "PREC_F32TC: tensor-core stem weight gradient unavailable");
+      stem_wgrad_done = true;
+    }
     if (!stem_wgrad_done) {
       LBC_CHECK(!stem_fast_used, "stem weight gradient: fast path failed after a fast forward");
       conv_backward_weight(stem, x0, tB, B, s);
@@ -750,7 +842,7 @@ class Net : public NetBase {
 std::unique_ptr<NetBase> make_net(NetKind kind, Precision prec, int max_batch) {
   LBC_CHECK(kind == NET_IMAGE_RESNET34 || kind == NET_BIRDVIEW_RESNET18, "unknown net kind");
   LBC_CHECK(max_batch >= 1, "max_batch must be >= 1");
-  if (prec == PREC_F32) return std::unique_ptr<NetBase>(new Net<float>(kind, prec, max_batch));
+  if (prec == PREC_F32 || prec == PREC_F32TC) return std::unique_ptr<NetBase>(new Net<float>(kind, prec, max_batch));
   if (prec == PREC_BF16) return std::unique_ptr<NetBase>(new Net<bf16>(kind, prec, max_batch));
   throw Error("unknown precision");
 }

@@ -15,7 +15,9 @@
 namespace lbc {
 
 enum NetKind { NET_IMAGE_RESNET34 = 0, NET_BIRDVIEW_RESNET18 = 1 };
-enum Precision { PREC_F32 = 0, PREC_BF16 = 1 };
+// PREC_F32TC: fp32 NHWC storage and fp32 BN / softmax / loss as PREC_F32, but every convolution runs on the tcgen05 tensor
+// cores with split-precision operands (hi + lo 16-bit planes, 3 MMAs per K block): parity-grade numerics at GEMM speed
+enum Precision { PREC_F32 = 0, PREC_BF16 = 1, PREC_F32TC = 2 };
 
 struct ParamInfo {
   std::string name;
@@ -39,6 +41,10 @@ struct ConvL {
   void* wp = nullptr;   // packed [Co][K][K][Ci]  (GEMM B operand of the forward conv)
   void* wpt = nullptr;  // packed [Ci][K][K][Co]  (GEMM B operand of the data gradient / deconv forward)
   void* wcomb = nullptr;  // block-entry 3x3/s2 conv only: [Ci][2*Co] = [centre tap of this conv | 1x1/s2 downsample]^T
+  // PREC_F32TC: the same three packs split into fp16 [hi | lo] planes per tap slab (x kTcWeightScale), rebuilt every forward
+  void* wp16 = nullptr;
+  void* wpt16 = nullptr;
+  void* wcomb16 = nullptr;
 };
 struct BNL {
   int C = 0;

@@ -253,6 +253,20 @@ void pack_weight_comb(lbc_stream_t s, const float* w1_ref, const float* wd_ref, 
   });
 }
 
+// stem 7x7 weights [64][C][7][7] -> GEMM rows [64][Kp], k = (kh*7+kw)*C + c, zero padded (the layout of pack_all type 3)
+inline void pack_stem_weight(lbc_stream_t s, const float* w_ref, float* wp, int C, int Kp) {
+  par_for<k_pack_w>(s, (int64_t)64 * Kp, [=] LBC_LAMBDA(int64_t i) {
+    int k = (int)(i % Kp);
+    int co = (int)(i / Kp);
+    float v = 0.f;
+    if (k < 49 * C) {
+      int tap = k / C, c = k - tap * C;
+      v = w_ref[((int64_t)co * C + c) * 49 + tap];
+    }
+    wp[i] = v;
+  });
+}
+
 // all weight packs of a network in ONE launch (table-driven; replaces ~230 tiny launches per step)
 //   type 0: [Co][Ci][K][K] -> [Co][K][K][Ci]      type 1: -> [Ci][K][K][Co] (transposed)
 //   type 2: block-entry combined [Ci][2Co]        type 3: stem [64][C][7][7] -> [64][Kp] (k = tap*C + c, zero padded)

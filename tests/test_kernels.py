@@ -407,10 +407,12 @@ def _stem_case(dev, N, C, H, W, precision, frames):
     normalize = C == 3
     xn = (img - _MEAN.view(1, 3, 1, 1)) / _STD.view(1, 3, 1, 1) if normalize else img
     xr, wr = _r(xn, precision), _r(wgt, precision)
+    if precision == 2:
+        xr, wr = xn.double(), wgt.double()
     y_ref = F.conv2d(xr, wr, None, 2, 3)
     OH, OW = y_ref.shape[2:]
     dy = _r(torch.randn(N, 64, OH, OW, generator=g), precision)
-    dw_ref = torch.nn.grad.conv2d_weight(xr, wgt.shape, dy, 2, 3)
+    dw_ref = torch.nn.grad.conv2d_weight(xr, wgt.shape, dy.to(xr.dtype), 2, 3)
     d = lambda t: None if t is None else t.contiguous().to(dev)
     imgd = d(img) if frames == "f32" else None
     u8d = d(u8) if frames == "u8" else (d(u8.permute(0, 2, 3, 1)) if frames == "u8hwc" else None)
@@ -420,10 +422,13 @@ def _stem_case(dev, N, C, H, W, precision, frames):
     y, dw = torch.empty(N, OH, OW, 64, device=dev), torch.empty(64, C, 7, 7, device=dev)
     stats = torch.empty(128, device=dev) if direct else None
     if precision == 1:
-        must = ["stem_conv_kernel", "stem_wgrad_kernel"] if direct else ["stem_im2col_kernel", "conv_gemm_kernel<64>", "wgrad_gemm_kernel<64>"]
+        # (teacher: 96 output columns -> the per-thread im2col writer, tag k_stem_im2col; 64-column rows use stem_im2col_kernel)
+        must = ["stem_conv_kernel", "stem_wgrad_kernel"] if direct else ["conv_gemm_kernel<64>", "wgrad_gemm_kernel<64>"]
+    elif precision == 2:
+        must = ["tc_stem_im2col_kernel", "conv_gemm_kernel<64,f32>", "wgrad_gemm_kernel<64>"]
     else:
         must = []
-    with Traced(dev, must, REF_TAGS if precision == 1 else ()):
+    with Traced(dev, must, (REF_TAGS if precision == 1 else (("k_conv_fwd", "k_conv_wgrad_part") if precision == 2 else ()))):
         _lib.check(L.lbc_op_stem(_lib.ptr(imgd), _lib.ptr(u8d), 1 if frames == "u8hwc" else 0, _lib.ptr(wd), int(normalize), N, C,
                                  H, W, _lib.ptr(x4), _lib.ptr(y), _lib.ptr(stats), _lib.ptr(dyd), _lib.ptr(dw), precision, None))
     if direct:
@@ -436,8 +441,8 @@ def _stem_case(dev, N, C, H, W, precision, frames):
         yb = y.cpu()
         assert (stats[:64].cpu().double() - yb.double().sum((0, 1, 2))).abs().max() < 2e-3 * max(1.0, float(yb.abs().sum((0, 1, 2)).max()))
         assert (stats[64:].cpu().double() - (yb.double() ** 2).sum((0, 1, 2))).abs().max() < 2e-3 * float((yb.double() ** 2).sum((0, 1, 2)).max())
-    assert _err(_nchw(y.cpu()), y_ref) < (1.2e-2 if precision == 1 else 2e-5)
-    assert _err(dw.cpu(), dw_ref) < (5e-3 if precision == 1 else 2e-5)
+    assert _err(_nchw(y.cpu()), y_ref) < {0: 2e-5, 1: 1.2e-2, 2: 3e-6}[precision]
+    assert _err(dw.cpu(), dw_ref) < {0: 2e-5, 1: 5e-3, 2: 3e-5}[precision]
 
 
 @pytest.mark.parametrize("C", [3, 7])
@@ -457,6 +462,12 @@ def test_stem_kernels_teacher_gpu(backend):
     _stem_case("cuda", 3, 7, 192, 192, 1, "f32")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,H,W", [(3, 160, 384), (7, 192, 192)])
+def test_stem_fp32tc_gpu(backend, C, H, W):
+    _stem_case("cuda", 2, C, H, W, 2, "f32")
+
+
 # ------------------------------------------------------------------ decoder: ConvTranspose2d + bias + ReLU ; block-entry data gradient
 def _deconv_case(dev, N, h, w, Cin, Cout, precision):
     """nn.ConvTranspose2d(Cin, Cout, 3, 2, 1, 1) + bias -> ReLU (image.py:39-46) through lbc_op_conv_dgrad (conv roles:
@@ -467,14 +478,15 @@ def _deconv_case(dev, N, h, w, Cin, Cout, precision):
     x = _r(torch.randn(N, Cin, h, w, generator=g), precision)
     wt = _r(torch.randn(Cin, Cout, 3, 3, generator=g) / (Cin * 2.25) ** 0.5, precision)
     bias = torch.randn(Cout, generator=g) * 0.2
-    ref = F.relu(F.conv_transpose2d(x, wt, bias, 2, 1, 1))
+    ref = F.relu(F.conv_transpose2d(x.double(), wt.double(), bias.double(), 2, 1, 1)) if precision == 2 else \
+        F.relu(F.conv_transpose2d(x, wt, bias, 2, 1, 1))
     xd, wd, bd = _nhwc(x).to(dev), wt.contiguous().to(dev), bias.to(dev)
     y = torch.empty(N, 2 * h, 2 * w, Cout, device=dev)
-    must = ["conv_gemm_kernel"] if precision == 1 else []
-    with Traced(dev, must, REF_TAGS if precision == 1 else ()):
+    must = ["conv_gemm_kernel"] if precision >= 1 else []
+    with Traced(dev, must, REF_TAGS if precision >= 1 else ()):
         _lib.check(L.lbc_op_conv_dgrad(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(y), N, 2 * h, 2 * w, Cout, Cin, 3, 2, 1, precision,
                                        _lib.ptr(bd), 1, None))
-    assert _err(_nchw(y.cpu()), ref) < (1.2e-2 if precision == 1 else 2e-5)
+    assert _err(_nchw(y.cpu()), ref) < {0: 2e-5, 1: 1.2e-2, 2: 3e-6}[precision]
 
 
 def test_deconv_bias_relu_cpu(backend):
@@ -485,6 +497,7 @@ def test_deconv_bias_relu_cpu(backend):
 @pytest.mark.parametrize("N,h,w,Cin,Cout", [(2, 5, 12, 640, 256), (2, 10, 24, 256, 128), (3, 20, 48, 128, 64), (2, 6, 6, 640, 256)])
 def test_deconv_bias_relu_kernels_gpu(backend, N, h, w, Cin, Cout):
     _deconv_case("cuda", N, h, w, Cin, Cout, 1)
+    _deconv_case("cuda", N, h, w, Cin, Cout, 2)
 
 
 def _block_dgrad_case(dev, N, H, W, Ci, Co, precision):
@@ -495,13 +508,14 @@ def _block_dgrad_case(dev, N, H, W, Ci, Co, precision):
     wd = _r(torch.randn(Co, Ci, 1, 1, generator=g) / Ci ** 0.5, precision)
     dy1 = _r(torch.randn(N, Co, H // 2, W // 2, generator=g), precision)
     dy2 = _r(torch.randn(N, Co, H // 2, W // 2, generator=g), precision)
-    ref = torch.nn.grad.conv2d_input((N, Ci, H, W), w1, dy1, 2, 1) + torch.nn.grad.conv2d_input((N, Ci, H, W), wd, dy2, 2, 0)
+    cv = (lambda t: t.double()) if precision == 2 else (lambda t: t)
+    ref = torch.nn.grad.conv2d_input((N, Ci, H, W), cv(w1), cv(dy1), 2, 1) + torch.nn.grad.conv2d_input((N, Ci, H, W), cv(wd), cv(dy2), 2, 0)
     a, b, w1d, wdd = _nhwc(dy1).to(dev), _nhwc(dy2).to(dev), w1.contiguous().to(dev), wd.contiguous().to(dev)
     dx = torch.empty(N, H, W, Ci, device=dev)
-    with Traced(dev, ["conv_gemm_kernel"] if precision == 1 else [], REF_TAGS if precision == 1 else ()):
+    with Traced(dev, ["conv_gemm_kernel"] if precision >= 1 else [], REF_TAGS if precision >= 1 else ()):
         _lib.check(L.lbc_op_block_dgrad_ds(_lib.ptr(a), _lib.ptr(b), _lib.ptr(w1d), _lib.ptr(wdd), _lib.ptr(dx), N, H, W, Ci, Co,
                                            precision, None))
-    assert _err(_nchw(dx.cpu()), ref) < (1.2e-2 if precision == 1 else 2e-5)
+    assert _err(_nchw(dx.cpu()), ref) < {0: 2e-5, 1: 1.2e-2, 2: 3e-5}[precision]
 
 
 def test_block_entry_dgrad_cpu(backend):
@@ -512,6 +526,7 @@ def test_block_entry_dgrad_cpu(backend):
 @pytest.mark.parametrize("N,H,W,Ci,Co", [(3, 40, 96, 64, 128), (5, 20, 48, 128, 256), (9, 10, 24, 256, 512), (2, 48, 48, 64, 128)])
 def test_block_entry_dgrad_kernels_gpu(backend, N, H, W, Ci, Co):
     _block_dgrad_case("cuda", N, H, W, Ci, Co, 1)
+    _block_dgrad_case("cuda", N, H, W, Ci, Co, 2)
 
 
 # ------------------------------------------------------------------ conv epilogue: centring shift + BatchNorm statistics partials

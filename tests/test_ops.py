@@ -261,6 +261,56 @@ def test_tcgen05_conv_gpu(backend, case, variant):
         _lib.check(_lib.lib().lbc_set_fast_kernels(1 | _variant_default()))
 
 
+def _conv_case_tc(case):
+    """fp32tc: fp32 operands as they are (no pre-rounding) through the split-precision tcgen05 GEMMs vs an fp64 torch
+    reference; error relative to the largest entry.  forward / ConvTranspose2d-style products are fp16 x fp16 planes
+    (22-bit significands), gradients ride in bf16 planes (16 bits)."""
+    from learningbycheating_b200 import _lib
+    N, H, W, Ci, Co, K, s, p = case
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, K, K, generator=g) / (Ci * K * K) ** 0.5
+    y_ref = F.conv2d(x.double(), w.double(), None, s, p)
+    OH, OW = y_ref.shape[2:]
+    dy = torch.randn(N, Co, OH, OW, generator=g) * 1e-4          # gradient-sized values: the bf16 planes must carry them
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, w.double(), dy.double(), s, p)
+    dw_ref = torch.nn.grad.conv2d_weight(x.double(), w.shape, dy.double(), s, p)
+    L = _lib.lib()
+    xd, wd, dyd = _nhwc(x).cuda(), w.contiguous().cuda(), _nhwc(dy).cuda()
+    y = torch.empty(N, OH, OW, Co, device="cuda")
+    _lib.check(L.lbc_op_conv_fwd(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(y), N, H, W, Ci, Co, K, s, p, 2, None, None, None))
+    dw = torch.empty(Co, Ci, K, K, device="cuda")
+    _lib.check(L.lbc_op_conv_wgrad(_lib.ptr(xd), _lib.ptr(dyd), _lib.ptr(dw), N, H, W, Ci, Co, K, s, p, 2, None))
+    errs = {"fwd": float((_nchw(y.cpu()).double() - y_ref).abs().max() / y_ref.abs().max()),
+            "wgrad": float((dw.cpu().double() - dw_ref).abs().max() / dw_ref.abs().max())}
+    if K == 3:
+        dx = torch.empty(N, H, W, Ci, device="cuda")
+        _lib.check(L.lbc_op_conv_dgrad(_lib.ptr(dyd), _lib.ptr(wd), _lib.ptr(dx), N, H, W, Ci, Co, K, s, p, 2, None, 0, None))
+        errs["dgrad"] = float((_nchw(dx.cpu()).double() - dx_ref).abs().max() / dx_ref.abs().max())
+    return errs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["base", "pair"])
+@pytest.mark.parametrize("case", FAST_CASES)
+def test_tcgen05_conv_fp32tc_gpu(backend, case, variant):
+    """LBC_PREC_F32TC convolutions at the real layer shapes: <= 3e-6 (forward) / 3e-5 (gradients) of the largest entry
+    against fp64, and the launch trace shows only split-precision tcgen05 kernels (\"...,f32>\")."""
+    from learningbycheating_b200 import _lib
+    from test_kernels import Traced
+    bits = {"base": 8 | 32 | 128, "pair": 4 | 16 | 64}[variant]
+    _lib.check(_lib.lib().lbc_set_fast_kernels(1 | bits))
+    try:
+        with Traced("cuda", ["conv_gemm_kernel<", "split16_kernel<f16>", "split16_kernel<bf16>"], ("k_conv_fwd", "k_conv_dgrad", "k_conv_wgrad_part")) as tr:
+            errs = _conv_case_tc(case)
+        assert not [k for k in tr.counts if k.startswith("conv_gemm_kernel<") and not k.endswith("f32>")], sorted(tr.counts)
+        assert "conv3x3_c64_kernel" not in tr.counts
+        print("fp32tc %s %s: %s" % (case, variant, {k: "%.2e" % v for k, v in errs.items()}))
+        assert errs["fwd"] < 3e-6 and errs["wgrad"] < 3e-5 and errs.get("dgrad", 0.0) < 3e-5, errs
+    finally:
+        _lib.check(_lib.lib().lbc_set_fast_kernels(1 | _variant_default()))
+
+
 @pytest.mark.gpu
 def test_tensor_core_accumulation_error_gpu(backend):
     """How far the fp32 TMEM accumulation of the tcgen05 MMAs sits from an fp64 sum of the same (bf16-exact) products:
