@@ -36,10 +36,7 @@ const char* lbc_build_info(void);
 /* enable / disable the tcgen05 + fused kernels (tests compare them with the correctness-first kernels).
  * bit 0: fast kernels on; bit 1: generic tap-per-box kernel for the 64->64 3x3 convolutions;
  * variant switches (absent bits keep the LBC_PAIR default): 4 / 8 = CTA-pair (cta_group::2) conv GEMMs on / off,
- * 16 / 32 = row-of-taps weight gradient on / off, 64 / 128 = its CTA-pair variant on / off;
- * candidates not yet measured on the B200 (default off, LBC_EXPERIMENTAL): 256 / 512 = pair-walking weight pack,
- * 1024 / 2048 = register-blocked waypoint-head kernels, 4096 / 8192 = capped grids for the one-element-per-thread kernels,
- * 16384 / 32768 = one-launch (cooperative) BatchNorm backward for L2-resident tensors. */
+ * 16 / 32 = row-of-taps weight gradient on / off, 64 / 128 = its CTA-pair variant on / off. */
 int lbc_set_fast_kernels(int enabled);
 
 /* ---- instrumentation used by bench.py ---- */

@@ -129,14 +129,6 @@ int lbc_set_fast_kernels(int enabled) {
   if (enabled & 64) m |= 4;     // 64 / 128 = CTA-pair variant of the row-of-taps weight gradient on / off
   if (enabled & 128) m &= ~4;
   fast::set_pair_mode(m);
-  if (enabled & 256) fast::set_experimental(fast::experimental() | 1);    // 256 / 512 = pair-walking weight pack on / off
-  if (enabled & 512) fast::set_experimental(fast::experimental() & ~1);
-  if (enabled & 1024) fast::set_experimental(fast::experimental() | 2);   // 1024 / 2048 = register-blocked head kernels on / off
-  if (enabled & 2048) fast::set_experimental(fast::experimental() & ~2);
-  if (enabled & 4096) fast::set_experimental(fast::experimental() | 4);   // 4096 / 8192 = capped par_for grids on / off
-  if (enabled & 8192) fast::set_experimental(fast::experimental() & ~4);
-  if (enabled & 16384) fast::set_experimental(fast::experimental() | 8);   // 16384 / 32768 = one-launch BatchNorm backward on / off
-  if (enabled & 32768) fast::set_experimental(fast::experimental() & ~8);
   return 0;
 }
 
@@ -373,13 +365,13 @@ int lbc_op_conv_dgrad(const float* dy, const float* w_ref, float* dx, int N, int
       ref::conv_dgrad<float>(s, dy, wp, dx, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, bias_ci, relu != 0, false);
     } else if (precision == PREC_F32TC) {
       // relu != 0 marks the ConvTranspose2d forward (dy is an activation: fp16 planes); otherwise dy is a gradient (bf16 planes)
+      const int fmt = relu ? fast::TC_F16 : fast::TC_BF16;
       float *wt = t.get<float>(nw), *w16 = t.get<float>(nw);
       ref::pack_weight_t<float>(s, w_ref, wt, Co, Ci, K);
-      LBC_CHECK(fast::tc_split(wt, w16, (int64_t)Ci * K * K, Co, fast::TC_F16, fast::kTcWeightScale, s), "tc_split unavailable");
+      LBC_CHECK(fast::tc_split(wt, w16, (int64_t)Ci * K * K, Co, fmt, fast::kTcWeightScale, s), "tc_split unavailable");
       c.wpt16 = w16;
       fast::TcWork tw = make_tcwork(t, ny * 4, 16);
-      LBC_CHECK(fast::conv_dgrad_tc(c, dy, nullptr, dx, N, bias_ci, relu != 0, relu ? fast::TC_F16 : fast::TC_BF16, tw, s),
-                "conv_dgrad_tc declined the shape");
+      LBC_CHECK(fast::conv_dgrad_tc(c, dy, nullptr, dx, N, bias_ci, relu != 0, fmt, tw, s), "conv_dgrad_tc declined the shape");
     } else {
       bf16 *xb = t.get<bf16>(nx), *wb = t.get<bf16>(nw), *yb = t.get<bf16>(ny);
       bf16* wtb = t.get<bf16>(nw);
@@ -415,8 +407,8 @@ int lbc_op_block_dgrad_ds(const float* dy1, const float* dy_ds, const float* w1_
       float *w1t = t.get<float>(nw), *w1t16 = t.get<float>(nw), *wc = t.get<float>(nc), *wc16 = t.get<float>(nc);
       ref::pack_weight_t<float>(s, w1_ref, w1t, Co, Ci, 3);
       ref::pack_weight_comb<float>(s, w1_ref, wd_ref, wc, Co, Ci);
-      LBC_CHECK(fast::tc_split(w1t, w1t16, (int64_t)Ci * 9, Co, fast::TC_F16, fast::kTcWeightScale, s) &&
-                    fast::tc_split(wc, wc16, (int64_t)Ci * 2, Co, fast::TC_F16, fast::kTcWeightScale, s),
+      LBC_CHECK(fast::tc_split(w1t, w1t16, (int64_t)Ci * 9, Co, fast::TC_BF16, fast::kTcWeightScale, s) &&
+                    fast::tc_split(wc, wc16, (int64_t)Ci * 2, Co, fast::TC_BF16, fast::kTcWeightScale, s),
                 "tc_split unavailable");
       c1.wpt16 = w1t16;
       c1.wcomb16 = wc16;
@@ -458,7 +450,7 @@ int lbc_op_conv_wgrad(const float* x, const float* dy, float* dw_ref, int N, int
       ref::conv_wgrad<float>(s, x, dy, dw_ref, N, H, W, Ci, Co, K, stride, pad, c.OH, c.OW, ws, wsn);
     } else if (precision == PREC_F32TC) {
       fast::TcWork tw = make_tcwork(t, nx * 4, ny * 4);
-      LBC_CHECK(fast::conv_wgrad_tc(c, x, nullptr, dy, dw_ref, N, fast::TC_F16, fast::TC_BF16, ws, wsn, tw, s),
+      LBC_CHECK(fast::conv_wgrad_tc(c, x, nullptr, dy, dw_ref, N, fast::TC_BF16, fast::TC_BF16, ws, wsn, tw, s),
                 "conv_wgrad_tc declined the shape");
     } else {
       bf16 *xb = t.get<bf16>(nx), *yb = t.get<bf16>(ny);
@@ -760,12 +752,15 @@ int lbc_op_stem(const float* img, const uint8_t* img_u8, int layout, const float
       LBC_CHECK(fast::tc_split(wp, wp16, 64, Kp, fast::TC_F16, fast::kTcWeightScale, s), "tc_split unavailable");
       g.wp16 = wp16;
       fast::TcWork tw = make_tcwork(t, npix * Kp * 4, npix * 64 * 4);
-      LBC_CHECK(fast::tc_stem_im2col(x0, tw.a16, N, C, H, W, OH, OW, Kp, s), "tc_stem_im2col unavailable");
-      if (y) LBC_CHECK(fast::conv_fwd_tc(g, nullptr, tw.a16, y, N, nullptr, false, fast::TC_F16, tw, s), "stem GEMM (tc) declined the shape");
+      if (y) {
+        LBC_CHECK(fast::tc_stem_im2col(x0, tw.a16, N, C, H, W, OH, OW, Kp, fast::TC_F16, s), "tc_stem_im2col unavailable");
+        LBC_CHECK(fast::conv_fwd_tc(g, nullptr, tw.a16, y, N, nullptr, false, fast::TC_F16, tw, s), "stem GEMM (tc) declined the shape");
+      }
       if (dy && dw) {
         int64_t wsn = 4 << 20;
         float *ws = t.get<float>(wsn), *dwc = t.get<float>((int64_t)64 * Kp);
-        LBC_CHECK(fast::conv_wgrad_tc(g, nullptr, tw.a16, dy, dwc, N, fast::TC_F16, fast::TC_BF16, ws, wsn, tw, s),
+        LBC_CHECK(fast::tc_stem_im2col(x0, tw.a16, N, C, H, W, OH, OW, Kp, fast::TC_BF16, s), "tc_stem_im2col unavailable");
+        LBC_CHECK(fast::conv_wgrad_tc(g, nullptr, tw.a16, dy, dwc, N, fast::TC_BF16, fast::TC_BF16, ws, wsn, tw, s),
                   "stem weight gradient (tc) declined the shape");
         LBC_CHECK(fast::stem_unpack_wgrad(dwc, dw, C, Kp, s), "stem_unpack_wgrad failed");
       }

@@ -160,8 +160,6 @@ inline const char* tag_name() {   // "... [with Tag = lbc::ref::k_conv_fwd]": wo
     ++::lbc::g_launches;                                \
     if (::lbc::g_trace_on) ::lbc::trace_note(name);     \
   } while (0)
-// > 0: par_for launches at most this many blocks and the threads walk the range with a grid stride (experimental() & 4)
-extern int g_par_for_max_blocks;
 struct ProfEntry {
   std::string cat;
   double flops, bytes;
@@ -222,9 +220,6 @@ inline void par_for(lbc_stream_t s, int64_t n, F f) {
   const int bs = 256;
   int64_t nb = (n + bs - 1) / bs;
   LBC_CHECK(nb < (1ll << 31), "par_for grid too large");
-  // EXPERIMENTAL: one-element threads make the 20 M-element kernels (stem_pad4, head_dlogits, adam) block-dispatch
-  // bound (88 K blocks of 256 one-element threads in 222 us); a capped grid lets each thread walk several elements
-  if (g_par_for_max_blocks > 0 && nb > g_par_for_max_blocks) nb = g_par_for_max_blocks;
   par_for_kernel<Tag, F><<<(unsigned)nb, bs, 0, s>>>(n, f);
   LBC_LAUNCHED(tag_name<Tag>());
   LBC_CUDA(cudaGetLastError());

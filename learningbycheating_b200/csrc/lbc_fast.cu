@@ -17,7 +17,6 @@ std::string trace_dump() {
   for (auto& kv : trace_map()) out += kv.first + "\t" + std::to_string(kv.second) + "\n";
   return out;
 }
-int g_par_for_max_blocks = 0;
 bool g_prof_on = false;
 std::vector<ProfEntry> g_prof;
 namespace fast {
@@ -25,32 +24,6 @@ namespace fast {
 static bool g_enabled = true;
 bool enabled() { return g_enabled; }
 void set_enabled(bool on) { g_enabled = on; }
-// candidates validated on the CPU (host-emulation build, bit-exact data movement) but not yet MEASURED on the B200;
-// off by default, switched by lbc_set_fast_kernels or LBC_EXPERIMENTAL (bit 0: pair-walking weight pack, bit 1:
-// register-blocked head kernels, bit 2: capped par_for grids, bit 3: one-launch BatchNorm backward)
-static int g_experimental = [] {
-  const char* e = getenv("LBC_EXPERIMENTAL");
-  return e ? atoi(e) : 0;
-}();
-static void apply_experimental() {
-  int cap = 0;
-#ifndef LBC_HOST_EMU
-  if (g_experimental & 4) {
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cap = (sms > 0 ? sms : 148) * 32;
-  }
-#endif
-  g_par_for_max_blocks = cap;
-}
-int experimental() { return g_experimental; }
-void set_experimental(int bits) {
-  g_experimental = bits;
-  apply_experimental();
-}
-static const bool g_experimental_applied = (apply_experimental(), true);
-
 
 #ifdef LBC_HOST_EMU
 bool stem_im2col_bf16(const float*, bf16*, int, int, int, int, int, int, int, bool, lbc_stream_t) { return false; }

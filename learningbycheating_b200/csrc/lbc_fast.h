@@ -13,8 +13,6 @@ namespace fast {
 // global switch (tests flip it to compare fast kernels against the correctness-first ones)
 bool enabled();
 void set_enabled(bool on);
-int experimental();            // bit 0: ref::pack_all_pairs instead of ref::pack_all; bit 1: register-blocked head kernels; bit 2: capped par_for grids; bit 3: one-launch (cooperative) BatchNorm backward
-void set_experimental(int bits);
 
 // stat_partial != null: the epilogue also writes per-tile column sums / sums of squares of the stored output
 // ([*stat_rows][2*Co] floats) so that the BatchNorm statistics pass over the tensor disappears.
@@ -80,8 +78,9 @@ inline bool conv_wgrad<bf16>(const ConvL& c, const bf16* x, const bf16* dy, floa
 // ---- fp32tc: parity-grade tensor-core convolutions over fp32 NHWC tensors (lbc_fast_conv.cu) --------------------
 // Every operand is split into two 16-bit planes, x ~ hi + lo, stored [rows][hi C | lo C]; the GEMM K loop accumulates
 // hi*hi + hi*lo + lo*hi in the fp32 TMEM accumulator and the epilogue stores fp32.  Formats: TC_F16 (11-bit significands:
-// hi + lo carries 22 bits; for activations and weights, whose range fp16 covers -- weights are pre-scaled by
-// kTcWeightScale, undone in the epilogue) and TC_BF16 (fp32's exponent range: for gradients; 16 bits).
+// hi + lo carries 22 bits; for the FORWARD pass, whose activations and weights fp16's range covers -- weights are pre-scaled
+// by kTcWeightScale, undone in the epilogue) and TC_BF16 (fp32's exponent range, 16 bits: every GEMM of the BACKWARD pass,
+// where one operand is a gradient).  Both operands of a GEMM use the same format (a tcgen05.mma restriction).
 enum { TC_F16 = 0, TC_BF16 = 1 };
 constexpr float kTcWeightScale = 64.0f;
 struct TcWork {       // two operand-split scratch buffers owned by the caller
@@ -90,18 +89,19 @@ struct TcWork {       // two operand-split scratch buffers owned by the caller
   int64_t a_bytes = 0, b_bytes = 0;
 };
 bool tc_split(const float* src, void* dst16, int64_t rows, int C, int fmt, float scale, lbc_stream_t s);
-// x [B,H,W,Ci] fp32 -> y [B,OH,OW,Co] fp32 (c.wp16); x_fmt: TC_F16 for an activation, TC_BF16 when x is a gradient
-// (the decoder's backward-data runs through the conv-role forward).  x16 != null: x is already split.
+// x [B,H,W,Ci] fp32 -> y [B,OH,OW,Co] fp32 (c.wp16, split in x_fmt); x_fmt: TC_F16 for an activation, TC_BF16 when x is a
+// gradient (the decoder's backward-data runs through the conv-role forward).  x16 != null: x is already split.
 bool conv_fwd_tc(const ConvL& c, const float* x, const void* x16, float* y, int B, const float* bias_co, bool relu, int x_fmt,
                  const TcWork& w, lbc_stream_t s);
-// dy [B,OH,OW,Co] -> dx [B,H,W,Ci] (+bias, ReLU) (c.wpt16); dy_ds != null: + the fused 1x1/s2 downsample gradient (c.wcomb16)
+// dy [B,OH,OW,Co] -> dx [B,H,W,Ci] (+bias, ReLU) (c.wpt16, split in dy_fmt); dy_ds != null: + the fused 1x1/s2 downsample
+// gradient (c.wcomb16)
 bool conv_dgrad_tc(const ConvL& c, const float* dy, const float* dy_ds, float* dx, int B, const float* bias_ci, bool relu,
                    int dy_fmt, const TcWork& w, lbc_stream_t s);
 // dw_ref [Co][Ci][K][K] = sum_pixels dy x;  x16 != null: x already split (stem column tensor, in w.a16)
 bool conv_wgrad_tc(const ConvL& c, const float* x, const void* x16, const float* dy, float* dw_ref, int B, int x_fmt, int dy_fmt,
                    float* scratch, int64_t scratch_floats, const TcWork& w, lbc_stream_t s);
-// stem: x0 [B,H,W,C] fp32 NHWC -> split column tensor [B*OH*OW][hi Kp | lo Kp] (k = (kh*7+kw)*C + c, zero padded), fp16
-bool tc_stem_im2col(const float* x0, void* col16, int B, int C, int H, int W, int OH, int OW, int Kp, lbc_stream_t s);
+// stem: x0 [B,H,W,C] fp32 NHWC -> split column tensor [B*OH*OW][hi Kp | lo Kp] (k = (kh*7+kw)*C + c, zero padded)
+bool tc_stem_im2col(const float* x0, void* col16, int B, int C, int H, int W, int OH, int OW, int Kp, int fmt, lbc_stream_t s);
 
 // ---- HBM-bound bf16 kernels (lbc_fast_elem.cu) -------------------------------------------------------------
 bool bn_stats_bf16(const bf16* x, int64_t M, int C, float* sums, lbc_stream_t s);

@@ -2499,8 +2499,9 @@ bool tc_split(const float* src, void* dst16, int64_t rows, int C, int fmt, float
   LBC_CUDA(cudaGetLastError());
   return true;
 }
-// one thread per (pixel, k): the 7x7/s2 window element k = (kh*7 + kw)*C + c of the NHWC fp32 image, split into fp16 hi | lo
-__global__ void __launch_bounds__(256) tc_stem_im2col_kernel(const float* __restrict__ x0, __half* __restrict__ col, int64_t npix,
+// one thread per (pixel, k): the 7x7/s2 window element k = (kh*7 + kw)*C + c of the NHWC fp32 image, split into hi | lo planes
+template <bool F16>
+__global__ void __launch_bounds__(256) tc_stem_im2col_kernel(const float* __restrict__ x0, uint16_t* __restrict__ col, int64_t npix,
                                                              int C, int H, int W, int OH, int OW, int Kp) {
   const int64_t n = npix * Kp;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -2517,18 +2518,30 @@ __global__ void __launch_bounds__(256) tc_stem_im2col_kernel(const float* __rest
       const int ih = oh * 2 - 3 + kh, iw = ow * 2 - 3 + kw;
       if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x0 + ((b * H + ih) * W + iw) * C + c);
     }
-    const float cv = fminf(fmaxf(v, -65504.f), 65504.f);
-    const __half h = __float2half_rn(cv);
-    col[pix * 2 * Kp + k] = h;
-    col[pix * 2 * Kp + Kp + k] = __float2half_rn(cv - __half2float(h));
+    uint16_t hi, lo;
+    if (F16) {
+      const float cv = fminf(fmaxf(v, -65504.f), 65504.f);
+      const __half h = __float2half_rn(cv);
+      hi = __half_as_ushort(h);
+      lo = __half_as_ushort(__float2half_rn(cv - __half2float(h)));
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi = __bfloat16_as_ushort(h);
+      lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+    }
+    col[pix * 2 * Kp + k] = hi;
+    col[pix * 2 * Kp + Kp + k] = lo;
   }
 }
-bool tc_stem_im2col(const float* x0, void* col16, int B, int C, int H, int W, int OH, int OW, int Kp, lbc_stream_t s) {
+bool tc_stem_im2col(const float* x0, void* col16, int B, int C, int H, int W, int OH, int OW, int Kp, int fmt, lbc_stream_t s) {
   const int64_t npix = (int64_t)B * OH * OW;
   int64_t blocks = (npix * Kp + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 32;
   if (blocks > cap) blocks = cap;
-  tc_stem_im2col_kernel<<<(unsigned)blocks, 256, 0, s>>>(x0, (__half*)col16, npix, C, H, W, OH, OW, Kp);
+  if (fmt == TC_F16)
+    tc_stem_im2col_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(x0, (uint16_t*)col16, npix, C, H, W, OH, OW, Kp);
+  else
+    tc_stem_im2col_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(x0, (uint16_t*)col16, npix, C, H, W, OH, OW, Kp);
   LBC_LAUNCHED("tc_stem_im2col_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -2551,7 +2564,9 @@ bool conv_fwd_tc(const ConvL& c, const float* x, const void* x16, float* y, int 
     if (!tc_split(x, w.a16, rows, c.Ci, x_fmt, 1.0f, s)) return false;
     x16 = w.a16;
   }
-  return conv_fwd_impl(c, x16, c.wp16, y, B, bias_co, relu, s, nullptr, nullptr, tc_mode(x_fmt, TC_F16, 1.0f / kTcWeightScale));
+  // (tcgen05.mma kind::f16 takes ONE 16-bit format per instruction: fp16 x bf16 traps as an illegal instruction on the B200,
+  // so c.wp16 must have been split in x_fmt)
+  return conv_fwd_impl(c, x16, c.wp16, y, B, bias_co, relu, s, nullptr, nullptr, tc_mode(x_fmt, x_fmt, 1.0f / kTcWeightScale));
 }
 bool conv_dgrad_tc(const ConvL& c, const float* dy, const float* dy_ds, float* dx, int B, const float* bias_ci, bool relu,
                    int dy_fmt, const TcWork& w, lbc_stream_t s) {
@@ -2562,11 +2577,11 @@ bool conv_dgrad_tc(const ConvL& c, const float* dy, const float* dy_ds, float* d
   if (!tc_split(dy, w.a16, rows, c.Co, dy_fmt, 1.0f, s)) return false;
   if (dy_ds && !tc_split(dy_ds, w.b16, rows, c.Co, dy_fmt, 1.0f, s)) return false;
   return conv_dgrad_impl(c, w.a16, c.wpt16, c.wcomb16, dx, B, bias_ci, relu, dy_ds ? w.b16 : nullptr, s,
-                         tc_mode(dy_fmt, TC_F16, 1.0f / kTcWeightScale));
+                         tc_mode(dy_fmt, dy_fmt, 1.0f / kTcWeightScale));   // c.wpt16 / c.wcomb16 split in dy_fmt
 }
 bool conv_wgrad_tc(const ConvL& c, const float* x, const void* x16, const float* dy, float* dw_ref, int B, int x_fmt, int dy_fmt,
                    float* scratch, int64_t scratch_floats, const TcWork& w, lbc_stream_t s) {
-  if (!enabled() || !supported(c)) return false;
+  if (!enabled() || !supported(c) || x_fmt != dy_fmt) return false;   // one operand format per MMA
   const int64_t rx = (int64_t)B * c.H * c.W, ry = (int64_t)B * c.OH * c.OW;
   if (ry * c.Co * 4 > w.b_bytes) return false;
   if (!x16) {
@@ -2592,7 +2607,7 @@ bool tc_split(const float*, void*, int64_t, int, int, float, lbc_stream_t) { ret
 bool conv_fwd_tc(const ConvL&, const float*, const void*, float*, int, const float*, bool, int, const TcWork&, lbc_stream_t) { return false; }
 bool conv_dgrad_tc(const ConvL&, const float*, const float*, float*, int, const float*, bool, int, const TcWork&, lbc_stream_t) { return false; }
 bool conv_wgrad_tc(const ConvL&, const float*, const void*, const float*, float*, int, int, int, float*, int64_t, const TcWork&, lbc_stream_t) { return false; }
-bool tc_stem_im2col(const float*, void*, int, int, int, int, int, int, int, lbc_stream_t) { return false; }
+bool tc_stem_im2col(const float*, void*, int, int, int, int, int, int, int, int, lbc_stream_t) { return false; }
 #endif
 
 }  // namespace fast

@@ -8,7 +8,6 @@
 #include "lbc_fast.h"
 
 #ifndef LBC_HOST_EMU
-#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #endif
 
@@ -359,8 +358,9 @@ __global__ void __launch_bounds__(256, OWN ? 3 : 4) bn_bwd_reduce_kernel(const u
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    red[t * 16 + j] = s0[j];
-    red[t * 16 + 8 + j] = s1[j] * rstd[cg * 8 + j];   // sum g*xhat = rstd * sum g*(x-mu)
+    s1[j] *= rstd[cg * 8 + j];   // sum g*xhat = rstd * sum g*(x-mu)   (scaled in the register too: row group 0 adds its own
+    red[t * 16 + j] = s0[j];     //  s1 below -- round 1 scaled only the shared-memory copy, so the block's first row group
+    red[t * 16 + 8 + j] = s1[j]; //  entered dgamma without rstd; found by tests/test_kernels.py::test_bn_backward_kernels_gpu)
   }
   __syncthreads();
   if (t < tpr) {
@@ -428,168 +428,6 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
   }
 }
 
-// EXPERIMENTAL (experimental() & 8; not yet measured on the B200): the three launches of BatchNorm backward (reduce ->
-// col_finalize -> apply) as ONE cooperative launch with two grid barriers, for tensors small enough that the second pass
-// is served by L2 (layers 3-4, decoder: 16-63 MB per tensor, where the three launches are launch/latency-bound: 17-25 us
-// each for 47-94 MB).  Phase bodies are those of bn_bwd_reduce_kernel / bn_bwd_apply_kernel; values written by other
-// blocks (partials, sums) are read with ld.global.cg after the barrier.
-template <bool OWN>
-__global__ void __launch_bounds__(256, 3) bn_bwd_fused_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
-                                                              const uint4* __restrict__ x, const float* __restrict__ mean,
-                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta_own, float* dgamma, float* dbeta,
-                                                              uint4* __restrict__ dx, int64_t M, int tpr, int rpi, int C,
-                                                              float* partial, float* sums) {
-  namespace cgr = cooperative_groups;
-  cgr::grid_group grid = cgr::this_grid();
-  extern __shared__ float red[];
-  const int t = threadIdx.x;
-  const int cg = t % tpr, r = t / tpr;
-  const int64_t stride = (int64_t)gridDim.x * rpi;
-  {
-    // ---------------- phase 1: per-block partial sums
-    float mu[8], s0[8], s1[8], sc[8], sh[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mu[j] = mean[cg * 8 + j];
-      s0[j] = s1[j] = 0.f;
-      sc[j] = OWN ? gamma[cg * 8 + j] * rstd[cg * 8 + j] : 0.f;
-      sh[j] = OWN ? beta_own[cg * 8 + j] - mu[j] * sc[j] : 0.f;
-    }
-#pragma unroll 2
-    for (int64_t row = (int64_t)blockIdx.x * rpi + r; row < M; row += stride) {
-      const int64_t i0 = row * tpr + cg;
-      const uint4 d0 = __ldg(dy + i0), x0 = __ldg(x + i0);
-      uint4 a0 = d0;
-      if (!OWN && act) a0 = __ldg(act + i0);
-      float fd[8], fx[8], fa[8];
-      unpack8(d0, fd);
-      unpack8(x0, fx);
-      unpack8(a0, fa);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (OWN) fa[j] = fx[j] * sc[j] + sh[j];
-        float g = ((OWN || act) && !(fa[j] > 0.f)) ? 0.f : fd[j];
-        s0[j] += g;
-        s1[j] += g * (fx[j] - mu[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      red[t * 16 + j] = s0[j];
-      red[t * 16 + 8 + j] = s1[j] * rstd[cg * 8 + j];
-    }
-    __syncthreads();
-    if (t < tpr) {
-      for (int rr = 1; rr < rpi; ++rr) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s0[j] += red[(rr * tpr + t) * 16 + j];
-          s1[j] += red[(rr * tpr + t) * 16 + 8 + j];
-        }
-      }
-      float* dst = partial + (int64_t)blockIdx.x * 2 * C;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        dst[t * 8 + j] = s0[j];
-        dst[C + t * 8 + j] = s1[j];
-      }
-    }
-  }
-  grid.sync();
-  // ---------------- phase 1b: column sums of the gridDim.x partial rows (fixed tree order -> deterministic)
-  {
-    const int C2 = 2 * C;
-    const int nt = (int)blockDim.x;
-    for (int col = blockIdx.x; col < C2; col += gridDim.x) {
-      float a = 0.f;
-      for (int p = t; p < (int)gridDim.x; p += nt) a += __ldcg(partial + (int64_t)p * C2 + col);
-      __syncthreads();
-      red[t] = a;
-      __syncthreads();
-      for (int h = 128; h > 0; h >>= 1) {
-        if (t < h && t + h < nt) red[t] += red[t + h];
-        __syncthreads();
-      }
-      if (t == 0) sums[col] = red[0];
-    }
-  }
-  grid.sync();
-  // ---------------- phase 2: dx
-  {
-    float k0[8], kb[8], ka[8], sh[8];
-    const float invM = 1.0f / (float)M;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
-      const float mu = mean[c], rs = rstd[c];
-      const float db = __ldcg(sums + c), dg = __ldcg(sums + C + c);
-      if (blockIdx.x == 0 && r == 0) {
-        dbeta[c] = db;
-        dgamma[c] = dg;
-      }
-      k0[j] = gamma[c] * rs;
-      sh[j] = OWN ? beta_own[c] - mu * k0[j] : 0.f;
-      kb[j] = -k0[j] * rs * dg * invM;
-      ka[j] = -k0[j] * db * invM - kb[j] * mu;
-    }
-    if (!dx) return;
-#pragma unroll 2
-    for (int64_t row = (int64_t)blockIdx.x * rpi + r; row < M; row += stride) {
-      const int64_t i0 = row * tpr + cg;
-      const uint4 d0 = __ldg(dy + i0), x0 = __ldg(x + i0);
-      uint4 a0 = d0;
-      if (!OWN && act) a0 = __ldg(act + i0);
-      float fd[8], fx[8], fa[8], o[8];
-      unpack8(d0, fd);
-      unpack8(x0, fx);
-      unpack8(a0, fa);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (OWN) fa[j] = fx[j] * k0[j] + sh[j];
-        float g = ((OWN || act) && !(fa[j] > 0.f)) ? 0.f : fd[j];
-        o[j] = fmaf(k0[j], g, fmaf(kb[j], fx[j], ka[j]));
-      }
-      dx[i0] = pack8(o);
-    }
-  }
-}
-template <bool OWN>
-static bool launch_bn_bwd_fused(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
-                                const float* gamma, const float* beta_own, float* dgamma, float* dbeta, bf16* dx, int64_t M,
-                                int C, float* part, float* sums, lbc_stream_t s) {
-  auto kern = bn_bwd_fused_kernel<OWN>;
-  RowGeom g = row_geom(M, C, 3);
-  const size_t smem = (size_t)g.threads * 16 * sizeof(float);
-  static int supported = -1, per_sm = 0;
-  if (supported < 0) {
-    int dev = 0, coop = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    supported = coop ? 1 : 0;
-  }
-  if (!supported) return false;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.threads, smem) != cudaSuccess || per_sm < 1) {
-    cudaGetLastError();
-    return false;
-  }
-  int grid = g.grid;
-  const int cap = per_sm * sm_count2();
-  if (grid > cap) grid = cap;       // every block must be resident for the grid barriers
-  const uint4* a0 = (const uint4*)dy;
-  const uint4* a1 = (const uint4*)mask_act;
-  const uint4* a2 = (const uint4*)x;
-  uint4* a9 = (uint4*)dx;
-  int tpr = g.tpr, rpi = g.rpi;
-  void* args[] = {&a0, &a1, &a2, &mean, &rstd, &gamma, &beta_own, &dgamma, &dbeta, &a9, &M, &tpr, &rpi, &C, &part, &sums};
-  if (cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)grid), dim3((unsigned)g.threads), args, smem, s) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  LBC_LAUNCHED((OWN ? "bn_bwd_fused_kernel<own>" : "bn_bwd_fused_kernel"));
-  return true;
-}
-
 bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
                  const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s,
                  const float* beta_own) {
@@ -602,16 +440,6 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
   RowGeom g = row_geom(M, C, 4);
   float* part = partial_buffer();
   if (!part) return false;
-  if ((experimental() & 8) && dx && (int64_t)M * C * 2 <= ((int64_t)64 << 20)) {   // <= 64 MB per tensor: second pass from L2
-    const bool ok = beta_own ? launch_bn_bwd_fused<true>(dy, mask_act, x, mean, rstd, gamma, beta_own, dgamma, dbeta, dx, M, C,
-                                                         part, sums, s)
-                             : launch_bn_bwd_fused<false>(dy, mask_act, x, mean, rstd, gamma, beta_own, dgamma, dbeta, dx, M, C,
-                                                          part, sums, s);
-    if (ok) {
-      LBC_CUDA(cudaGetLastError());
-      return true;
-    }
-  }
   if (beta_own) {
     RowGeom g3 = row_geom(M, C, 3);
     bn_bwd_reduce_kernel<true><<<g3.grid, g3.threads, g3.threads * 16 * sizeof(float), s>>>(

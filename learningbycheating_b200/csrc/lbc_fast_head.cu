@@ -52,37 +52,9 @@ bool head_fold(ref::HeadParams hp, float* fold, lbc_stream_t s) {
   return true;
 }
 
-__global__ void __launch_bounds__(128) head_logits_kernel(const uint4* __restrict__ h, const float* __restrict__ fold,
-                                                          float* __restrict__ logits, int64_t npix, int HW) {
-  __shared__ float A[1300];
-  for (int i = threadIdx.x; i < 1300; i += 128) A[i] = fold[i];
-  __syncthreads();
-  const int64_t pix = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (pix >= npix) return;
-  float acc[20];
-#pragma unroll
-  for (int kj = 0; kj < 20; ++kj) acc[kj] = A[1280 + kj];
-#pragma unroll
-  for (int v = 0; v < 8; ++v) {
-    float f[8];
-    unpack8h(__ldg(h + pix * 8 + v), f);
-#pragma unroll
-    for (int kj = 0; kj < 20; ++kj) {
-      float a = acc[kj];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) a += A[kj * 64 + v * 8 + e] * f[e];
-      acc[kj] = a;
-    }
-  }
-  const int64_t n = pix / HW;
-  const int p = (int)(pix - n * HW);
-#pragma unroll
-  for (int kj = 0; kj < 20; ++kj) logits[(n * 20 + kj) * HW + p] = acc[kj];
-}
-
-// EXPERIMENTAL (experimental() & 2; not yet measured on the B200).  head_logits_kernel issues one broadcast LDS per FMA
-// (1280 per pixel) and is shared-memory-issue bound (116 us for a 126 MB read).  Here a thread owns FOUR pixels and reads
-// the folded coefficients as float4, so one LDS.128 feeds 16 FMAs.  Same accumulation order per (pixel, kj) -> bit-identical.
+// A thread owns FOUR pixels and reads the folded coefficients as float4, so one LDS.128 feeds 16 FMAs (a one-pixel-per-
+// thread version issued one broadcast LDS per FMA, 1280 per pixel, and was shared-memory-issue bound: 116 us for a 126 MB
+// read at B = 256).
 __global__ void __launch_bounds__(128) head_logits4_kernel(const uint4* __restrict__ h, const float* __restrict__ fold,
                                                            float* __restrict__ logits, int64_t npix, int HW) {
   __shared__ __align__(16) float A[1300];
@@ -208,67 +180,12 @@ bool head_forward_bf16(const bf16* h, ref::HeadParams hp, float* fold, float* lo
   if (HW > 4096) return false;
   head_fold(hp, fold, s);
   const int64_t npix = (int64_t)N * HW;
-  if (experimental() & 2)
-    head_logits4_kernel<<<(unsigned)((npix + 511) / 512), 128, 0, s>>>((const uint4*)h, fold, logits, npix, HW);
-  else
-    head_logits_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, s>>>((const uint4*)h, fold, logits, npix, HW);
-  LBC_LAUNCHED(((experimental() & 2) ? "head_logits4_kernel" : "head_logits_kernel"));
+  head_logits4_kernel<<<(unsigned)((npix + 511) / 512), 128, 0, s>>>((const uint4*)h, fold, logits, npix, HW);
+  LBC_LAUNCHED("head_logits4_kernel");
   head_softmax_kernel<<<N * 20, 128, 0, s>>>(logits, rowmax, rowsum, preds, H, W);
   LBC_LAUNCHED("head_softmax_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
-}
-
-// S[kj][c] += sum_pix dl[n,kj,pix]*hhat[n,pix,c] (c<64), S[kj][64] += sum dl   (double atomics, S pre-zeroed)
-__global__ void __launch_bounds__(256) head_s_kernel(const float* __restrict__ dlogits, const uint4* __restrict__ h,
-                                                     const float* __restrict__ mean, const float* __restrict__ rstd, double* S,
-                                                     int N, int HW) {
-  __shared__ float dl[20][128];
-  __shared__ float hh[128][65];
-  const int t = threadIdx.x;
-  const int c = t & 63, grp = t >> 6;  // 4 groups x 5 kj
-  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  float acc0[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  const int tiles_per_img = (HW + 127) / 128;
-  const int ntiles = N * tiles_per_img;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int n = tile / tiles_per_img;
-    const int p0 = (tile - n * tiles_per_img) * 128;
-    const int np = min(128, HW - p0);
-    __syncthreads();
-    for (int i = t; i < 20 * 128; i += 256) {
-      int kj = i >> 7, p = i & 127;
-      dl[kj][p] = p < np ? dlogits[((int64_t)n * 20 + kj) * HW + p0 + p] : 0.f;
-    }
-    for (int i = t; i < 128 * 8; i += 256) {
-      int p = i >> 3, v = i & 7;
-      float f[8];
-      if (p < np) {
-        unpack8h(__ldg(h + ((int64_t)n * HW + p0 + p) * 8 + v), f);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = 0.f;
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) hh[p][v * 8 + e] = p < np ? (f[e] - mean[v * 8 + e]) * rstd[v * 8 + e] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int p = 0; p < 128; ++p) {
-      const float x = hh[p][c];
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const float d = dl[grp * 5 + j][p];
-        acc[j] += d * x;
-        if (c == 0) acc0[j] += d;
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    atomicAdd(&S[(grp * 5 + j) * 65 + c], (double)acc[j]);
-    if (c == 0) atomicAdd(&S[(grp * 5 + j) * 65 + 64], (double)acc0[j]);
-  }
 }
 
 // coef[0..64) = c0, coef[64..128) = c1 :  dh = A^T dl - c0 - hhat*c1
@@ -284,52 +201,8 @@ bool head_coef(ref::HeadParams hp, ref::HeadGrads hg, float* coef, float invM, l
   });
   return true;
 }
-// d(pre-ReLU deconv output)[pix][c] = (h>0) * (sum_kj A[kj][c] dl[kj] - c0[c] - hhat[c]*c1[c])
-__global__ void __launch_bounds__(128) head_dh_kernel(const float* __restrict__ dlogits, const uint4* __restrict__ h,
-                                                      const float* __restrict__ fold, const float* __restrict__ coef,
-                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                      uint4* __restrict__ dh, int64_t npix, int HW) {
-  __shared__ float A[1280];
-  __shared__ float cf[256];  // c0, c1, mean, rstd
-  for (int i = threadIdx.x; i < 1280; i += 128) A[i] = fold[i];
-  if (threadIdx.x < 64) {
-    cf[threadIdx.x] = coef[threadIdx.x];
-    cf[64 + threadIdx.x] = coef[64 + threadIdx.x];
-    cf[128 + threadIdx.x] = mean[threadIdx.x];
-    cf[192 + threadIdx.x] = rstd[threadIdx.x];
-  }
-  __syncthreads();
-  const int64_t pix = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (pix >= npix) return;
-  const int64_t n = pix / HW;
-  const int p = (int)(pix - n * HW);
-  float d[20];
-#pragma unroll
-  for (int kj = 0; kj < 20; ++kj) d[kj] = dlogits[(n * 20 + kj) * HW + p];
-#pragma unroll
-  for (int v = 0; v < 8; ++v) {
-    float f[8], o[8];
-    unpack8h(__ldg(h + pix * 8 + v), f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = v * 8 + e;
-      float a = 0.f;
-#pragma unroll
-      for (int kj = 0; kj < 20; ++kj) a += A[kj * 64 + c] * d[kj];
-      const float xh = (f[e] - cf[128 + c]) * cf[192 + c];
-      a = a - cf[c] - xh * cf[64 + c];
-      o[e] = f[e] > 0.f ? a : 0.f;
-    }
-    uint4 w;
-    __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) hb[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-    dh[pix * 8 + v] = w;
-  }
-}
-
-// EXPERIMENTAL (experimental() & 2): four pixels per thread, coefficients read as float4 over channels (one LDS.128 per
-// 16 FMAs instead of one LDS per FMA).  Same accumulation order per (pixel, channel) -> bit-identical to head_dh_kernel.
+// d(pre-ReLU deconv output)[pix][c] = (h>0) * (sum_kj A[kj][c] dl[kj] - c0[c] - hhat[c]*c1[c]);
+// four pixels per thread, coefficients read as float4 over channels (one LDS.128 per 16 FMAs).
 __global__ void __launch_bounds__(128) head_dh4_kernel(const float* __restrict__ dlogits, const uint4* __restrict__ h,
                                                        const float* __restrict__ fold, const float* __restrict__ coef,
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -401,9 +274,9 @@ __global__ void __launch_bounds__(128) head_dh4_kernel(const float* __restrict__
   }
 }
 
-// EXPERIMENTAL (experimental() & 2): moment matrix with 4 channels x 5 kj x 4 pixels per inner step (9 LDS.128 per 80 FMAs
-// instead of 6 LDS per 5 FMAs).  Thread = (channel quad 0..15, kj group 0..3, pixel quarter 0..3); the four pixel quarters are
-// combined in shared memory before the double atomics.  Summation order differs from head_s_kernel (tolerance-level equal).
+// S[kj][c] += sum_pix dl[n,kj,pix]*hhat[n,pix,c] (c<64), S[kj][64] += sum dl   (double atomics, S pre-zeroed):
+// moment matrix with 4 channels x 5 kj x 4 pixels per inner step (9 LDS.128 per 80 FMAs).  Thread = (channel quad 0..15,
+// kj group 0..3, pixel quarter 0..3); the four pixel quarters are combined in shared memory before the double atomics.
 __global__ void __launch_bounds__(256) head_s4_kernel(const float* __restrict__ dlogits, const uint4* __restrict__ h,
                                                       const float* __restrict__ mean, const float* __restrict__ rstd, double* S,
                                                       int N, int HW) {
@@ -490,11 +363,8 @@ bool head_backward_s_bf16(const float* dlogits, const bf16* h, const float* mean
   int grid = sm_count3() * 2;
   int ntiles = N * ((HW + 127) / 128);
   if (grid > ntiles) grid = ntiles;
-  if (experimental() & 2)
-    head_s4_kernel<<<grid, 256, 0, s>>>(dlogits, (const uint4*)h, mean, rstd, S, N, HW);
-  else
-    head_s_kernel<<<grid, 256, 0, s>>>(dlogits, (const uint4*)h, mean, rstd, S, N, HW);
-  LBC_LAUNCHED(((experimental() & 2) ? "head_s4_kernel" : "head_s_kernel"));
+  head_s4_kernel<<<grid, 256, 0, s>>>(dlogits, (const uint4*)h, mean, rstd, S, N, HW);
+  LBC_LAUNCHED("head_s4_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -503,13 +373,9 @@ bool head_backward_dh_bf16(const float* dlogits, const bf16* h, ref::HeadParams 
   if (!enabled()) return false;
   const int64_t npix = (int64_t)N * HW;
   head_coef(hp, hg, coef, 1.0f / (float)npix, s);
-  if (experimental() & 2)
-    head_dh4_kernel<<<(unsigned)((npix + 511) / 512), 128, 0, s>>>(dlogits, (const uint4*)h, fold, coef, hp.mean[0], hp.rstd[0],
-                                                                 (uint4*)dh, npix, HW);
-  else
-    head_dh_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, s>>>(dlogits, (const uint4*)h, fold, coef, hp.mean[0], hp.rstd[0],
-                                                                (uint4*)dh, npix, HW);
-  LBC_LAUNCHED(((experimental() & 2) ? "head_dh4_kernel" : "head_dh_kernel"));
+  head_dh4_kernel<<<(unsigned)((npix + 511) / 512), 128, 0, s>>>(dlogits, (const uint4*)h, fold, coef, hp.mean[0], hp.rstd[0],
+                                                               (uint4*)dh, npix, HW);
+  LBC_LAUNCHED("head_dh4_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }

@@ -8,7 +8,8 @@
 
 namespace lbc {
 long long g_launches = 0;   // normally defined by lbc_fast.cu
-int g_par_for_max_blocks = 0;
+bool g_trace_on = false;
+void trace_note(const char*) {}
 bool g_prof_on = false;
 std::vector<ProfEntry> g_prof;
 }  // namespace lbc

@@ -131,7 +131,7 @@ def test_bn_forward_kernels_gpu(backend, M, C, relu, res, shift):
 
 
 # ------------------------------------------------------------------ BatchNorm backward
-def _bn_bwd_case(dev, M, C, mode, precision, fused=False):
+def _bn_bwd_case(dev, M, C, mode, precision):
     """mode: 'plain' | 'mask' (a separate activation's ReLU mask on dy) | 'own' (mask = relu of this BN's own output)"""
     _lib = _L()
     L = _lib.lib()
@@ -139,6 +139,16 @@ def _bn_bwd_case(dev, M, C, mode, precision, fused=False):
     x = _r(torch.randn(M, C, generator=g) * 1.5 + 0.3, precision)
     gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5
     dy = _r(torch.randn(M, C, generator=g), precision)
+    if mode == "own":
+        # the fast kernels recompute the mask (bn(x) > 0) from x: move the few x whose BN output sits within rounding
+        # distance of zero (bf16-exact steps), so that the reference and the kernel cannot disagree on any mask bit
+        for _ in range(8):
+            y0 = F.batch_norm(x.t().reshape(1, C, M, 1), None, None, gamma, beta, True, 0.1, 1e-5).reshape(C, M).t()
+            near = y0.abs() < 4e-3
+            if not bool(near.any()):
+                break
+            x = _r(torch.where(near, x + 0.0625, x), 1)
+        assert not bool(near.any())
     xt = x.t().reshape(1, C, M, 1).clone().requires_grad_(True)
     gp, bp = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     y = F.batch_norm(xt, None, None, gp, bp, True, 0.1, 1e-5)
@@ -147,18 +157,14 @@ def _bn_bwd_case(dev, M, C, mode, precision, fused=False):
         act = _r(torch.randn(M, C, generator=g), precision)
     elif mode == "own":
         act = y.detach().reshape(C, M).t().clamp_min(0)
-        # keep the mask decision away from the rounding boundary of the recomputed x*sc+sh (bf16 inputs are exact)
-        act = torch.where(y.detach().reshape(C, M).t().abs() < 1e-3, torch.zeros_like(act), act)
     dym = dy if act is None else dy * (act > 0).float()
     y.backward(dym.t().reshape(1, C, M, 1))
-    if mode == "own":   # elements the kernel may legitimately mask the other way: exclude from dx comparison only
-        near = (y.detach().reshape(C, M).t().abs() < 1e-3)
     d = lambda t: None if t is None else t.contiguous().to(dev)
     xd, dyd, gd, bd, ad = d(x), d(dy), d(gamma), d(beta), d(act)
     dg, db, dx = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty(M, C, device=dev)
     own = mode == "own"
     if precision == 1:
-        must = ["bn_bwd_fused_kernel"] if fused else ["bn_bwd_reduce_kernel", "bn_bwd_apply_kernel"]
+        must = ["bn_bwd_reduce_kernel", "bn_bwd_apply_kernel"]
         if own:
             must = [m + "<own>" for m in must]
     else:
@@ -167,20 +173,11 @@ def _bn_bwd_case(dev, M, C, mode, precision, fused=False):
     with Traced(dev, must, never):     # (the op wrapper recomputes the batch statistics with the correctness-first pass)
         _lib.check(L.lbc_op_bn_bwd(_lib.ptr(dyd), _lib.ptr(xd), _lib.ptr(gd), _lib.ptr(dg), _lib.ptr(db), _lib.ptr(dx), M, C,
                                    precision, _lib.ptr(ad), _lib.ptr(bd), 1 if own else 0, None))
-    tol = 1.2e-2 if precision == 1 else 1e-4
-    if mode == "own" and bool(near.any()):
-        # a flipped mask element changes dgamma/dbeta by one term: bound by the largest |dy|
-        slack = float(near.sum()) * float(dy.abs().max()) * 4
-    else:
-        slack = 0.0
-    assert (dg.cpu() - gp.grad).abs().max() <= 2e-4 * max(1.0, gp.grad.abs().max().item()) * (30 if precision == 1 else 1) + slack
-    assert (db.cpu() - bp.grad).abs().max() <= 2e-4 * max(1.0, bp.grad.abs().max().item()) * (30 if precision == 1 else 1) + slack
-    dx_ref = xt.grad.reshape(C, M).t()
-    got = dx.cpu()
-    if mode == "own":
-        keep = (~near).float()
-        got, dx_ref = got * keep, dx_ref * keep
-    assert _err(got, dx_ref) < tol + (1e-2 if slack else 0)
+    # dgamma / dbeta are fp32 sums of exact (bf16 x bf16) products on both paths
+    scale = max(1.0, gp.grad.abs().max().item(), bp.grad.abs().max().item())
+    assert (dg.cpu() - gp.grad).abs().max() <= 2e-4 * scale, (dg.cpu() - gp.grad).abs().max()
+    assert (db.cpu() - bp.grad).abs().max() <= 2e-4 * scale
+    assert _err(dx.cpu(), xt.grad.reshape(C, M).t()) < (1.2e-2 if precision == 1 else 1e-4)     # dx is stored in bf16
 
 
 @pytest.mark.parametrize("mode", ["plain", "mask", "own"])
@@ -194,18 +191,6 @@ def test_bn_backward_cpu(backend, mode, precision):
 @pytest.mark.parametrize("mode", ["plain", "mask", "own"])
 def test_bn_backward_kernels_gpu(backend, M, C, mode):
     _bn_bwd_case("cuda", M, C, mode, 1)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["plain", "mask", "own"])
-def test_bn_backward_one_launch_kernel_gpu(backend, mode):
-    """the cooperative reduce -> grid sync -> apply variant (lbc_set_fast_kernels bit 16384)"""
-    _lib = _L()
-    _lib.check(_lib.lib().lbc_set_fast_kernels(1 | 16384))
-    try:
-        _bn_bwd_case("cuda", 9 * 10 * 24, 256, mode, 1, fused=True)
-    finally:
-        _lib.check(_lib.lib().lbc_set_fast_kernels(1 | 32768))
 
 
 # ------------------------------------------------------------------ masked adds
@@ -362,16 +347,6 @@ def test_heads_cpu(backend, precision):
 @pytest.mark.parametrize("use_pred", [False, True])
 def test_head_kernels_gpu(backend, N, H, W, use_pred):
     _head_case("cuda", N, H, W, 1, use_pred)
-
-
-@pytest.mark.gpu
-def test_head_kernels_register_blocked_variant_gpu(backend):
-    _lib = _L()
-    _lib.check(_lib.lib().lbc_set_fast_kernels(1 | 1024))
-    try:
-        _head_case("cuda", 3, 40, 96, 1, True)
-    finally:
-        _lib.check(_lib.lib().lbc_set_fast_kernels(1 | 2048))
 
 
 @pytest.mark.gpu

@@ -263,8 +263,8 @@ def test_tcgen05_conv_gpu(backend, case, variant):
 
 def _conv_case_tc(case):
     """fp32tc: fp32 operands as they are (no pre-rounding) through the split-precision tcgen05 GEMMs vs an fp64 torch
-    reference; error relative to the largest entry.  forward / ConvTranspose2d-style products are fp16 x fp16 planes
-    (22-bit significands), gradients ride in bf16 planes (16 bits)."""
+    reference; error relative to the largest entry.  forward / ConvTranspose2d products are fp16 x fp16 planes (22-bit
+    significands); the backward GEMMs (one operand is a gradient) use bf16 x bf16 planes (16 bits, fp32's range)."""
     from learningbycheating_b200 import _lib
     N, H, W, Ci, Co, K, s, p = case
     g = torch.Generator().manual_seed(3)
