@@ -108,7 +108,7 @@ struct ConvGemmParams {
   int valid_n;                      // batch size (rows of images >= valid_n are the zero-filled tail)
   // split-precision mode (fp32tc): both operands are stored as two 16-bit planes [hi | lo] along K (A: channels
   // [0,a_plane) hi, [a_plane,2*a_plane) lo; B: every tap slab [hi b_plane | lo b_plane]); the K loop runs the three
-  // products hi*hi + hi*lo + lo*hi into the same fp32 accumulator.  fmt: UMMA 16-bit operand format (0 = fp16, 1 = bf16).
+  // products hi*lo + lo*hi + hi*hi into the same fp32 accumulator.  fmt: UMMA 16-bit operand format (0 = fp16, 1 = bf16).
   int split, a_plane, b_plane;
   uint32_t fmt_a, fmt_b;
   float out_scale;                  // accumulator scale applied in the epilogue (undoes the power-of-two operand scaling)
@@ -351,13 +351,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         const int w0 = (m_tile % p.tiles_w) * p.TW;
         const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
-          const int mid = p.tap_map[tap];
-          const CUtensorMap* ma = mid == 0 ? &mA0 : (mid == 1 ? &mA1 : (mid == 2 ? &mA2 : &mA3));
-          const int dh = p.tap_dh[tap], dw = p.tap_dw[tap], koff = p.tap_koff[tap];
-          for (int term = 0; term < nterm; ++term) {   // split mode: hi*hi, hi*lo, lo*hi
-            const int ac0 = term == 2 ? p.a_plane : 0;
-            const int bc0 = koff + (term == 1 ? p.b_plane : 0);
+        // split mode: the two cross terms (hi*lo, lo*hi) go first, the hi*hi term last.  The tensor core adds into the
+        // fp32 accumulator with truncation (measured: bias ~ -5e-7 of the accumulator per ~100 accumulation steps), so
+        // only the K/16 steps of the hi*hi term should run against a full-size accumulator.
+        for (int term = 0; term < nterm; ++term) {
+          const int ac0 = (p.split && term == 1) ? p.a_plane : 0;   // term 0: A hi x B lo, 1: A lo x B hi, 2: A hi x B hi
+          const int bplane = (p.split && term == 0) ? p.b_plane : 0;
+          for (int tap = 0; tap < p.num_taps; ++tap) {
+            const int mid = p.tap_map[tap];
+            const CUtensorMap* ma = mid == 0 ? &mA0 : (mid == 1 ? &mA1 : (mid == 2 ? &mA2 : &mA3));
+            const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+            const int bc0 = p.tap_koff[tap] + bplane;
             for (int kc = 0; kc < p.k_chunks; ++kc) {
               mbar_wait(&empty[stage], phase ^ 1);
               uint8_t* sa = smem + stage * SP::STAGE_BYTES;
@@ -1714,7 +1718,7 @@ struct WgradParams {
   // 128-row MMA is full instead of half zero padding
   int swap, num_combos, chunks_per_tap;
   // split-precision mode: dy = [hi | lo] planes of dy_plane channels, x = [hi | lo] planes of x_plane channels; the K
-  // (pixel) loop runs 3 x k_tiles_real tiles: (dy hi, x hi), (dy hi, x lo), (dy lo, x hi).  k_tiles = 3 * k_tiles_real.
+  // (pixel) loop runs 3 x k_tiles_real tiles: (dy hi, x lo), (dy lo, x hi), (dy hi, x hi).  k_tiles = 3 * k_tiles_real.
   int split, k_tiles_real, dy_plane, x_plane;
   uint32_t fmt_dy, fmt_x;   // UMMA formats (0 = fp16, 1 = bf16)
 };
@@ -1812,7 +1816,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
       for (int kt2 = kt0; kt2 < kt1; ++kt2) {
         const int term = p.split ? kt2 / p.k_tiles_real : 0;
         const int kt = kt2 - term * p.k_tiles_real;
-        const int dyo = term == 2 ? p.dy_plane : 0, xo = term == 1 ? p.x_plane : 0;
+        const int dyo = (p.split && term == 1) ? p.dy_plane : 0;   // term 0: dy hi x x lo, 1: dy lo x x hi, 2: hi x hi (last:
+        const int xo = (p.split && term == 0) ? p.x_plane : 0;     //  see the note on accumulator truncation in conv_gemm_kernel)
         const int w0 = (kt % p.tiles_w) * p.TW;
         const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -1999,7 +2004,8 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
       for (int kt2 = kt0; kt2 < kt1; ++kt2) {
         const int term = p.split ? kt2 / p.k_tiles_real : 0;
         const int kt = kt2 - term * p.k_tiles_real;
-        const int dyo = term == 2 ? p.dy_plane : 0, xo = term == 1 ? p.x_plane : 0;
+        const int dyo = (p.split && term == 1) ? p.dy_plane : 0;   // term 0: dy hi x x lo, 1: dy lo x x hi, 2: hi x hi (last:
+        const int xo = (p.split && term == 0) ? p.x_plane : 0;     //  see the note on accumulator truncation in conv_gemm_kernel)
         const int w0 = (kt % p.tiles_w) * p.TW;
         const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.TN;
