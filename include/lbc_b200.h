@@ -83,6 +83,16 @@ int lbc_net_forward_u8(lbc_net_t* net, const uint8_t* image_u8, int layout, cons
  * and/or out_preds [B,4,5,2] (NULL = none); writes every on-path parameter gradient into the bound
  * gradient array (overwrites, like backward() after zero_grad()). */
 int lbc_net_backward(lbc_net_t* net, const float* d_pred, const float* d_preds, void* stream);
+/* Data-parallel overlap (new: the reference is single-GPU; SURVEY.md 8(e) "one all-reduce, bucketed in reverse-execution
+ * order and overlapped with backward").  The on-path gradients form lbc_net_num_grad_buckets() contiguous ranges of the flat
+ * gradient array, numbered in the order backward completes them (0 = heads + decoder ... last = layer1 + stem; conv.fc.* is in
+ * no bucket: it is never trained).  After lbc_net_enable_grad_events(net, 1), lbc_net_backward records one CUDA event per
+ * bucket on its stream, and lbc_net_stream_wait_grads makes another stream wait for bucket k of the latest backward -- the
+ * caller then launches that bucket's ncclAllReduce there while the rest of backward still runs. */
+int lbc_net_num_grad_buckets(const lbc_net_t* net);
+int lbc_net_grad_bucket(const lbc_net_t* net, int bucket, int64_t* offset, int64_t* numel);
+int lbc_net_enable_grad_events(lbc_net_t* net, int on);
+int lbc_net_stream_wait_grads(lbc_net_t* net, int bucket, void* stream);
 /* copy an internal activation out as fp32 NCHW ("stem.raw", "stem.pool", "conv.layer1.0", ...,
  * "deconv.1|4|7", "logits"); returns element count or -1 */
 int64_t lbc_net_read_tap(lbc_net_t* net, const char* name, float* out, int64_t capacity, void* stream);

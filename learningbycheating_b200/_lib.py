@@ -49,6 +49,10 @@ def _declare(lib):
         "lbc_net_forward_u8": (i, [vp, vp, i, vp, vp, i, i, vp, vp, vp]),
         "lbc_net_backward": (i, [vp, vp, vp, vp]),
         "lbc_net_read_tap": (i64, [vp, ctypes.c_char_p, vp, i64, vp]),
+        "lbc_net_num_grad_buckets": (i, [vp]),
+        "lbc_net_grad_bucket": (i, [vp, i, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
+        "lbc_net_enable_grad_events": (i, [vp, i]),
+        "lbc_net_stream_wait_grads": (i, [vp, i, vp]),
         "lbc_phase0_target": (i, [vp, vp, i64, f, f, f, f, f, vp]),
         "lbc_l1_loss": (i, [vp, vp, i, i, f, f, f, f, f, vp, vp, vp, vp]),
         "lbc_phase1_convert_fwd": (i, [vp, vp, i64, f, f, f, f, f, vp]),

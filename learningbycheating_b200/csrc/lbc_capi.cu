@@ -238,6 +238,20 @@ int lbc_net_forward_u8(lbc_net_t* net, const uint8_t* image_u8, int layout, cons
 int lbc_net_backward(lbc_net_t* net, const float* d_pred, const float* d_preds, void* stream) {
   return guarded([&] { net->impl->backward(d_pred, d_preds, S(stream)); });
 }
+int lbc_net_num_grad_buckets(const lbc_net_t* net) { return (int)net->impl->buckets.size(); }
+int lbc_net_grad_bucket(const lbc_net_t* net, int bucket, int64_t* offset, int64_t* numel) {
+  return guarded([&] {
+    LBC_CHECK(bucket >= 0 && bucket < (int)net->impl->buckets.size(), "gradient bucket index out of range");
+    *offset = net->impl->buckets[bucket].offset;
+    *numel = net->impl->buckets[bucket].numel;
+  });
+}
+int lbc_net_enable_grad_events(lbc_net_t* net, int on) {
+  return guarded([&] { net->impl->enable_grad_events(on != 0); });
+}
+int lbc_net_stream_wait_grads(lbc_net_t* net, int bucket, void* stream) {
+  return guarded([&] { net->impl->stream_wait_bucket(bucket, S(stream)); });
+}
 int64_t lbc_net_read_tap(lbc_net_t* net, const char* name, float* out, int64_t capacity, void* stream) {
   int64_t n = -1;
   int rc = guarded([&] { n = net->impl->read_tap(name, out, capacity, S(stream)); });

@@ -28,6 +28,28 @@ void nhwc_to_nchw_f32(lbc_stream_t s, const T* x, float* out, int N, int H, int 
 }
 }  // namespace ref
 
+void NetBase::enable_grad_events(bool on) {
+#ifndef LBC_HOST_EMU
+  for (GradBucket& b : buckets) {
+    if (on && !b.event) {
+      cudaEvent_t e;
+      LBC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      b.event = e;
+    }
+  }
+#endif
+  grad_events = on;
+}
+void NetBase::stream_wait_bucket(int bucket, lbc_stream_t s) {
+  LBC_CHECK(bucket >= 0 && bucket < (int)buckets.size(), "gradient bucket index out of range");
+  LBC_CHECK(grad_events, "gradient events are not enabled (lbc_net_enable_grad_events)");
+#ifndef LBC_HOST_EMU
+  LBC_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)buckets[bucket].event, 0));
+#else
+  (void)s;
+#endif
+}
+
 static const float kBnEps = 1e-5f;
 static const float kBnMomentum = 0.1f;
 
@@ -98,6 +120,18 @@ class Net : public NetBase {
   }
   ~Net() override {
     for (void* p : allocs) dev_free(p);
+#ifndef LBC_HOST_EMU
+    for (GradBucket& b : buckets)
+      if (b.event) cudaEventDestroy((cudaEvent_t)b.event);
+#endif
+  }
+  void mark_bucket(int k, lbc_stream_t s) {   // bucket k's gradients are all enqueued on s
+#ifndef LBC_HOST_EMU
+    if (grad_events && buckets[k].event) LBC_CUDA(cudaEventRecord((cudaEvent_t)buckets[k].event, s));
+#else
+    (void)k;
+    (void)s;
+#endif
   }
   size_t workspace_bytes() const override { return total_bytes; }
 
@@ -393,6 +427,27 @@ class Net : public NetBase {
     LBC_CUDA(cudaMemcpy(pack_dev, pack_host.data(), sizeof(ref::PackEntry) * pack_host.size(), cudaMemcpyHostToDevice));
 #endif
     head_fold = alloc<float>(1300 + 128 + 28);
+    // gradient buckets (ranges of the flat array in state_dict order: stem, layer1..4, [conv.fc: never trained], decoder, heads)
+    {
+      auto off_of = [&](const std::string& prefix) {
+        for (const ParamInfo& pi : params)
+          if (pi.name.compare(0, prefix.size(), prefix) == 0) return pi.offset;
+        return n_params;
+      };
+      const int64_t o_l2 = off_of("conv.layer2."), o_l3 = off_of("conv.layer3."), o_l4 = off_of("conv.layer4."),
+                    o_fc = off_of("conv.fc."), o_dec = off_of("deconv.");
+      buckets.resize(5);
+      buckets[0].offset = o_dec;
+      buckets[0].numel = n_params - o_dec;
+      buckets[1].offset = o_l4;
+      buckets[1].numel = o_fc - o_l4;
+      buckets[2].offset = o_l3;
+      buckets[2].numel = o_l4 - o_l3;
+      buckets[3].offset = o_l2;
+      buckets[3].numel = o_l3 - o_l2;
+      buckets[4].offset = 0;
+      buckets[4].numel = o_l2;
+    }
   }
 
   // ------------------------------------------------------------------ op wrappers (fast-path hooks)
@@ -737,6 +792,7 @@ class Net : public NetBase {
       bn_backward(dbn[i], tA, nullptr, dec_in[i], gnext, Min, s);
       std::swap(gcur, gnext);
     }
+    mark_bucket(0, s);
     // drop the 128 speed channels (no gradient path to a parameter through them)
     ref::slice_channels<T>(s, gcur, gnext, (int64_t)B * trunk_h * trunk_w, 640, 512);
     std::swap(gcur, gnext);
@@ -772,6 +828,10 @@ class Net : public NetBase {
         add_masked(gnext, gcur, b.out, ne, s);
       }
       std::swap(gcur, gnext);
+      // a stage is complete when its entry block (the one with the downsample branch) has been differentiated
+      if (b.ds && b.Cout == 512) mark_bucket(1, s);
+      if (b.ds && b.Cout == 256) mark_bucket(2, s);
+      if (b.ds && b.Cout == 128) mark_bucket(3, s);
     }
     // stem: maxpool -> relu -> bn -> conv1 weight gradient (no input gradient)
     int64_t Ms = (int64_t)B * stem_oh * stem_ow;
@@ -812,6 +872,7 @@ class Net : public NetBase {
       LBC_CHECK(!stem_fast_used, "stem weight gradient: fast path failed after a fast forward");
       conv_backward_weight(stem, x0, tB, B, s);
     }
+    mark_bucket(4, s);
   }
 
   // ------------------------------------------------------------------ taps

@@ -80,6 +80,18 @@ class NetBase {
   // debugging / parity taps: copy a named internal tensor out as fp32 NCHW
   virtual int64_t read_tap(const char* name, float* out, int64_t cap, lbc_stream_t s) = 0;
   virtual size_t workspace_bytes() const = 0;
+  // gradient buckets in the order backward() completes them (0 = heads + decoder, then layer4, layer3, layer2, and
+  // layer1 + stem last): each one contiguous [offset, offset + numel) range of the flat gradient array.  With events
+  // enabled, backward() records one event per bucket on its stream right after the bucket's last gradient kernel, so a
+  // second stream can start the bucket's all-reduce while the rest of backward still runs.
+  struct GradBucket {
+    int64_t offset = 0, numel = 0;
+    void* event = nullptr;
+  };
+  std::vector<GradBucket> buckets;
+  bool grad_events = false;
+  void enable_grad_events(bool on);
+  void stream_wait_bucket(int bucket, lbc_stream_t s);
 };
 
 std::unique_ptr<NetBase> make_net(NetKind kind, Precision prec, int max_batch);

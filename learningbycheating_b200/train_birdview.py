@@ -58,3 +58,31 @@ def train_or_eval(criterion, net, data, optim, is_train, config, is_first_epoch)
         if is_first_epoch and i == 10:
             break
     return losses_seen
+
+
+def train(config, data_train=None, data_val=None, net=None, optim=None):
+    """train_birdview.py:155-181.  ``train(config)`` alone follows the reference (model from ``config['model_args']``, resume
+    from the newest ``model-*.th`` in ``config['log_dir']`` when ``config['resume']``, data through the dataset hook,
+    checkpoints on SAVE_EPOCHS); anything passed explicitly is used as is."""
+    import glob
+    import os
+
+    from . import _train_common as tc
+    from .birdview import BirdViewPolicyModelSS
+    from .optim import Adam
+    if data_train is None or data_val is None:
+        data_train, data_val = tc.load_data(config)
+    criterion = LocationLoss(w=192, h=192, choice='l1')
+    if net is None:
+        net = BirdViewPolicyModelSS(config['model_args']['backbone']).to(config['device'])
+        if config.get('resume'):
+            ckpts = sorted(glob.glob(os.path.join(str(config['log_dir']), 'model-*.th')),
+                           key=lambda p_: int(os.path.basename(p_)[6:-3]))
+            net.load_state_dict(torch.load(ckpts[-1], map_location=config['device']))
+    optim = optim or Adam(net.parameters(), lr=config['optimizer_args']['lr'])
+    for epoch in range(int(config['max_epoch']) + 1):
+        train_or_eval(criterion, net, data_train, optim, True, config, epoch == 0)
+        train_or_eval(criterion, net, data_val, None, False, config, epoch == 0)
+        tc.save_checkpoint(net, config, epoch, SAVE_EPOCHS)
+        _log.end_epoch()
+    return net

@@ -89,15 +89,29 @@ def train_or_eval(coord_converter, criterion, net, teacher_net, data, optim, is_
     return losses_seen
 
 
-def train(config, data_train, data_val, net, teacher_net, optim=None):
-    """train_image_phase0.py:214-242 with the data iterables, models and optimiser supplied by the caller
-    (checkpoint / LMDB / config-file I/O stay with the host application)."""
+def train(config, data_train=None, data_val=None, net=None, teacher_net=None, optim=None):
+    """train_image_phase0.py:214-242.  ``train(config)`` alone follows the reference: models from ``config['model_args']`` /
+    ``config['teacher_args']['model_path']``, data through the dataset hook (_train_common.load_data), checkpoints on
+    SAVE_EPOCHS into ``config['log_dir']``.  Anything passed explicitly (iterables, models, optimiser) is used as is."""
+    from . import _train_common as tc
+    from .birdview import BirdViewPolicyModelSS
+    from .image import ImagePolicyModelSS
     from .optim import Adam
-    criterion = LocationLoss(**config['camera_args'])
-    coord_converter = CoordConverter(**config['camera_args'])
+    if data_train is None or data_val is None:
+        data_train, data_val = tc.load_data(config)
+    criterion = LocationLoss(device=config['device'], **config['camera_args'])
+    if net is None:
+        net = ImagePolicyModelSS(config['model_args']['backbone'],
+                                 pretrained=config['model_args'].get('imagenet_pretrained', False)).to(config['device'])
+    if teacher_net is None:
+        teacher_net = BirdViewPolicyModelSS(tc.teacher_backbone(config)).to(config['device'])
+        teacher_net.load_state_dict(torch.load(config['teacher_args']['model_path'], map_location=config['device']))
+    teacher_net.eval()
+    coord_converter = CoordConverter(device=config['device'], **config['camera_args'])
     optim = optim or Adam(net.parameters(), lr=config['optimizer_args']['lr'])
     for epoch in range(int(config['max_epoch']) + 1):
         train_or_eval(coord_converter, criterion, net, teacher_net, data_train, optim, True, config, epoch == 0)
         train_or_eval(coord_converter, criterion, net, teacher_net, data_val, None, False, config, epoch == 0)
+        tc.save_checkpoint(net, config, epoch, SAVE_EPOCHS)
         _log.end_epoch()
     return net

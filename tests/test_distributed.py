@@ -42,8 +42,31 @@ def _worker(rank, world, port, out_dir):
     pred, _ = net(b["rgb"], b["speed"], oh)
     loss = p0.LocationLoss(device="cpu")(pred, tgt).mean()
     opt.zero_grad()
-    loss.backward()
-    local_grad = net._lbc.flat_grads.clone()
+    if rank == 0:       # the bucket table: contiguous ranges in backward order covering exactly the trained parameters
+        from learningbycheating_b200.distributed import grad_buckets
+        bk = grad_buckets(net)
+        assert len(bk) == 5 and bk[-1][0] == 0
+        covered = torch.zeros(net._lbc.flat_grads.numel(), dtype=torch.bool)
+        for off, n in bk:
+            assert not covered[off:off + n].any()
+            covered[off:off + n] = True
+        for p_, view, _, on_path in net._lbc.param_views:
+            o = view.storage_offset()
+            assert bool(covered[o:o + view.numel()].all()) == on_path, "bucket coverage != on-path parameters"
+    # both ranks reduce through the bucketed path (on the GPU the same buckets ride a side stream under backward)
+    local = {}
+    hook = net._lbc
+    import learningbycheating_b200.distributed as D
+    orig = D.dist.all_reduce
+
+    def spy(t, *a, **k):
+        if "g" not in local:
+            local["g"] = hook.flat_grads.clone()      # the local gradient, before the first bucket is summed
+        return orig(t, *a, **k)
+    D.dist.all_reduce = spy
+    dp.backward(loss)
+    D.dist.all_reduce = orig
+    local_grad = local["g"]
     p_before = net._lbc.flat_params.clone()
     dp.step_after_backward()
     torch.save(dict(local_grad=local_grad, summed=net._lbc.flat_grads.clone(), p_before=p_before,

@@ -249,6 +249,55 @@ def test_student_step_gpu_fp32(backend, B, phase):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "fp32tc"])
+def test_config1_plumbing_B8_gpu(backend, precision):
+    """BASELINE config 1: the reference's phase-0 loop at batch 8 -- three DIFFERENT batches through
+    train_image_phase0.train_or_eval of this package (engine + fused Adam) and through the oracle port of the reference loop
+    (training/train_image_phase0.py:152-209): same loss sequence, same final weights up to Adam's sign noise."""
+    import lbc_oracle as orc
+    import learningbycheating_b200 as lbc
+    from learningbycheating_b200 import train_image_phase0 as p0
+    B, steps = 8, 3
+    s, t = build_models("cuda", precision)
+    sd0 = {k: v.detach().cpu().clone() for k, v in s.state_dict().items()}
+    td0 = {k: v.detach().cpu().clone() for k, v in t.state_dict().items()}
+    batches = [orc.synthetic_batch(B, seed=11 + i) for i in range(steps)]
+    data = [(b["rgb"], b["birdview"], b["location"], b["command"], b["speed"]) for b in batches]
+    opt = lbc.Adam(s.parameters(), lr=1e-4)
+    t.eval()
+    ls = p0.train_or_eval(p0.CoordConverter(device="cuda"), p0.LocationLoss(device="cuda"), s, t, data, opt, True,
+                          dict(device="cuda", log_iterations=1000), False)
+    ls = [float(x) for x in ls]
+    osd, ost = orc.leafify(sd0), orc.new_adam_state()
+    ref = [float(orc.train_step(osd, td0, b["rgb"], b["birdview"], b["speed"], b["command"], 0, adam_state=ost)["loss_mean"])
+           for b in batches]
+    print("config1 B=8 [%s] loss sequence: engine %s  reference loop %s" % (precision, ["%.6f" % x for x in ls], ["%.6f" % x for x in ref]))
+    tol0 = 1e-5 if precision == "fp32" else LOSS_TOL
+    assert abs(ls[0] - ref[0]) <= tol0 * ref[0]
+    for a, b in zip(ls[1:], ref[1:]):      # later steps: Adam's first updates are lr*sign(g) -- sign noise on ~zero gradients
+        assert abs(a - b) <= 5e-3 * b
+    # final weights: the accumulated update of every trained tensor points the same way as the reference's
+    post = {k: v.detach().cpu() for k, v in s.state_dict().items()}
+    num = den_a = den_b = 0.0
+    for k, w0 in sd0.items():
+        if not w0.dtype.is_floating_point or k.endswith(("running_mean", "running_var")) or k.startswith("conv.fc"):
+            continue
+        if k.startswith("location_pred.") and (k.endswith(".0.bias") or k.endswith(".1.bias")):
+            continue                         # exactly-zero gradients (softmax shift invariance): pure rounding noise
+        da, db = (post[k] - w0).double().flatten(), (osd[k].detach() - w0).double().flatten()
+        assert float((da - db).abs().max()) <= 2.05e-4 * steps, k
+        num += float(da @ db)
+        den_a += float(da @ da)
+        den_b += float(db @ db)
+    cos = num / (den_a * den_b) ** 0.5
+    print("config1 B=8 [%s]: cosine(update, reference update) = %.5f" % (precision, cos))
+    assert cos > 0.98
+    for k in ("conv.bn1.running_mean", "conv.layer4.2.bn2.running_var", "deconv.0.running_mean"):
+        np.testing.assert_allclose(post[k].numpy(), osd[k].detach().numpy(), rtol=2e-3, atol=1e-5, err_msg=k)
+    assert int(post["conv.bn1.num_batches_tracked"]) == steps
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("B,phase", [(2, 0), (4, 0), (2, 1), (4, 1)])
 def test_student_step_gpu_fp32tc(backend, B, phase):
     """LBC_PREC_F32TC: the golden step through the tcgen05 split-precision convolutions at the north-star tolerance."""

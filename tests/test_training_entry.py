@@ -1,0 +1,47 @@
+"""train(config) with the reference's signature (training/train_image_phase0.py:214-242): models built from the config,
+teacher loaded from its checkpoint, data through the dataset hook, epoch-0 dry run, checkpoint on SAVE_EPOCHS."""
+import os
+
+import torch
+
+from lbc_testing import batch_on, build_models
+
+
+def test_train_config_reference_signature_cpu(backend, tmp_path, monkeypatch):
+    monkeypatch.setenv("LBC_B200_PRECISION", "fp32")       # models built inside train() take the package default
+    import learningbycheating_b200 as lbc
+    from learningbycheating_b200 import train_image_phase0 as p0
+    dev = backend
+    _, teacher = build_models(dev, "fp32", teacher_all_branch=False)
+    tpath = tmp_path / "teacher" / "model-128.th"
+    os.makedirs(tpath.parent)
+    torch.save(teacher.state_dict(), tpath)
+    b = batch_on("cpu", 2)
+    batch = (b["rgb"], b["birdview"], b["location"], b["command"], b["speed"])
+    calls = []
+
+    def loader(**data_args):
+        calls.append(data_args)
+        return [batch], [batch]
+
+    config = dict(log_dir=str(tmp_path / "run"), log_iterations=1000, max_epoch=1, device=torch.device(dev),
+                  optimizer_args=dict(lr=1e-4), data_args=dict(dataset_dir="unused", batch_size=2), data_loader=loader,
+                  model_args=dict(model="image_ss", imagenet_pretrained=False, backbone="resnet34"),
+                  camera_args=dict(w=384, h=160, fov=90, world_y=1.4, fixed_offset=4.0),
+                  teacher_args=dict(model_path=str(tpath)))
+    torch.manual_seed(0)
+    net = p0.train(config)
+    assert calls == [dict(dataset_dir="unused", batch_size=2)]
+    assert isinstance(net, lbc.ImagePolicyModelSS)
+    # epoch 0 is the reference's dry run (no optimizer step), epoch 1 trains once: one BN update per train-mode forward
+    assert int(net.conv.bn1.num_batches_tracked) == 2
+    ck = tmp_path / "run" / "model-1.th"
+    assert ck.exists()
+    sd = torch.load(ck)
+    assert list(sd.keys()) == list(net.state_dict().keys())
+    # without a dataset the entry point says so instead of guessing
+    import pytest
+    cfg2 = dict(config)
+    cfg2.pop("data_loader")
+    with pytest.raises(lbc.LbcError, match="no dataset"):
+        p0.train(cfg2)
