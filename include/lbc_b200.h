@@ -144,10 +144,14 @@ int lbc_op_conv_wgrad(const float* x, const float* dy, float* dw_ref, int N, int
                       int stride, int pad, int precision, void* stream);
 int lbc_op_bn_train(const float* x, const float* gamma, const float* beta, const float* residual, int relu,
                     float* y, float* mean, float* var, int64_t M, int C, int precision, float* running_mean,
-                    float* running_var, float* negshift, void* stream);
+                    float* running_var, float* negshift, uint8_t* mask_bits_out, void* stream);
+/* use_mask_bits (bf16 path): hand the mask to the kernels as one bit per element ([M][C/8] bytes, the format
+ * lbc_op_bn_train's mask_bits_out has) instead of the activation tensor */
 int lbc_op_bn_bwd(const float* dy, const float* x, const float* gamma, float* dgamma, float* dbeta, float* dx,
-                  int64_t M, int C, int precision, const float* mask_act, const float* beta, int own_relu, void* stream);
-int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mode, int precision, void* stream);
+                  int64_t M, int C, int precision, const float* mask_act, const float* beta, int own_relu, int use_mask_bits,
+                  void* stream);
+int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mode, int precision, int use_mask_bits,
+              void* stream);
 int lbc_op_maxpool(const float* x, float* y, const float* dy, float* dx, int N, int H, int W, int C, void* stream);
 int lbc_op_bn_relu_maxpool(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                            float* y, const float* dy, float* dx, int N, int H, int W, int C, int precision, void* stream);

@@ -481,14 +481,14 @@ int lbc_op_conv_wgrad(const float* x, const float* dy, float* dw_ref, int N, int
 // replaced by -(batch mean of the true x).
 int lbc_op_bn_train(const float* x, const float* gamma, const float* beta, const float* residual, int relu,
                     float* y, float* mean, float* var, int64_t M, int C, int precision, float* running_mean,
-                    float* running_var, float* negshift, void* stream) {
+                    float* running_var, float* negshift, uint8_t* mask_bits_out, void* stream) {
   return guarded([&] {
     require_device();
     lbc_stream_t s = S(stream);
     Tmp t;
     float* rstd = t.get<float>(C);
     if (precision == PREC_F32) {
-      LBC_CHECK(!negshift, "lbc_op_bn_train: the centring shift exists on the bf16 path only");
+      LBC_CHECK(!negshift && !mask_bits_out, "lbc_op_bn_train: centring shift / mask bits exist on the bf16 path only");
       double* ws = t.get<double>(1 << 20);
       ref::bn_stats<float>(s, x, M, C, mean, var, ws);
       ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, running_mean, running_var);
@@ -503,8 +503,8 @@ int lbc_op_bn_train(const float* x, const float* gamma, const float* beta, const
       ref::cast<float, bf16>(s, x, xb, n);
       if (residual) ref::cast<float, bf16>(s, residual, rb, n);
       if (!fast::Fast<bf16>::bn_fwd(xb, M, C, gamma, beta, 1e-5f, 0.1f, rm, rv, mean, rstd, rb, relu != 0, true, yb, sums,
-                                    negshift, s)) {
-        LBC_CHECK(!negshift, "lbc_op_bn_train: centring shift requested but the fast kernels did not run");
+                                    negshift, s, 0, mask_bits_out)) {
+        LBC_CHECK(!negshift && !mask_bits_out, "lbc_op_bn_train: centring shift / mask bits requested but the fast kernels did not run");
         double* ws = t.get<double>(1 << 20);
         ref::bn_stats<bf16>(s, xb, M, C, mean, var, ws);
         ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, rm, rv);
@@ -521,7 +521,8 @@ int lbc_op_bn_train(const float* x, const float* gamma, const float* beta, const
 // (mask_act > 0) -- the in-place ReLU that follows the BN; own_relu != 0: that activation is relu(bn(x)) of this very BN
 // (beta required), which the fast kernels recompute from x instead of reading mask_act.
 int lbc_op_bn_bwd(const float* dy, const float* x, const float* gamma, float* dgamma, float* dbeta, float* dx,
-                  int64_t M, int C, int precision, const float* mask_act, const float* beta, int own_relu, void* stream) {
+                  int64_t M, int C, int precision, const float* mask_act, const float* beta, int own_relu, int use_mask_bits,
+                  void* stream) {
   return guarded([&] {
     require_device();
     lbc_stream_t s = S(stream);
@@ -543,9 +544,15 @@ int lbc_op_bn_bwd(const float* dy, const float* x, const float* gamma, float* dg
       ref::cast<float, bf16>(s, x, xb, n);
       ref::cast<float, bf16>(s, dy, dyb, n);
       if (mask_act) ref::cast<float, bf16>(s, mask_act, mb, n);
+      uint8_t* bits = nullptr;
+      if (use_mask_bits && mask_act && !own_relu) {   // the mask as the bits bn_apply_kernel writes for the block-final ReLU
+        bits = t.get<uint8_t>(n / 8);
+        ref::pack_mask_bits<bf16>(s, mb, bits, n / 8);
+      }
       ref::bn_stats<bf16>(s, xb, M, C, mean, var, ws);
       ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, nullptr, nullptr);
-      if (!fast::Fast<bf16>::bn_bwd(dyb, mb, xb, mean, rstd, gamma, dgamma, dbeta, dxb, M, C, sums, s, own_relu ? beta : nullptr)) {
+      if (!fast::Fast<bf16>::bn_bwd(dyb, mb, xb, mean, rstd, gamma, dgamma, dbeta, dxb, M, C, sums, s, own_relu ? beta : nullptr,
+                                    bits)) {
         if (mb) ref::relu_mask_inplace<bf16>(s, dyb, mb, n);
         ref::bn_bwd<bf16>(s, dyb, xb, mean, rstd, gamma, dgamma, dbeta, dxb, M, C, ws);
       }
@@ -555,7 +562,8 @@ int lbc_op_bn_bwd(const float* dy, const float* x, const float* gamma, float* dg
   });
 }
 // masked adds of the residual backward: mode 0 dst += src; 1 dst += src*(act>0); 2 dst *= (act>0)
-int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mode, int precision, void* stream) {
+int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mode, int precision, int use_mask_bits,
+              void* stream) {
   return guarded([&] {
     require_device();
     lbc_stream_t s = S(stream);
@@ -570,7 +578,12 @@ int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mod
       ref::cast<float, bf16>(s, dst, d, n);
       if (src) ref::cast<float, bf16>(s, src, sr, n);
       if (act) ref::cast<float, bf16>(s, act, a, n);
-      if (!fast::Fast<bf16>::ew(d, sr, a, n, mode, s)) {
+      uint8_t* bits = nullptr;
+      if (use_mask_bits && act && mode != 0) {
+        bits = t.get<uint8_t>(n / 8);
+        ref::pack_mask_bits<bf16>(s, a, bits, n / 8);
+      }
+      if (!fast::Fast<bf16>::ew(d, sr, a, n, mode, s, bits)) {
         if (mode == 0) ref::add_inplace<bf16>(s, d, sr, n);
         else if (mode == 1) ref::add_masked_inplace<bf16>(s, d, sr, a, n);
         else ref::relu_mask_inplace<bf16>(s, d, a, n);

@@ -107,11 +107,14 @@ bool tc_stem_im2col(const float* x0, void* col16, int B, int C, int H, int W, in
 bool bn_stats_bf16(const bf16* x, int64_t M, int C, float* sums, lbc_stream_t s);
 bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
-                   const bf16* residual, bool relu, bool train, bf16* y, float* negshift, lbc_stream_t s);
+                   const bf16* residual, bool relu, bool train, bf16* y, float* negshift, lbc_stream_t s,
+                   uint8_t* maskbits = nullptr);   // maskbits [M][C/8]: also emit (y > 0) as one bit per element
+// beta_own: mask_act is relu(this BN's output) -> recomputed from x.  mask_bits: the (act > 0) mask as the bits bn_apply_bf16
+// wrote (16x fewer bytes than reading the activation; mask_act is then only a flag)
 bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
                  const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s,
-                 const float* beta_own = nullptr);   // beta_own: mask_act is relu(this BN's output) -> recomputed from x
-bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s);
+                 const float* beta_own = nullptr, const uint8_t* mask_bits = nullptr);
+bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s, const uint8_t* mask_bits = nullptr);
 bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           bf16* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, lbc_stream_t s);
 bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
@@ -121,10 +124,10 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
 // generic-T front ends: only T = bf16 has fast kernels
 template <class T> struct Fast {
   static bool bn_fwd(const T*, int64_t, int, const float*, const float*, float, float, float*, float*, float*, float*,
-                     const T*, bool, bool, T*, float*, float*, lbc_stream_t, int = 0) { return false; }
+                     const T*, bool, bool, T*, float*, float*, lbc_stream_t, int = 0, uint8_t* = nullptr) { return false; }
   static bool bn_bwd(const T*, const T*, const T*, const float*, const float*, const float*, float*, float*, T*, int64_t, int,
-                     float*, lbc_stream_t, const float* = nullptr) { return false; }
-  static bool ew(T*, const T*, const T*, int64_t, int, lbc_stream_t) { return false; }
+                     float*, lbc_stream_t, const float* = nullptr, const uint8_t* = nullptr) { return false; }
+  static bool ew(T*, const T*, const T*, int64_t, int, lbc_stream_t, const uint8_t* = nullptr) { return false; }
   static bool colsum(const T*, int64_t, int, float*, float*, lbc_stream_t) { return false; }
   static bool pool_fwd(const T*, const float*, const float*, const float*, const float*, T*, uint8_t*, int, int, int, int, int,
                        int, lbc_stream_t) { return false; }
@@ -135,7 +138,7 @@ template <> struct Fast<bf16> {
   // train: statistics + apply (two launches); eval: apply with the running statistics.  sums: >= 2C floats scratch
   static bool bn_fwd(const bf16* x, int64_t M, int C, const float* gamma, const float* beta, float eps, float momentum,
                      float* rm, float* rv, float* saved_mean, float* saved_rstd, const bf16* res, bool relu, bool train,
-                     bf16* y, float* sums, float* negshift, lbc_stream_t s, int conv_stat_rows = 0) {
+                     bf16* y, float* sums, float* negshift, lbc_stream_t s, int conv_stat_rows = 0, uint8_t* maskbits = nullptr) {
     if (!enabled()) return false;
     if (train && conv_stat_rows > 0) {   // statistics partials already written by the producing conv's epilogue
       if (!col_finalize_bf16(stat_partial_buffer(), conv_stat_rows, 2 * C, sums, s)) return false;
@@ -143,17 +146,17 @@ template <> struct Fast<bf16> {
       return false;
     }
     return bn_apply_bf16(x, sums, M, C, gamma, beta, eps, momentum, rm, rv, saved_mean, saved_rstd, res, relu, train, y,
-                         negshift, s);
+                         negshift, s, maskbits);
   }
   static bool bn_bwd(const bf16* dy, const bf16* mask, const bf16* x, const float* mean, const float* rstd, const float* gamma,
                      float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s,
-                     const float* beta_own = nullptr) {
+                     const float* beta_own = nullptr, const uint8_t* mask_bits = nullptr) {
     if (!enabled()) return false;
-    return bn_bwd_bf16(dy, mask, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, sums, s, beta_own);
+    return bn_bwd_bf16(dy, mask, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, sums, s, beta_own, mask_bits);
   }
-  static bool ew(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s) {
+  static bool ew(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s, const uint8_t* mask_bits = nullptr) {
     if (!enabled()) return false;
-    return ew_bf16(dst, src, act, n, mode, s);
+    return ew_bf16(dst, src, act, n, mode, s, mask_bits);
   }
   // column sums (deconv bias gradient) = first half of the BN statistics kernel's output
   static bool colsum(const bf16* x, int64_t M, int C, float* out_via_sums, float* sums, lbc_stream_t s) {

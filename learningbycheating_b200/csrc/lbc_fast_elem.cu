@@ -32,6 +32,18 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return v;
 }
+// bit j = (bf16 element j of v > 0)
+__device__ __forceinline__ uint8_t positive_bits(const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t b = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+    b |= (uint32_t)((lo & 0x7fffu) != 0 && !(lo & 0x8000u)) << (2 * i);
+    b |= (uint32_t)((hi & 0x7fffu) != 0 && !(hi & 0x8000u)) << (2 * i + 1);
+  }
+  return (uint8_t)b;
+}
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -207,6 +219,7 @@ struct BnApplyArgs {
   float* saved_mean;
   float* saved_rstd;
   float* negshift;     // x holds (conv output + negshift[c]); null = no centring shift
+  uint8_t* maskbits;   // optional [M][C/8]: bit j of byte (row, channel group) = (stored output channel 8g+j > 0)
   int64_t M;
   int C, tpr, rpi;
   float eps, momentum;
@@ -269,7 +282,9 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const BnApplyArgs a) {
       if (a.relu) v = fmaxf(v, 0.f);
       f[j] = v;
     }
-    a.y[i0] = pack8(f);
+    const uint4 o0 = pack8(f);
+    a.y[i0] = o0;
+    if (a.maskbits) a.maskbits[i0] = positive_bits(o0);
     if (has1) {
       unpack8(v1, f);
       if (a.res) unpack8(r1, g);
@@ -280,18 +295,21 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const BnApplyArgs a) {
         if (a.relu) v = fmaxf(v, 0.f);
         f[j] = v;
       }
-      a.y[i1] = pack8(f);
+      const uint4 o1 = pack8(f);
+      a.y[i1] = o1;
+      if (a.maskbits) a.maskbits[i1] = positive_bits(o1);
     }
   }
 }
 
 bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
-                   const bf16* residual, bool relu, bool train, bf16* y, float* negshift, lbc_stream_t s) {
+                   const bf16* residual, bool relu, bool train, bf16* y, float* negshift, lbc_stream_t s, uint8_t* maskbits) {
   if (C % 8 || C > 2560) return false;
   RowGeom g = row_geom(M, C, 8);
   BnApplyArgs a;
   a.negshift = negshift;
+  a.maskbits = maskbits;
   a.x = (const uint4*)x;
   a.res = (const uint4*)residual;
   a.y = (uint4*)y;
@@ -318,12 +336,14 @@ bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const flo
 
 // ------------------------------------------------------------------------------------------- BN backward
 // pass 1: sums[0..C) += sum dy_m ; sums[C..2C) += sum dy_m * xhat,  dy_m = dy * (act > 0) when act != null
+// (mbits != null: the mask comes as one byte per (row, 8 channels) written by bn_apply_kernel instead of the activation)
 template <bool OWN>
 __global__ void __launch_bounds__(256, OWN ? 3 : 4) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
                                                             const uint4* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, int64_t M, int tpr, int rpi,
                                                             float* partial, int C, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta_own) {
+                                                            const float* __restrict__ beta_own,
+                                                            const uint8_t* __restrict__ mbits) {
   extern __shared__ float red[];
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
@@ -343,7 +363,9 @@ __global__ void __launch_bounds__(256, OWN ? 3 : 4) bn_bwd_reduce_kernel(const u
     const int64_t i0 = row * tpr + cg;
     const uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
     uint4 a0 = d0;
-    if (!OWN && act) a0 = ldg_stream(act + i0);
+    uint32_t mb = 0xffu;
+    if (!OWN && mbits) mb = __ldg(mbits + i0);
+    else if (!OWN && act) a0 = ldg_stream(act + i0);
     float fd[8], fx[8], fa[8];
     unpack8(d0, fd);
     unpack8(x0, fx);
@@ -352,6 +374,7 @@ __global__ void __launch_bounds__(256, OWN ? 3 : 4) bn_bwd_reduce_kernel(const u
     for (int j = 0; j < 8; ++j) {
       if (OWN) fa[j] = fx[j] * sc[j] + sh[j];
       float g = ((OWN || act) && !(fa[j] > 0.f)) ? 0.f : fd[j];
+      if (!OWN && !((mb >> j) & 1u)) g = 0.f;
       s0[j] += g;
       s1[j] += g * (fx[j] - mu[j]);
     }
@@ -386,7 +409,8 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ sums, float* dgamma, float* dbeta,
                                                            uint4* __restrict__ dx, int64_t M, int tpr, int rpi, int C,
-                                                           const float* __restrict__ beta_own) {
+                                                           const float* __restrict__ beta_own,
+                                                           const uint8_t* __restrict__ mbits) {
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
   // dx = k0*(g - db/M - xhat*dg/M) = k0*g + kb*x + ka,  kb = -k0*rstd*dg/M,  ka = -k0*db/M - kb*mean
@@ -413,7 +437,9 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
     const int64_t i0 = row * tpr + cg;
     const uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
     uint4 a0 = d0;
-    if (!OWN && act) a0 = ldg_stream(act + i0);
+    uint32_t mb = 0xffu;
+    if (!OWN && mbits) mb = __ldg(mbits + i0);
+    else if (!OWN && act) a0 = ldg_stream(act + i0);
     float fd[8], fx[8], fa[8], o[8];
     unpack8(d0, fd);
     unpack8(x0, fx);
@@ -422,6 +448,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
     for (int j = 0; j < 8; ++j) {
       if (OWN) fa[j] = fx[j] * k0[j] + sh[j];
       float g = ((OWN || act) && !(fa[j] > 0.f)) ? 0.f : fd[j];
+      if (!OWN && !((mb >> j) & 1u)) g = 0.f;
       o[j] = fmaf(k0[j], g, fmaf(kb[j], fx[j], ka[j]));
     }
     dx[i0] = pack8(o);
@@ -430,34 +457,36 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
 
 bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
                  const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s,
-                 const float* beta_own) {
+                 const float* beta_own, const uint8_t* mask_bits) {
   if (C % 8 || C > 2560) return false;
   static const bool recompute = [] {
     const char* e = getenv("LBC_BN_MASK_RECOMPUTE");
     return e ? atoi(e) != 0 : true;
   }();
   if (!recompute || !mask_act) beta_own = nullptr;
+  if (beta_own) mask_bits = nullptr;
   RowGeom g = row_geom(M, C, 4);
   float* part = partial_buffer();
   if (!part) return false;
   if (beta_own) {
     RowGeom g3 = row_geom(M, C, 3);
     bn_bwd_reduce_kernel<true><<<g3.grid, g3.threads, g3.threads * 16 * sizeof(float), s>>>(
-        (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g3.tpr, g3.rpi, part, C, gamma, beta_own);
+        (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g3.tpr, g3.rpi, part, C, gamma, beta_own, nullptr);
     LBC_LAUNCHED("bn_bwd_reduce_kernel<own>");
     col_finalize(part, g3.grid, 2 * C, sums, s);
     bn_bwd_apply_kernel<true><<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd,
-                                                          gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own);
+                                                          gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own, nullptr);
     LBC_LAUNCHED("bn_bwd_apply_kernel<own>");
     LBC_CUDA(cudaGetLastError());
     return true;
   }
+  if (mask_bits) mask_act = nullptr;   // the bits replace the activation read
   bn_bwd_reduce_kernel<false><<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
-      (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, gamma, beta_own);
+      (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, gamma, beta_own, mask_bits);
   LBC_LAUNCHED("bn_bwd_reduce_kernel");
   col_finalize(part, g.grid, 2 * C, sums, s);
   bn_bwd_apply_kernel<false><<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd,
-                                                         gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own);
+                                                         gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own, mask_bits);
   LBC_LAUNCHED("bn_bwd_apply_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -465,14 +494,22 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
 
 // ------------------------------------------------------------------------------------------- elementwise
 // mode 0: dst = dst + src ; mode 1: dst = dst + src*(act>0) ; mode 2: dst = dst*(act>0) (src ignored)
+// (mbits != null: the mask is one byte per 8 elements, as written by bn_apply_kernel, instead of the activation)
 __global__ void __launch_bounds__(256) ew_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
-                                                 const uint4* __restrict__ act, int64_t n, int mode) {
+                                                 const uint4* __restrict__ act, int64_t n, int mode,
+                                                 const uint8_t* __restrict__ mbits) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float a[8], b[8], m[8];
     unpack8(dst[i], a);
     if (mode != 2) unpack8(ldg_stream(src + i), b);
-    if (mode != 0) unpack8(ldg_stream(act + i), m);
+    if (mbits) {
+      const uint32_t mb = __ldg(mbits + i);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = ((mb >> j) & 1u) ? 1.f : 0.f;
+    } else if (mode != 0) {
+      unpack8(ldg_stream(act + i), m);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (mode == 0) a[j] += b[j];
@@ -482,13 +519,14 @@ __global__ void __launch_bounds__(256) ew_kernel(uint4* __restrict__ dst, const 
     dst[i] = pack8(a);
   }
 }
-bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s) {
+bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s, const uint8_t* mask_bits) {
   if (n % 8) return false;
+  if (mode == 0) mask_bits = nullptr;
   int64_t nv = n / 8;
   int64_t blocks = (nv + 255) / 256;
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
-  ew_kernel<<<(unsigned)blocks, 256, 0, s>>>((uint4*)dst, (const uint4*)src, (const uint4*)act, nv, mode);
+  ew_kernel<<<(unsigned)blocks, 256, 0, s>>>((uint4*)dst, (const uint4*)src, (const uint4*)act, nv, mode, mask_bits);
   LBC_LAUNCHED("ew_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -579,13 +617,18 @@ bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, c
 }
 // d(bn-relu output)[n,h,w,:] = sum over the <=4 pooling windows that selected (h,w), times the ReLU mask recomputed
 // from the raw conv output; written as the upstream gradient of the stem BatchNorm.
+// One thread owns a 2x2 block of input pixels (x 8 channels): the four pixels are touched by exactly the four windows
+// (ph|ph+1, pw|pw+1), with FIXED tap codes per (pixel, window) -- so every thread runs the same nine compare-adds and loads
+// each window once.  (Round 1's one-pixel-per-thread kernel looked at up to nine (kh, kw) candidates per pixel with
+// parity-dependent branches that diverged inside every warp: 518 us for 1.19 GB at B = 256.)
 template <typename IdxT>
 __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
                                                                const uint4* __restrict__ x, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, uint4* __restrict__ dx, int N,
                                                                int H, int W, int tpr, int OH, int OW) {
-  const IdxT total = (IdxT)N * H * W * tpr;
+  const int H2 = H >> 1, W2 = W >> 1;
+  const IdxT total = (IdxT)N * H2 * W2 * tpr;
   const IdxT stride = (IdxT)gridDim.x * blockDim.x;   // multiple of tpr
   IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = (int)(i % (IdxT)tpr);
@@ -598,57 +641,69 @@ __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __re
   }
   for (; i < total; i += stride) {
     IdxT p = i / (IdxT)tpr;
-    const int iw = (int)(p % (IdxT)W);
-    p /= (IdxT)W;
-    const int ih = (int)(p % (IdxT)H);
-    const int b = (int)(p / (IdxT)H);
-    float acc[8];
+    const int pw = (int)(p % (IdxT)W2);
+    p /= (IdxT)W2;
+    const int ph = (int)(p % (IdxT)H2);
+    const int b = (int)(p / (IdxT)H2);
+    float acc[2][2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+      for (int b2 = 0; b2 < 2; ++b2)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[a2][b2][j] = 0.f;
     const int64_t ob = (int64_t)b * OH * OW * tpr + cg;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int t = ih + 1 - kh;
-      if (t < 0 || (t & 1)) continue;
-      const int oh = t >> 1;
+    for (int wy = 0; wy < 2; ++wy) {
+      const int oh = ph + wy;
       if (oh >= OH) continue;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int u = iw + 1 - kw;
-        if (u < 0 || (u & 1)) continue;
-        const int ow = u >> 1;
+      for (int wx = 0; wx < 2; ++wx) {
+        const int ow = pw + wx;
         if (ow >= OW) continue;
-        const int64_t o = ob + (oh * OW + ow) * tpr;
+        const int64_t o = ob + ((int64_t)oh * OW + ow) * tpr;
         const uint2 id = __ldg(idx + o);
         float g[8];
         unpack8(__ldg(dy + o), g);
-        const uint32_t want = (uint32_t)(kh * 3 + kw);
+        // window (ph+wy, pw+wx) covers pixel (a2, b2) of this block with tap kh = 1 + a2 - 2*wy, kw = 1 + b2 - 2*wx
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t sel = ((j < 4 ? id.x : id.y) >> ((j & 3) * 8)) & 0xffu;
-          if (sel == want) acc[j] += g[j];
-        }
+        for (int a2 = wy; a2 < 2; ++a2)
+#pragma unroll
+          for (int b2 = wx; b2 < 2; ++b2) {
+            const uint32_t want = (uint32_t)((1 + a2 - 2 * wy) * 3 + (1 + b2 - 2 * wx));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t sel = ((j < 4 ? id.x : id.y) >> ((j & 3) * 8)) & 0xffu;
+              if (sel == want) acc[a2][b2][j] += g[j];
+            }
+          }
       }
     }
-    float f[8];
-    unpack8(ldg_stream(x + i), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float v = f[j] * sc[j] + sh[j];
-      if (!(v > 0.f)) acc[j] = 0.f;
-    }
-    dx[i] = pack8(acc);
+    for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+      for (int b2 = 0; b2 < 2; ++b2) {
+        const int64_t e = (((int64_t)b * H + (2 * ph + a2)) * W + (2 * pw + b2)) * tpr + cg;
+        float f[8];
+        unpack8(ldg_stream(x + e), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = f[j] * sc[j] + sh[j];
+          if (!(v > 0.f)) acc[a2][b2][j] = 0.f;
+        }
+        dx[e] = pack8(acc[a2][b2]);
+      }
   }
 }
 bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, bf16* dx, int N, int H, int W, int C, int OH, int OW,
                            lbc_stream_t s) {
-  if (C % 8 || 256 % (C / 8)) return false;
-  int64_t total = (int64_t)N * H * W * (C / 8);
+  if (C % 8 || 256 % (C / 8) || (H & 1) || (W & 1)) return false;
+  int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
-  if (total < (int64_t)1 << 31)
+  if ((int64_t)N * H * W * (C / 8) < (int64_t)1 << 31)
     maxpool_relu_bwd_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean,
                                                                         rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW);
   else
@@ -662,10 +717,10 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
 #else  // LBC_HOST_EMU
 bool bn_stats_bf16(const bf16*, int64_t, int, float*, lbc_stream_t) { return false; }
 bool bn_apply_bf16(const bf16*, const float*, int64_t, int, const float*, const float*, float, float, float*, float*, float*,
-                   float*, const bf16*, bool, bool, bf16*, float*, lbc_stream_t) { return false; }
+                   float*, const bf16*, bool, bool, bf16*, float*, lbc_stream_t, uint8_t*) { return false; }
 bool bn_bwd_bf16(const bf16*, const bf16*, const bf16*, const float*, const float*, const float*, float*, float*, bf16*,
-                 int64_t, int, float*, lbc_stream_t, const float*) { return false; }
-bool ew_bf16(bf16*, const bf16*, const bf16*, int64_t, int, lbc_stream_t) { return false; }
+                 int64_t, int, float*, lbc_stream_t, const float*, const uint8_t*) { return false; }
+bool ew_bf16(bf16*, const bf16*, const bf16*, int64_t, int, lbc_stream_t, const uint8_t*) { return false; }
 float* stat_partial_buffer() { return nullptr; }
 int64_t stat_partial_capacity() { return 0; }
 bool col_finalize_bf16(const float*, int, int, float*, lbc_stream_t) { return false; }

@@ -62,6 +62,9 @@ class Net : public NetBase {
     bool ds = false;
     int Cin, Cout, Hin, Win, Hout, Wout;
     T *r1 = nullptr, *a1 = nullptr, *r2 = nullptr, *rd = nullptr, *idn = nullptr, *out = nullptr;
+    bool obits_ok = false;
+    uint8_t* obits = nullptr;   // bf16 path: (out > 0) as one bit per element, written by bn2's apply kernel; the three
+                                // backward consumers of that mask read 1/16 of the bytes of `out`
     const T* xin = nullptr;
     std::string name;
   };
@@ -102,6 +105,7 @@ class Net : public NetBase {
   float* head_fold = nullptr;  // folded BN+1x1 map A[20][64], b'[20]; coef c0/c1 [128]
   bool stem_pool_fused = false;
   // PREC_F32TC (T = float): convolutions on the tensor cores with split-precision operands
+  bool mask_bits_valid = false;   // the last bn_forward call wrote its mask bits (fast bf16 path)
   bool tc = false;
   fast::TcWork tcw;
   bool stem_tc_used = false;
@@ -294,6 +298,7 @@ class Net : public NetBase {
         b.a1 = alloc<T>(ne);
         b.r2 = alloc<T>(ne);
         b.out = alloc<T>(ne);
+        if (std::is_same<T, bf16>::value) b.obits = alloc<uint8_t>(ne / 8);
         if (b.ds) {
           b.rd = alloc<T>(ne);
           b.idn = alloc<T>(ne);
@@ -532,13 +537,16 @@ class Net : public NetBase {
     ref::conv_wgrad<T>(s, x, dy, G + c.w_off, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, ws_f, ws_f_n);
   }
   void bn_forward(BNL& bn, const T* x, int64_t M, const T* residual, bool relu, T* y, bool train, lbc_stream_t s,
-                  bool shifted = false, int conv_stat_rows = 0) {
+                  bool shifted = false, int conv_stat_rows = 0, uint8_t* maskbits = nullptr) {
     // algorithmic bytes: stats read (train) + apply read (+residual) + write
     ProfScope ps("bn_fwd", s, 0, (double)M * bn.C * sizeof(T) * ((train && conv_stat_rows == 0 ? 1 : 0) + 2 + (residual ? 1 : 0)));
     if (fast::Fast<T>::bn_fwd(x, M, bn.C, P + bn.g_off, P + bn.b_off, kBnEps, kBnMomentum, BUF + bn.rm_off, BUF + bn.rv_off,
                               bn.mean, bn.rstd, residual, relu, train, y, bn_sums, shifted ? bn.negshift : nullptr, s,
-                              conv_stat_rows))
+                              conv_stat_rows, maskbits)) {
+      mask_bits_valid = maskbits != nullptr;
       return;
+    }
+    mask_bits_valid = false;
     LBC_CHECK(conv_stat_rows == 0, "BatchNorm fast path unavailable after a statistics-emitting convolution");
     LBC_CHECK(!shifted, "BatchNorm fast path unavailable after a shifted convolution");
     if (train) {
@@ -553,11 +561,12 @@ class Net : public NetBase {
   // Correctness-first path: masks dy in place first; fast path: the mask is fused into both passes, dy untouched.
   // own_relu: mask_act is relu(bn(x)) of this very BatchNorm (no residual): the fast kernels then recompute the mask
   // from x instead of reading the activation (2 of the 7 tensor passes disappear).
-  void bn_backward(BNL& bn, T* dy, const T* mask_act, const T* x, T* dx, int64_t M, lbc_stream_t s, bool own_relu = false) {
-    // algorithmic bytes: reduce pass reads dy,(mask),x ; apply pass reads dy,(mask),x writes dx
-    ProfScope ps("bn_bwd", s, 0, (double)M * bn.C * sizeof(T) * (5 + (mask_act && !own_relu ? 2 : 0)));
+  void bn_backward(BNL& bn, T* dy, const T* mask_act, const T* x, T* dx, int64_t M, lbc_stream_t s, bool own_relu = false,
+                   const uint8_t* mask_bits = nullptr) {
+    // algorithmic bytes: reduce pass reads dy,(mask),x ; apply pass reads dy,(mask),x writes dx (mask as bits: 1/16 pass each)
+    ProfScope ps("bn_bwd", s, 0, (double)M * bn.C * sizeof(T) * (5 + (mask_act && !own_relu ? (mask_bits ? 0.125 : 2) : 0)));
     if (fast::Fast<T>::bn_bwd(dy, mask_act, x, bn.mean, bn.rstd, P + bn.g_off, G + bn.g_off, G + bn.b_off, dx, M, bn.C,
-                              bn_sums, s, own_relu ? P + bn.b_off : nullptr))
+                              bn_sums, s, own_relu ? P + bn.b_off : nullptr, mask_bits))
       return;
     if (mask_act) ref::relu_mask_inplace<T>(s, dy, mask_act, M * bn.C);
     ref::bn_bwd<T>(s, dy, x, bn.mean, bn.rstd, P + bn.g_off, G + bn.g_off, G + bn.b_off, dx, M, bn.C, ws_d);
@@ -567,9 +576,9 @@ class Net : public NetBase {
     if (fast::Fast<T>::ew(g, nullptr, act, n, 2, s)) return;
     ref::relu_mask_inplace<T>(s, g, act, n);
   }
-  void add_masked(T* dst, const T* g, const T* act, int64_t n, lbc_stream_t s) {
-    ProfScope ps("elementwise", s, 0, (double)n * sizeof(T) * 4);
-    if (fast::Fast<T>::ew(dst, g, act, n, 1, s)) return;
+  void add_masked(T* dst, const T* g, const T* act, int64_t n, lbc_stream_t s, const uint8_t* mask_bits = nullptr) {
+    ProfScope ps("elementwise", s, 0, (double)n * sizeof(T) * (mask_bits ? 3.0625 : 4));
+    if (fast::Fast<T>::ew(dst, g, act, n, 1, s, mask_bits)) return;
     ref::add_masked_inplace<T>(s, dst, g, act, n);
   }
   HeadCtx hc;
@@ -691,7 +700,8 @@ class Net : public NetBase {
         identity = b.idn;
       }
       bool sh2 = conv_forward(b.c2, b.a1, b.r2, B, s, b.b2.negshift, &sr);
-      bn_forward(b.b2, b.r2, M, identity, true, b.out, train, s, sh2, sr);
+      bn_forward(b.b2, b.r2, M, identity, true, b.out, train, s, sh2, sr, train ? b.obits : nullptr);
+      b.obits_ok = mask_bits_valid;
     }
     // late fusion of speed (image.py:77-79)
     const T* trunk = blocks.back().out;
@@ -802,13 +812,14 @@ class Net : public NetBase {
       int64_t M = (int64_t)B * b.Hout * b.Wout;
       int64_t ne = M * b.Cout;
       // gcur = d(out); the block-final ReLU mask (out > 0) is applied inside every consumer of gcur
-      bn_backward(b.b2, gcur, b.out, b.r2, tA, M, s);  // tA = d r2
+      const uint8_t* ob = b.obits_ok ? b.obits : nullptr;
+      bn_backward(b.b2, gcur, b.out, b.r2, tA, M, s, false, ob);  // tA = d r2
       conv_backward_weight(b.c2, b.a1, tA, B, s);
       conv_backward_data(b.c2, tA, tB, B, false, s);   // tB = d a1 (before the ReLU mask a1 > 0)
       bn_backward(b.b1, tB, b.a1, b.r1, tA, M, s, true);   // tA = d r1 (mask a1 > 0 recomputed from r1)
       conv_backward_weight(b.c1, b.xin, tA, B, s);
       if (b.ds) {
-        bn_backward(b.bd, gcur, b.out, b.rd, tB, M, s);  // tB = d rd (d a1 is dead by now)
+        bn_backward(b.bd, gcur, b.out, b.rd, tB, M, s, false, ob);  // tB = d rd (d a1 is dead by now)
         conv_backward_weight(b.cd, b.xin, tB, B, s);
         bool fused = false;
         {
@@ -825,7 +836,7 @@ class Net : public NetBase {
         }
       } else {
         conv_backward_data(b.c1, tA, gnext, B, false, s);  // gnext = d xin (main path)
-        add_masked(gnext, gcur, b.out, ne, s);
+        add_masked(gnext, gcur, b.out, ne, s, ob);
       }
       std::swap(gcur, gnext);
       // a stage is complete when its entry block (the one with the downsample branch) has been differentiated

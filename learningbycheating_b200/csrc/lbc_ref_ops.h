@@ -457,6 +457,16 @@ inline void bn_finalize_sums(lbc_stream_t s, const float* sums, int C, int64_t M
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * ((double)M / (double)(M > 1 ? M - 1 : 1)));
   });
 }
+// bits[i] = (act[8i+j] > 0) in bit j: the mask format bn_apply_kernel emits on the bf16 path (tests build it from an activation)
+struct k_mask_bits;
+template <class T>
+void pack_mask_bits(lbc_stream_t s, const T* act, uint8_t* bits, int64_t n8) {
+  par_for<k_mask_bits>(s, n8, [=] LBC_LAMBDA(int64_t i) {
+    unsigned b = 0;
+    for (int j = 0; j < 8; ++j) b |= (unsigned)(ldf(act, i * 8 + j) > 0.f) << j;
+    bits[i] = (uint8_t)b;
+  });
+}
 struct k_rstd_to_var;
 inline void rstd_to_var(lbc_stream_t s, const float* rstd, float* var_biased, int C, float eps) {
   par_for<k_rstd_to_var>(s, C, [=] LBC_LAMBDA(int64_t c) { var_biased[c] = 1.0f / (rstd[c] * rstd[c]) - eps; });

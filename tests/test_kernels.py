@@ -86,11 +86,16 @@ def _bn_fwd_case(dev, M, C, relu, with_res, precision, shift):
     xd, gd, bd, rd = d(xs), d(gamma), d(beta), d(res)
     rm, rv, nsd = d(rm0.clone()), d(rv0.clone()), d(ns)
     y, mean, var = torch.empty(M, C, device=dev), torch.empty(C, device=dev), torch.empty(C, device=dev)
+    bits = torch.zeros(M, C // 8, dtype=torch.uint8, device=dev) if (precision == 1 and dev == "cuda") else None
     must = ["bn_stats_kernel", "col_finalize_kernel", "bn_apply_kernel"] if precision == 1 else []
     with Traced(dev, must, REF_TAGS if precision == 1 else ()):
         _lib.check(L.lbc_op_bn_train(_lib.ptr(xd), _lib.ptr(gd), _lib.ptr(bd), _lib.ptr(rd), int(relu), _lib.ptr(y),
                                      _lib.ptr(mean), _lib.ptr(var), M, C, precision, _lib.ptr(rm), _lib.ptr(rv),
-                                     _lib.ptr(nsd), None))
+                                     _lib.ptr(nsd), _lib.ptr(bits), None))
+    if bits is not None:     # the (y > 0) bits the backward kernels use instead of re-reading the activation
+        yb = (y.cpu() > 0).reshape(M, C // 8, 8).to(torch.int32)
+        ref_bits = sum(yb[:, :, j] << j for j in range(8)).to(torch.uint8)
+        assert torch.equal(bits.cpu(), ref_bits)
     tol = 1.2e-2 if precision == 1 else 2e-5
     if shift:       # statistics of the ROUNDED shifted tensor; the apply un-shifts implicitly
         xs64 = xs.double()
@@ -131,7 +136,7 @@ def test_bn_forward_kernels_gpu(backend, M, C, relu, res, shift):
 
 
 # ------------------------------------------------------------------ BatchNorm backward
-def _bn_bwd_case(dev, M, C, mode, precision):
+def _bn_bwd_case(dev, M, C, mode, precision, use_bits=False):
     """mode: 'plain' | 'mask' (a separate activation's ReLU mask on dy) | 'own' (mask = relu of this BN's own output)"""
     _lib = _L()
     L = _lib.lib()
@@ -172,7 +177,7 @@ def _bn_bwd_case(dev, M, C, mode, precision):
     never = tuple(t for t in REF_TAGS if t not in ("k_bn_sum_part", "k_bn_var_part")) if precision == 1 else ()
     with Traced(dev, must, never):     # (the op wrapper recomputes the batch statistics with the correctness-first pass)
         _lib.check(L.lbc_op_bn_bwd(_lib.ptr(dyd), _lib.ptr(xd), _lib.ptr(gd), _lib.ptr(dg), _lib.ptr(db), _lib.ptr(dx), M, C,
-                                   precision, _lib.ptr(ad), _lib.ptr(bd), 1 if own else 0, None))
+                                   precision, _lib.ptr(ad), _lib.ptr(bd), 1 if own else 0, 1 if use_bits else 0, None))
     # dgamma / dbeta are fp32 sums of exact (bf16 x bf16) products on both paths
     scale = max(1.0, gp.grad.abs().max().item(), bp.grad.abs().max().item())
     assert (dg.cpu() - gp.grad).abs().max() <= 2e-4 * scale, (dg.cpu() - gp.grad).abs().max()
@@ -191,10 +196,12 @@ def test_bn_backward_cpu(backend, mode, precision):
 @pytest.mark.parametrize("mode", ["plain", "mask", "own"])
 def test_bn_backward_kernels_gpu(backend, M, C, mode):
     _bn_bwd_case("cuda", M, C, mode, 1)
+    if mode == "mask":       # the same mask handed over as bits (the block-final ReLU of the training step)
+        _bn_bwd_case("cuda", M, C, mode, 1, use_bits=True)
 
 
 # ------------------------------------------------------------------ masked adds
-def _ew_case(dev, precision):
+def _ew_case(dev, precision, use_bits=False):
     _lib = _L()
     L = _lib.lib()
     g = torch.Generator().manual_seed(11)
@@ -205,7 +212,7 @@ def _ew_case(dev, precision):
         ad, bd, md = a.clone().to(dev), b.to(dev), m.to(dev)
         with Traced(dev, ["ew_kernel"] if precision == 1 else [], REF_TAGS if precision == 1 else ()):
             _lib.check(L.lbc_op_ew(_lib.ptr(ad), _lib.ptr(bd) if mode != 2 else None, _lib.ptr(md) if mode != 0 else None, n, mode,
-                                   precision, None))
+                                   precision, 1 if use_bits else 0, None))
         assert _err(ad.cpu(), ref) < (8e-3 if precision == 1 else 1e-6), mode
 
 
@@ -217,6 +224,7 @@ def test_masked_adds_cpu(backend, precision):
 @pytest.mark.gpu
 def test_masked_add_kernel_gpu(backend):
     _ew_case("cuda", 1)
+    _ew_case("cuda", 1, use_bits=True)
 
 
 # ------------------------------------------------------------------ stem tail: BN + ReLU + MaxPool and its backward
@@ -397,8 +405,7 @@ def _stem_case(dev, N, C, H, W, precision, frames):
     y, dw = torch.empty(N, OH, OW, 64, device=dev), torch.empty(64, C, 7, 7, device=dev)
     stats = torch.empty(128, device=dev) if direct else None
     if precision == 1:
-        # (teacher: 96 output columns -> the per-thread im2col writer, tag k_stem_im2col; 64-column rows use stem_im2col_kernel)
-        must = ["stem_conv_kernel", "stem_wgrad_kernel"] if direct else ["conv_gemm_kernel<64>", "wgrad_gemm_kernel<64>"]
+        must = ["stem_conv_kernel", "stem_wgrad_kernel"] if direct else ["stem_im2col_kernel", "conv_gemm_kernel<64>", "wgrad_gemm_kernel<64>"]
     elif precision == 2:
         must = ["tc_stem_im2col_kernel", "conv_gemm_kernel<64,f32>", "wgrad_gemm_kernel<64>"]
     else:

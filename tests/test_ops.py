@@ -90,13 +90,13 @@ def _bn_case(dev, M, C, relu, with_res):
     xd, gd, bd, rd, dyd = d(x), d(gamma), d(beta), d(res), d(dy)     # keep the device copies alive across the calls
     y, mean, var = torch.empty(M, C, device=dev), torch.empty(C, device=dev), torch.empty(C, device=dev)
     _lib.check(L.lbc_op_bn_train(_lib.ptr(xd), _lib.ptr(gd), _lib.ptr(bd), _lib.ptr(rd), int(relu),
-                                 _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var), M, C, 0, None, None, None, None))
+                                 _lib.ptr(y), _lib.ptr(mean), _lib.ptr(var), M, C, 0, None, None, None, None, None))
     assert (y.cpu() - out_ref).abs().max() < 2e-5
     assert (mean.cpu() - x.mean(0)).abs().max() < 1e-5
     assert (var.cpu() - x.var(0, unbiased=False)).abs().max() < 2e-5
     dg, db, dx = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty(M, C, device=dev)
     _lib.check(L.lbc_op_bn_bwd(_lib.ptr(dyd), _lib.ptr(xd), _lib.ptr(gd), _lib.ptr(dg), _lib.ptr(db),
-                               _lib.ptr(dx), M, C, 0, None, None, 0, None))
+                               _lib.ptr(dx), M, C, 0, None, None, 0, 0, None))
     assert (dg.cpu() - gp.grad).abs().max() < 1e-4 * max(1.0, gp.grad.abs().max().item())
     assert (db.cpu() - bp.grad).abs().max() < 1e-4 * max(1.0, bp.grad.abs().max().item())
     assert (dx.cpu() - xt.grad.reshape(C, M).t()).abs().max() < 2e-5
