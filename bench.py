@@ -307,7 +307,19 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py (our arm) needs a B200; there is no CPU path"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
     if world > 1:
+        # pin this rank to the CPUs next to its GPU before any pinned host buffer is allocated: pinned pages land on that
+        # NUMA node, so the per-step host->device copies of the end-to-end loop do not cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            numa = sorted(os.sched_getaffinity(0))
+            numa = "%d cpus (%d..%d)" % (len(numa), numa[0], numa[-1])
+        except Exception as e:      # affinity is an optimisation, never a requirement
+            numa = "unavailable: %s" % str(e)[:80]
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     pair = args.pair if args.pair >= 0 else int(os.environ.get("LBC_PAIR", "7") or 0)   # bit 0: CTA-pair GEMMs, bit 1: wgrad3
@@ -459,7 +471,7 @@ def run_ours(args):
                                batch_per_gpu=B, parallelism="dp%d" % world, step=wl["step"],
                                l2="inputs+activations per step (>5 GB) far exceed the 126 MB L2; no explicit flush",
                                fast_kernels=not args.no_fast, cta_pair_gemm=bool(pair & 1), wgrad_row_of_taps=bool(pair & 2),
-                               wgrad_cta_pair=bool(pair & 4), allreduce=("bucketed, overlapped with backward" if w.dp.overlap else "single, after backward") if world > 1 else "none"),
+                               wgrad_cta_pair=bool(pair & 4), cpu_affinity=numa, allreduce=("bucketed, overlapped with backward" if w.dp.overlap else "single, after backward") if world > 1 else "none"),
                    e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, steps=e2e_steps,
                             frames="uint8 host frames (pinned), copied on the prefetch stream every step",
                             fp32_frames=dict(value=e2e_fp32, h2d_bytes_per_step=h2d_fp32)),
