@@ -24,6 +24,12 @@ void set_c64_variant(bool on);   // resident-weight / shared-row variant of the 
 float* stat_partial_buffer();      // shared scratch of the statistics partials (single stream); null if the allocation failed
 int64_t stat_partial_capacity();   // its size in floats
 bool col_finalize_bf16(const float* partial, int rows, int C2, float* sums, lbc_stream_t s);
+// train-mode BatchNorm statistics from partial rows ([rows][2C]: sum | sum of squares; null = the shared partial buffer) in
+// one launch: mean / rstd, running buffers, centring shift and the (scale | shift) pair scsh[2C] for bn_apply_bf16
+bool bn_finalize_bf16(const float* partial, int rows, int C, int64_t M, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
+                      float* negshift, float* scsh, float* sums, lbc_stream_t s);
+bool bn_stats_partials_bf16(const bf16* x, int64_t M, int C, int* rows, lbc_stream_t s);
 
 template <class T>
 inline bool conv_fwd(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s, const float* bias_co = nullptr,
@@ -105,7 +111,7 @@ bool tc_stem_im2col(const float* x0, void* col16, int B, int C, int H, int W, in
 
 // ---- HBM-bound bf16 kernels (lbc_fast_elem.cu) -------------------------------------------------------------
 bool bn_stats_bf16(const bf16* x, int64_t M, int C, float* sums, lbc_stream_t s);
-bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const float* gamma, const float* beta, float eps,
+bool bn_apply_bf16(const bf16* x, const float* scsh, int64_t M, int C, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
                    const bf16* residual, bool relu, bool train, bf16* y, float* negshift, lbc_stream_t s,
                    uint8_t* maskbits = nullptr);   // maskbits [M][C/8]: also emit (y > 0) as one bit per element
@@ -135,15 +141,20 @@ template <class T> struct Fast {
                        int, int, int, int, lbc_stream_t) { return false; }
 };
 template <> struct Fast<bf16> {
-  // train: statistics + apply (two launches); eval: apply with the running statistics.  sums: >= 2C floats scratch
+  // train: (statistics pass) + finalize + apply; eval: apply with the running statistics.  sums: >= 2C floats scratch
+  // (receives the scale | shift pair of the finalize kernel)
   static bool bn_fwd(const bf16* x, int64_t M, int C, const float* gamma, const float* beta, float eps, float momentum,
                      float* rm, float* rv, float* saved_mean, float* saved_rstd, const bf16* res, bool relu, bool train,
                      bf16* y, float* sums, float* negshift, lbc_stream_t s, int conv_stat_rows = 0, uint8_t* maskbits = nullptr) {
     if (!enabled()) return false;
-    if (train && conv_stat_rows > 0) {   // statistics partials already written by the producing conv's epilogue
-      if (!col_finalize_bf16(stat_partial_buffer(), conv_stat_rows, 2 * C, sums, s)) return false;
-    } else if (train && !bn_stats_bf16(x, M, C, sums, s)) {
-      return false;
+    if (train) {
+      // partial rows: written by the producing conv's epilogue (conv_stat_rows > 0), else by a statistics pass over x;
+      // then ONE launch: column sums + mean / rstd + running buffers + centring shift + (scale | shift)
+      int rows = conv_stat_rows;
+      if (rows <= 0 && !bn_stats_partials_bf16(x, M, C, &rows, s)) return false;
+      if (!bn_finalize_bf16(nullptr, rows, C, M, gamma, beta, eps, momentum, rm, rv, saved_mean, saved_rstd, negshift, sums,
+                            nullptr, s))
+        return false;
     }
     return bn_apply_bf16(x, sums, M, C, gamma, beta, eps, momentum, rm, rv, saved_mean, saved_rstd, res, relu, train, y,
                          negshift, s, maskbits);
@@ -182,6 +193,8 @@ template <> struct Fast<bf16> {
 bool head_forward_bf16(const bf16* h, ref::HeadParams hp, float* fold, float* logits, float* rowmax, float* rowsum,
                        float* preds, int N, int H, int W, lbc_stream_t s);
 bool head_softmax_f32(const float* logits, float* rowmax, float* rowsum, float* preds, int N, int H, int W, lbc_stream_t s);
+bool head_dlogits_f32(const float* logits, const float* rowmax, const float* rowsum, const float* preds, const float* onehot,
+                      const float* d_pred, const float* d_preds, float* dlogits, int N, int H, int W, lbc_stream_t s);
 bool head_backward_s_bf16(const float* dlogits, const bf16* h, const float* mean, const float* rstd, double* S, int N, int HW,
                           lbc_stream_t s);
 bool head_backward_dh_bf16(const float* dlogits, const bf16* h, ref::HeadParams hp, ref::HeadGrads hg, const float* fold,

@@ -608,7 +608,7 @@ struct SmemPlanKw {
   static constexpr int OUT_OFF = STAGES * AKW_BYTES + BRES_BYTES;
   static constexpr int BAR_OFF = OUT_OFF + A_BYTES;
   static constexpr int RED_OFF = BAR_OFF + 256;
-  static constexpr int TOTAL = RED_OFF + 2048 + 1024;
+  static constexpr int TOTAL = RED_OFF + 2048 + 256 + 1024;   // 128 x 4 floats reduction scratch + 64 bias floats + alignment slack
 };
 
 __device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
@@ -619,6 +619,71 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo(uint32_t smem_addr, ui
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+// ---- BatchNorm statistics of the N = 64 kernels (conv3x3_c64_kernel, stem_conv_kernel) ----
+// Epilogue thread e (0..127) owns the column pair 2*(e % 32) and the 32 staged rows [32*(e/32), 32*(e/32)+32): after a
+// tile's bf16 outputs sit in the staging buffer it reads its 32 x 4 bytes back and adds them to FOUR registers that live
+// across all tiles of the persistent CTA.  Round 1 reduced and wrote one partial row per TILE (a shared-memory exchange,
+// a named barrier and a global store per tile, 7680 / 30720 partial rows per launch for col_finalize to sum): the forward
+// launches of the layer-1 kernel took 132 us against 82 us for the same GEMM without statistics.  Now: one partial row per
+// CTA, written once at the end.
+struct ColStat {
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+};
+__device__ __forceinline__ void colstat_accumulate(ColStat& cs, const uint8_t* out_stage, int e, int valid_rows) {
+  const int pair = e & 31, sub = e >> 5;
+  const int col = 2 * pair;
+  const uint8_t* boxp = out_stage + ((col & 7) >> 1) * 4;
+  const int chunk = col >> 3;
+  const int r0 = sub * 32;
+  if (valid_rows >= r0 + 32) {   // whole strip valid (every tile but the batch tail): 32 independent loads
+    uint32_t w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int r = r0 + i;
+      w[i] = *reinterpret_cast<const uint32_t*>(boxp + r * 128 + ((chunk ^ (r & 7)) << 4));
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float a = __uint_as_float(w[i] << 16), b = __uint_as_float(w[i] & 0xffff0000u);
+      cs.s0 += a;
+      cs.s1 += b;
+      cs.q0 += a * a;
+      cs.q1 += b * b;
+    }
+  } else {
+    for (int r = r0; r < r0 + 32 && r < valid_rows; ++r) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(boxp + r * 128 + ((chunk ^ (r & 7)) << 4));
+      const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+      cs.s0 += a;
+      cs.s1 += b;
+      cs.q0 += a * a;
+      cs.q1 += b * b;
+    }
+  }
+}
+// end of the CTA: combine the four row strips of every column pair and write this CTA's partial row [2*64]
+__device__ __forceinline__ void colstat_flush(const ColStat& cs, float* red, int e, float* dst_row) {
+  red[e * 4 + 0] = cs.s0;
+  red[e * 4 + 1] = cs.s1;
+  red[e * 4 + 2] = cs.q0;
+  red[e * 4 + 3] = cs.q1;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (e < 32) {
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int t2 = 0; t2 < 4; ++t2) {
+      s0 += red[(t2 * 32 + e) * 4 + 0];
+      s1 += red[(t2 * 32 + e) * 4 + 1];
+      q0 += red[(t2 * 32 + e) * 4 + 2];
+      q1 += red[(t2 * 32 + e) * 4 + 3];
+    }
+    dst_row[2 * e] = s0;
+    dst_row[2 * e + 1] = s1;
+    dst_row[64 + 2 * e] = q0;
+    dst_row[64 + 2 * e + 1] = q1;
+  }
 }
 
 template <int STAGES>
@@ -726,11 +791,16 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool issuer = (threadIdx.x == 64);
+    const int e = threadIdx.x - 64;
+    float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
+    float* bias_s = red + 512;   // 64 per-channel constants (zeros without a bias): broadcast LDS.128 instead of 64 LDG per tile
+    if (e < 64) bias_s[e] = p.bias ? __ldg(p.bias + e) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    ColStat cs;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_tile = tile;
       const int w0 = (tile % p.tiles_w) * 8;
       const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
       const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -743,25 +813,23 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t r[32];
         tmem_ld32(taddr + ch * 32, r);
-        const int col0 = ch * 32;
         uint8_t* rowp = out_stage + row * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float a = __uint_as_float(r[j * 8 + e * 2]);
-            float b = __uint_as_float(r[j * 8 + e * 2 + 1]);
-            if (p.bias) {
-              a += __ldg(p.bias + col0 + j * 8 + e * 2);
-              b += __ldg(p.bias + col0 + j * 8 + e * 2 + 1);
-            }
+          for (int e2 = 0; e2 < 4; ++e2) {
+            float a = __uint_as_float(r[j * 8 + e2 * 2]) + bb[e2 * 2];
+            float b = __uint_as_float(r[j * 8 + e2 * 2 + 1]) + bb[e2 * 2 + 1];
             if (p.relu) {
               a = fmaxf(a, 0.f);
               b = fmaxf(b, 0.f);
             }
             __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            pk[e2] = *reinterpret_cast<uint32_t*>(&h);
           }
           const int chunk16 = (ch & 1) * 4 + j;
           *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -776,46 +844,12 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (p.stat_partial) {
-        constexpr int PAIRS = BN / 2, TPP = 128 / PAIRS, RPT = 128 / TPP;
-        float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
-        const int e = threadIdx.x - 64;
-        const int pair = e % PAIRS, sub = e / PAIRS;
-        const int col = 2 * pair;
-        const uint8_t* boxp = out_stage + ((col & 7) >> 1) * 4;
-        const int chunk = (col & 63) >> 3;
         int nvalid = p.valid_n - n0;
         nvalid = nvalid < 0 ? 0 : (nvalid > p.TN ? p.TN : nvalid);
-        const int valid_rows = nvalid * p.TH * 8;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        for (int r2 = sub * RPT; r2 < (sub + 1) * RPT && r2 < valid_rows; ++r2) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(boxp + r2 * 128 + ((chunk ^ (r2 & 7)) << 4));
-          const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
-          s0 += a;
-          s1 += b;
-          q0 += a * a;
-          q1 += b * b;
-        }
-        red[e * 4 + 0] = s0;
-        red[e * 4 + 1] = s1;
-        red[e * 4 + 2] = q0;
-        red[e * 4 + 3] = q1;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (sub == 0) {
-#pragma unroll
-          for (int t2 = 1; t2 < TPP; ++t2) {
-            s0 += red[(t2 * PAIRS + pair) * 4 + 0];
-            s1 += red[(t2 * PAIRS + pair) * 4 + 1];
-            q0 += red[(t2 * PAIRS + pair) * 4 + 2];
-            q1 += red[(t2 * PAIRS + pair) * 4 + 3];
-          }
-          float* dst = p.stat_partial + (int64_t)m_tile * 2 * p.stat_C + col;
-          dst[0] = s0;
-          dst[1] = s1;
-          dst[p.stat_C] = q0;
-          dst[p.stat_C + 1] = q1;
-        }
+        colstat_accumulate(cs, out_stage, e, nvalid * p.TH * 8);
       }
     }
+    if (p.stat_partial) colstat_flush(cs, red, e, p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C);
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -849,7 +883,7 @@ struct SmemPlanStem {
   static constexpr int OUT_OFF = STAGES * ASTEM_BYTES + BRES_BYTES;
   static constexpr int BAR_OFF = OUT_OFF + A_BYTES;
   static constexpr int RED_OFF = BAR_OFF + 256;
-  static constexpr int TOTAL = RED_OFF + 2048 + 1024;
+  static constexpr int TOTAL = RED_OFF + 2048 + 256 + 1024;
 };
 __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -960,11 +994,16 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool issuer = (threadIdx.x == 64);
+    const int e = threadIdx.x - 64;
+    float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
+    float* bias_s = red + 512;
+    if (e < 64) bias_s[e] = p.bias ? __ldg(p.bias + e) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    ColStat cs;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_tile = tile;
       const int w0 = (tile % p.tiles_w) * p.TW;
       const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
       const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -977,21 +1016,19 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant_
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t r[32];
         tmem_ld32(taddr + ch * 32, r);
-        const int col0 = ch * 32;
         uint8_t* rowp = out_stage + row * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float a = __uint_as_float(r[j * 8 + e * 2]);
-            float b = __uint_as_float(r[j * 8 + e * 2 + 1]);
-            if (p.bias) {
-              a += __ldg(p.bias + col0 + j * 8 + e * 2);
-              b += __ldg(p.bias + col0 + j * 8 + e * 2 + 1);
-            }
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float a = __uint_as_float(r[j * 8 + e2 * 2]) + bb[e2 * 2];
+            const float b = __uint_as_float(r[j * 8 + e2 * 2 + 1]) + bb[e2 * 2 + 1];
             __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            pk[e2] = *reinterpret_cast<uint32_t*>(&h);
           }
           const int chunk16 = (ch & 1) * 4 + j;
           *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -1006,46 +1043,12 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant_
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (p.stat_partial) {
-        constexpr int PAIRS = BN / 2, TPP = 128 / PAIRS, RPT = 128 / TPP;
-        float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
-        const int e = threadIdx.x - 64;
-        const int pair = e % PAIRS, sub = e / PAIRS;
-        const int col = 2 * pair;
-        const uint8_t* boxp = out_stage + ((col & 7) >> 1) * 4;
-        const int chunk = (col & 63) >> 3;
         int nvalid = p.valid_n - n0;
         nvalid = nvalid < 0 ? 0 : (nvalid > p.TN ? p.TN : nvalid);
-        const int valid_rows = nvalid * p.TH * p.TW;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        for (int r2 = sub * RPT; r2 < (sub + 1) * RPT && r2 < valid_rows; ++r2) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(boxp + r2 * 128 + ((chunk ^ (r2 & 7)) << 4));
-          const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
-          s0 += a;
-          s1 += b;
-          q0 += a * a;
-          q1 += b * b;
-        }
-        red[e * 4 + 0] = s0;
-        red[e * 4 + 1] = s1;
-        red[e * 4 + 2] = q0;
-        red[e * 4 + 3] = q1;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (sub == 0) {
-#pragma unroll
-          for (int t2 = 1; t2 < TPP; ++t2) {
-            s0 += red[(t2 * PAIRS + pair) * 4 + 0];
-            s1 += red[(t2 * PAIRS + pair) * 4 + 1];
-            q0 += red[(t2 * PAIRS + pair) * 4 + 2];
-            q1 += red[(t2 * PAIRS + pair) * 4 + 3];
-          }
-          float* dst = p.stat_partial + (int64_t)m_tile * 2 * p.stat_C + col;
-          dst[0] = s0;
-          dst[1] = s1;
-          dst[p.stat_C] = q0;
-          dst[p.stat_C + 1] = q1;
-        }
+        colstat_accumulate(cs, out_stage, e, nvalid * p.TH * p.TW);
       }
     }
+    if (p.stat_partial) colstat_flush(cs, red, e, p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C);
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1400,7 +1403,8 @@ static bool try_conv3x3_c64(const bf16* in, const void* wpack, bf16* out, int B,
   p.stat_partial = stat_partial;
   p.stat_C = 64;
   p.valid_n = B;
-  if (stat_rows) *stat_rows = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int tiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
+  if (stat_rows) *stat_rows = tiles_total < sm_count() ? tiles_total : sm_count();   // one partial row per persistent CTA
   const int64_t eb = 2;
   CUtensorMap mA = make_map_4d(in, 64, W, H, B, 64 * eb, (int64_t)W * 64 * eb, (int64_t)H * W * 64 * eb, 10, TH, TN);
   CUtensorMap mB = make_map_2d(wpack, (int64_t)9 * 64, 64, 64);
@@ -1466,7 +1470,10 @@ bool stem_conv_bf16(const bf16* x4, const bf16* w224, bf16* raw, int B, int H, i
   p.stat_partial = stat_partial;
   p.stat_C = 64;
   p.valid_n = B;
-  if (stat_rows) *stat_rows = p.tiles_w * p.tiles_h * p.tiles_n;
+  {
+    const int tiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
+    if (stat_rows) *stat_rows = tiles_total < 2 * sm_count() ? tiles_total : 2 * sm_count();   // one partial row per CTA
+  }
   const int64_t pitch = (int64_t)(W + 8) * 8, img = pitch * (H + 6);
   CUtensorMap mX0 = make_map_stem(x4, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN);
   CUtensorMap mX1 = make_map_stem((const uint8_t*)x4 + pitch, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN);

@@ -186,6 +186,119 @@ static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_s
   LBC_LAUNCHED("col_finalize_kernel");
 }
 
+// Train-mode BatchNorm statistics in ONE small launch: column sums of the partial rows (sum | sum of squares per channel),
+// then, in the same threads, everything that depends on them -- batch mean / rstd (double), the running-buffer update
+// (momentum, unbiased variance), the centring-shift update, and the affine pair (scale, shift) the apply kernel needs.
+// Round 1 left the finalisation to the PROLOGUE of bn_apply_kernel: every one of its 303 K threads redid the double-
+// precision mean / variance / rsqrt for its eight channels, a ~13 us floor per launch that dominated the layer-3/4
+// tensors (20 us per launch for 31 MB).  One block per 32 channels, 1024 threads = 32 channels x 32 row lanes.
+struct BnFinalizeArgs {
+  const float* partial;   // [P][2C]
+  int P, C;
+  int64_t M;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  float* saved_mean;
+  float* saved_rstd;
+  float* negshift;        // may be null
+  float* scsh;            // out: [2C] = scale | shift
+  float* sums;            // out (optional): [2C] raw column sums
+};
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const BnFinalizeArgs a) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int pl = threadIdx.x >> 5;
+  __shared__ float red0[32][33], red1[32][33];
+  float s0 = 0.f, s1 = 0.f;
+  if (c < a.C) {
+    const float* p0 = a.partial + c;
+    int p = pl;
+    for (; p + 96 < a.P; p += 128) {   // four independent row loads in flight per accumulator
+      const float a0 = p0[(int64_t)p * 2 * a.C], a1 = p0[(int64_t)(p + 32) * 2 * a.C], a2 = p0[(int64_t)(p + 64) * 2 * a.C],
+                  a3 = p0[(int64_t)(p + 96) * 2 * a.C];
+      const float b0 = p0[(int64_t)p * 2 * a.C + a.C], b1 = p0[(int64_t)(p + 32) * 2 * a.C + a.C],
+                  b2 = p0[(int64_t)(p + 64) * 2 * a.C + a.C], b3 = p0[(int64_t)(p + 96) * 2 * a.C + a.C];
+      s0 += (a0 + a1) + (a2 + a3);
+      s1 += (b0 + b1) + (b2 + b3);
+    }
+    for (; p < a.P; p += 32) {
+      s0 += p0[(int64_t)p * 2 * a.C];
+      s1 += p0[(int64_t)p * 2 * a.C + a.C];
+    }
+  }
+  red0[pl][threadIdx.x & 31] = s0;
+  red1[pl][threadIdx.x & 31] = s1;
+  __syncthreads();
+  if (pl == 0 && c < a.C) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      t0 += red0[i][threadIdx.x & 31];
+      t1 += red1[i][threadIdx.x & 31];
+    }
+    if (a.sums) {
+      a.sums[c] = t0;
+      a.sums[a.C + c] = t1;
+    }
+    const double m = (double)t0 / (double)a.M;
+    double var = (double)t1 / (double)a.M - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)m;
+    const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    a.saved_mean[c] = mean;
+    a.saved_rstd[c] = rstd;
+    const float true_mean = a.negshift ? (float)(m - (double)a.negshift[c]) : mean;
+    if (a.negshift) a.negshift[c] = -true_mean;   // centring estimate for the next forward pass
+    a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * true_mean;
+    const double unb = var * ((double)a.M / (double)(a.M > 1 ? a.M - 1 : 1));
+    a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unb;
+    const float sc = a.gamma[c] * rstd;
+    a.scsh[c] = sc;
+    a.scsh[a.C + c] = a.beta[c] - mean * sc;
+  }
+}
+// sums (optional) / scsh: [2C] each.  partial = null: the shared partial buffer (conv epilogue / bn_stats rows)
+bool bn_finalize_bf16(const float* partial, int rows, int C, int64_t M, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
+                      float* negshift, float* scsh, float* sums, lbc_stream_t s) {
+  if (!partial) partial = partial_buffer();
+  if (!partial || rows <= 0 || (int64_t)rows * 2 * C > kPartialFloats) return false;
+  BnFinalizeArgs a;
+  a.partial = partial;
+  a.P = rows;
+  a.C = C;
+  a.M = M;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.eps = eps;
+  a.momentum = momentum;
+  a.running_mean = running_mean;
+  a.running_var = running_var;
+  a.saved_mean = saved_mean;
+  a.saved_rstd = saved_rstd;
+  a.negshift = negshift;
+  a.scsh = scsh;
+  a.sums = sums;
+  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(a);
+  LBC_LAUNCHED("bn_finalize_kernel");
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
+// bn_stats_kernel without the column pass: leaves *rows partial rows in the shared partial buffer
+bool bn_stats_partials_bf16(const bf16* x, int64_t M, int C, int* rows, lbc_stream_t s) {
+  if (C % 8 || C > 2560) return false;
+  RowGeom g = row_geom(M, C, 6);
+  float* part = partial_buffer();
+  if (!part) return false;
+  bn_stats_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>((const uint4*)x, M, g.tpr, g.rpi, part, C);
+  LBC_LAUNCHED("bn_stats_kernel");
+  LBC_CUDA(cudaGetLastError());
+  *rows = g.grid;
+  return true;
+}
+
 float* stat_partial_buffer() { return partial_buffer(); }
 bool col_finalize_bf16(const float* partial, int rows, int C2, float* sums, lbc_stream_t s) {
   if (!partial || (int64_t)rows * C2 > kPartialFloats) return false;
@@ -211,7 +324,7 @@ struct BnApplyArgs {
   const uint4* x;
   const uint4* res;
   uint4* y;
-  const float* sums;   // train: [2C] sum / sumsq
+  const float* scsh;   // train: [2C] scale | shift from bn_finalize_kernel
   const float* gamma;
   const float* beta;
   float* running_mean;
@@ -232,32 +345,19 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const BnApplyArgs a) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cg * 8 + j;
-    float mean, rstd;
-    if (a.train) {
-      double m = (double)a.sums[c] / (double)a.M;
-      double var = (double)a.sums[a.C + c] / (double)a.M - m * m;
-      if (var < 0.0) var = 0.0;
-      mean = (float)m;
-      rstd = (float)(1.0 / sqrt(var + (double)a.eps));
-      if (blockIdx.x == 0 && r == 0) {
-        a.saved_mean[c] = mean;
-        a.saved_rstd[c] = rstd;
-        const float true_mean = a.negshift ? (float)(m - (double)a.negshift[c]) : mean;
-        if (a.negshift) a.negshift[c] = -true_mean;   // centring estimate for the next forward pass
-        a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * true_mean;
-        double unb = var * ((double)a.M / (double)(a.M > 1 ? a.M - 1 : 1));
-        a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unb;
-      }
+    if (a.train) {   // statistics, running buffers, (scale, shift): bn_finalize_kernel
+      sc[j] = a.scsh[c];
+      sh[j] = a.scsh[a.C + c];
     } else {
-      mean = a.running_mean[c] + (a.negshift ? a.negshift[c] : 0.f);
-      rstd = 1.0f / sqrtf(a.running_var[c] + a.eps);
+      const float mean = a.running_mean[c] + (a.negshift ? a.negshift[c] : 0.f);
+      const float rstd = 1.0f / sqrtf(a.running_var[c] + a.eps);
       if (blockIdx.x == 0 && r == 0) {
         a.saved_mean[c] = mean;
         a.saved_rstd[c] = rstd;
       }
+      sc[j] = a.gamma[c] * rstd;
+      sh[j] = a.beta[c] - mean * sc[j];
     }
-    sc[j] = a.gamma[c] * rstd;
-    sh[j] = a.beta[c] - mean * sc[j];
   }
   const int64_t stride = (int64_t)gridDim.x * a.rpi;
   for (int64_t row = (int64_t)blockIdx.x * a.rpi + r; row < a.M; row += 2 * stride) {
@@ -302,7 +402,7 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const BnApplyArgs a) {
   }
 }
 
-bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const float* gamma, const float* beta, float eps,
+bool bn_apply_bf16(const bf16* x, const float* scsh, int64_t M, int C, const float* gamma, const float* beta, float eps,
                    float momentum, float* running_mean, float* running_var, float* saved_mean, float* saved_rstd,
                    const bf16* residual, bool relu, bool train, bf16* y, float* negshift, lbc_stream_t s, uint8_t* maskbits) {
   if (C % 8 || C > 2560) return false;
@@ -313,7 +413,7 @@ bool bn_apply_bf16(const bf16* x, const float* sums, int64_t M, int C, const flo
   a.x = (const uint4*)x;
   a.res = (const uint4*)residual;
   a.y = (uint4*)y;
-  a.sums = sums;
+  a.scsh = scsh;
   a.gamma = gamma;
   a.beta = beta;
   a.running_mean = running_mean;
@@ -723,6 +823,9 @@ bool bn_bwd_bf16(const bf16*, const bf16*, const bf16*, const float*, const floa
 bool ew_bf16(bf16*, const bf16*, const bf16*, int64_t, int, lbc_stream_t, const uint8_t*) { return false; }
 float* stat_partial_buffer() { return nullptr; }
 int64_t stat_partial_capacity() { return 0; }
+bool bn_finalize_bf16(const float*, int, int, int64_t, const float*, const float*, float, float, float*, float*, float*, float*,
+                      float*, float*, float*, lbc_stream_t) { return false; }
+bool bn_stats_partials_bf16(const bf16*, int64_t, int, int*, lbc_stream_t) { return false; }
 bool col_finalize_bf16(const float*, int, int, float*, lbc_stream_t) { return false; }
 bool bn_relu_maxpool_bf16(const bf16*, const float*, const float*, const float*, const float*, bf16*, uint8_t*, int, int, int,
                           int, int, int, lbc_stream_t) { return false; }

@@ -74,7 +74,9 @@ void head_backward(HeadCtx& h, const T* hfeat, const float* onehot, const float*
                    ref::HeadGrads hg, T* dh, int N, lbc_stream_t s) {
   const int HW = h.H * h.W;
   ref::HeadParams hp = h.params(true);
-  ref::head_dlogits(s, h.logits, h.rowmax, h.rowsum, h.preds, onehot, d_pred, d_preds, h.dlogits, N, h.H, h.W);
+  if (!(h.fast_used && fast::head_dlogits_f32(h.logits, h.rowmax, h.rowsum, h.preds, onehot, d_pred, d_preds, h.dlogits, N, h.H,
+                                              h.W, s)))
+    ref::head_dlogits(s, h.logits, h.rowmax, h.rowsum, h.preds, onehot, d_pred, d_preds, h.dlogits, N, h.H, h.W);
   h.mask_fused = false;
   bool s_done = false;
   if (std::is_same<T, bf16>::value && h.fast_used)

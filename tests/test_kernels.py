@@ -38,7 +38,7 @@ def _err(got, ref):
     return (got.double() - ref.double()).abs().max().item() / max(ref.double().abs().max().item(), 1e-30)
 
 
-REF_TAGS = ("k_conv_fwd", "k_conv_dgrad", "k_conv_wgrad_part", "k_bn_sum_part", "k_bn_var_part", "k_bn_apply",
+REF_TAGS = ("k_head_dlogits", "k_conv_fwd", "k_conv_dgrad", "k_conv_wgrad_part", "k_bn_sum_part", "k_bn_var_part", "k_bn_apply",
             "k_bn_bwd_part", "k_bn_bwd_apply", "k_maxpool_fwd", "k_maxpool_bwd", "k_relu_mask", "k_add]", "k_head_logits",
             "k_head_softmax", "k_head_s_part", "k_head_dh", "k_colsum_part", "k_input_nhwc")
 
@@ -319,7 +319,7 @@ def _head_case(dev, N, H, W, precision, use_pred):
     dg, db, dw, dbi = (torch.empty_like(t, device=dev) for t in (gamma, beta, w, bias))
     dh = torch.empty(N, H * W, 64, device=dev)
     masked = ctypes.c_int(0)
-    must = ["bn_stats_kernel", "head_logits", "head_softmax_kernel", "head_s", "head_dh"] if precision == 1 else []
+    must = ["bn_stats_kernel", "head_logits", "head_softmax_kernel", "head_dlogits_kernel", "head_s", "head_dh"] if precision == 1 else []
     with Traced(dev, must, REF_TAGS if precision == 1 else ()):
         _lib.check(L.lbc_op_head(_lib.ptr(hd), _lib.ptr(gd), _lib.ptr(bd), _lib.ptr(wd), _lib.ptr(bid), N, H, W, _lib.ptr(rm),
                                  _lib.ptr(rv), _lib.ptr(logits), _lib.ptr(preds), _lib.ptr(ohd), _lib.ptr(dpd), _lib.ptr(dpsd),
