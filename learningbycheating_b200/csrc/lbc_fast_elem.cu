@@ -213,19 +213,23 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const BnFinalizeArgs 
   __shared__ float red0[32][33], red1[32][33];
   float s0 = 0.f, s1 = 0.f;
   if (c < a.C) {
+    // up to 16 rows x 2 columns in flight per thread: the loop is pure L2 latency (1920 partial rows after a layer-2 conv)
     const float* p0 = a.partial + c;
-    int p = pl;
-    for (; p + 96 < a.P; p += 128) {   // four independent row loads in flight per accumulator
-      const float a0 = p0[(int64_t)p * 2 * a.C], a1 = p0[(int64_t)(p + 32) * 2 * a.C], a2 = p0[(int64_t)(p + 64) * 2 * a.C],
-                  a3 = p0[(int64_t)(p + 96) * 2 * a.C];
-      const float b0 = p0[(int64_t)p * 2 * a.C + a.C], b1 = p0[(int64_t)(p + 32) * 2 * a.C + a.C],
-                  b2 = p0[(int64_t)(p + 64) * 2 * a.C + a.C], b3 = p0[(int64_t)(p + 96) * 2 * a.C + a.C];
-      s0 += (a0 + a1) + (a2 + a3);
-      s1 += (b0 + b1) + (b2 + b3);
-    }
-    for (; p < a.P; p += 32) {
-      s0 += p0[(int64_t)p * 2 * a.C];
-      s1 += p0[(int64_t)p * 2 * a.C + a.C];
+    const int64_t rs = (int64_t)2 * a.C;
+    for (int p = pl; p < a.P; p += 32 * 16) {
+      float v0[16], v1[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int pr = p + 32 * u;
+        const bool ok = pr < a.P;
+        v0[u] = ok ? __ldcg(p0 + (int64_t)pr * rs) : 0.f;
+        v1[u] = ok ? __ldcg(p0 + (int64_t)pr * rs + a.C) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        s0 += v0[u];
+        s1 += v1[u];
+      }
     }
   }
   red0[pl][threadIdx.x & 31] = s0;

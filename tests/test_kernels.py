@@ -87,7 +87,7 @@ def _bn_fwd_case(dev, M, C, relu, with_res, precision, shift):
     rm, rv, nsd = d(rm0.clone()), d(rv0.clone()), d(ns)
     y, mean, var = torch.empty(M, C, device=dev), torch.empty(C, device=dev), torch.empty(C, device=dev)
     bits = torch.zeros(M, C // 8, dtype=torch.uint8, device=dev) if (precision == 1 and dev == "cuda") else None
-    must = ["bn_stats_kernel", "col_finalize_kernel", "bn_apply_kernel"] if precision == 1 else []
+    must = ["bn_stats_kernel", "bn_finalize_kernel", "bn_apply_kernel"] if precision == 1 else []
     with Traced(dev, must, REF_TAGS if precision == 1 else ()):
         _lib.check(L.lbc_op_bn_train(_lib.ptr(xd), _lib.ptr(gd), _lib.ptr(bd), _lib.ptr(rd), int(relu), _lib.ptr(y),
                                      _lib.ptr(mean), _lib.ptr(var), M, C, precision, _lib.ptr(rm), _lib.ptr(rv),
