@@ -155,6 +155,8 @@ int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mod
 int lbc_op_maxpool(const float* x, float* y, const float* dy, float* dx, int N, int H, int W, int C, void* stream);
 int lbc_op_bn_relu_maxpool(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                            float* y, const float* dy, float* dx, int N, int H, int W, int C, int precision, void* stream);
+int lbc_op_stem_tail(const float* x, const float* gamma, const float* beta, float* y, const float* dy, float* dgamma,
+                     float* dbeta, float* dx, int N, int H, int W, int C, int precision, void* stream);
 int lbc_op_spatial_softmax(const float* logits, float* out_xy, int rows, int H, int W, int precision, void* stream);
 int lbc_op_head(const float* h, const float* gamma, const float* beta, const float* w, const float* bias, int N, int H, int W,
                 float* running_mean, float* running_var, float* logits_out, float* preds_out, const float* onehot,

@@ -70,6 +70,7 @@ def _declare(lib):
         "lbc_op_ew": (i, [vp, vp, vp, i64, i, i, i, vp]),
         "lbc_op_maxpool": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
         "lbc_op_bn_relu_maxpool": (i, [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]),
+        "lbc_op_stem_tail": (i, [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]),
         "lbc_op_spatial_softmax": (i, [vp, vp, i, i, i, i, vp]),
         "lbc_op_head": (i, [vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                             ctypes.POINTER(i), i, vp]),

@@ -651,6 +651,52 @@ int lbc_op_bn_relu_maxpool(const float* x, const float* mean, const float* rstd,
     sync_stream(s);
   });
 }
+// Whole stem tail, train mode: y = maxpool3x3/s2/p1(relu(batchnorm(x))) with batch statistics, and its backward from
+// dy [N][OH][OW][C]: dgamma, dbeta, dx [N][H][W][C] (resnet.py:149-152).  bf16 path: the fused BN+ReLU+MaxPool forward and the
+// two-pass pool-backward + BatchNorm-backward kernels (the masked gradient of the BN output is never stored).
+int lbc_op_stem_tail(const float* x, const float* gamma, const float* beta, float* y, const float* dy, float* dgamma,
+                     float* dbeta, float* dx, int N, int H, int W, int C, int precision, void* stream) {
+  return guarded([&] {
+    require_device();
+    lbc_stream_t s = S(stream);
+    int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+    Tmp t;
+    const int64_t M = (int64_t)N * H * W, nx = M * C, ny = (int64_t)N * OH * OW * C;
+    uint8_t* idx = t.get<uint8_t>(ny);
+    double* ws = t.get<double>(1 << 20);
+    float *mean = t.get<float>(C), *var = t.get<float>(C), *rstd = t.get<float>(C);
+    if (precision == PREC_F32) {
+      float *a = t.get<float>(nx), *g = t.get<float>(nx);
+      ref::bn_stats<float>(s, x, M, C, mean, var, ws);
+      ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, nullptr, nullptr);
+      ref::bn_apply<float>(s, x, mean, rstd, gamma, beta, nullptr, true, a, M, C);
+      ref::maxpool_fwd<float>(s, a, y, idx, N, H, W, C, OH, OW);
+      ref::maxpool_bwd<float>(s, dy, idx, g, N, H, W, C, OH, OW);
+      ref::relu_mask_inplace<float>(s, g, a, nx);
+      ref::bn_bwd<float>(s, g, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, ws);
+    } else {
+      bf16 *xb = t.get<bf16>(nx), *yb = t.get<bf16>(ny), *dyb = t.get<bf16>(ny), *dxb = t.get<bf16>(nx);
+      float* sums = t.get<float>(2 * C);
+      ref::cast<float, bf16>(s, x, xb, nx);
+      ref::cast<float, bf16>(s, dy, dyb, ny);
+      ref::bn_stats<bf16>(s, xb, M, C, mean, var, ws);
+      ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, nullptr, nullptr);
+      bool ok = fast::Fast<bf16>::pool_fwd(xb, mean, rstd, gamma, beta, yb, idx, N, H, W, C, OH, OW, s) &&
+                fast::stem_pool_bn_bwd_bf16(dyb, idx, xb, mean, rstd, gamma, beta, dgamma, dbeta, dxb, N, H, W, C, OH, OW, sums, s);
+      if (!ok) {
+        bf16 *a = t.get<bf16>(nx), *g = t.get<bf16>(nx);
+        ref::bn_apply<bf16>(s, xb, mean, rstd, gamma, beta, nullptr, true, a, M, C);
+        ref::maxpool_fwd<bf16>(s, a, yb, idx, N, H, W, C, OH, OW);
+        ref::maxpool_bwd<bf16>(s, dyb, idx, g, N, H, W, C, OH, OW);
+        ref::relu_mask_inplace<bf16>(s, g, a, nx);
+        ref::bn_bwd<bf16>(s, g, xb, mean, rstd, gamma, dgamma, dbeta, dxb, M, C, ws);
+      }
+      ref::cast<bf16, float>(s, yb, y, ny);
+      ref::cast<bf16, float>(s, dxb, dx, nx);
+    }
+    sync_stream(s);
+  });
+}
 int lbc_op_spatial_softmax(const float* logits, float* out_xy, int rows, int H, int W, int precision, void* stream) {
   return guarded([&] {
     require_device();

@@ -271,9 +271,58 @@ def test_bn_relu_maxpool_cpu(backend, precision):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,H,W", [(2, 80, 192), (3, 96, 96), (1, 10, 12)])
+@pytest.mark.parametrize("N,H,W", [(2, 80, 192), (3, 96, 96), (1, 12, 16)])
 def test_bn_relu_maxpool_kernels_gpu(backend, N, H, W):
     _pool_case("cuda", N, H, W, 64, 1)
+
+
+def _stem_tail_case(dev, N, H, W, C, precision):
+    """train-mode BN -> ReLU -> MaxPool and its whole backward (dgamma, dbeta, d raw) vs torch autograd"""
+    _lib = _L()
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(41)
+    x = _r(torch.randn(N, C, H, W, generator=g) * 1.4 + 0.2, precision).requires_grad_(True)
+    gamma = (torch.rand(C, generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.3).requires_grad_(True)
+    z = F.batch_norm(x, None, None, gamma, beta, True, 0.1, 1e-5)
+    a = z.clamp_min(0)
+    if precision == 1:       # the bf16 path pools the ROUNDED activation
+        a = a + (_r(a.detach(), 1) - a.detach())
+    y_ref = F.max_pool2d(a, 3, 2, 1)
+    dy = _r(torch.randn(y_ref.shape, generator=g), precision)
+    (y_ref * dy).sum().backward()
+    d = lambda t: t.detach().contiguous().to(dev)
+    xd, dyd, gd, bd = d(_nhwc(x)), d(_nhwc(dy)), d(gamma), d(beta)
+    OH, OW = y_ref.shape[2:]
+    y, dx = torch.empty(N, OH, OW, C, device=dev), torch.empty(N, H, W, C, device=dev)
+    dg, db = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    must = ["bn_relu_maxpool_kernel", "maxpool_relu_bwd_kernel<bn_reduce>", "maxpool_relu_bwd_kernel<bn_apply>"] if precision == 1 else []
+    never = tuple(t for t in REF_TAGS if t not in ("k_bn_sum_part", "k_bn_var_part")) if precision == 1 else ()
+    with Traced(dev, must, never):
+        _lib.check(L.lbc_op_stem_tail(_lib.ptr(xd), _lib.ptr(gd), _lib.ptr(bd), _lib.ptr(y), _lib.ptr(dyd), _lib.ptr(dg), _lib.ptr(db),
+                                      _lib.ptr(dx), N, H, W, C, precision, None))
+    assert _err(_nchw(y.cpu()), y_ref.detach()) < (8e-3 if precision == 1 else 1e-5)
+    scale = max(1.0, gamma.grad.abs().max().item(), beta.grad.abs().max().item())
+    tol = 5e-3 if precision == 1 else 1e-4       # bf16: a tie between equal rounded activations may move a gradient to a neighbour
+    assert (dg.cpu() - gamma.grad).abs().max() <= tol * scale
+    assert (db.cpu() - beta.grad).abs().max() <= tol * scale
+    ref, got = x.grad, _nchw(dx.cpu())
+    if precision == 1:
+        bad = ((got - ref).abs() > 2e-2 * ref.abs().max()).float().mean().item()
+        assert bad < 2e-3, bad
+    else:
+        assert _err(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_stem_tail_cpu(backend, precision):
+    _stem_tail_case(backend, 2, 10, 12, 8, precision)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,H,W", [(2, 80, 192), (3, 96, 96)])
+def test_stem_tail_kernels_gpu(backend, N, H, W):
+    _stem_tail_case("cuda", N, H, W, 64, 1)
 
 
 # ------------------------------------------------------------------ the four heads
