@@ -837,27 +837,28 @@ int lbc_op_stem(const float* img, const uint8_t* img_u8, int layout, const float
                   "stem weight gradient (tc) declined the shape");
         LBC_CHECK(fast::stem_unpack_wgrad(dwc, dw, C, Kp, s), "stem_unpack_wgrad failed");
       }
-    } else if (C <= 4) {
-      bf16 *x4 = t.get<bf16>((int64_t)N * (H + 6) * (W + 8) * 4), *w224 = t.get<bf16>(64 * 224), *yb = t.get<bf16>(ny);
+    } else if (fast::stem_ch(C) && !(C > 4 && normalize)) {
+      const int CH = fast::stem_ch(C);
+      bf16 *x4 = t.get<bf16>((int64_t)N * (H + 6) * (W + 8) * CH), *w224 = t.get<bf16>(64 * 7 * 8 * CH), *yb = t.get<bf16>(ny);
       bool ok = img_u8 && !img ? fast::stem_pad4_u8_bf16(img_u8, layout, x4, N, C, H, W, normalize != 0, s)
                                : fast::stem_pad4_bf16(imgf, x4, N, C, H, W, normalize != 0, s);
       LBC_CHECK(ok, "lbc_op_stem: stem_pad4 unavailable (fast kernels disabled or host-emulation build)");
-      if (x4_out) ref::cast<bf16, float>(s, x4, x4_out, (int64_t)N * (H + 6) * (W + 8) * 4);
+      if (x4_out) ref::cast<bf16, float>(s, x4, x4_out, (int64_t)N * (H + 6) * (W + 8) * CH);
       LBC_CHECK(fast::stem_pack_w224_bf16(w_ref, w224, C, s), "stem_pack_w224 failed");
       if (y) {
         int rows = 0;
         float* part = stats_out ? fast::stat_partial_buffer() : nullptr;
-        LBC_CHECK(fast::stem_conv_bf16(x4, w224, yb, N, H, W, OH, OW, nullptr, part, &rows, s), "stem_conv_bf16 declined the shape");
+        LBC_CHECK(fast::stem_conv_bf16(x4, w224, yb, N, H, W, OH, OW, nullptr, part, &rows, s, CH), "stem_conv_bf16 declined the shape");
         if (stats_out) LBC_CHECK(part && fast::col_finalize_bf16(part, rows, 128, stats_out, s), "col_finalize failed");
         ref::cast<bf16, float>(s, yb, y, ny);
       }
       if (dy && dw) {
         bf16* dyb = t.get<bf16>(ny);
         ref::cast<float, bf16>(s, dy, dyb, ny);
-        LBC_CHECK(fast::stem_wgrad_bf16(x4, dyb, dw, N, C, H, W, OH, OW, s), "stem_wgrad_bf16 declined the shape");
+        LBC_CHECK(fast::stem_wgrad_bf16(x4, dyb, dw, N, C, H, W, OH, OW, s, CH), "stem_wgrad_bf16 declined the shape");
       }
-    } else {   // C > 4 (teacher, 7 channels): explicit bf16 column tensor + the generic GEMM kernels as a 1x1 convolution
-      LBC_CHECK(!x4_out && !stats_out, "lbc_op_stem: x4_out / stats_out need C <= 4");
+    } else {   // C > 8: explicit bf16 column tensor + the generic GEMM kernels as a 1x1 convolution
+      LBC_CHECK(!x4_out && !stats_out, "lbc_op_stem: x4_out / stats_out need C <= 8");
       const int Kp = ((49 * C + 63) / 64) * 64;
       bf16 *col = t.get<bf16>((int64_t)N * OH * OW * Kp), *wp = t.get<bf16>((int64_t)64 * Kp), *yb = t.get<bf16>(ny);
       ConvL g = make_conv(OH, OW, Kp, 64, 1, 1, 0);

@@ -213,10 +213,53 @@ static bool launch_stem_pad4(const void* img, bf16* x4, int B, int C, int H, int
   LBC_CUDA(cudaGetLastError());
   return true;
 }
+// 8-channel padded image (C_in 5..8: the teacher's 7-channel bird's-eye view): one thread per padded pixel, one 16-byte store
+template <bool U8>
+__global__ void __launch_bounds__(256) stem_pad8_kernel(const void* __restrict__ img, int layout, uint4* __restrict__ x8, int B,
+                                                        int C, int H, int W) {
+  const int HP = H + 6, WP = W + 8;
+  const int64_t n = (int64_t)B * HP * WP;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % WP);
+    const int64_t t = i / WP;
+    const int row = (int)(t % HP);
+    const int b = (int)(t / HP);
+    const int ih = row - 3, iw = col - 4;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      for (int c = 0; c < C; ++c) {
+        if (U8) {
+          const int64_t j = layout == 1 ? (((int64_t)b * H + ih) * W + iw) * C + c : (((int64_t)b * C + c) * H + ih) * W + iw;
+          v[c] = (float)__ldg((const uint8_t*)img + j) / 255.0f;
+        } else {
+          v[c] = __ldg((const float*)img + (((int64_t)b * C + c) * H + ih) * W + iw);
+        }
+      }
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = (uint32_t)float_to_bf16(v[2 * q]).v | ((uint32_t)float_to_bf16(v[2 * q + 1]).v << 16);
+    x8[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+template <bool U8>
+static bool launch_stem_pad8(const void* img, int layout, bf16* x8, int B, int C, int H, int W, lbc_stream_t s) {
+  const int64_t n = (int64_t)B * (H + 6) * (W + 8);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)sms * 16;
+  if (blocks > cap) blocks = cap;
+  stem_pad8_kernel<U8><<<(unsigned)blocks, 256, 0, s>>>(img, layout, (uint4*)x8, B, C, H, W);
+  LBC_LAUNCHED(U8 ? "stem_pad8_kernel<u8>" : "stem_pad8_kernel<f32>");
+  LBC_CUDA(cudaGetLastError());
+  return true;
+}
 struct k_stem_pad4;
 struct k_stem_w224;
 // x4[b][ih+3][iw+4][c] = normalised pixel (c < C), zero elsewhere (borders, 4th channel)
 bool stem_pad4_bf16(const float* img, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s) {
+  if (enabled() && C > 4 && C <= 8 && !normalize) return launch_stem_pad8<false>(img, 0, x4, B, C, H, W, s);
   if (!enabled() || C > 4) return false;
   if (W % 4 == 0 && (C == 3 || !normalize)) return launch_stem_pad4<0>(img, x4, B, C, H, W, normalize, s);
   const int HP = H + 6, WP = W + 8;
@@ -252,6 +295,7 @@ struct k_stem_pad4_u8;
 // two-step path (u8_to_f32_nchw + stem_pad4_bf16), so the result is bit-identical while the 189 MB fp32 image
 // (one write + one read per step at B = 256) never exists.
 bool stem_pad4_u8_bf16(const uint8_t* img, int layout, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s) {
+  if (enabled() && C > 4 && C <= 8 && !normalize) return launch_stem_pad8<true>(img, layout, x4, B, C, H, W, s);
   if (!enabled() || C > 4) return false;
   if (W % 4 == 0 && (C == 3 || !normalize))
     return layout == 1 ? launch_stem_pad4<2>(img, x4, B, C, H, W, normalize, s) : launch_stem_pad4<1>(img, x4, B, C, H, W, normalize, s);
@@ -283,14 +327,17 @@ bool stem_pad4_u8_bf16(const uint8_t* img, int layout, bf16* x4, int B, int C, i
   });
   return true;
 }
-// w224[co][kh][kw'][c]: kw' = kw + 1 in 0..7 (kw' = 0 and c >= C are zero)
+// w224[co][kh][kw'][c], c < CH = stem_ch(C): kw' = kw + 1 in 0..7 (kw' = 0 and c >= C are zero)
 bool stem_pack_w224_bf16(const float* w_ref, bf16* w224, int C, lbc_stream_t s) {
-  par_for<k_stem_w224>(s, (int64_t)64 * 224, [=] __device__(int64_t i) {
-    int e = (int)(i % 32);
-    int64_t t = i / 32;
+  const int CH = stem_ch(C);
+  if (!CH) return false;
+  const int KR = 8 * CH;
+  par_for<k_stem_w224>(s, (int64_t)64 * 7 * KR, [=] __device__(int64_t i) {
+    int e = (int)(i % KR);
+    int64_t t = i / KR;
     int kh = (int)(t % 7);
     int co = (int)(t / 7);
-    int kwp = e >> 2, c = e & 3;
+    int kwp = e / CH, c = e % CH;
     float v = 0.f;
     if (kwp >= 1 && c < C) v = w_ref[(((int64_t)co * C + c) * 7 + kh) * 7 + (kwp - 1)];
     w224[i] = float_to_bf16(v);

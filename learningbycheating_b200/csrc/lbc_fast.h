@@ -212,13 +212,16 @@ bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, i
 bool stem_pack_weight_bf16(const float* w_ref, bf16* wp, int C, int Kp, lbc_stream_t s);      // [64][C][7][7] -> [64][Kp]
 bool stem_unpack_wgrad(const float* dw_col, float* dw_ref, int C, int Kp, lbc_stream_t s);    // [64][Kp] -> [64][C][7][7]
 
-// ---- stem without a column tensor (C_in <= 4): zero-padded NHWC4 bf16 image + overlapping-window TMA (lbc_fast_conv.cu)
+// ---- stem without a column tensor: zero-padded NHWC bf16 image [B][H+6][W+8][CH] + overlapping-window TMA (lbc_fast_conv.cu).
+// CH = 4 for C_in <= 4 (camera), CH = 8 for C_in <= 8 (the teacher's 7-channel bird's-eye view): stem_ch(C_in).
+inline int stem_ch(int C) { return C <= 4 ? 4 : (C <= 8 ? 8 : 0); }
 bool stem_pad4_bf16(const float* img, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s);
 bool stem_pad4_u8_bf16(const uint8_t* img, int layout, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s);
-bool stem_pack_w224_bf16(const float* w_ref, bf16* w224, int C, lbc_stream_t s);   // [64][C][7][7] -> [64][7][8 px][4 ch]
+bool stem_pack_w224_bf16(const float* w_ref, bf16* w224, int C, lbc_stream_t s);   // [64][C][7][7] -> [64][7][8 px][CH ch]
 bool stem_conv_bf16(const bf16* x4, const bf16* w224, bf16* raw, int B, int H, int W, int OH, int OW, const float* bias,
-                    float* stat_partial, int* stat_rows, lbc_stream_t s);
-bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C, int H, int W, int OH, int OW, lbc_stream_t s);
+                    float* stat_partial, int* stat_rows, lbc_stream_t s, int CH = 4);
+bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C, int H, int W, int OH, int OW, lbc_stream_t s,
+                     int CH = 4);
 
 }  // namespace fast
 }  // namespace lbc

@@ -875,12 +875,20 @@ struct StemParams {
   int stat_C;
   int valid_n;
 };
+// CH = channels of the padded image (4: camera RGB, 8: the 7-channel bird's-eye view): one kernel row of one output pixel is
+// 8 px x CH ch = 8*CH bf16 = 64 or 128 contiguous bytes (SWIZZLE_64B / SWIZZLE_128B operands)
+template <int CH>
+struct StemGeom {
+  static constexpr int ROWB = CH * 16;             // bytes of one window row
+  static constexpr int A_BYTES_ = 128 * ROWB;      // one A box: 128 output pixels
+  static constexpr int KROW = 8 * CH;              // K elements per kernel row
+};
 constexpr int ASTEM_BYTES = 128 * 64;
 
-template <int STAGES>
+template <int STAGES, int CH = 4>
 struct SmemPlanStem {
-  static constexpr int BRES_BYTES = 7 * 64 * 64;
-  static constexpr int OUT_OFF = STAGES * ASTEM_BYTES + BRES_BYTES;
+  static constexpr int BRES_BYTES = 7 * 64 * StemGeom<CH>::ROWB;
+  static constexpr int OUT_OFF = STAGES * StemGeom<CH>::A_BYTES_ + BRES_BYTES;
   static constexpr int BAR_OFF = OUT_OFF + A_BYTES;
   static constexpr int RED_OFF = BAR_OFF + 256;
   static constexpr int TOTAL = RED_OFF + 2048 + 256 + 1024;
@@ -895,11 +903,13 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
   return d;
 }
 
-template <int STAGES>
-__global__ void __launch_bounds__(192, 2)
+template <int STAGES, int CH>
+__global__ void __launch_bounds__(192, CH == 4 ? 2 : 1)
 stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant__ CUtensorMap mX1,
                  const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mO, const StemParams p) {
-  typedef SmemPlanStem<STAGES> SP;
+  typedef SmemPlanStem<STAGES, CH> SP;
+  constexpr int ASTEM_BYTES = StemGeom<CH>::A_BYTES_;   // (shadows the 4-channel constant)
+  constexpr int WROW_BYTES = 64 * StemGeom<CH>::ROWB;   // weights of one kernel row: 64 output channels
   constexpr int BN = 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -941,7 +951,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant_
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(bfull, SP::BRES_BYTES);
-      for (int kh = 0; kh < 7; ++kh) tma_load_2d(&mB, bres + kh * 4096, bfull, kh * 32, 0);
+      for (int kh = 0; kh < 7; ++kh) tma_load_2d(&mB, bres + kh * WROW_BYTES, bfull, kh * StemGeom<CH>::KROW, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -975,10 +985,11 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant_
         mbar_wait(&full[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const uint64_t ad = umma_desc_k_sw64(smem_u32(smem + stage * ASTEM_BYTES));
-          const uint64_t bd = umma_desc_k_sw64(smem_u32(bres + kh * 4096));
+          const uint32_t aaddr = smem_u32(smem + stage * ASTEM_BYTES), baddr = smem_u32(bres + kh * WROW_BYTES);
+          const uint64_t ad = CH == 4 ? umma_desc_k_sw64(aaddr) : umma_desc_k_sw128(aaddr);
+          const uint64_t bd = CH == 4 ? umma_desc_k_sw64(baddr) : umma_desc_k_sw128(baddr);
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk)
+          for (int kk = 0; kk < StemGeom<CH>::KROW / 16; ++kk)
             umma_bf16(tmem_d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (kh | kk) != 0);
           umma_commit(&empty[stage]);
           if (kh == 6) umma_commit(&tfull[acc]);
@@ -1076,11 +1087,14 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw64(uint32_t smem_addr, uint32
   d |= (uint64_t)4 << 61;
   return d;
 }
-template <int STAGES>
+template <int STAGES, int CH>
 __global__ void __launch_bounds__(192, 1)
 stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant__ CUtensorMap mX0,
                   const __grid_constant__ CUtensorMap mX1, const StemWgradParams p) {
-  constexpr int A_ST = 4 * ASTEM_BYTES, STAGE_BYTES = A_ST + A_BYTES;
+  constexpr int ASTEM_BYTES = StemGeom<CH>::A_BYTES_;
+  constexpr int KROW = StemGeom<CH>::KROW;         // window elements of one kernel row = M rows it contributes
+  constexpr int RPT = 128 / KROW;                  // kernel rows per 128-row M tile (4 or 2)
+  constexpr int A_ST = RPT * ASTEM_BYTES, STAGE_BYTES = A_ST + A_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -1107,8 +1121,9 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const int mt = blockIdx.x & 1;          // kernel rows 4*mt .. 4*mt+3
-  const int split = blockIdx.x >> 1;
+  constexpr int MT = 8 / RPT;               // M tiles covering kernel rows 0..7 (row 7 does not exist)
+  const int mt = blockIdx.x % MT;          // kernel rows RPT*mt .. RPT*mt+RPT-1
+  const int split = blockIdx.x / MT;
   const int kt0 = split * p.k_per_split;
   int kt1 = kt0 + p.k_per_split;
   if (kt1 > p.k_tiles) kt1 = p.k_tiles;
@@ -1126,8 +1141,8 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
         uint8_t* sa = smem + stage * STAGE_BYTES;
         mbar_expect_tx(&full[stage], STAGE_BYTES);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int kh = mt * 4 + j;
+        for (int j = 0; j < RPT; ++j) {
+          int kh = mt * RPT + j;
           if (kh > 6) kh = 6;   // row 7 does not exist: load a valid duplicate, its output rows are skipped
           tma_load_4d((kh & 1) ? &mX1 : &mX0, sa + j * ASTEM_BYTES, &full[stage], 0, w0, h0 + (kh >> 1), n0);
         }
@@ -1148,11 +1163,12 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t ad = umma_desc_mn_sw64(sa, ASTEM_BYTES);
+        const uint64_t ad = CH == 4 ? umma_desc_mn_sw64(sa, ASTEM_BYTES) : umma_desc_mn_sw128(sa, ASTEM_BYTES);
         const uint64_t bd = umma_desc_mn_sw128(sa + A_ST, A_BYTES);
+        constexpr int A_STEP = 16 * StemGeom<CH>::ROWB;   // 16 pixels per MMA: two 8-row groups of the A rows (64 / 128 B each)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)   // 16 pixels per MMA: two 8-row groups = 1024 B (A, 64-B rows) / 2048 B (B, 128-B rows)
-          umma_bf16(tmem_base, ad + (uint64_t)(kk * (1024 >> 4)), bd + (uint64_t)(kk * (2048 >> 4)), idesc, (k | kk) != 0);
+        for (int kk = 0; kk < 8; ++kk)   // B: two 8-row groups of 128-byte rows = 2048 B
+          umma_bf16(tmem_base, ad + (uint64_t)(kk * (A_STEP >> 4)), bd + (uint64_t)(kk * (2048 >> 4)), idesc, (k | kk) != 0);
         umma_commit(&empty[stage]);
         if (k == n_k - 1) umma_commit(tfull);
       }
@@ -1165,9 +1181,9 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
   } else if (n_k > 0) {
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int kh = mt * 4 + (m >> 5);
-    const int e = m & 31;
-    const int kwp = e >> 2, c = e & 3;
+    const int kh = mt * RPT + m / KROW;
+    const int e = m % KROW;
+    const int kwp = e / CH, c = e % CH;
     mbar_wait(tfull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -1424,29 +1440,31 @@ static bool try_conv3x3_c64(const bf16* in, const void* wpack, bf16* out, int B,
 }
 
 
-// ---- stem host side: x4 = zero-padded NHWC4 bf16 image [B][H+6][W+8][4] ----
+// ---- stem host side: x4 = zero-padded NHWC bf16 image [B][H+6][W+8][CH], CH = 4 (C_in <= 4) or 8 (C_in <= 8) ----
 static CUtensorMap make_map_stem(const void* base, int OW, int rows2, int B, int64_t pitch_bytes, int64_t img_bytes, int bw,
-                                 int bh, int bn) {
+                                 int bh, int bn, int CH) {
   CUtensorMap m;
-  cuuint64_t dims[4] = {32, (cuuint64_t)OW, (cuuint64_t)rows2, (cuuint64_t)B};
-  cuuint64_t strides[3] = {16, (cuuint64_t)(2 * pitch_bytes), (cuuint64_t)img_bytes};   // 16 B: overlapping 64-byte windows
-  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  // W stride = one output pixel = 2 input pixels: overlapping 8-pixel windows (accepted by cuTensorMapEncodeTiled, verified)
+  cuuint64_t dims[4] = {(cuuint64_t)(8 * CH), (cuuint64_t)OW, (cuuint64_t)rows2, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)(2 * CH * 2), (cuuint64_t)(2 * pitch_bytes), (cuuint64_t)img_bytes};
+  cuuint32_t box[4] = {(cuuint32_t)(8 * CH), (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CH == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LBC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stem window map) failed: " + std::to_string((int)r));
   return m;
 }
-static CUtensorMap make_map_2d_sw64(const void* base, int64_t K, int64_t rows, int brows) {
+static CUtensorMap make_map_stem_w(const void* base, int64_t rows, int brows, int CH) {   // weights [64][7 * 8*CH]
   CUtensorMap m;
+  const int64_t K = 7 * 8 * CH;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(K * 2)};
-  cuuint32_t box[2] = {32, (cuuint32_t)brows};
+  cuuint32_t box[2] = {(cuuint32_t)(8 * CH), (cuuint32_t)brows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CH == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LBC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stem weights) failed: " + std::to_string((int)r));
   return m;
 }
@@ -1456,10 +1474,28 @@ static bool stem_geometry(int OH, int OW, int B, int& TW, int& TH, int& TN) {
   TN = 128 / (TW * TH);
   return (OW % TW) == 0 && (OH % TH) == 0 && TN <= 256;
 }
-// raw[B,OH,OW,64] = conv7x7/s2(x4) (+ negshift), optional BN statistics partials
+template <int CH>
+static void launch_stem_conv(const CUtensorMap& mX0, const CUtensorMap& mX1, const CUtensorMap& mB, const CUtensorMap& mO,
+                             const StemParams& p, lbc_stream_t s) {
+  constexpr int STAGES = CH == 4 ? 7 : 5;
+  constexpr int PER_SM = CH == 4 ? 2 : 1;
+  typedef SmemPlanStem<STAGES, CH> SP;
+  static_assert(SP::TOTAL <= 232448, "stem smem plan exceeds 227 KB");
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(stem_conv_kernel<STAGES, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    configured = true;
+  }
+  int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  int grid = tiles < PER_SM * sm_count() ? tiles : PER_SM * sm_count();
+  stem_conv_kernel<STAGES, CH><<<grid, 192, SP::TOTAL, s>>>(mX0, mX1, mB, mO, p);
+  LBC_LAUNCHED(CH == 4 ? "stem_conv_kernel" : "stem_conv_kernel<8ch>");
+  LBC_CUDA(cudaGetLastError());
+}
+// raw[B,OH,OW,64] = conv7x7/s2(x4) (+ negshift), optional BN statistics partials; x4 / w224 in the CH-channel layouts
 bool stem_conv_bf16(const bf16* x4, const bf16* w224, bf16* raw, int B, int H, int W, int OH, int OW, const float* bias,
-                    float* stat_partial, int* stat_rows, lbc_stream_t s) {
-  if ((H % 2) || (W % 2) || OH * 2 != H || OW * 2 != W) return false;
+                    float* stat_partial, int* stat_rows, lbc_stream_t s, int CH) {
+  if ((H % 2) || (W % 2) || OH * 2 != H || OW * 2 != W || (CH != 4 && CH != 8)) return false;
   StemParams p;
   memset(&p, 0, sizeof(p));
   if (!stem_geometry(OH, OW, B, p.TW, p.TH, p.TN)) return false;
@@ -1472,30 +1508,40 @@ bool stem_conv_bf16(const bf16* x4, const bf16* w224, bf16* raw, int B, int H, i
   p.valid_n = B;
   {
     const int tiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
-    if (stat_rows) *stat_rows = tiles_total < 2 * sm_count() ? tiles_total : 2 * sm_count();   // one partial row per CTA
+    const int ctas = (CH == 4 ? 2 : 1) * sm_count();
+    if (stat_rows) *stat_rows = tiles_total < ctas ? tiles_total : ctas;   // one partial row per CTA
   }
-  const int64_t pitch = (int64_t)(W + 8) * 8, img = pitch * (H + 6);
-  CUtensorMap mX0 = make_map_stem(x4, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN);
-  CUtensorMap mX1 = make_map_stem((const uint8_t*)x4 + pitch, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN);
-  CUtensorMap mB = make_map_2d_sw64(w224, 224, 64, 64);
+  const int64_t pitch = (int64_t)(W + 8) * CH * 2, img = pitch * (H + 6);
+  CUtensorMap mX0 = make_map_stem(x4, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN, CH);
+  CUtensorMap mX1 = make_map_stem((const uint8_t*)x4 + pitch, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN, CH);
+  CUtensorMap mB = make_map_stem_w(w224, 64, 64, CH);
   const int64_t eb = 2;
   CUtensorMap mO = make_map_4d(raw, 64, OW, OH, B, 64 * eb, (int64_t)OW * 64 * eb, (int64_t)OH * OW * 64 * eb, p.TW, p.TH, p.TN);
-  typedef SmemPlanStem<7> SP;
-  static bool configured = false;
-  if (!configured) {
-    LBC_CUDA(cudaFuncSetAttribute(stem_conv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
-    configured = true;
-  }
-  int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
-  stem_conv_kernel<7><<<grid, 192, SP::TOTAL, s>>>(mX0, mX1, mB, mO, p);
-  LBC_LAUNCHED("stem_conv_kernel");
-  LBC_CUDA(cudaGetLastError());
+  if (CH == 4)
+    launch_stem_conv<4>(mX0, mX1, mB, mO, p, s);
+  else
+    launch_stem_conv<8>(mX0, mX1, mB, mO, p, s);
   return true;
 }
+template <int CH>
+static void launch_stem_wgrad(const CUtensorMap& mDY, const CUtensorMap& mX0, const CUtensorMap& mX1, const StemWgradParams& p,
+                              lbc_stream_t s) {
+  constexpr int STAGES = 4;
+  constexpr int MT = 8 / (128 / (8 * CH));   // M tiles: 2 (CH = 4) or 4 (CH = 8)
+  const int smem = STAGES * ((128 / (8 * CH)) * StemGeom<CH>::A_BYTES_ + A_BYTES) + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<STAGES, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  stem_wgrad_kernel<STAGES, CH><<<MT * p.splits, 192, smem, s>>>(mDY, mX0, mX1, p);
+  LBC_LAUNCHED(CH == 4 ? "stem_wgrad_kernel" : "stem_wgrad_kernel<8ch>");
+  LBC_CUDA(cudaGetLastError());
+}
 // dw_ref[64][C][7][7] = sum_pixels dy x window(x4); dw_ref is zeroed here
-bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C, int H, int W, int OH, int OW, lbc_stream_t s) {
-  if ((H % 2) || (W % 2) || OH * 2 != H || OW * 2 != W || C > 4) return false;
+bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C, int H, int W, int OH, int OW, lbc_stream_t s,
+                     int CH) {
+  if ((H % 2) || (W % 2) || OH * 2 != H || OW * 2 != W || C > CH || (CH != 4 && CH != 8)) return false;
   StemWgradParams p;
   memset(&p, 0, sizeof(p));
   if (!stem_geometry(OH, OW, B, p.TW, p.TH, p.TN)) return false;
@@ -1503,28 +1549,22 @@ bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C
   p.tiles_h = OH / p.TH;
   p.tiles_n = (B + p.TN - 1) / p.TN;
   p.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  int splits = sm_count() / 2;
+  int splits = sm_count() / (CH == 4 ? 2 : 4);
   if (splits > p.k_tiles / 4) splits = p.k_tiles / 4 > 0 ? p.k_tiles / 4 : 1;
   p.k_per_split = (p.k_tiles + splits - 1) / splits;
   p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
   p.C = C;
   p.dw_ref = dw_ref;
-  const int64_t pitch = (int64_t)(W + 8) * 8, img = pitch * (H + 6);
-  CUtensorMap mX0 = make_map_stem(x4, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN);
-  CUtensorMap mX1 = make_map_stem((const uint8_t*)x4 + pitch, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN);
+  const int64_t pitch = (int64_t)(W + 8) * CH * 2, img = pitch * (H + 6);
+  CUtensorMap mX0 = make_map_stem(x4, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN, CH);
+  CUtensorMap mX1 = make_map_stem((const uint8_t*)x4 + pitch, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN, CH);
   const int64_t eb = 2;
   CUtensorMap mDY = make_map_4d(dy, 64, OW, OH, B, 64 * eb, (int64_t)OW * 64 * eb, (int64_t)OH * OW * 64 * eb, p.TW, p.TH, p.TN);
-  constexpr int STAGES = 4;
-  const int smem = STAGES * (4 * ASTEM_BYTES + A_BYTES) + 256 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    LBC_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
   LBC_CUDA(cudaMemsetAsync(dw_ref, 0, sizeof(float) * 64 * C * 49, s));
-  stem_wgrad_kernel<STAGES><<<2 * p.splits, 192, smem, s>>>(mDY, mX0, mX1, p);
-  LBC_LAUNCHED("stem_wgrad_kernel");
-  LBC_CUDA(cudaGetLastError());
+  if (CH == 4)
+    launch_stem_wgrad<4>(mDY, mX0, mX1, p, s);
+  else
+    launch_stem_wgrad<8>(mDY, mX0, mX1, p, s);
   return true;
 }
 
@@ -2615,8 +2655,8 @@ bool conv_dgrad_ds_bf16(const ConvL&, const bf16*, const bf16*, bf16*, int, lbc_
 void set_c64_variant(bool) {}
 void set_pair_mode(int) {}
 int pair_mode() { return 0; }
-bool stem_conv_bf16(const bf16*, const bf16*, bf16*, int, int, int, int, int, const float*, float*, int*, lbc_stream_t) { return false; }
-bool stem_wgrad_bf16(const bf16*, const bf16*, float*, int, int, int, int, int, int, lbc_stream_t) { return false; }
+bool stem_conv_bf16(const bf16*, const bf16*, bf16*, int, int, int, int, int, const float*, float*, int*, lbc_stream_t, int) { return false; }
+bool stem_wgrad_bf16(const bf16*, const bf16*, float*, int, int, int, int, int, int, lbc_stream_t, int) { return false; }
 bool tc_split(const float*, void*, int64_t, int, int, float, lbc_stream_t) { return false; }
 bool conv_fwd_tc(const ConvL&, const float*, const void*, float*, int, const float*, bool, int, const TcWork&, lbc_stream_t) { return false; }
 bool conv_dgrad_tc(const ConvL&, const float*, const float*, float*, int, const float*, bool, int, const TcWork&, lbc_stream_t) { return false; }

@@ -195,7 +195,7 @@ static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_s
 struct BnFinalizeArgs {
   const float* partial;   // [P][2C]
   int P, C;
-  int64_t M;
+  double inv_m, unbias;   // 1 / M and M / (M - 1)
   const float* gamma;
   const float* beta;
   float eps, momentum;
@@ -246,17 +246,23 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const BnFinalizeArgs 
       a.sums[c] = t0;
       a.sums[a.C + c] = t1;
     }
-    const double m = (double)t0 / (double)a.M;
-    double var = (double)t1 / (double)a.M - m * m;
+    // double only where it matters (sum / M and the E[x^2] - mean^2 cancellation), with multiplications by host-computed
+    // reciprocals; 1/sqrt = float rsqrt + one Newton step in double (the software double division / square root sequences
+    // made this kernel 3 us slower than the plain column sum it replaced)
+    const double m = (double)t0 * a.inv_m;
+    double var = (double)t1 * a.inv_m - m * m;
     if (var < 0.0) var = 0.0;
+    const double v = var + (double)a.eps;
+    double r = (double)rsqrtf((float)v);
+    r = r * (1.5 - 0.5 * v * r * r);
     const float mean = (float)m;
-    const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float rstd = (float)r;
     a.saved_mean[c] = mean;
     a.saved_rstd[c] = rstd;
     const float true_mean = a.negshift ? (float)(m - (double)a.negshift[c]) : mean;
     if (a.negshift) a.negshift[c] = -true_mean;   // centring estimate for the next forward pass
     a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * true_mean;
-    const double unb = var * ((double)a.M / (double)(a.M > 1 ? a.M - 1 : 1));
+    const double unb = var * a.unbias;
     a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unb;
     const float sc = a.gamma[c] * rstd;
     a.scsh[c] = sc;
@@ -273,7 +279,8 @@ bool bn_finalize_bf16(const float* partial, int rows, int C, int64_t M, const fl
   a.partial = partial;
   a.P = rows;
   a.C = C;
-  a.M = M;
+  a.inv_m = 1.0 / (double)M;
+  a.unbias = (double)M / (double)(M > 1 ? M - 1 : 1);
   a.gamma = gamma;
   a.beta = beta;
   a.eps = eps;
@@ -642,6 +649,67 @@ bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, l
 // Both pooling kernels are instruction-bound, not HBM-bound, so: index arithmetic in IdxT (32-bit whenever the element
 // count allows), and the per-channel constants hoisted out of the grid-stride loop (the stride is a multiple of tpr,
 // so a thread keeps its channel group).
+// One thread per (output position, 8 channels)
+template <typename IdxT>
+__global__ void __launch_bounds__(256) bn_relu_maxpool1_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, uint4* __restrict__ y,
+                                                              uint2* __restrict__ idx, int N, int H, int W, int tpr, int OH,
+                                                              int OW) {
+  const IdxT total = (IdxT)N * OH * OW * tpr;
+  const IdxT stride = (IdxT)gridDim.x * blockDim.x;   // multiple of tpr (tpr divides 256)
+  IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = (int)(i % (IdxT)tpr);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    sc[j] = gamma[c] * rstd[c];
+    sh[j] = beta[c] - mean[c] * sc[j];
+  }
+  for (; i < total; i += stride) {
+    IdxT p = i / (IdxT)tpr;
+    const int ow = (int)(p % (IdxT)OW);
+    p /= (IdxT)OW;
+    const int oh = (int)(p % (IdxT)OH);
+    const int b = (int)(p / (IdxT)OH);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+    const uint4* xb = x + (int64_t)b * H * W * tpr + cg;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * 2 - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * 2 - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        float f[8];
+        unpack8(__ldg(xb + (ih * W + iw) * tpr), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = fmaxf(f[j] * sc[j] + sh[j], 0.f);
+          // compare on the bf16-rounded activation, exactly what a materialised a_stem would hold
+          v = __bfloat162float(__float2bfloat16_rn(v));
+          if (v > best[j]) {
+            best[j] = v;
+            bi[j] = kh * 3 + kw;
+          }
+        }
+      }
+    }
+    y[i] = pack8(best);
+    uint2 id;
+    id.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    id.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    idx[i] = id;
+  }
+}
 // One thread computes a 2x2 block of pooled outputs (x 8 channels) from the 5x5 input patch they share: 25 loads +
 // BN/ReLU/round transforms for 4 outputs instead of 36 (the windows of neighbouring outputs overlap by one row / column).
 // Input pixels are visited in row-major order, so every window still sees its taps in (kh, kw) order and "first maximum"
@@ -735,17 +803,29 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const uint4* __res
 }
 bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           bf16* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, lbc_stream_t s) {
-  if (C % 8 || 256 % (C / 8) || (OH & 1) || (OW & 1)) return false;
-  int64_t total = (int64_t)N * (OH / 2) * (OW / 2) * (C / 8);
+  if (C % 8 || 256 % (C / 8)) return false;
+  static const int variant = [] {   // LBC_POOL_FWD: 0 = one output per thread, 1 = 2x2 output blocks (A/B on one box)
+    const char* e = getenv("LBC_POOL_FWD");
+    return e ? atoi(e) : 0;
+  }();
+  const bool blk = variant == 1 && !(OH & 1) && !(OW & 1);
+  int64_t total = blk ? (int64_t)N * (OH / 2) * (OW / 2) * (C / 8) : (int64_t)N * OH * OW * (C / 8);
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
-  if ((int64_t)N * H * W * (C / 8) < (int64_t)1 << 31)
+  const bool i32 = (int64_t)N * H * W * (C / 8) < (int64_t)1 << 31;
+  if (blk && i32)
     bn_relu_maxpool_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
                                                                        (uint2*)idx, N, H, W, C / 8, OH, OW);
-  else
+  else if (blk)
     bn_relu_maxpool_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
                                                                       (uint2*)idx, N, H, W, C / 8, OH, OW);
+  else if (i32)
+    bn_relu_maxpool1_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
+                                                                        (uint2*)idx, N, H, W, C / 8, OH, OW);
+  else
+    bn_relu_maxpool1_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
+                                                                       (uint2*)idx, N, H, W, C / 8, OH, OW);
   LBC_LAUNCHED("bn_relu_maxpool_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -922,7 +1002,11 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
 bool stem_pool_bn_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, float* dgamma, float* dbeta, bf16* dx, int N, int H, int W,
                            int C, int OH, int OW, float* sums, lbc_stream_t s) {
-  if (!enabled() || C % 8 || 256 % (C / 8) || (H & 1) || (W & 1)) return false;
+  static const int fused = [] {   // LBC_STEM_TAIL: 1 = pool backward fused into the BatchNorm backward, 0 = three kernels
+    const char* e = getenv("LBC_STEM_TAIL");
+    return e ? atoi(e) : 0;
+  }();
+  if (!fused || !enabled() || C % 8 || 256 % (C / 8) || (H & 1) || (W & 1)) return false;
   float* part = partial_buffer();
   if (!part) return false;
   int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);

@@ -257,9 +257,10 @@ class Net : public NetBase {
       stem_dw_col = alloc<float>(64 * Kp);
       if (tc) {
         stem_gemm.wp16 = alloc<float>(64 * Kp);
-      } else if (in_ch <= 4) {
-        stem_x4 = alloc<T>(B * (in_h + 6) * (in_w + 8) * 4);
-        stem_w224 = alloc<T>(64 * 224);
+      } else if (fast::stem_ch(in_ch)) {   // zero-padded NHWC4 / NHWC8 image + overlapping-window TMA: no column tensor
+        const int CH = fast::stem_ch(in_ch);
+        stem_x4 = alloc<T>(B * (in_h + 6) * (in_w + 8) * CH);
+        stem_w224 = alloc<T>(64 * 7 * 8 * CH);
       } else {
         stem_col = alloc<T>(B * stem_oh * stem_ow * Kp);
       }
@@ -634,7 +635,7 @@ class Net : public NetBase {
                           : fast::stem_pad4_bf16(image, (bf16*)stem_x4, B, in_ch, in_h, in_w, normalize, s)) &&
                 fast::stem_pack_w224_bf16(P + stem.w_off, (bf16*)stem_w224, in_ch, s) &&
                 fast::stem_conv_bf16((const bf16*)stem_x4, (const bf16*)stem_w224, (bf16*)r_stem, B, in_h, in_w, stem_oh,
-                                     stem_ow, stem_bn.negshift, part, &stem_stat_rows, s);
+                                     stem_ow, stem_bn.negshift, part, &stem_stat_rows, s, fast::stem_ch(in_ch));
       LBC_CHECK(ok, "stem direct (overlapping-window TMA) path failed");
       stem_fast_used = stem_direct_used = true;
       if (!part) stem_stat_rows = 0;
@@ -873,7 +874,7 @@ class Net : public NetBase {
     if (stem_direct_used) {
       ProfScope ps("conv_wgrad", s, conv_flops(stem, B), 0);
       stem_wgrad_done = fast::stem_wgrad_bf16((const bf16*)stem_x4, (const bf16*)tB, G + stem.w_off, B, in_ch, in_h, in_w,
-                                              stem_oh, stem_ow, s);
+                                              stem_oh, stem_ow, s, fast::stem_ch(in_ch));
       LBC_CHECK(stem_wgrad_done, "stem direct weight gradient failed");
     } else if (stem_fast_used) {
       ProfScope ps("conv_wgrad", s, conv_flops(stem, B), 0);

@@ -449,8 +449,9 @@ def _stem_case(dev, N, C, H, W, precision, frames):
     imgd = d(img) if frames == "f32" else None
     u8d = d(u8) if frames == "u8" else (d(u8.permute(0, 2, 3, 1)) if frames == "u8hwc" else None)
     wd, dyd = d(wgt), d(_nhwc(dy))
-    direct = precision == 1 and C <= 4
-    x4 = torch.empty(N, H + 6, W + 8, 4, device=dev) if direct else None
+    direct = precision == 1 and C <= 8        # padded NHWC4 (camera) / NHWC8 (7-channel bird's-eye view) operand
+    CH = 4 if C <= 4 else 8
+    x4 = torch.empty(N, H + 6, W + 8, CH, device=dev) if direct else None
     y, dw = torch.empty(N, OH, OW, 64, device=dev), torch.empty(64, C, 7, 7, device=dev)
     stats = torch.empty(128, device=dev) if direct else None
     if precision == 1:
@@ -464,7 +465,7 @@ def _stem_case(dev, N, C, H, W, precision, frames):
                                  H, W, _lib.ptr(x4), _lib.ptr(y), _lib.ptr(stats), _lib.ptr(dyd), _lib.ptr(dw), precision, None))
     if direct:
         # a2: NormalizeV2 fused into the writer of the padded operand -- bit-exact bf16 rounding of (x-mean)/std
-        pad = torch.zeros(N, H + 6, W + 8, 4)
+        pad = torch.zeros(N, H + 6, W + 8, CH)
         pad[:, 3:3 + H, 4:4 + W, :C] = _nhwc(xr)
         got = x4.cpu()
         assert (got - pad).abs().max() <= 2 ** -7 * 3, (got - pad).abs().max()        # at most one bf16 ulp (division rounding)
@@ -489,8 +490,9 @@ def test_stem_kernels_student_gpu(backend, frames):
 
 
 @pytest.mark.gpu
-def test_stem_kernels_teacher_gpu(backend):
-    _stem_case("cuda", 3, 7, 192, 192, 1, "f32")
+@pytest.mark.parametrize("frames", ["f32", "u8"])
+def test_stem_kernels_teacher_gpu(backend, frames):
+    _stem_case("cuda", 3, 7, 192, 192, 1, frames)
 
 
 @pytest.mark.gpu
