@@ -652,8 +652,8 @@ int lbc_op_bn_relu_maxpool(const float* x, const float* mean, const float* rstd,
   });
 }
 // Whole stem tail, train mode: y = maxpool3x3/s2/p1(relu(batchnorm(x))) with batch statistics, and its backward from
-// dy [N][OH][OW][C]: dgamma, dbeta, dx [N][H][W][C] (resnet.py:149-152).  bf16 path: the fused BN+ReLU+MaxPool forward and the
-// two-pass pool-backward + BatchNorm-backward kernels (the masked gradient of the BN output is never stored).
+// dy [N][OH][OW][C]: dgamma, dbeta, dx [N][H][W][C] (resnet.py:149-152).  bf16 path: the fused BN+ReLU+MaxPool forward, the
+// 2x2-block pool-backward kernel (with the ReLU mask recomputed from x) and the BatchNorm backward kernels, as the step runs them.
 int lbc_op_stem_tail(const float* x, const float* gamma, const float* beta, float* y, const float* dy, float* dgamma,
                      float* dbeta, float* dx, int N, int H, int W, int C, int precision, void* stream) {
   return guarded([&] {
@@ -681,8 +681,10 @@ int lbc_op_stem_tail(const float* x, const float* gamma, const float* beta, floa
       ref::cast<float, bf16>(s, dy, dyb, ny);
       ref::bn_stats<bf16>(s, xb, M, C, mean, var, ws);
       ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, nullptr, nullptr);
+      bf16* gb = t.get<bf16>(nx);   // gradient of the BN output = pool backward x ReLU mask
       bool ok = fast::Fast<bf16>::pool_fwd(xb, mean, rstd, gamma, beta, yb, idx, N, H, W, C, OH, OW, s) &&
-                fast::stem_pool_bn_bwd_bf16(dyb, idx, xb, mean, rstd, gamma, beta, dgamma, dbeta, dxb, N, H, W, C, OH, OW, sums, s);
+                fast::Fast<bf16>::pool_bwd(dyb, idx, xb, mean, rstd, gamma, beta, gb, N, H, W, C, OH, OW, s) &&
+                fast::Fast<bf16>::bn_bwd(gb, nullptr, xb, mean, rstd, gamma, dgamma, dbeta, dxb, M, C, sums, s);
       if (!ok) {
         bf16 *a = t.get<bf16>(nx), *g = t.get<bf16>(nx);
         ref::bn_apply<bf16>(s, xb, mean, rstd, gamma, beta, nullptr, true, a, M, C);

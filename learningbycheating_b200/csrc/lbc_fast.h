@@ -127,11 +127,6 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
                            const float* gamma, const float* beta, bf16* dx, int N, int H, int W, int C, int OH, int OW,
                            lbc_stream_t s);
 
-// stem tail backward in two passes: MaxPool backward + ReLU mask + BatchNorm backward (the masked gradient tensor is never stored)
-bool stem_pool_bn_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
-                           const float* gamma, const float* beta, float* dgamma, float* dbeta, bf16* dx, int N, int H, int W,
-                           int C, int OH, int OW, float* sums, lbc_stream_t s);
-
 // generic-T front ends: only T = bf16 has fast kernels
 template <class T> struct Fast {
   static bool bn_fwd(const T*, int64_t, int, const float*, const float*, float, float, float*, float*, float*, float*,

@@ -270,7 +270,8 @@ struct SmemPlan {
   static constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
   static constexpr int RED_OFF = BAR_OFF + 256;       // 128 x 4 floats: column-statistics scratch
-  static constexpr int TOTAL = RED_OFF + 2048 + 1024;  // barriers + scratch + alignment slack
+  static constexpr int CSTAT_OFF = RED_OFF + 2048;    // [2][Co <= 512] floats: this CTA's running column sums / sums of squares
+  static constexpr int TOTAL = CSTAT_OFF + 4096 + 1024;  // barriers + scratch + alignment slack
 };
 
 // ------------------------------------------------------------------------------------------- the kernel
@@ -434,6 +435,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool issuer = (threadIdx.x == 64);
+    // BatchNorm statistics: ONE partial row per CTA (the column sums of all its tiles, accumulated in shared memory in the
+    // fixed order of the tile walk), so the finalize kernel reads gridDim.x rows instead of one per 128-position tile
+    float* cstat = reinterpret_cast<float*>(smem + SP::CSTAT_OFF);
+    if (!OUT_F32 && p.stat_partial) {
+      for (int i = threadIdx.x - 64; i < 2 * p.stat_C; i += 128) cstat[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     int it = 0;
     for (int tile = walk0; tile < num_tiles; tile += walk_step, ++it) {
       const int acc = it & 1;
@@ -551,15 +559,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
               }
             }
           }
-          if (sub == 0) {
-            float* dst = p.stat_partial + (int64_t)m_tile * 2 * p.stat_C + n_tile * BN + hp * CW + col;
-            dst[0] = s0;
-            dst[1] = s1;
-            dst[p.stat_C] = q0;
-            dst[p.stat_C + 1] = q1;
+          if (sub == 0) {   // (the same thread owns a column pair in every tile: no race on cstat)
+            float* dst = cstat + n_tile * BN + hp * CW + col;
+            dst[0] += s0;
+            dst[1] += s1;
+            dst[p.stat_C] += q0;
+            dst[p.stat_C + 1] += q1;
           }
         }
       }
+    }
+    if (!OUT_F32 && p.stat_partial) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* dst = p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C;
+      for (int i = threadIdx.x - 64; i < 2 * p.stat_C; i += 128) dst[i] = cstat[i];
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -1238,7 +1251,7 @@ static bool tile_geometry(int OH, int OW, int B, ConvGemmParams& p) {
 }
 
 template <int BN, int STAGES, bool OUT_F32 = false>
-static void launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUtensorMap& mO, const ConvGemmParams& p,
+static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUtensorMap& mO, const ConvGemmParams& p,
                         lbc_stream_t s) {
   typedef SmemPlan<BN, STAGES, false, OUT_F32> SP;
   static bool configured = false;
@@ -1255,10 +1268,11 @@ static void launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUte
   else
     LBC_LAUNCHED((BN == 64 ? "conv_gemm_kernel<64>" : BN == 128 ? "conv_gemm_kernel<128>" : "conv_gemm_kernel<256>"));
   LBC_CUDA(cudaGetLastError());
+  return grid;
 }
 // CTA-pair variant: clusters of 2 (one TPC), persistent over ceil(tiles_m/2) * n_tiles_n pair tiles
 template <int BN, int STAGES, bool OUT_F32 = false>
-static void launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, const CUtensorMap& mO, const ConvGemmParams& p,
+static int launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, const CUtensorMap& mO, const ConvGemmParams& p,
                              lbc_stream_t s) {
   typedef SmemPlan<BN, STAGES, true, OUT_F32> SP;
   static_assert(SP::TOTAL <= 232448, "smem plan of the CTA-pair kernel exceeds 227 KB");
@@ -1297,6 +1311,7 @@ static void launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, c
   else
     LBC_LAUNCHED((BN == 128 ? "conv_gemm_kernel<128,pair>" : "conv_gemm_kernel<256,pair>"));
   LBC_CUDA(cudaGetLastError());
+  return 2 * clusters;
 }
 // kernel variants (LBC_PAIR overrides; tests toggle them through lbc_set_fast_kernels):
 //   bit 0: CTA-pair (cta_group::2) kernels for the BN >= 128 conv GEMMs   bit 1: row-of-taps weight gradient
@@ -1326,39 +1341,21 @@ static void apply_mode(ConvGemmParams& p, const GemmMode& m, int a_plane, int b_
   p.out_scale = m.out_scale;
 }
 // mB: weights [rows][K]; the box height is chosen here (BN rows, or BN/2 for the CTA-pair kernels)
-static void dispatch_gemm(int BN, const CUtensorMap* mA, const void* wbase, int64_t wK, int64_t wrows, const CUtensorMap& mO,
+// returns the number of CTAs launched (= rows of statistics partials, when asked for)
+static int dispatch_gemm(int BN, const CUtensorMap* mA, const void* wbase, int64_t wK, int64_t wrows, const CUtensorMap& mO,
                           const ConvGemmParams& p, lbc_stream_t s, bool out_f32 = false) {
   const bool pair = (g_pair_mode & 1) && BN >= 128;
   if (pair) {
     CUtensorMap mB = make_map_2d(wbase, wK, wrows, BN / 2);
-    if (out_f32) {
-      if (BN == 128)
-        launch_gemm_pair<128, 7, true>(mA, mB, mO, p, s);
-      else
-        launch_gemm_pair<256, 4, true>(mA, mB, mO, p, s);
-    } else if (BN == 128) {
-      launch_gemm_pair<128, 7>(mA, mB, mO, p, s);
-    } else {
-      launch_gemm_pair<256, 4>(mA, mB, mO, p, s);
-    }
-    return;
+    if (out_f32) return BN == 128 ? launch_gemm_pair<128, 7, true>(mA, mB, mO, p, s) : launch_gemm_pair<256, 4, true>(mA, mB, mO, p, s);
+    return BN == 128 ? launch_gemm_pair<128, 7>(mA, mB, mO, p, s) : launch_gemm_pair<256, 4>(mA, mB, mO, p, s);
   }
   CUtensorMap mB = make_map_2d(wbase, wK, wrows, BN);
-  if (out_f32) {
-    if (BN == 64)
-      launch_gemm<64, 6, true>(mA, mB, mO, p, s);
-    else if (BN == 128)
-      launch_gemm<128, 5, true>(mA, mB, mO, p, s);
-    else
-      launch_gemm<256, 3, true>(mA, mB, mO, p, s);
-    return;
-  }
-  if (BN == 64)
-    launch_gemm<64, 6>(mA, mB, mO, p, s);
-  else if (BN == 128)
-    launch_gemm<128, 5>(mA, mB, mO, p, s);
-  else
-    launch_gemm<256, 3>(mA, mB, mO, p, s);
+  if (out_f32)
+    return BN == 64    ? launch_gemm<64, 6, true>(mA, mB, mO, p, s)
+           : BN == 128 ? launch_gemm<128, 5, true>(mA, mB, mO, p, s)
+                       : launch_gemm<256, 3, true>(mA, mB, mO, p, s);
+  return BN == 64 ? launch_gemm<64, 6>(mA, mB, mO, p, s) : BN == 128 ? launch_gemm<128, 5>(mA, mB, mO, p, s) : launch_gemm<256, 3>(mA, mB, mO, p, s);
 }
 // N tile: 256 where it divides, unless the 128-wide tiling fills the persistent grid's rounds clearly better
 // (static round-robin over 148 CTAs: 480 tiles = 3.24 rounds -> 81 %, 960 tiles = 6.49 -> 93 %).
@@ -1586,11 +1583,10 @@ static bool conv_fwd_impl(const ConvL& c, const void* x, const void* wpack, void
   p.k_chunks = c.Ci / 64;
   p.bias = bias_co;   // per-output-channel constant added before the rounding (centring shift, see lbc_net.cu)
   p.relu = relu ? 1 : 0;
-  p.stat_partial = m.out_f32 ? nullptr : stat_partial;
+  p.stat_partial = (m.out_f32 || c.Co > 512) ? nullptr : stat_partial;   // (the per-CTA accumulator holds 2 x 512 floats)
   p.stat_C = c.Co;
   p.valid_n = B;
   apply_mode(p, m, c.Ci, c.Ci);
-  if (stat_rows) *stat_rows = m.out_f32 ? 0 : p.tiles_w * p.tiles_h * p.tiles_n;
   CUtensorMap mA[4];
   const int64_t eb = 2;
   const bf16* xb = (const bf16*)x;
@@ -1624,7 +1620,8 @@ static bool conv_fwd_impl(const ConvL& c, const void* x, const void* wpack, void
   const int64_t eo = m.out_f32 ? 4 : 2;
   CUtensorMap mO = make_map_4d(y, c.Co, c.OW, c.OH, B, c.Co * eo, (int64_t)c.OW * c.Co * eo, (int64_t)c.OH * c.OW * c.Co * eo,
                                p.TW, p.TH, p.TN, m.out_f32);
-  dispatch_gemm(BN, mA, wpack, (int64_t)c.K * c.K * CA, c.Co, mO, p, s, m.out_f32);
+  const int ctas = dispatch_gemm(BN, mA, wpack, (int64_t)c.K * c.K * CA, c.Co, mO, p, s, m.out_f32);
+  if (stat_rows) *stat_rows = p.stat_partial ? ctas : 0;   // one row of statistics partials per persistent CTA
   return true;
 }
 bool conv_fwd_bf16(const ConvL& c, const bf16* x, bf16* y, int B, const float* bias_co, lbc_stream_t s,

@@ -649,9 +649,8 @@ bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, l
 // Both pooling kernels are instruction-bound, not HBM-bound, so: index arithmetic in IdxT (32-bit whenever the element
 // count allows), and the per-channel constants hoisted out of the grid-stride loop (the stride is a multiple of tpr,
 // so a thread keeps its channel group).
-// One thread per (output position, 8 channels)
 template <typename IdxT>
-__global__ void __launch_bounds__(256) bn_relu_maxpool1_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, uint4* __restrict__ y,
                                                               uint2* __restrict__ idx, int N, int H, int W, int tpr, int OH,
@@ -710,122 +709,21 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool1_kernel(const uint4* __re
     idx[i] = id;
   }
 }
-// One thread computes a 2x2 block of pooled outputs (x 8 channels) from the 5x5 input patch they share: 25 loads +
-// BN/ReLU/round transforms for 4 outputs instead of 36 (the windows of neighbouring outputs overlap by one row / column).
-// Input pixels are visited in row-major order, so every window still sees its taps in (kh, kw) order and "first maximum"
-// keeps the meaning of nn.MaxPool2d.  OH, OW even.
-template <typename IdxT>
-__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
-                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, uint4* __restrict__ y,
-                                                              uint2* __restrict__ idx, int N, int H, int W, int tpr, int OH,
-                                                              int OW) {
-  const int OH2 = OH >> 1, OW2 = OW >> 1;
-  const IdxT total = (IdxT)N * OH2 * OW2 * tpr;
-  const IdxT stride = (IdxT)gridDim.x * blockDim.x;   // multiple of tpr (tpr divides 256)
-  IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
-  const int cg = (int)(i % (IdxT)tpr);
-  float sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
-    sc[j] = gamma[c] * rstd[c];
-    sh[j] = beta[c] - mean[c] * sc[j];
-  }
-  for (; i < total; i += stride) {
-    IdxT p = i / (IdxT)tpr;
-    const int qw = (int)(p % (IdxT)OW2);
-    p /= (IdxT)OW2;
-    const int qh = (int)(p % (IdxT)OH2);
-    const int b = (int)(p / (IdxT)OH2);
-    float best[2][2][8];
-    uint32_t bi[2][2][2];   // packed tap codes, 4 channels x 8 bits per word
-#pragma unroll
-    for (int a2 = 0; a2 < 2; ++a2)
-#pragma unroll
-      for (int b2 = 0; b2 < 2; ++b2) {
-        bi[a2][b2][0] = bi[a2][b2][1] = 0u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) best[a2][b2][j] = -INFINITY;
-      }
-    const uint4* xb = x + (int64_t)b * H * W * tpr + cg;
-    const int ih0 = 4 * qh - 1, iw0 = 4 * qw - 1;   // patch origin: input rows ih0..ih0+4, cols iw0..iw0+4
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {
-      const int ih = ih0 + r;
-      if (ih < 0 || ih >= H) continue;
-#pragma unroll
-      for (int c5 = 0; c5 < 5; ++c5) {
-        const int iw = iw0 + c5;
-        if (iw < 0 || iw >= W) continue;
-        float f[8];
-        unpack8(__ldg(xb + ((int64_t)ih * W + iw) * tpr), f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v = fmaxf(f[j] * sc[j] + sh[j], 0.f);
-          // compare on the bf16-rounded activation, exactly what a materialised a_stem would hold
-          f[j] = __bfloat162float(__float2bfloat16_rn(v));
-        }
-        // patch row r belongs to output row a2 with tap kh = r - 2*a2 in 0..2 (same for columns)
-#pragma unroll
-        for (int a2 = 0; a2 < 2; ++a2) {
-          const int kh = r - 2 * a2;
-          if (kh < 0 || kh > 2) continue;
-#pragma unroll
-          for (int b2 = 0; b2 < 2; ++b2) {
-            const int kw = c5 - 2 * b2;
-            if (kw < 0 || kw > 2) continue;
-            const uint32_t code = (uint32_t)(kh * 3 + kw);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (f[j] > best[a2][b2][j]) {
-                best[a2][b2][j] = f[j];
-                const int sft = (j & 3) * 8;
-                bi[a2][b2][j >> 2] = (bi[a2][b2][j >> 2] & ~(0xffu << sft)) | (code << sft);
-              }
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int a2 = 0; a2 < 2; ++a2)
-#pragma unroll
-      for (int b2 = 0; b2 < 2; ++b2) {
-        const int64_t o = (((int64_t)b * OH + (2 * qh + a2)) * OW + (2 * qw + b2)) * tpr + cg;
-        y[o] = pack8(best[a2][b2]);
-        uint2 id;
-        id.x = bi[a2][b2][0];
-        id.y = bi[a2][b2][1];
-        idx[o] = id;
-      }
-  }
-}
 bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           bf16* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, lbc_stream_t s) {
   if (C % 8 || 256 % (C / 8)) return false;
-  static const int variant = [] {   // LBC_POOL_FWD: 0 = one output per thread, 1 = 2x2 output blocks (A/B on one box)
-    const char* e = getenv("LBC_POOL_FWD");
-    return e ? atoi(e) : 0;
-  }();
-  const bool blk = variant == 1 && !(OH & 1) && !(OW & 1);
-  int64_t total = blk ? (int64_t)N * (OH / 2) * (OW / 2) * (C / 8) : (int64_t)N * OH * OW * (C / 8);
+  // (a variant computing 2x2 output blocks from the shared 5x5 patch -- 25 instead of 36 loads + transforms -- measured
+  // 0.05 ms per step SLOWER on the same box, 14.498 vs 14.450 ms: more registers, fewer threads; not kept)
+  int64_t total = (int64_t)N * OH * OW * (C / 8);
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
-  const bool i32 = (int64_t)N * H * W * (C / 8) < (int64_t)1 << 31;
-  if (blk && i32)
+  if ((int64_t)N * H * W * (C / 8) < (int64_t)1 << 31)
     bn_relu_maxpool_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
                                                                        (uint2*)idx, N, H, W, C / 8, OH, OW);
-  else if (blk)
+  else
     bn_relu_maxpool_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
                                                                       (uint2*)idx, N, H, W, C / 8, OH, OW);
-  else if (i32)
-    bn_relu_maxpool1_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
-                                                                        (uint2*)idx, N, H, W, C / 8, OH, OW);
-  else
-    bn_relu_maxpool1_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
-                                                                       (uint2*)idx, N, H, W, C / 8, OH, OW);
   LBC_LAUNCHED("bn_relu_maxpool_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -836,43 +734,26 @@ bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, c
 // (ph|ph+1, pw|pw+1), with FIXED tap codes per (pixel, window) -- so every thread runs the same nine compare-adds and loads
 // each window once.  (Round 1's one-pixel-per-thread kernel looked at up to nine (kh, kw) candidates per pixel with
 // parity-dependent branches that diverged inside every warp: 518 us for 1.19 GB at B = 256.)
-// MODE 0: dx = that gradient (the upstream gradient of the stem BatchNorm), written out.
-// MODE 1 / 2: the stem BatchNorm backward FUSED on top, so the 503 MB gradient tensor (B = 256) is never written or
-// re-read: MODE 1 accumulates this block's sum g and sum g*(x - mean)*rstd into a partial row (then col_finalize),
-// MODE 2 recomputes g and writes d(raw conv output) = k0*g + kb*x + ka directly.  (Unfused: pool backward 1.2 GB +
-// BN reduce 1.0 GB + BN apply 1.5 GB of traffic; fused: 0.7 + 1.2 GB.)
-template <typename IdxT, int MODE>
+// (A variant that fused the stem BatchNorm backward on top -- recomputing this gradient in the reduce and in the apply pass
+// instead of storing it, 1.9 GB instead of 3.7 GB of traffic at B = 256 -- measured the SAME step time on the same box,
+// 14.451 vs 14.450 ms: these kernels are bound by instruction issue, not by HBM; not kept.)
+template <typename IdxT>
 __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
                                                                const uint4* __restrict__ x, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, uint4* __restrict__ dx, int N,
-                                                               int H, int W, int tpr, int OH, int OW, float* partial,
-                                                               const float* __restrict__ sums, float* dgamma, float* dbeta) {
-  extern __shared__ float red[];   // MODE 1: [256][16]
+                                                               int H, int W, int tpr, int OH, int OW) {
   const int H2 = H >> 1, W2 = W >> 1;
   const IdxT total = (IdxT)N * H2 * W2 * tpr;
   const IdxT stride = (IdxT)gridDim.x * blockDim.x;   // multiple of tpr
   IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = (int)(i % (IdxT)tpr);
-  float sc[8], sh[8], mu[8], s0[8], s1[8], kb[8], ka[8];
+  float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cg * 8 + j;
     sc[j] = gamma[c] * rstd[c];
     sh[j] = beta[c] - mean[c] * sc[j];
-    mu[j] = mean[c];
-    s0[j] = s1[j] = 0.f;
-    kb[j] = ka[j] = 0.f;
-    if (MODE == 2) {
-      const float invM = 1.0f / ((float)N * (float)H * (float)W);
-      const float db = sums[c], dg = sums[tpr * 8 + c];
-      if (blockIdx.x == 0 && threadIdx.x < tpr) {
-        dbeta[c] = db;
-        dgamma[c] = dg;
-      }
-      kb[j] = -sc[j] * rstd[c] * dg * invM;
-      ka[j] = -sc[j] * db * invM - kb[j] * mu[j];
-    }
   }
   for (; i < total; i += stride) {
     IdxT p = i / (IdxT)tpr;
@@ -926,63 +807,9 @@ __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __re
           const float v = f[j] * sc[j] + sh[j];
           if (!(v > 0.f)) acc[a2][b2][j] = 0.f;
         }
-        if (MODE == 0) {
-          dx[e] = pack8(acc[a2][b2]);
-        } else if (MODE == 1) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s0[j] += acc[a2][b2][j];
-            s1[j] += acc[a2][b2][j] * (f[j] - mu[j]);
-          }
-        } else {
-          float o8[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o8[j] = fmaf(sc[j], acc[a2][b2][j], fmaf(kb[j], f[j], ka[j]));
-          dx[e] = pack8(o8);
-        }
+        dx[e] = pack8(acc[a2][b2]);
       }
   }
-  if (MODE == 1) {
-    const int t = threadIdx.x;
-    const int rpi = 256 / tpr;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s1[j] *= rstd[cg * 8 + j];
-      red[t * 16 + j] = s0[j];
-      red[t * 16 + 8 + j] = s1[j];
-    }
-    __syncthreads();
-    if (t < tpr) {   // thread t has channel group t (blockDim = 256 is a multiple of tpr)
-      for (int rr = 1; rr < rpi; ++rr) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s0[j] += red[(rr * tpr + t) * 16 + j];
-          s1[j] += red[(rr * tpr + t) * 16 + 8 + j];
-        }
-      }
-      const int C = tpr * 8;
-      float* dst = partial + (int64_t)blockIdx.x * 2 * C;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        dst[t * 8 + j] = s0[j];
-        dst[C + t * 8 + j] = s1[j];
-      }
-    }
-  }
-}
-template <int MODE>
-static void launch_pool_bwd(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
-                            const float* gamma, const float* beta, bf16* dx, int N, int H, int W, int C, int OH, int OW,
-                            int blocks, float* partial, const float* sums, float* dgamma, float* dbeta, lbc_stream_t s) {
-  const size_t smem = MODE == 1 ? 256 * 16 * sizeof(float) : 0;
-  if ((int64_t)N * H * W * (C / 8) < (int64_t)1 << 31)
-    maxpool_relu_bwd_kernel<uint32_t, MODE><<<(unsigned)blocks, 256, smem, s>>>(
-        (const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean, rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW, partial,
-        sums, dgamma, dbeta);
-  else
-    maxpool_relu_bwd_kernel<int64_t, MODE><<<(unsigned)blocks, 256, smem, s>>>(
-        (const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean, rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW, partial,
-        sums, dgamma, dbeta);
 }
 bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, bf16* dx, int N, int H, int W, int C, int OH, int OW,
@@ -992,35 +819,13 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
-  launch_pool_bwd<0>(dy, idx, x, mean, rstd, gamma, beta, dx, N, H, W, C, OH, OW, (int)blocks, nullptr, nullptr, nullptr, nullptr, s);
+  if ((int64_t)N * H * W * (C / 8) < (int64_t)1 << 31)
+    maxpool_relu_bwd_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean,
+                                                                        rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW);
+  else
+    maxpool_relu_bwd_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean,
+                                                                       rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW);
   LBC_LAUNCHED("maxpool_relu_bwd_kernel");
-  LBC_CUDA(cudaGetLastError());
-  return true;
-}
-// MaxPool backward + ReLU mask + BatchNorm backward of the stem in two passes over (dy, idx, raw): dgamma / dbeta and
-// dx = d(raw conv output); sums: >= 2C floats scratch
-bool stem_pool_bn_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,
-                           const float* gamma, const float* beta, float* dgamma, float* dbeta, bf16* dx, int N, int H, int W,
-                           int C, int OH, int OW, float* sums, lbc_stream_t s) {
-  static const int fused = [] {   // LBC_STEM_TAIL: 1 = pool backward fused into the BatchNorm backward, 0 = three kernels
-    const char* e = getenv("LBC_STEM_TAIL");
-    return e ? atoi(e) : 0;
-  }();
-  if (!fused || !enabled() || C % 8 || 256 % (C / 8) || (H & 1) || (W & 1)) return false;
-  float* part = partial_buffer();
-  if (!part) return false;
-  int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
-  int64_t blocks = (total + 255) / 256;
-  int64_t cap = (int64_t)sm_count2() * 6;
-  if (blocks > cap) blocks = cap;
-  launch_pool_bwd<1>(dy, idx, x, mean, rstd, gamma, beta, nullptr, N, H, W, C, OH, OW, (int)blocks, part, nullptr, nullptr, nullptr, s);
-  LBC_LAUNCHED("maxpool_relu_bwd_kernel<bn_reduce>");
-  col_finalize(part, (int)blocks, 2 * C, sums, s);
-  int64_t blocks2 = (total + 255) / 256;
-  cap = (int64_t)sm_count2() * 8;
-  if (blocks2 > cap) blocks2 = cap;
-  launch_pool_bwd<2>(dy, idx, x, mean, rstd, gamma, beta, dx, N, H, W, C, OH, OW, (int)blocks2, nullptr, sums, dgamma, dbeta, s);
-  LBC_LAUNCHED("maxpool_relu_bwd_kernel<bn_apply>");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -1042,8 +847,7 @@ bool bn_relu_maxpool_bf16(const bf16*, const float*, const float*, const float*,
                           int, int, int, lbc_stream_t) { return false; }
 bool maxpool_relu_bwd_bf16(const bf16*, const uint8_t*, const bf16*, const float*, const float*, const float*, const float*,
                            bf16*, int, int, int, int, int, int, lbc_stream_t) { return false; }
-bool stem_pool_bn_bwd_bf16(const bf16*, const uint8_t*, const bf16*, const float*, const float*, const float*, const float*, float*,
-                           float*, bf16*, int, int, int, int, int, int, float*, lbc_stream_t) { return false; }
+
 #endif
 
 }  // namespace fast

@@ -847,17 +847,7 @@ class Net : public NetBase {
     }
     // stem: maxpool -> relu -> bn -> conv1 weight gradient (no input gradient)
     int64_t Ms = (int64_t)B * stem_oh * stem_ow;
-    bool stem_tail_fused = false;
-    if (stem_pool_fused && std::is_same<T, bf16>::value) {
-      // pool backward + ReLU mask + BatchNorm backward in two passes over (d pool, idx, raw): algorithmic bytes = raw read
-      // twice + dx written once (+ the pooled gradient / indices, 1/4 size)
-      ProfScope ps("bn_bwd", s, 0, (double)Ms * 64 * sizeof(T) * 3.75);
-      stem_tail_fused = fast::stem_pool_bn_bwd_bf16((const bf16*)gcur, pool_idx, (const bf16*)r_stem, stem_bn.mean, stem_bn.rstd,
-                                                    P + stem_bn.g_off, P + stem_bn.b_off, G + stem_bn.g_off, G + stem_bn.b_off,
-                                                    (bf16*)tB, B, stem_oh, stem_ow, 64, pool_h, pool_w, bn_sums, s);
-    }
-    if (stem_tail_fused) {
-    } else if (stem_pool_fused) {
+    if (stem_pool_fused) {
       ProfScope ps("pool", s, 0, (double)Ms * 64 * sizeof(T) * 2.5);
       bool ok = fast::Fast<T>::pool_bwd(gcur, pool_idx, r_stem, stem_bn.mean, stem_bn.rstd, P + stem_bn.g_off,
                                         P + stem_bn.b_off, tA, B, stem_oh, stem_ow, 64, pool_h, pool_w, s);

@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, overlap=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -36,7 +36,7 @@ def _worker(rank, world, port, out_dir):
     b = batch_on("cpu", 2, seed=1 + rank)
     oh = lbc.one_hot(b["command"])
     tgt = torch.rand(2, 5, 2, generator=torch.Generator().manual_seed(7 + rank)) * torch.tensor([384.0, 160.0])
-    dp = DataParallel(net, opt)
+    dp = DataParallel(net, opt, overlap=overlap)
     net.lbc_flat_state(2)
     dp.sync_initial_state()
     pred, _ = net(b["rgb"], b["speed"], oh)
@@ -53,7 +53,7 @@ def _worker(rank, world, port, out_dir):
         for p_, view, _, on_path in net._lbc.param_views:
             o = view.storage_offset()
             assert bool(covered[o:o + view.numel()].all()) == on_path, "bucket coverage != on-path parameters"
-    # both ranks reduce through the bucketed path (on the GPU the same buckets ride a side stream under backward)
+    # overlap=True: the bucketed path (on the GPU the same buckets ride a side stream under backward); False: one all-reduce
     local = {}
     hook = net._lbc
     import learningbycheating_b200.distributed as D
@@ -64,22 +64,23 @@ def _worker(rank, world, port, out_dir):
             local["g"] = hook.flat_grads.clone()      # the local gradient, before the first bucket is summed
         return orig(t, *a, **k)
     D.dist.all_reduce = spy
+    p_before = net._lbc.flat_params.clone()
     dp.backward(loss)
+    dp.step_after_backward()
     D.dist.all_reduce = orig
     local_grad = local["g"]
-    p_before = net._lbc.flat_params.clone()
-    dp.step_after_backward()
     torch.save(dict(local_grad=local_grad, summed=net._lbc.flat_grads.clone(), p_before=p_before,
                     p_after=net._lbc.flat_params.clone(), loss=float(loss)), os.path.join(out_dir, "r%d.pt" % rank))
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(900)
-def test_dp2_gloo_matches_manual_average(tmp_path):
+@pytest.mark.parametrize("overlap", [False, True], ids=["one_allreduce", "bucketed"])
+def test_dp2_gloo_matches_manual_average(tmp_path, overlap):
     from learningbycheating_b200 import build
     build.build_hostemu()
     port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), overlap), nprocs=2, join=True)
     r0 = torch.load(tmp_path / "r0.pt")
     r1 = torch.load(tmp_path / "r1.pt")
     # identical starting point after the broadcast, identical result after the step

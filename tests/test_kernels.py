@@ -296,7 +296,7 @@ def _stem_tail_case(dev, N, H, W, C, precision):
     OH, OW = y_ref.shape[2:]
     y, dx = torch.empty(N, OH, OW, C, device=dev), torch.empty(N, H, W, C, device=dev)
     dg, db = torch.empty(C, device=dev), torch.empty(C, device=dev)
-    must = ["bn_relu_maxpool_kernel", "maxpool_relu_bwd_kernel<bn_reduce>", "maxpool_relu_bwd_kernel<bn_apply>"] if precision == 1 else []
+    must = ["bn_relu_maxpool_kernel", "maxpool_relu_bwd_kernel", "bn_bwd_reduce_kernel", "bn_bwd_apply_kernel"] if precision == 1 else []
     never = tuple(t for t in REF_TAGS if t not in ("k_bn_sum_part", "k_bn_var_part")) if precision == 1 else ()
     with Traced(dev, must, never):
         _lib.check(L.lbc_op_stem_tail(_lib.ptr(xd), _lib.ptr(gd), _lib.ptr(bd), _lib.ptr(y), _lib.ptr(dyd), _lib.ptr(dg), _lib.ptr(db),

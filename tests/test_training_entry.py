@@ -2,6 +2,7 @@
 teacher loaded from its checkpoint, data through the dataset hook, epoch-0 dry run, checkpoint on SAVE_EPOCHS."""
 import os
 
+import pytest
 import torch
 
 from lbc_testing import batch_on, build_models
@@ -45,3 +46,34 @@ def test_train_config_reference_signature_cpu(backend, tmp_path, monkeypatch):
     cfg2.pop("data_loader")
     with pytest.raises(lbc.LbcError, match="no dataset"):
         p0.train(cfg2)
+
+
+@pytest.mark.gpu
+def test_cuda_prefetcher_fixed_slots_gpu():
+    """data.CudaPrefetcher: same tuples out as in, on the device; ragged last batch; staging buffers allocated once
+    (no allocator growth in the steady state); early exit + re-iteration keeps the slot ordering safe."""
+    from learningbycheating_b200.data import CudaPrefetcher
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randint(0, 256, (8 if i < 6 else 5, 3, 16, 24), dtype=torch.uint8, generator=g),
+                torch.rand(8 if i < 6 else 5, generator=g), None, i) for i in range(7)]
+    pf = CudaPrefetcher(batches, "cuda:0")
+    seen = 0
+    for i, (a, b, c, k) in enumerate(pf):
+        assert a.is_cuda and b.is_cuda and c is None and k == i
+        # consume with a kernel that takes a while so that the next copies really overlap
+        assert torch.equal(a.cpu(), batches[i][0]) and torch.equal(b.cpu(), batches[i][1])
+        seen += 1
+    assert seen == 7
+    torch.cuda.synchronize()
+    m0 = torch.cuda.memory_reserved()
+    for rep in range(3):
+        for i, (a, b, c, k) in enumerate(pf):
+            s = a.float().sum() + b.sum()
+            if rep == 1 and i == 2:
+                break
+        assert torch.isfinite(s)
+    # results stay right after an early exit
+    for i, (a, b, c, k) in enumerate(pf):
+        assert torch.equal(a.cpu(), batches[i][0])
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_reserved() <= m0 + (4 << 20)
