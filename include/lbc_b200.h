@@ -36,8 +36,12 @@ const char* lbc_build_info(void);
 /* enable / disable the tcgen05 + fused kernels (tests compare them with the correctness-first kernels).
  * bit 0: fast kernels on; bit 1: generic tap-per-box kernel for the 64->64 3x3 convolutions;
  * variant switches (absent bits keep the LBC_PAIR default): 4 / 8 = CTA-pair (cta_group::2) conv GEMMs on / off,
- * 16 / 32 = row-of-taps weight gradient on / off, 64 / 128 = its CTA-pair variant on / off. */
+ * 16 / 32 = row-of-taps weight gradient on / off, 64 / 128 = its CTA-pair variant on / off,
+ * 256 / 512 = space-to-depth layout of the RGB stem operand on / off. */
 int lbc_set_fast_kernels(int enabled);
+/* layout code of the padded stem operand lbc_op_stem's x4_out shows (bf16 path): 4 = [N][H+6][W+8][4], 8 = [N][H+6][W+8][8],
+ * 16 = the 4-channel image with every 2x2 pixel block contiguous, [N][(H+6)/2][(W+8)/2][2][2][4]; 0 = column tensor */
+int lbc_stem_layout(int C, int W, int normalize);
 
 /* ---- instrumentation used by bench.py ---- */
 /* number of kernels this library has launched so far (all streams) */

@@ -29,6 +29,7 @@ def _declare(lib):
         "lbc_device_kind": (i, []),
         "lbc_build_info": (ctypes.c_char_p, []),
         "lbc_set_fast_kernels": (i, [i]),
+        "lbc_stem_layout": (i, [i, i, i]),
         "lbc_kernel_launch_count": (ctypes.c_longlong, []),
         "lbc_prof_enable": (i, [i]),
         "lbc_prof_reset": (i, []),

@@ -128,9 +128,12 @@ int lbc_set_fast_kernels(int enabled) {
   if (enabled & 32) m &= ~2;
   if (enabled & 64) m |= 4;     // 64 / 128 = CTA-pair variant of the row-of-taps weight gradient on / off
   if (enabled & 128) m &= ~4;
+  if (enabled & 256) m |= 8;    // 256 / 512 = space-to-depth layout of the RGB stem operand on / off
+  if (enabled & 512) m &= ~8;
   fast::set_pair_mode(m);
   return 0;
 }
+int lbc_stem_layout(int C, int W, int normalize) { return fast::stem_ch(C, W, normalize != 0); }
 
 long long lbc_kernel_launch_count(void) { return g_launches; }
 int lbc_prof_enable(int on) {
@@ -840,13 +843,13 @@ int lbc_op_stem(const float* img, const uint8_t* img_u8, int layout, const float
         LBC_CHECK(fast::stem_unpack_wgrad(dwc, dw, C, Kp, s), "stem_unpack_wgrad failed");
       }
     } else if (fast::stem_ch(C) && !(C > 4 && normalize)) {
-      const int CH = fast::stem_ch(C);
-      bf16 *x4 = t.get<bf16>((int64_t)N * (H + 6) * (W + 8) * CH), *w224 = t.get<bf16>(64 * 7 * 8 * CH), *yb = t.get<bf16>(ny);
+      const int CH = fast::stem_ch(C, W, normalize != 0), XC = fast::stem_x_ch(CH);
+      bf16 *x4 = t.get<bf16>((int64_t)N * (H + 6) * (W + 8) * XC), *w224 = t.get<bf16>(fast::stem_w_elems(CH)), *yb = t.get<bf16>(ny);
       bool ok = img_u8 && !img ? fast::stem_pad4_u8_bf16(img_u8, layout, x4, N, C, H, W, normalize != 0, s)
                                : fast::stem_pad4_bf16(imgf, x4, N, C, H, W, normalize != 0, s);
       LBC_CHECK(ok, "lbc_op_stem: stem_pad4 unavailable (fast kernels disabled or host-emulation build)");
-      if (x4_out) ref::cast<bf16, float>(s, x4, x4_out, (int64_t)N * (H + 6) * (W + 8) * CH);
-      LBC_CHECK(fast::stem_pack_w224_bf16(w_ref, w224, C, s), "stem_pack_w224 failed");
+      if (x4_out) ref::cast<bf16, float>(s, x4, x4_out, (int64_t)N * (H + 6) * (W + 8) * XC);
+      LBC_CHECK(fast::stem_pack_w224_bf16(w_ref, w224, C, s, CH), "stem_pack_w224 failed");
       if (y) {
         int rows = 0;
         float* part = stats_out ? fast::stat_partial_buffer() : nullptr;

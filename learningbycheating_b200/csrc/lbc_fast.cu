@@ -30,7 +30,7 @@ bool stem_im2col_bf16(const float*, bf16*, int, int, int, int, int, int, int, bo
 bool stem_pack_weight_bf16(const float*, bf16*, int, int, lbc_stream_t) { return false; }
 bool stem_pad4_bf16(const float*, bf16*, int, int, int, int, bool, lbc_stream_t) { return false; }
 bool stem_pad4_u8_bf16(const uint8_t*, int, bf16*, int, int, int, int, bool, lbc_stream_t) { return false; }
-bool stem_pack_w224_bf16(const float*, bf16*, int, lbc_stream_t) { return false; }
+bool stem_pack_w224_bf16(const float*, bf16*, int, lbc_stream_t, int) { return false; }
 bool stem_unpack_wgrad(const float*, float*, int, int, lbc_stream_t) { return false; }
 #else
 struct k_stem_im2col;
@@ -153,9 +153,11 @@ bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, i
 // KIND 0: fp32 [B,C,H,W]; 1: uint8 [B,C,H,W]; 2: uint8 [B,H,W,C].  Same per-element expressions as the one-pixel writers
 // below (bit-identical output); 32-byte stores, 16-byte / 4-byte vector loads, 4x fewer threads (round 1: 222 us for the
 // 132 MB tensor at B = 256, bound by block dispatch of 16.6 M one-pixel threads).
+// s2d: the same values in the space-to-depth arrangement ([row/2][col/2][row&1][col&1][4]): the thread's two pixel pairs go
+// to the 16-byte halves (row parity) of two neighbouring 32-byte 2x2 blocks
 template <int KIND>
 __global__ void __launch_bounds__(256) stem_pad4_kernel(const void* __restrict__ img, uint4* __restrict__ x4, int B, int C, int H,
-                                                        int W, int normalize) {
+                                                        int W, int normalize, int s2d) {
   const int HP = H + 6, WG = (W + 8) / 4;
   const int64_t n = (int64_t)B * HP * WG;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -196,19 +198,27 @@ __global__ void __launch_bounds__(256) stem_pad4_kernel(const void* __restrict__
       w[2 * p] = (uint32_t)float_to_bf16(v[p][0]).v | ((uint32_t)float_to_bf16(v[p][1]).v << 16);
       w[2 * p + 1] = (uint32_t)float_to_bf16(v[p][2]).v | ((uint32_t)float_to_bf16(v[p][3]).v << 16);
     }
-    x4[i * 2] = make_uint4(w[0], w[1], w[2], w[3]);
-    x4[i * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    if (s2d) {
+      // 2x2 block (Y, X) = 16 elements = two 16-byte halves (row parity a); this thread holds blocks X = 2*gcol, 2*gcol + 1
+      const int64_t blk = ((int64_t)b * (HP / 2) + (row >> 1)) * (2 * WG) + 2 * gcol;
+      x4[blk * 2 + (row & 1)] = make_uint4(w[0], w[1], w[2], w[3]);
+      x4[(blk + 1) * 2 + (row & 1)] = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+      x4[i * 2] = make_uint4(w[0], w[1], w[2], w[3]);
+      x4[i * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
   }
 }
 template <int KIND>
 static bool launch_stem_pad4(const void* img, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s) {
+  const int s2d = stem_ch(C, W, normalize) == 16 ? 1 : 0;
   const int64_t n = (int64_t)B * (H + 6) * ((W + 8) / 4);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t blocks = (n + 255) / 256, cap = (int64_t)sms * 16;
   if (blocks > cap) blocks = cap;
-  stem_pad4_kernel<KIND><<<(unsigned)blocks, 256, 0, s>>>(img, (uint4*)x4, B, C, H, W, normalize ? 1 : 0);
+  stem_pad4_kernel<KIND><<<(unsigned)blocks, 256, 0, s>>>(img, (uint4*)x4, B, C, H, W, normalize ? 1 : 0, s2d);
   LBC_LAUNCHED(KIND == 0 ? "stem_pad4_kernel<f32>" : "stem_pad4_kernel<u8>");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -328,9 +338,23 @@ bool stem_pad4_u8_bf16(const uint8_t* img, int layout, bf16* x4, int B, int C, i
   return true;
 }
 // w224[co][kh][kw'][c], c < CH = stem_ch(C): kw' = kw + 1 in 0..7 (kw' = 0 and c >= C are zero)
-bool stem_pack_w224_bf16(const float* w_ref, bf16* w224, int C, lbc_stream_t s) {
-  const int CH = stem_ch(C);
+struct k_stem_w256;
+bool stem_pack_w224_bf16(const float* w_ref, bf16* w224, int C, lbc_stream_t s, int CH) {
+  if (!CH) CH = stem_ch(C);
   if (!CH) return false;
+  if (CH == 16) {   // space-to-depth: K index = [row pair 4][column pair 4][row parity][column parity][4 ch]
+    par_for<k_stem_w256>(s, (int64_t)64 * 256, [=] __device__(int64_t i) {
+      const int e = (int)(i % 64);
+      const int khp = (int)((i / 64) % 4);
+      const int co = (int)(i / 256);
+      const int xs = e >> 4, a = (e >> 3) & 1, b2 = (e >> 2) & 1, c = e & 3;
+      const int kh = 2 * khp + a, kwp = 2 * xs + b2;
+      float v = 0.f;
+      if (kh < 7 && kwp >= 1 && c < C) v = w_ref[(((int64_t)co * C + c) * 7 + kh) * 7 + (kwp - 1)];
+      w224[i] = float_to_bf16(v);
+    });
+    return true;
+  }
   const int KR = 8 * CH;
   par_for<k_stem_w224>(s, (int64_t)64 * 7 * KR, [=] __device__(int64_t i) {
     int e = (int)(i % KR);

@@ -208,11 +208,23 @@ bool stem_pack_weight_bf16(const float* w_ref, bf16* wp, int C, int Kp, lbc_stre
 bool stem_unpack_wgrad(const float* dw_col, float* dw_ref, int C, int Kp, lbc_stream_t s);    // [64][Kp] -> [64][C][7][7]
 
 // ---- stem without a column tensor: zero-padded NHWC bf16 image [B][H+6][W+8][CH] + overlapping-window TMA (lbc_fast_conv.cu).
-// CH = 4 for C_in <= 4 (camera), CH = 8 for C_in <= 8 (the teacher's 7-channel bird's-eye view): stem_ch(C_in).
-inline int stem_ch(int C) { return C <= 4 ? 4 : (C <= 8 ? 8 : 0); }
+// Layout code CH = stem_ch(C_in, W, normalize):
+//   4  C_in <= 4 (camera): [B][H+6][W+8][4], one kernel row of one output pixel = 8 px x 4 ch = 64 contiguous bytes, 7 rows
+//   8  C_in <= 8 (the teacher's 7-channel bird's-eye view): [B][H+6][W+8][8], 128-byte window rows, 7 rows
+//   16 C_in <= 4, space-to-depth: [B][(H+6)/2][(W+8)/2][2 row parity][2 column parity][4] -- the SAME padded pixels with every
+//      2x2 block contiguous, so the 7x7/s2 convolution is a 4x4/s1 one over 16 channels: 4 window rows of 4 x 16 = 64
+//      elements = 128 bytes per output pixel instead of 7 rows of 64 bytes (the kernels are bound by TMA row requests)
+bool stem_s2d();   // LBC_STEM_S2D (default on)
+inline int stem_ch(int C, int W = 0, bool normalize = false) {
+  if (C <= 4) return (stem_s2d() && W > 0 && W % 4 == 0 && (C == 3 || !normalize)) ? 16 : 4;
+  return C <= 8 ? 8 : 0;
+}
+inline int stem_x_ch(int CH) { return CH == 16 ? 4 : CH; }                            // channels of the padded image
+inline int stem_w_elems(int CH) { return CH == 16 ? 64 * 4 * 64 : 64 * 7 * 8 * CH; }  // packed weights
 bool stem_pad4_bf16(const float* img, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s);
 bool stem_pad4_u8_bf16(const uint8_t* img, int layout, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s);
-bool stem_pack_w224_bf16(const float* w_ref, bf16* w224, int C, lbc_stream_t s);   // [64][C][7][7] -> [64][7][8 px][CH ch]
+// [64][C][7][7] -> [64][7][8 px][CH ch]  (CH = 16: [64][4 row pairs][4 column pairs][2][2][4])
+bool stem_pack_w224_bf16(const float* w_ref, bf16* w224, int C, lbc_stream_t s, int CH = 0);
 bool stem_conv_bf16(const bf16* x4, const bf16* w224, bf16* raw, int B, int H, int W, int OH, int OW, const float* bias,
                     float* stat_partial, int* stat_rows, lbc_stream_t s, int CH = 4);
 bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C, int H, int W, int OH, int OW, lbc_stream_t s,

@@ -888,19 +888,22 @@ struct StemParams {
   int stat_C;
   int valid_n;
 };
-// CH = channels of the padded image (4: camera RGB, 8: the 7-channel bird's-eye view): one kernel row of one output pixel is
-// 8 px x CH ch = 8*CH bf16 = 64 or 128 contiguous bytes (SWIZZLE_64B / SWIZZLE_128B operands)
+// CH = layout code of the padded image (lbc_fast.h: stem_ch): 4 = camera RGB, 8 = the 7-channel bird's-eye view -- one kernel
+// row of one output pixel is 8 px x CH ch = 64 or 128 contiguous bytes (SWIZZLE_64B / SWIZZLE_128B operands), 7 rows;
+// 16 = RGB space-to-depth -- one kernel ROW PAIR is 4 blocks x 16 = 64 elements = 128 bytes, 4 rows (K = 256 instead of 224,
+// but 4 x 128 TMA row requests per tile instead of 7 x 128: these kernels are bound by TMA rows, not by the tensor pipe)
 template <int CH>
 struct StemGeom {
-  static constexpr int ROWB = CH * 16;             // bytes of one window row
+  static constexpr int ROWB = CH == 4 ? 64 : 128;  // bytes of one window row
   static constexpr int A_BYTES_ = 128 * ROWB;      // one A box: 128 output pixels
-  static constexpr int KROW = 8 * CH;              // K elements per kernel row
+  static constexpr int KROW = ROWB / 2;            // K elements per window row
+  static constexpr int NROWS = CH == 16 ? 4 : 7;   // window rows per output pixel
 };
 constexpr int ASTEM_BYTES = 128 * 64;
 
 template <int STAGES, int CH = 4>
 struct SmemPlanStem {
-  static constexpr int BRES_BYTES = 7 * 64 * StemGeom<CH>::ROWB;
+  static constexpr int BRES_BYTES = StemGeom<CH>::NROWS * 64 * StemGeom<CH>::ROWB;
   static constexpr int OUT_OFF = STAGES * StemGeom<CH>::A_BYTES_ + BRES_BYTES;
   static constexpr int BAR_OFF = OUT_OFF + A_BYTES;
   static constexpr int RED_OFF = BAR_OFF + 256;
@@ -917,12 +920,13 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
 }
 
 template <int STAGES, int CH>
-__global__ void __launch_bounds__(192, CH == 4 ? 2 : 1)
+__global__ void __launch_bounds__(192, CH == 8 ? 1 : 2)
 stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant__ CUtensorMap mX1,
                  const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mO, const StemParams p) {
   typedef SmemPlanStem<STAGES, CH> SP;
   constexpr int ASTEM_BYTES = StemGeom<CH>::A_BYTES_;   // (shadows the 4-channel constant)
   constexpr int WROW_BYTES = 64 * StemGeom<CH>::ROWB;   // weights of one kernel row: 64 output channels
+  constexpr int NROWS = StemGeom<CH>::NROWS;
   constexpr int BN = 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -964,17 +968,20 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant_
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(bfull, SP::BRES_BYTES);
-      for (int kh = 0; kh < 7; ++kh) tma_load_2d(&mB, bres + kh * WROW_BYTES, bfull, kh * StemGeom<CH>::KROW, 0);
+      for (int kh = 0; kh < NROWS; ++kh) tma_load_2d(&mB, bres + kh * WROW_BYTES, bfull, kh * StemGeom<CH>::KROW, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int w0 = (tile % p.tiles_w) * p.TW;
         const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
-        for (int kh = 0; kh < 7; ++kh) {
+        for (int kh = 0; kh < NROWS; ++kh) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], ASTEM_BYTES);
-          tma_load_4d((kh & 1) ? &mX1 : &mX0, smem + stage * ASTEM_BYTES, &full[stage], 0, w0, h0 + (kh >> 1), n0);
+          if (CH == 16)   // space-to-depth: row pair kh of the window = block row h0 + kh
+            tma_load_4d(&mX0, smem + stage * ASTEM_BYTES, &full[stage], 0, w0, h0 + kh, n0);
+          else            // even / odd padded rows through their own maps
+            tma_load_4d((kh & 1) ? &mX1 : &mX0, smem + stage * ASTEM_BYTES, &full[stage], 0, w0, h0 + (kh >> 1), n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -994,7 +1001,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant_
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kh = 0; kh < 7; ++kh) {
+      for (int kh = 0; kh < NROWS; ++kh) {
         mbar_wait(&full[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
@@ -1005,7 +1012,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant_
           for (int kk = 0; kk < StemGeom<CH>::KROW / 16; ++kk)
             umma_bf16(tmem_d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (kh | kk) != 0);
           umma_commit(&empty[stage]);
-          if (kh == 6) umma_commit(&tfull[acc]);
+          if (kh == NROWS - 1) umma_commit(&tfull[acc]);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -1106,6 +1113,7 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
                   const __grid_constant__ CUtensorMap mX1, const StemWgradParams p) {
   constexpr int ASTEM_BYTES = StemGeom<CH>::A_BYTES_;
   constexpr int KROW = StemGeom<CH>::KROW;         // window elements of one kernel row = M rows it contributes
+  constexpr int NROWS = StemGeom<CH>::NROWS;
   constexpr int RPT = 128 / KROW;                  // kernel rows per 128-row M tile (4 or 2)
   constexpr int A_ST = RPT * ASTEM_BYTES, STAGE_BYTES = A_ST + A_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -1134,7 +1142,7 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  constexpr int MT = 8 / RPT;               // M tiles covering kernel rows 0..7 (row 7 does not exist)
+  constexpr int MT = (NROWS + RPT - 1) / RPT;   // M tiles covering the window rows (7 rows: row 7 does not exist)
   const int mt = blockIdx.x % MT;          // kernel rows RPT*mt .. RPT*mt+RPT-1
   const int split = blockIdx.x / MT;
   const int kt0 = split * p.k_per_split;
@@ -1156,8 +1164,11 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
           int kh = mt * RPT + j;
-          if (kh > 6) kh = 6;   // row 7 does not exist: load a valid duplicate, its output rows are skipped
-          tma_load_4d((kh & 1) ? &mX1 : &mX0, sa + j * ASTEM_BYTES, &full[stage], 0, w0, h0 + (kh >> 1), n0);
+          if (kh > NROWS - 1) kh = NROWS - 1;   // row 7 does not exist: load a valid duplicate, its output rows are skipped
+          if (CH == 16)
+            tma_load_4d(&mX0, sa + j * ASTEM_BYTES, &full[stage], 0, w0, h0 + kh, n0);
+          else
+            tma_load_4d((kh & 1) ? &mX1 : &mX0, sa + j * ASTEM_BYTES, &full[stage], 0, w0, h0 + (kh >> 1), n0);
         }
         tma_load_4d(&mDY, sa + A_ST, &full[stage], 0, w0, h0, n0);
         if (++stage == STAGES) {
@@ -1194,9 +1205,12 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
   } else if (n_k > 0) {
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int kh = mt * RPT + m / KROW;
+    const int wr = mt * RPT + m / KROW;   // window row
     const int e = m % KROW;
-    const int kwp = e / CH, c = e % CH;
+    // CH = 16: e = [column pair 4][row parity][column parity][4 ch] of row pair wr
+    const int kh = CH == 16 ? 2 * wr + ((e >> 3) & 1) : wr;
+    const int kwp = CH == 16 ? 2 * (e >> 4) + ((e >> 2) & 1) : e / CH;
+    const int c = CH == 16 ? (e & 3) : e % CH;
     mbar_wait(tfull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -1316,13 +1330,15 @@ static int launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, co
 // kernel variants (LBC_PAIR overrides; tests toggle them through lbc_set_fast_kernels):
 //   bit 0: CTA-pair (cta_group::2) kernels for the BN >= 128 conv GEMMs   bit 1: row-of-taps weight gradient
 //   bit 2: CTA-pair variant of the row-of-taps weight gradient (Co % 256 == 0)
-// All three validated on the B200 (parity tests green, 16.61 -> 15.87 ms per step at B = 256), hence on by default.
+//   bit 3: space-to-depth operand layout of the RGB stem (lbc_fast.h: stem_ch)
+// Bits 0-2 validated on the B200 (parity tests green, 16.61 -> 15.87 ms per step at B = 256), hence on by default.
 static int g_pair_mode = [] {
   const char* e = getenv("LBC_PAIR");
-  return e ? atoi(e) : 7;
+  return e ? atoi(e) : 15;
 }();
 void set_pair_mode(int mode) { g_pair_mode = mode; }
 int pair_mode() { return g_pair_mode; }
+bool stem_s2d() { return (g_pair_mode & 8) != 0; }
 
 // Operand / output format of one implicit GEMM.  Default = the bf16 training step.  fp32tc (parity-grade tensor-core
 // mode): operands are [hi | lo] 16-bit planes of fp32 tensors (3 MMAs per K block), the output is stored as fp32.
@@ -1442,9 +1458,12 @@ static CUtensorMap make_map_stem(const void* base, int OW, int rows2, int B, int
                                  int bh, int bn, int CH) {
   CUtensorMap m;
   // W stride = one output pixel = 2 input pixels: overlapping 8-pixel windows (accepted by cuTensorMapEncodeTiled, verified)
-  cuuint64_t dims[4] = {(cuuint64_t)(8 * CH), (cuuint64_t)OW, (cuuint64_t)rows2, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)(2 * CH * 2), (cuuint64_t)(2 * pitch_bytes), (cuuint64_t)img_bytes};
-  cuuint32_t box[4] = {(cuuint32_t)(8 * CH), (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  // CH = 16 (space-to-depth): window = 4 blocks of 16, W stride = one block (32 B), H stride = one block row (pitch_bytes)
+  const int kel = CH == 16 ? 64 : 8 * CH;
+  const int64_t wstride = CH == 16 ? 32 : 2 * CH * 2, hstride = CH == 16 ? pitch_bytes : 2 * pitch_bytes;
+  cuuint64_t dims[4] = {(cuuint64_t)kel, (cuuint64_t)OW, (cuuint64_t)rows2, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)wstride, (cuuint64_t)hstride, (cuuint64_t)img_bytes};
+  cuuint32_t box[4] = {(cuuint32_t)kel, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CH == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1452,12 +1471,13 @@ static CUtensorMap make_map_stem(const void* base, int OW, int rows2, int B, int
   LBC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stem window map) failed: " + std::to_string((int)r));
   return m;
 }
-static CUtensorMap make_map_stem_w(const void* base, int64_t rows, int brows, int CH) {   // weights [64][7 * 8*CH]
+static CUtensorMap make_map_stem_w(const void* base, int64_t rows, int brows, int CH) {   // weights [64][window rows x KROW]
   CUtensorMap m;
-  const int64_t K = 7 * 8 * CH;
+  const int krow = CH == 16 ? 64 : 8 * CH;
+  const int64_t K = (CH == 16 ? 4 : 7) * krow;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(K * 2)};
-  cuuint32_t box[2] = {(cuuint32_t)(8 * CH), (cuuint32_t)brows};
+  cuuint32_t box[2] = {(cuuint32_t)krow, (cuuint32_t)brows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CH == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1471,13 +1491,11 @@ static bool stem_geometry(int OH, int OW, int B, int& TW, int& TH, int& TN) {
   TN = 128 / (TW * TH);
   return (OW % TW) == 0 && (OH % TH) == 0 && TN <= 256;
 }
-template <int CH>
-static void launch_stem_conv(const CUtensorMap& mX0, const CUtensorMap& mX1, const CUtensorMap& mB, const CUtensorMap& mO,
-                             const StemParams& p, lbc_stream_t s) {
-  constexpr int STAGES = CH == 4 ? 7 : 5;
-  constexpr int PER_SM = CH == 4 ? 2 : 1;
+template <int CH, int STAGES, int PER_SM>
+static int launch_stem_conv(const CUtensorMap& mX0, const CUtensorMap& mX1, const CUtensorMap& mB, const CUtensorMap& mO,
+                            const StemParams& p, lbc_stream_t s) {
   typedef SmemPlanStem<STAGES, CH> SP;
-  static_assert(SP::TOTAL <= 232448, "stem smem plan exceeds 227 KB");
+  static_assert(PER_SM * SP::TOTAL <= 232448 - PER_SM * 1024, "stem smem plan exceeds 227 KB per SM");
   static bool configured = false;
   if (!configured) {
     LBC_CUDA(cudaFuncSetAttribute(stem_conv_kernel<STAGES, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
@@ -1486,13 +1504,14 @@ static void launch_stem_conv(const CUtensorMap& mX0, const CUtensorMap& mX1, con
   int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int grid = tiles < PER_SM * sm_count() ? tiles : PER_SM * sm_count();
   stem_conv_kernel<STAGES, CH><<<grid, 192, SP::TOTAL, s>>>(mX0, mX1, mB, mO, p);
-  LBC_LAUNCHED(CH == 4 ? "stem_conv_kernel" : "stem_conv_kernel<8ch>");
+  LBC_LAUNCHED(CH == 4 ? "stem_conv_kernel" : CH == 8 ? "stem_conv_kernel<8ch>" : "stem_conv_kernel<s2d>");
   LBC_CUDA(cudaGetLastError());
+  return grid;
 }
 // raw[B,OH,OW,64] = conv7x7/s2(x4) (+ negshift), optional BN statistics partials; x4 / w224 in the CH-channel layouts
 bool stem_conv_bf16(const bf16* x4, const bf16* w224, bf16* raw, int B, int H, int W, int OH, int OW, const float* bias,
                     float* stat_partial, int* stat_rows, lbc_stream_t s, int CH) {
-  if ((H % 2) || (W % 2) || OH * 2 != H || OW * 2 != W || (CH != 4 && CH != 8)) return false;
+  if ((H % 2) || (W % 2) || OH * 2 != H || OW * 2 != W || (CH != 4 && CH != 8 && CH != 16)) return false;
   StemParams p;
   memset(&p, 0, sizeof(p));
   if (!stem_geometry(OH, OW, B, p.TW, p.TH, p.TN)) return false;
@@ -1503,42 +1522,50 @@ bool stem_conv_bf16(const bf16* x4, const bf16* w224, bf16* raw, int B, int H, i
   p.stat_partial = stat_partial;
   p.stat_C = 64;
   p.valid_n = B;
-  {
-    const int tiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int ctas = (CH == 4 ? 2 : 1) * sm_count();
-    if (stat_rows) *stat_rows = tiles_total < ctas ? tiles_total : ctas;   // one partial row per CTA
-  }
-  const int64_t pitch = (int64_t)(W + 8) * CH * 2, img = pitch * (H + 6);
+  // bytes of one padded row (CH = 16: of one row of 2x2 blocks) and of one image
+  const int64_t pitch = CH == 16 ? (int64_t)(W + 8) * 16 : (int64_t)(W + 8) * CH * 2;
+  const int64_t img = (int64_t)(W + 8) * (H + 6) * stem_x_ch(CH) * 2;
   CUtensorMap mX0 = make_map_stem(x4, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN, CH);
   CUtensorMap mX1 = make_map_stem((const uint8_t*)x4 + pitch, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN, CH);
   CUtensorMap mB = make_map_stem_w(w224, 64, 64, CH);
   const int64_t eb = 2;
   CUtensorMap mO = make_map_4d(raw, 64, OW, OH, B, 64 * eb, (int64_t)OW * 64 * eb, (int64_t)OH * OW * 64 * eb, p.TW, p.TH, p.TN);
+  static const int s2d_cfg = [] {
+    const char* e = getenv("LBC_STEM_S2D_CFG");   // 1: 3 stages, 2 CTAs per SM; 0: 5 stages, 1 CTA per SM
+    return e ? atoi(e) : 1;
+  }();
+  int ctas;
   if (CH == 4)
-    launch_stem_conv<4>(mX0, mX1, mB, mO, p, s);
+    ctas = launch_stem_conv<4, 7, 2>(mX0, mX1, mB, mO, p, s);
+  else if (CH == 8)
+    ctas = launch_stem_conv<8, 5, 1>(mX0, mX1, mB, mO, p, s);
+  else if (s2d_cfg)
+    ctas = launch_stem_conv<16, 3, 2>(mX0, mX1, mB, mO, p, s);
   else
-    launch_stem_conv<8>(mX0, mX1, mB, mO, p, s);
+    ctas = launch_stem_conv<16, 5, 1>(mX0, mX1, mB, mO, p, s);
+  if (stat_rows) *stat_rows = ctas;   // one partial row per CTA
   return true;
 }
 template <int CH>
 static void launch_stem_wgrad(const CUtensorMap& mDY, const CUtensorMap& mX0, const CUtensorMap& mX1, const StemWgradParams& p,
                               lbc_stream_t s) {
   constexpr int STAGES = 4;
-  constexpr int MT = 8 / (128 / (8 * CH));   // M tiles: 2 (CH = 4) or 4 (CH = 8)
-  const int smem = STAGES * ((128 / (8 * CH)) * StemGeom<CH>::A_BYTES_ + A_BYTES) + 256 + 1024;
+  constexpr int RPT = 128 / StemGeom<CH>::KROW;
+  constexpr int MT = (StemGeom<CH>::NROWS + RPT - 1) / RPT;   // M tiles: 2 (CH = 4, 16) or 4 (CH = 8)
+  const int smem = STAGES * (RPT * StemGeom<CH>::A_BYTES_ + A_BYTES) + 256 + 1024;
   static bool configured = false;
   if (!configured) {
     LBC_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<STAGES, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   stem_wgrad_kernel<STAGES, CH><<<MT * p.splits, 192, smem, s>>>(mDY, mX0, mX1, p);
-  LBC_LAUNCHED(CH == 4 ? "stem_wgrad_kernel" : "stem_wgrad_kernel<8ch>");
+  LBC_LAUNCHED(CH == 4 ? "stem_wgrad_kernel" : CH == 8 ? "stem_wgrad_kernel<8ch>" : "stem_wgrad_kernel<s2d>");
   LBC_CUDA(cudaGetLastError());
 }
 // dw_ref[64][C][7][7] = sum_pixels dy x window(x4); dw_ref is zeroed here
 bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C, int H, int W, int OH, int OW, lbc_stream_t s,
                      int CH) {
-  if ((H % 2) || (W % 2) || OH * 2 != H || OW * 2 != W || C > CH || (CH != 4 && CH != 8)) return false;
+  if ((H % 2) || (W % 2) || OH * 2 != H || OW * 2 != W || C > stem_x_ch(CH) || (CH != 4 && CH != 8 && CH != 16)) return false;
   StemWgradParams p;
   memset(&p, 0, sizeof(p));
   if (!stem_geometry(OH, OW, B, p.TW, p.TH, p.TN)) return false;
@@ -1546,13 +1573,14 @@ bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C
   p.tiles_h = OH / p.TH;
   p.tiles_n = (B + p.TN - 1) / p.TN;
   p.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  int splits = sm_count() / (CH == 4 ? 2 : 4);
+  int splits = sm_count() / (CH == 8 ? 4 : 2);   // M tiles per split: 2 (CH = 4, 16) or 4 (CH = 8)
   if (splits > p.k_tiles / 4) splits = p.k_tiles / 4 > 0 ? p.k_tiles / 4 : 1;
   p.k_per_split = (p.k_tiles + splits - 1) / splits;
   p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
   p.C = C;
   p.dw_ref = dw_ref;
-  const int64_t pitch = (int64_t)(W + 8) * CH * 2, img = pitch * (H + 6);
+  const int64_t pitch = CH == 16 ? (int64_t)(W + 8) * 16 : (int64_t)(W + 8) * CH * 2;
+  const int64_t img = (int64_t)(W + 8) * (H + 6) * stem_x_ch(CH) * 2;
   CUtensorMap mX0 = make_map_stem(x4, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN, CH);
   CUtensorMap mX1 = make_map_stem((const uint8_t*)x4 + pitch, OW, (H + 6) / 2, B, pitch, img, p.TW, p.TH, p.TN, CH);
   const int64_t eb = 2;
@@ -1560,8 +1588,10 @@ bool stem_wgrad_bf16(const bf16* x4, const bf16* dy, float* dw_ref, int B, int C
   LBC_CUDA(cudaMemsetAsync(dw_ref, 0, sizeof(float) * 64 * C * 49, s));
   if (CH == 4)
     launch_stem_wgrad<4>(mDY, mX0, mX1, p, s);
-  else
+  else if (CH == 8)
     launch_stem_wgrad<8>(mDY, mX0, mX1, p, s);
+  else
+    launch_stem_wgrad<16>(mDY, mX0, mX1, p, s);
   return true;
 }
 
@@ -2652,6 +2682,7 @@ bool conv_dgrad_ds_bf16(const ConvL&, const bf16*, const bf16*, bf16*, int, lbc_
 void set_c64_variant(bool) {}
 void set_pair_mode(int) {}
 int pair_mode() { return 0; }
+bool stem_s2d() { return false; }
 bool stem_conv_bf16(const bf16*, const bf16*, bf16*, int, int, int, int, int, const float*, float*, int*, lbc_stream_t, int) { return false; }
 bool stem_wgrad_bf16(const bf16*, const bf16*, float*, int, int, int, int, int, int, lbc_stream_t, int) { return false; }
 bool tc_split(const float*, void*, int64_t, int, int, float, lbc_stream_t) { return false; }

@@ -52,60 +52,138 @@ bool head_fold(ref::HeadParams hp, float* fold, lbc_stream_t s) {
   return true;
 }
 
-// A thread owns FOUR pixels and reads the folded coefficients as float4, so one LDS.128 feeds 16 FMAs (a one-pixel-per-
-// thread version issued one broadcast LDS per FMA, 1280 per pixel, and was shared-memory-issue bound: 116 us for a 126 MB
-// read at B = 256).
-__global__ void __launch_bounds__(128) head_logits4_kernel(const uint4* __restrict__ h, const float* __restrict__ fold,
-                                                           float* __restrict__ logits, int64_t npix, int HW) {
-  __shared__ __align__(16) float A[1300];
-  for (int i = threadIdx.x; i < 1300; i += 128) A[i] = fold[i];
-  __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * 512 + threadIdx.x;
-  float acc[4][20];
+// ---- warp-level tensor-core building blocks (mma.sync m16n8k16 bf16 -> fp32) of the three head GEMMs ----
+// The head products are tiny (K = 64 or 20, N = 20 or 64) and sit between a 126 MB activation read and a 78 MB logits
+// read/write: they only have to keep up with HBM.  The CUDA-core versions (four pixels per thread, coefficients from shared
+// memory) were bound by neither -- 92 / 177 / 156 us for kernels whose traffic is worth 31 / 31 / 51 us.  Here one warp
+// owns 32 pixels, the 64-channel rows are staged with cp.async into a 128-byte-swizzled tile (ldmatrix reads it without bank
+// conflicts) and fp32 operands (folded weights, dlogits) enter as bf16 hi + lo pairs (two or three MMAs per product, ~2^-17
+// relative), so the results stay at fp32 level while the FMAs move to the tensor pipe.
+__device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// bf16 hi / lo split of an fp32 pair (low half = first element, as the MMA fragments want)
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 hx = __float2bfloat16_rn(x), hy = __float2bfloat16_rn(y);
+  const __nv_bfloat16 lx = __float2bfloat16_rn(x - __bfloat162float(hx)), ly = __float2bfloat16_rn(y - __bfloat162float(hy));
+  hi = (uint32_t)__bfloat16_as_ushort(hx) | ((uint32_t)__bfloat16_as_ushort(hy) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(lx) | ((uint32_t)__bfloat16_as_ushort(ly) << 16);
+}
+// stage the [128 pixels][64 channels] bf16 tile of image n starting at pixel p0 (np valid pixels, the rest zero-filled):
+// 16-byte chunk c of row r lands at chunk (c ^ (r & 7)) -- the 128-byte swizzle
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const bf16* h, int64_t pix0, int np) {
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(h) + pix0 * 128;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int kj = 0; kj < 20; ++kj) acc[i][kj] = A[1280 + kj];
-#pragma unroll 1
-  for (int v = 0; v < 8; ++v) {
-    float f[4][8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t pix = base + 128 * i;
-      if (pix < npix) {
-        unpack8h(__ldg(h + pix * 8 + v), f[i]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[i][e] = 0.f;
-      }
-    }
-#pragma unroll
-    for (int kj = 0; kj < 20; ++kj) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&A[kj * 64 + v * 8]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&A[kj * 64 + v * 8 + 4]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float a = acc[i][kj];
-        a += a0.x * f[i][0];
-        a += a0.y * f[i][1];
-        a += a0.z * f[i][2];
-        a += a0.w * f[i][3];
-        a += a1.x * f[i][4];
-        a += a1.y * f[i][5];
-        a += a1.z * f[i][6];
-        a += a1.w * f[i][7];
-        acc[i][kj] = a;
-      }
-    }
+  for (int j = 0; j < 8; ++j) {
+    const int i = threadIdx.x + 128 * j;
+    const int r = i >> 3, c = i & 7;
+    const uint32_t dst = smem_addr(tile + r * 128 + ((c ^ (r & 7)) << 4));
+    const int bytes = r < np ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + (r < np ? (int64_t)r * 128 + c * 16 : 0)),
+                 "r"(bytes)
+                 : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void stage_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// logits[n][kj][p] = b'[kj] + sum_c A[kj][c] h[n,p,c]:  D[32 px per warp][24] = H[32][64] x (A_hi + A_lo)^T
+__global__ void __launch_bounds__(128) head_logits_mma_kernel(const bf16* __restrict__ h, const float* __restrict__ fold,
+                                                               float* __restrict__ logits, int N, int HW) {
+  extern __shared__ __align__(1024) uint8_t hs_smem[];
+  uint8_t* tile[2] = {hs_smem, hs_smem + 16384};
+  float(*out)[132] = reinterpret_cast<float(*)[132]>(hs_smem + 32768);   // [20][128 px (+4)]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t bh[4][3][2], bl[4][3][2];
+  float bias[3][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t pix = base + 128 * i;
-    if (pix >= npix) continue;
-    const int64_t n = pix / HW;
-    const int p = (int)(pix - n * HW);
+  for (int nt = 0; nt < 3; ++nt) {
+    const int kj = nt * 8 + g;
 #pragma unroll
-    for (int kj = 0; kj < 20; ++kj) logits[(n * 20 + kj) * HW + p] = acc[i][kj];
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c = ks * 16 + half * 8 + 2 * t;
+        const float w0 = kj < 20 ? __ldg(fold + kj * 64 + c) : 0.f, w1 = kj < 20 ? __ldg(fold + kj * 64 + c + 1) : 0.f;
+        split2(w0, w1, bh[ks][nt][half], bl[ks][nt][half]);
+      }
+    bias[nt][0] = nt * 8 + 2 * t < 20 ? __ldg(fold + 1280 + nt * 8 + 2 * t) : 0.f;
+    bias[nt][1] = nt * 8 + 2 * t + 1 < 20 ? __ldg(fold + 1280 + nt * 8 + 2 * t + 1) : 0.f;
+  }
+  const int tiles_per_img = (HW + 127) / 128;
+  const int ntiles = N * tiles_per_img;
+  int tl = blockIdx.x, buf = 0;
+  if (tl < ntiles) {
+    const int n = tl / tiles_per_img, p0 = (tl - n * tiles_per_img) * 128;
+    stage_tile(tile[0], h, (int64_t)n * HW + p0, min(128, HW - p0));
+  }
+  for (; tl < ntiles; tl += gridDim.x, buf ^= 1) {
+    const int n = tl / tiles_per_img, p0 = (tl - n * tiles_per_img) * 128;
+    const int np = min(128, HW - p0);
+    const int nx = tl + gridDim.x;
+    if (nx < ntiles) {
+      const int n2 = nx / tiles_per_img, q0 = (nx - n2 * tiles_per_img) * 128;
+      stage_tile(tile[buf ^ 1], h, (int64_t)n2 * HW + q0, min(128, HW - q0));
+      stage_wait_1();
+    } else {
+      stage_wait_all();
+    }
+    __syncthreads();   // tile[buf] complete; every thread is past the previous tile's store loop (out is free)
+    const uint32_t tb = smem_addr(tile[buf]);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float acc[3][4];
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        acc[nt][0] = acc[nt][2] = bias[nt][0];
+        acc[nt][1] = acc[nt][3] = bias[nt][1];
+      }
+      const int r = warp * 32 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;   // ldmatrix row of this lane
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+        const int chunk = ks * 2 + (lane >> 4);
+        ldsm_x4(a, tb + r * 128 + ((chunk ^ (r & 7)) << 4));
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          mma_16816(acc[nt], a, bl[ks][nt][0], bl[ks][nt][1]);
+          mma_16816(acc[nt], a, bh[ks][nt][0], bh[ks][nt][1]);
+        }
+      }
+      const int px = warp * 32 + mt * 16 + g;
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const int kj = nt * 8 + 2 * t;
+        if (kj < 20) {
+          out[kj][px] = acc[nt][0];
+          out[kj + 1][px] = acc[nt][1];
+          out[kj][px + 8] = acc[nt][2];
+          out[kj + 1][px + 8] = acc[nt][3];
+        }
+      }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < np) {
+      float* dst = logits + ((int64_t)n * 20) * HW + p0 + threadIdx.x;
+#pragma unroll
+      for (int kj = 0; kj < 20; ++kj) dst[(int64_t)kj * HW] = out[kj][threadIdx.x];
+    }
   }
 }
 
@@ -179,9 +257,19 @@ bool head_forward_bf16(const bf16* h, ref::HeadParams hp, float* fold, float* lo
   const int HW = H * W;
   if (HW > 4096) return false;
   head_fold(hp, fold, s);
-  const int64_t npix = (int64_t)N * HW;
-  head_logits4_kernel<<<(unsigned)((npix + 511) / 512), 128, 0, s>>>((const uint4*)h, fold, logits, npix, HW);
-  LBC_LAUNCHED("head_logits4_kernel");
+  {
+    constexpr int SMEM = 32768 + 20 * 132 * 4;
+    static bool configured = false;
+    if (!configured) {
+      LBC_CUDA(cudaFuncSetAttribute(head_logits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      configured = true;
+    }
+    const int ntiles = N * ((HW + 127) / 128);
+    int grid = sm_count3() * 4;
+    if (grid > ntiles) grid = ntiles;
+    head_logits_mma_kernel<<<grid, 128, SMEM, s>>>(h, fold, logits, N, HW);
+    LBC_LAUNCHED("head_logits_mma_kernel");
+  }
   head_softmax_kernel<<<N * 20, 128, 0, s>>>(logits, rowmax, rowsum, preds, H, W);
   LBC_LAUNCHED("head_softmax_kernel");
   LBC_CUDA(cudaGetLastError());
@@ -201,76 +289,106 @@ bool head_coef(ref::HeadParams hp, ref::HeadGrads hg, float* coef, float invM, l
   });
   return true;
 }
-// d(pre-ReLU deconv output)[pix][c] = (h>0) * (sum_kj A[kj][c] dl[kj] - c0[c] - hhat[c]*c1[c]);
-// four pixels per thread, coefficients read as float4 over channels (one LDS.128 per 16 FMAs).
-__global__ void __launch_bounds__(128) head_dh4_kernel(const float* __restrict__ dlogits, const uint4* __restrict__ h,
-                                                       const float* __restrict__ fold, const float* __restrict__ coef,
-                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                       uint4* __restrict__ dh, int64_t npix, int HW) {
-  __shared__ __align__(16) float A[1280];
-  __shared__ __align__(16) float cf[256];  // c0, c1, mean, rstd
-  for (int i = threadIdx.x; i < 1280; i += 128) A[i] = fold[i];
+// d(pre-ReLU deconv output)[pix][c] = (h>0) * (sum_kj A[kj][c] dl[kj] - c0[c] - hhat[c]*c1[c]):
+// D[32 px per warp][64] = dl^T[32][20 -> 32] x A[32][64] with hi / lo pairs on both sides (3 MMAs per product); the epilogue
+// reads h from the staged tile and writes the bf16 result over it in place, the tile then leaves with 16-byte stores.
+__global__ void __launch_bounds__(128) head_dh_mma_kernel(const float* __restrict__ dlogits, const bf16* __restrict__ h,
+                                                          const float* __restrict__ fold, const float* __restrict__ coef,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          bf16* __restrict__ dh, int N, int HW) {
+  extern __shared__ __align__(1024) uint8_t hs_smem[];
+  uint8_t* tile[2] = {hs_smem, hs_smem + 16384};
+  float* cf = reinterpret_cast<float*>(hs_smem + 32768);   // c0 | c1 | mean | rstd
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
   if (threadIdx.x < 64) {
     cf[threadIdx.x] = coef[threadIdx.x];
     cf[64 + threadIdx.x] = coef[64 + threadIdx.x];
     cf[128 + threadIdx.x] = mean[threadIdx.x];
     cf[192 + threadIdx.x] = rstd[threadIdx.x];
   }
-  __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * 512 + threadIdx.x;
-  float d[4][20];
+  uint32_t bh[2][8][2], bl[2][8][2];   // B[k = kj][n = c] = A[kj][c]
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t pix = base + 128 * i;
-    const bool ok = pix < npix;
-    const int64_t n = ok ? pix / HW : 0;
-    const int p = ok ? (int)(pix - n * HW) : 0;
+  for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-    for (int kj = 0; kj < 20; ++kj) d[i][kj] = ok ? dlogits[(n * 20 + kj) * HW + p] : 0.f;
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int kj = ks * 16 + half * 8 + 2 * t, c = nt * 8 + g;
+        const float w0 = kj < 20 ? __ldg(fold + kj * 64 + c) : 0.f, w1 = kj + 1 < 20 ? __ldg(fold + (kj + 1) * 64 + c) : 0.f;
+        split2(w0, w1, bh[ks][nt][half], bl[ks][nt][half]);
+      }
+  const int tiles_per_img = (HW + 127) / 128;
+  const int ntiles = N * tiles_per_img;
+  int tl = blockIdx.x, buf = 0;
+  if (tl < ntiles) {
+    const int n = tl / tiles_per_img, p0 = (tl - n * tiles_per_img) * 128;
+    stage_tile(tile[0], h, (int64_t)n * HW + p0, min(128, HW - p0));
   }
-#pragma unroll 1
-  for (int v = 0; v < 8; ++v) {
-    float acc[4][8];
+  for (; tl < ntiles; tl += gridDim.x, buf ^= 1) {
+    const int n = tl / tiles_per_img, p0 = (tl - n * tiles_per_img) * 128;
+    const int np = min(128, HW - p0);
+    // this warp's dlogits fragments (global, 8 consecutive pixels per kj row and load = full 32-byte sectors)
+    uint32_t ah[2][2][4], al[2][2][4];
+    const float* dl = dlogits + ((int64_t)n * 20) * HW + p0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+      for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-    for (int kj = 0; kj < 20; ++kj) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&A[kj * 64 + v * 8]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&A[kj * 64 + v * 8 + 4]);
+        for (int q = 0; q < 4; ++q) {
+          const int px = warp * 32 + mt * 16 + g + (q & 1) * 8;
+          const int kj = ks * 16 + (q >> 1) * 8 + 2 * t;
+          const float v0 = (px < np && kj < 20) ? __ldg(dl + (int64_t)kj * HW + px) : 0.f;
+          const float v1 = (px < np && kj + 1 < 20) ? __ldg(dl + (int64_t)(kj + 1) * HW + px) : 0.f;
+          split2(v0, v1, ah[mt][ks][q], al[mt][ks][q]);
+        }
+    const int nx = tl + gridDim.x;
+    if (nx < ntiles) {
+      const int n2 = nx / tiles_per_img, q0 = (nx - n2 * tiles_per_img) * 128;
+      stage_tile(tile[buf ^ 1], h, (int64_t)n2 * HW + q0, min(128, HW - q0));   // (free: barrier at the end of the last tile)
+      stage_wait_1();
+    } else {
+      stage_wait_all();
+    }
+    __syncthreads();
+    uint8_t* tb = tile[buf];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float dk = d[i][kj];
-        acc[i][0] += a0.x * dk;
-        acc[i][1] += a0.y * dk;
-        acc[i][2] += a0.z * dk;
-        acc[i][3] += a0.w * dk;
-        acc[i][4] += a1.x * dk;
-        acc[i][5] += a1.y * dk;
-        acc[i][6] += a1.z * dk;
-        acc[i][7] += a1.w * dk;
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          mma_16816(acc, al[mt][ks], bh[ks][nt][0], bh[ks][nt][1]);
+          mma_16816(acc, ah[mt][ks], bl[ks][nt][0], bl[ks][nt][1]);
+          mma_16816(acc, ah[mt][ks], bh[ks][nt][0], bh[ks][nt][1]);
+        }
+        const int c = nt * 8 + 2 * t;
+        const float c00 = cf[c], c01 = cf[c + 1], c10 = cf[64 + c], c11 = cf[64 + c + 1];
+        const float m0 = cf[128 + c], m1 = cf[128 + c + 1], r0 = cf[192 + c], r1 = cf[192 + c + 1];
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const int row = warp * 32 + mt * 16 + g + hrow * 8;
+          uint32_t* hp = reinterpret_cast<uint32_t*>(tb + row * 128 + ((nt ^ (row & 7)) << 4) + t * 4);
+          const uint32_t hw = *hp;
+          const float f0 = __uint_as_float(hw << 16), f1 = __uint_as_float(hw & 0xffff0000u);
+          const float o0 = f0 > 0.f ? acc[hrow * 2] - c00 - (f0 - m0) * r0 * c10 : 0.f;
+          const float o1 = f1 > 0.f ? acc[hrow * 2 + 1] - c01 - (f1 - m1) * r1 * c11 : 0.f;
+          __nv_bfloat162 o = __floats2bfloat162_rn(o0, o1);
+          *hp = *reinterpret_cast<uint32_t*>(&o);
+        }
       }
     }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(dh) + ((int64_t)n * HW + p0) * 8;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t pix = base + 128 * i;
-      if (pix >= npix) continue;
-      float f[8], o[8];
-      unpack8h(__ldg(h + pix * 8 + v), f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = v * 8 + e;
-        const float xh = (f[e] - cf[128 + c]) * cf[192 + c];
-        const float a = acc[i][e] - cf[c] - xh * cf[64 + c];
-        o[e] = f[e] > 0.f ? a : 0.f;
-      }
-      uint4 w;
-      __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) hb[q] = __floats2bfloat162_rn(o[2 * q], o[2 * q + 1]);
-      dh[pix * 8 + v] = w;
+    for (int j = 0; j < 8; ++j) {
+      const int i = threadIdx.x + 128 * j;
+      const int r = i >> 3, c = i & 7;
+      if (r < np) dst[i] = *reinterpret_cast<const uint4*>(tb + r * 128 + ((c ^ (r & 7)) << 4));
     }
+    __syncthreads();   // the tile has left: the next iteration's cp.async may refill this buffer
   }
 }
 
@@ -316,81 +434,105 @@ bool head_dlogits_f32(const float* logits, const float* rowmax, const float* row
 }
 
 // S[kj][c] += sum_pix dl[n,kj,pix]*hhat[n,pix,c] (c<64), S[kj][64] += sum dl   (double atomics, S pre-zeroed):
-// moment matrix with 4 channels x 5 kj x 4 pixels per inner step (9 LDS.128 per 80 FMAs).  Thread = (channel quad 0..15,
-// kj group 0..3, pixel quarter 0..3); the four pixel quarters are combined in shared memory before the double atomics.
-__global__ void __launch_bounds__(256) head_s4_kernel(const float* __restrict__ dlogits, const uint4* __restrict__ h,
-                                                      const float* __restrict__ mean, const float* __restrict__ rstd, double* S,
-                                                      int N, int HW) {
-  __shared__ __align__(16) float smem_f[128 * 68 + 20 * 128];   // 45 KB: hh | dl ; `part` reuses the hh space at the end
-  float(*hh)[68] = reinterpret_cast<float(*)[68]>(smem_f);
-  float(*dl)[128] = reinterpret_cast<float(*)[128]>(smem_f + 128 * 68);
-  float(*part)[20][65] = reinterpret_cast<float(*)[20][65]>(smem_f);   // 4 x 20 x 65 floats = 20.8 KB <= 34.8 KB
-  const int t = threadIdx.x;
-  const int cq = t & 15, grp = (t >> 4) & 3, pq = t >> 6;
-  float acc[5][4];
-  float acc0[5];
+// D[20 -> 32][64 (+8: a tile of ones gives sum dl)] += dl[32][128 px] x H[128 px][64], K = pixels; warp w owns pixels
+// [32w, 32w+32) of every tile (K split over the warps), dl enters as hi + lo bf16 pairs, H as stored.  The accumulators
+// (raw moments sum dl*h) live across the block's tiles; at the end  S = rstd*(raw - mean * sum dl)  per block, then doubles.
+__global__ void __launch_bounds__(128) head_s_mma_kernel(const float* __restrict__ dlogits, const bf16* __restrict__ h,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         double* S, int N, int HW) {
+  extern __shared__ __align__(1024) uint8_t hs_smem[];
+  uint8_t* tile[2] = {hs_smem, hs_smem + 16384};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  float acc[2][9][4];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    acc0[j] = 0.f;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-  }
+    for (int nt = 0; nt < 9; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
   const int tiles_per_img = (HW + 127) / 128;
   const int ntiles = N * tiles_per_img;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int n = tile / tiles_per_img;
-    const int p0 = (tile - n * tiles_per_img) * 128;
+  int tl = blockIdx.x, buf = 0;
+  if (tl < ntiles) {
+    const int n = tl / tiles_per_img, p0 = (tl - n * tiles_per_img) * 128;
+    stage_tile(tile[0], h, (int64_t)n * HW + p0, min(128, HW - p0));
+  }
+  for (; tl < ntiles; tl += gridDim.x, buf ^= 1) {
+    const int n = tl / tiles_per_img, p0 = (tl - n * tiles_per_img) * 128;
     const int np = min(128, HW - p0);
-    __syncthreads();
-    for (int i = t; i < 20 * 128; i += 256) {
-      int kj = i >> 7, p = i & 127;
-      dl[kj][p] = p < np ? dlogits[((int64_t)n * 20 + kj) * HW + p0 + p] : 0.f;
-    }
-    for (int i = t; i < 128 * 8; i += 256) {
-      int p = i >> 3, v = i & 7;
-      float f[8];
-      if (p < np) {
-        unpack8h(__ldg(h + ((int64_t)n * HW + p0 + p) * 8 + v), f);
-      } else {
+    // A fragments: dl[kj = 16 mt + g (+8)][px = 32 w + 16 ks + 2t (+8), +1]  (HW is even: 8-byte loads)
+    uint32_t ah[2][2][4], al[2][2][4];
+    const float* dl = dlogits + ((int64_t)n * 20) * HW + p0;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = 0.f;
-      }
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) hh[p][v * 8 + e] = p < np ? (f[e] - mean[v * 8 + e]) * rstd[v * 8 + e] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 2
-    for (int pp = 0; pp < 32; pp += 4) {
-      const int p = pq * 32 + pp;
-      float4 x[4];
+      for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4*>(&hh[p + i][cq * 4]);
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const float4 d4 = *reinterpret_cast<const float4*>(&dl[grp * 5 + j][p]);
-        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[j][0] += dv[i] * x[i].x;
-          acc[j][1] += dv[i] * x[i].y;
-          acc[j][2] += dv[i] * x[i].z;
-          acc[j][3] += dv[i] * x[i].w;
+        for (int q = 0; q < 4; ++q) {
+          const int kj = mt * 16 + g + (q & 1) * 8;
+          const int px = warp * 32 + ks * 16 + (q >> 1) * 8 + 2 * t;
+          float2 v = make_float2(0.f, 0.f);
+          if (kj < 20 && px < np) v = __ldg(reinterpret_cast<const float2*>(dl + (int64_t)kj * HW + px));   // np is even too
+          split2(v.x, v.y, ah[mt][ks][q], al[mt][ks][q]);
         }
-        if (cq == 0) acc0[j] += (dv[0] + dv[1]) + (dv[2] + dv[3]);
+    const int nx = tl + gridDim.x;
+    __syncthreads();   // every warp is done reading tile[buf ^ 1] (the previous tile)
+    if (nx < ntiles) {
+      const int n2 = nx / tiles_per_img, q0 = (nx - n2 * tiles_per_img) * 128;
+      stage_tile(tile[buf ^ 1], h, (int64_t)n2 * HW + q0, min(128, HW - q0));
+      stage_wait_1();
+    } else {
+      stage_wait_all();
+    }
+    __syncthreads();
+    const uint32_t tb = smem_addr(tile[buf]);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      // B fragments: H[k = px][n = c], transposed 8x8 loads; lane -> (matrix j = lane / 8: k half j & 1, channel half j >> 1)
+      const int krow = warp * 32 + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int np2 = 0; np2 < 4; ++np2) {   // channel tiles 2 np2, 2 np2 + 1
+        uint32_t b[4];
+        const int chunk = np2 * 2 + (lane >> 4);
+        ldsm_x4_trans(b, tb + krow * 128 + ((chunk ^ (krow & 7)) << 4));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_16816(acc[mt][2 * np2], al[mt][ks], b[0], b[1]);
+          mma_16816(acc[mt][2 * np2], ah[mt][ks], b[0], b[1]);
+          mma_16816(acc[mt][2 * np2 + 1], al[mt][ks], b[2], b[3]);
+          mma_16816(acc[mt][2 * np2 + 1], ah[mt][ks], b[2], b[3]);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {   // ones: sum over pixels of dl
+        mma_16816(acc[mt][8], al[mt][ks], 0x3F803F80u, 0x3F803F80u);
+        mma_16816(acc[mt][8], ah[mt][ks], 0x3F803F80u, 0x3F803F80u);
       }
     }
   }
+  stage_wait_all();
   __syncthreads();
+  // combine the four warps (K split) and publish: part[w][kj 0..19][c 0..64]
+  float(*part)[20][65] = reinterpret_cast<float(*)[20][65]>(hs_smem);   // 4 x 20 x 65 floats = 20.8 KB
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) part[pq][grp * 5 + j][cq * 4 + e] = acc[j][e];
-    if (cq == 0) part[pq][grp * 5 + j][64] = acc0[j];
-  }
+    for (int nt = 0; nt < 9; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kj = mt * 16 + g + (e >> 1) * 8, c = nt * 8 + 2 * t + (e & 1);
+        if (kj < 20 && c < 65) part[warp][kj][c] = acc[mt][nt][e];
+      }
   __syncthreads();
-  for (int i = t; i < 20 * 65; i += 256) {
+  for (int i = threadIdx.x; i < 20 * 65; i += 128) {
     const int kj = i / 65, c = i - kj * 65;
-    const float v = (part[0][kj][c] + part[1][kj][c]) + (part[2][kj][c] + part[3][kj][c]);
+    const float raw = (part[0][kj][c] + part[1][kj][c]) + (part[2][kj][c] + part[3][kj][c]);
+    float v = raw;
+    if (c < 64) {
+      const float s0 = (part[0][kj][64] + part[1][kj][64]) + (part[2][kj][64] + part[3][kj][64]);
+      v = (raw - mean[c] * s0) * rstd[c];
+    }
     atomicAdd(&S[kj * 65 + c], (double)v);
   }
 }
@@ -400,12 +542,13 @@ __global__ void __launch_bounds__(256) head_s4_kernel(const float* __restrict__ 
 bool head_backward_s_bf16(const float* dlogits, const bf16* h, const float* mean, const float* rstd, double* S, int N, int HW,
                           lbc_stream_t s) {
   if (!enabled()) return false;
+  if (HW & 1) return false;   // (8-byte dlogits loads)
   LBC_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 20 * 65, s));
   int grid = sm_count3() * 2;
   int ntiles = N * ((HW + 127) / 128);
   if (grid > ntiles) grid = ntiles;
-  head_s4_kernel<<<grid, 256, 0, s>>>(dlogits, (const uint4*)h, mean, rstd, S, N, HW);
-  LBC_LAUNCHED("head_s4_kernel");
+  head_s_mma_kernel<<<grid, 128, 32768, s>>>(dlogits, h, mean, rstd, S, N, HW);
+  LBC_LAUNCHED("head_s_mma_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }
@@ -414,9 +557,11 @@ bool head_backward_dh_bf16(const float* dlogits, const bf16* h, ref::HeadParams 
   if (!enabled()) return false;
   const int64_t npix = (int64_t)N * HW;
   head_coef(hp, hg, coef, 1.0f / (float)npix, s);
-  head_dh4_kernel<<<(unsigned)((npix + 511) / 512), 128, 0, s>>>(dlogits, (const uint4*)h, fold, coef, hp.mean[0], hp.rstd[0],
-                                                               (uint4*)dh, npix, HW);
-  LBC_LAUNCHED("head_dh4_kernel");
+  const int ntiles = N * ((HW + 127) / 128);
+  int grid = sm_count3() * 4;
+  if (grid > ntiles) grid = ntiles;
+  head_dh_mma_kernel<<<grid, 128, 32768 + 1024, s>>>(dlogits, h, fold, coef, hp.mean[0], hp.rstd[0], dh, N, HW);
+  LBC_LAUNCHED("head_dh_mma_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
 }

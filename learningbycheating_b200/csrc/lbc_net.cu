@@ -83,6 +83,7 @@ class Net : public NetBase {
   T* stem_x4 = nullptr;
   T* stem_w224 = nullptr;
   bool stem_direct_used = false;
+  int stem_layout = 0;   // fast::stem_ch code of stem_x4 / stem_w224 (4, 8, 16)
   std::vector<Block> blocks;
   int trunk_h, trunk_w;
   BNL dbn[3];
@@ -258,9 +259,9 @@ class Net : public NetBase {
       if (tc) {
         stem_gemm.wp16 = alloc<float>(64 * Kp);
       } else if (fast::stem_ch(in_ch)) {   // zero-padded NHWC4 / NHWC8 image + overlapping-window TMA: no column tensor
-        const int CH = fast::stem_ch(in_ch);
-        stem_x4 = alloc<T>(B * (in_h + 6) * (in_w + 8) * CH);
-        stem_w224 = alloc<T>(64 * 7 * 8 * CH);
+        stem_layout = fast::stem_ch(in_ch, in_w, normalize);
+        stem_x4 = alloc<T>(B * (in_h + 6) * (in_w + 8) * fast::stem_x_ch(stem_layout));
+        stem_w224 = alloc<T>(fast::stem_w_elems(stem_layout));
       } else {
         stem_col = alloc<T>(B * stem_oh * stem_ow * Kp);
       }
@@ -633,9 +634,9 @@ class Net : public NetBase {
       float* part = (train && part_fits) ? fast::stat_partial_buffer() : nullptr;
       bool ok = (u8_image ? fast::stem_pad4_u8_bf16(u8_image, u8_layout, (bf16*)stem_x4, B, in_ch, in_h, in_w, normalize, s)
                           : fast::stem_pad4_bf16(image, (bf16*)stem_x4, B, in_ch, in_h, in_w, normalize, s)) &&
-                fast::stem_pack_w224_bf16(P + stem.w_off, (bf16*)stem_w224, in_ch, s) &&
+                fast::stem_pack_w224_bf16(P + stem.w_off, (bf16*)stem_w224, in_ch, s, stem_layout) &&
                 fast::stem_conv_bf16((const bf16*)stem_x4, (const bf16*)stem_w224, (bf16*)r_stem, B, in_h, in_w, stem_oh,
-                                     stem_ow, stem_bn.negshift, part, &stem_stat_rows, s, fast::stem_ch(in_ch));
+                                     stem_ow, stem_bn.negshift, part, &stem_stat_rows, s, stem_layout);
       LBC_CHECK(ok, "stem direct (overlapping-window TMA) path failed");
       stem_fast_used = stem_direct_used = true;
       if (!part) stem_stat_rows = 0;
@@ -864,7 +865,7 @@ class Net : public NetBase {
     if (stem_direct_used) {
       ProfScope ps("conv_wgrad", s, conv_flops(stem, B), 0);
       stem_wgrad_done = fast::stem_wgrad_bf16((const bf16*)stem_x4, (const bf16*)tB, G + stem.w_off, B, in_ch, in_h, in_w,
-                                              stem_oh, stem_ow, s, fast::stem_ch(in_ch));
+                                              stem_oh, stem_ow, s, stem_layout);
       LBC_CHECK(stem_wgrad_done, "stem direct weight gradient failed");
     } else if (stem_fast_used) {
       ProfScope ps("conv_wgrad", s, conv_flops(stem, B), 0);

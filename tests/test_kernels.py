@@ -428,10 +428,18 @@ def test_spatial_softmax_kernel_gpu(backend):
 _MEAN, _STD = torch.tensor([0.485, 0.456, 0.406]), torch.tensor([0.229, 0.224, 0.225])
 
 
-def _stem_case(dev, N, C, H, W, precision, frames):
+def _stem_case(dev, N, C, H, W, precision, frames, s2d=True):
     """frames: 'f32' | 'u8' ([N,C,H,W] uint8) | 'u8hwc' (the on-disk [N,H,W,C])"""
     _lib = _L()
     L = _lib.lib()
+    _lib.check(L.lbc_set_fast_kernels(1 | (256 if s2d else 512)))
+    try:
+        _stem_case_body(_lib, L, dev, N, C, H, W, precision, frames, s2d)
+    finally:
+        _lib.check(L.lbc_set_fast_kernels(1 | 256))
+
+
+def _stem_case_body(_lib, L, dev, N, C, H, W, precision, frames, s2d):
     g = torch.Generator().manual_seed(23)
     u8 = torch.randint(0, 256, (N, C, H, W), dtype=torch.uint8, generator=g)
     img = u8.float() / 255
@@ -450,12 +458,15 @@ def _stem_case(dev, N, C, H, W, precision, frames):
     u8d = d(u8) if frames == "u8" else (d(u8.permute(0, 2, 3, 1)) if frames == "u8hwc" else None)
     wd, dyd = d(wgt), d(_nhwc(dy))
     direct = precision == 1 and C <= 8        # padded NHWC4 (camera) / NHWC8 (7-channel bird's-eye view) operand
+    layout = L.lbc_stem_layout(C, W, int(normalize))          # 16: NHWC4 with every 2x2 pixel block contiguous (space to depth)
+    assert layout == (8 if C > 4 else 16 if (s2d and W % 4 == 0) else 4) or not direct
     CH = 4 if C <= 4 else 8
     x4 = torch.empty(N, H + 6, W + 8, CH, device=dev) if direct else None
     y, dw = torch.empty(N, OH, OW, 64, device=dev), torch.empty(64, C, 7, 7, device=dev)
     stats = torch.empty(128, device=dev) if direct else None
     if precision == 1:
-        must = ["stem_conv_kernel", "stem_wgrad_kernel"] if direct else ["stem_im2col_kernel", "conv_gemm_kernel<64>", "wgrad_gemm_kernel<64>"]
+        tag = {4: "", 8: "<8ch>", 16: "<s2d>"}.get(layout, "")
+        must = ["stem_conv_kernel" + tag, "stem_wgrad_kernel" + tag] if direct else ["stem_im2col_kernel", "conv_gemm_kernel<64>", "wgrad_gemm_kernel<64>"]
     elif precision == 2:
         must = ["tc_stem_im2col_kernel", "conv_gemm_kernel<64,f32>", "wgrad_gemm_kernel<64>"]
     else:
@@ -468,6 +479,8 @@ def _stem_case(dev, N, C, H, W, precision, frames):
         pad = torch.zeros(N, H + 6, W + 8, CH)
         pad[:, 3:3 + H, 4:4 + W, :C] = _nhwc(xr)
         got = x4.cpu()
+        if layout == 16:   # [N][(H+6)/2][(W+8)/2][row parity][column parity][4] -> [N][H+6][W+8][4]
+            got = got.reshape(N, (H + 6) // 2, (W + 8) // 2, 2, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(N, H + 6, W + 8, 4)
         assert (got - pad).abs().max() <= 2 ** -7 * 3, (got - pad).abs().max()        # at most one bf16 ulp (division rounding)
         assert ((got - pad).abs() > 0).float().mean() < 1e-3
         yb = y.cpu()
@@ -484,9 +497,18 @@ def test_stem_cpu(backend, C):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("s2d", [True, False], ids=["s2d", "rows7"])
 @pytest.mark.parametrize("frames", ["f32", "u8", "u8hwc"])
-def test_stem_kernels_student_gpu(backend, frames):
-    _stem_case("cuda", 3, 3, 160, 384, 1, frames)
+def test_stem_kernels_student_gpu(backend, frames, s2d):
+    _stem_case("cuda", 3, 3, 160, 384, 1, frames, s2d)
+
+
+@pytest.mark.gpu
+def test_stem_kernels_odd_shapes_gpu(backend):
+    """batch tail (N not a multiple of the tile's image count) in both operand layouts; 4 input channels"""
+    _stem_case("cuda", 5, 3, 32, 64, 1, "u8")
+    _stem_case("cuda", 5, 3, 32, 64, 1, "u8", s2d=False)
+    _stem_case("cuda", 2, 4, 32, 64, 1, "f32")
 
 
 @pytest.mark.gpu
