@@ -153,72 +153,82 @@ bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, i
 // KIND 0: fp32 [B,C,H,W]; 1: uint8 [B,C,H,W]; 2: uint8 [B,H,W,C].  Same per-element expressions as the one-pixel writers
 // below (bit-identical output); 32-byte stores, 16-byte / 4-byte vector loads, 4x fewer threads (round 1: 222 us for the
 // 132 MB tensor at B = 256, bound by block dispatch of 16.6 M one-pixel threads).
-// s2d: the same values in the space-to-depth arrangement ([row/2][col/2][row&1][col&1][4]): the thread's two pixel pairs go
-// to the 16-byte halves (row parity) of two neighbouring 32-byte 2x2 blocks
-template <int KIND>
+// Four padded pixels of ROWS padded rows per thread.  ROWS = 1: [B][H+6][W+8][4], 32 contiguous bytes per thread.
+// ROWS = 2 (space-to-depth operand, lbc_fast.h: stem_ch = 16): rows 2Y, 2Y+1 -> the two 2x2 blocks (Y, 2*gcol), (Y, 2*gcol+1)
+// = 64 contiguous bytes per thread ([row parity][column parity][4 ch] per block).  (Writing one row per thread in that layout
+// stored 16-byte pieces 32 bytes apart -- half sectors, completed by another warp: 117 us instead of 97 us per launch.)
+template <int KIND, int ROWS>
 __global__ void __launch_bounds__(256) stem_pad4_kernel(const void* __restrict__ img, uint4* __restrict__ x4, int B, int C, int H,
-                                                        int W, int normalize, int s2d) {
+                                                        int W, int normalize) {
   const int HP = H + 6, WG = (W + 8) / 4;
-  const int64_t n = (int64_t)B * HP * WG;
+  const int64_t n = (int64_t)B * (HP / ROWS) * WG;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int gcol = (int)(i % WG);
     const int64_t t = i / WG;
-    const int row = (int)(t % HP);
-    const int b = (int)(t / HP);
-    const int ih = row - 3, iw = gcol * 4 - 4;
-    float v[4][4];
+    const int yrow = (int)(t % (HP / ROWS));
+    const int b = (int)(t / (HP / ROWS));
+    const int iw = gcol * 4 - 4;
+    uint32_t w[ROWS][8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+    for (int rr = 0; rr < ROWS; ++rr) {
+      const int ih = yrow * ROWS + rr - 3;
+      float v[4][4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[p][c] = 0.f;
-    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-      for (int c = 0; c < C; ++c) {
-        float x[4];
-        if (KIND == 0) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>((const float*)img + (((int64_t)b * C + c) * H + ih) * W + iw));
-          x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-        } else if (KIND == 1) {
-          const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>((const uint8_t*)img + (((int64_t)b * C + c) * H + ih) * W + iw));
+      for (int p = 0; p < 4; ++p)
 #pragma unroll
-          for (int p = 0; p < 4; ++p) x[p] = (float)((q >> (8 * p)) & 0xffu) / 255.0f;
-        } else {
-          const uint8_t* src = (const uint8_t*)img + (((int64_t)b * H + ih) * W + iw) * C + c;
+        for (int c = 0; c < 4; ++c) v[p][c] = 0.f;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        for (int c = 0; c < C; ++c) {
+          float x[4];
+          if (KIND == 0) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>((const float*)img + (((int64_t)b * C + c) * H + ih) * W + iw));
+            x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+          } else if (KIND == 1) {
+            const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>((const uint8_t*)img + (((int64_t)b * C + c) * H + ih) * W + iw));
 #pragma unroll
-          for (int p = 0; p < 4; ++p) x[p] = (float)__ldg(src + p * C) / 255.0f;
+            for (int p = 0; p < 4; ++p) x[p] = (float)((q >> (8 * p)) & 0xffu) / 255.0f;
+          } else {
+            const uint8_t* src = (const uint8_t*)img + (((int64_t)b * H + ih) * W + iw) * C + c;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) x[p] = (float)__ldg(src + p * C) / 255.0f;
+          }
+          const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+          const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) v[p][c] = normalize ? (x[p] - mean) / sd : x[p];
         }
-        const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
-        const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+      }
 #pragma unroll
-        for (int p = 0; p < 4; ++p) v[p][c] = normalize ? (x[p] - mean) / sd : x[p];
+      for (int p = 0; p < 4; ++p) {
+        w[rr][2 * p] = (uint32_t)float_to_bf16(v[p][0]).v | ((uint32_t)float_to_bf16(v[p][1]).v << 16);
+        w[rr][2 * p + 1] = (uint32_t)float_to_bf16(v[p][2]).v | ((uint32_t)float_to_bf16(v[p][3]).v << 16);
       }
     }
-    uint32_t w[8];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      w[2 * p] = (uint32_t)float_to_bf16(v[p][0]).v | ((uint32_t)float_to_bf16(v[p][1]).v << 16);
-      w[2 * p + 1] = (uint32_t)float_to_bf16(v[p][2]).v | ((uint32_t)float_to_bf16(v[p][3]).v << 16);
-    }
-    if (s2d) {
-      // 2x2 block (Y, X) = 16 elements = two 16-byte halves (row parity a); this thread holds blocks X = 2*gcol, 2*gcol + 1
-      const int64_t blk = ((int64_t)b * (HP / 2) + (row >> 1)) * (2 * WG) + 2 * gcol;
-      x4[blk * 2 + (row & 1)] = make_uint4(w[0], w[1], w[2], w[3]);
-      x4[(blk + 1) * 2 + (row & 1)] = make_uint4(w[4], w[5], w[6], w[7]);
+    if (ROWS == 1) {
+      x4[i * 2] = make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]);
+      x4[i * 2 + 1] = make_uint4(w[0][4], w[0][5], w[0][6], w[0][7]);
     } else {
-      x4[i * 2] = make_uint4(w[0], w[1], w[2], w[3]);
-      x4[i * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+      // block (Y, X) = 32 bytes = [row 2Y: px 2X, 2X+1][row 2Y+1: px 2X, 2X+1]; this thread: X = 2*gcol, 2*gcol + 1
+      x4[i * 4] = make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]);
+      x4[i * 4 + 1] = make_uint4(w[ROWS - 1][0], w[ROWS - 1][1], w[ROWS - 1][2], w[ROWS - 1][3]);
+      x4[i * 4 + 2] = make_uint4(w[0][4], w[0][5], w[0][6], w[0][7]);
+      x4[i * 4 + 3] = make_uint4(w[ROWS - 1][4], w[ROWS - 1][5], w[ROWS - 1][6], w[ROWS - 1][7]);
     }
   }
 }
 template <int KIND>
 static bool launch_stem_pad4(const void* img, bf16* x4, int B, int C, int H, int W, bool normalize, lbc_stream_t s) {
-  const int s2d = stem_ch(C, W, normalize) == 16 ? 1 : 0;
-  const int64_t n = (int64_t)B * (H + 6) * ((W + 8) / 4);
+  const bool s2d = stem_ch(C, W, normalize) == 16;
+  const int64_t n = (int64_t)B * ((H + 6) / (s2d ? 2 : 1)) * ((W + 8) / 4);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t blocks = (n + 255) / 256, cap = (int64_t)sms * 16;
   if (blocks > cap) blocks = cap;
-  stem_pad4_kernel<KIND><<<(unsigned)blocks, 256, 0, s>>>(img, (uint4*)x4, B, C, H, W, normalize ? 1 : 0, s2d);
+  if (s2d)
+    stem_pad4_kernel<KIND, 2><<<(unsigned)blocks, 256, 0, s>>>(img, (uint4*)x4, B, C, H, W, normalize ? 1 : 0);
+  else
+    stem_pad4_kernel<KIND, 1><<<(unsigned)blocks, 256, 0, s>>>(img, (uint4*)x4, B, C, H, W, normalize ? 1 : 0);
   LBC_LAUNCHED(KIND == 0 ? "stem_pad4_kernel<f32>" : "stem_pad4_kernel<u8>");
   LBC_CUDA(cudaGetLastError());
   return true;

@@ -85,7 +85,7 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
 }
 // stage the [128 pixels][64 channels] bf16 tile of image n starting at pixel p0 (np valid pixels, the rest zero-filled):
 // 16-byte chunk c of row r lands at chunk (c ^ (r & 7)) -- the 128-byte swizzle
-__device__ __forceinline__ void stage_tile(uint8_t* tile, const bf16* h, int64_t pix0, int np) {
+__device__ __forceinline__ void stage_h(uint8_t* tile, const bf16* h, int64_t pix0, int np) {
   const uint8_t* src = reinterpret_cast<const uint8_t*>(h) + pix0 * 128;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -97,7 +97,25 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const bf16* h, int64_t
                  "r"(bytes)
                  : "memory");
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const bf16* h, int64_t pix0, int np) {
+  stage_h(tile, h, pix0, np);
+  stage_commit();
+}
+// the 20 dlogits rows of the same 128 pixels ([20][PAD] floats, PAD chosen by the reader against bank conflicts): rows of
+// 512 contiguous bytes in global memory (HW % 4 == 0), pixels >= np zero-filled
+template <int PAD>
+__device__ __forceinline__ void stage_dl(float* dst, const float* dl, int HW, int np) {
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int i = threadIdx.x + 128 * j;
+    const int kj = i >> 5, px = (i & 31) * 4;
+    const int bytes = px < np ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(dst + kj * PAD + px)),
+                 "l"(dl + (int64_t)kj * HW + (px < np ? px : 0)), "r"(bytes)
+                 : "memory");
+  }
 }
 __device__ __forceinline__ void stage_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void stage_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -299,6 +317,8 @@ __global__ void __launch_bounds__(128) head_dh_mma_kernel(const float* __restric
   extern __shared__ __align__(1024) uint8_t hs_smem[];
   uint8_t* tile[2] = {hs_smem, hs_smem + 16384};
   float* cf = reinterpret_cast<float*>(hs_smem + 32768);   // c0 | c1 | mean | rstd
+  constexpr int DPAD = 132;                                 // A fragments read dls[kj = 2t (+1)][px = g]: banks 8t + g (+4)
+  float* dls[2] = {reinterpret_cast<float*>(hs_smem + 33792), reinterpret_cast<float*>(hs_smem + 33792 + 20 * DPAD * 4)};
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   if (threadIdx.x < 64) {
@@ -323,14 +343,27 @@ __global__ void __launch_bounds__(128) head_dh_mma_kernel(const float* __restric
   int tl = blockIdx.x, buf = 0;
   if (tl < ntiles) {
     const int n = tl / tiles_per_img, p0 = (tl - n * tiles_per_img) * 128;
-    stage_tile(tile[0], h, (int64_t)n * HW + p0, min(128, HW - p0));
+    stage_h(tile[0], h, (int64_t)n * HW + p0, min(128, HW - p0));
+    stage_dl<DPAD>(dls[0], dlogits + ((int64_t)n * 20) * HW + p0, HW, min(128, HW - p0));
+    stage_commit();
   }
   for (; tl < ntiles; tl += gridDim.x, buf ^= 1) {
     const int n = tl / tiles_per_img, p0 = (tl - n * tiles_per_img) * 128;
     const int np = min(128, HW - p0);
-    // this warp's dlogits fragments (global, 8 consecutive pixels per kj row and load = full 32-byte sectors)
+    const int nx = tl + gridDim.x;
+    if (nx < ntiles) {
+      const int n2 = nx / tiles_per_img, q0 = (nx - n2 * tiles_per_img) * 128;
+      stage_h(tile[buf ^ 1], h, (int64_t)n2 * HW + q0, min(128, HW - q0));   // (free: barrier at the end of the last tile)
+      stage_dl<DPAD>(dls[buf ^ 1], dlogits + ((int64_t)n2 * 20) * HW + q0, HW, min(128, HW - q0));
+      stage_commit();
+      stage_wait_1();
+    } else {
+      stage_wait_all();
+    }
+    __syncthreads();
+    // this warp's dlogits fragments, hi / lo pairs
     uint32_t ah[2][2][4], al[2][2][4];
-    const float* dl = dlogits + ((int64_t)n * 20) * HW + p0;
+    const float* dl = dls[buf];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -339,19 +372,10 @@ __global__ void __launch_bounds__(128) head_dh_mma_kernel(const float* __restric
         for (int q = 0; q < 4; ++q) {
           const int px = warp * 32 + mt * 16 + g + (q & 1) * 8;
           const int kj = ks * 16 + (q >> 1) * 8 + 2 * t;
-          const float v0 = (px < np && kj < 20) ? __ldg(dl + (int64_t)kj * HW + px) : 0.f;
-          const float v1 = (px < np && kj + 1 < 20) ? __ldg(dl + (int64_t)(kj + 1) * HW + px) : 0.f;
+          const float v0 = kj < 20 ? dl[kj * DPAD + px] : 0.f;
+          const float v1 = kj + 1 < 20 ? dl[(kj + 1) * DPAD + px] : 0.f;
           split2(v0, v1, ah[mt][ks][q], al[mt][ks][q]);
         }
-    const int nx = tl + gridDim.x;
-    if (nx < ntiles) {
-      const int n2 = nx / tiles_per_img, q0 = (nx - n2 * tiles_per_img) * 128;
-      stage_tile(tile[buf ^ 1], h, (int64_t)n2 * HW + q0, min(128, HW - q0));   // (free: barrier at the end of the last tile)
-      stage_wait_1();
-    } else {
-      stage_wait_all();
-    }
-    __syncthreads();
     uint8_t* tb = tile[buf];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -442,6 +466,8 @@ __global__ void __launch_bounds__(128) head_s_mma_kernel(const float* __restrict
                                                          double* S, int N, int HW) {
   extern __shared__ __align__(1024) uint8_t hs_smem[];
   uint8_t* tile[2] = {hs_smem, hs_smem + 16384};
+  constexpr int DPAD = 136;   // A fragments read 8 bytes at dls[kj = g][px = 2t]: banks 8g + 2t over a half warp
+  float* dls[2] = {reinterpret_cast<float*>(hs_smem + 32768), reinterpret_cast<float*>(hs_smem + 32768 + 20 * DPAD * 4)};
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   float acc[2][9][4];
@@ -456,14 +482,26 @@ __global__ void __launch_bounds__(128) head_s_mma_kernel(const float* __restrict
   int tl = blockIdx.x, buf = 0;
   if (tl < ntiles) {
     const int n = tl / tiles_per_img, p0 = (tl - n * tiles_per_img) * 128;
-    stage_tile(tile[0], h, (int64_t)n * HW + p0, min(128, HW - p0));
+    stage_h(tile[0], h, (int64_t)n * HW + p0, min(128, HW - p0));
+    stage_dl<DPAD>(dls[0], dlogits + ((int64_t)n * 20) * HW + p0, HW, min(128, HW - p0));
+    stage_commit();
   }
   for (; tl < ntiles; tl += gridDim.x, buf ^= 1) {
-    const int n = tl / tiles_per_img, p0 = (tl - n * tiles_per_img) * 128;
-    const int np = min(128, HW - p0);
-    // A fragments: dl[kj = 16 mt + g (+8)][px = 32 w + 16 ks + 2t (+8), +1]  (HW is even: 8-byte loads)
+    const int nx = tl + gridDim.x;
+    __syncthreads();   // every warp is done with the previous tile (its buffers are refilled now)
+    if (nx < ntiles) {
+      const int n2 = nx / tiles_per_img, q0 = (nx - n2 * tiles_per_img) * 128;
+      stage_h(tile[buf ^ 1], h, (int64_t)n2 * HW + q0, min(128, HW - q0));
+      stage_dl<DPAD>(dls[buf ^ 1], dlogits + ((int64_t)n2 * 20) * HW + q0, HW, min(128, HW - q0));
+      stage_commit();
+      stage_wait_1();
+    } else {
+      stage_wait_all();
+    }
+    __syncthreads();
+    // A fragments: dl[kj = 16 mt + g (+8)][px = 32 w + 16 ks + 2t (+8), +1], hi / lo pairs
     uint32_t ah[2][2][4], al[2][2][4];
-    const float* dl = dlogits + ((int64_t)n * 20) * HW + p0;
+    const float* dl = dls[buf];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -473,19 +511,9 @@ __global__ void __launch_bounds__(128) head_s_mma_kernel(const float* __restrict
           const int kj = mt * 16 + g + (q & 1) * 8;
           const int px = warp * 32 + ks * 16 + (q >> 1) * 8 + 2 * t;
           float2 v = make_float2(0.f, 0.f);
-          if (kj < 20 && px < np) v = __ldg(reinterpret_cast<const float2*>(dl + (int64_t)kj * HW + px));   // np is even too
+          if (kj < 20) v = *reinterpret_cast<const float2*>(dl + kj * DPAD + px);
           split2(v.x, v.y, ah[mt][ks][q], al[mt][ks][q]);
         }
-    const int nx = tl + gridDim.x;
-    __syncthreads();   // every warp is done reading tile[buf ^ 1] (the previous tile)
-    if (nx < ntiles) {
-      const int n2 = nx / tiles_per_img, q0 = (nx - n2 * tiles_per_img) * 128;
-      stage_tile(tile[buf ^ 1], h, (int64_t)n2 * HW + q0, min(128, HW - q0));
-      stage_wait_1();
-    } else {
-      stage_wait_all();
-    }
-    __syncthreads();
     const uint32_t tb = smem_addr(tile[buf]);
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
@@ -542,12 +570,18 @@ __global__ void __launch_bounds__(128) head_s_mma_kernel(const float* __restrict
 bool head_backward_s_bf16(const float* dlogits, const bf16* h, const float* mean, const float* rstd, double* S, int N, int HW,
                           lbc_stream_t s) {
   if (!enabled()) return false;
-  if (HW & 1) return false;   // (8-byte dlogits loads)
+  if (HW & 3) return false;   // (16-byte dlogits staging)
   LBC_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 20 * 65, s));
   int grid = sm_count3() * 2;
   int ntiles = N * ((HW + 127) / 128);
   if (grid > ntiles) grid = ntiles;
-  head_s_mma_kernel<<<grid, 128, 32768, s>>>(dlogits, h, mean, rstd, S, N, HW);
+  constexpr int SMEM = 32768 + 2 * 20 * 136 * 4;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(head_s_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  head_s_mma_kernel<<<grid, 128, SMEM, s>>>(dlogits, h, mean, rstd, S, N, HW);
   LBC_LAUNCHED("head_s_mma_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -560,7 +594,13 @@ bool head_backward_dh_bf16(const float* dlogits, const bf16* h, ref::HeadParams 
   const int ntiles = N * ((HW + 127) / 128);
   int grid = sm_count3() * 4;
   if (grid > ntiles) grid = ntiles;
-  head_dh_mma_kernel<<<grid, 128, 32768 + 1024, s>>>(dlogits, h, fold, coef, hp.mean[0], hp.rstd[0], dh, N, HW);
+  constexpr int SMEM = 32768 + 1024 + 2 * 20 * 132 * 4;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(head_dh_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  head_dh_mma_kernel<<<grid, 128, SMEM, s>>>(dlogits, h, fold, coef, hp.mean[0], hp.rstd[0], dh, N, HW);
   LBC_LAUNCHED("head_dh_mma_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
