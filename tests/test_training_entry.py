@@ -77,3 +77,57 @@ def test_cuda_prefetcher_fixed_slots_gpu():
         assert torch.equal(a.cpu(), batches[i][0])
     torch.cuda.synchronize()
     assert torch.cuda.memory_reserved() <= m0 + (4 << 20)
+
+
+def test_phase1_batch_aug_and_speed_noise_cpu(backend, monkeypatch):
+    """a17 (training/train_image_phase1.py:131-154,170-189): a [B, batch_aug, 3, H, W] frame tensor is flattened and the
+    per-sample inputs are repeated batch_aug times (numpy.repeat order); in training the speed gets N(0, speed_noise)
+    noise clamped to [0, 10] BEFORE it is repeated; evaluation passes the speed through."""
+    import numpy as np
+    from learningbycheating_b200 import train_image_phase1 as p1
+    # repeat == numpy.repeat along dim 0 (the reference's helper is an index_select over arange(n).repeat)
+    a = torch.arange(12.).reshape(3, 4)
+    assert torch.equal(p1.repeat(a, 2), torch.from_numpy(np.repeat(a.numpy(), 2, axis=0)))
+    assert torch.equal(p1.repeat(a, 3, dim=1), torch.from_numpy(np.repeat(a.numpy(), 3, axis=1)))
+
+    dev = backend
+    s, t = build_models(dev, "fp32")
+    s.eval()
+    t.eval()
+    b = batch_on(dev, 2)
+    B, aug = 1, 2
+    rgb5 = b["rgb"].reshape(B, aug, 3, 160, 384)
+    data = [(rgb5, b["birdview"][:B], b["location"][:B], b["command"][:B], b["speed"][:B])]
+    conv, crit = p1.CoordConverter(fixed_offset=4.0, device=dev), p1.LocationLoss()
+    config = dict(device=dev, log_iterations=1000, speed_noise=0.0)
+    seen = []
+    orig = type(t).forward
+
+    def spy(self, birdview, speed, command):
+        seen.append((birdview.clone(), speed.clone(), command.clone()))
+        return orig(self, birdview, speed, command)
+    monkeypatch.setattr(type(t), "forward", spy)
+    got = p1.train_or_eval(conv, crit, s, t, data, None, False, config, False)
+    # the same thing by hand on the flattened batch
+    import learningbycheating_b200 as lbc
+    oh = lbc.one_hot(b["command"][:B].cpu()).to(dev)
+    bev2, sp2, oh2 = (torch.repeat_interleave(x, aug, 0) for x in (b["birdview"][:B], b["speed"][:B], oh))
+    with torch.no_grad():
+        _, tl = orig(t, bev2, sp2, oh2)
+        _, pl = s(b["rgb"], sp2, oh2)
+        want = crit(conv(pl), tl).mean()
+    assert abs(float(got[0]) - float(want)) < 1e-6
+    assert seen[0][0].shape[0] == B * aug and torch.equal(seen[0][1], sp2) and torch.equal(seen[0][2], oh2)
+
+    # speed noise: training only, clamped, drawn per SAMPLE (before the repeat)
+    seen.clear()
+    monkeypatch.setattr(torch, "randn", lambda size, device=None: torch.tensor([100.0], device=device).expand(size))
+    config["speed_noise"] = 1.0
+    p1.train_or_eval(conv, crit, s, t, data, None, False, config, False)             # eval: untouched
+    assert torch.equal(seen[-1][1], sp2)
+    s.train()
+    p1.train_or_eval(conv, crit, s, t, data, None, True, config, True)               # first-epoch dry run: no optimizer step
+    assert torch.equal(seen[-1][1], torch.full_like(sp2, 10.0))
+    monkeypatch.setattr(torch, "randn", lambda size, device=None: torch.tensor([-100.0], device=device).expand(size))
+    p1.train_or_eval(conv, crit, s, t, data, None, True, config, True)
+    assert torch.equal(seen[-1][1], torch.zeros_like(sp2))
