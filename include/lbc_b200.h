@@ -86,6 +86,15 @@ int lbc_net_forward_u8(lbc_net_t* net, const uint8_t* image_u8, int layout, cons
 /* loss.backward() through the network (train_image_phase0.py:184): upstream gradients wrt out_pred [B,5,2]
  * and/or out_preds [B,4,5,2] (NULL = none); writes every on-path parameter gradient into the bound
  * gradient array (overwrites, like backward() after zero_grad()). */
+/* Low-latency eval forward (replaces the per-frame model call of ImageAgent.run_step, bird_view/models/image.py:124-196):
+ * same results as lbc_net_forward(..., train = 0), replayed as one CUDA graph per (B, input kind) on an engine-owned stream
+ * that is joined to `stream` with events.  Exactly one of image (fp32 [B,C,H,W]) / image_u8 (layout 0 [B,C,H,W], 1 [B,H,W,C])
+ * is non-null.  weights_changed != 0: the parameters were modified since the previous lbc_net_infer call (the weight
+ * operands are re-packed before the replay; training-mode calls in between re-pack on their own). */
+int lbc_net_infer(lbc_net_t* net, const float* image, const uint8_t* image_u8, int layout, const float* speed,
+                  const float* command_onehot, int B, int weights_changed, float* out_pred, float* out_preds, void* stream);
+/* number of CUDA-graph replays lbc_net_infer has issued (0 on the host-emulation build and while a path is not capturable) */
+int lbc_net_infer_replays(const lbc_net_t* net);
 int lbc_net_backward(lbc_net_t* net, const float* d_pred, const float* d_preds, void* stream);
 /* Data-parallel overlap (new: the reference is single-GPU; SURVEY.md 8(e) "one all-reduce, bucketed in reverse-execution
  * order and overlapped with backward").  The on-path gradients form lbc_net_num_grad_buckets() contiguous ranges of the flat

@@ -48,6 +48,8 @@ def _declare(lib):
         "lbc_net_bind": (i, [vp, vp, vp, vp]),
         "lbc_net_forward": (i, [vp, vp, vp, vp, i, i, vp, vp, vp]),
         "lbc_net_forward_u8": (i, [vp, vp, i, vp, vp, i, i, vp, vp, vp]),
+        "lbc_net_infer": (i, [vp, vp, vp, i, vp, vp, i, i, vp, vp, vp]),
+        "lbc_net_infer_replays": (i, [vp]),
         "lbc_net_backward": (i, [vp, vp, vp, vp]),
         "lbc_net_read_tap": (i64, [vp, ctypes.c_char_p, vp, i64, vp]),
         "lbc_net_num_grad_buckets": (i, [vp]),

@@ -115,6 +115,14 @@ def _head_params(ow, oh, steps=5, commands=4):
 _PARAM_OWNER = {}
 
 
+def _infer_graph_max_b():
+    """Eval-mode forwards of at most this many samples go through lbc_net_infer (one CUDA-graph replay); 0 disables."""
+    try:
+        return int(os.environ.get("LBC_B200_INFER_GRAPH_MAX_B", "16"))
+    except ValueError:
+        return 16
+
+
 def owner_of(param):
     ref = _PARAM_OWNER.get(id(param))
     return ref() if ref is not None else None
@@ -140,6 +148,9 @@ class _NativeState:
         # number, an autograd node may differentiate only the generation it produced, and only once
         self.fwd_gen = 0
         self.bwd_done_gen = -1
+        # low-latency inference (lbc_net_infer): what the packed weight operands were last built from
+        self.param_epoch = 0          # bumped by lbc.Adam (its kernel writes through the raw pointer)
+        self.infer_seen = None        # (flat_params._version, param_epoch) at the previous graph replay
 
     def destroy(self):
         if self.handle is not None:
@@ -346,6 +357,17 @@ class PolicyNetBase(nn.Module):
         x, velocity, command = x.contiguous(), velocity.contiguous(), command.contiguous()
         pred = torch.empty(B, 5, 2, dtype=torch.float32, device=st.device)
         preds = torch.empty(B, 4, 5, 2, dtype=torch.float32, device=st.device)
+        if not train and st.device.type == "cuda" and B <= _infer_graph_max_b():
+            # per-frame inference (ImageAgent.run_step): one CUDA-graph replay instead of ~130 launches
+            seen = (st.flat_params._version, st.param_epoch)
+            changed = seen != st.infer_seen
+            st.infer_seen = seen
+            u8 = x.dtype == torch.uint8
+            layout = 1 if (u8 and tuple(x.shape[1:]) != tuple(self._lbc_input_shape)) else 0
+            _lib.check(_lib.lib().lbc_net_infer(st.handle, None if u8 else _lib.ptr(x), _lib.ptr(x) if u8 else None, layout,
+                                                _lib.ptr(velocity), _lib.ptr(command), B, 1 if changed else 0, _lib.ptr(pred),
+                                                _lib.ptr(preds), _lib.stream_ptr(st.device)))
+            return pred, preds
         if x.dtype == torch.uint8:
             layout = 0 if tuple(x.shape[1:]) == tuple(self._lbc_input_shape) else 1
             _lib.check(_lib.lib().lbc_net_forward_u8(st.handle, _lib.ptr(x), layout, _lib.ptr(velocity), _lib.ptr(command),

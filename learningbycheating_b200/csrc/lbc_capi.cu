@@ -238,6 +238,13 @@ int lbc_net_forward_u8(lbc_net_t* net, const uint8_t* image_u8, int layout, cons
     net->impl->forward_u8(image_u8, layout, speed, command_onehot, B, train != 0, out_pred, out_preds, S(stream));
   });
 }
+int lbc_net_infer(lbc_net_t* net, const float* image, const uint8_t* image_u8, int layout, const float* speed,
+                  const float* command_onehot, int B, int weights_changed, float* out_pred, float* out_preds, void* stream) {
+  return guarded([&] {
+    net->impl->infer(image, image_u8, layout, speed, command_onehot, B, weights_changed != 0, out_pred, out_preds, S(stream));
+  });
+}
+int lbc_net_infer_replays(const lbc_net_t* net) { return net->impl->infer_replays; }
 int lbc_net_backward(lbc_net_t* net, const float* d_pred, const float* d_preds, void* stream) {
   return guarded([&] { net->impl->backward(d_pred, d_preds, S(stream)); });
 }

@@ -28,6 +28,136 @@ void nhwc_to_nchw_f32(lbc_stream_t s, const T* x, float* out, int N, int H, int 
 }
 }  // namespace ref
 
+#ifndef LBC_HOST_EMU
+void NetBase::infer_release() {
+  for (InferGraph& g : infer_graphs)
+    if (g.exec) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
+  infer_graphs.clear();
+  for (void* p : {(void*)inf_img, (void*)inf_speed, (void*)inf_onehot, (void*)inf_pred, (void*)inf_preds, (void*)inf_img_u8})
+    if (p) cudaFree(p);
+  inf_img = inf_speed = inf_onehot = inf_pred = inf_preds = nullptr;
+  inf_img_u8 = nullptr;
+  if (infer_ev_in) cudaEventDestroy((cudaEvent_t)infer_ev_in);
+  if (infer_ev_out) cudaEventDestroy((cudaEvent_t)infer_ev_out);
+  if (infer_stream) cudaStreamDestroy((cudaStream_t)infer_stream);
+  infer_ev_in = infer_ev_out = infer_stream = nullptr;
+}
+void NetBase::infer(const float* image, const uint8_t* image_u8, int layout, const float* speed, const float* onehot, int B,
+                    bool weights_changed, float* out_pred, float* out_preds, lbc_stream_t s) {
+  LBC_CHECK((image != nullptr) != (image_u8 != nullptr), "lbc_net_infer: exactly one of image / image_u8");
+  LBC_CHECK(speed && onehot, "lbc_net_infer: null input");
+  LBC_CHECK(B >= 1 && B <= max_batch, "lbc_net_infer: batch " + std::to_string(B) + " outside [1, max_batch]");
+  LBC_CHECK(P && BUF, "lbc_net_infer: parameters not bound");
+  const int64_t img_n = (int64_t)max_batch * in_ch * in_h * in_w;
+  if (!infer_stream) {
+    cudaStream_t st;
+    cudaEvent_t e0, e1;
+    LBC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    LBC_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    LBC_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    infer_stream = st;
+    infer_ev_in = e0;
+    infer_ev_out = e1;
+    LBC_CUDA(cudaMalloc((void**)&inf_speed, sizeof(float) * max_batch));
+    LBC_CUDA(cudaMalloc((void**)&inf_onehot, sizeof(float) * max_batch * 4));
+    LBC_CUDA(cudaMalloc((void**)&inf_pred, sizeof(float) * max_batch * 10));
+    LBC_CUDA(cudaMalloc((void**)&inf_preds, sizeof(float) * max_batch * 40));
+  }
+  if (image && !inf_img) LBC_CUDA(cudaMalloc((void**)&inf_img, sizeof(float) * img_n));
+  if (image_u8 && !inf_img_u8) LBC_CUDA(cudaMalloc((void**)&inf_img_u8, (size_t)img_n));
+  cudaStream_t is = (cudaStream_t)infer_stream;
+  lbc_stream_t ls = (lbc_stream_t)infer_stream;
+  // join the caller's stream, stage the inputs at fixed addresses
+  LBC_CUDA(cudaEventRecord((cudaEvent_t)infer_ev_in, (cudaStream_t)s));
+  LBC_CUDA(cudaStreamWaitEvent(is, (cudaEvent_t)infer_ev_in, 0));
+  const int64_t n_img = (int64_t)B * in_ch * in_h * in_w;
+  if (image) dev_copy(inf_img, image, sizeof(float) * n_img, ls);
+  if (image_u8) dev_copy(inf_img_u8, image_u8, (size_t)n_img, ls);
+  dev_copy(inf_speed, speed, sizeof(float) * B, ls);
+  dev_copy(inf_onehot, onehot, sizeof(float) * B * 4, ls);
+  if (weights_changed || !packs_current) {
+    repack(ls);
+    packs_current = true;
+  }
+  const int kind_in = image ? 0 : 1;
+  const int variant = (fast::enabled() ? 1 : 0) | (fast::pair_mode() << 1);
+  InferGraph* g = nullptr;
+  for (InferGraph& c : infer_graphs)
+    if (c.B == B && c.kind == kind_in && c.layout == layout && c.variant == variant) g = &c;
+  auto run = [&] {
+    const bool keep = packs_current;
+    skip_pack = true;
+    try {
+      if (image)
+        forward(inf_img, inf_speed, inf_onehot, B, false, inf_pred, inf_preds, ls);
+      else
+        forward_u8(inf_img_u8, layout, inf_speed, inf_onehot, B, false, inf_pred, inf_preds, ls);
+    } catch (...) {
+      skip_pack = false;
+      throw;
+    }
+    skip_pack = false;
+    packs_current = keep;
+  };
+  if (!g || infer_no_graph) {
+    const bool prof = g_prof_on;
+    g_prof_on = false;   // (event brackets cannot be captured)
+    try {
+      run();   // eager: this call's result, and every one-time attribute / occupancy query / lazy allocation of the path
+    } catch (...) {
+      g_prof_on = prof;
+      throw;
+    }
+    if (!infer_no_graph) {
+      // capture the same call sequence; a path that cannot be captured keeps running eagerly (results are the eager run's)
+      cudaGraphExec_t exec = nullptr;
+      bool ok = cudaStreamBeginCapture(is, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        try {
+          run();
+        } catch (...) {
+          ok = false;
+        }
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamEndCapture(is, &graph) != cudaSuccess || !graph) ok = false;
+        if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+        if (graph) cudaGraphDestroy(graph);
+      }
+      if (ok && exec) {
+        InferGraph ng;
+        ng.B = B;
+        ng.kind = kind_in;
+        ng.layout = layout;
+        ng.variant = variant;
+        ng.exec = exec;
+        infer_graphs.push_back(ng);
+      } else {
+        cudaGetLastError();
+        infer_no_graph = true;
+      }
+    }
+    g_prof_on = prof;
+  } else {
+    LBC_CUDA(cudaGraphLaunch((cudaGraphExec_t)g->exec, is));
+    ++infer_replays;
+  }
+  if (out_preds) dev_copy(out_preds, inf_preds, sizeof(float) * B * 40, ls);
+  if (out_pred) dev_copy(out_pred, inf_pred, sizeof(float) * B * 10, ls);
+  LBC_CUDA(cudaEventRecord((cudaEvent_t)infer_ev_out, is));
+  LBC_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)infer_ev_out, 0));
+}
+#else
+void NetBase::infer_release() {}
+void NetBase::infer(const float* image, const uint8_t* image_u8, int layout, const float* speed, const float* onehot, int B,
+                    bool, float* out_pred, float* out_preds, lbc_stream_t s) {
+  LBC_CHECK((image != nullptr) != (image_u8 != nullptr), "lbc_net_infer: exactly one of image / image_u8");
+  if (image)
+    forward(image, speed, onehot, B, false, out_pred, out_preds, s);
+  else
+    forward_u8(image_u8, layout, speed, onehot, B, false, out_pred, out_preds, s);
+}
+#endif
+
 void NetBase::enable_grad_events(bool on) {
 #ifndef LBC_HOST_EMU
   for (GradBucket& b : buckets) {
@@ -458,6 +588,7 @@ class Net : public NetBase {
   }
 
   // ------------------------------------------------------------------ op wrappers (fast-path hooks)
+  void repack(lbc_stream_t s) override { pack_weights(s); }
   void pack_weights(lbc_stream_t s) {
     ProfScope ps("pack", s, 0, 0);
     if (fast::enabled())   // pair walk: coalesced stores, no div/mod per element (271 -> ~170 us per forward at measured B = 256)
@@ -618,7 +749,10 @@ class Net : public NetBase {
     LBC_CHECK(!train || B * head_h * head_w > 1, "train-mode BatchNorm needs more than one value per channel");
     cur_B = B;
     cur_train = train;
-    pack_weights(s);
+    if (!skip_pack) {
+      pack_weights(s);
+      packs_current = false;   // (whoever updates the parameters next does not tell the engine)
+    }
     dev_copy(onehot_saved, onehot, sizeof(float) * B * 4, s);
     dev_copy(speed_saved, speed, sizeof(float) * B, s);
     if (!train && negshift_all && fast::enabled()) ref::negate_into(s, BUF, negshift_all, n_buffers);  // centre on running_mean
@@ -771,6 +905,7 @@ class Net : public NetBase {
     LBC_CHECK(G, "lbc_net_backward: gradient buffer not bound");
     LBC_CHECK(cur_B > 0 && cur_train, "lbc_net_backward: no train-mode forward to differentiate");
     LBC_CHECK(d_pred || d_preds, "lbc_net_backward: no upstream gradient");
+    packs_current = false;
     const int B = cur_B;
     const int HW = head_h * head_w;
     T* gcur = g[0];

@@ -57,7 +57,7 @@ struct BNL {
 
 class NetBase {
  public:
-  virtual ~NetBase() {}
+  virtual ~NetBase() { infer_release(); }
   NetKind kind;
   Precision prec;
   int max_batch = 0;
@@ -77,6 +77,27 @@ class NetBase {
   virtual void forward_u8(const uint8_t* image, int layout, const float* speed, const float* onehot, int B, bool train,
                           float* out_pred, float* out_preds, lbc_stream_t s) = 0;
   virtual void backward(const float* d_pred, const float* d_preds, lbc_stream_t s) = 0;
+  // ---- low-latency inference (ImageAgent.run_step is a B = 1 eval forward, image.py:124-196) ----
+  // An eval forward is ~130 launches of a few microseconds each: at B = 1 the host-side launch cost IS the latency.  infer()
+  // copies the inputs into engine-owned buffers, replays the forward as ONE CUDA graph (captured on first use per batch size /
+  // input kind on an engine-owned stream; the caller's stream is joined with events) and copies the results out.  The
+  // weight operands are packed OUTSIDE the graph, only when the caller says the parameters changed.
+  virtual void repack(lbc_stream_t s) = 0;
+  void infer(const float* image, const uint8_t* image_u8, int layout, const float* speed, const float* onehot, int B,
+             bool weights_changed, float* out_pred, float* out_preds, lbc_stream_t s);
+  bool skip_pack = false;       // set by infer() around forward(): the packs are current
+  bool packs_current = false;   // cleared by every forward() that packs and by backward()
+  bool infer_no_graph = false;  // a capture failed: infer() keeps running the eager call sequence
+  struct InferGraph {
+    int B = 0, kind = 0, layout = 0, variant = 0;
+    void* exec = nullptr;
+  };
+  std::vector<InferGraph> infer_graphs;
+  int infer_replays = 0;        // graph launches so far (tests assert that the graph path really ran)
+  void *infer_stream = nullptr, *infer_ev_in = nullptr, *infer_ev_out = nullptr;
+  float *inf_img = nullptr, *inf_speed = nullptr, *inf_onehot = nullptr, *inf_pred = nullptr, *inf_preds = nullptr;
+  uint8_t* inf_img_u8 = nullptr;
+  void infer_release();
   // debugging / parity taps: copy a named internal tensor out as fp32 NCHW
   virtual int64_t read_tap(const char* name, float* out, int64_t cap, lbc_stream_t s) = 0;
   virtual size_t workspace_bytes() const = 0;

@@ -52,6 +52,7 @@ class Adam:
         if closure is not None:
             raise NotImplementedError("closure is not used by the reference loops")
         st = self._locate()
+        st.param_epoch += 1       # the parameters change below without torch noticing (see common.py: lbc_net_infer)
         flat, gflat = st.flat_params, st.flat_grads
         have = [p.grad is not None for p, _, _, on in st.param_views if on]
         if not any(have):

@@ -507,3 +507,67 @@ def test_full_size_properties_gpu(backend):
     with torch.no_grad():
         p, ps = s(b["rgb"], b["speed"], lbc.one_hot(b["command"].cpu()).to(dev))
     assert p.abs().max() <= 1.0 and ps.abs().max() <= 1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["bf16", "fp32tc", "fp32"])
+def test_inference_graph_gpu(backend, precision, monkeypatch):
+    """small eval batches go through lbc_net_infer (one CUDA-graph replay per call).  Same bits as the
+    eager eval forward; follows parameter changes made by load_state_dict, in-place edits and lbc.Adam; float and uint8
+    frames; batch sizes interleaved."""
+    import learningbycheating_b200 as lbc
+    from learningbycheating_b200 import _lib
+    dev = "cuda"
+    s, _ = build_models(dev, precision)
+    s.eval()
+    b = batch_on(dev, 2)
+    oh = lbc.one_hot(b["command"].cpu()).to(dev)
+    u8 = (b["rgb"] * 255).round().to(torch.uint8)
+    replays = lambda: _lib.lib().lbc_net_infer_replays(s._lbc.handle)
+
+    def eager(x, n):
+        monkeypatch.setenv("LBC_B200_INFER_GRAPH_MAX_B", "0")
+        with torch.no_grad():
+            out = [t.clone() for t in s(x[:n], b["speed"][:n], oh[:n])]
+        monkeypatch.setenv("LBC_B200_INFER_GRAPH_MAX_B", "16")
+        return out
+
+    def graph(x, n):
+        with torch.no_grad():
+            return [t.clone() for t in s(x[:n], b["speed"][:n], oh[:n])]
+
+    ref1 = eager(b["rgb"], 1)
+    r0 = replays()
+    first = graph(b["rgb"], 1)            # eager run + capture
+    again = graph(b["rgb"], 1)            # replay
+    assert replays() == r0 + 1, "the CUDA-graph path did not run"
+    for a, c, d in zip(ref1, first, again):
+        assert torch.equal(a, c) and torch.equal(a, d)
+    # another input through the same graph; B = 2 gets its own graph; uint8 frames ([B,H,W,C]) too
+    flipped = b["rgb"].flip(0)
+    assert all(torch.equal(a, c) for a, c in zip(eager(flipped, 1), graph(flipped, 1)))
+    graph(b["rgb"], 2)
+    assert all(torch.equal(a, c) for a, c in zip(eager(b["rgb"], 2), graph(b["rgb"], 2)))
+    hwc = u8.permute(0, 2, 3, 1).contiguous()
+    graph(hwc, 1)
+    assert all(torch.equal(a, c) for a, c in zip(eager(hwc, 1), graph(hwc, 1)))
+    assert all(torch.equal(a, c) for a, c in zip(ref1, graph(b["rgb"], 1)))
+    # parameter changes: in place, load_state_dict, the package's Adam after a training step
+    with torch.no_grad():
+        s.location_pred[0][1].weight.mul_(1.5)
+    changed = graph(b["rgb"], 1)
+    assert not torch.equal(changed[1], ref1[1]) and all(torch.equal(a, c) for a, c in zip(eager(b["rgb"], 1), changed))
+    sd = {k: v.clone() for k, v in s.state_dict().items()}
+    sd["conv.conv1.weight"] = sd["conv.conv1.weight"] * 0.5
+    s.load_state_dict(sd)
+    assert all(torch.equal(a, c) for a, c in zip(eager(b["rgb"], 1), graph(b["rgb"], 1)))
+    opt = lbc.Adam(s.parameters(), lr=1e-3)
+    s.train()
+    pred, _ = s(b["rgb"], b["speed"], oh)
+    pred.abs().mean().backward()
+    s.eval()
+    before = graph(b["rgb"], 1)
+    opt.step()
+    after = graph(b["rgb"], 1)
+    assert not torch.equal(before[1], after[1]) and all(torch.equal(a, c) for a, c in zip(eager(b["rgb"], 1), after))
+    assert replays() >= r0 + 8
