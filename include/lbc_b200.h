@@ -165,6 +165,11 @@ int lbc_op_bn_bwd(const float* dy, const float* x, const float* gamma, float* dg
                   void* stream);
 int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mode, int precision, int use_mask_bits,
               void* stream);
+/* dst += src * (act > 0), then BatchNorm backward of dst * (act_prev > 0) wrt x (batch statistics of x): the residual
+ * blocks' d(out) chain, resnet.py:41-53 backward (bf16 path: add + reduce pass in one kernel) */
+int lbc_op_resid_bn_bwd(float* dst, const float* src, const float* act, const float* x, const float* act_prev,
+                        const float* gamma, float* dgamma, float* dbeta, float* dx, int64_t M, int C, int precision,
+                        void* stream);
 int lbc_op_maxpool(const float* x, float* y, const float* dy, float* dx, int N, int H, int W, int C, void* stream);
 int lbc_op_bn_relu_maxpool(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                            float* y, const float* dy, float* dx, int N, int H, int W, int C, int precision, void* stream);

@@ -71,6 +71,7 @@ def _declare(lib):
         "lbc_op_bn_train": (i, [vp, vp, vp, vp, i, vp, vp, vp, i64, i, i, vp, vp, vp, vp, vp]),
         "lbc_op_bn_bwd": (i, [vp, vp, vp, vp, vp, vp, i64, i, i, vp, vp, i, i, vp]),
         "lbc_op_ew": (i, [vp, vp, vp, i64, i, i, i, vp]),
+        "lbc_op_resid_bn_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i, i, vp]),
         "lbc_op_maxpool": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
         "lbc_op_bn_relu_maxpool": (i, [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]),
         "lbc_op_stem_tail": (i, [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]),

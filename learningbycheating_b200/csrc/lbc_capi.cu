@@ -571,6 +571,58 @@ int lbc_op_bn_bwd(const float* dy, const float* x, const float* gamma, float* dg
     sync_stream(s);
   });
 }
+// The residual blocks' d(out) chain in one op (resnet.py:41-53 backward): dst += src * (act > 0), then the BatchNorm backward
+// of  dst * (act_prev > 0)  with respect to x (batch statistics of x).  bf16 path: the add and the reduce pass are ONE kernel
+// (bn_bwd_reduce_kernel<resid>), both masks travel as bits, then col_finalize + bn_bwd_apply_kernel.
+int lbc_op_resid_bn_bwd(float* dst, const float* src, const float* act, const float* x, const float* act_prev,
+                        const float* gamma, float* dgamma, float* dbeta, float* dx, int64_t M, int C, int precision,
+                        void* stream) {
+  return guarded([&] {
+    require_device();
+    lbc_stream_t s = S(stream);
+    Tmp t;
+    double* ws = t.get<double>(1 << 20);
+    float *mean = t.get<float>(C), *var = t.get<float>(C), *rstd = t.get<float>(C);
+    const int64_t n = M * C;
+    if (precision == PREC_F32) {
+      ref::add_masked_inplace<float>(s, dst, src, act, n);
+      float* dym = t.get<float>(n);
+      dev_copy(dym, dst, sizeof(float) * n, s);
+      ref::relu_mask_inplace<float>(s, dym, act_prev, n);
+      ref::bn_stats<float>(s, x, M, C, mean, var, ws);
+      ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, nullptr, nullptr);
+      ref::bn_bwd<float>(s, dym, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, ws);
+    } else {
+      bf16 *d = t.get<bf16>(n), *sr = t.get<bf16>(n), *a = t.get<bf16>(n), *ap = t.get<bf16>(n), *xb = t.get<bf16>(n),
+           *dxb = t.get<bf16>(n);
+      float* sums = t.get<float>(2 * C);
+      uint8_t *bits = t.get<uint8_t>(n / 8), *pbits = t.get<uint8_t>(n / 8);
+      ref::cast<float, bf16>(s, dst, d, n);
+      ref::cast<float, bf16>(s, src, sr, n);
+      ref::cast<float, bf16>(s, act, a, n);
+      ref::cast<float, bf16>(s, act_prev, ap, n);
+      ref::cast<float, bf16>(s, x, xb, n);
+      ref::pack_mask_bits<bf16>(s, a, bits, n / 8);
+      ref::pack_mask_bits<bf16>(s, ap, pbits, n / 8);
+      ref::bn_stats<bf16>(s, xb, M, C, mean, var, ws);
+      ref::bn_finalize(s, mean, var, C, M, 1e-5f, 0.1f, rstd, nullptr, nullptr);
+      int rows = 0;
+      if (fast::Fast<bf16>::resid_bn_reduce(d, sr, bits, xb, mean, rstd, pbits, M, C, &rows, s)) {
+        LBC_CHECK(fast::Fast<bf16>::bn_bwd(d, ap, xb, mean, rstd, gamma, dgamma, dbeta, dxb, M, C, sums, s, nullptr, pbits, rows),
+                  "lbc_op_resid_bn_bwd: BatchNorm backward fast path unavailable");
+      } else {
+        ref::add_masked_inplace<bf16>(s, d, sr, a, n);
+        bf16* dm = t.get<bf16>(n);
+        dev_copy(dm, d, sizeof(bf16) * n, s);
+        ref::relu_mask_inplace<bf16>(s, dm, ap, n);
+        ref::bn_bwd<bf16>(s, dm, xb, mean, rstd, gamma, dgamma, dbeta, dxb, M, C, ws);
+      }
+      ref::cast<bf16, float>(s, d, dst, n);
+      ref::cast<bf16, float>(s, dxb, dx, n);
+    }
+    sync_stream(s);
+  });
+}
 // masked adds of the residual backward: mode 0 dst += src; 1 dst += src*(act>0); 2 dst *= (act>0)
 int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mode, int precision, int use_mask_bits,
               void* stream) {

@@ -119,7 +119,9 @@ bool bn_apply_bf16(const bf16* x, const float* scsh, int64_t M, int C, const flo
 // wrote (16x fewer bytes than reading the activation; mask_act is then only a flag)
 bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
                  const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s,
-                 const float* beta_own = nullptr, const uint8_t* mask_bits = nullptr);
+                 const float* beta_own = nullptr, const uint8_t* mask_bits = nullptr, int pre_rows = 0);
+bool resid_bn_reduce_bf16(bf16* dst, const bf16* src, const uint8_t* src_bits, const bf16* x, const float* mean, const float* rstd,
+                          const uint8_t* mask_bits, int64_t M, int C, int* rows, lbc_stream_t s);
 bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s, const uint8_t* mask_bits = nullptr);
 bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           bf16* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, lbc_stream_t s);
@@ -132,7 +134,9 @@ template <class T> struct Fast {
   static bool bn_fwd(const T*, int64_t, int, const float*, const float*, float, float, float*, float*, float*, float*,
                      const T*, bool, bool, T*, float*, float*, lbc_stream_t, int = 0, uint8_t* = nullptr) { return false; }
   static bool bn_bwd(const T*, const T*, const T*, const float*, const float*, const float*, float*, float*, T*, int64_t, int,
-                     float*, lbc_stream_t, const float* = nullptr, const uint8_t* = nullptr) { return false; }
+                     float*, lbc_stream_t, const float* = nullptr, const uint8_t* = nullptr, int = 0) { return false; }
+  static bool resid_bn_reduce(T*, const T*, const uint8_t*, const T*, const float*, const float*, const uint8_t*, int64_t, int,
+                              int*, lbc_stream_t) { return false; }
   static bool ew(T*, const T*, const T*, int64_t, int, lbc_stream_t, const uint8_t* = nullptr) { return false; }
   static bool colsum(const T*, int64_t, int, float*, float*, lbc_stream_t) { return false; }
   static bool pool_fwd(const T*, const float*, const float*, const float*, const float*, T*, uint8_t*, int, int, int, int, int,
@@ -161,9 +165,14 @@ template <> struct Fast<bf16> {
   }
   static bool bn_bwd(const bf16* dy, const bf16* mask, const bf16* x, const float* mean, const float* rstd, const float* gamma,
                      float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s,
-                     const float* beta_own = nullptr, const uint8_t* mask_bits = nullptr) {
+                     const float* beta_own = nullptr, const uint8_t* mask_bits = nullptr, int pre_rows = 0) {
     if (!enabled()) return false;
-    return bn_bwd_bf16(dy, mask, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, sums, s, beta_own, mask_bits);
+    return bn_bwd_bf16(dy, mask, x, mean, rstd, gamma, dgamma, dbeta, dx, M, C, sums, s, beta_own, mask_bits, pre_rows);
+  }
+  static bool resid_bn_reduce(bf16* dst, const bf16* src, const uint8_t* src_bits, const bf16* x, const float* mean,
+                              const float* rstd, const uint8_t* mask_bits, int64_t M, int C, int* rows, lbc_stream_t s) {
+    if (!enabled()) return false;
+    return resid_bn_reduce_bf16(dst, src, src_bits, x, mean, rstd, mask_bits, M, C, rows, s);
   }
   static bool ew(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s, const uint8_t* mask_bits = nullptr) {
     if (!enabled()) return false;

@@ -448,13 +448,19 @@ bool bn_apply_bf16(const bf16* x, const float* scsh, int64_t M, int C, const flo
 // ------------------------------------------------------------------------------------------- BN backward
 // pass 1: sums[0..C) += sum dy_m ; sums[C..2C) += sum dy_m * xhat,  dy_m = dy * (act > 0) when act != null
 // (mbits != null: the mask comes as one byte per (row, 8 channels) written by bn_apply_kernel instead of the activation)
-template <bool OWN>
-__global__ void __launch_bounds__(256, OWN ? 3 : 4) bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ act,
+// RESID (the residual blocks' d(out) chain): dy is produced HERE, dy = dy + (rbits ? rsrc : 0) -- the masked residual add of
+// the block that was just differentiated -- stored back (bf16) and reduced as the upstream gradient of the previous block's
+// bn2 in the same pass: the separate ew_kernel launch and the reduce kernel's read of dy disappear (8.25 instead of 10.25
+// bytes per element for the pair).
+template <bool OWN, bool RESID = false>
+__global__ void __launch_bounds__(256, OWN ? 3 : 4) bn_bwd_reduce_kernel(const uint4* dy, const uint4* __restrict__ act,
                                                             const uint4* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, int64_t M, int tpr, int rpi,
                                                             float* partial, int C, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta_own,
-                                                            const uint8_t* __restrict__ mbits) {
+                                                            const uint8_t* __restrict__ mbits,
+                                                            const uint4* __restrict__ rsrc = nullptr,
+                                                            const uint8_t* __restrict__ rbits = nullptr, uint4* dy_out = nullptr) {
   extern __shared__ float red[];
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
@@ -472,7 +478,19 @@ __global__ void __launch_bounds__(256, OWN ? 3 : 4) bn_bwd_reduce_kernel(const u
 #pragma unroll(OWN ? 4 : 2)
   for (int64_t row = (int64_t)blockIdx.x * rpi + r; row < M; row += stride) {
     const int64_t i0 = row * tpr + cg;
-    const uint4 d0 = ldg_stream(dy + i0), x0 = ldg_stream(x + i0);
+    uint4 d0 = ldg_stream(dy + i0);
+    const uint4 x0 = ldg_stream(x + i0);
+    if (RESID) {
+      const uint4 r0 = ldg_stream(rsrc + i0);
+      const uint32_t rb = __ldg(rbits + i0);
+      float fs[8], fr[8];
+      unpack8(d0, fs);
+      unpack8(r0, fr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fs[j] += ((rb >> j) & 1u) ? fr[j] : 0.f;
+      d0 = pack8(fs);                               // the stored (rounded) sum is what every later consumer reads
+      dy_out[i0] = d0;
+    }
     uint4 a0 = d0;
     uint32_t mb = 0xffu;
     if (!OWN && mbits) mb = __ldg(mbits + i0);
@@ -568,7 +586,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
 
 bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const float* mean, const float* rstd,
                  const float* gamma, float* dgamma, float* dbeta, bf16* dx, int64_t M, int C, float* sums, lbc_stream_t s,
-                 const float* beta_own, const uint8_t* mask_bits) {
+                 const float* beta_own, const uint8_t* mask_bits, int pre_rows) {
   if (C % 8 || C > 2560) return false;
   static const bool recompute = [] {
     const char* e = getenv("LBC_BN_MASK_RECOMPUTE");
@@ -592,10 +610,15 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
     return true;
   }
   if (mask_bits) mask_act = nullptr;   // the bits replace the activation read
-  bn_bwd_reduce_kernel<false><<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
-      (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, gamma, beta_own, mask_bits);
-  LBC_LAUNCHED("bn_bwd_reduce_kernel");
-  col_finalize(part, g.grid, 2 * C, sums, s);
+  if (pre_rows > 0) {
+    // the partial rows are already in the shared scratch: resid_bn_reduce_bf16 reduced while it produced dy
+    col_finalize(part, pre_rows, 2 * C, sums, s);
+  } else {
+    bn_bwd_reduce_kernel<false><<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
+        (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, gamma, beta_own, mask_bits);
+    LBC_LAUNCHED("bn_bwd_reduce_kernel");
+    col_finalize(part, g.grid, 2 * C, sums, s);
+  }
   bn_bwd_apply_kernel<false><<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd,
                                                          gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own, mask_bits);
   LBC_LAUNCHED("bn_bwd_apply_kernel");
@@ -830,12 +853,31 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
   return true;
 }
 
+// dst += src * bits(src_bits)  (the masked residual add) AND the reduce pass of the BatchNorm that consumes dst next:
+// partial rows of [sum g | sum g*xhat], g = dst * bits(mask_bits), left in the shared scratch for bn_bwd_bf16(..., pre_rows)
+bool resid_bn_reduce_bf16(bf16* dst, const bf16* src, const uint8_t* src_bits, const bf16* x, const float* mean, const float* rstd,
+                          const uint8_t* mask_bits, int64_t M, int C, int* rows, lbc_stream_t s) {
+  if (C % 8 || C > 2560 || !src_bits || !mask_bits) return false;
+  RowGeom g = row_geom(M, C, 4);
+  float* part = partial_buffer();
+  if (!part) return false;
+  bn_bwd_reduce_kernel<false, true><<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
+      (const uint4*)dst, nullptr, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, nullptr, nullptr, mask_bits,
+      (const uint4*)src, src_bits, (uint4*)dst);
+  LBC_LAUNCHED("bn_bwd_reduce_kernel<resid>");
+  LBC_CUDA(cudaGetLastError());
+  *rows = g.grid;
+  return true;
+}
+
 #else  // LBC_HOST_EMU
 bool bn_stats_bf16(const bf16*, int64_t, int, float*, lbc_stream_t) { return false; }
 bool bn_apply_bf16(const bf16*, const float*, int64_t, int, const float*, const float*, float, float, float*, float*, float*,
                    float*, const bf16*, bool, bool, bf16*, float*, lbc_stream_t, uint8_t*) { return false; }
 bool bn_bwd_bf16(const bf16*, const bf16*, const bf16*, const float*, const float*, const float*, float*, float*, bf16*,
-                 int64_t, int, float*, lbc_stream_t, const float*, const uint8_t*) { return false; }
+                 int64_t, int, float*, lbc_stream_t, const float*, const uint8_t*, int) { return false; }
+bool resid_bn_reduce_bf16(bf16*, const bf16*, const uint8_t*, const bf16*, const float*, const float*, const uint8_t*, int64_t, int,
+                          int*, lbc_stream_t) { return false; }
 bool ew_bf16(bf16*, const bf16*, const bf16*, int64_t, int, lbc_stream_t, const uint8_t*) { return false; }
 float* stat_partial_buffer() { return nullptr; }
 int64_t stat_partial_capacity() { return 0; }

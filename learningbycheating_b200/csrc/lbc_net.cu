@@ -29,10 +29,14 @@ void nhwc_to_nchw_f32(lbc_stream_t s, const T* x, float* out, int N, int H, int 
 }  // namespace ref
 
 #ifndef LBC_HOST_EMU
-void NetBase::infer_release() {
+void NetBase::infer_drop_graphs() {
   for (InferGraph& g : infer_graphs)
     if (g.exec) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
   infer_graphs.clear();
+  packs_current = false;
+}
+void NetBase::infer_release() {
+  infer_drop_graphs();
   for (void* p : {(void*)inf_img, (void*)inf_speed, (void*)inf_onehot, (void*)inf_pred, (void*)inf_preds, (void*)inf_img_u8})
     if (p) cudaFree(p);
   inf_img = inf_speed = inf_onehot = inf_pred = inf_preds = nullptr;
@@ -147,6 +151,7 @@ void NetBase::infer(const float* image, const uint8_t* image_u8, int layout, con
   LBC_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)infer_ev_out, 0));
 }
 #else
+void NetBase::infer_drop_graphs() {}
 void NetBase::infer_release() {}
 void NetBase::infer(const float* image, const uint8_t* image_u8, int layout, const float* speed, const float* onehot, int B,
                     bool, float* out_pred, float* out_preds, lbc_stream_t s) {
@@ -694,13 +699,16 @@ class Net : public NetBase {
   // Correctness-first path: masks dy in place first; fast path: the mask is fused into both passes, dy untouched.
   // own_relu: mask_act is relu(bn(x)) of this very BatchNorm (no residual): the fast kernels then recompute the mask
   // from x instead of reading the activation (2 of the 7 tensor passes disappear).
+  // pre_rows > 0: the reduce pass already ran inside add_masked_reduce (its partial rows are in the shared scratch)
   void bn_backward(BNL& bn, T* dy, const T* mask_act, const T* x, T* dx, int64_t M, lbc_stream_t s, bool own_relu = false,
-                   const uint8_t* mask_bits = nullptr) {
+                   const uint8_t* mask_bits = nullptr, int pre_rows = 0) {
     // algorithmic bytes: reduce pass reads dy,(mask),x ; apply pass reads dy,(mask),x writes dx (mask as bits: 1/16 pass each)
-    ProfScope ps("bn_bwd", s, 0, (double)M * bn.C * sizeof(T) * (5 + (mask_act && !own_relu ? (mask_bits ? 0.125 : 2) : 0)));
+    const double passes = pre_rows > 0 ? 3 + 0.0625 : 5 + (mask_act && !own_relu ? (mask_bits ? 0.125 : 2) : 0);
+    ProfScope ps("bn_bwd", s, 0, (double)M * bn.C * sizeof(T) * passes);
     if (fast::Fast<T>::bn_bwd(dy, mask_act, x, bn.mean, bn.rstd, P + bn.g_off, G + bn.g_off, G + bn.b_off, dx, M, bn.C,
-                              bn_sums, s, own_relu ? P + bn.b_off : nullptr, mask_bits))
+                              bn_sums, s, own_relu ? P + bn.b_off : nullptr, mask_bits, pre_rows))
       return;
+    LBC_CHECK(pre_rows == 0, "BatchNorm backward fast path unavailable after a fused residual-add + reduce");
     if (mask_act) ref::relu_mask_inplace<T>(s, dy, mask_act, M * bn.C);
     ref::bn_bwd<T>(s, dy, x, bn.mean, bn.rstd, P + bn.g_off, G + bn.g_off, G + bn.b_off, dx, M, bn.C, ws_d);
   }
@@ -713,6 +721,23 @@ class Net : public NetBase {
     ProfScope ps("elementwise", s, 0, (double)n * sizeof(T) * (mask_bits ? 3.0625 : 4));
     if (fast::Fast<T>::ew(dst, g, act, n, 1, s, mask_bits)) return;
     ref::add_masked_inplace<T>(s, dst, g, act, n);
+  }
+  // dst += g * mask (the residual branch of the block just differentiated) fused with the reduce pass of the BatchNorm
+  // that consumes dst next (the previous block's bn2, mask = that block's output bits); returns its partial rows or 0
+  int add_masked_reduce(T* dst, const T* g, const uint8_t* g_bits, BNL& next_bn, const T* next_x, const uint8_t* next_bits,
+                        int64_t M, lbc_stream_t s) {
+    if (!g_bits || !next_bits) return 0;
+    static const bool on = [] {
+      const char* e = getenv("LBC_RESID_FUSE");   // 0: separate ew_kernel + reduce launches (A/B)
+      return e ? atoi(e) != 0 : true;
+    }();
+    if (!on) return 0;
+    int rows = 0;
+    // algorithmic bytes: dst read + written, g read, x read, two bit masks
+    ProfScope ps("elementwise", s, 0, (double)M * next_bn.C * sizeof(T) * 4.125);
+    if (!fast::Fast<T>::resid_bn_reduce(dst, g, g_bits, next_x, next_bn.mean, next_bn.rstd, next_bits, M, next_bn.C, &rows, s))
+      return 0;
+    return rows;
   }
   HeadCtx hc;
   HeadCtx& head_ctx() {   // (parameter / buffer pointers follow the currently bound flat arrays)
@@ -944,13 +969,15 @@ class Net : public NetBase {
     ref::slice_channels<T>(s, gcur, gnext, (int64_t)B * trunk_h * trunk_w, 640, 512);
     std::swap(gcur, gnext);
     // residual blocks in reverse
+    int pending_rows = 0;   // partial rows of the NEXT bn2 backward, when its reduce pass was fused into the residual add
     for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
       Block& b = blocks[bi];
       int64_t M = (int64_t)B * b.Hout * b.Wout;
       int64_t ne = M * b.Cout;
       // gcur = d(out); the block-final ReLU mask (out > 0) is applied inside every consumer of gcur
       const uint8_t* ob = b.obits_ok ? b.obits : nullptr;
-      bn_backward(b.b2, gcur, b.out, b.r2, tA, M, s, false, ob);  // tA = d r2
+      bn_backward(b.b2, gcur, b.out, b.r2, tA, M, s, false, ob, pending_rows);  // tA = d r2
+      pending_rows = 0;
       conv_backward_weight(b.c2, b.a1, tA, B, s);
       conv_backward_data(b.c2, tA, tB, B, false, s);   // tB = d a1 (before the ReLU mask a1 > 0)
       bn_backward(b.b1, tB, b.a1, b.r1, tA, M, s, true);   // tA = d r1 (mask a1 > 0 recomputed from r1)
@@ -973,7 +1000,11 @@ class Net : public NetBase {
         }
       } else {
         conv_backward_data(b.c1, tA, gnext, B, false, s);  // gnext = d xin (main path)
-        add_masked(gnext, gcur, b.out, ne, s, ob);
+        // + the residual branch; when the block before this one has the same shape, its bn2 reduce pass rides along
+        if (bi > 0 && blocks[bi - 1].obits_ok && blocks[bi - 1].Cout == b.Cout && blocks[bi - 1].Hout == b.Hout &&
+            blocks[bi - 1].Wout == b.Wout)
+          pending_rows = add_masked_reduce(gnext, gcur, ob, blocks[bi - 1].b2, blocks[bi - 1].r2, blocks[bi - 1].obits, M, s);
+        if (pending_rows == 0) add_masked(gnext, gcur, b.out, ne, s, ob);
       }
       std::swap(gcur, gnext);
       // a stage is complete when its entry block (the one with the downsample branch) has been differentiated

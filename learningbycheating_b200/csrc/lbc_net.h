@@ -67,10 +67,12 @@ class NetBase {
   int64_t n_params = 0, n_buffers = 0;
   float *P = nullptr, *G = nullptr, *BUF = nullptr;  // bound flat arrays
   void bind(float* p, float* g, float* b) {
+    if (p != P || b != BUF) infer_drop_graphs();   // captured launches carry the old parameter / buffer addresses
     P = p;
     G = g;
     BUF = b;
   }
+  void infer_drop_graphs();
   virtual void forward(const float* image, const float* speed, const float* onehot, int B, bool train,
                        float* out_pred, float* out_preds, lbc_stream_t s) = 0;
   // uint8 frames ([B,C,H,W] or [B,H,W,C]): ToTensor's /255 on the device, then the float path

@@ -227,6 +227,46 @@ def test_masked_add_kernel_gpu(backend):
     _ew_case("cuda", 1, use_bits=True)
 
 
+# ------------------------------------------------------------------ residual add fused with the next BatchNorm's reduce pass
+def _resid_bn_case(dev, M, C, precision):
+    """dst += src * (act > 0); BatchNorm backward of dst * (act_prev > 0) wrt x  (the d(out) chain between two BasicBlocks)"""
+    _lib = _L()
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(31)
+    dst, src, act, act_prev = (_r(torch.randn(M, C, generator=g), precision) for _ in range(4))
+    x = _r(torch.randn(M, C, generator=g) * 1.5 + 0.3, precision)
+    gamma = torch.rand(C, generator=g) + 0.5
+    summed = _r(dst + src * (act > 0).float(), precision)             # the stored (rounded) sum is what the BN consumes
+    xt = x.t().reshape(1, C, M, 1).clone().requires_grad_(True)
+    gp, bp = gamma.clone().requires_grad_(True), torch.zeros(C, requires_grad=True)
+    y = F.batch_norm(xt, None, None, gp, bp, True, 0.1, 1e-5)
+    y.backward((summed * (act_prev > 0).float()).t().reshape(1, C, M, 1))
+    d = lambda t: t.contiguous().to(dev)
+    dd, sd, ad, apd, xd, gd = d(dst.clone()), d(src), d(act), d(act_prev), d(x), d(gamma)
+    dg, db, dx = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty(M, C, device=dev)
+    must = ["bn_bwd_reduce_kernel<resid>", "col_finalize_kernel", "bn_bwd_apply_kernel"] if precision == 1 else []
+    never = tuple(t for t in REF_TAGS if t not in ("k_bn_sum_part", "k_bn_var_part")) if precision == 1 else ()
+    with Traced(dev, must, never):
+        _lib.check(L.lbc_op_resid_bn_bwd(_lib.ptr(dd), _lib.ptr(sd), _lib.ptr(ad), _lib.ptr(xd), _lib.ptr(apd), _lib.ptr(gd),
+                                         _lib.ptr(dg), _lib.ptr(db), _lib.ptr(dx), M, C, precision, None))
+    assert _err(dd.cpu(), summed) < (1e-6 if precision == 0 else 1e-6)      # same rounding on both sides
+    scale = max(1.0, gp.grad.abs().max().item(), bp.grad.abs().max().item())
+    assert (dg.cpu() - gp.grad).abs().max() <= 2e-4 * scale
+    assert (db.cpu() - bp.grad).abs().max() <= 2e-4 * scale
+    assert _err(dx.cpu(), xt.grad.reshape(C, M).t()) < (1.2e-2 if precision == 1 else 1e-4)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_resid_bn_backward_cpu(backend, precision):
+    _resid_bn_case(backend, 900, 64, precision)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,C", [(3 * 40 * 96, 64), (2 * 20 * 48, 128), (9 * 10 * 24, 256), (33 * 5 * 12, 512)])
+def test_resid_bn_backward_kernel_gpu(backend, M, C):
+    _resid_bn_case("cuda", M, C, 1)
+
+
 # ------------------------------------------------------------------ stem tail: BN + ReLU + MaxPool and its backward
 def _pool_case(dev, N, H, W, C, precision):
     _lib = _L()
