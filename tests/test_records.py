@@ -26,7 +26,9 @@ def _episode(n, seed=0):
     return d, pos
 
 
-def test_record_samples_cpu():
+def test_record_samples_cpu(monkeypatch):
+    import sys
+    monkeypatch.setitem(sys.modules, "lmdb", None)      # the oracle's reference importer may have left a mock `lmdb` behind
     d, pos = _episode(40)
     data = records.ImageRecords([d], gap=5, n_step=5)
     assert len(data) == 40 - 25
