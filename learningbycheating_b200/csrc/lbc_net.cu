@@ -230,6 +230,89 @@ class Net : public NetBase {
   float *onehot_saved = nullptr, *speed_saved = nullptr;
   double* headS = nullptr;
   T* g[4];
+  // ---- backward overlap (bf16 throughput mode): the weight gradients leave the dependency chain of backward() -- nothing
+  // but the optimizer reads them -- so they run on a second, low-priority stream while the chain (BatchNorm backward ->
+  // data gradient -> BatchNorm backward ...) runs on a high-priority one.  The HBM-bound BatchNorm / elementwise kernels of
+  // the chain then share the SMs with tensor-bound weight-gradient GEMMs, and weight-gradient CTAs fill the partial last
+  // wave of the persistent data-gradient GEMMs.  d(r2) / d(r1) / d(rd), the gradients a weight-gradient GEMM reads, rotate
+  // through kRing extra buffers so that the chain does not have to wait for the side stream before it moves on; every
+  // buffer carries the event of its last side-stream reader, waited for before the chain overwrites it (wr()).
+  static constexpr int kRing = 4;
+  T* gring[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  bool ovl_capable = false;   // ring buffers + streams exist
+  bool ovl = false;           // the running backward() uses them
+  int ring_next = 0;
+#ifndef LBC_HOST_EMU
+  cudaStream_t side_stream = nullptr, chain_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_join = nullptr, ev_in = nullptr, ev_out = nullptr;
+  cudaEvent_t gdone[4 + kRing] = {};
+#endif
+  bool gpending[4 + kRing] = {};
+  int gindex(const T* p) const {
+    for (int i = 0; i < 4; ++i)
+      if (p == g[i]) return i;
+    for (int i = 0; i < kRing; ++i)
+      if (p == gring[i]) return 4 + i;
+    return -1;
+  }
+  // the chain is about to overwrite gradient buffer p: wait for its last side-stream reader
+  T* wr(T* p, lbc_stream_t s) {
+#ifndef LBC_HOST_EMU
+    if (ovl) {
+      const int i = gindex(p);
+      if (i >= 0 && gpending[i]) {
+        LBC_CUDA(cudaStreamWaitEvent(s, gdone[i], 0));
+        gpending[i] = false;
+      }
+    }
+#else
+    (void)s;
+#endif
+    return p;
+  }
+  // next buffer for a gradient that a side-stream weight gradient will read (serial mode: the caller's fallback)
+  T* ring(T* fallback, lbc_stream_t s) {
+    if (!ovl) return fallback;
+    T* p = gring[ring_next];
+    ring_next = (ring_next + 1) % kRing;
+    return wr(p, s);
+  }
+  // everything enqueued on the chain so far is what the next side-stream weight gradient depends on
+  void mark_ready(lbc_stream_t s) {
+#ifndef LBC_HOST_EMU
+    if (ovl) LBC_CUDA(cudaEventRecord(ev_ready, s));
+#else
+    (void)s;
+#endif
+  }
+  // weight gradient of conv c: on the side stream after the last mark_ready() (overlap mode) or in line on s
+  void wgrad_side(const ConvL& c, const T* x, const T* dy, int B, lbc_stream_t s, bool x_is_grad, const T* gbuf) {
+#ifndef LBC_HOST_EMU
+    if (ovl) {
+      LBC_CUDA(cudaStreamWaitEvent(side_stream, ev_ready, 0));
+      conv_backward_weight(c, x, dy, B, side_stream, x_is_grad);
+      const int i = gindex(gbuf);
+      LBC_CHECK(i >= 0, "wgrad_side: operand is not a gradient buffer");
+      LBC_CUDA(cudaEventRecord(gdone[i], side_stream));
+      gpending[i] = true;
+      return;
+    }
+#else
+    (void)gbuf;
+#endif
+    conv_backward_weight(c, x, dy, B, s, x_is_grad);
+  }
+  // all side-stream work enqueued so far completes before anything enqueued on s from here on
+  void join_side(lbc_stream_t s) {
+#ifndef LBC_HOST_EMU
+    if (!ovl) return;
+    LBC_CUDA(cudaEventRecord(ev_join, side_stream));
+    LBC_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
+    for (bool& b : gpending) b = false;
+#else
+    (void)s;
+#endif
+  }
   float* ws_f = nullptr;
   int64_t ws_f_n = 0;
   double* ws_d = nullptr;
@@ -263,11 +346,26 @@ class Net : public NetBase {
 #ifndef LBC_HOST_EMU
     for (GradBucket& b : buckets)
       if (b.event) cudaEventDestroy((cudaEvent_t)b.event);
+    if (side_stream) {
+      cudaStreamSynchronize(side_stream);
+      cudaStreamDestroy(side_stream);
+    }
+    if (chain_stream) {
+      cudaStreamSynchronize(chain_stream);
+      cudaStreamDestroy(chain_stream);
+    }
+    for (cudaEvent_t e : {ev_ready, ev_join, ev_in, ev_out})
+      if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : gdone)
+      if (e) cudaEventDestroy(e);
 #endif
   }
   void mark_bucket(int k, lbc_stream_t s) {   // bucket k's gradients are all enqueued on s
 #ifndef LBC_HOST_EMU
-    if (grad_events && buckets[k].event) LBC_CUDA(cudaEventRecord((cudaEvent_t)buckets[k].event, s));
+    if (grad_events && buckets[k].event) {
+      join_side(s);   // (overlap mode) the bucket's weight gradients run on the side stream
+      LBC_CUDA(cudaEventRecord((cudaEvent_t)buckets[k].event, s));
+    }
 #else
     (void)k;
     (void)s;
@@ -485,6 +583,19 @@ class Net : public NetBase {
     // ---- scratch
     int64_t gmax = B * stem_oh * stem_ow * 64;
     for (int i = 0; i < 4; ++i) g[i] = alloc<T>(gmax);
+#ifndef LBC_HOST_EMU
+    if (std::is_same<T, bf16>::value && !tc) {
+      // ring buffers hold block-level gradients only (largest: layer 1 = the pooled stem output's shape)
+      for (int i = 0; i < kRing; ++i) gring[i] = alloc<T>(B * pool_h * pool_w * 64);
+      int lo = 0, hi = 0;
+      LBC_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority (0), hi = greatest (negative)
+      LBC_CUDA(cudaStreamCreateWithPriority(&side_stream, cudaStreamNonBlocking, lo));
+      LBC_CUDA(cudaStreamCreateWithPriority(&chain_stream, cudaStreamNonBlocking, hi));
+      for (cudaEvent_t* e : {&ev_ready, &ev_join, &ev_in, &ev_out}) LBC_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+      for (cudaEvent_t& e : gdone) LBC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ovl_capable = true;
+    }
+#endif
     ws_f_n = 4 << 20;
     ws_f = alloc<float>(ws_f_n);
     int64_t wd = (1 << 20);
@@ -926,13 +1037,32 @@ class Net : public NetBase {
   }
 
   // ------------------------------------------------------------------ backward
-  void backward(const float* d_pred, const float* d_preds, lbc_stream_t s) override {
+  void backward(const float* d_pred, const float* d_preds, lbc_stream_t s_in) override {
     LBC_CHECK(G, "lbc_net_backward: gradient buffer not bound");
     LBC_CHECK(cur_B > 0 && cur_train, "lbc_net_backward: no train-mode forward to differentiate");
     LBC_CHECK(d_pred || d_preds, "lbc_net_backward: no upstream gradient");
     packs_current = false;
     const int B = cur_B;
     const int HW = head_h * head_w;
+    lbc_stream_t s = s_in;
+    // overlap mode (see the members above): LBC_WGRAD_OVERLAP=0 keeps every kernel on the caller's stream; the per-category
+    // profiler brackets launches of ONE stream with events, so it also runs the serial schedule
+    static const int ovl_mode = [] {
+      const char* e = getenv("LBC_WGRAD_OVERLAP");   // 0 (default until measured): serial, 1: side stream, chain on the caller's stream, 2: + high-priority chain
+      return e ? atoi(e) : 0;
+    }();
+    ovl = ovl_capable && ovl_mode > 0 && !g_prof_on;
+    ring_next = 0;
+#ifndef LBC_HOST_EMU
+    if (ovl) {
+      for (bool& b : gpending) b = false;
+      if (ovl_mode >= 2) {
+        LBC_CUDA(cudaEventRecord(ev_in, s_in));
+        LBC_CUDA(cudaStreamWaitEvent(chain_stream, ev_in, 0));
+        s = chain_stream;
+      }
+    }
+#endif
     T* gcur = g[0];
     T* tA = g[1];
     T* tB = g[2];
@@ -959,14 +1089,15 @@ class Net : public NetBase {
       if (!(i == 2 && head_mask_fused)) relu_mask(gcur, dec_out[i], Mout * c.Ci, s);
       if (!fast::Fast<T>::colsum(gcur, Mout, c.Ci, G + c.b_off, bn_sums, s))
         ref::colsum<T>(s, gcur, Mout, c.Ci, G + c.b_off, ws_d);
-      conv_backward_weight(c, gcur, dec_bn[i], B, s, true);  // conv-role x = d(out), dy = deconv input
-      conv_forward(c, gcur, tA, B, s, nullptr, nullptr, true);
-      bn_backward(dbn[i], tA, nullptr, dec_in[i], gnext, Min, s);
+      mark_ready(s);
+      conv_forward(c, gcur, wr(tA, s), B, s, nullptr, nullptr, true);
+      wgrad_side(c, gcur, dec_bn[i], B, s, true, gcur);  // conv-role x = d(out), dy = deconv input
+      bn_backward(dbn[i], tA, nullptr, dec_in[i], wr(gnext, s), Min, s);
       std::swap(gcur, gnext);
     }
     mark_bucket(0, s);
     // drop the 128 speed channels (no gradient path to a parameter through them)
-    ref::slice_channels<T>(s, gcur, gnext, (int64_t)B * trunk_h * trunk_w, 640, 512);
+    ref::slice_channels<T>(s, gcur, wr(gnext, s), (int64_t)B * trunk_h * trunk_w, 640, 512);
     std::swap(gcur, gnext);
     // residual blocks in reverse
     int pending_rows = 0;   // partial rows of the NEXT bn2 backward, when its reduce pass was fused into the residual add
@@ -976,30 +1107,37 @@ class Net : public NetBase {
       int64_t ne = M * b.Cout;
       // gcur = d(out); the block-final ReLU mask (out > 0) is applied inside every consumer of gcur
       const uint8_t* ob = b.obits_ok ? b.obits : nullptr;
-      bn_backward(b.b2, gcur, b.out, b.r2, tA, M, s, false, ob, pending_rows);  // tA = d r2
+      T* d_r2 = ring(tA, s);
+      bn_backward(b.b2, gcur, b.out, b.r2, d_r2, M, s, false, ob, pending_rows);
       pending_rows = 0;
-      conv_backward_weight(b.c2, b.a1, tA, B, s);
-      conv_backward_data(b.c2, tA, tB, B, false, s);   // tB = d a1 (before the ReLU mask a1 > 0)
-      bn_backward(b.b1, tB, b.a1, b.r1, tA, M, s, true);   // tA = d r1 (mask a1 > 0 recomputed from r1)
-      conv_backward_weight(b.c1, b.xin, tA, B, s);
+      mark_ready(s);
+      conv_backward_data(b.c2, d_r2, wr(tB, s), B, false, s);   // tB = d a1 (before the ReLU mask a1 > 0)
+      wgrad_side(b.c2, b.a1, d_r2, B, s, false, d_r2);
+      T* d_r1 = ring(tA, s);
+      bn_backward(b.b1, tB, b.a1, b.r1, d_r1, M, s, true);   // mask a1 > 0 recomputed from r1
+      mark_ready(s);
       if (b.ds) {
-        bn_backward(b.bd, gcur, b.out, b.rd, tB, M, s, false, ob);  // tB = d rd (d a1 is dead by now)
-        conv_backward_weight(b.cd, b.xin, tB, B, s);
+        T* d_rd = ring(tB, s);   // (serial mode: d a1 is dead by now)
+        bn_backward(b.bd, gcur, b.out, b.rd, d_rd, M, s, false, ob);
+        wgrad_side(b.c1, b.xin, d_r1, B, s, false, d_r1);
+        mark_ready(s);
         bool fused = false;
         {
           ProfScope ps("conv_dgrad", s, conv_flops(b.c1, B) + conv_flops(b.cd, B), 0);
           if (tc)
-            fused = fast::conv_dgrad_tc(b.c1, (const float*)tA, (const float*)tB, (float*)gnext, B, nullptr, false, fast::TC_BF16,
+            fused = fast::conv_dgrad_tc(b.c1, (const float*)d_r1, (const float*)d_rd, (float*)gnext, B, nullptr, false, fast::TC_BF16,
                                         tcw, s);
           else
-            fused = fast::conv_dgrad_ds<T>(b.c1, tA, tB, gnext, B, s);   // gnext = dgrad(conv1) + dgrad(downsample)
+            fused = fast::conv_dgrad_ds<T>(b.c1, d_r1, d_rd, wr(gnext, s), B, s);   // gnext = dgrad(conv1) + dgrad(downsample)
         }
         if (!fused) {
-          conv_backward_data(b.c1, tA, gnext, B, false, s);
-          conv_backward_data(b.cd, tB, gnext, B, true, s);
+          conv_backward_data(b.c1, d_r1, wr(gnext, s), B, false, s);
+          conv_backward_data(b.cd, d_rd, gnext, B, true, s);
         }
+        wgrad_side(b.cd, b.xin, d_rd, B, s, false, d_rd);
       } else {
-        conv_backward_data(b.c1, tA, gnext, B, false, s);  // gnext = d xin (main path)
+        conv_backward_data(b.c1, d_r1, wr(gnext, s), B, false, s);  // gnext = d xin (main path)
+        wgrad_side(b.c1, b.xin, d_r1, B, s, false, d_r1);
         // + the residual branch; when the block before this one has the same shape, its bn2 reduce pass rides along
         if (bi > 0 && blocks[bi - 1].obits_ok && blocks[bi - 1].Cout == b.Cout && blocks[bi - 1].Hout == b.Hout &&
             blocks[bi - 1].Wout == b.Wout)
@@ -1017,15 +1155,15 @@ class Net : public NetBase {
     if (stem_pool_fused) {
       ProfScope ps("pool", s, 0, (double)Ms * 64 * sizeof(T) * 2.5);
       bool ok = fast::Fast<T>::pool_bwd(gcur, pool_idx, r_stem, stem_bn.mean, stem_bn.rstd, P + stem_bn.g_off,
-                                        P + stem_bn.b_off, tA, B, stem_oh, stem_ow, 64, pool_h, pool_w, s);
+                                        P + stem_bn.b_off, wr(tA, s), B, stem_oh, stem_ow, 64, pool_h, pool_w, s);
       LBC_CHECK(ok, "stem MaxPool/ReLU backward fast path failed");
-      bn_backward(stem_bn, tA, nullptr, r_stem, tB, Ms, s);
+      bn_backward(stem_bn, tA, nullptr, r_stem, wr(tB, s), Ms, s);
     } else {
       {
         ProfScope ps("pool", s, 0, (double)Ms * 64 * sizeof(T) * 1.25);
-        ref::maxpool_bwd<T>(s, gcur, pool_idx, tA, B, stem_oh, stem_ow, 64, pool_h, pool_w);
+        ref::maxpool_bwd<T>(s, gcur, pool_idx, wr(tA, s), B, stem_oh, stem_ow, 64, pool_h, pool_w);
       }
-      bn_backward(stem_bn, tA, a_stem, r_stem, tB, Ms, s);
+      bn_backward(stem_bn, tA, a_stem, r_stem, wr(tB, s), Ms, s);
     }
     bool stem_wgrad_done = false;
     if (stem_direct_used) {
@@ -1051,7 +1189,16 @@ class Net : public NetBase {
       LBC_CHECK(!stem_fast_used, "stem weight gradient: fast path failed after a fast forward");
       conv_backward_weight(stem, x0, tB, B, s);
     }
+    // (the stem's weight gradient is the last kernel of the chain: nothing left to overlap it with)
+    join_side(s);
     mark_bucket(4, s);
+#ifndef LBC_HOST_EMU
+    if (s != s_in) {
+      LBC_CUDA(cudaEventRecord(ev_out, s));
+      LBC_CUDA(cudaStreamWaitEvent(s_in, ev_out, 0));
+    }
+#endif
+    ovl = false;
   }
 
   // ------------------------------------------------------------------ taps
