@@ -39,6 +39,13 @@ const char* lbc_build_info(void);
  * 16 / 32 = row-of-taps weight gradient on / off, 64 / 128 = its CTA-pair variant on / off,
  * 256 / 512 = space-to-depth layout of the RGB stem operand on / off. */
 int lbc_set_fast_kernels(int enabled);
+/* launch schedule of the bf16 throughput mode (a negative argument keeps the current value; the environment variables
+ * LBC_WGRAD_OVERLAP / LBC_PDL set the initial ones).  wgrad_overlap: 0 = every kernel of backward on the caller's stream,
+ * 1 = weight gradients on an engine-owned low-priority stream, 2 = and the dependency chain of backward on an engine-owned
+ * high-priority stream (joined with the caller's stream by events on entry and exit).  pdl: 1 = every kernel is launched
+ * with programmatic stream serialization (its prologue overlaps the tail of its predecessor).  Results do not depend on
+ * either switch. */
+int lbc_set_schedule(int wgrad_overlap, int pdl);
 /* layout code of the padded stem operand lbc_op_stem's x4_out shows (bf16 path): 4 = [N][H+6][W+8][4], 8 = [N][H+6][W+8][8],
  * 16 = the 4-channel image with every 2x2 pixel block contiguous, [N][(H+6)/2][(W+8)/2][2][2][4]; 0 = column tensor */
 int lbc_stem_layout(int C, int W, int normalize);

@@ -29,6 +29,7 @@ def _declare(lib):
         "lbc_device_kind": (i, []),
         "lbc_build_info": (ctypes.c_char_p, []),
         "lbc_set_fast_kernels": (i, [i]),
+        "lbc_set_schedule": (i, [i, i]),
         "lbc_stem_layout": (i, [i, i, i]),
         "lbc_kernel_launch_count": (ctypes.c_longlong, []),
         "lbc_prof_enable": (i, [i]),
@@ -137,6 +138,11 @@ def ptr(t):
     elif not t.is_cuda:
         raise LbcError("liblbc_b200 takes CUDA tensors only (got a %s tensor); no CPU path exists" % t.device)
     return ctypes.c_void_p(t.data_ptr())
+
+
+def set_schedule(wgrad_overlap=-1, pdl=-1):
+    """Launch schedule of the bf16 mode (include/lbc_b200.h: lbc_set_schedule); negative = keep."""
+    check(lib().lbc_set_schedule(int(wgrad_overlap), int(pdl)))
 
 
 def trace(on):

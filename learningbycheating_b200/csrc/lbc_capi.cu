@@ -133,6 +133,15 @@ int lbc_set_fast_kernels(int enabled) {
   fast::set_pair_mode(m);
   return 0;
 }
+int lbc_set_schedule(int wgrad_overlap, int pdl) {
+  if (wgrad_overlap >= 0) g_wgrad_overlap = wgrad_overlap > 2 ? 2 : wgrad_overlap;
+#ifndef LBC_HOST_EMU
+  if (pdl >= 0) g_pdl = pdl ? 1 : 0;
+#else
+  (void)pdl;
+#endif
+  return 0;
+}
 int lbc_stem_layout(int C, int W, int normalize) { return fast::stem_ch(C, W, normalize != 0); }
 
 long long lbc_kernel_launch_count(void) { return g_launches; }

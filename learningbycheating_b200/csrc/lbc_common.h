@@ -195,6 +195,58 @@ struct ProfScope {
   }
 };
 
+// ------------------------------------------------------------------ launches (programmatic dependent launch)
+// Every kernel of the library starts with pdl_wait(); pdl_trigger(); (after smem-only setup, before its first global access)
+// and is launched through LBC_LAUNCH.  With g_pdl on (LBC_PDL, lbc_set_pdl) the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization: the grid may be scheduled while its predecessor in the stream still
+// runs (its CTAs take SMs as the predecessor's retire and sit in griddepcontrol.wait until the predecessor has completed
+// and flushed), so the launch latency and the prologue (barrier init, TMEM allocation) of ~450 dependent launches per step
+// leave the critical path.  The trigger comes right after the wait, so at most two consecutive grids overlap.  Without the
+// attribute griddepcontrol.wait returns at once.
+extern int g_wgrad_overlap;   // schedule of backward() in the bf16 mode (lbc_net.cu), lbc_set_schedule
+#ifndef LBC_HOST_EMU
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+struct LaunchCfg {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  LaunchCfg(dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x = 1) {
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    int n = 0;
+    if (cluster_x > 1) {
+      attr[n].id = cudaLaunchAttributeClusterDimension;
+      attr[n].val.clusterDim.x = (unsigned)cluster_x;
+      attr[n].val.clusterDim.y = 1;
+      attr[n].val.clusterDim.z = 1;
+      ++n;
+    }
+    if (g_pdl) {
+      attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = (unsigned)n;
+  }
+};
+// kern: a kernel function pointer (name a template instantiation through `auto k = kernel<...>;` first)
+#define LBC_LAUNCH(kern, grid, block, smem, stream, ...)                                  \
+  do {                                                                                    \
+    ::lbc::LaunchCfg lc_(grid, block, smem, stream);                                      \
+    LBC_CUDA(cudaLaunchKernelEx(&lc_.cfg, kern, __VA_ARGS__));                            \
+  } while (0)
+#define LBC_LAUNCH_CLUSTER(kern, cluster_x, grid, block, smem, stream, ...)               \
+  do {                                                                                    \
+    ::lbc::LaunchCfg lc_(grid, block, smem, stream, cluster_x);                           \
+    LBC_CUDA(cudaLaunchKernelEx(&lc_.cfg, kern, __VA_ARGS__));                            \
+  } while (0)
+#endif
+
 // ------------------------------------------------------------------ par_for
 // The correctness-first kernels are "independent thread" kernels: one logical thread per
 // output element, no shared memory, no atomics -> bitwise deterministic, and the same body
@@ -209,6 +261,8 @@ inline void par_for(lbc_stream_t, int64_t n, F f) {
 #else
 template <class Tag, class F>
 __global__ void __launch_bounds__(256) par_for_kernel(int64_t n, F f) {
+  pdl_wait();
+  pdl_trigger();
   // grid-stride walk; with the default (uncapped) grid the stride covers the whole range: exactly one iteration per thread
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 #pragma unroll 1   // no trip-count arithmetic in front of the (normally single) iteration
@@ -220,9 +274,9 @@ inline void par_for(lbc_stream_t s, int64_t n, F f) {
   const int bs = 256;
   int64_t nb = (n + bs - 1) / bs;
   LBC_CHECK(nb < (1ll << 31), "par_for grid too large");
-  par_for_kernel<Tag, F><<<(unsigned)nb, bs, 0, s>>>(n, f);
+  auto kern = par_for_kernel<Tag, F>;
+  LBC_LAUNCH(kern, dim3((unsigned)nb), dim3(bs), 0, s, n, f);
   LBC_LAUNCHED(tag_name<Tag>());
-  LBC_CUDA(cudaGetLastError());
 }
 #endif
 

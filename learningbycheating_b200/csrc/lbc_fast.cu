@@ -18,6 +18,16 @@ std::string trace_dump() {
   return out;
 }
 bool g_prof_on = false;
+int g_wgrad_overlap = [] {
+  const char* e = getenv("LBC_WGRAD_OVERLAP");   // lbc_net.cu backward(): 0 serial, 1 side stream, 2 + high-priority chain; 0 until measured
+  return e ? atoi(e) : 0;
+}();
+#ifndef LBC_HOST_EMU
+int g_pdl = [] {
+  const char* e = getenv("LBC_PDL");   // programmatic dependent launch of every kernel (lbc_common.h); 0 until measured
+  return e ? atoi(e) : 0;
+}();
+#endif
 std::vector<ProfEntry> g_prof;
 namespace fast {
 
@@ -43,6 +53,8 @@ struct k_stem_unpack;
 // staged in shared memory and written back as one contiguous 64*Kp*2-byte run with 16-byte stores.
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, uint4* __restrict__ col, int C, int H,
                                                           int W, int OH, int OW, int Kp, int normalize, int SEG) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ uint16_t tile[];  // [SEG][Kp + 2]: odd word stride -> lanes (positions) hit distinct banks
   const int KS = Kp + 2;
   const int segs = OW / SEG;
@@ -104,7 +116,7 @@ bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, i
       configured = true;
     }
     if (smem <= 64 * 514 * 2) {
-      stem_im2col_kernel<<<B * OH * (OW / SEG), 256, smem, s>>>(img, (uint4*)col, C, H, W, OH, OW, Kp, normalize ? 1 : 0, SEG);
+      { auto k_ = stem_im2col_kernel; LBC_LAUNCH(k_, dim3(B * OH * (OW / SEG)), dim3(256), smem, s, img, (uint4*)col, C, H, W, OH, OW, Kp, normalize ? 1 : 0, SEG); }
       LBC_LAUNCHED("stem_im2col_kernel");
       LBC_CUDA(cudaGetLastError());
       return true;
@@ -160,6 +172,8 @@ bool stem_im2col_bf16(const float* img, bf16* col, int B, int C, int H, int W, i
 template <int KIND, int ROWS>
 __global__ void __launch_bounds__(256) stem_pad4_kernel(const void* __restrict__ img, uint4* __restrict__ x4, int B, int C, int H,
                                                         int W, int normalize) {
+  pdl_wait();
+  pdl_trigger();
   const int HP = H + 6, WG = (W + 8) / 4;
   const int64_t n = (int64_t)B * (HP / ROWS) * WG;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -226,9 +240,9 @@ static bool launch_stem_pad4(const void* img, bf16* x4, int B, int C, int H, int
   int64_t blocks = (n + 255) / 256, cap = (int64_t)sms * 16;
   if (blocks > cap) blocks = cap;
   if (s2d)
-    stem_pad4_kernel<KIND, 2><<<(unsigned)blocks, 256, 0, s>>>(img, (uint4*)x4, B, C, H, W, normalize ? 1 : 0);
+    { auto k_ = stem_pad4_kernel<KIND, 2>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, img, (uint4*)x4, B, C, H, W, normalize ? 1 : 0); }
   else
-    stem_pad4_kernel<KIND, 1><<<(unsigned)blocks, 256, 0, s>>>(img, (uint4*)x4, B, C, H, W, normalize ? 1 : 0);
+    { auto k_ = stem_pad4_kernel<KIND, 1>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, img, (uint4*)x4, B, C, H, W, normalize ? 1 : 0); }
   LBC_LAUNCHED(KIND == 0 ? "stem_pad4_kernel<f32>" : "stem_pad4_kernel<u8>");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -237,6 +251,8 @@ static bool launch_stem_pad4(const void* img, bf16* x4, int B, int C, int H, int
 template <bool U8>
 __global__ void __launch_bounds__(256) stem_pad8_kernel(const void* __restrict__ img, int layout, uint4* __restrict__ x8, int B,
                                                         int C, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
   const int HP = H + 6, WP = W + 8;
   const int64_t n = (int64_t)B * HP * WP;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -270,7 +286,7 @@ static bool launch_stem_pad8(const void* img, int layout, bf16* x8, int B, int C
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t blocks = (n + 255) / 256, cap = (int64_t)sms * 16;
   if (blocks > cap) blocks = cap;
-  stem_pad8_kernel<U8><<<(unsigned)blocks, 256, 0, s>>>(img, layout, (uint4*)x8, B, C, H, W);
+  { auto k_ = stem_pad8_kernel<U8>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, img, layout, (uint4*)x8, B, C, H, W); }
   LBC_LAUNCHED(U8 ? "stem_pad8_kernel<u8>" : "stem_pad8_kernel<f32>");
   LBC_CUDA(cudaGetLastError());
   return true;

@@ -328,6 +328,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched shared / tensor memory only
+  pdl_trigger();
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   const int nterm = p.split ? 3 : 1;
@@ -740,6 +742,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched shared / tensor memory only
+  pdl_trigger();
   const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
 
   if (warp == 0) {
@@ -963,6 +967,8 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap mX0, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched shared / tensor memory only
+  pdl_trigger();
   const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
 
   if (warp == 0) {
@@ -1142,6 +1148,8 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched shared / tensor memory only
+  pdl_trigger();
   constexpr int MT = (NROWS + RPT - 1) / RPT;   // M tiles covering the window rows (7 rows: row 7 does not exist)
   const int mt = blockIdx.x % MT;          // kernel rows RPT*mt .. RPT*mt+RPT-1
   const int split = blockIdx.x / MT;
@@ -1276,7 +1284,7 @@ static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUten
   }
   int tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_kernel<BN, STAGES, false, OUT_F32><<<grid, 192, SP::TOTAL, s>>>(mA[0], mA[1], mA[2], mA[3], mB, mO, p);
+  { auto k_ = conv_gemm_kernel<BN, STAGES, false, OUT_F32>; LBC_LAUNCH(k_, dim3(grid), dim3(192), SP::TOTAL, s, mA[0], mA[1], mA[2], mA[3], mB, mO, p); }
   if (OUT_F32)
     LBC_LAUNCHED((BN == 64 ? "conv_gemm_kernel<64,f32>" : BN == 128 ? "conv_gemm_kernel<128,f32>" : "conv_gemm_kernel<256,f32>"));
   else
@@ -1318,8 +1326,8 @@ static int launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, co
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   const int pair_tiles = ((tiles_m + 1) / 2) * p.n_tiles_n;
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
-  cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
-  LBC_CUDA(cudaLaunchKernelEx(&cfg, kern, mA[0], mA[1], mA[2], mA[3], mBhalf, mO, p));
+  LBC_LAUNCH_CLUSTER(kern, 2, dim3((unsigned)(2 * clusters)), dim3(192), SP::TOTAL, (cudaStream_t)s, mA[0], mA[1], mA[2], mA[3], mBhalf,
+                     mO, p);
   if (OUT_F32)
     LBC_LAUNCHED((BN == 128 ? "conv_gemm_kernel<128,pair,f32>" : "conv_gemm_kernel<256,pair,f32>"));
   else
@@ -1446,7 +1454,7 @@ static bool try_conv3x3_c64(const bf16* in, const void* wpack, bf16* out, int B,
   }
   int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  conv3x3_c64_kernel<5><<<grid, 192, SP::TOTAL, s>>>(mA, mB, mO, p);
+  { auto k_ = conv3x3_c64_kernel<5>; LBC_LAUNCH(k_, dim3(grid), dim3(192), SP::TOTAL, s, mA, mB, mO, p); }
   LBC_LAUNCHED("conv3x3_c64_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -1503,7 +1511,7 @@ static int launch_stem_conv(const CUtensorMap& mX0, const CUtensorMap& mX1, cons
   }
   int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int grid = tiles < PER_SM * sm_count() ? tiles : PER_SM * sm_count();
-  stem_conv_kernel<STAGES, CH><<<grid, 192, SP::TOTAL, s>>>(mX0, mX1, mB, mO, p);
+  { auto k_ = stem_conv_kernel<STAGES, CH>; LBC_LAUNCH(k_, dim3(grid), dim3(192), SP::TOTAL, s, mX0, mX1, mB, mO, p); }
   LBC_LAUNCHED(CH == 4 ? "stem_conv_kernel" : CH == 8 ? "stem_conv_kernel<8ch>" : "stem_conv_kernel<s2d>");
   LBC_CUDA(cudaGetLastError());
   return grid;
@@ -1558,7 +1566,7 @@ static void launch_stem_wgrad(const CUtensorMap& mDY, const CUtensorMap& mX0, co
     LBC_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<STAGES, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  stem_wgrad_kernel<STAGES, CH><<<MT * p.splits, 192, smem, s>>>(mDY, mX0, mX1, p);
+  { auto k_ = stem_wgrad_kernel<STAGES, CH>; LBC_LAUNCH(k_, dim3(MT * p.splits), dim3(192), smem, s, mDY, mX0, mX1, p); }
   LBC_LAUNCHED(CH == 4 ? "stem_wgrad_kernel" : CH == 8 ? "stem_wgrad_kernel<8ch>" : "stem_wgrad_kernel<s2d>");
   LBC_CUDA(cudaGetLastError());
 }
@@ -1849,6 +1857,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched shared / tensor memory only
+  pdl_trigger();
 
   // decode this CTA's work: (split, co_tile, tap, ci_tile)   [swap mode: (split, combo pair)]
   int id = blockIdx.x;
@@ -2055,6 +2065,8 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
     __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched shared / tensor memory only
+  pdl_trigger();
 
   // this CTA's work: (split, co tile [pair: co-tile pair + rank], kernel row, ci_tile)
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
@@ -2200,6 +2212,8 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
 // through a shared-memory transpose so that the reference layout is written as one contiguous 2304-byte run.
 __global__ void __launch_bounds__(160) wgrad3_reduce_kernel(const float4* __restrict__ part, float* __restrict__ dst, int Co,
                                                             int Ci, int splits) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __align__(16) float tile[64 * 9];
   const int cblocks = Ci / 64;
   const int co = blockIdx.x / cblocks, ci0 = (blockIdx.x % cblocks) * 64;
@@ -2242,6 +2256,8 @@ __global__ void __launch_bounds__(160) wgrad3_reduce_kernel(const float4* __rest
 
 // packed fp32 [Co][taps][Ci] -> reference layout [Co][Ci][K][K]
 __global__ void wgrad_unpack_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int Ci, int KK) {
+  pdl_wait();
+  pdl_trigger();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t n = (int64_t)Co * Ci * KK;
   if (i >= n) return;
@@ -2261,7 +2277,7 @@ static void launch_wgrad(const CUtensorMap& mDY, const CUtensorMap* mX, const Wg
     configured = true;
   }
   int grid = p.swap ? p.splits * ((p.num_combos + 1) / 2) : p.splits * p.co_tiles * p.num_taps * p.ci_tiles;
-  wgrad_gemm_kernel<BNW, STAGES><<<grid, 192, SP::TOTAL, s>>>(mDY, mX[0], mX[1], mX[2], mX[3], p);
+  { auto k_ = wgrad_gemm_kernel<BNW, STAGES>; LBC_LAUNCH(k_, dim3(grid), dim3(192), SP::TOTAL, s, mDY, mX[0], mX[1], mX[2], mX[3], p); }
   LBC_LAUNCHED((BNW == 64 ? "wgrad_gemm_kernel<64>" : "wgrad_gemm_kernel<128>"));
   LBC_CUDA(cudaGetLastError());
 }
@@ -2299,22 +2315,9 @@ static void launch_wgrad3(const CUtensorMap& mDY, const CUtensorMap* mX, const W
     configured = true;
   }
   if (!PAIR) {
-    kern<<<grid, 192, SP::TOTAL, s>>>(mDY, mX[0], mX[1], mX[2], mX[3], p);
+    { auto k_ = kern; LBC_LAUNCH(k_, dim3(grid), dim3(192), SP::TOTAL, s, mDY, mX[0], mX[1], mX[2], mX[3], p); }
   } else {
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    cfg.blockDim = dim3(192, 1, 1);
-    cfg.dynamicSmemBytes = SP::TOTAL;
-    cfg.stream = (cudaStream_t)s;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    LBC_CUDA(cudaLaunchKernelEx(&cfg, kern, mDY, mX[0], mX[1], mX[2], mX[3], p));
+    LBC_LAUNCH_CLUSTER(kern, 2, dim3((unsigned)grid), dim3(192), SP::TOTAL, (cudaStream_t)s, mDY, mX[0], mX[1], mX[2], mX[3], p);
   }
   LBC_LAUNCHED((PAIR ? "wgrad3_gemm_kernel<pair>" : "wgrad3_gemm_kernel"));
 }
@@ -2424,7 +2427,7 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
     launch_wgrad3<5, true>(mDY, mX, p, grid, s);
   else
     launch_wgrad3<3, false>(mDY, mX, p, grid, s);
-  wgrad3_reduce_kernel<<<(unsigned)(c.Co * (c.Ci / 64)), 160, 0, s>>>((const float4*)p.out, dw_ref, c.Co, c.Ci, p.splits);
+  { auto k_ = wgrad3_reduce_kernel; LBC_LAUNCH(k_, dim3((unsigned)(c.Co * (c.Ci / 64))), dim3(160), 0, s, (const float4*)p.out, dw_ref, c.Co, c.Ci, p.splits); }
   LBC_LAUNCHED("wgrad3_reduce_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -2522,7 +2525,7 @@ static bool conv_wgrad_impl(const ConvL& c, const bf16* x, const bf16* dy, float
   else
     launch_wgrad<64, 4>(mDY, mX, p, s);
   int64_t n = wsize;
-  wgrad_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(scratch, dw_ref, c.Co, c.Ci, KK);
+  { auto k_ = wgrad_unpack_kernel; LBC_LAUNCH(k_, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, scratch, dw_ref, c.Co, c.Ci, KK); }
   LBC_LAUNCHED("wgrad_unpack_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -2538,6 +2541,8 @@ bool conv_wgrad_bf16(const ConvL& c, const bf16* x, const bf16* dy, float* dw_re
 template <bool F16>
 __global__ void __launch_bounds__(256) split16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, int64_t rows,
                                                       int C8, float scale) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t n = rows * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / C8;
@@ -2573,9 +2578,9 @@ bool tc_split(const float* src, void* dst16, int64_t rows, int C, int fmt, float
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   if (fmt == TC_F16)
-    split16_kernel<true><<<(unsigned)blocks, 256, 0, s>>>((const float4*)src, (uint4*)dst16, rows, C / 8, scale);
+    { auto k_ = split16_kernel<true>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, (const float4*)src, (uint4*)dst16, rows, C / 8, scale); }
   else
-    split16_kernel<false><<<(unsigned)blocks, 256, 0, s>>>((const float4*)src, (uint4*)dst16, rows, C / 8, scale);
+    { auto k_ = split16_kernel<false>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, (const float4*)src, (uint4*)dst16, rows, C / 8, scale); }
   LBC_LAUNCHED(fmt == TC_F16 ? "split16_kernel<f16>" : "split16_kernel<bf16>");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -2584,6 +2589,8 @@ bool tc_split(const float* src, void* dst16, int64_t rows, int C, int fmt, float
 template <bool F16>
 __global__ void __launch_bounds__(256) tc_stem_im2col_kernel(const float* __restrict__ x0, uint16_t* __restrict__ col, int64_t npix,
                                                              int C, int H, int W, int OH, int OW, int Kp) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t n = npix * Kp;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pix = i / Kp;
@@ -2620,9 +2627,9 @@ bool tc_stem_im2col(const float* x0, void* col16, int B, int C, int H, int W, in
   const int64_t cap = (int64_t)sm_count() * 32;
   if (blocks > cap) blocks = cap;
   if (fmt == TC_F16)
-    tc_stem_im2col_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(x0, (uint16_t*)col16, npix, C, H, W, OH, OW, Kp);
+    { auto k_ = tc_stem_im2col_kernel<true>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, x0, (uint16_t*)col16, npix, C, H, W, OH, OW, Kp); }
   else
-    tc_stem_im2col_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(x0, (uint16_t*)col16, npix, C, H, W, OH, OW, Kp);
+    { auto k_ = tc_stem_im2col_kernel<false>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, x0, (uint16_t*)col16, npix, C, H, W, OH, OW, Kp); }
   LBC_LAUNCHED("tc_stem_im2col_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;

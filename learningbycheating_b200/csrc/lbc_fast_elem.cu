@@ -81,6 +81,8 @@ static RowGeom row_geom(int64_t M, int C, int blocks_per_sm) {
 // partials are reduced by col_finalize kernels -> deterministic results.
 __global__ void __launch_bounds__(256, 6) bn_stats_kernel(const uint4* __restrict__ x, int64_t M, int tpr, int rpi, float* partial,
                                                        int C) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float red[];  // [threads][16]
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(256, 6) bn_stats_kernel(const uint4* __restric
 // the (<= 32) block results are combined with one fp32 atomic each into the pre-zeroed sums.
 __global__ void __launch_bounds__(1024) col_finalize_kernel(const float* __restrict__ partial, int P, int C2, float* sums,
                                                             int rows_per_block, int use_atomic) {
+  pdl_wait();
+  pdl_trigger();
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int pl = threadIdx.x >> 5;
   __shared__ float red[32][33];
@@ -182,7 +186,7 @@ static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_s
   const int rows_per_block = (P + rb - 1) / rb;
   rb = (P + rows_per_block - 1) / rows_per_block;
   if (rb > 1) cudaMemsetAsync(sums, 0, sizeof(float) * C2, s);
-  col_finalize_kernel<<<dim3((C2 + 31) / 32, rb), 1024, 0, s>>>(partial, P, C2, sums, rows_per_block, rb > 1 ? 1 : 0);
+  { auto k_ = col_finalize_kernel; LBC_LAUNCH(k_, dim3(dim3((C2 + 31) / 32, rb)), dim3(1024), 0, s, partial, P, C2, sums, rows_per_block, rb > 1 ? 1 : 0); }
   LBC_LAUNCHED("col_finalize_kernel");
 }
 
@@ -208,6 +212,8 @@ struct BnFinalizeArgs {
   float* sums;            // out (optional): [2C] raw column sums
 };
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const BnFinalizeArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int pl = threadIdx.x >> 5;
   __shared__ float red0[32][33], red1[32][33];
@@ -292,7 +298,7 @@ bool bn_finalize_bf16(const float* partial, int rows, int C, int64_t M, const fl
   a.negshift = negshift;
   a.scsh = scsh;
   a.sums = sums;
-  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(a);
+  { auto k_ = bn_finalize_kernel; LBC_LAUNCH(k_, dim3((C + 31) / 32), dim3(1024), 0, s, a); }
   LBC_LAUNCHED("bn_finalize_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -303,7 +309,7 @@ bool bn_stats_partials_bf16(const bf16* x, int64_t M, int C, int* rows, lbc_stre
   RowGeom g = row_geom(M, C, 6);
   float* part = partial_buffer();
   if (!part) return false;
-  bn_stats_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>((const uint4*)x, M, g.tpr, g.rpi, part, C);
+  { auto k_ = bn_stats_kernel; LBC_LAUNCH(k_, dim3(g.grid), dim3(g.threads), g.threads * 16 * sizeof(float), s, (const uint4*)x, M, g.tpr, g.rpi, part, C); }
   LBC_LAUNCHED("bn_stats_kernel");
   LBC_CUDA(cudaGetLastError());
   *rows = g.grid;
@@ -323,7 +329,7 @@ bool bn_stats_bf16(const bf16* x, int64_t M, int C, float* sums, lbc_stream_t s)
   RowGeom g = row_geom(M, C, 6);
   float* part = partial_buffer();
   if (!part) return false;
-  bn_stats_kernel<<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>((const uint4*)x, M, g.tpr, g.rpi, part, C);
+  { auto k_ = bn_stats_kernel; LBC_LAUNCH(k_, dim3(g.grid), dim3(g.threads), g.threads * 16 * sizeof(float), s, (const uint4*)x, M, g.tpr, g.rpi, part, C); }
   LBC_LAUNCHED("bn_stats_kernel");
   col_finalize(part, g.grid, 2 * C, sums, s);
   LBC_CUDA(cudaGetLastError());
@@ -350,6 +356,8 @@ struct BnApplyArgs {
   int relu, train;
 };
 __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const BnApplyArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int t = threadIdx.x;
   const int cg = t % a.tpr, r = t / a.tpr;
   float sc[8], sh[8];
@@ -439,7 +447,7 @@ bool bn_apply_bf16(const bf16* x, const float* scsh, int64_t M, int C, const flo
   a.momentum = momentum;
   a.relu = relu ? 1 : 0;
   a.train = train ? 1 : 0;
-  bn_apply_kernel<<<g.grid, g.threads, 0, s>>>(a);
+  { auto k_ = bn_apply_kernel; LBC_LAUNCH(k_, dim3(g.grid), dim3(g.threads), 0, s, a); }
   LBC_LAUNCHED("bn_apply_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -461,6 +469,8 @@ __global__ void __launch_bounds__(256, OWN ? 3 : 4) bn_bwd_reduce_kernel(const u
                                                             const uint8_t* __restrict__ mbits,
                                                             const uint4* __restrict__ rsrc = nullptr,
                                                             const uint8_t* __restrict__ rbits = nullptr, uint4* dy_out = nullptr) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float red[];
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
@@ -540,6 +550,8 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const uint4* __res
                                                            uint4* __restrict__ dx, int64_t M, int tpr, int rpi, int C,
                                                            const float* __restrict__ beta_own,
                                                            const uint8_t* __restrict__ mbits) {
+  pdl_wait();
+  pdl_trigger();
   const int t = threadIdx.x;
   const int cg = t % tpr, r = t / tpr;
   // dx = k0*(g - db/M - xhat*dg/M) = k0*g + kb*x + ka,  kb = -k0*rstd*dg/M,  ka = -k0*db/M - kb*mean
@@ -599,12 +611,10 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
   if (!part) return false;
   if (beta_own) {
     RowGeom g3 = row_geom(M, C, 3);
-    bn_bwd_reduce_kernel<true><<<g3.grid, g3.threads, g3.threads * 16 * sizeof(float), s>>>(
-        (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g3.tpr, g3.rpi, part, C, gamma, beta_own, nullptr);
+    { auto k_ = bn_bwd_reduce_kernel<true>; LBC_LAUNCH(k_, dim3(g3.grid), dim3(g3.threads), g3.threads * 16 * sizeof(float), s,  (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g3.tpr, g3.rpi, part, C, gamma, beta_own, nullptr, nullptr, nullptr, nullptr); }
     LBC_LAUNCHED("bn_bwd_reduce_kernel<own>");
     col_finalize(part, g3.grid, 2 * C, sums, s);
-    bn_bwd_apply_kernel<true><<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd,
-                                                          gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own, nullptr);
+    { auto k_ = bn_bwd_apply_kernel<true>; LBC_LAUNCH(k_, dim3(g.grid), dim3(g.threads), 0, s, (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own, nullptr); }
     LBC_LAUNCHED("bn_bwd_apply_kernel<own>");
     LBC_CUDA(cudaGetLastError());
     return true;
@@ -614,13 +624,11 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
     // the partial rows are already in the shared scratch: resid_bn_reduce_bf16 reduced while it produced dy
     col_finalize(part, pre_rows, 2 * C, sums, s);
   } else {
-    bn_bwd_reduce_kernel<false><<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
-        (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, gamma, beta_own, mask_bits);
+    { auto k_ = bn_bwd_reduce_kernel<false>; LBC_LAUNCH(k_, dim3(g.grid), dim3(g.threads), g.threads * 16 * sizeof(float), s,  (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, gamma, beta_own, mask_bits, nullptr, nullptr, nullptr); }
     LBC_LAUNCHED("bn_bwd_reduce_kernel");
     col_finalize(part, g.grid, 2 * C, sums, s);
   }
-  bn_bwd_apply_kernel<false><<<g.grid, g.threads, 0, s>>>((const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd,
-                                                         gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own, mask_bits);
+  { auto k_ = bn_bwd_apply_kernel<false>; LBC_LAUNCH(k_, dim3(g.grid), dim3(g.threads), 0, s, (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own, mask_bits); }
   LBC_LAUNCHED("bn_bwd_apply_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -632,6 +640,8 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
 __global__ void __launch_bounds__(256) ew_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
                                                  const uint4* __restrict__ act, int64_t n, int mode,
                                                  const uint8_t* __restrict__ mbits) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float a[8], b[8], m[8];
@@ -660,7 +670,7 @@ bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, l
   int64_t blocks = (nv + 255) / 256;
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
-  ew_kernel<<<(unsigned)blocks, 256, 0, s>>>((uint4*)dst, (const uint4*)src, (const uint4*)act, nv, mode, mask_bits);
+  { auto k_ = ew_kernel; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, (uint4*)dst, (const uint4*)src, (const uint4*)act, nv, mode, mask_bits); }
   LBC_LAUNCHED("ew_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -678,6 +688,8 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const uint4* __res
                                                               const float* __restrict__ beta, uint4* __restrict__ y,
                                                               uint2* __restrict__ idx, int N, int H, int W, int tpr, int OH,
                                                               int OW) {
+  pdl_wait();
+  pdl_trigger();
   const IdxT total = (IdxT)N * OH * OW * tpr;
   const IdxT stride = (IdxT)gridDim.x * blockDim.x;   // multiple of tpr (tpr divides 256)
   IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
@@ -742,11 +754,9 @@ bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, c
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
   if ((int64_t)N * H * W * (C / 8) < (int64_t)1 << 31)
-    bn_relu_maxpool_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
-                                                                       (uint2*)idx, N, H, W, C / 8, OH, OW);
+    { auto k_ = bn_relu_maxpool_kernel<uint32_t>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, (const uint4*)x, mean, rstd, gamma, beta, (uint4*)y, (uint2*)idx, N, H, W, C / 8, OH, OW); }
   else
-    bn_relu_maxpool_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)x, mean, rstd, gamma, beta, (uint4*)y,
-                                                                      (uint2*)idx, N, H, W, C / 8, OH, OW);
+    { auto k_ = bn_relu_maxpool_kernel<int64_t>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, (const uint4*)x, mean, rstd, gamma, beta, (uint4*)y, (uint2*)idx, N, H, W, C / 8, OH, OW); }
   LBC_LAUNCHED("bn_relu_maxpool_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -766,6 +776,8 @@ __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __re
                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, uint4* __restrict__ dx, int N,
                                                                int H, int W, int tpr, int OH, int OW) {
+  pdl_wait();
+  pdl_trigger();
   const int H2 = H >> 1, W2 = W >> 1;
   const IdxT total = (IdxT)N * H2 * W2 * tpr;
   const IdxT stride = (IdxT)gridDim.x * blockDim.x;   // multiple of tpr
@@ -843,11 +855,9 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
   int64_t cap = (int64_t)sm_count2() * 16;
   if (blocks > cap) blocks = cap;
   if ((int64_t)N * H * W * (C / 8) < (int64_t)1 << 31)
-    maxpool_relu_bwd_kernel<uint32_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean,
-                                                                        rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW);
+    { auto k_ = maxpool_relu_bwd_kernel<uint32_t>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, (const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean, rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW); }
   else
-    maxpool_relu_bwd_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean,
-                                                                       rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW);
+    { auto k_ = maxpool_relu_bwd_kernel<int64_t>; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, (const uint4*)dy, (const uint2*)idx, (const uint4*)x, mean, rstd, gamma, beta, (uint4*)dx, N, H, W, C / 8, OH, OW); }
   LBC_LAUNCHED("maxpool_relu_bwd_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -861,9 +871,7 @@ bool resid_bn_reduce_bf16(bf16* dst, const bf16* src, const uint8_t* src_bits, c
   RowGeom g = row_geom(M, C, 4);
   float* part = partial_buffer();
   if (!part) return false;
-  bn_bwd_reduce_kernel<false, true><<<g.grid, g.threads, g.threads * 16 * sizeof(float), s>>>(
-      (const uint4*)dst, nullptr, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, nullptr, nullptr, mask_bits,
-      (const uint4*)src, src_bits, (uint4*)dst);
+  { auto k_ = bn_bwd_reduce_kernel<false, true>; LBC_LAUNCH(k_, dim3(g.grid), dim3(g.threads), g.threads * 16 * sizeof(float), s,  (const uint4*)dst, nullptr, (const uint4*)x, mean, rstd, M, g.tpr, g.rpi, part, C, nullptr, nullptr, mask_bits, (const uint4*)src, src_bits, (uint4*)dst); }
   LBC_LAUNCHED("bn_bwd_reduce_kernel<resid>");
   LBC_CUDA(cudaGetLastError());
   *rows = g.grid;

@@ -123,6 +123,8 @@ __device__ __forceinline__ void stage_wait_1() { asm volatile("cp.async.wait_gro
 // logits[n][kj][p] = b'[kj] + sum_c A[kj][c] h[n,p,c]:  D[32 px per warp][24] = H[32][64] x (A_hi + A_lo)^T
 __global__ void __launch_bounds__(128) head_logits_mma_kernel(const bf16* __restrict__ h, const float* __restrict__ fold,
                                                                float* __restrict__ logits, int N, int HW) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t hs_smem[];
   uint8_t* tile[2] = {hs_smem, hs_smem + 16384};
   float(*out)[132] = reinterpret_cast<float(*)[132]>(hs_smem + 32768);   // [20][128 px (+4)]
@@ -208,6 +210,8 @@ __global__ void __launch_bounds__(128) head_logits_mma_kernel(const bf16* __rest
 // one block per (n, kj) row; HW <= 128*32
 __global__ void __launch_bounds__(128) head_softmax_kernel(const float* __restrict__ logits, float* __restrict__ rowmax,
                                                            float* __restrict__ rowsum, float* __restrict__ preds, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
   const int HW = H * W;
   const float* l = logits + (int64_t)blockIdx.x * HW;
   float v[32];
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(128) head_softmax_kernel(const float* __restri
 // SpatialSoftmax alone (common.py:136-152) over [N*20] rows of H*W logits
 bool head_softmax_f32(const float* logits, float* rowmax, float* rowsum, float* preds, int N, int H, int W, lbc_stream_t s) {
   if (!enabled() || H * W > 4096) return false;
-  head_softmax_kernel<<<N * 20, 128, 0, s>>>(logits, rowmax, rowsum, preds, H, W);
+  { auto k_ = head_softmax_kernel; LBC_LAUNCH(k_, dim3(N * 20), dim3(128), 0, s, logits, rowmax, rowsum, preds, H, W); }
   LBC_LAUNCHED("head_softmax_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -285,10 +289,10 @@ bool head_forward_bf16(const bf16* h, ref::HeadParams hp, float* fold, float* lo
     const int ntiles = N * ((HW + 127) / 128);
     int grid = sm_count3() * 4;
     if (grid > ntiles) grid = ntiles;
-    head_logits_mma_kernel<<<grid, 128, SMEM, s>>>(h, fold, logits, N, HW);
+    { auto k_ = head_logits_mma_kernel; LBC_LAUNCH(k_, dim3(grid), dim3(128), SMEM, s, h, fold, logits, N, HW); }
     LBC_LAUNCHED("head_logits_mma_kernel");
   }
-  head_softmax_kernel<<<N * 20, 128, 0, s>>>(logits, rowmax, rowsum, preds, H, W);
+  { auto k_ = head_softmax_kernel; LBC_LAUNCH(k_, dim3(N * 20), dim3(128), 0, s, logits, rowmax, rowsum, preds, H, W); }
   LBC_LAUNCHED("head_softmax_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -314,6 +318,8 @@ __global__ void __launch_bounds__(128) head_dh_mma_kernel(const float* __restric
                                                           const float* __restrict__ fold, const float* __restrict__ coef,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           bf16* __restrict__ dh, int N, int HW) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t hs_smem[];
   uint8_t* tile[2] = {hs_smem, hs_smem + 16384};
   float* cf = reinterpret_cast<float*>(hs_smem + 32768);   // c0 | c1 | mean | rstd
@@ -424,6 +430,8 @@ __global__ void __launch_bounds__(128) head_dlogits_kernel(const float* __restri
                                                            const float* __restrict__ onehot, const float* __restrict__ d_pred,
                                                            const float* __restrict__ d_preds, float* __restrict__ dlogits, int H,
                                                            int W) {
+  pdl_wait();
+  pdl_trigger();
   const int HW = H * W;
   const int r = blockIdx.x;
   const int kj = r % 20, b = r / 20;
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(128) head_dlogits_kernel(const float* __restri
 bool head_dlogits_f32(const float* logits, const float* rowmax, const float* rowsum, const float* preds, const float* onehot,
                       const float* d_pred, const float* d_preds, float* dlogits, int N, int H, int W, lbc_stream_t s) {
   if (!enabled()) return false;
-  head_dlogits_kernel<<<N * 20, 128, 0, s>>>(logits, rowmax, rowsum, preds, onehot, d_pred, d_preds, dlogits, H, W);
+  { auto k_ = head_dlogits_kernel; LBC_LAUNCH(k_, dim3(N * 20), dim3(128), 0, s, logits, rowmax, rowsum, preds, onehot, d_pred, d_preds, dlogits, H, W); }
   LBC_LAUNCHED("head_dlogits_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -464,6 +472,8 @@ bool head_dlogits_f32(const float* logits, const float* rowmax, const float* row
 __global__ void __launch_bounds__(128) head_s_mma_kernel(const float* __restrict__ dlogits, const bf16* __restrict__ h,
                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                                          double* S, int N, int HW) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t hs_smem[];
   uint8_t* tile[2] = {hs_smem, hs_smem + 16384};
   constexpr int DPAD = 136;   // A fragments read 8 bytes at dls[kj = g][px = 2t]: banks 8g + 2t over a half warp
@@ -581,7 +591,7 @@ bool head_backward_s_bf16(const float* dlogits, const bf16* h, const float* mean
     LBC_CUDA(cudaFuncSetAttribute(head_s_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  head_s_mma_kernel<<<grid, 128, SMEM, s>>>(dlogits, h, mean, rstd, S, N, HW);
+  { auto k_ = head_s_mma_kernel; LBC_LAUNCH(k_, dim3(grid), dim3(128), SMEM, s, dlogits, h, mean, rstd, S, N, HW); }
   LBC_LAUNCHED("head_s_mma_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
@@ -600,7 +610,7 @@ bool head_backward_dh_bf16(const float* dlogits, const bf16* h, ref::HeadParams 
     LBC_CUDA(cudaFuncSetAttribute(head_dh_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  head_dh_mma_kernel<<<grid, 128, SMEM, s>>>(dlogits, h, fold, coef, hp.mean[0], hp.rstd[0], dh, N, HW);
+  { auto k_ = head_dh_mma_kernel; LBC_LAUNCH(k_, dim3(grid), dim3(128), SMEM, s, dlogits, h, fold, coef, hp.mean[0], hp.rstd[0], dh, N, HW); }
   LBC_LAUNCHED("head_dh_mma_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;

@@ -1047,10 +1047,7 @@ class Net : public NetBase {
     lbc_stream_t s = s_in;
     // overlap mode (see the members above): LBC_WGRAD_OVERLAP=0 keeps every kernel on the caller's stream; the per-category
     // profiler brackets launches of ONE stream with events, so it also runs the serial schedule
-    static const int ovl_mode = [] {
-      const char* e = getenv("LBC_WGRAD_OVERLAP");   // 0 (default until measured): serial, 1: side stream, chain on the caller's stream, 2: + high-priority chain
-      return e ? atoi(e) : 0;
-    }();
+    const int ovl_mode = g_wgrad_overlap;   // 0: serial, 1: side stream, 2: + high-priority chain (lbc_set_schedule / LBC_WGRAD_OVERLAP)
     ovl = ovl_capable && ovl_mode > 0 && !g_prof_on;
     ring_next = 0;
 #ifndef LBC_HOST_EMU

@@ -510,6 +510,55 @@ def test_full_size_properties_gpu(backend):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B", [8, 256])
+def test_launch_schedule_does_not_change_results_gpu(backend, B):
+    """lbc_set_schedule: weight gradients on the side stream (with and without the high-priority chain stream) and
+    programmatic dependent launch reorder / overlap kernels, they must not change a single result beyond the fp32
+    atomics of the split-K weight gradients: same batch, same weights, four schedules, three steps each (the second and
+    third step start while the side stream may still hold work of the previous one unless the joins are right)."""
+    import learningbycheating_b200 as lbc
+    from learningbycheating_b200 import _lib, train_image_phase0 as p0
+    dev = "cuda"
+    b = batch_on(dev, B)
+    oh = lbc.one_hot(b["command"].cpu()).to(dev)
+    target = (torch.rand(B, 5, 2, generator=torch.Generator().manual_seed(5)) * torch.tensor([384.0, 160.0])).to(dev)
+
+    def run(ovl, pdl):
+        _lib.set_schedule(ovl, pdl)
+        try:
+            s, _ = build_models(dev, "bf16")
+            s.train()
+            opt = lbc.Adam(s.parameters(), lr=1e-4)
+            out = []
+            for _ in range(3):
+                pred, preds = s(b["rgb"], b["speed"], oh)
+                loss = p0.LocationLoss(device=dev)(pred, target).mean()
+                opt.zero_grad()
+                loss.backward()
+                grads = {k: q.grad.detach().clone() for k, q in s.named_parameters() if q.grad is not None}
+                opt.step()
+                out.append((pred.detach().clone(), float(loss), grads))
+            torch.cuda.synchronize()
+            return out
+        finally:
+            _lib.set_schedule(0, 0)
+
+    ref = run(0, 0)
+    for ovl, pdl in ((1, 0), (2, 0), (0, 1), (2, 1)):
+        got = run(ovl, pdl)
+        for step, ((p0_, l0, g0), (p1_, l1, g1)) in enumerate(zip(ref, got)):
+            tag = "schedule (%d, %d) step %d" % (ovl, pdl, step)
+            # step 0 sees identical weights: only atomics order differs; later steps inherit that through Adam (lr 1e-4)
+            tol = 1e-5 if step == 0 else 2e-2
+            assert (p0_ - p1_).abs().max().item() <= tol, tag
+            assert abs(l0 - l1) <= tol * max(1.0, abs(l0)), tag
+            if step == 0:
+                for k in g0:
+                    d = (g0[k] - g1[k]).abs().max().item()
+                    assert d <= 1e-4 * max(g0[k].abs().max().item(), 1e-6), (tag, k, d)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["bf16", "fp32tc", "fp32"])
 def test_inference_graph_gpu(backend, precision, monkeypatch):
     """small eval batches go through lbc_net_infer (one CUDA-graph replay per call).  Same bits as the
