@@ -20,7 +20,7 @@ except Exception as ex:
     print(f, "failed", ex); print(open(f.replace(".json", ".err")).read()[-800:])
 PY
 }
-for v in "0 0" "2 0" "1 0" "0 1" "2 1" "0 0" "2 1"; do
+for v in "0 0" "2 0" "1 0" "0 1" "2 1"; do
   set -- $v
   LBC_WGRAD_OVERLAP=$1 LBC_PDL=$2 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/r2q_ab_ovl$1_pdl$2.json 2> $O/r2q_ab_ovl$1_pdl$2.err
   show $O/r2q_ab_ovl$1_pdl$2.json
