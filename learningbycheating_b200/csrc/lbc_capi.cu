@@ -130,6 +130,10 @@ int lbc_set_fast_kernels(int enabled) {
   if (enabled & 128) m &= ~4;
   if (enabled & 256) m |= 8;    // 256 / 512 = space-to-depth layout of the RGB stem operand on / off
   if (enabled & 512) m &= ~8;
+  if (enabled & 1024) m |= 16;    // 1024 / 2048 = shared-row CTA-pair kernel for the 3x3/s1 convolutions with 128-wide N tiles on / off
+  if (enabled & 2048) m &= ~16;
+  if (enabled & 4096) m |= 32;    // 4096 / 8192 = ... also for the layers whose channel count is a multiple of 256
+  if (enabled & 8192) m &= ~32;
   fast::set_pair_mode(m);
   return 0;
 }

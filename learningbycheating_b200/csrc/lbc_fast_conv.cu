@@ -876,6 +876,303 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------- 3x3/s1, shared activation rows, CTA pair
+// The 128-channel layers (N tile = 128) need 24 KB of operands per 256 tensor cycles with one TMA box per tap -- 96 B/clk
+// against the ~68 B/clk an SM ingests (measured: layer-2 GEMMs at 48 % tensor-pipe, 66 us for the 72.5 GFLOP the 256-wide
+// layers do in 52).  This variant is conv_gemm_kernel<.., PAIR> with conv3x3_c64_kernel's operand scheme: ONE activation box
+// per kernel ROW and 64-channel chunk ({64 ch, 8+2 columns, TH, TN} = 160 rows of 128 B) feeds the three kw taps through
+// UMMA descriptors started 0/1/2 rows into it (8-pixel-wide tiles: one 8-row core-matrix group per image row, groups
+// 1280 B apart), so a stage is 20 KB of A + 3 x 8 KB of B for 3 x 256 tensor cycles = 57 B/clk.
+// Epilogue: per-channel constants from shared memory (broadcast LDS.128); BatchNorm statistics in 16 registers per thread
+// (one 16-byte chunk of 8 channels x 16 rows of the staged bf16 tile per thread and tile), combined once per CTA.
+struct ConvRowParams {
+  int TH, TN, tiles_w, tiles_h, tiles_n;   // 128-position tile = TN x TH x 8
+  int n_tiles_n, k_chunks;                 // N tiles of BN output channels; 64-channel K chunks
+  int row_dh[3];                           // spatial row offset of kernel-row group g
+  int shift[3][3];                         // row shift (0..2) into the 10-wide box for tap j of group g
+  int koff[3][3];                          // K offset of that tap's chunk 0 in the packed weight matrix
+  const float* bias;
+  int relu;
+  float* stat_partial;
+  int stat_C;
+  int valid_n;
+};
+template <int BN, int STAGES>
+struct SmemPlanRow {
+  static constexpr int B_TAP = (BN / 2) * 128;                 // this CTA's half of one tap's weight tile
+  static constexpr int STAGE_BYTES = AKW_BYTES + 3 * B_TAP;    // 20 KB + 3 x 8 KB
+  static constexpr int OUT_OFF = STAGES * STAGE_BYTES;
+  static constexpr int OUT_BYTES = (BN / 64) * A_BYTES;
+  static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
+  static constexpr int BIAS_OFF = BAR_OFF + 256;               // BN floats
+  static constexpr int RED_OFF = BIAS_OFF + BN * 4;            // 128 threads x 16 floats
+  static constexpr int CSTAT_OFF = RED_OFF + 128 * 16 * 4;     // [2][Co <= 512] floats
+  static constexpr int TOTAL = CSTAT_OFF + 4096 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_row_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
+                const __grid_constant__ CUtensorMap mO, const ConvRowParams p) {
+  static_assert(BN == 128, "statistics mapping: 16 chunks of 8 channels x 8 groups of 16 rows");
+  typedef SmemPlanRow<BN, STAGES> SP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* out_stage = smem + SP::OUT_OFF;
+  uint64_t* full = (uint64_t*)(smem + SP::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 256);   // the epilogue threads of both CTAs arrive on the leader's
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched shared / tensor memory only
+  pdl_trigger();
+
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int k_iters = 3 * p.k_chunks;
+  const uint32_t crank = cluster_ctarank();
+  const int walk0 = (int)(blockIdx.x >> 1);
+  const int walk_step = (int)(gridDim.x >> 1);
+  const int num_tiles = ((tiles_m + 1) / 2) * p.n_tiles_n;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = walk0; tile < num_tiles; tile += walk_step) {
+        const int n_tile = tile % p.n_tiles_n;
+        const int m_tile = 2 * (tile / p.n_tiles_n) + (int)crank;   // (odd tiles_m: one past the end = past the batch, zero-filled)
+        const int w0 = (m_tile % p.tiles_w) * 8;
+        const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int g = 0; g < 3; ++g) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * SP::STAGE_BYTES;
+            if (crank == 0) mbar_expect_tx(&full[stage], 2 * SP::STAGE_BYTES);
+            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+            tma_load_4d_pair(&mA, sa, lead_full, kc * 64, w0 - 1, h0 + p.row_dh[g], n0);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              tma_load_2d_pair(&mB, sa + AKW_BYTES + j * SP::B_TAP, lead_full, p.koff[g][j] + kc * 64,
+                               n_tile * BN + (int)crank * (BN / 2));
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = walk0; tile < num_tiles && crank == 0; tile += walk_step, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      int g = 0;
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * SP::STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const uint64_t ad = umma_desc_k_sw128_sbo(sa + p.shift[g][j] * 128, 1280);
+            const uint64_t bd = umma_desc_k_sw128(sa + AKW_BYTES + j * SP::B_TAP);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_pair(tmem_d, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (k | j | kk) != 0);
+          }
+          umma_commit_pair(&empty[stage]);
+          if (k == k_iters - 1) umma_commit_pair(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++g == 3) g = 0;
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 64);
+    const int e = threadIdx.x - 64;
+    float* bias_s = reinterpret_cast<float*>(smem + SP::BIAS_OFF);
+    float* red = reinterpret_cast<float*>(smem + SP::RED_OFF);
+    float* cstat = reinterpret_cast<float*>(smem + SP::CSTAT_OFF);
+    const bool stats = p.stat_partial != nullptr;
+    if (stats)
+      for (int i = e; i < 2 * p.stat_C; i += 128) cstat[i] = 0.f;
+    // statistics: thread e owns the 16-byte chunk (8 channels) `cidx` of the 16 staged rows [16*rg, 16*rg + 16)
+    const int cidx = e & 15, rg = e >> 4;
+    float as[8], aq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) as[i] = aq[i] = 0.f;
+    int cur_nt = -1;
+    // fixed-order combination of the eight row groups of every channel, added to this CTA's running row
+    auto flush = [&](int nt) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        red[e * 16 + i] = as[i];
+        red[e * 16 + 8 + i] = aq[i];
+        as[i] = aq[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float s = 0.f, q2 = 0.f;
+#pragma unroll
+      for (int r2 = 0; r2 < 8; ++r2) {
+        s += red[(r2 * 16 + (e >> 3)) * 16 + (e & 7)];
+        q2 += red[(r2 * 16 + (e >> 3)) * 16 + 8 + (e & 7)];
+      }
+      cstat[nt * BN + e] += s;
+      cstat[p.stat_C + nt * BN + e] += q2;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    int it = 0;
+    for (int tile = walk0; tile < num_tiles; tile += walk_step, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int n_tile = tile % p.n_tiles_n;
+      const int m_tile = 2 * (tile / p.n_tiles_n) + (int)crank;
+      const int w0 = (m_tile % p.tiles_w) * 8;
+      const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.TH;
+      const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.TN;
+      if (n_tile != cur_nt) {   // (uniform over the CTA)
+        if (stats && cur_nt >= 0) flush(cur_nt);
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the previous tile's reads of bias_s are done
+        bias_s[e] = p.bias ? __ldg(p.bias + n_tile * BN + e) : 0.f;
+        cur_nt = n_tile;
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging buffer free again
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        uint8_t* rowp = out_stage + (ch >> 1) * A_BYTES + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            float a = __uint_as_float(r[j * 8 + e2 * 2]) + bb[e2 * 2];
+            float b = __uint_as_float(r[j * 8 + e2 * 2 + 1]) + bb[e2 * 2 + 1];
+            if (p.relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[e2] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const int chunk16 = (ch & 1) * 4 + j;
+          *reinterpret_cast<uint4*>(rowp + ((chunk16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));   // on the leader's barrier (256 arrivals per phase)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b) tma_store_4d(&mO, out_stage + b * A_BYTES, n_tile * BN + b * 64, w0, h0, n0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (stats && m_tile < tiles_m) {
+        int nvalid = p.valid_n - n0;
+        nvalid = nvalid < 0 ? 0 : (nvalid > p.TN ? p.TN : nvalid);
+        const int valid_rows = nvalid * p.TH * 8;
+        const uint8_t* boxp = out_stage + (cidx >> 3) * A_BYTES;
+        const int chunk = cidx & 7;
+        if (valid_rows >= rg * 16 + 16) {
+          uint4 w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r2 = rg * 16 + i;
+            w[i] = *reinterpret_cast<const uint4*>(boxp + r2 * 128 + ((chunk ^ (r2 & 7)) << 4));
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t ww[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) {
+              const float a = __uint_as_float(ww[t2] << 16), b = __uint_as_float(ww[t2] & 0xffff0000u);
+              as[2 * t2] += a;
+              as[2 * t2 + 1] += b;
+              aq[2 * t2] += a * a;
+              aq[2 * t2 + 1] += b * b;
+            }
+          }
+        } else {
+          for (int r2 = rg * 16; r2 < rg * 16 + 16 && r2 < valid_rows; ++r2) {
+            const uint4 w = *reinterpret_cast<const uint4*>(boxp + r2 * 128 + ((chunk ^ (r2 & 7)) << 4));
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) {
+              const float a = __uint_as_float(ww[t2] << 16), b = __uint_as_float(ww[t2] & 0xffff0000u);
+              as[2 * t2] += a;
+              as[2 * t2 + 1] += b;
+              aq[2 * t2] += a * a;
+              aq[2 * t2 + 1] += b * b;
+            }
+          }
+        }
+      }
+    }
+    if (stats) {
+      if (cur_nt >= 0) flush(cur_nt);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* dst = p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C;
+      for (int i = e; i < 2 * p.stat_C; i += 128) dst[i] = cstat[i];
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  cluster_sync_all();   // the peer's smem / TMEM are operands of the leader's MMAs until both CTAs are done
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes);
 
 // ------------------------------------------------------------------------------------------- stem 7x7/s2 (C_in <= 4)
@@ -1461,6 +1758,68 @@ static bool try_conv3x3_c64(const bf16* in, const void* wpack, bf16* out, int B,
 }
 
 
+// 3x3 / stride 1 / pad 1 with 128-wide N tiles on the shared-row CTA-pair kernel (forward: mirrored = false; data gradient:
+// mirrored = true with the transposed pack).  in [B,H,W,Cin], wpack [Cout][9][Cin], out [B,H,W,Cout]; returns the number of
+// CTAs launched (= rows of statistics partials) or 0 when the layer does not fit the kernel.
+//   g_pair_mode bit 4: layers with Cout % 256 != 0 (layer 2, the teacher's layer 2)   bit 5: also Cout % 256 == 0 (layer 3)
+static int try_conv_row(const bf16* in, const void* wpack, bf16* out, int B, int H, int W, int Cin, int Cout, bool mirrored,
+                        const float* bias, bool relu, float* stat_partial, lbc_stream_t s) {
+  constexpr int BN = 128, STAGES = 4;
+  if (!(g_pair_mode & 1)) return 0;
+  if (!(g_pair_mode & (Cout % 256 == 0 ? 32 : 16))) return 0;
+  if ((W % 8) || (Cin % 64) || (Cout % BN) || Cout > 512) return 0;
+  ConvRowParams p;
+  memset(&p, 0, sizeof(p));
+  const int TH = pow2_divisor(H, 16);
+  const int TN = 16 / TH;
+  p.TH = TH;
+  p.TN = TN;
+  p.tiles_w = W / 8;
+  p.tiles_h = H / TH;
+  p.tiles_n = (B + TN - 1) / TN;
+  p.n_tiles_n = Cout / BN;
+  p.k_chunks = Cin / 64;
+  for (int g = 0; g < 3; ++g) {
+    p.row_dh[g] = g - 1;                       // group g covers spatial row offset g - 1
+    const int kh = mirrored ? 2 - g : g;
+    for (int j = 0; j < 3; ++j) {
+      const int dw = mirrored ? 1 - j : j - 1;   // column offset of tap kw = j; box column 0 is w0 - 1
+      p.shift[g][j] = dw + 1;
+      p.koff[g][j] = (kh * 3 + j) * Cin;
+    }
+  }
+  p.bias = bias;
+  p.relu = relu ? 1 : 0;
+  p.stat_partial = stat_partial;
+  p.stat_C = Cout;
+  p.valid_n = B;
+  const int64_t eb = 2;
+  CUtensorMap mA = make_map_4d(in, Cin, W, H, B, Cin * eb, (int64_t)W * Cin * eb, (int64_t)H * W * Cin * eb, 10, TH, TN);
+  CUtensorMap mB = make_map_2d(wpack, (int64_t)9 * Cin, Cout, BN / 2);
+  CUtensorMap mO = make_map_4d(out, Cout, W, H, B, Cout * eb, (int64_t)W * Cout * eb, (int64_t)H * W * Cout * eb, 8, TH, TN);
+  typedef SmemPlanRow<BN, STAGES> SP;
+  static_assert(SP::TOTAL <= 232448, "smem plan of the shared-row kernel exceeds 227 KB");
+  auto kern = conv_row_kernel<BN, STAGES>;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    LBC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    LaunchCfg q(dim3((unsigned)(sm_count() / 2 * 2)), dim3(192), SP::TOTAL, (cudaStream_t)s, 2);
+    q.cfg.numAttrs = 1;   // (the cluster attribute only)
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &q.cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = sm_count() / 2;
+    }
+    max_clusters = n < sm_count() / 2 ? n : sm_count() / 2;
+  }
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int pair_tiles = ((tiles_m + 1) / 2) * p.n_tiles_n;
+  const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
+  LBC_LAUNCH_CLUSTER(kern, 2, dim3((unsigned)(2 * clusters)), dim3(192), SP::TOTAL, (cudaStream_t)s, mA, mB, mO, p);
+  LBC_LAUNCHED("conv_row_kernel<128>");
+  return 2 * clusters;
+}
+
 // ---- stem host side: x4 = zero-padded NHWC bf16 image [B][H+6][W+8][CH], CH = 4 (C_in <= 4) or 8 (C_in <= 8) ----
 static CUtensorMap make_map_stem(const void* base, int OW, int rows2, int B, int64_t pitch_bytes, int64_t img_bytes, int bw,
                                  int bh, int bn, int CH) {
@@ -1611,6 +1970,14 @@ static bool conv_fwd_impl(const ConvL& c, const void* x, const void* wpack, void
   if (!m.split && !m.out_f32 && c.K == 3 && c.stride == 1 && c.Ci == 64 && c.Co == 64 && !relu &&
       try_conv3x3_c64((const bf16*)x, wpack, (bf16*)y, B, c.H, c.W, false, bias_co, false, stat_partial, stat_rows, s))
     return true;
+  if (!m.split && !m.out_f32 && c.K == 3 && c.stride == 1 && c.pad == 1) {
+    float* part = c.Co > 512 ? nullptr : stat_partial;
+    const int ctas = try_conv_row((const bf16*)x, wpack, (bf16*)y, B, c.H, c.W, c.Ci, c.Co, false, bias_co, relu, part, s);
+    if (ctas > 0) {
+      if (stat_rows) *stat_rows = part ? ctas : 0;
+      return true;
+    }
+  }
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   if (!tile_geometry(c.OH, c.OW, B, p)) return false;
@@ -1700,6 +2067,9 @@ static bool conv_dgrad_impl(const ConvL& c, const void* dy_v, const void* wt, co
   if (c.stride == 1) {
     if (!m.split && !m.out_f32 && c.K == 3 && c.Ci == 64 && c.Co == 64 && !dy_ds &&
         try_conv3x3_c64(dy, wt, (bf16*)dx_v, B, c.H, c.W, true, bias_ci, relu, nullptr, nullptr, s))
+      return true;
+    if (!m.split && !m.out_f32 && c.K == 3 && c.pad == 1 && !dy_ds &&
+        try_conv_row(dy, wt, (bf16*)dx_v, B, c.H, c.W, c.Co, c.Ci, true, bias_ci, relu, nullptr, s) > 0)
       return true;
     ConvGemmParams p;
     memset(&p, 0, sizeof(p));
