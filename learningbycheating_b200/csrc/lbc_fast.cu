@@ -19,13 +19,13 @@ std::string trace_dump() {
 }
 bool g_prof_on = false;
 int g_wgrad_overlap = [] {
-  const char* e = getenv("LBC_WGRAD_OVERLAP");   // lbc_net.cu backward(): 0 serial, 1 side stream, 2 + high-priority chain; 0 until measured
-  return e ? atoi(e) : 0;
+  const char* e = getenv("LBC_WGRAD_OVERLAP");   // lbc_net.cu backward(): 0 serial, 1 side stream (default: 13.78 -> 12.94 ms per step on one box), 2 + high-priority chain (13.12)
+  return e ? atoi(e) : 1;
 }();
 #ifndef LBC_HOST_EMU
 int g_pdl = [] {
-  const char* e = getenv("LBC_PDL");   // programmatic dependent launch of every kernel (lbc_common.h); 0 until measured
-  return e ? atoi(e) : 0;
+  const char* e = getenv("LBC_PDL");   // programmatic dependent launch of every kernel (lbc_common.h); 13.78 -> 13.16 ms per step alone
+  return e ? atoi(e) : 1;
 }();
 #endif
 std::vector<ProfEntry> g_prof;

@@ -541,7 +541,7 @@ def test_launch_schedule_does_not_change_results_gpu(backend, B):
             torch.cuda.synchronize()
             return out
         finally:
-            _lib.set_schedule(0, 0)
+            _lib.set_schedule(int(os.environ.get("LBC_WGRAD_OVERLAP", "1")), int(os.environ.get("LBC_PDL", "1")))
 
     ref = run(0, 0)
     for ovl, pdl in ((1, 0), (2, 0), (0, 1), (2, 1)):
