@@ -577,7 +577,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       asm volatile("bar.sync 1, 128;" ::: "memory");
       float* dst = p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C;
       for (int i = threadIdx.x - 64; i < 2 * p.stat_C; i += 128) dst[i] = cstat[i];
-      bn_tail_run(p.tail, p.stat_partial, threadIdx.x - 64);
+      bn_tail_run(p.tail, p.stat_partial, threadIdx.x - 64, tmem_slot + 1);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -872,7 +872,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant
     }
     if (p.stat_partial) {
       colstat_flush(cs, red, e, p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C);
-      bn_tail_run(p.tail, p.stat_partial, e);
+      bn_tail_run(p.tail, p.stat_partial, e, tmem_slot + 1);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -1171,7 +1171,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
       asm volatile("bar.sync 1, 128;" ::: "memory");
       float* dst = p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C;
       for (int i = e; i < 2 * p.stat_C; i += 128) dst[i] = cstat[i];
-      bn_tail_run(p.tail, p.stat_partial, e);
+      bn_tail_run(p.tail, p.stat_partial, e, tmem_slot + 1);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }

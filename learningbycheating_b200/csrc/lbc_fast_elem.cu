@@ -206,8 +206,6 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const BnFinalizeArgs 
   const int pl = threadIdx.x >> 5;
   __shared__ float red0[32][33], red1[32][33];
   float s0 = 0.f, s1 = 0.f;
-  BnChannelIn in;
-  if (pl == 0 && c < a.C) in = bn_channel_in(a, c);   // in flight together with the partial rows
   if (c < a.C) {
     // up to 16 rows x 2 columns in flight per thread: the loop is pure L2 latency (1920 partial rows after a layer-2 conv)
     const float* p0 = a.partial + c;
@@ -238,7 +236,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const BnFinalizeArgs 
       t0 += red0[i][threadIdx.x & 31];
       t1 += red1[i][threadIdx.x & 31];
     }
-    bn_finalize_channel(a, c, t0, t1, in);   // lbc_bn_tail.h (shared with the convolution epilogues' tail mode)
+    bn_finalize_channel(a, c, t0, t1);   // lbc_bn_tail.h (shared with the convolution epilogues' tail mode)
   }
 }
 // sums (optional) / scsh: [2C] each.  partial = null: the shared partial buffer (conv epilogue / bn_stats rows)
