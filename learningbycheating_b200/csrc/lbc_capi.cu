@@ -134,8 +134,6 @@ int lbc_set_fast_kernels(int enabled) {
   if (enabled & 2048) m &= ~16;
   if (enabled & 4096) m |= 32;    // 4096 / 8192 = ... also for the layers whose channel count is a multiple of 256
   if (enabled & 8192) m &= ~32;
-  if (enabled & 16384) fast::set_bn_tail(true);    // 16384 / 32768 = BatchNorm statistics finalised by the convolution's last CTA on / off
-  if (enabled & 32768) fast::set_bn_tail(false);
   fast::set_pair_mode(m);
   return 0;
 }

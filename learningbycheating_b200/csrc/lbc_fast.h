@@ -132,9 +132,7 @@ bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, co
 // generic-T front ends: only T = bf16 has fast kernels
 template <class T> struct Fast {
   static bool bn_fwd(const T*, int64_t, int, const float*, const float*, float, float, float*, float*, float*, float*,
-                     const T*, bool, bool, T*, float*, float*, lbc_stream_t, int = 0, uint8_t* = nullptr, bool = false) {
-    return false;
-  }
+                     const T*, bool, bool, T*, float*, float*, lbc_stream_t, int = 0, uint8_t* = nullptr) { return false; }
   static bool bn_bwd(const T*, const T*, const T*, const float*, const float*, const float*, float*, float*, T*, int64_t, int,
                      float*, lbc_stream_t, const float* = nullptr, const uint8_t* = nullptr, int = 0) { return false; }
   static bool resid_bn_reduce(T*, const T*, const uint8_t*, const T*, const float*, const float*, const uint8_t*, int64_t, int,
@@ -151,12 +149,9 @@ template <> struct Fast<bf16> {
   // (receives the scale | shift pair of the finalize kernel)
   static bool bn_fwd(const bf16* x, int64_t M, int C, const float* gamma, const float* beta, float eps, float momentum,
                      float* rm, float* rv, float* saved_mean, float* saved_rstd, const bf16* res, bool relu, bool train,
-                     bf16* y, float* sums, float* negshift, lbc_stream_t s, int conv_stat_rows = 0, uint8_t* maskbits = nullptr,
-                     bool finalized = false) {
+                     bf16* y, float* sums, float* negshift, lbc_stream_t s, int conv_stat_rows = 0, uint8_t* maskbits = nullptr) {
     if (!enabled()) return false;
-    // finalized: the producing convolution's last CTA already ran the finalisation (lbc_bn_tail.h): mean / rstd, running
-    // buffers, centring shift and (scale | shift) in `sums` are in place
-    if (train && !finalized) {
+    if (train) {
       // partial rows: written by the producing conv's epilogue (conv_stat_rows > 0), else by a statistics pass over x;
       // then ONE launch: column sums + mean / rstd + running buffers + centring shift + (scale | shift)
       int rows = conv_stat_rows;
@@ -228,7 +223,6 @@ bool stem_unpack_wgrad(const float* dw_col, float* dw_ref, int C, int Kp, lbc_st
 //   16 C_in <= 4, space-to-depth: [B][(H+6)/2][(W+8)/2][2 row parity][2 column parity][4] -- the SAME padded pixels with every
 //      2x2 block contiguous, so the 7x7/s2 convolution is a 4x4/s1 one over 16 channels: 4 window rows of 4 x 16 = 64
 //      elements = 128 bytes per output pixel instead of 7 rows of 64 bytes (the kernels are bound by TMA row requests)
-void set_bn_tail(bool on);   // statistics finalisation by the convolution's last CTA (lbc_bn_tail.h) on / off
 bool stem_s2d();   // LBC_STEM_S2D (default on)
 inline int stem_ch(int C, int W = 0, bool normalize = false) {
   if (C <= 4) return (stem_s2d() && W > 0 && W % 4 == 0 && (C == 3 || !normalize)) ? 16 : 4;

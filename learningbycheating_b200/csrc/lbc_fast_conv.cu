@@ -27,7 +27,6 @@
 #include <tuple>
 
 #include "lbc_fast.h"
-#include "lbc_bn_tail.h"
 
 namespace lbc {
 namespace fast {
@@ -113,7 +112,6 @@ struct ConvGemmParams {
   int split, a_plane, b_plane;
   uint32_t fmt_a, fmt_b;
   float out_scale;                  // accumulator scale applied in the epilogue (undoes the power-of-two operand scaling)
-  BnTail tail;                      // statistics finalisation by the last CTA (lbc_bn_tail.h); enabled = 0: partial rows only
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -577,7 +575,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       asm volatile("bar.sync 1, 128;" ::: "memory");
       float* dst = p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C;
       for (int i = threadIdx.x - 64; i < 2 * p.stat_C; i += 128) dst[i] = cstat[i];
-      bn_tail_run(p.tail, p.stat_partial, threadIdx.x - 64, tmem_slot + 1);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -616,7 +613,6 @@ struct ConvKwParams {
   float* stat_partial;
   int stat_C;
   int valid_n;
-  BnTail tail;
 };
 constexpr int AKW_BYTES = 160 * 128;
 
@@ -870,10 +866,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant
         colstat_accumulate(cs, out_stage, e, nvalid * p.TH * 8);
       }
     }
-    if (p.stat_partial) {
-      colstat_flush(cs, red, e, p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C);
-      bn_tail_run(p.tail, p.stat_partial, e, tmem_slot + 1);
-    }
+    if (p.stat_partial) colstat_flush(cs, red, e, p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C);
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -903,7 +896,6 @@ struct ConvRowParams {
   float* stat_partial;
   int stat_C;
   int valid_n;
-  BnTail tail;
 };
 template <int BN, int STAGES>
 struct SmemPlanRow {
@@ -1171,7 +1163,6 @@ conv_row_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
       asm volatile("bar.sync 1, 128;" ::: "memory");
       float* dst = p.stat_partial + (int64_t)blockIdx.x * 2 * p.stat_C;
       for (int i = e; i < 2 * p.stat_C; i += 128) dst[i] = cstat[i];
-      bn_tail_run(p.tail, p.stat_partial, e, tmem_slot + 1);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -1641,46 +1632,6 @@ static int launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, co
   LBC_CUDA(cudaGetLastError());
   return 2 * clusters;
 }
-// ---- statistics tail (lbc_bn_tail.h): armed by the caller of conv_fwd, attached to the next statistics-emitting launch ----
-static BnFinalizeArgs g_tail_args;
-static bool g_tail_armed = false, g_tail_fired = false;
-static unsigned* tail_counter() {
-  static unsigned* p = [] {
-    void* q = nullptr;
-    if (cudaMalloc(&q, 256) != cudaSuccess) {
-      cudaGetLastError();
-      return (unsigned*)nullptr;
-    }
-    cudaMemset(q, 0, 256);
-    return (unsigned*)q;
-  }();
-  return p;
-}
-static bool g_tail_on = [] {
-  const char* e = getenv("LBC_BN_TAIL");   // 0: always the separate bn_finalize_kernel launch (A/B; lbc_set_fast_kernels 16384 / 32768)
-  return e ? atoi(e) != 0 : true;
-}();
-void set_bn_tail(bool on) { g_tail_on = on; }
-void bn_tail_arm(const BnFinalizeArgs& a) {
-  g_tail_args = a;
-  g_tail_armed = g_tail_on;
-  g_tail_fired = false;
-}
-void bn_tail_disarm() { g_tail_armed = false; }
-bool bn_tail_fired() { return g_tail_fired; }
-bool bn_tail_take(BnTail* out, int C) {
-  out->enabled = 0;
-  if (!g_tail_armed || g_tail_args.C != C) return false;
-  unsigned* ctr = tail_counter();
-  if (!ctr) return false;
-  out->enabled = 1;
-  out->counter = ctr;
-  out->a = g_tail_args;
-  g_tail_armed = false;
-  g_tail_fired = true;
-  return true;
-}
-
 // kernel variants (LBC_PAIR overrides; tests toggle them through lbc_set_fast_kernels):
 //   bit 0: CTA-pair (cta_group::2) kernels for the BN >= 128 conv GEMMs   bit 1: row-of-taps weight gradient
 //   bit 2: CTA-pair variant of the row-of-taps weight gradient (Co % 256 == 0)
@@ -1788,7 +1739,6 @@ static bool try_conv3x3_c64(const bf16* in, const void* wpack, bf16* out, int B,
   p.stat_partial = stat_partial;
   p.stat_C = 64;
   p.valid_n = B;
-  if (stat_partial) bn_tail_take(&p.tail, 64);
   const int tiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
   if (stat_rows) *stat_rows = tiles_total < sm_count() ? tiles_total : sm_count();   // one partial row per persistent CTA
   const int64_t eb = 2;
@@ -1845,7 +1795,6 @@ static int try_conv_row(const bf16* in, const void* wpack, bf16* out, int B, int
   p.stat_partial = stat_partial;
   p.stat_C = Cout;
   p.valid_n = B;
-  if (stat_partial) bn_tail_take(&p.tail, Cout);
   const int64_t eb = 2;
   CUtensorMap mA = make_map_4d(in, Cin, W, H, B, Cin * eb, (int64_t)W * Cin * eb, (int64_t)H * W * Cin * eb, 10, TH, TN);
   CUtensorMap mB = make_map_2d(wpack, (int64_t)9 * Cin, Cout, BN / 2);
@@ -2044,7 +1993,6 @@ static bool conv_fwd_impl(const ConvL& c, const void* x, const void* wpack, void
   p.stat_partial = (m.out_f32 || c.Co > 512) ? nullptr : stat_partial;   // (the per-CTA accumulator holds 2 x 512 floats)
   p.stat_C = c.Co;
   p.valid_n = B;
-  if (p.stat_partial) bn_tail_take(&p.tail, c.Co);
   apply_mode(p, m, c.Ci, c.Ci);
   CUtensorMap mA[4];
   const int64_t eb = 2;
@@ -2847,13 +2795,7 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
   p.out = wgrad3_partials((int64_t)p.splits * wsize);
   if (!p.out) return false;
   const int grid = p.splits * out_tiles;   // pair: consecutive blocks (2c, 2c+1) form the cluster of co tiles (2c', 2c'+1)
-  static const int pair_stages = [] {
-    const char* e = getenv("LBC_W3_STAGES");   // 4: 160 KB instead of 200 KB of shared memory (room for co-resident BatchNorm blocks)
-    return e ? atoi(e) : 5;
-  }();
-  if (pair && pair_stages == 4)
-    launch_wgrad3<4, true>(mDY, mX, p, grid, s);
-  else if (pair)
+  if (pair)
     launch_wgrad3<5, true>(mDY, mX, p, grid, s);
   else
     launch_wgrad3<3, false>(mDY, mX, p, grid, s);
@@ -3112,7 +3054,6 @@ bool conv_wgrad_tc(const ConvL& c, const float* x, const void* x16, const float*
 }
 
 #else   // LBC_HOST_EMU: no tensor cores on the host; the executor runs the correctness-first kernels
-void set_bn_tail(bool) {}
 bool conv_fwd_bf16(const ConvL&, const bf16*, bf16*, int, const float*, lbc_stream_t, float*, int*) { return false; }
 bool conv_dgrad_bf16(const ConvL&, const bf16*, bf16*, int, const float*, bool, lbc_stream_t) { return false; }
 bool conv_wgrad_bf16(const ConvL&, const bf16*, const bf16*, float*, int, float*, int64_t, lbc_stream_t) { return false; }

@@ -6,7 +6,6 @@
 // per channel per block.  Reference ops: nn.BatchNorm2d in train mode + nn.ReLU(inplace) + residual add
 // (resnet.py:31-53, image.py:38-46) and their autograd backward (SURVEY.md 9.1 closed forms).
 #include "lbc_fast.h"
-#include "lbc_bn_tail.h"
 
 #ifndef LBC_HOST_EMU
 #include <cuda_bf16.h>
@@ -181,8 +180,6 @@ static float* partial_buffer() {
 }
 int64_t stat_partial_capacity() { return kPartialFloats; }
 static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_stream_t s) {
-  static const int skip = getenv("LBC_EXPERIMENT_SKIP_FINALIZE") ? atoi(getenv("LBC_EXPERIMENT_SKIP_FINALIZE")) : 0;   // timing experiment only (bit 1): results are garbage
-  if (skip & 2) return;
   int rb = P / 512;          // >= 512 rows per block (16 per thread) before splitting
   if (rb > 32) rb = 32;
   if (rb < 1) rb = 1;
@@ -199,6 +196,21 @@ static void col_finalize(const float* partial, int P, int C2, float* sums, lbc_s
 // Round 1 left the finalisation to the PROLOGUE of bn_apply_kernel: every one of its 303 K threads redid the double-
 // precision mean / variance / rsqrt for its eight channels, a ~13 us floor per launch that dominated the layer-3/4
 // tensors (20 us per launch for 31 MB).  One block per 32 channels, 1024 threads = 32 channels x 32 row lanes.
+struct BnFinalizeArgs {
+  const float* partial;   // [P][2C]
+  int P, C;
+  double inv_m, unbias;   // 1 / M and M / (M - 1)
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  float* saved_mean;
+  float* saved_rstd;
+  float* negshift;        // may be null
+  float* scsh;            // out: [2C] = scale | shift
+  float* sums;            // out (optional): [2C] raw column sums
+};
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const BnFinalizeArgs a) {
   pdl_wait();
   pdl_trigger();
@@ -236,7 +248,31 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const BnFinalizeArgs 
       t0 += red0[i][threadIdx.x & 31];
       t1 += red1[i][threadIdx.x & 31];
     }
-    bn_finalize_channel(a, c, t0, t1);   // lbc_bn_tail.h (shared with the convolution epilogues' tail mode)
+    if (a.sums) {
+      a.sums[c] = t0;
+      a.sums[a.C + c] = t1;
+    }
+    // double only where it matters (sum / M and the E[x^2] - mean^2 cancellation), with multiplications by host-computed
+    // reciprocals; 1/sqrt = float rsqrt + one Newton step in double (the software double division / square root sequences
+    // made this kernel 3 us slower than the plain column sum it replaced)
+    const double m = (double)t0 * a.inv_m;
+    double var = (double)t1 * a.inv_m - m * m;
+    if (var < 0.0) var = 0.0;
+    const double v = var + (double)a.eps;
+    double r = (double)rsqrtf((float)v);
+    r = r * (1.5 - 0.5 * v * r * r);
+    const float mean = (float)m;
+    const float rstd = (float)r;
+    a.saved_mean[c] = mean;
+    a.saved_rstd[c] = rstd;
+    const float true_mean = a.negshift ? (float)(m - (double)a.negshift[c]) : mean;
+    if (a.negshift) a.negshift[c] = -true_mean;   // centring estimate for the next forward pass
+    a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * true_mean;
+    const double unb = var * a.unbias;
+    a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unb;
+    const float sc = a.gamma[c] * rstd;
+    a.scsh[c] = sc;
+    a.scsh[a.C + c] = a.beta[c] - mean * sc;
   }
 }
 // sums (optional) / scsh: [2C] each.  partial = null: the shared partial buffer (conv epilogue / bn_stats rows)
@@ -262,8 +298,6 @@ bool bn_finalize_bf16(const float* partial, int rows, int C, int64_t M, const fl
   a.negshift = negshift;
   a.scsh = scsh;
   a.sums = sums;
-  static const int skip = getenv("LBC_EXPERIMENT_SKIP_FINALIZE") ? atoi(getenv("LBC_EXPERIMENT_SKIP_FINALIZE")) : 0;   // timing experiment only (bit 0): results are garbage
-  if (skip & 1) return true;
   { auto k_ = bn_finalize_kernel; LBC_LAUNCH(k_, dim3((C + 31) / 32), dim3(1024), 0, s, a); }
   LBC_LAUNCHED("bn_finalize_kernel");
   LBC_CUDA(cudaGetLastError());
@@ -575,12 +609,6 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
   RowGeom g = row_geom(M, C, 4);
   float* part = partial_buffer();
   if (!part) return false;
-  static const bool skip_own = getenv("LBC_EXPERIMENT_SKIP_OWNREDUCE") != nullptr;   // timing experiment only: what fusing this pass away would buy
-  if (beta_own && skip_own) {
-    { auto k_ = bn_bwd_apply_kernel<true>; LBC_LAUNCH(k_, dim3(g.grid), dim3(g.threads), 0, s, (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, gamma, sums, dgamma, dbeta, (uint4*)dx, M, g.tpr, g.rpi, C, beta_own, nullptr); }
-    LBC_LAUNCHED("bn_bwd_apply_kernel<own>");
-    return true;
-  }
   if (beta_own) {
     RowGeom g3 = row_geom(M, C, 3);
     { auto k_ = bn_bwd_reduce_kernel<true>; LBC_LAUNCH(k_, dim3(g3.grid), dim3(g3.threads), g3.threads * 16 * sizeof(float), s,  (const uint4*)dy, (const uint4*)mask_act, (const uint4*)x, mean, rstd, M, g3.tpr, g3.rpi, part, C, gamma, beta_own, nullptr, nullptr, nullptr, nullptr); }

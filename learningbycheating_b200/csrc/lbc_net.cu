@@ -2,7 +2,6 @@
 // BirdViewPolicyModelSS('resnet18') and runs forward / backward over NHWC activations in HBM.
 // Reference call stack being replaced: SURVEY.md 3.3 (image.py:64-89, resnet.py:148-159,38-54).
 #include "lbc_net.h"
-#include "lbc_bn_tail.h"
 
 #include <algorithm>
 #include <type_traits>
@@ -740,13 +739,9 @@ class Net : public NetBase {
   // returns true when the per-channel centring shift `negshift` was added to the stored output (fast path only)
   // stat_rows != null: ask the fast kernel to also emit the BatchNorm statistics partials of its output
   // (*stat_rows = number of partial rows, 0 when not emitted)
-  // tail_bn != null (with stat_rows): ask the kernel's last CTA to finalise that BatchNorm's statistics as well
-  // (lbc_bn_tail.h); conv_finalized tells the bn_forward call that follows whether it happened
-  bool conv_finalized = false;
   bool conv_forward(const ConvL& c, const T* x, T* y, int B, lbc_stream_t s, const float* negshift = nullptr,
-                    int* stat_rows = nullptr, bool x_is_grad = false, const BNL* tail_bn = nullptr) {
+                    int* stat_rows = nullptr, bool x_is_grad = false) {
     ProfScope ps("conv_fwd", s, conv_flops(c, B), 0);
-    conv_finalized = false;
     if (stat_rows) *stat_rows = 0;
     float* part = (stat_rows && cur_train && (int64_t)c.Co * 2 * ((int64_t)B * c.OH * c.OW / 128 + 64) <= fast::stat_partial_capacity())
                       ? fast::stat_partial_buffer()
@@ -758,38 +753,7 @@ class Net : public NetBase {
                 "PREC_F32TC: tensor-core convolution unavailable for this layer");
       return false;
     }
-#ifndef LBC_HOST_EMU
-    if (tail_bn && part && std::is_same<T, bf16>::value) {
-      const int64_t M = (int64_t)B * c.OH * c.OW;
-      fast::BnFinalizeArgs a;
-      memset(&a, 0, sizeof(a));
-      a.C = tail_bn->C;
-      a.inv_m = 1.0 / (double)M;
-      a.unbias = (double)M / (double)(M > 1 ? M - 1 : 1);
-      a.gamma = P + tail_bn->g_off;
-      a.beta = P + tail_bn->b_off;
-      a.eps = kBnEps;
-      a.momentum = kBnMomentum;
-      a.running_mean = BUF + tail_bn->rm_off;
-      a.running_var = BUF + tail_bn->rv_off;
-      a.saved_mean = tail_bn->mean;
-      a.saved_rstd = tail_bn->rstd;
-      a.negshift = negshift ? tail_bn->negshift : nullptr;
-      a.scsh = bn_sums;
-      a.sums = nullptr;
-      fast::bn_tail_arm(a);
-    }
-#else
-    (void)tail_bn;
-#endif
-    const bool fast_ok = fast::conv_fwd<T>(c, x, y, B, s, negshift, part, &rows);
-#ifndef LBC_HOST_EMU
-    if (tail_bn && part && std::is_same<T, bf16>::value) {
-      conv_finalized = fast_ok && fast::bn_tail_fired();
-      fast::bn_tail_disarm();
-    }
-#endif
-    if (fast_ok) {
+    if (fast::conv_fwd<T>(c, x, y, B, s, negshift, part, &rows)) {
       if (stat_rows && part) *stat_rows = rows;
       return negshift != nullptr;
     }
@@ -810,8 +774,6 @@ class Net : public NetBase {
   }
   // x_is_grad: the conv-role x is a gradient and dy an activation (weight gradient of a ConvTranspose2d)
   void conv_backward_weight(const ConvL& c, const T* x, const T* dy, int B, lbc_stream_t s, bool x_is_grad = false) {
-    static const bool skip = getenv("LBC_EXPERIMENT_SKIP_WGRAD") != nullptr;   // timing experiment only: no weight gradients
-    if (skip) return;
     ProfScope ps("conv_wgrad", s, conv_flops(c, B), 0);
     if (tc) {
       (void)x_is_grad;   // either way one operand is a gradient: bf16 planes for both
@@ -824,12 +786,12 @@ class Net : public NetBase {
     ref::conv_wgrad<T>(s, x, dy, G + c.w_off, B, c.H, c.W, c.Ci, c.Co, c.K, c.stride, c.pad, c.OH, c.OW, ws_f, ws_f_n);
   }
   void bn_forward(BNL& bn, const T* x, int64_t M, const T* residual, bool relu, T* y, bool train, lbc_stream_t s,
-                  bool shifted = false, int conv_stat_rows = 0, uint8_t* maskbits = nullptr, bool finalized = false) {
+                  bool shifted = false, int conv_stat_rows = 0, uint8_t* maskbits = nullptr) {
     // algorithmic bytes: stats read (train) + apply read (+residual) + write
     ProfScope ps("bn_fwd", s, 0, (double)M * bn.C * sizeof(T) * ((train && conv_stat_rows == 0 ? 1 : 0) + 2 + (residual ? 1 : 0)));
     if (fast::Fast<T>::bn_fwd(x, M, bn.C, P + bn.g_off, P + bn.b_off, kBnEps, kBnMomentum, BUF + bn.rm_off, BUF + bn.rv_off,
                               bn.mean, bn.rstd, residual, relu, train, y, bn_sums, shifted ? bn.negshift : nullptr, s,
-                              conv_stat_rows, maskbits, finalized && conv_stat_rows > 0)) {
+                              conv_stat_rows, maskbits)) {
       mask_bits_valid = maskbits != nullptr;
       return;
     }
@@ -1001,17 +963,16 @@ class Net : public NetBase {
       int64_t M = (int64_t)B * b.Hout * b.Wout;
       // each conv's statistics partials live in ONE shared scratch: finalise (inside bn_forward) before the next conv
       int sr = 0;
-      // (train: the convolution's last CTA also finalises the statistics of the BatchNorm it feeds, lbc_bn_tail.h)
-      bool sh1 = conv_forward(b.c1, b.xin, b.r1, B, s, b.b1.negshift, &sr, false, train ? &b.b1 : nullptr);
-      bn_forward(b.b1, b.r1, M, nullptr, true, b.a1, train, s, sh1, sr, nullptr, conv_finalized);
+      bool sh1 = conv_forward(b.c1, b.xin, b.r1, B, s, b.b1.negshift, &sr);
+      bn_forward(b.b1, b.r1, M, nullptr, true, b.a1, train, s, sh1, sr);
       const T* identity = b.xin;
       if (b.ds) {
-        bool shd = conv_forward(b.cd, b.xin, b.rd, B, s, b.bd.negshift, &sr, false, train ? &b.bd : nullptr);
-        bn_forward(b.bd, b.rd, M, nullptr, false, b.idn, train, s, shd, sr, nullptr, conv_finalized);
+        bool shd = conv_forward(b.cd, b.xin, b.rd, B, s, b.bd.negshift, &sr);
+        bn_forward(b.bd, b.rd, M, nullptr, false, b.idn, train, s, shd, sr);
         identity = b.idn;
       }
-      bool sh2 = conv_forward(b.c2, b.a1, b.r2, B, s, b.b2.negshift, &sr, false, train ? &b.b2 : nullptr);
-      bn_forward(b.b2, b.r2, M, identity, true, b.out, train, s, sh2, sr, train ? b.obits : nullptr, conv_finalized);
+      bool sh2 = conv_forward(b.c2, b.a1, b.r2, B, s, b.b2.negshift, &sr);
+      bn_forward(b.b2, b.r2, M, identity, true, b.out, train, s, sh2, sr, train ? b.obits : nullptr);
       b.obits_ok = mask_bits_valid;
     }
     // late fusion of speed (image.py:77-79)

@@ -216,7 +216,7 @@ def _variant_default():
     import os
     m = int(os.environ.get("LBC_PAIR", "63") or 0)
     return ((4 if m & 1 else 8) | (16 if m & 2 else 32) | (64 if m & 4 else 128) | (1024 if m & 16 else 2048) |
-            (4096 if m & 32 else 8192) | (16384 if int(os.environ.get("LBC_BN_TAIL", "1") or 0) else 32768))
+            (4096 if m & 32 else 8192))
 
 
 def _expected_conv_kernels(case, variant):
