@@ -179,6 +179,10 @@ int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mod
 int lbc_op_resid_bn_bwd(float* dst, const float* src, const float* act, const float* x, const float* act_prev,
                         const float* gamma, float* dgamma, float* dbeta, float* dx, int64_t M, int C, int precision,
                         void* stream);
+/* dst [M][Cd] = src [M][0:min(Cs, Cd)], channels Cs.. filled with fill[m / rows_per_fill]: the late fusion of the speed
+ * (image.py:77-79: Cd = 640, Cs = 512, fill = speed) and, with Cd < Cs and fill = NULL, the slice of its backward */
+int lbc_op_copy_channels(const float* src, float* dst, int64_t M, int Cd, int Cs, const float* fill, int rows_per_fill,
+                         int precision, void* stream);
 int lbc_op_maxpool(const float* x, float* y, const float* dy, float* dx, int N, int H, int W, int C, void* stream);
 int lbc_op_bn_relu_maxpool(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                            float* y, const float* dy, float* dx, int N, int H, int W, int C, int precision, void* stream);

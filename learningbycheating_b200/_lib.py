@@ -30,6 +30,7 @@ def _declare(lib):
         "lbc_build_info": (ctypes.c_char_p, []),
         "lbc_set_fast_kernels": (i, [i]),
         "lbc_set_schedule": (i, [i, i]),
+        "lbc_op_copy_channels": (i, [vp, vp, i64, i, i, vp, i, i, vp]),
         "lbc_stem_layout": (i, [i, i, i]),
         "lbc_kernel_launch_count": (ctypes.c_longlong, []),
         "lbc_prof_enable": (i, [i]),

@@ -668,6 +668,33 @@ int lbc_op_ew(float* dst, const float* src, const float* act, int64_t n, int mod
     sync_stream(s);
   });
 }
+int lbc_op_copy_channels(const float* src, float* dst, int64_t M, int Cd, int Cs, const float* fill, int rows_per_fill,
+                         int precision, void* stream) {
+  return guarded([&] {
+    require_device();
+    lbc_stream_t s = S(stream);
+    LBC_CHECK(Cd <= Cs || (fill && rows_per_fill >= 1), "lbc_op_copy_channels: Cd > Cs needs a fill vector");
+    LBC_CHECK(Cd <= Cs || (Cs == 512 && Cd == 640), "lbc_op_copy_channels: widening is the 512 + 128 speed fusion");
+    Tmp t;
+    if (precision == PREC_F32) {
+      if (Cd > Cs)
+        ref::concat_speed<float>(s, src, fill, dst, (int)(M / rows_per_fill), rows_per_fill, Cs, Cd - Cs);
+      else
+        ref::slice_channels<float>(s, src, dst, M, Cs, Cd);
+    } else {
+      bf16 *sb = t.get<bf16>(M * Cs), *db = t.get<bf16>(M * Cd);
+      ref::cast<float, bf16>(s, src, sb, M * Cs);
+      if (!fast::copy_channels<bf16>(db, sb, M, Cd, Cs, fill, rows_per_fill, s)) {
+        if (Cd > Cs)
+          ref::concat_speed<bf16>(s, sb, fill, db, (int)(M / rows_per_fill), rows_per_fill, Cs, Cd - Cs);
+        else
+          ref::slice_channels<bf16>(s, sb, db, M, Cs, Cd);
+      }
+      ref::cast<bf16, float>(s, db, dst, M * Cd);
+    }
+    sync_stream(s);
+  });
+}
 int lbc_op_maxpool(const float* x, float* y, const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
   return guarded([&] {
     require_device();

@@ -123,6 +123,18 @@ bool bn_bwd_bf16(const bf16* dy, const bf16* mask_act, const bf16* x, const floa
 bool resid_bn_reduce_bf16(bf16* dst, const bf16* src, const uint8_t* src_bits, const bf16* x, const float* mean, const float* rstd,
                           const uint8_t* mask_bits, int64_t M, int C, int* rows, lbc_stream_t s);
 bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, lbc_stream_t s, const uint8_t* mask_bits = nullptr);
+// dst [M][Cd] = src [M][0:min(Cs, Cd)], channels beyond Cs = fill[m / rows_per_fill] (speed fusion forward / its slice backward)
+bool copy_channels_bf16(bf16* dst, const bf16* src, int64_t M, int Cd, int Cs, const float* fill, int rows_per_fill, lbc_stream_t s);
+template <class T>
+inline bool copy_channels(T*, const T*, int64_t, int, int, const float*, int, lbc_stream_t) {
+  return false;
+}
+template <>
+inline bool copy_channels<bf16>(bf16* dst, const bf16* src, int64_t M, int Cd, int Cs, const float* fill, int rows_per_fill,
+                                lbc_stream_t s) {
+  if (!enabled()) return false;
+  return copy_channels_bf16(dst, src, M, Cd, Cs, fill, rows_per_fill, s);
+}
 bool bn_relu_maxpool_bf16(const bf16* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           bf16* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, lbc_stream_t s);
 bool maxpool_relu_bwd_bf16(const bf16* dy, const uint8_t* idx, const bf16* x, const float* mean, const float* rstd,

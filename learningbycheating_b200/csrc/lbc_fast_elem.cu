@@ -686,6 +686,40 @@ bool ew_bf16(bf16* dst, const bf16* src, const bf16* act, int64_t n, int mode, l
   return true;
 }
 
+// dst[m, 0:Cd] = src[m, 0:min(Cs, Cd)], channels beyond Cs filled with fill[m / rows_per_fill] (bf16-rounded): the late
+// fusion of the speed (image.py:77-79: 512 trunk channels + 128 copies of the speed) and, with Cd < Cs, the slice that drops
+// those channels again in backward.  One 16-byte vector per thread (the one-element-per-thread par_for versions took 42 and
+// 34 us for 20 MB).
+__global__ void __launch_bounds__(256) copy_channels_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, int64_t M,
+                                                            int cd8, int cs8, const float* __restrict__ fill, int rows_per_fill) {
+  pdl_wait();
+  pdl_trigger();
+  const int64_t n = M * cd8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / cd8;
+    const int j = (int)(i - m * cd8);
+    if (j < cs8) {
+      dst[i] = ldg_stream(src + m * cs8 + j);
+    } else {
+      float f[8];
+      const float v = __ldg(fill + m / rows_per_fill);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = v;
+      dst[i] = pack8(f);
+    }
+  }
+}
+bool copy_channels_bf16(bf16* dst, const bf16* src, int64_t M, int Cd, int Cs, const float* fill, int rows_per_fill, lbc_stream_t s) {
+  if ((Cd % 8) || (Cs % 8) || (Cd > Cs && !fill) || rows_per_fill < 1) return false;
+  const int64_t n = M * (Cd / 8);
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count2() * 16;
+  if (blocks > cap) blocks = cap;
+  { auto k_ = copy_channels_kernel; LBC_LAUNCH(k_, dim3((unsigned)blocks), dim3(256), 0, s, (uint4*)dst, (const uint4*)src, M, Cd / 8, Cs / 8, fill, rows_per_fill); }
+  LBC_LAUNCHED("copy_channels_kernel");
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------- stem BN+ReLU+MaxPool
 // pool[n,oh,ow,:] = max over the 3x3/s2/p1 window of relu(bn(x)); idx = kh*3+kw of the first maximum.
 // (resnet.py:150-152).  One thread per (output position, 8 channels); the BN+ReLU activation is never written.
@@ -897,6 +931,7 @@ bool bn_bwd_bf16(const bf16*, const bf16*, const bf16*, const float*, const floa
 bool resid_bn_reduce_bf16(bf16*, const bf16*, const uint8_t*, const bf16*, const float*, const float*, const uint8_t*, int64_t, int,
                           int*, lbc_stream_t) { return false; }
 bool ew_bf16(bf16*, const bf16*, const bf16*, int64_t, int, lbc_stream_t, const uint8_t*) { return false; }
+bool copy_channels_bf16(bf16*, const bf16*, int64_t, int, int, const float*, int, lbc_stream_t) { return false; }
 float* stat_partial_buffer() { return nullptr; }
 int64_t stat_partial_capacity() { return 0; }
 bool bn_finalize_bf16(const float*, int, int, int64_t, const float*, const float*, float, float, float*, float*, float*, float*,

@@ -885,8 +885,25 @@ class Net : public NetBase {
     LBC_CHECK(!train || B * head_h * head_w > 1, "train-mode BatchNorm needs more than one value per channel");
     cur_B = B;
     cur_train = train;
+    // the weight operands of the residual blocks / decoder are packed on the side stream while the stem runs (the stem has its
+    // own small pack): 0.15 ms of gather traffic next to 0.65 ms of TMA- and HBM-bound stem kernels
+    bool pack_on_side = false;
     if (!skip_pack) {
-      pack_weights(s);
+#ifndef LBC_HOST_EMU
+      static const bool side_ok = [] {
+        const char* e = getenv("LBC_PACK_SIDE");   // 0: pack on the caller's stream (A/B)
+        return e ? atoi(e) != 0 : true;
+      }();
+      pack_on_side = side_ok && ovl_capable && g_wgrad_overlap > 0 && !g_prof_on && std::is_same<T, bf16>::value && stem_x4 &&
+                     fast::enabled();
+      if (pack_on_side) {
+        LBC_CUDA(cudaEventRecord(ev_ready, s));                  // after the optimizer step that wrote the parameters
+        LBC_CUDA(cudaStreamWaitEvent(side_stream, ev_ready, 0));
+        pack_weights(side_stream);
+        LBC_CUDA(cudaEventRecord(ev_join, side_stream));
+      } else
+#endif
+        pack_weights(s);
       packs_current = false;   // (whoever updates the parameters next does not tell the engine)
     }
     dev_copy(onehot_saved, onehot, sizeof(float) * B * 4, s);
@@ -958,6 +975,11 @@ class Net : public NetBase {
         ref::maxpool_fwd<T>(s, a_stem, pool, pool_idx, B, stem_oh, stem_ow, 64, pool_h, pool_w);
       }
     }
+#ifndef LBC_HOST_EMU
+    if (pack_on_side) LBC_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
+#else
+    (void)pack_on_side;
+#endif
     // residual blocks
     for (Block& b : blocks) {
       int64_t M = (int64_t)B * b.Hout * b.Wout;
@@ -978,7 +1000,8 @@ class Net : public NetBase {
     // late fusion of speed (image.py:77-79)
     const T* trunk = blocks.back().out;
     int hw = trunk_h * trunk_w;
-    ref::concat_speed<T>(s, trunk, speed, dec_in[0], B, hw, 512, 128);
+    if (!fast::copy_channels<T>(dec_in[0], trunk, (int64_t)B * hw, 640, 512, speed, hw, s))
+      ref::concat_speed<T>(s, trunk, speed, dec_in[0], B, hw, 512, 128);
     // decoder: BN -> deconv(+bias) -> ReLU
     int h = trunk_h, w = trunk_w;
     for (int i = 0; i < 3; ++i) {
@@ -1094,7 +1117,8 @@ class Net : public NetBase {
     }
     mark_bucket(0, s);
     // drop the 128 speed channels (no gradient path to a parameter through them)
-    ref::slice_channels<T>(s, gcur, wr(gnext, s), (int64_t)B * trunk_h * trunk_w, 640, 512);
+    if (!fast::copy_channels<T>(wr(gnext, s), gcur, (int64_t)B * trunk_h * trunk_w, 512, 640, nullptr, 1, s))
+      ref::slice_channels<T>(s, gcur, gnext, (int64_t)B * trunk_h * trunk_w, 640, 512);
     std::swap(gcur, gnext);
     // residual blocks in reverse
     int pending_rows = 0;   // partial rows of the NEXT bn2 backward, when its reduce pass was fused into the residual add

@@ -227,6 +227,38 @@ def test_masked_add_kernel_gpu(backend):
     _ew_case("cuda", 1, use_bits=True)
 
 
+# ------------------------------------------------------------------ speed fusion (image.py:77-79) and its slice in backward
+def _copy_channels_case(dev, precision):
+    _lib = _L()
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(13)
+    N, HW = 5, 60
+    trunk = _r(torch.randn(N * HW, 512, generator=g), precision)
+    speed = torch.rand(N, generator=g) * 10
+    wide = torch.empty(N * HW, 640)
+    wd = wide.to(dev)
+    with Traced(dev, ["copy_channels_kernel"] if precision == 1 else [], REF_TAGS if precision == 1 else ()):
+        _lib.check(L.lbc_op_copy_channels(_lib.ptr(trunk.to(dev)), _lib.ptr(wd), N * HW, 640, 512, _lib.ptr(speed.to(dev)), HW,
+                                          precision, None))
+    ref = torch.cat([trunk, _r(speed, precision).repeat_interleave(HW)[:, None].expand(-1, 128)], 1)
+    assert torch.equal(wd.cpu(), ref)
+    gwide = _r(torch.randn(N * HW, 640, generator=g), precision)
+    nd = torch.empty(N * HW, 512).to(dev)
+    with Traced(dev, ["copy_channels_kernel"] if precision == 1 else [], REF_TAGS if precision == 1 else ()):
+        _lib.check(L.lbc_op_copy_channels(_lib.ptr(gwide.to(dev)), _lib.ptr(nd), N * HW, 512, 640, None, 1, precision, None))
+    assert torch.equal(nd.cpu(), gwide[:, :512])
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_copy_channels_cpu(backend, precision):
+    _copy_channels_case(backend, precision)
+
+
+@pytest.mark.gpu
+def test_copy_channels_kernel_gpu(backend):
+    _copy_channels_case("cuda", 1)
+
+
 # ------------------------------------------------------------------ residual add fused with the next BatchNorm's reduce pass
 def _resid_bn_case(dev, M, C, precision):
     """dst += src * (act > 0); BatchNorm backward of dst * (act_prev > 0) wrt x  (the d(out) chain between two BasicBlocks)"""
