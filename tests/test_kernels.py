@@ -235,17 +235,15 @@ def _copy_channels_case(dev, precision):
     N, HW = 5, 60
     trunk = _r(torch.randn(N * HW, 512, generator=g), precision)
     speed = torch.rand(N, generator=g) * 10
-    wide = torch.empty(N * HW, 640)
-    wd = wide.to(dev)
+    wd, td, sd = torch.empty(N * HW, 640).to(dev), trunk.to(dev), speed.to(dev)   # (named: the pointers must stay alive)
     with Traced(dev, ["copy_channels_kernel"] if precision == 1 else [], REF_TAGS if precision == 1 else ()):
-        _lib.check(L.lbc_op_copy_channels(_lib.ptr(trunk.to(dev)), _lib.ptr(wd), N * HW, 640, 512, _lib.ptr(speed.to(dev)), HW,
-                                          precision, None))
+        _lib.check(L.lbc_op_copy_channels(_lib.ptr(td), _lib.ptr(wd), N * HW, 640, 512, _lib.ptr(sd), HW, precision, None))
     ref = torch.cat([trunk, _r(speed, precision).repeat_interleave(HW)[:, None].expand(-1, 128)], 1)
     assert torch.equal(wd.cpu(), ref)
     gwide = _r(torch.randn(N * HW, 640, generator=g), precision)
-    nd = torch.empty(N * HW, 512).to(dev)
+    nd, gd = torch.empty(N * HW, 512).to(dev), gwide.to(dev)
     with Traced(dev, ["copy_channels_kernel"] if precision == 1 else [], REF_TAGS if precision == 1 else ()):
-        _lib.check(L.lbc_op_copy_channels(_lib.ptr(gwide.to(dev)), _lib.ptr(nd), N * HW, 512, 640, None, 1, precision, None))
+        _lib.check(L.lbc_op_copy_channels(_lib.ptr(gd), _lib.ptr(nd), N * HW, 512, 640, None, 1, precision, None))
     assert torch.equal(nd.cpu(), gwide[:, :512])
 
 
