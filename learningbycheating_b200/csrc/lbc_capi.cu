@@ -134,6 +134,8 @@ int lbc_set_fast_kernels(int enabled) {
   if (enabled & 2048) m &= ~16;
   if (enabled & 4096) m |= 32;    // 4096 / 8192 = ... also for the layers whose channel count is a multiple of 256
   if (enabled & 8192) m &= ~32;
+  if (enabled & 16384) m |= 64;    // 16384 / 32768 = all-nine-taps weight gradient of the 64 -> 64 3x3 convolutions on / off
+  if (enabled & 32768) m &= ~64;
   fast::set_pair_mode(m);
   return 0;
 }

@@ -1636,6 +1636,7 @@ static int launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, co
 //   bit 0: CTA-pair (cta_group::2) kernels for the BN >= 128 conv GEMMs   bit 1: row-of-taps weight gradient
 //   bit 2: CTA-pair variant of the row-of-taps weight gradient (Co % 256 == 0)
 //   bit 3: space-to-depth operand layout of the RGB stem (lbc_fast.h: stem_ch)
+//   bit 6: all-nine-taps weight gradient of the 64 -> 64 3x3 convolutions (try_wgrad9)
 //   bit 4 / 5: shared-row CTA-pair kernel for the 3x3/s1 convolutions of the 128-channel / 256-channel layers (try_conv_row;
 //   same-box A/B at B = 256: 13.79 -> 13.56 -> 13.36 ms per step, profiles/r2_ab_rowk_schedule.md)
 // Bits 0-2 validated on the B200 (parity tests green, 16.61 -> 15.87 ms per step at B = 256), hence on by default.
@@ -2364,6 +2365,176 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------- 3x3/s1 weight gradient, 64 -> 64 channels
+// Layer 1 (and the teacher's): dW[co][tap][ci] for Co = Ci = 64.  wgrad_gemm_kernel's swap mode gives every CTA one PAIR of
+// taps and streams 48 KB of operands per 384 MMA cycles -- 125 B/clk against the ~68 B/clk an SM ingests, so it runs at 36-39 %
+// tensor pipe (87 us for 72.5 GFLOP).  Here ONE CTA owns all nine taps for its share of the pixels:
+//   * per K step of 128 output pixels (8 columns x TH rows x TN images) it loads the dy tile (16 KB) and ONE x box with a
+//     halo, {64 ch, 8+2, TH+2, TN} (25 KB): 41 KB for all nine taps = 24 B/clk;
+//   * x is the MN-major A operand (a pixel is one 128-byte row of 64 channels).  Tap (dh, dw) is the same box read from row
+//     (dh+1)*10 + (dw+1) on, with 8-pixel K groups 1280 B apart (one image row of the tile); an MMA covers 16 pixels = two
+//     image rows of one image, so every MMA gets its own start address and the image boundary never falls inside one;
+//   * M = 128 = TWO taps x 64 input channels: the second 64-row block of the A descriptor starts LBO bytes after the first,
+//     and LBO is simply the address distance of the two taps in the box (128 B for (dw, dw+1), 1024 B for tap 2 -> tap 3);
+//     five tap pairs (the ninth tap is paired with a dummy whose rows are dropped) -> five TMEM accumulators of 64 columns.
+// Split-K: one CTA per SM, partials [split][Co][9][Ci] with plain stores, summed by wgrad3_reduce_kernel.
+struct Wgrad9Params {
+  int TH, TN, tiles_w, tiles_h, tiles_n;
+  int k_tiles, k_per_split;
+  float* out;   // [splits][64][9][64] fp32 partials
+};
+template <int STAGES>
+struct Wgrad9Smem {
+  static constexpr int DY_BYTES = A_BYTES;          // 128 pixels x 64 co
+  static constexpr int X_BYTES = 26 * 1024;         // {64, 10, TH+2, TN}: <= 200 rows of 128 B (+ slack for the dummy tap)
+  static constexpr int STAGE_BYTES = DY_BYTES + X_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_sbo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // distance between 64-element MN blocks
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // distance between 8-row K groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+wgrad9_c64_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant__ CUtensorMap mX, const Wgrad9Params p) {
+  typedef Wgrad9Smem<STAGES> SP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + SP::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 512;   // five accumulators of 64 columns
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched shared / tensor memory only
+  pdl_trigger();
+
+  const int split = blockIdx.x;
+  const int kt0 = split * p.k_per_split;
+  int kt1 = kt0 + p.k_per_split;
+  if (kt1 > p.k_tiles) kt1 = p.k_tiles;
+  const int n_k = kt1 > kt0 ? kt1 - kt0 : 0;
+  const uint32_t x_bytes = (uint32_t)(10 * (p.TH + 2) * p.TN * 128);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        const int w0 = (kt % p.tiles_w) * 8;
+        const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (kt / (p.tiles_w * p.tiles_h)) * p.TN;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * SP::STAGE_BYTES;
+        mbar_expect_tx(&full[stage], SP::DY_BYTES + x_bytes);
+        tma_load_4d(&mDY, sa, &full[stage], 0, w0, h0, n0);
+        tma_load_4d(&mX, sa + SP::DY_BYTES, &full[stage], 0, w0 - 1, h0 - 1, n0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // D = f32, A (x) and B (dy) bf16, both MN-major (bits 15, 16), N = 64, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    const int half_th = p.TH >> 1;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < n_k; ++k) {
+      mbar_wait(&full[stage], phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t sdy = smem_u32(smem + stage * SP::STAGE_BYTES);
+        const uint32_t sx = sdy + SP::DY_BYTES;
+#pragma unroll 1
+        for (int kk = 0; kk < 8; ++kk) {   // 16 pixels = two image rows (2 * rp, 2 * rp + 1) of image ni of the tile
+          const int ni = kk / half_th, rp = kk - ni * half_th;
+          const uint64_t bd = umma_desc_mn_sw128_sbo(sdy + kk * 2048, A_BYTES, 1024);
+          const uint32_t xrow0 = (uint32_t)((ni * (p.TH + 2) + 2 * rp) * 10);   // box row of (image row 2*rp - 1, column w0 - 1)
+#pragma unroll
+          for (int a = 0; a < 5; ++a) {
+            const int t = 2 * a;                       // taps (t, t + 1); the ninth tap is paired with a dummy
+            const int dh = t / 3, dw = t % 3;          // (offsets + 1)
+            const uint32_t lbo = (a == 1) ? 1024u : 128u;
+            const uint64_t ad = umma_desc_mn_sw128_sbo(sx + (xrow0 + dh * 10 + dw) * 128, lbo, 1280);
+            umma_bf16(tmem_base + a * 64, ad, bd, idesc, (k | kk) != 0);
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (k == n_k - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;      // accumulator row: (tap of the pair, input channel)
+    const int which = m >> 6, ci = m & 63;
+    float* dst0 = p.out + (int64_t)split * 64 * 9 * 64;
+    if (n_k > 0) {
+      mbar_wait(tfull, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int a = 0; a < 5; ++a) {
+      const int tap = 2 * a + which;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t r[32];
+        if (n_k > 0) {
+          tmem_ld32(taddr + a * 64 + ch * 32, r);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (tap < 9) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int co = ch * 32 + j;
+            dst0[((int64_t)co * 9 + tap) * 64 + ci] = __uint_as_float(r[j]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------- 3x3 weight gradient, row of taps
 // The one-tap kernel above moves 64 KB of operands into the SM per 4.2 MFLOP (64 FLOP/B).  Measured on the B200 one SM
 // ingests ~65-70 B/clk from L2 (wgrad_gemm_kernel<128,3>: 64 KB per ~950 clk), so that kernel runs at half the
@@ -2720,6 +2891,42 @@ static int wgrad3_pair_slots() {
   }();
   return slots;
 }
+// 3x3 / stride 1 / 64 -> 64 channels: all nine taps per CTA (wgrad9_c64_kernel); g_pair_mode bit 6
+static bool try_wgrad9(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, lbc_stream_t s, const GemmMode& m) {
+  if (!(g_pair_mode & 64) || m.split) return false;
+  if (c.K != 3 || c.stride != 1 || c.pad != 1 || c.Ci != 64 || c.Co != 64 || (c.W % 8)) return false;
+  Wgrad9Params p;
+  memset(&p, 0, sizeof(p));
+  p.TH = pow2_divisor(c.H, 16);
+  if (p.TH < 2) return false;
+  p.TN = 16 / p.TH;
+  p.tiles_w = c.W / 8;
+  p.tiles_h = c.H / p.TH;
+  p.tiles_n = (B + p.TN - 1) / p.TN;
+  p.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  int splits = p.k_tiles < sm_count() ? p.k_tiles : sm_count();
+  p.k_per_split = (p.k_tiles + splits - 1) / splits;
+  splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
+  const int64_t wsize = (int64_t)64 * 9 * 64;
+  p.out = wgrad3_partials((int64_t)splits * wsize);
+  if (!p.out) return false;
+  const int64_t eb = 2;
+  CUtensorMap mDY = make_map_4d(dy, 64, c.W, c.H, B, 64 * eb, (int64_t)c.W * 64 * eb, (int64_t)c.H * c.W * 64 * eb, 8, p.TH, p.TN);
+  CUtensorMap mX = make_map_4d(x, 64, c.W, c.H, B, 64 * eb, (int64_t)c.W * 64 * eb, (int64_t)c.H * c.W * 64 * eb, 10, p.TH + 2, p.TN);
+  typedef Wgrad9Smem<4> SP;
+  static_assert(SP::TOTAL <= 232448, "wgrad9 smem plan exceeds 227 KB");
+  auto kern = wgrad9_c64_kernel<4>;
+  static bool configured = false;
+  if (!configured) {
+    LBC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL));
+    configured = true;
+  }
+  LBC_LAUNCH(kern, dim3((unsigned)splits), dim3(192), SP::TOTAL, s, mDY, mX, p);
+  LBC_LAUNCHED("wgrad9_c64_kernel");
+  { auto k_ = wgrad3_reduce_kernel; LBC_LAUNCH(k_, dim3(64u), dim3(160), 0, s, (const float4*)p.out, dw_ref, 64, 64, splits); }
+  LBC_LAUNCHED("wgrad3_reduce_kernel");
+  return true;
+}
 static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_ref, int B, float* scratch, lbc_stream_t s,
                        const GemmMode& m) {
   (void)scratch;
@@ -2814,6 +3021,7 @@ static bool conv_wgrad_impl(const ConvL& c, const bf16* x, const bf16* dy, float
   const int KK = c.K * c.K;
   const int64_t wsize = (int64_t)c.Co * KK * c.Ci;
   if (wsize > scratch_floats) return false;
+  if (try_wgrad9(c, x, dy, dw_ref, B, s, m)) return true;
   if (try_wgrad3(c, x, dy, dw_ref, B, scratch, s, m)) return true;
   const int CX = m.split ? 2 * c.Ci : c.Ci, CY = m.split ? 2 * c.Co : c.Co;
   WgradParams p;

@@ -209,6 +209,7 @@ FAST_CASES = [
     (2, 48, 48, 64, 64, 3, 1, 1),      # teacher layer1
     (5, 6, 6, 512, 512, 3, 1, 1),      # teacher layer4
     (3, 24, 24, 128, 128, 3, 1, 1),    # teacher layer2 (TH=8, TN=2 -> batch tail tile)
+    (9, 40, 96, 64, 64, 3, 1, 1),      # layer1, 300 pixel tiles: several K steps per CTA in the nine-tap weight gradient
 ]
 
 
@@ -216,7 +217,7 @@ def _variant_default():
     import os
     m = int(os.environ.get("LBC_PAIR", "63") or 0)
     return ((4 if m & 1 else 8) | (16 if m & 2 else 32) | (64 if m & 4 else 128) | (1024 if m & 16 else 2048) |
-            (4096 if m & 32 else 8192))
+            (4096 if m & 32 else 8192) | (16384 if m & 64 else 32768))
 
 
 def _expected_conv_kernels(case, variant):
@@ -236,7 +237,10 @@ def _expected_conv_kernels(case, variant):
     if K == 3 and not c64:
         must.append("conv_row_kernel<128>" if row(Ci) else gemm(Ci))   # data gradient: N tile over the input channels
     w3 = variant in ("wgrad3", "wgrad3pair") and K == 3 and Co % 128 == 0 and Ci % 128 == 0
-    if w3:
+    if variant == "wgrad9" and K == 3 and s == 1 and Ci == 64 and Co == 64 and W % 8 == 0:
+        must.append("wgrad9_c64_kernel")              # all nine taps per CTA, x box with a halo
+        must.append("wgrad3_reduce_kernel")
+    elif w3:
         must.append("wgrad3_gemm_kernel<pair>" if (variant == "wgrad3pair" and Co % 256 == 0) else "wgrad3_gemm_kernel")
         must.append("wgrad3_reduce_kernel")
     else:
@@ -246,7 +250,7 @@ def _expected_conv_kernels(case, variant):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["base", "pair", "wgrad3", "wgrad3pair", "rowk", "rowk256"])
+@pytest.mark.parametrize("variant", ["base", "pair", "wgrad3", "wgrad3pair", "rowk", "rowk256", "wgrad9"])
 @pytest.mark.parametrize("case", FAST_CASES)
 def test_tcgen05_conv_gpu(backend, case, variant):
     """fast (tcgen05) kernels (forward, data gradient, weight gradient) vs torch on bf16-rounded operands.
@@ -259,9 +263,11 @@ def test_tcgen05_conv_gpu(backend, case, variant):
     from learningbycheating_b200 import _lib
     from test_kernels import Traced
     bits = {"base": 8 | 32 | 128, "pair": 4 | 32 | 128, "wgrad3": 8 | 16 | 128, "wgrad3pair": 8 | 16 | 64,
-            "rowk": 4 | 32 | 128 | 1024 | 8192, "rowk256": 4 | 32 | 128 | 1024 | 4096}[variant]
-    if variant in ("base", "pair", "wgrad3", "wgrad3pair"):
+            "rowk": 4 | 32 | 128 | 1024 | 8192, "rowk256": 4 | 32 | 128 | 1024 | 4096, "wgrad9": 8 | 32 | 128 | 16384}[variant]
+    if variant in ("base", "pair", "wgrad3", "wgrad3pair", "wgrad9"):
         bits |= 2048 | 8192
+    if variant != "wgrad9":
+        bits |= 32768
     _lib.check(_lib.lib().lbc_set_fast_kernels(1 | bits))
     try:
         never = ("k_conv_fwd", "k_conv_wgrad_part") + (() if case[5] == 1 else ("k_conv_dgrad",))
