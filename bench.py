@@ -491,6 +491,10 @@ def run_ours(args):
 
 
 def main():
+    # `kill -USR1 <pid>` (or `timeout -s USR1 ...`) dumps the Python stack of every thread: tells a device hang from a host one
+    import faulthandler
+    import signal
+    faulthandler.register(signal.SIGUSR1, all_threads=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
