@@ -324,7 +324,7 @@ def run_ours(args):
     L = _lib.lib()
     # kernel variants (lbc_b200.h: lbc_set_fast_kernels): bit 0 CTA-pair GEMMs, 1 row-of-taps weight gradient, 2 its CTA-pair
     # variant, (3 stem layout: the library default), 4 / 5 shared-row kernel for the 128- / 256-channel 3x3 convolutions
-    pair = args.pair if args.pair >= 0 else int(os.environ.get("LBC_PAIR", "63") or 0)
+    pair = args.pair if args.pair >= 0 else int(os.environ.get("LBC_PAIR", "127") or 0)
     L.lbc_set_fast_kernels((0 if args.no_fast else 1) | (4 if pair & 1 else 8) | (16 if pair & 2 else 32) | (64 if pair & 4 else 128) |
                            (1024 if pair & 16 else 2048) | (4096 if pair & 32 else 8192) | (16384 if pair & 64 else 32768))
     B = args.batch

@@ -1636,13 +1636,14 @@ static int launch_gemm_pair(const CUtensorMap* mA, const CUtensorMap& mBhalf, co
 //   bit 0: CTA-pair (cta_group::2) kernels for the BN >= 128 conv GEMMs   bit 1: row-of-taps weight gradient
 //   bit 2: CTA-pair variant of the row-of-taps weight gradient (Co % 256 == 0)
 //   bit 3: space-to-depth operand layout of the RGB stem (lbc_fast.h: stem_ch)
-//   bit 6: all-nine-taps weight gradient of the 64 -> 64 3x3 convolutions (try_wgrad9)
+//   bit 6: all-nine-taps weight gradient of the 64 -> 64 3x3 convolutions (try_wgrad9; same-box A/B 12.54 -> 12.30 ms per step,
+//   conv_wgrad 2.96 -> 2.86 ms; 30 consecutive bench runs + memcheck clean, tools/gpu_r2_z2.sh)
 //   bit 4 / 5: shared-row CTA-pair kernel for the 3x3/s1 convolutions of the 128-channel / 256-channel layers (try_conv_row;
 //   same-box A/B at B = 256: 13.79 -> 13.56 -> 13.36 ms per step, profiles/r2_ab_rowk_schedule.md)
 // Bits 0-2 validated on the B200 (parity tests green, 16.61 -> 15.87 ms per step at B = 256), hence on by default.
 static int g_pair_mode = [] {
   const char* e = getenv("LBC_PAIR");
-  return e ? atoi(e) : 63;
+  return e ? atoi(e) : 127;
 }();
 void set_pair_mode(int mode) { g_pair_mode = mode; }
 int pair_mode() { return g_pair_mode; }

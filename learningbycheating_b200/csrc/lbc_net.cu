@@ -237,8 +237,9 @@ class Net : public NetBase {
   // wave of the persistent data-gradient GEMMs.  d(r2) / d(r1) / d(rd), the gradients a weight-gradient GEMM reads, rotate
   // through kRing extra buffers so that the chain does not have to wait for the side stream before it moves on; every
   // buffer carries the event of its last side-stream reader, waited for before the chain overwrites it (wr()).
-  static constexpr int kRing = 4;
-  T* gring[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kRing = 8;   // allocated; ring_n of them rotate (LBC_RING)
+  int ring_n = 4;
+  T* gring[kRing] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ovl_capable = false;   // ring buffers + streams exist
   bool ovl = false;           // the running backward() uses them
   int ring_next = 0;
@@ -274,7 +275,7 @@ class Net : public NetBase {
   T* ring(T* fallback, lbc_stream_t s) {
     if (!ovl) return fallback;
     T* p = gring[ring_next];
-    ring_next = (ring_next + 1) % kRing;
+    ring_next = (ring_next + 1) % ring_n;
     return wr(p, s);
   }
   // everything enqueued on the chain so far is what the next side-stream weight gradient depends on
@@ -586,7 +587,12 @@ class Net : public NetBase {
 #ifndef LBC_HOST_EMU
     if (std::is_same<T, bf16>::value && !tc) {
       // ring buffers hold block-level gradients only (largest: layer 1 = the pooled stem output's shape)
-      for (int i = 0; i < kRing; ++i) gring[i] = alloc<T>(B * pool_h * pool_w * 64);
+      {
+        const char* e = getenv("LBC_RING");
+        const int r = e ? atoi(e) : 4;
+        ring_n = r < 2 ? 2 : (r > kRing ? kRing : r);
+      }
+      for (int i = 0; i < ring_n; ++i) gring[i] = alloc<T>(B * pool_h * pool_w * 64);
       int lo = 0, hi = 0;
       LBC_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority (0), hi = greatest (negative)
       LBC_CUDA(cudaStreamCreateWithPriority(&side_stream, cudaStreamNonBlocking, lo));

@@ -215,7 +215,7 @@ FAST_CASES = [
 
 def _variant_default():
     import os
-    m = int(os.environ.get("LBC_PAIR", "63") or 0)
+    m = int(os.environ.get("LBC_PAIR", "127") or 0)
     return ((4 if m & 1 else 8) | (16 if m & 2 else 32) | (64 if m & 4 else 128) | (1024 if m & 16 else 2048) |
             (4096 if m & 32 else 8192) | (16384 if m & 64 else 32768))
 
