@@ -2465,7 +2465,17 @@ wgrad9_c64_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
     // D = f32, A (x) and B (dy) bf16, both MN-major (bits 15, 16), N = 64, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
+    // the issuing thread is the bottleneck of a 40-MMA stage unless its per-MMA work is a couple of integer adds: the box
+    // offsets of the eight 16-pixel K steps and the five constant descriptor halves are computed once
     const int half_th = p.TH >> 1;
+    uint32_t xoff[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int ni = kk / half_th, rp = kk - ni * half_th;
+      xoff[kk] = (uint32_t)((ni * (p.TH + 2) + 2 * rp) * 10 * 128);   // box row of (image row 2*rp - 1, column w0 - 1), in bytes
+    }
+    const uint64_t a_hi128 = umma_desc_mn_sw128_sbo(0, 128, 1280), a_hi1024 = umma_desc_mn_sw128_sbo(0, 1024, 1280);
+    const uint64_t b_hi = umma_desc_mn_sw128_sbo(0, A_BYTES, 1024);
     int stage = 0;
     uint32_t phase = 0;
     for (int k = 0; k < n_k; ++k) {
@@ -2474,17 +2484,15 @@ wgrad9_c64_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constant
       if (elect_one()) {
         const uint32_t sdy = smem_u32(smem + stage * SP::STAGE_BYTES);
         const uint32_t sx = sdy + SP::DY_BYTES;
-#pragma unroll 1
+#pragma unroll
         for (int kk = 0; kk < 8; ++kk) {   // 16 pixels = two image rows (2 * rp, 2 * rp + 1) of image ni of the tile
-          const int ni = kk / half_th, rp = kk - ni * half_th;
-          const uint64_t bd = umma_desc_mn_sw128_sbo(sdy + kk * 2048, A_BYTES, 1024);
-          const uint32_t xrow0 = (uint32_t)((ni * (p.TH + 2) + 2 * rp) * 10);   // box row of (image row 2*rp - 1, column w0 - 1)
+          const uint64_t bd = b_hi | (uint64_t)(((sdy + kk * 2048) & 0x3FFFF) >> 4);
+          const uint32_t xa = sx + xoff[kk];
 #pragma unroll
           for (int a = 0; a < 5; ++a) {
-            const int t = 2 * a;                       // taps (t, t + 1); the ninth tap is paired with a dummy
-            const int dh = t / 3, dw = t % 3;          // (offsets + 1)
-            const uint32_t lbo = (a == 1) ? 1024u : 128u;
-            const uint64_t ad = umma_desc_mn_sw128_sbo(sx + (xrow0 + dh * 10 + dw) * 128, lbo, 1280);
+            constexpr int kTapOff[5] = {(0 * 10 + 0) * 128, (0 * 10 + 2) * 128, (1 * 10 + 1) * 128, (2 * 10 + 0) * 128, (2 * 10 + 2) * 128};
+            // taps (2a, 2a + 1); the ninth tap is paired with a dummy; tap 2 -> tap 3 is one box row minus two columns away
+            const uint64_t ad = (a == 1 ? a_hi1024 : a_hi128) | (uint64_t)(((xa + kTapOff[a]) & 0x3FFFF) >> 4);
             umma_bf16(tmem_base + a * 64, ad, bd, idesc, (k | kk) != 0);
           }
         }
@@ -2754,33 +2762,49 @@ wgrad3_gemm_kernel(const __grid_constant__ CUtensorMap mDY, const __grid_constan
 // thread and ran at 0.9 TB/s (30 us for 28 MB of L2-resident partials, 0.83 ms per step); here every thread keeps eight
 // independent 16-byte loads in flight over the splits, sums them in a fixed order (deterministic), and the 576 results go
 // through a shared-memory transpose so that the reference layout is written as one contiguous 2304-byte run.
-__global__ void __launch_bounds__(160) wgrad3_reduce_kernel(const float4* __restrict__ part, float* __restrict__ dst, int Co,
-                                                            int Ci, int splits) {
+// (second session: the splits are dealt to kRedGroups groups of 144 threads -- group g sums splits g, g + G, ... -- and the
+//  group sums are combined in a fixed order through shared memory: with one group the 148-split reduction behind the nine-tap
+//  kernel took 42 us on 64 blocks, pure L2 latency)
+constexpr int kRedGroups = 4;
+__global__ void __launch_bounds__(144 * kRedGroups) wgrad3_reduce_kernel(const float4* __restrict__ part, float* __restrict__ dst,
+                                                                          int Co, int Ci, int splits) {
   pdl_wait();
   pdl_trigger();
   __shared__ __align__(16) float tile[64 * 9];
+  __shared__ float4 gsum[kRedGroups - 1][144];
   const int cblocks = Ci / 64;
   const int co = blockIdx.x / cblocks, ci0 = (blockIdx.x % cblocks) * 64;
-  const int t = threadIdx.x / 16, c4 = threadIdx.x % 16;   // 9 taps x 16 float4
-  if (threadIdx.x < 144) {
-    const int64_t n4 = (int64_t)Co * 9 * Ci / 4;
-    const float4* src = part + (((int64_t)co * 9 + t) * Ci + ci0) / 4 + c4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int s = 0;
-    for (; s + 8 <= splits; s += 8) {
-      float4 v[8];
+  const int grp = threadIdx.x / 144, l = threadIdx.x % 144;
+  const int t = l / 16, c4 = l % 16;   // 9 taps x 16 float4
+  const int64_t n4 = (int64_t)Co * 9 * Ci / 4;
+  const float4* src = part + (((int64_t)co * 9 + t) * Ci + ci0) / 4 + c4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int sp = grp;
+  for (; sp + 7 * kRedGroups < splits; sp += 8 * kRedGroups) {
+    float4 v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + (int64_t)(s + j) * n4);
+    for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + (int64_t)(sp + j * kRedGroups) * n4);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc.x += v[j].x;
-        acc.y += v[j].y;
-        acc.z += v[j].z;
-        acc.w += v[j].w;
-      }
+    for (int j = 0; j < 8; ++j) {
+      acc.x += v[j].x;
+      acc.y += v[j].y;
+      acc.z += v[j].z;
+      acc.w += v[j].w;
     }
-    for (; s < splits; ++s) {
-      const float4 v = __ldcg(src + (int64_t)s * n4);
+  }
+  for (; sp < splits; sp += kRedGroups) {
+    const float4 v = __ldcg(src + (int64_t)sp * n4);
+    acc.x += v.x;
+    acc.y += v.y;
+    acc.z += v.z;
+    acc.w += v.w;
+  }
+  if (grp > 0) gsum[grp - 1][l] = acc;
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int g = 0; g < kRedGroups - 1; ++g) {
+      const float4 v = gsum[g][l];
       acc.x += v.x;
       acc.y += v.y;
       acc.z += v.z;
@@ -2924,7 +2948,7 @@ static bool try_wgrad9(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
   }
   LBC_LAUNCH(kern, dim3((unsigned)splits), dim3(192), SP::TOTAL, s, mDY, mX, p);
   LBC_LAUNCHED("wgrad9_c64_kernel");
-  { auto k_ = wgrad3_reduce_kernel; LBC_LAUNCH(k_, dim3(64u), dim3(160), 0, s, (const float4*)p.out, dw_ref, 64, 64, splits); }
+  { auto k_ = wgrad3_reduce_kernel; LBC_LAUNCH(k_, dim3(64u), dim3(144 * kRedGroups), 0, s, (const float4*)p.out, dw_ref, 64, 64, splits); }
   LBC_LAUNCHED("wgrad3_reduce_kernel");
   return true;
 }
@@ -3007,7 +3031,7 @@ static bool try_wgrad3(const ConvL& c, const bf16* x, const bf16* dy, float* dw_
     launch_wgrad3<5, true>(mDY, mX, p, grid, s);
   else
     launch_wgrad3<3, false>(mDY, mX, p, grid, s);
-  { auto k_ = wgrad3_reduce_kernel; LBC_LAUNCH(k_, dim3((unsigned)(c.Co * (c.Ci / 64))), dim3(160), 0, s, (const float4*)p.out, dw_ref, c.Co, c.Ci, p.splits); }
+  { auto k_ = wgrad3_reduce_kernel; LBC_LAUNCH(k_, dim3((unsigned)(c.Co * (c.Ci / 64))), dim3(144 * kRedGroups), 0, s, (const float4*)p.out, dw_ref, c.Co, c.Ci, p.splits); }
   LBC_LAUNCHED("wgrad3_reduce_kernel");
   LBC_CUDA(cudaGetLastError());
   return true;
