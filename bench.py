@@ -326,7 +326,8 @@ def run_ours(args):
     # variant, (3 stem layout: the library default), 4 / 5 shared-row kernel for the 128- / 256-channel 3x3 convolutions
     pair = args.pair if args.pair >= 0 else int(os.environ.get("LBC_PAIR", "127") or 0)
     L.lbc_set_fast_kernels((0 if args.no_fast else 1) | (4 if pair & 1 else 8) | (16 if pair & 2 else 32) | (64 if pair & 4 else 128) |
-                           (1024 if pair & 16 else 2048) | (4096 if pair & 32 else 8192) | (16384 if pair & 64 else 32768))
+                           (1024 if pair & 16 else 2048) | (4096 if pair & 32 else 8192) | (16384 if pair & 64 else 32768) |
+                           (65536 if pair & 128 else 131072))
     B = args.batch
     wl = WORKLOADS[args.workload]
     w = Workload(args.workload, args, dev, rank, torch)
@@ -477,7 +478,7 @@ def run_ours(args):
                                batch_per_gpu=B, parallelism="dp%d" % world, step=wl["step"],
                                l2="inputs+activations per step (>5 GB) far exceed the 126 MB L2; no explicit flush",
                                fast_kernels=not args.no_fast, cta_pair_gemm=bool(pair & 1), wgrad_row_of_taps=bool(pair & 2),
-                               wgrad_cta_pair=bool(pair & 4), shared_row_conv=("layers 2-3" if pair & 32 else "layer 2" if pair & 16 else "off"), wgrad_nine_taps_c64=bool(pair & 64),
+                               wgrad_cta_pair=bool(pair & 4), shared_row_conv=("layers 2-3" if pair & 32 else "layer 2" if pair & 16 else "off"), wgrad_nine_taps_c64=bool(pair & 64), layer1_on_pair_kernel=bool(pair & 128),
                                schedule=dict(wgrad_side_stream=int(os.environ.get("LBC_WGRAD_OVERLAP", "1")),
                                              pdl=int(os.environ.get("LBC_PDL", "1"))), cpu_affinity=numa, allreduce=("bucketed, overlapped with backward" if w.dp.overlap else "single, after backward") if world > 1 else "none"),
                    e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, steps=e2e_steps,

@@ -40,7 +40,8 @@ const char* lbc_build_info(void);
  * 256 / 512 = space-to-depth layout of the RGB stem operand on / off,
  * 1024 / 2048 = shared-row CTA-pair kernel (one activation box per kernel row) for the 3x3/s1 convolutions of the
  * 128-channel layers on / off, 4096 / 8192 = the same for the layers whose channel count is a multiple of 256,
- * 16384 / 32768 = weight gradient of the 64 -> 64 3x3 convolutions with all nine taps per CTA on / off. */
+ * 16384 / 32768 = weight gradient of the 64 -> 64 3x3 convolutions with all nine taps per CTA on / off,
+ * 65536 / 131072 = the 64 -> 64 3x3/s1 convolutions on the shared-row CTA-pair kernel (64-wide N tiles) on / off. */
 int lbc_set_fast_kernels(int enabled);
 /* launch schedule of the bf16 throughput mode (a negative argument keeps the current value; the environment variables
  * LBC_WGRAD_OVERLAP / LBC_PDL set the initial ones).  wgrad_overlap: 0 = every kernel of backward on the caller's stream,

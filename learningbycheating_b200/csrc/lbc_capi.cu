@@ -136,6 +136,8 @@ int lbc_set_fast_kernels(int enabled) {
   if (enabled & 8192) m &= ~32;
   if (enabled & 16384) m |= 64;    // 16384 / 32768 = all-nine-taps weight gradient of the 64 -> 64 3x3 convolutions on / off
   if (enabled & 32768) m &= ~64;
+  if (enabled & 65536) m |= 128;    // 65536 / 131072 = 64-channel 3x3/s1 convolutions on the shared-row CTA-pair kernel (64-wide N tiles) on / off
+  if (enabled & 131072) m &= ~128;
   fast::set_pair_mode(m);
   return 0;
 }

@@ -914,7 +914,9 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 conv_row_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
                 const __grid_constant__ CUtensorMap mO, const ConvRowParams p) {
-  static_assert(BN == 128, "statistics mapping: 16 chunks of 8 channels x 8 groups of 16 rows");
+  static_assert(BN == 128 || BN == 64, "N tile of the shared-row kernel");
+  // statistics mapping: CH 16-byte chunks (8 channels) per staged row, RG groups of RPG rows; thread e -> chunk e % CH, group e / CH
+  constexpr int CH = BN / 8, RG = 128 / CH, RPG = 128 / RG;
   typedef SmemPlanRow<BN, STAGES> SP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1037,8 +1039,8 @@ conv_row_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
     const bool stats = p.stat_partial != nullptr;
     if (stats)
       for (int i = e; i < 2 * p.stat_C; i += 128) cstat[i] = 0.f;
-    // statistics: thread e owns the 16-byte chunk (8 channels) `cidx` of the 16 staged rows [16*rg, 16*rg + 16)
-    const int cidx = e & 15, rg = e >> 4;
+    // statistics: thread e owns the 16-byte chunk (8 channels) `cidx` of the RPG staged rows [RPG*rg, RPG*rg + RPG)
+    const int cidx = e % CH, rg = e / CH;
     float as[8], aq[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) as[i] = aq[i] = 0.f;
@@ -1052,14 +1054,16 @@ conv_row_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
         as[i] = aq[i] = 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      float s = 0.f, q2 = 0.f;
+      if (e < BN) {   // column e: the RG row groups in order
+        float s = 0.f, q2 = 0.f;
 #pragma unroll
-      for (int r2 = 0; r2 < 8; ++r2) {
-        s += red[(r2 * 16 + (e >> 3)) * 16 + (e & 7)];
-        q2 += red[(r2 * 16 + (e >> 3)) * 16 + 8 + (e & 7)];
+        for (int r2 = 0; r2 < RG; ++r2) {
+          s += red[(r2 * CH + (e >> 3)) * 16 + (e & 7)];
+          q2 += red[(r2 * CH + (e >> 3)) * 16 + 8 + (e & 7)];
+        }
+        cstat[nt * BN + e] += s;
+        cstat[p.stat_C + nt * BN + e] += q2;
       }
-      cstat[nt * BN + e] += s;
-      cstat[p.stat_C + nt * BN + e] += q2;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
     int it = 0;
@@ -1074,7 +1078,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
       if (n_tile != cur_nt) {   // (uniform over the CTA)
         if (stats && cur_nt >= 0) flush(cur_nt);
         asm volatile("bar.sync 1, 128;" ::: "memory");   // the previous tile's reads of bias_s are done
-        bias_s[e] = p.bias ? __ldg(p.bias + n_tile * BN + e) : 0.f;
+        if (e < BN) bias_s[e] = p.bias ? __ldg(p.bias + n_tile * BN + e) : 0.f;
         cur_nt = n_tile;
       }
       mbar_wait(&tfull[acc], acc_phase);
@@ -1123,15 +1127,15 @@ conv_row_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
         const int valid_rows = nvalid * p.TH * 8;
         const uint8_t* boxp = out_stage + (cidx >> 3) * A_BYTES;
         const int chunk = cidx & 7;
-        if (valid_rows >= rg * 16 + 16) {
-          uint4 w[16];
+        if (valid_rows >= rg * RPG + RPG) {
+          uint4 w[RPG];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r2 = rg * 16 + i;
+          for (int i = 0; i < RPG; ++i) {
+            const int r2 = rg * RPG + i;
             w[i] = *reinterpret_cast<const uint4*>(boxp + r2 * 128 + ((chunk ^ (r2 & 7)) << 4));
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < RPG; ++i) {
             const uint32_t ww[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
 #pragma unroll
             for (int t2 = 0; t2 < 4; ++t2) {
@@ -1143,7 +1147,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
             }
           }
         } else {
-          for (int r2 = rg * 16; r2 < rg * 16 + 16 && r2 < valid_rows; ++r2) {
+          for (int r2 = rg * RPG; r2 < rg * RPG + RPG && r2 < valid_rows; ++r2) {
             const uint4 w = *reinterpret_cast<const uint4*>(boxp + r2 * 128 + ((chunk ^ (r2 & 7)) << 4));
             const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -1714,6 +1718,7 @@ void set_c64_variant(bool on) { g_c64_variant = on; }
 static bool try_conv3x3_c64(const bf16* in, const void* wpack, bf16* out, int B, int H, int W, bool mirrored,
                             const float* bias, bool relu, float* stat_partial, int* stat_rows, lbc_stream_t s) {
   if (!g_c64_variant || (W % 8) != 0) return false;
+  if ((g_pair_mode & 129) == 129) return false;   // bit 7 (+ CTA pairs): the shared-row CTA-pair kernel with 64-wide N tiles takes it
   ConvKwParams p;
   memset(&p, 0, sizeof(p));
   int TH = pow2_divisor(H, 16);
@@ -1766,11 +1771,12 @@ static bool try_conv3x3_c64(const bf16* in, const void* wpack, bf16* out, int B,
 // mirrored = true with the transposed pack).  in [B,H,W,Cin], wpack [Cout][9][Cin], out [B,H,W,Cout]; returns the number of
 // CTAs launched (= rows of statistics partials) or 0 when the layer does not fit the kernel.
 //   g_pair_mode bit 4: layers with Cout % 256 != 0 (layer 2, the teacher's layer 2)   bit 5: also Cout % 256 == 0 (layer 3)
-static int try_conv_row(const bf16* in, const void* wpack, bf16* out, int B, int H, int W, int Cin, int Cout, bool mirrored,
-                        const float* bias, bool relu, float* stat_partial, lbc_stream_t s) {
-  constexpr int BN = 128, STAGES = 4;
+//   bit 7: the 64-channel layers (layer 1) on the same kernel with 64-wide N tiles instead of conv3x3_c64_kernel
+template <int BN, int STAGES>
+static int try_conv_row_t(const bf16* in, const void* wpack, bf16* out, int B, int H, int W, int Cin, int Cout, bool mirrored,
+                          const float* bias, bool relu, float* stat_partial, lbc_stream_t s) {
   if (!(g_pair_mode & 1)) return 0;
-  if (!(g_pair_mode & (Cout % 256 == 0 ? 32 : 16))) return 0;
+  if (!(g_pair_mode & (BN == 64 ? 128 : (Cout % 256 == 0 ? 32 : 16)))) return 0;
   if ((W % 8) || (Cin % 64) || (Cout % BN) || Cout > 512) return 0;
   ConvRowParams p;
   memset(&p, 0, sizeof(p));
@@ -1820,8 +1826,13 @@ static int try_conv_row(const bf16* in, const void* wpack, bf16* out, int B, int
   const int pair_tiles = ((tiles_m + 1) / 2) * p.n_tiles_n;
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
   LBC_LAUNCH_CLUSTER(kern, 2, dim3((unsigned)(2 * clusters)), dim3(192), SP::TOTAL, (cudaStream_t)s, mA, mB, mO, p);
-  LBC_LAUNCHED("conv_row_kernel<128>");
+  LBC_LAUNCHED(BN == 64 ? "conv_row_kernel<64>" : "conv_row_kernel<128>");
   return 2 * clusters;
+}
+static int try_conv_row(const bf16* in, const void* wpack, bf16* out, int B, int H, int W, int Cin, int Cout, bool mirrored,
+                        const float* bias, bool relu, float* stat_partial, lbc_stream_t s) {
+  if (Cout == 64) return try_conv_row_t<64, 6>(in, wpack, out, B, H, W, Cin, Cout, mirrored, bias, relu, stat_partial, s);
+  return try_conv_row_t<128, 4>(in, wpack, out, B, H, W, Cin, Cout, mirrored, bias, relu, stat_partial, s);
 }
 
 // ---- stem host side: x4 = zero-padded NHWC bf16 image [B][H+6][W+8][CH], CH = 4 (C_in <= 4) or 8 (C_in <= 8) ----

@@ -659,7 +659,8 @@ def test_block_entry_dgrad_kernels_gpu(backend, N, H, W, Ci, Co):
 @pytest.mark.parametrize("case", [(3, 40, 96, 64, 64, 3, 1), (3, 40, 96, 64, 128, 3, 2), (3, 40, 96, 64, 128, 1, 2),
                                   (9, 10, 24, 256, 256, 3, 1), (33, 5, 12, 512, 512, 3, 1), (2, 48, 48, 64, 64, 3, 1),
                                   (3, 20, 48, 128, 128, 3, 1, "row"), (9, 10, 24, 256, 256, 3, 1, "row"),
-                                  (3, 24, 24, 128, 128, 3, 1, "row"), (300, 20, 48, 128, 128, 3, 1, "row")])
+                                  (3, 24, 24, 128, 128, 3, 1, "row"), (300, 20, 48, 128, 128, 3, 1, "row"),
+                                  (3, 40, 96, 64, 64, 3, 1, "row64"), (40, 40, 96, 64, 64, 3, 1, "row64")])
 def test_conv_epilogue_statistics_gpu(backend, case):
     """sum / sum of squares of the STORED bf16 output, emitted by the GEMM epilogue, vs the column sums of that output;
     the per-channel shift is added before rounding"""
@@ -677,9 +678,10 @@ def test_conv_epilogue_statistics_gpu(backend, case):
     y = torch.empty(N, ref.shape[2], ref.shape[3], Co, device="cuda")
     stats = torch.empty(2 * Co, device="cuda")
     from test_ops import _variant_default
-    _lib.check(L.lbc_set_fast_kernels(1 | ((1024 | 4096) if row else (2048 | 8192))))
+    row64 = row and case[7] == "row64"
+    _lib.check(L.lbc_set_fast_kernels(1 | (65536 if row64 else 131072) | ((1024 | 4096) if row else (2048 | 8192))))
     try:
-        with Traced("cuda", ["conv_row_kernel<128>" if row else
+        with Traced("cuda", ["conv_row_kernel<64>" if row64 else "conv_row_kernel<128>" if row else
                              "conv3x3_c64_kernel" if (Ci == Co == 64 and K == 3) else "conv_gemm_kernel", "col_finalize_kernel"]):
             _lib.check(L.lbc_op_conv_fwd(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(y), N, H, W, Ci, Co, K, s, p, 1, _lib.ptr(sd),
                                          _lib.ptr(stats), None))

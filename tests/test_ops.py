@@ -217,23 +217,24 @@ def _variant_default():
     import os
     m = int(os.environ.get("LBC_PAIR", "127") or 0)
     return ((4 if m & 1 else 8) | (16 if m & 2 else 32) | (64 if m & 4 else 128) | (1024 if m & 16 else 2048) |
-            (4096 if m & 32 else 8192) | (16384 if m & 64 else 32768))
+            (4096 if m & 32 else 8192) | (16384 if m & 64 else 32768) | (65536 if m & 128 else 131072))
 
 
 def _expected_conv_kernels(case, variant):
     """kernel families the three ops of `case` must launch under `variant` (names as in lbc_trace_dump)"""
     N, H, W, Ci, Co, K, s, p = case
-    pair = variant in ("pair", "rowk", "rowk256")
+    pair = variant in ("pair", "rowk", "rowk256", "row64")
     def gemm(n_out):
         bn = 64 if n_out == 64 else (256 if n_out % 256 == 0 else 128)
         return "conv_gemm_kernel<%d%s>" % (bn, ",pair" if (pair and bn >= 128) else "")
     c64 = (K == 3 and s == 1 and Ci == 64 and Co == 64 and W % 8 == 0)
+    c64_name = "conv_row_kernel<64>" if variant == "row64" else "conv3x3_c64_kernel"   # row64: layer 1 on the CTA-pair kernel
     # rowk / rowk256: the shared-row CTA-pair kernel takes the 3x3/s1 convolutions with 128-wide N tiles (rowk256: also
     # the layers whose channel count is a multiple of 256)
     def row(n_out):
         ok = variant in ("rowk", "rowk256") and K == 3 and s == 1 and W % 8 == 0 and n_out % 128 == 0 and n_out <= 512
         return ok and (n_out % 256 != 0 or variant == "rowk256")
-    must = ["conv3x3_c64_kernel" if c64 else ("conv_row_kernel<128>" if row(Co) else gemm(Co))]
+    must = [c64_name if c64 else ("conv_row_kernel<128>" if row(Co) else gemm(Co))]
     if K == 3 and not c64:
         must.append("conv_row_kernel<128>" if row(Ci) else gemm(Ci))   # data gradient: N tile over the input channels
     w3 = variant in ("wgrad3", "wgrad3pair") and K == 3 and Co % 128 == 0 and Ci % 128 == 0
@@ -250,7 +251,7 @@ def _expected_conv_kernels(case, variant):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["base", "pair", "wgrad3", "wgrad3pair", "rowk", "rowk256", "wgrad9"])
+@pytest.mark.parametrize("variant", ["base", "pair", "wgrad3", "wgrad3pair", "rowk", "rowk256", "wgrad9", "row64"])
 @pytest.mark.parametrize("case", FAST_CASES)
 def test_tcgen05_conv_gpu(backend, case, variant):
     """fast (tcgen05) kernels (forward, data gradient, weight gradient) vs torch on bf16-rounded operands.
@@ -263,11 +264,12 @@ def test_tcgen05_conv_gpu(backend, case, variant):
     from learningbycheating_b200 import _lib
     from test_kernels import Traced
     bits = {"base": 8 | 32 | 128, "pair": 4 | 32 | 128, "wgrad3": 8 | 16 | 128, "wgrad3pair": 8 | 16 | 64,
-            "rowk": 4 | 32 | 128 | 1024 | 8192, "rowk256": 4 | 32 | 128 | 1024 | 4096, "wgrad9": 8 | 32 | 128 | 16384}[variant]
-    if variant in ("base", "pair", "wgrad3", "wgrad3pair", "wgrad9"):
+            "rowk": 4 | 32 | 128 | 1024 | 8192, "rowk256": 4 | 32 | 128 | 1024 | 4096, "wgrad9": 8 | 32 | 128 | 16384, "row64": 4 | 32 | 128}[variant]
+    if variant in ("base", "pair", "wgrad3", "wgrad3pair", "wgrad9", "row64"):
         bits |= 2048 | 8192
     if variant != "wgrad9":
         bits |= 32768
+    bits |= 65536 if variant == "row64" else 131072
     _lib.check(_lib.lib().lbc_set_fast_kernels(1 | bits))
     try:
         never = ("k_conv_fwd", "k_conv_wgrad_part") + (() if case[5] == 1 else ("k_conv_dgrad",))
