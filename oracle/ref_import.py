@@ -8,8 +8,8 @@ only in the build container, never on the GPU box) so that
 Nothing in learningbycheating_b200/ may import this module.
 
 Shims; every one lives outside /root/reference:
-  1. MagicMock stubs for carla, pygame, lmdb, imgaug, imageio, tensorboardX
-     (import chain: bird_view/models/agent.py:5, utils/carla_utils.py:12-15, ...)
+  1. MagicMock stubs for carla, pygame, lmdb, imgaug, imageio, tensorboardX, removed from sys.modules again
+     once the reference is imported (import chain: bird_view/models/agent.py:5, utils/carla_utils.py:12-15, ...)
   2. sys.modules['train_util'] = utils.train_utils   (training/train_image_phase0.py:25)
   3. sys.path += bird_view/, training/, PythonAPI/
   4. torch.Tensor.cuda = identity on a GPU-less host (bird_view/models/common.py:105-106)
@@ -39,6 +39,7 @@ def load():
         raise RuntimeError("reference tree not present at %s" % REF_ROOT)
     import torch
 
+    stubbed = []
     for name in ["carla", "pygame", "pygame.locals", "lmdb", "imgaug",
                  "imgaug.augmenters", "imageio", "tensorboardX"]:
         if name not in sys.modules:
@@ -47,6 +48,7 @@ def load():
             m.__name__ = name
             m.__spec__ = None
             sys.modules[name] = m
+            stubbed.append(name)
     for sub in ["bird_view", "training", "PythonAPI", ""]:
         p = os.path.join(REF_ROOT, sub) if sub else REF_ROOT
         if p not in sys.path:
@@ -80,5 +82,9 @@ def load():
         phase1=train_image_phase1,
         birdview=train_birdview,
     )
+    # the reference modules keep their own references to the stubs; anything imported later (the package's optional
+    # `import lmdb`, tests of its "module missing" paths) must not find a MagicMock posing as the real module
+    for name in stubbed:
+        sys.modules.pop(name, None)
     _loaded["ns"] = ns
     return ns
