@@ -11,7 +11,24 @@ using namespace lbc;
 
 struct lbc_net {
   std::unique_ptr<NetBase> impl;
+  int device = -1;   // CUDA device the engine (workspace, streams, events) lives on
 };
+// The library's scratch buffers (statistics partials, split-K partials), kernel attributes and occupancy figures are
+// process-wide and belong to the device of the FIRST engine: one process drives one GPU (torchrun's model).  A second engine
+// on another device, or a call with another device current, is an error here rather than a corrupted buffer later.
+static int g_engine_device = -1;
+static void check_device(const lbc_net* net, const char* what) {
+#ifndef LBC_HOST_EMU
+  int dev = -1;
+  cudaGetDevice(&dev);
+  if (dev != net->device)
+    throw Error(std::string(what) + ": CUDA device " + std::to_string(dev) + " is current, the engine lives on device " +
+                std::to_string(net->device) + " (torch.cuda.set_device before calling; one process per GPU)");
+#else
+  (void)net;
+  (void)what;
+#endif
+}
 
 static thread_local std::string g_err;
 
@@ -198,6 +215,16 @@ int lbc_net_create(int kind, int precision, int max_batch, lbc_net_t** out) {
     require_device();
     LBC_CHECK(out, "null out pointer");
     lbc_net* n = new lbc_net;
+#ifndef LBC_HOST_EMU
+    cudaGetDevice(&n->device);
+    if (g_engine_device < 0) g_engine_device = n->device;
+    if (n->device != g_engine_device) {
+      const int d = n->device;
+      delete n;
+      throw Error("lbc_net_create: this process already runs engines on CUDA device " + std::to_string(g_engine_device) +
+                  "; device " + std::to_string(d) + " needs its own process (the library's scratch buffers are per process)");
+    }
+#endif
     try {
       n->impl = make_net((NetKind)kind, (Precision)precision, max_batch);
     } catch (...) {
@@ -244,6 +271,7 @@ int lbc_net_bind(lbc_net_t* net, float* params, float* grads, float* buffers) {
 int lbc_net_forward(lbc_net_t* net, const float* image, const float* speed, const float* command_onehot, int B,
                     int train, float* out_pred, float* out_preds, void* stream) {
   return guarded([&] {
+    check_device(net, "lbc_net_forward");
     LBC_CHECK(image && speed && command_onehot, "lbc_net_forward: null input");
     net->impl->forward(image, speed, command_onehot, B, train != 0, out_pred, out_preds, S(stream));
   });
@@ -251,6 +279,7 @@ int lbc_net_forward(lbc_net_t* net, const float* image, const float* speed, cons
 int lbc_net_forward_u8(lbc_net_t* net, const uint8_t* image_u8, int layout, const float* speed,
                        const float* command_onehot, int B, int train, float* out_pred, float* out_preds, void* stream) {
   return guarded([&] {
+    check_device(net, "lbc_net_forward_u8");
     LBC_CHECK(image_u8 && speed && command_onehot, "lbc_net_forward_u8: null input");
     net->impl->forward_u8(image_u8, layout, speed, command_onehot, B, train != 0, out_pred, out_preds, S(stream));
   });
@@ -258,12 +287,16 @@ int lbc_net_forward_u8(lbc_net_t* net, const uint8_t* image_u8, int layout, cons
 int lbc_net_infer(lbc_net_t* net, const float* image, const uint8_t* image_u8, int layout, const float* speed,
                   const float* command_onehot, int B, int weights_changed, float* out_pred, float* out_preds, void* stream) {
   return guarded([&] {
+    check_device(net, "lbc_net_infer");
     net->impl->infer(image, image_u8, layout, speed, command_onehot, B, weights_changed != 0, out_pred, out_preds, S(stream));
   });
 }
 int lbc_net_infer_replays(const lbc_net_t* net) { return net->impl->infer_replays; }
 int lbc_net_backward(lbc_net_t* net, const float* d_pred, const float* d_preds, void* stream) {
-  return guarded([&] { net->impl->backward(d_pred, d_preds, S(stream)); });
+  return guarded([&] {
+    check_device(net, "lbc_net_backward");
+    net->impl->backward(d_pred, d_preds, S(stream));
+  });
 }
 int lbc_net_num_grad_buckets(const lbc_net_t* net) { return (int)net->impl->buckets.size(); }
 int lbc_net_grad_bucket(const lbc_net_t* net, int bucket, int64_t* offset, int64_t* numel) {
@@ -281,7 +314,10 @@ int lbc_net_stream_wait_grads(lbc_net_t* net, int bucket, void* stream) {
 }
 int64_t lbc_net_read_tap(lbc_net_t* net, const char* name, float* out, int64_t capacity, void* stream) {
   int64_t n = -1;
-  int rc = guarded([&] { n = net->impl->read_tap(name, out, capacity, S(stream)); });
+  int rc = guarded([&] {
+    check_device(net, "lbc_net_read_tap");
+    n = net->impl->read_tap(name, out, capacity, S(stream));
+  });
   return rc == 0 ? n : -1;
 }
 
