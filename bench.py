@@ -335,6 +335,19 @@ def run_ours(args):
 
     step()                      # builds the native engines (allocations) outside every timed region
     w.dp.sync_initial_state()
+    # watchdog over the device phases (normally seconds): a run that makes no progress dumps every thread's Python stack and
+    # exits non-zero instead of sitting in its caller's timeout without a word (seen once in ~100 runs, never reproduced)
+    import faulthandler
+    limit = float(os.environ.get("LBC_BENCH_WATCHDOG_S", "0") or 0) or (600.0 + 2.0 * (args.steps + args.warmup))
+    done = threading.Event()
+
+    def watchdog():
+        if not done.wait(limit):
+            sys.stderr.write("bench.py: device phase exceeded %.0f s -- stack of every thread follows\n" % limit)
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+            sys.stderr.flush()
+            os._exit(3)
+    threading.Thread(target=watchdog, daemon=True).start()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()         # comes up during the warm-up; only samples after sampler.mark() are reported
@@ -461,6 +474,7 @@ def run_ours(args):
                                      unit="GB/s", frac=bn_gbs / peaks["hbm"], bytes="algorithmic (DESIGN.md section 3)"),
                     per_category=cats)
 
+    done.set()                  # device phases over: the CPU baseline below takes its own time
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = cpu_threads()
