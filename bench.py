@@ -329,12 +329,6 @@ def run_ours(args):
                            (1024 if pair & 16 else 2048) | (4096 if pair & 32 else 8192) | (16384 if pair & 64 else 32768) |
                            (65536 if pair & 128 else 131072))
     B = args.batch
-    wl = WORKLOADS[args.workload]
-    w = Workload(args.workload, args, dev, rank, torch)
-    step = w.step
-
-    step()                      # builds the native engines (allocations) outside every timed region
-    w.dp.sync_initial_state()
     # watchdog over the device phases (normally seconds): a run that makes no progress dumps every thread's Python stack and
     # exits non-zero instead of sitting in its caller's timeout without a word (seen once in ~100 runs, never reproduced)
     import faulthandler
@@ -348,6 +342,12 @@ def run_ours(args):
             sys.stderr.flush()
             os._exit(3)
     threading.Thread(target=watchdog, daemon=True).start()
+    wl = WORKLOADS[args.workload]
+    w = Workload(args.workload, args, dev, rank, torch)
+    step = w.step
+
+    step()                      # builds the native engines (allocations) outside every timed region
+    w.dp.sync_initial_state()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()         # comes up during the warm-up; only samples after sampler.mark() are reported
