@@ -14,16 +14,18 @@ def load_data(config):
     provides ``config['data_loader']``, a callable taking ``**config['data_args']`` and returning (data_train, data_val)."""
     loader = config.get('data_loader')
     if loader is None:
-        # the package's own reader of the collector's LMDB episodes (records.py; image-agent samples, no augmentation)
+        # the package's own reader of the collector's LMDB episodes (records.py; no imgaug augmentation)
         args = config.get('data_args', {})
         try:
             import lmdb  # noqa: F401
             have_lmdb = True
         except ImportError:
             have_lmdb = False
-        if have_lmdb and args.get('dataset_dir') and config.get('model_args', {}).get('model', 'image_ss') == 'image_ss':
+        if have_lmdb and args.get('dataset_dir'):
             from . import records
-            return records.get_image(**args)
+            if config.get('model_args', {}).get('model', 'image_ss') == 'image_ss':
+                return records.get_image(**args)
+            return records.get_birdview(**args)      # the privileged agent's dataset, with its rotation / shift jitter
         raise _lib.LbcError("train(config): no dataset -- pass data_train/data_val, or set config['data_loader'] to a callable "
                             "(**data_args) -> (data_train, data_val); records.get_image reads the collector's LMDB episodes "
                             "when the `lmdb` module is installed")
